@@ -1,0 +1,594 @@
+// msb_kernels.cuh -- sm_100a kernels of the hot path (see DESIGN.md for the
+// data layout, the per-kernel roofline and the algorithmic bytes).
+#pragma once
+#include "msb_math.cuh"
+
+namespace msb {
+
+enum Kind : int { KIND_TABLE = 0, KIND_GP = 1, KIND_NICH = 2, KIND_NIW = 3 };
+enum ColType : int { COL_U8 = 0, COL_U16 = 1, COL_U32 = 2, COL_F32 = 3 };
+
+constexpr uint32_t GP_SENTINEL = 0xFFFFFFFFu;
+
+// Per-feature descriptor, one array in device memory per state.
+struct FeatDev {
+  int32_t family;     // Family
+  int32_t kind;       // Kind
+  int32_t coltype;    // ColType
+  uint32_t dim;       // dd categories / niw dimension / bb 2
+  uint32_t ncat;      // table categories: bb 2, dd dim, gp cap; index ncat = zero row (masked)
+  uint32_t rows;      // rows of this feature's parameter chunk (each row = KT floats)
+  uint32_t rowoff;    // first row of the chunk inside a k-tile region
+  uint32_t ss_w;      // doubles per group slot
+  const void *col;    // Value-typed column, n elements (niw: n x dim floats)
+  uint64_t hp_off;    // into hp[]
+  uint64_t ss_off;    // into ss[] / delta[]: block[slot * ss_w + j]
+  double asum;        // dd: sum of alphas
+  // AoS source record (row_major_dataview layout, runtime_type.hpp:123-134)
+  uint64_t src_off;
+  uint64_t msk_off;
+  uint32_t src_prim;
+  uint32_t src_n;
+};
+
+// ---------------------------------------------------------------------------
+// AoS -> SoA pack: applies runtime_cast (runtime_type.hpp:145-166) once per
+// cell and folds the mask in-band (sentinel value per column type).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double load_prim(const uint8_t *p, uint32_t prim) {
+  switch (prim) {
+    case 0: return (double)(*p != 0);
+    case 1: return (double)*(const int8_t *)p;
+    case 2: return (double)*p;
+    case 3: { int16_t v; memcpy(&v, p, 2); return (double)v; }
+    case 4: { uint16_t v; memcpy(&v, p, 2); return (double)v; }
+    case 5: { int32_t v; memcpy(&v, p, 4); return (double)v; }
+    case 6: { uint32_t v; memcpy(&v, p, 4); return (double)v; }
+    case 7: { long long v; memcpy(&v, p, 8); return (double)v; }
+    case 8: { unsigned long long v; memcpy(&v, p, 8); return (double)v; }
+    case 9: { float v; memcpy(&v, p, 4); return (double)v; }
+    default: { double v; memcpy(&v, p, 8); return v; }
+  }
+}
+__device__ __forceinline__ uint32_t prim_size(uint32_t prim) {
+  const uint32_t sz[11] = {1, 1, 1, 2, 2, 4, 4, 8, 8, 4, 8};
+  return sz[prim];
+}
+
+__global__ void pack_kernel(const uint8_t *__restrict__ data, const uint8_t *__restrict__ mask, size_t n,
+                            size_t rowsize, size_t maskrowsize, const FeatDev *__restrict__ feats, int nfeat) {
+  const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = blockIdx.y;
+  if (row >= n || d >= nfeat) return;
+  const FeatDev f = feats[d];
+  const uint8_t *src = data + row * rowsize + f.src_off;
+  bool masked = false;
+  if (mask) {
+    const uint8_t *m = mask + row * maskrowsize + f.msk_off;
+    for (uint32_t i = 0; i < f.src_n; i++) masked |= (m[i] != 0);
+  }
+  const uint32_t ps = prim_size(f.src_prim);
+  if (f.kind == KIND_NIW) {
+    float *dst = (float *)f.col + row * (size_t)f.dim;
+    for (uint32_t i = 0; i < f.dim; i++) dst[i] = (float)load_prim(src + i * ps, f.src_prim);
+    if (masked) dst[0] = CUDART_NAN_F;
+    return;
+  }
+  const double v = load_prim(src, f.src_prim);
+  if (f.kind == KIND_NICH) {
+    ((float *)f.col)[row] = masked ? CUDART_NAN_F : (float)v;
+  } else if (f.kind == KIND_GP) {
+    uint32_t x = v < 0.0 ? 0u : (v >= 4294967294.0 ? 4294967294u : (uint32_t)v);
+    ((uint32_t *)f.col)[row] = masked ? GP_SENTINEL : x;
+  } else {  // bb / dd category; out-of-range categories are treated as masked
+    uint32_t x = f.ncat;
+    if (!masked) {
+      if (f.family == FAM_BB) x = (v != 0.0) ? 1u : 0u;
+      else if (v >= 0.0 && v < (double)f.ncat) x = (uint32_t)v;
+    }
+    if (f.coltype == COL_U8) ((uint8_t *)f.col)[row] = (uint8_t)x;
+    else if (f.coltype == COL_U16) ((uint16_t *)f.col)[row] = (uint16_t)x;
+    else ((uint32_t *)f.col)[row] = x;
+  }
+}
+
+// max over a gp column (ignoring masked cells): sizes the lookup table
+__global__ void colmax_u32_kernel(const uint32_t *__restrict__ col, size_t n, uint32_t *out) {
+  uint32_t m = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t v = col[i];
+    if (v != GP_SENTINEL && v > m) m = v;
+  }
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// ---------------------------------------------------------------------------
+// Parameter build: everything that depends on (group, feature[, category]) but
+// not on the row is evaluated once per sweep, in fp64, and laid out as the
+// score kernel streams it: for k-tile t, feature d: chunk[rows_d][KT] floats.
+// ---------------------------------------------------------------------------
+__global__ void build_params_kernel(const FeatDev *__restrict__ feats, int nfeat, const double *__restrict__ hp,
+                                    const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols,
+                                    int KT, size_t region_rows, float *__restrict__ params) {
+  const int d = blockIdx.x, kt = blockIdx.y;
+  const FeatDev f = feats[d];
+  if (f.rows == 0) return;
+  float *chunk = params + ((size_t)kt * region_rows + f.rowoff) * KT;
+  const double *fhp = hp + f.hp_off;
+  const int total = (int)f.rows * KT;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int xr = i / KT, kl = i - xr * KT;
+    const int col = kt * KT + kl;
+    float v = 0.f;
+    if (col < ncols) {
+      const double *gss = ss + f.ss_off + (size_t)col2slot[col] * f.ss_w;
+      if (f.kind == KIND_TABLE) {
+        if ((uint32_t)xr < f.ncat)
+          v = (float)(f.family == FAM_BB ? bb_score(fhp, gss, xr) : dd_score(fhp, f.asum, gss, (uint32_t)xr));
+      } else if (f.kind == KIND_GP) {
+        const GpPost p = gp_post(fhp, gss);
+        if ((uint32_t)xr < f.ncat) v = (float)gp_score(p, (double)xr);
+        else if ((uint32_t)xr == f.ncat) v = 0.f;
+        else if ((uint32_t)xr == f.ncat + 1) v = (float)p.a;
+        else if ((uint32_t)xr == f.ncat + 2) v = (float)p.ca;
+        else v = (float)p.l1pb;
+      } else if (f.kind == KIND_NICH) {
+        const NichPost p = nich_post(fhp, gss);
+        v = xr == 0 ? (float)p.mu : xr == 1 ? (float)p.s : xr == 2 ? (float)p.c1 : (float)p.c0;
+      }
+    }
+    chunk[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Score kernel.  One warp owns RW rows; lane l owns V consecutive groups of the
+// block's k-tile (KT = 32 V), so a (row, feature) lookup is one conflict-free
+// shared-memory read of 128 V bytes per warp and the value x is warp-uniform
+// (broadcast from the lane that loaded it).  Accumulators acc[RW][V] stay in
+// registers across all features; the N x K result is written once, coalesced.
+// ---------------------------------------------------------------------------
+template <int V> struct VecF;
+template <> struct VecF<1> { float v[1]; __device__ void load(const float *p) { v[0] = *p; } };
+template <> struct VecF<2> { float v[2]; __device__ void load(const float *p) { const float2 t = *(const float2 *)p; v[0] = t.x; v[1] = t.y; } };
+template <> struct VecF<4> { float v[4]; __device__ void load(const float *p) { const float4 t = *(const float4 *)p; v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
+
+template <int V>
+__device__ __forceinline__ void store_vec(float *p, const float *a) {
+  if constexpr (V == 1) *p = a[0];
+  else if constexpr (V == 2) *(float2 *)p = make_float2(a[0], a[1]);
+  else *(float4 *)p = make_float4(a[0], a[1], a[2], a[3]);
+}
+
+constexpr int SCORE_WARPS = 8;
+
+template <int V, int RW>
+__global__ void __launch_bounds__(SCORE_WARPS * 32)
+score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restrict__ params, size_t region_rows,
+             const float *__restrict__ base, float *__restrict__ scores, size_t ld, size_t row_lo, size_t row_hi) {
+  constexpr int KT = 32 * V;
+  extern __shared__ float4 smem4[];
+  float *smem = reinterpret_cast<float *>(smem4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t row0 = row_lo + ((size_t)blockIdx.x * SCORE_WARPS + warp) * RW;
+  const int kt = blockIdx.y;
+  const float *region = params + (size_t)kt * region_rows * KT;
+  const size_t myrow = row0 + lane;
+  const bool valid = lane < RW && myrow < row_hi;
+
+  float acc[RW][V];
+#pragma unroll
+  for (int r = 0; r < RW; r++)
+#pragma unroll
+    for (int v = 0; v < V; v++) acc[r][v] = 0.f;
+
+  for (int d = 0; d < nfeat; d++) {
+    const FeatDev f = feats[d];
+    if (f.rows == 0) continue;
+    // this lane's row value for feature d (global load issued before the chunk copy)
+    uint32_t xi = f.ncat;
+    float xf = CUDART_NAN_F;
+    if (valid) {
+      if (f.coltype == COL_U8) xi = ((const uint8_t *)f.col)[myrow];
+      else if (f.coltype == COL_U16) xi = ((const uint16_t *)f.col)[myrow];
+      else if (f.coltype == COL_U32) xi = ((const uint32_t *)f.col)[myrow];
+      else xf = ((const float *)f.col)[myrow];
+    } else if (f.kind == KIND_GP) {
+      xi = GP_SENTINEL;
+    }
+    __syncthreads();  // previous chunk fully consumed
+    {
+      const float4 *src = reinterpret_cast<const float4 *>(region + (size_t)f.rowoff * KT);
+      const int n4 = (int)f.rows * (KT / 4);
+      for (int i = threadIdx.x; i < n4; i += SCORE_WARPS * 32) smem4[i] = src[i];
+    }
+    __syncthreads();
+    if (f.kind == KIND_TABLE) {
+#pragma unroll
+      for (int r = 0; r < RW; r++) {
+        const uint32_t x = __shfl_sync(0xffffffffu, xi, r);
+        VecF<V> t;
+        t.load(smem + (size_t)x * KT + lane * V);
+#pragma unroll
+        for (int v = 0; v < V; v++) acc[r][v] += t.v[v];
+      }
+    } else if (f.kind == KIND_GP) {
+      const uint32_t cap = f.ncat;
+      const uint32_t xrow = xi == GP_SENTINEL ? cap : (xi < cap ? xi : cap + 1);
+#pragma unroll
+      for (int r = 0; r < RW; r++) {
+        const uint32_t x = __shfl_sync(0xffffffffu, xrow, r);
+        if (x <= cap) {
+          VecF<V> t;
+          t.load(smem + (size_t)x * KT + lane * V);
+#pragma unroll
+          for (int v = 0; v < V; v++) acc[r][v] += t.v[v];
+        } else {  // count beyond the table: evaluate the closed form (rare)
+          const float xv = (float)__shfl_sync(0xffffffffu, xi, r);
+          const float lgx1 = lgammaf(xv + 1.f);
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const float a = smem[(size_t)(cap + 1) * KT + lane * V + v];
+            const float ca = smem[(size_t)(cap + 2) * KT + lane * V + v];
+            const float l1pb = smem[(size_t)(cap + 3) * KT + lane * V + v];
+            acc[r][v] += lgammaf(a + xv) - lgx1 + ca - xv * l1pb;
+          }
+        }
+      }
+    } else {  // KIND_NICH
+      VecF<V> mu, s, c1, c0;
+      mu.load(smem + 0 * KT + lane * V);
+      s.load(smem + 1 * KT + lane * V);
+      c1.load(smem + 2 * KT + lane * V);
+      c0.load(smem + 3 * KT + lane * V);
+#pragma unroll
+      for (int r = 0; r < RW; r++) {
+        const float x = __shfl_sync(0xffffffffu, xf, r);
+        if (x == x) {
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const float t = (x - mu.v[v]) * s.v[v];
+            acc[r][v] += fmaf(c1.v[v], log1p_pos(t * t), c0.v[v]);
+          }
+        }
+      }
+    }
+  }
+  // epilogue: + log(pseudocount) (group_manager.hpp:274-283), coalesced 128 V-byte stores
+  VecF<V> b;
+  b.load(base + (size_t)kt * KT + lane * V);
+#pragma unroll
+  for (int r = 0; r < RW; r++) {
+    const size_t row = row0 + r;
+    if (row < row_hi) {
+      float o[V];
+#pragma unroll
+      for (int v = 0; v < V; v++) o[v] = acc[r][v] + b.v[v];
+      store_vec<V>(scores + (row - row_lo) * ld + (size_t)kt * KT + lane * V, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Direct scorer: closed forms straight from the suffstats in fp64, no tables.
+// Used for single-entity score_value (entity_state.hpp:60-72) and as an
+// independent on-device cross-check of the table path.  Scalar families only.
+// ---------------------------------------------------------------------------
+__global__ void score_direct_kernel(const FeatDev *__restrict__ feats, int nfeat, const double *__restrict__ hp,
+                                    const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols,
+                                    const float *__restrict__ base, float *__restrict__ scores, size_t ld,
+                                    size_t row_lo, size_t row_hi) {
+  const size_t row = row_lo + blockIdx.x;
+  if (row >= row_hi) return;
+  for (int col = threadIdx.x; col < ncols; col += blockDim.x) {
+    const int slot = col2slot[col];
+    double s = 0.0;
+    for (int d = 0; d < nfeat; d++) {
+      const FeatDev f = feats[d];
+      const double *fhp = hp + f.hp_off;
+      const double *gss = ss + f.ss_off + (size_t)slot * f.ss_w;
+      if (f.kind == KIND_TABLE) {
+        uint32_t x;
+        if (f.coltype == COL_U8) x = ((const uint8_t *)f.col)[row];
+        else if (f.coltype == COL_U16) x = ((const uint16_t *)f.col)[row];
+        else x = ((const uint32_t *)f.col)[row];
+        if (x >= f.ncat) continue;
+        s += f.family == FAM_BB ? bb_score(fhp, gss, (int)x) : dd_score(fhp, f.asum, gss, x);
+      } else if (f.kind == KIND_GP) {
+        const uint32_t x = ((const uint32_t *)f.col)[row];
+        if (x == GP_SENTINEL) continue;
+        s += gp_score(gp_post(fhp, gss), (double)x);
+      } else if (f.kind == KIND_NICH) {
+        const float x = ((const float *)f.col)[row];
+        if (x != x) continue;
+        s += nich_score(nich_post(fhp, gss), (double)x);
+      }
+    }
+    scores[(row - row_lo) * ld + col] = (float)(s + (double)base[col]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// NIW: per-group preparation (posterior, Cholesky, inverse factor) in fp64.
+//   hp = [mu[d], kappa, psi[d*d], nu]   ss = [count, sum_x[d], sum_xxT[d*d]]
+// Outputs per column k: W[k] = L^-1 (row-major d x d, float), bias[k] = W mu',
+// coef[k] = {c0, -(dof+d)/2, 1/dof}.  score = c0 + c1 log1p(|W x - bias|^2 / dof).
+// ---------------------------------------------------------------------------
+__global__ void niw_prepare_kernel(FeatDev f, const double *__restrict__ hp, const double *__restrict__ ss,
+                                   const int32_t *__restrict__ col2slot, float *__restrict__ W,
+                                   float *__restrict__ bias, float *__restrict__ coef) {
+  extern __shared__ double sm[];
+  const int d = (int)f.dim;
+  double *A = sm;            // d*d
+  double *mu = A + d * d;    // d
+  double *Winv = mu + d;     // d*d
+  __shared__ double s_logdiag;
+  __shared__ int s_fail;
+  const int k = blockIdx.x;
+  const double *fhp = hp + f.hp_off;
+  const double *gss = ss + f.ss_off + (size_t)col2slot[k] * f.ss_w;
+  const double *mu0 = fhp, kappa0 = fhp[d], *psi0 = fhp + d + 1, nu0 = fhp[d + 1 + (size_t)d * d];
+  const double n = gss[0];
+  const double *sx = gss + 1, *sxx = gss + 1 + d;
+  const double kn = kappa0 + n, nun = nu0 + n;
+  const double dof = nun - (double)d + 1.0;
+  const double scale = (kn + 1.0) / (kn * dof);
+  if (threadIdx.x == 0) { s_fail = 0; s_logdiag = 0.0; }
+  for (int i = threadIdx.x; i < d; i += blockDim.x) mu[i] = (kappa0 * mu0[i] + sx[i]) / kn;
+  __syncthreads();
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int i = e / d, j = e - i * d;
+    A[e] = (psi0[e] + sxx[e] + kappa0 * mu0[i] * mu0[j] - kn * mu[i] * mu[j]) * scale;
+  }
+  __syncthreads();
+  // right-looking Cholesky, lower triangle in place
+  for (int j = 0; j < d; j++) {
+    if (threadIdx.x == 0) {
+      const double v = A[j * d + j];
+      if (!(v > 0.0)) s_fail = 1;
+      A[j * d + j] = sqrt(v > 0.0 ? v : 1.0);
+    }
+    __syncthreads();
+    const double ljj = A[j * d + j];
+    for (int i = j + 1 + threadIdx.x; i < d; i += blockDim.x) A[i * d + j] /= ljj;
+    __syncthreads();
+    const int rem = d - j - 1;
+    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
+      const int a = j + 1 + e / rem, b = j + 1 + e % rem;
+      if (b <= a) A[a * d + b] -= A[a * d + j] * A[b * d + j];
+    }
+    __syncthreads();
+  }
+  // W = L^-1: thread c solves L w = e_c by forward substitution
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    for (int i = 0; i < d; i++) {
+      double t = (i == c) ? 1.0 : 0.0;
+      for (int m = c; m < i; m++) t -= A[i * d + m] * Winv[m * d + c];
+      Winv[i * d + c] = i < c ? 0.0 : t / A[i * d + i];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ld = 0.0;
+    for (int i = 0; i < d; i++) ld += log(A[i * d + i]);
+    s_logdiag = ld;
+  }
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) W[(size_t)k * d * d + e] = (float)Winv[e];
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    double b = 0.0;
+    for (int j = 0; j <= i; j++) b += Winv[i * d + j] * mu[j];
+    bias[(size_t)k * d + i] = (float)b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double c0 = lgamma(0.5 * (dof + d)) - lgamma(0.5 * dof) - 0.5 * d * log(dof * CUDART_PI) - s_logdiag;
+    coef[(size_t)k * 4 + 0] = s_fail ? CUDART_NAN_F : (float)c0;
+    coef[(size_t)k * 4 + 1] = (float)(-0.5 * (dof + d));
+    coef[(size_t)k * 4 + 2] = (float)(1.0 / dof);
+    coef[(size_t)k * 4 + 3] = 0.f;
+  }
+}
+
+// CUDA-core NIW scorer (any dim): thread per row, W_k staged in shared memory.
+// scores[row][k] += c0 + c1 log1p(q / dof).  The tcgen05 path replaces this
+// for dim == 64 (msb_niw_tc.cuh).
+__global__ void niw_score_simt_kernel(const float *__restrict__ X, int d, const float *__restrict__ W,
+                                      const float *__restrict__ bias, const float *__restrict__ coef,
+                                      float *__restrict__ scores, size_t ld, size_t row_lo, size_t row_hi) {
+  extern __shared__ float smf[];
+  float *Wk = smf;          // d*d
+  float *bk = Wk + d * d;   // d
+  const int k = blockIdx.y;
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) Wk[e] = W[(size_t)k * d * d + e];
+  for (int e = threadIdx.x; e < d; e += blockDim.x) bk[e] = bias[(size_t)k * d + e];
+  __syncthreads();
+  const size_t row = row_lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= row_hi) return;
+  const float *x = X + row * (size_t)d;
+  if (x[0] != x[0]) return;  // masked
+  float q = 0.f;
+  for (int i = 0; i < d; i++) {
+    float y = -bk[i];
+    for (int j = 0; j <= i; j++) y = fmaf(Wk[i * d + j], x[j], y);
+    q = fmaf(y, y, q);
+  }
+  const float c0 = coef[(size_t)k * 4 + 0], c1 = coef[(size_t)k * 4 + 1], idof = coef[(size_t)k * 4 + 2];
+  scores[(row - row_lo) * ld + k] += c0 + c1 * log1pf(q * idof);
+}
+
+// ---------------------------------------------------------------------------
+// Sampler: util.hpp:125-156 exactly -- max, exp, double accumulation in group
+// order, float division, sequential dart subtraction with last-index fallback.
+// The order of the floating-point operations is part of the contract (the
+// checker must reproduce the draw bit for bit), so one thread walks one row.
+// ---------------------------------------------------------------------------
+__global__ void sample_kernel(const float *__restrict__ scores, size_t ld, int K, size_t nrows,
+                              const float *__restrict__ uniforms, uint64_t seed, uint64_t sweep, uint64_t row_id0,
+                              const int32_t *__restrict__ col2slot, int32_t *__restrict__ out_col,
+                              int32_t *__restrict__ out_slot) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const float *s = scores + i * ld;
+  float m = s[0];
+  for (int k = 1; k < K; k++) m = fmaxf(m, s[k]);
+  double acc_d = 0.0;
+  for (int k = 0; k < K; k++) acc_d = __dadd_rn(acc_d, (double)msb_expf(__fsub_rn(s[k], m)));
+  const float acc = __double2float_rn(acc_d);
+  float dart = uniforms ? uniforms[i] : philox_u01(seed, row_id0 + i, sweep);
+  int pick = K - 1;
+  for (int k = 0; k < K; k++) {
+    const float p = __fdiv_rn(msb_expf(__fsub_rn(s[k], m)), acc);
+    dart = __fsub_rn(dart, p);
+    if (dart <= 0.f) { pick = k; break; }
+  }
+  if (out_col) out_col[i] = pick;
+  if (out_slot) out_slot[i] = col2slot ? col2slot[pick] : pick;
+}
+
+__global__ void philox_fill_kernel(uint64_t seed, uint64_t sweep, uint64_t row0, size_t n, float *out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = philox_u01(seed, row0 + i, sweep);
+}
+
+// ---------------------------------------------------------------------------
+// Suffstat update: remove_value(old group) / add_value(new group) for every
+// (row, feature) cell whose row moved (base.hpp:25-26).  All device suffstats
+// are additive fp64 (integers exact), so the deltas can be summed across GPUs.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
+
+__global__ void update_kernel(const FeatDev *__restrict__ feats, int nfeat, const int32_t *__restrict__ old_slot,
+                              const int32_t *__restrict__ new_slot, size_t row_lo, size_t row_hi,
+                              double *__restrict__ delta) {
+  const size_t row = row_lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = blockIdx.y;
+  if (row >= row_hi) return;
+  const int a = old_slot ? old_slot[row] : -1;
+  const int b = new_slot ? new_slot[row - row_lo] : -1;
+  if (a == b) return;
+  const FeatDev f = feats[d];
+  double *blk = delta + f.ss_off;
+  if (f.kind == KIND_TABLE) {
+    uint32_t x;
+    if (f.coltype == COL_U8) x = ((const uint8_t *)f.col)[row];
+    else if (f.coltype == COL_U16) x = ((const uint16_t *)f.col)[row];
+    else x = ((const uint32_t *)f.col)[row];
+    if (x >= f.ncat) return;
+    if (f.family == FAM_BB) {  // ss = [heads, tails]
+      const int j = x ? 0 : 1;
+      if (a >= 0) atomic_add_f64(blk + (size_t)a * 2 + j, -1.0);
+      if (b >= 0) atomic_add_f64(blk + (size_t)b * 2 + j, 1.0);
+    } else {  // ss = [count_sum, counts[dim]]
+      if (a >= 0) { atomic_add_f64(blk + (size_t)a * f.ss_w, -1.0); atomic_add_f64(blk + (size_t)a * f.ss_w + 1 + x, -1.0); }
+      if (b >= 0) { atomic_add_f64(blk + (size_t)b * f.ss_w, 1.0); atomic_add_f64(blk + (size_t)b * f.ss_w + 1 + x, 1.0); }
+    }
+  } else if (f.kind == KIND_GP) {  // ss = [count, sum, log_prod]
+    const uint32_t x = ((const uint32_t *)f.col)[row];
+    if (x == GP_SENTINEL) return;
+    const double xd = (double)x, lf = lgamma(xd + 1.0);
+    if (a >= 0) { double *p = blk + (size_t)a * 3; atomic_add_f64(p, -1.0); atomic_add_f64(p + 1, -xd); atomic_add_f64(p + 2, -lf); }
+    if (b >= 0) { double *p = blk + (size_t)b * 3; atomic_add_f64(p, 1.0); atomic_add_f64(p + 1, xd); atomic_add_f64(p + 2, lf); }
+  } else if (f.kind == KIND_NICH) {  // ss = [count, sum x, sum x^2]
+    const float xf = ((const float *)f.col)[row];
+    if (xf != xf) return;
+    const double xd = (double)xf, x2 = xd * xd;
+    if (a >= 0) { double *p = blk + (size_t)a * 3; atomic_add_f64(p, -1.0); atomic_add_f64(p + 1, -xd); atomic_add_f64(p + 2, -x2); }
+    if (b >= 0) { double *p = blk + (size_t)b * 3; atomic_add_f64(p, 1.0); atomic_add_f64(p + 1, xd); atomic_add_f64(p + 2, x2); }
+  }
+}
+
+// NIW update: one warp per moved row, lanes over the d + d*d moment entries.
+__global__ void update_niw_kernel(FeatDev f, const int32_t *__restrict__ old_slot, const int32_t *__restrict__ new_slot,
+                                  size_t row_lo, size_t row_hi, double *__restrict__ delta) {
+  const size_t row = row_lo + (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= row_hi) return;
+  const int a = old_slot ? old_slot[row] : -1;
+  const int b = new_slot ? new_slot[row - row_lo] : -1;
+  if (a == b) return;
+  const int d = (int)f.dim;
+  const float *x = (const float *)f.col + row * (size_t)d;
+  if (x[0] != x[0]) return;
+  double *blk = delta + f.ss_off;
+  if (lane == 0) {
+    if (a >= 0) atomic_add_f64(blk + (size_t)a * f.ss_w, -1.0);
+    if (b >= 0) atomic_add_f64(blk + (size_t)b * f.ss_w, 1.0);
+  }
+  for (int e = lane; e < d + d * d; e += 32) {
+    double v;
+    if (e < d) v = (double)x[e];
+    else { const int i = (e - d) / d, j = (e - d) - i * d; v = (double)x[i] * (double)x[j]; }
+    if (a >= 0) atomic_add_f64(blk + (size_t)a * f.ss_w + 1 + e, -v);
+    if (b >= 0) atomic_add_f64(blk + (size_t)b * f.ss_w + 1 + e, v);
+  }
+}
+
+// CRP bookkeeping (group_manager.hpp:218-248): per-group entity counts,
+// assignment vector, number of moved rows.
+__global__ void commit_assign_kernel(int32_t *__restrict__ assign, const int32_t *__restrict__ new_slot,
+                                     size_t row_lo, size_t row_hi, double *__restrict__ delta_counts,
+                                     unsigned long long *__restrict__ moved) {
+  const size_t row = row_lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= row_hi) return;
+  const int a = assign[row], b = new_slot[row - row_lo];
+  if (a == b) return;
+  if (a >= 0) atomic_add_f64(delta_counts + a, -1.0);
+  if (b >= 0) atomic_add_f64(delta_counts + b, 1.0);
+  assign[row] = b;
+  atomicAdd(moved, 1ull);
+}
+
+__global__ void apply_delta_kernel(double *__restrict__ ss, double *__restrict__ delta, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { ss[i] += delta[i]; delta[i] = 0.0; }
+}
+
+// gid <-> slot translation of the assignment vector
+__global__ void map_i32_to_i64_kernel(const int32_t *__restrict__ in, const int64_t *__restrict__ table, size_t n,
+                                      int64_t *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] < 0 ? -1 : table[in[i]];
+}
+
+// ---------------------------------------------------------------------------
+// Single-value plugin calls (models/base.hpp:25-27) on the device.  ss here is
+// the reference's field representation (nich: count, mean, count_times_variance).
+// op: 0 score, 1 add, 2 remove.
+// ---------------------------------------------------------------------------
+__global__ void value_op_kernel(int family, uint32_t dim, int op, const double *__restrict__ hp, double *__restrict__ ss,
+                                const double *__restrict__ x, float *__restrict__ score) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double sgn = op == 2 ? -1.0 : 1.0;
+  if (family == FAM_BB) {
+    if (op == 0) *score = (float)bb_score(hp, ss, x[0] != 0.0);
+    else ss[x[0] != 0.0 ? 0 : 1] += sgn;
+  } else if (family == FAM_DD) {
+    const uint32_t xi = (uint32_t)x[0];
+    if (op == 0) {
+      double asum = 0.0;
+      for (uint32_t i = 0; i < dim; i++) asum += hp[i];
+      *score = xi < dim ? (float)dd_score(hp, asum, ss, xi) : CUDART_NAN_F;
+    } else if (xi < dim) { ss[0] += sgn; ss[1 + xi] += sgn; }
+  } else if (family == FAM_GP) {
+    if (op == 0) *score = (float)gp_score(gp_post(hp, ss), x[0]);
+    else { ss[0] += sgn; ss[1] += sgn * x[0]; ss[2] += sgn * lgamma(x[0] + 1.0); }
+  } else if (family == FAM_NICH) {
+    double add[3] = {ss[0], ss[0] * ss[1], ss[2] + ss[0] * ss[1] * ss[1]};  // -> (n, sum x, sum x^2)
+    if (op == 0) *score = (float)nich_score(nich_post(hp, add), x[0]);
+    else {
+      add[0] += sgn; add[1] += sgn * x[0]; add[2] += sgn * x[0] * x[0];
+      ss[0] = add[0];
+      ss[1] = add[0] > 0.0 ? add[1] / add[0] : 0.0;
+      double ctv = add[0] > 1.0 ? add[2] - add[1] * ss[1] : 0.0;
+      ss[2] = ctv > 0.0 ? ctv : 0.0;
+    }
+  } else if (family == FAM_NIW && op != 0) {
+    ss[0] += sgn;
+    for (uint32_t i = 0; i < dim; i++) ss[1 + i] += sgn * x[i];
+    for (uint32_t i = 0; i < dim; i++)
+      for (uint32_t j = 0; j < dim; j++) ss[1 + dim + i * dim + j] += sgn * x[i] * x[j];
+  }
+}
+
+}  // namespace msb

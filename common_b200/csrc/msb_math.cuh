@@ -1,0 +1,131 @@
+// msb_math.cuh -- device math shared by the kernels of the hot path.
+//
+// Closed forms of the conjugate families the reference reaches through
+// distributions_group<T>::score_value (include/microscopes/models/
+// distributions.hpp:280-285 in the reference tree); the maths itself lives in
+// the un-vendored `distributions` library and is restated from the published
+// posterior-predictive formulas.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace msb {
+
+enum Family : int { FAM_BB = 0, FAM_BNB = 1, FAM_GP = 2, FAM_NICH = 3, FAM_DD = 4, FAM_NIW = 5 };
+
+// ---------------------------------------------------------------------------
+// msb_expf: exp() built only from correctly rounded IEEE-754 binary32
+// operations in a fixed order, so that the CPU checker can reproduce it bit for
+// bit (sampler contract).  Explicit _rn intrinsics are never
+// contracted or reassociated by nvcc.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float msb_expf(float x) {
+  if (!(x >= -104.0f)) return x != x ? x : 0.0f;
+  if (x > 88.0f) x = 88.0f;
+  const float kf = rintf(__fmul_rn(x, 1.44269504f));
+  float r = __fmaf_rn(kf, -0.693145752f, x);
+  r = __fmaf_rn(kf, -1.42860677e-6f, r);
+  float p = 1.9875691500e-4f;
+  p = __fmaf_rn(p, r, 1.3981999507e-3f);
+  p = __fmaf_rn(p, r, 8.3334519073e-3f);
+  p = __fmaf_rn(p, r, 4.1665795894e-2f);
+  p = __fmaf_rn(p, r, 1.6666665459e-1f);
+  p = __fmaf_rn(p, r, 5.0000001201e-1f);
+  const float r2 = __fmul_rn(r, r);
+  p = __fmaf_rn(p, r2, r);
+  p = __fadd_rn(p, 1.0f);
+  const int k = (int)kf;
+  const int k1 = k / 2, k2 = k - k1;
+  const float a = __int_as_float((k1 + 127) << 23);
+  const float b = __int_as_float((k2 + 127) << 23);
+  return __fmul_rn(__fmul_rn(p, a), b);
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  key = seed, counter = (row, sweep).
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t row, uint64_t sweep, uint32_t out[4]) {
+  uint32_t c0 = (uint32_t)row, c1 = (uint32_t)(row >> 32), c2 = (uint32_t)sweep, c3 = (uint32_t)(sweep >> 32);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__host__ __device__ __forceinline__ float philox_u01(uint64_t seed, uint64_t row, uint64_t sweep) {
+  uint32_t r[4];
+  philox4x32_10(seed, row, sweep, r);
+  return (float)(r[0] >> 8) * 5.9604644775390625e-8f;  // [0,1)
+}
+
+// ---------------------------------------------------------------------------
+// fp64 closed forms over the device suffstat representation (all additive):
+//   bb   ss = [heads, tails]                 hp = [alpha, beta]
+//   dd   ss = [count_sum, counts[dim]]       hp = alphas[dim]   (asum passed in)
+//   gp   ss = [count, sum, log_prod]         hp = [alpha, inv_beta]
+//   nich ss = [count, sum x, sum x^2]        hp = [mu, kappa, sigmasq, nu]
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double bb_score(const double *hp, const double *ss, int x) {
+  const double a = hp[0] + ss[0], b = hp[1] + ss[1];
+  return log((x ? a : b) / (a + b));
+}
+__device__ __forceinline__ double dd_score(const double *hp, double asum, const double *ss, uint32_t x) {
+  return log((hp[x] + ss[1 + x]) / (asum + ss[0]));
+}
+struct GpPost { double a, b, ca, l1pb; };  // ca = -lgamma(a) + a log b - a log1p(b)
+__device__ __forceinline__ GpPost gp_post(const double *hp, const double *ss) {
+  GpPost p;
+  p.a = hp[0] + ss[1];
+  p.b = hp[1] + ss[0];
+  p.l1pb = log1p(p.b);
+  p.ca = -lgamma(p.a) + p.a * log(p.b) - p.a * p.l1pb;
+  return p;
+}
+__device__ __forceinline__ double gp_score(const GpPost &p, double x) {
+  return lgamma(p.a + x) - lgamma(x + 1.0) + p.ca - x * p.l1pb;
+}
+struct NichPost { double mu, s, c1, c0; };  // score = c0 + c1 * log1p(((x - mu) s)^2)
+__device__ __forceinline__ NichPost nich_post(const double *hp, const double *ss) {
+  const double n = ss[0];
+  const double mean = n > 0.0 ? ss[1] / n : 0.0;
+  double ctv = n > 0.0 ? ss[2] - ss[1] * mean : 0.0;
+  if (ctv < 0.0) ctv = 0.0;
+  const double mu1 = hp[0] - mean;
+  const double kappa = hp[1] + n;
+  const double nu = hp[3] + n;
+  const double sigmasq = (hp[3] * hp[2] + ctv + (n * hp[1] * mu1 * mu1) / kappa) / nu;
+  const double lambda = kappa / ((kappa + 1.0) * sigmasq);
+  NichPost p;
+  p.mu = (hp[1] * hp[0] + mean * n) / kappa;
+  p.s = sqrt(lambda / nu);
+  p.c1 = -0.5 * nu - 0.5;
+  p.c0 = lgamma(0.5 * nu + 0.5) - lgamma(0.5 * nu) + 0.5 * log(lambda / (CUDART_PI * nu));
+  return p;
+}
+__device__ __forceinline__ double nich_score(const NichPost &p, double x) {
+  const double t = (x - p.mu) * p.s;
+  return p.c0 + p.c1 * log1p(t * t);
+}
+
+// fp32 log1p(z), z >= 0, for the nich inner loop: relative error ~1e-7 for
+// z < 1/16 (degree-5 polynomial, FMA pipe) and MUFU.LG2 above (relative error
+// <= 2^-22 / log2(1.0625) = 2.7e-6 in the worst case just above the switch).
+__device__ __forceinline__ float log1p_pos(float z) {
+  float p = -1.0f / 6.0f;
+  p = fmaf(p, z, 0.2f);
+  p = fmaf(p, z, -0.25f);
+  p = fmaf(p, z, 1.0f / 3.0f);
+  p = fmaf(p, z, -0.5f);
+  p = fmaf(p, z, 1.0f);
+  const float small = p * z;
+  const float big = __log2f(1.0f + z) * 0.693147180559945f;
+  return z < 0.0625f ? small : big;
+}
+
+}  // namespace msb

@@ -1,0 +1,1206 @@
+// mscope_b200.cu -- implementation of the C ABI declared in include/mscope_b200.h.
+// Host orchestration only; all arithmetic of the hot path runs in the kernels of
+// msb_kernels.cuh / msb_niw_tc.cuh on the context's CUDA stream.
+#include "../../include/mscope_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "msb_kernels.cuh"
+#include "msb_niw_tc.cuh"
+
+using namespace msb;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
+
+#define CU_TRY(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(MSB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+#define MSB_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != MSB_OK) return _s; \
+  } while (0)
+#define REQUIRE(cond, msg) \
+  do { if (!(cond)) return fail(MSB_ERR_INVALID, msg); } while (0)
+
+extern "C" MSB_API const char *msb_last_error(void) { return g_last_error.c_str(); }
+extern "C" MSB_API int msb_abi_version(void) { return MSB_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------
+struct msb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint64_t launches = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+};
+
+struct msb_dataview {
+  msb_ctx *ctx = nullptr;
+  size_t n = 0, D = 0, rowsize = 0, maskrowsize = 0;
+  std::vector<msb_runtime_type> types;
+  std::vector<size_t> off, moff;
+  uint8_t *d_data = nullptr, *d_mask = nullptr;
+  bool owns = false;
+};
+
+struct PhaseEvents { cudaEvent_t e[6]; };
+
+struct msb_state {
+  msb_ctx *ctx = nullptr;
+  size_t D = 0, kmax = 0;
+  std::vector<msb_model_desc> models;
+  std::vector<FeatDev> feats;
+  FeatDev *d_feats = nullptr;
+  bool feats_dirty = true;
+  // hypers
+  std::vector<double> h_hp;
+  double *d_hp = nullptr;
+  bool hp_dirty = true;
+  // suffstats: [counts kmax | per-feature blocks]
+  size_t SS = 0;
+  double *d_ss = nullptr, *d_delta = nullptr;
+  // CRP bookkeeping (group_manager.hpp:48-306)
+  double alpha = 1.0;
+  size_t gcount = 0;
+  std::map<size_t, int> gid2slot;
+  std::vector<int64_t> slot2gid;
+  std::vector<int> free_slots;
+  std::vector<double> h_counts;
+  // data
+  msb_dataview *dv = nullptr;
+  size_t n = 0;
+  std::vector<void *> cols;
+  int32_t *d_assign = nullptr;
+  size_t region_rows = 0, max_chunk_rows = 0;
+  bool has_niw = false, has_scalar = false;
+  // workspaces
+  float *d_params = nullptr; size_t params_cap = 0;
+  float *d_scores = nullptr; size_t scores_cap = 0;
+  float *d_base = nullptr; size_t base_cap = 0;
+  int32_t *d_col2slot = nullptr; size_t col_cap = 0;
+  int64_t *d_slot2gid = nullptr;
+  int32_t *d_newslot = nullptr, *d_newcol = nullptr; size_t row_cap = 0;
+  float *d_uniforms = nullptr;
+  unsigned long long *d_counter = nullptr;
+  std::vector<float *> d_niwW, d_niwBias, d_niwCoef, d_niwB;
+  size_t niw_cols_cap = 0;
+  // last score
+  int V = 2; size_t ld = 0, last_rows = 0, last_cols = 0;
+  std::vector<int32_t> h_col2slot;
+  std::vector<size_t> h_colgid;
+  std::vector<PhaseEvents> events;
+  float last_ms[5] = {0, 0, 0, 0, 0};
+};
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
+  do {                                                                   \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);     \
+    (ctx)->launches++;                                                   \
+    CU_TRY(cudaGetLastError());                                          \
+  } while (0)
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+template <typename K> static cudaError_t opt_in_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
+  REQUIRE(out, "msb_ctx_create: out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(MSB_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  REQUIRE(device >= 0 && device < ndev, "msb_ctx_create: bad device index");
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(MSB_ERR_UNSUPPORTED, "this library is built for sm_100a (B200) only; device is sm_" +
+                                         std::to_string(prop.major) + std::to_string(prop.minor));
+  msb_ctx *c = new msb_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  if (stream) c->stream = (cudaStream_t)stream;
+  else { CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  CU_TRY(opt_in_smem(score_kernel<1, 32>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<2, 32>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<4, 16>, c->smem_optin));
+  CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin));
+  CU_TRY(opt_in_smem(niw_score_simt_kernel, c->smem_optin));
+  MSB_TRY(niw_tc_init(c->smem_optin, g_last_error));
+  *out = c;
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_ctx_destroy(msb_ctx *ctx) {
+  if (!ctx) return MSB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_ctx_synchronize(msb_ctx *ctx) {
+  REQUIRE(ctx, "ctx is NULL");
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return MSB_OK;
+}
+extern "C" MSB_API void *msb_ctx_stream(msb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" MSB_API int msb_ctx_launch_count(msb_ctx *ctx, uint64_t *out) {
+  REQUIRE(ctx && out, "NULL argument");
+  *out = ctx->launches;
+  return MSB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// dataview
+// ---------------------------------------------------------------------------
+static const size_t k_prim_size[MSB_TYPE_NELEMS] = {1, 1, 1, 2, 2, 4, 4, 8, 8, 4, 8};
+
+extern "C" MSB_API int msb_dataview_create(msb_ctx *ctx, const void *data, const void *mask, size_t n,
+                                   const msb_runtime_type *types, size_t nfeatures, int on_device,
+                                   msb_dataview **out) {
+  REQUIRE(ctx && types && out, "msb_dataview_create: NULL argument");
+  REQUIRE(data || n == 0, "msb_dataview_create: data is NULL");
+  REQUIRE(nfeatures > 0, "msb_dataview_create: no features");
+  CU_TRY(cudaSetDevice(ctx->device));
+  msb_dataview *dv = new msb_dataview();
+  dv->ctx = ctx; dv->n = n; dv->D = nfeatures;
+  dv->types.assign(types, types + nfeatures);
+  size_t o = 0, mo = 0;
+  for (size_t d = 0; d < nfeatures; d++) {  // runtime_type.hpp:123-134
+    if (types[d].prim < 0 || types[d].prim >= MSB_TYPE_NELEMS || types[d].n == 0) {
+      delete dv;
+      return fail(MSB_ERR_INVALID, "msb_dataview_create: bad runtime type for feature " + std::to_string(d));
+    }
+    dv->off.push_back(o); dv->moff.push_back(mo);
+    o += (size_t)types[d].n * k_prim_size[types[d].prim];
+    mo += types[d].n;
+  }
+  dv->rowsize = o; dv->maskrowsize = mo;
+  if (on_device) {
+    dv->d_data = (uint8_t *)data; dv->d_mask = (uint8_t *)mask; dv->owns = false;
+  } else {
+    dv->owns = true;
+    if (n) {
+      CU_TRY(cudaMalloc(&dv->d_data, n * dv->rowsize));
+      CU_TRY(cudaMemcpyAsync(dv->d_data, data, n * dv->rowsize, cudaMemcpyHostToDevice, ctx->stream));
+      if (mask) {
+        CU_TRY(cudaMalloc(&dv->d_mask, n * dv->maskrowsize));
+        CU_TRY(cudaMemcpyAsync(dv->d_mask, mask, n * dv->maskrowsize, cudaMemcpyHostToDevice, ctx->stream));
+      }
+    }
+  }
+  *out = dv;
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_dataview_destroy(msb_dataview *dv) {
+  if (!dv) return MSB_OK;
+  cudaSetDevice(dv->ctx->device);
+  cudaStreamSynchronize(dv->ctx->stream);
+  if (dv->owns) { cudaFree(dv->d_data); cudaFree(dv->d_mask); }
+  delete dv;
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_dataview_size(const msb_dataview *dv, size_t *n) { REQUIRE(dv && n, "NULL argument"); *n = dv->n; return MSB_OK; }
+extern "C" MSB_API int msb_dataview_nfeatures(const msb_dataview *dv, size_t *d) { REQUIRE(dv && d, "NULL argument"); *d = dv->D; return MSB_OK; }
+extern "C" MSB_API int msb_dataview_rowsize(const msb_dataview *dv, size_t *rowsize, size_t *maskrowsize) {
+  REQUIRE(dv, "NULL argument");
+  if (rowsize) *rowsize = dv->rowsize;
+  if (maskrowsize) *maskrowsize = dv->maskrowsize;
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_dataview_get_row(msb_dataview *dv, size_t idx, void *row_out, void *mask_out) {
+  REQUIRE(dv && row_out, "NULL argument");
+  REQUIRE(idx < dv->n, "invalid position");  // dataview.cpp:131
+  CU_TRY(cudaSetDevice(dv->ctx->device));
+  CU_TRY(cudaMemcpyAsync(row_out, dv->d_data + idx * dv->rowsize, dv->rowsize, cudaMemcpyDeviceToHost, dv->ctx->stream));
+  if (mask_out) {
+    if (dv->d_mask) CU_TRY(cudaMemcpyAsync(mask_out, dv->d_mask + idx * dv->maskrowsize, dv->maskrowsize, cudaMemcpyDeviceToHost, dv->ctx->stream));
+    else memset(mask_out, 0, dv->maskrowsize);
+  }
+  CU_TRY(cudaStreamSynchronize(dv->ctx->stream));
+  return MSB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// model layouts
+// ---------------------------------------------------------------------------
+static size_t hp_size(const msb_model_desc &m) {
+  switch (m.family) {
+    case MSB_FAMILY_BB: case MSB_FAMILY_GP: return 2;
+    case MSB_FAMILY_NICH: return 4;
+    case MSB_FAMILY_DD: return m.dim;
+    case MSB_FAMILY_NIW: return (size_t)m.dim * m.dim + m.dim + 2;
+    default: return 0;
+  }
+}
+static size_t ss_size(const msb_model_desc &m) {
+  switch (m.family) {
+    case MSB_FAMILY_BB: return 2;
+    case MSB_FAMILY_GP: case MSB_FAMILY_NICH: return 3;
+    case MSB_FAMILY_DD: return (size_t)m.dim + 1;
+    case MSB_FAMILY_NIW: return (size_t)m.dim * m.dim + m.dim + 1;
+    default: return 0;
+  }
+}
+extern "C" MSB_API size_t msb_model_hp_size(const msb_model_desc *m) { return m ? hp_size(*m) : 0; }
+extern "C" MSB_API size_t msb_model_ss_size(const msb_model_desc *m) { return m ? ss_size(*m) : 0; }
+
+static int check_model(const msb_model_desc &m, size_t d) {
+  switch (m.family) {
+    case MSB_FAMILY_BB: case MSB_FAMILY_GP: case MSB_FAMILY_NICH: return MSB_OK;
+    case MSB_FAMILY_DD:
+      if (m.dim == 0) return fail(MSB_ERR_INVALID, "no elements");  // distributions.hpp:429
+      if (m.dim > 1024) return fail(MSB_ERR_UNSUPPORTED, "dd with more than 1024 categories is not built yet");
+      return MSB_OK;
+    case MSB_FAMILY_NIW:
+      if (m.dim == 0) return fail(MSB_ERR_INVALID, "no elements");  // distributions.hpp:478
+      if (m.dim > 96) return fail(MSB_ERR_UNSUPPORTED, "niw with dim > 96 is not built yet");
+      return MSB_OK;
+    default:
+      return fail(MSB_ERR_UNSUPPORTED, "model family " + std::to_string(m.family) + " of feature " + std::to_string(d) + " is not built");
+  }
+}
+
+// key -> (offset, count) inside the flat hp / ss vectors (distributions.hpp:21-56,165-199)
+static int hp_field(const msb_model_desc &m, const std::string &key, size_t *off, size_t *cnt) {
+  const size_t d = m.dim;
+  switch (m.family) {
+    case MSB_FAMILY_BB:
+      if (key == "alpha") { *off = 0; *cnt = 1; return MSB_OK; }
+      if (key == "beta") { *off = 1; *cnt = 1; return MSB_OK; }
+      break;
+    case MSB_FAMILY_GP:
+      if (key == "alpha") { *off = 0; *cnt = 1; return MSB_OK; }
+      if (key == "inv_beta") { *off = 1; *cnt = 1; return MSB_OK; }
+      break;
+    case MSB_FAMILY_NICH:
+      if (key == "mu") { *off = 0; *cnt = 1; return MSB_OK; }
+      if (key == "kappa") { *off = 1; *cnt = 1; return MSB_OK; }
+      if (key == "sigmasq") { *off = 2; *cnt = 1; return MSB_OK; }
+      if (key == "nu") { *off = 3; *cnt = 1; return MSB_OK; }
+      break;
+    case MSB_FAMILY_DD:
+      if (key == "alphas") { *off = 0; *cnt = d; return MSB_OK; }
+      break;
+    case MSB_FAMILY_NIW:
+      if (key == "mu") { *off = 0; *cnt = d; return MSB_OK; }
+      if (key == "kappa") { *off = d; *cnt = 1; return MSB_OK; }
+      if (key == "psi") { *off = d + 1; *cnt = d * d; return MSB_OK; }
+      if (key == "nu") { *off = d + 1 + d * d; *cnt = 1; return MSB_OK; }
+      break;
+    default: break;
+  }
+  return fail(MSB_ERR_KEY, "Unknown shared HP param key: " + key);
+}
+static int ss_field(const msb_model_desc &m, const std::string &key, size_t *off, size_t *cnt) {
+  const size_t d = m.dim;
+  switch (m.family) {
+    case MSB_FAMILY_BB:
+      if (key == "heads") { *off = 0; *cnt = 1; return MSB_OK; }
+      if (key == "tails") { *off = 1; *cnt = 1; return MSB_OK; }
+      break;
+    case MSB_FAMILY_GP:
+      if (key == "count") { *off = 0; *cnt = 1; return MSB_OK; }
+      if (key == "sum") { *off = 1; *cnt = 1; return MSB_OK; }
+      if (key == "log_prod") { *off = 2; *cnt = 1; return MSB_OK; }
+      break;
+    case MSB_FAMILY_NICH:
+      if (key == "count") { *off = 0; *cnt = 1; return MSB_OK; }
+      if (key == "mean") { *off = 1; *cnt = 1; return MSB_OK; }
+      if (key == "count_times_variance") { *off = 2; *cnt = 1; return MSB_OK; }
+      break;
+    case MSB_FAMILY_DD:
+      if (key == "count_sum") { *off = 0; *cnt = 1; return MSB_OK; }
+      if (key == "counts") { *off = 1; *cnt = d; return MSB_OK; }
+      break;
+    case MSB_FAMILY_NIW:
+      if (key == "count") { *off = 0; *cnt = 1; return MSB_OK; }
+      if (key == "sum_x") { *off = 1; *cnt = d; return MSB_OK; }
+      if (key == "sum_xxT") { *off = 1 + d; *cnt = d * d; return MSB_OK; }
+      break;
+    default: break;
+  }
+  return fail(MSB_ERR_KEY, "Unknown group SS param key: " + key);
+}
+
+// ---------------------------------------------------------------------------
+// state
+// ---------------------------------------------------------------------------
+extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *models, size_t nfeatures, size_t max_groups,
+                                msb_state **out) {
+  REQUIRE(ctx && models && out, "msb_state_create: NULL argument");
+  REQUIRE(nfeatures > 0 && max_groups > 0, "msb_state_create: empty state");
+  REQUIRE(max_groups < (1u << 30), "msb_state_create: too many groups");
+  for (size_t d = 0; d < nfeatures; d++) MSB_TRY(check_model(models[d], d));
+  CU_TRY(cudaSetDevice(ctx->device));
+  msb_state *st = new msb_state();
+  st->ctx = ctx; st->D = nfeatures; st->kmax = max_groups;
+  st->models.assign(models, models + nfeatures);
+  st->feats.resize(nfeatures);
+  size_t hpo = 0, sso = max_groups;  // group counts first
+  for (size_t d = 0; d < nfeatures; d++) {
+    FeatDev &f = st->feats[d];
+    memset(&f, 0, sizeof(f));
+    const msb_model_desc &m = models[d];
+    f.family = m.family; f.dim = m.dim;
+    f.hp_off = hpo; f.ss_off = sso; f.ss_w = (uint32_t)ss_size(m);
+    hpo += hp_size(m);
+    sso += max_groups * ss_size(m);
+    switch (m.family) {
+      case MSB_FAMILY_BB: f.kind = KIND_TABLE; f.coltype = COL_U8; f.ncat = 2; f.dim = 2; st->has_scalar = true; break;
+      case MSB_FAMILY_DD:
+        f.kind = KIND_TABLE; f.ncat = m.dim; st->has_scalar = true;
+        f.coltype = m.dim + 1 <= 256 ? COL_U8 : (m.dim + 1 <= 65536 ? COL_U16 : COL_U32);
+        break;
+      case MSB_FAMILY_GP: f.kind = KIND_GP; f.coltype = COL_U32; f.ncat = 1; st->has_scalar = true; break;
+      case MSB_FAMILY_NICH: f.kind = KIND_NICH; f.coltype = COL_F32; st->has_scalar = true; break;
+      case MSB_FAMILY_NIW: f.kind = KIND_NIW; f.coltype = COL_F32; st->has_niw = true; break;
+    }
+  }
+  st->SS = sso;
+  // default hyperparameters: microscopes/models.pyx:189,211,223,238,264-269
+  st->h_hp.assign(hpo, 0.0);
+  for (size_t d = 0; d < nfeatures; d++) {
+    double *h = st->h_hp.data() + st->feats[d].hp_off;
+    const msb_model_desc &m = models[d];
+    switch (m.family) {
+      case MSB_FAMILY_BB: case MSB_FAMILY_GP: h[0] = h[1] = 1.0; break;
+      case MSB_FAMILY_NICH: h[0] = 0.0; h[1] = h[2] = h[3] = 1.0; break;
+      case MSB_FAMILY_DD: for (uint32_t i = 0; i < m.dim; i++) h[i] = 1.0; st->feats[d].asum = (double)m.dim; break;
+      case MSB_FAMILY_NIW:
+        h[m.dim] = 1.0;
+        for (uint32_t i = 0; i < m.dim; i++) h[m.dim + 1 + (size_t)i * m.dim + i] = 1.0;
+        h[m.dim + 1 + (size_t)m.dim * m.dim] = (double)m.dim;
+        break;
+    }
+  }
+  CU_TRY(cudaMalloc(&st->d_feats, sizeof(FeatDev) * nfeatures));
+  CU_TRY(cudaMalloc(&st->d_hp, sizeof(double) * std::max<size_t>(hpo, 1)));
+  CU_TRY(cudaMalloc(&st->d_ss, sizeof(double) * st->SS));
+  CU_TRY(cudaMalloc(&st->d_delta, sizeof(double) * st->SS));
+  CU_TRY(cudaMemsetAsync(st->d_ss, 0, sizeof(double) * st->SS, ctx->stream));
+  CU_TRY(cudaMemsetAsync(st->d_delta, 0, sizeof(double) * st->SS, ctx->stream));
+  CU_TRY(cudaMalloc(&st->d_counter, sizeof(unsigned long long) * 4));
+  CU_TRY(cudaMalloc(&st->d_slot2gid, sizeof(int64_t) * max_groups));
+  st->slot2gid.assign(max_groups, -1);
+  st->h_counts.assign(max_groups, 0.0);
+  for (int s = (int)max_groups - 1; s >= 0; s--) st->free_slots.push_back(s);
+  st->cols.assign(nfeatures, nullptr);
+  st->d_niwW.assign(nfeatures, nullptr); st->d_niwBias.assign(nfeatures, nullptr);
+  st->d_niwCoef.assign(nfeatures, nullptr); st->d_niwB.assign(nfeatures, nullptr);
+  *out = st;
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_state_destroy(msb_state *st) {
+  if (!st) return MSB_OK;
+  cudaSetDevice(st->ctx->device);
+  cudaStreamSynchronize(st->ctx->stream);
+  for (void *c : st->cols) cudaFree(c);
+  for (size_t d = 0; d < st->D; d++) { cudaFree(st->d_niwW[d]); cudaFree(st->d_niwBias[d]); cudaFree(st->d_niwCoef[d]); cudaFree(st->d_niwB[d]); }
+  cudaFree(st->d_feats); cudaFree(st->d_hp); cudaFree(st->d_ss); cudaFree(st->d_delta); cudaFree(st->d_counter);
+  cudaFree(st->d_slot2gid); cudaFree(st->d_assign); cudaFree(st->d_params); cudaFree(st->d_scores);
+  cudaFree(st->d_base); cudaFree(st->d_col2slot); cudaFree(st->d_newslot); cudaFree(st->d_newcol); cudaFree(st->d_uniforms);
+  for (auto &pe : st->events) for (auto &e : pe.e) cudaEventDestroy(e);
+  delete st;
+  return MSB_OK;
+}
+
+static int sync_small(msb_state *st) {  // upload hypers / feature descriptors if they changed
+  if (st->hp_dirty) {
+    CU_TRY(cudaMemcpyAsync(st->d_hp, st->h_hp.data(), sizeof(double) * st->h_hp.size(), cudaMemcpyHostToDevice, st->ctx->stream));
+    st->hp_dirty = false;
+  }
+  if (st->feats_dirty) {
+    CU_TRY(cudaMemcpyAsync(st->d_feats, st->feats.data(), sizeof(FeatDev) * st->D, cudaMemcpyHostToDevice, st->ctx->stream));
+    st->feats_dirty = false;
+  }
+  // the host vectors are pageable: the copies above have completed on return
+  return MSB_OK;
+}
+
+static void layout_chunks(msb_state *st) {
+  uint32_t ro = 0, mx = 0;
+  for (auto &f : st->feats) {
+    switch (f.kind) {
+      case KIND_TABLE: f.rows = f.ncat + 1; break;
+      case KIND_GP: f.rows = f.ncat + 4; break;
+      case KIND_NICH: f.rows = 4; break;
+      default: f.rows = 0; break;
+    }
+    f.rowoff = ro;
+    ro += f.rows;
+    mx = std::max(mx, f.rows);
+  }
+  st->region_rows = ro;
+  st->max_chunk_rows = mx;
+  st->feats_dirty = true;
+}
+
+extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
+  REQUIRE(st && dv, "msb_state_bind: NULL argument");
+  REQUIRE(dv->ctx == st->ctx, "msb_state_bind: dataview belongs to another context");
+  REQUIRE(dv->D == st->D, "msb_state_bind: feature count mismatch");
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  for (size_t d = 0; d < st->D; d++) {
+    const msb_runtime_type &t = dv->types[d];
+    const msb_model_desc &m = st->models[d];
+    if (m.family == MSB_FAMILY_NIW) REQUIRE(t.n == m.dim, "shapes do not match");  // distributions.hpp:218
+    else REQUIRE(t.n == 1, "scalar model bound to a vector field");               // distributions.hpp:209
+  }
+  for (void *&c : st->cols) { cudaFree(c); c = nullptr; }
+  cudaFree(st->d_assign); st->d_assign = nullptr;
+  st->dv = dv; st->n = dv->n;
+  const size_t n = std::max<size_t>(dv->n, 1);
+  for (size_t d = 0; d < st->D; d++) {
+    FeatDev &f = st->feats[d];
+    size_t bytes;
+    if (f.kind == KIND_NIW) bytes = n * f.dim * sizeof(float);
+    else bytes = n * (f.coltype == COL_U8 ? 1 : f.coltype == COL_U16 ? 2 : 4);
+    CU_TRY(cudaMalloc(&st->cols[d], bytes + 16));
+    f.col = st->cols[d];
+    f.src_off = dv->off[d]; f.msk_off = dv->moff[d];
+    f.src_prim = (uint32_t)dv->types[d].prim; f.src_n = dv->types[d].n;
+  }
+  st->feats_dirty = true;
+  MSB_TRY(sync_small(st));
+  if (dv->n) {
+    dim3 grid(cdiv(dv->n, 256), (unsigned)st->D);
+    LAUNCH(ctx, pack_kernel, grid, 256, 0, dv->d_data, dv->d_mask, dv->n, dv->rowsize, dv->maskrowsize, st->d_feats, (int)st->D);
+  }
+  // size the gp lookup tables from the column maxima
+  std::vector<size_t> gp;
+  for (size_t d = 0; d < st->D; d++) if (st->feats[d].kind == KIND_GP) gp.push_back(d);
+  if (!gp.empty()) {
+    uint32_t *d_max = nullptr;
+    CU_TRY(cudaMalloc(&d_max, sizeof(uint32_t) * gp.size()));
+    CU_TRY(cudaMemsetAsync(d_max, 0, sizeof(uint32_t) * gp.size(), ctx->stream));
+    if (dv->n)
+      for (size_t i = 0; i < gp.size(); i++)
+        LAUNCH(ctx, colmax_u32_kernel, std::min<unsigned>(cdiv(dv->n, 256), 1024), 256, 0,
+               (const uint32_t *)st->cols[gp[i]], dv->n, d_max + i);
+    std::vector<uint32_t> h_max(gp.size());
+    CU_TRY(cudaMemcpyAsync(h_max.data(), d_max, sizeof(uint32_t) * gp.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_max);
+    const uint32_t cap_limit = 252;  // chunk rows = cap + 4 <= 256
+    for (size_t i = 0; i < gp.size(); i++) st->feats[gp[i]].ncat = std::min<uint32_t>(h_max[i] + 1, cap_limit);
+  }
+  layout_chunks(st);
+  CU_TRY(cudaMalloc(&st->d_assign, sizeof(int32_t) * n));
+  CU_TRY(cudaMemsetAsync(st->d_assign, 0xFF, sizeof(int32_t) * n, ctx->stream));  // all -1
+  return MSB_OK;
+}
+
+// ---- hypers / suffstats ------------------------------------------------------
+extern "C" MSB_API int msb_state_set_hp(msb_state *st, size_t feature, const char *key, const double *v, size_t count) {
+  REQUIRE(st && key && v, "NULL argument");
+  REQUIRE(feature < st->D, "bad feature index");
+  size_t off, cnt;
+  MSB_TRY(hp_field(st->models[feature], key, &off, &cnt));
+  REQUIRE(count == cnt, "wrong dimension");  // distributions.hpp:436
+  double *h = st->h_hp.data() + st->feats[feature].hp_off;
+  for (size_t i = 0; i < cnt; i++) h[off + i] = v[i];
+  if (st->models[feature].family == MSB_FAMILY_DD) {
+    double a = 0.0;
+    for (uint32_t i = 0; i < st->models[feature].dim; i++) a += h[i];
+    st->feats[feature].asum = a;
+    st->feats_dirty = true;
+  }
+  st->hp_dirty = true;
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_state_get_hp(msb_state *st, size_t feature, const char *key, double *v, size_t count) {
+  REQUIRE(st && key && v, "NULL argument");
+  REQUIRE(feature < st->D, "bad feature index");
+  size_t off, cnt;
+  MSB_TRY(hp_field(st->models[feature], key, &off, &cnt));
+  REQUIRE(count == cnt, "wrong dimension");
+  const double *h = st->h_hp.data() + st->feats[feature].hp_off;
+  for (size_t i = 0; i < cnt; i++) v[i] = h[off + i];
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_state_set_cluster_hp(msb_state *st, const char *key, double v) {
+  REQUIRE(st && key, "NULL argument");
+  if (std::string(key) != "alpha") return fail(MSB_ERR_KEY, std::string("unknown key: ") + key);  // group_manager.hpp:130
+  REQUIRE(v > 0.0, "alpha must be positive");  // group_manager.hpp:120
+  st->alpha = v;
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_state_get_cluster_hp(msb_state *st, const char *key, double *v) {
+  REQUIRE(st && key && v, "NULL argument");
+  if (std::string(key) != "alpha") return fail(MSB_ERR_KEY, std::string("unknown key: ") + key);
+  *v = st->alpha;
+  return MSB_OK;
+}
+
+static int slot_of(msb_state *st, size_t gid, int *slot) {
+  auto it = st->gid2slot.find(gid);
+  if (it == st->gid2slot.end()) return fail(MSB_ERR_INVALID, "invalid gid");  // group_manager.hpp:157
+  *slot = it->second;
+  return MSB_OK;
+}
+
+// device (additive) <-> reference field representation for one group of one feature
+static void ss_to_ref(const msb_model_desc &m, std::vector<double> &s) {
+  if (m.family == MSB_FAMILY_NICH) {
+    const double n = s[0], mean = n > 0 ? s[1] / n : 0.0;
+    double ctv = n > 0 ? s[2] - s[1] * mean : 0.0;
+    if (ctv < 0) ctv = 0;
+    s[1] = mean; s[2] = ctv;
+  }
+}
+static void ss_from_ref(const msb_model_desc &m, std::vector<double> &s) {
+  if (m.family == MSB_FAMILY_NICH) {
+    const double n = s[0], mean = s[1], ctv = s[2];
+    s[1] = n * mean; s[2] = ctv + n * mean * mean;
+  }
+}
+
+extern "C" MSB_API int msb_state_get_ss(msb_state *st, size_t feature, size_t gid, const char *key, double *v, size_t count) {
+  REQUIRE(st && key && v, "NULL argument");
+  REQUIRE(feature < st->D, "bad feature index");
+  size_t off, cnt; int slot;
+  MSB_TRY(ss_field(st->models[feature], key, &off, &cnt));
+  REQUIRE(count == cnt, "wrong dimension");
+  MSB_TRY(slot_of(st, gid, &slot));
+  const FeatDev &f = st->feats[feature];
+  std::vector<double> s(f.ss_w);
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  CU_TRY(cudaMemcpyAsync(s.data(), st->d_ss + f.ss_off + (size_t)slot * f.ss_w, sizeof(double) * f.ss_w, cudaMemcpyDeviceToHost, st->ctx->stream));
+  CU_TRY(cudaStreamSynchronize(st->ctx->stream));
+  ss_to_ref(st->models[feature], s);
+  for (size_t i = 0; i < cnt; i++) v[i] = s[off + i];
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_state_set_ss(msb_state *st, size_t feature, size_t gid, const char *key, const double *v, size_t count) {
+  REQUIRE(st && key && v, "NULL argument");
+  REQUIRE(feature < st->D, "bad feature index");
+  size_t off, cnt; int slot;
+  MSB_TRY(ss_field(st->models[feature], key, &off, &cnt));
+  REQUIRE(count == cnt, "wrong dimension");
+  MSB_TRY(slot_of(st, gid, &slot));
+  const FeatDev &f = st->feats[feature];
+  std::vector<double> s(f.ss_w);
+  double *dst = st->d_ss + f.ss_off + (size_t)slot * f.ss_w;
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  CU_TRY(cudaMemcpyAsync(s.data(), dst, sizeof(double) * f.ss_w, cudaMemcpyDeviceToHost, st->ctx->stream));
+  CU_TRY(cudaStreamSynchronize(st->ctx->stream));
+  ss_to_ref(st->models[feature], s);
+  for (size_t i = 0; i < cnt; i++) s[off + i] = v[i];
+  ss_from_ref(st->models[feature], s);
+  CU_TRY(cudaMemcpyAsync(dst, s.data(), sizeof(double) * f.ss_w, cudaMemcpyHostToDevice, st->ctx->stream));
+  CU_TRY(cudaStreamSynchronize(st->ctx->stream));
+  return MSB_OK;
+}
+
+// ---- groups (group_manager.hpp:133-216) -------------------------------------
+extern "C" MSB_API int msb_state_nentities(msb_state *st, size_t *n) { REQUIRE(st && n, "NULL argument"); *n = st->n; return MSB_OK; }
+extern "C" MSB_API int msb_state_ngroups(msb_state *st, size_t *n) { REQUIRE(st && n, "NULL argument"); *n = st->gid2slot.size(); return MSB_OK; }
+extern "C" MSB_API int msb_state_groups(msb_state *st, size_t *gids, size_t cap, size_t *n) {
+  REQUIRE(st && n, "NULL argument");
+  *n = st->gid2slot.size();
+  if (gids) {
+    REQUIRE(cap >= *n, "buffer too small");
+    size_t i = 0;
+    for (auto &p : st->gid2slot) gids[i++] = p.first;
+  }
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_state_empty_groups(msb_state *st, size_t *gids, size_t cap, size_t *n) {
+  REQUIRE(st && n, "NULL argument");
+  size_t c = 0;
+  for (auto &p : st->gid2slot)
+    if (st->h_counts[p.second] == 0.0) {
+      if (gids) { REQUIRE(c < cap, "buffer too small"); gids[c] = p.first; }
+      c++;
+    }
+  *n = c;
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_state_groupsize(msb_state *st, size_t gid, size_t *count) {
+  REQUIRE(st && count, "NULL argument");
+  int slot;
+  MSB_TRY(slot_of(st, gid, &slot));
+  *count = (size_t)st->h_counts[slot];
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_state_create_group(msb_state *st, size_t *gid) {
+  REQUIRE(st && gid, "NULL argument");
+  if (st->free_slots.empty()) return fail(MSB_ERR_NOMEM, "max_groups reached");
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  const int slot = st->free_slots.back();
+  st->free_slots.pop_back();
+  const size_t g = st->gcount++;  // group_manager.hpp:199
+  st->gid2slot[g] = slot;
+  st->slot2gid[slot] = (int64_t)g;
+  st->h_counts[slot] = 0.0;
+  // Group::init: zero suffstats (distributions.hpp:351)
+  CU_TRY(cudaMemsetAsync(st->d_ss + slot, 0, sizeof(double), st->ctx->stream));
+  for (auto &f : st->feats)
+    CU_TRY(cudaMemsetAsync(st->d_ss + f.ss_off + (size_t)slot * f.ss_w, 0, sizeof(double) * f.ss_w, st->ctx->stream));
+  *gid = g;
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_state_delete_group(msb_state *st, size_t gid) {
+  REQUIRE(st, "NULL argument");
+  int slot;
+  MSB_TRY(slot_of(st, gid, &slot));
+  if (st->h_counts[slot] != 0.0) return fail(MSB_ERR_STATE, "group not empty");  // group_manager.hpp:211
+  st->gid2slot.erase(gid);
+  st->slot2gid[slot] = -1;
+  st->free_slots.push_back(slot);
+  return MSB_OK;
+}
+
+// ---- workspace helpers ---------------------------------------------------------
+template <typename T> static int ensure(T **p, size_t *cap, size_t need) {
+  if (*cap >= need && *p) return MSB_OK;
+  if (*p) { CU_TRY(cudaFree(*p)); *p = nullptr; }
+  const size_t ncap = need + need / 8 + 64;
+  cudaError_t e = cudaMalloc(p, sizeof(T) * ncap);
+  if (e != cudaSuccess) { *cap = 0; return fail(MSB_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+  *cap = ncap;
+  return MSB_OK;
+}
+
+static int ensure_rows(msb_state *st, size_t nrows) {
+  if (st->row_cap >= nrows && st->d_newslot) return MSB_OK;
+  cudaFree(st->d_newslot); cudaFree(st->d_newcol); cudaFree(st->d_uniforms);
+  st->d_newslot = st->d_newcol = nullptr; st->d_uniforms = nullptr;
+  const size_t cap = nrows + 64;
+  CU_TRY(cudaMalloc(&st->d_newslot, sizeof(int32_t) * cap));
+  CU_TRY(cudaMalloc(&st->d_newcol, sizeof(int32_t) * cap));
+  CU_TRY(cudaMalloc(&st->d_uniforms, sizeof(float) * cap));
+  st->row_cap = cap;
+  return MSB_OK;
+}
+
+static int choose_v(const msb_state *st, size_t ncols) {
+  if (const char *e = getenv("MSB_SCORE_V")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) return v;
+  }
+  const size_t budget = 96 * 1024;  // per-chunk shared memory we are willing to spend
+  auto fits = [&](int v) { return st->max_chunk_rows * 32 * v * sizeof(float) <= budget; };
+  if (ncols <= 32) return 1;
+  if (ncols >= 256 && fits(4)) return 4;
+  if (fits(2)) return 2;
+  return 1;
+}
+
+// Column order = ascending gid (std::map iteration order of group_manager.hpp:171-178);
+// base[c] = log(pseudocount) (group_manager.hpp:274-283).
+static int prepare_columns(msb_state *st) {
+  msb_ctx *ctx = st->ctx;
+  const size_t K = st->gid2slot.size();
+  REQUIRE(K > 0, "no groups");
+  st->V = choose_v(st, K);
+  const size_t KT = 32 * (size_t)st->V;
+  st->ld = (K + KT - 1) / KT * KT;
+  st->h_col2slot.resize(K); st->h_colgid.resize(K);
+  size_t nempty = 0;
+  for (auto &p : st->gid2slot) if (st->h_counts[p.second] == 0.0) nempty++;
+  std::vector<float> base(st->ld, -INFINITY);
+  size_t c = 0;
+  for (auto &p : st->gid2slot) {
+    st->h_col2slot[c] = p.second; st->h_colgid[c] = p.first;
+    const double cnt = st->h_counts[p.second];
+    const float pseudo = cnt != 0.0 ? (float)cnt : (float)st->alpha / (float)nempty;
+    base[c] = (float)std::log((double)pseudo);
+    c++;
+  }
+  MSB_TRY(ensure(&st->d_base, &st->base_cap, st->ld));
+  MSB_TRY(ensure(&st->d_col2slot, &st->col_cap, K));
+  CU_TRY(cudaMemcpyAsync(st->d_base, base.data(), sizeof(float) * st->ld, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(st->d_col2slot, st->h_col2slot.data(), sizeof(int32_t) * K, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(st->d_slot2gid, st->slot2gid.data(), sizeof(int64_t) * st->kmax, cudaMemcpyHostToDevice, ctx->stream));
+  return MSB_OK;
+}
+
+static int build_params(msb_state *st) {
+  msb_ctx *ctx = st->ctx;
+  const size_t K = st->h_col2slot.size();
+  MSB_TRY(sync_small(st));
+  const size_t KT = 32 * (size_t)st->V;
+  const size_t ktiles = st->ld / KT;
+  if (st->has_scalar) {
+    MSB_TRY(ensure(&st->d_params, &st->params_cap, ktiles * st->region_rows * KT));
+    dim3 grid((unsigned)st->D, (unsigned)ktiles);
+    LAUNCH(ctx, build_params_kernel, grid, 256, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot, (int)K,
+           (int)KT, st->region_rows, st->d_params);
+  }
+  if (st->has_niw) {
+    for (size_t d = 0; d < st->D; d++) {
+      const FeatDev &f = st->feats[d];
+      if (f.kind != KIND_NIW) continue;
+      if (st->niw_cols_cap < K || !st->d_niwW[d]) {
+        cudaFree(st->d_niwW[d]); cudaFree(st->d_niwBias[d]); cudaFree(st->d_niwCoef[d]); cudaFree(st->d_niwB[d]);
+        const size_t cap = st->ld + 64;
+        CU_TRY(cudaMalloc(&st->d_niwW[d], sizeof(float) * cap * f.dim * f.dim));
+        CU_TRY(cudaMalloc(&st->d_niwBias[d], sizeof(float) * cap * f.dim));
+        CU_TRY(cudaMalloc(&st->d_niwCoef[d], sizeof(float) * cap * 4));
+        CU_TRY(cudaMalloc(&st->d_niwB[d], niw_tc_operand_bytes(cap, f.dim)));
+      }
+      const size_t smem = (2 * (size_t)f.dim * f.dim + f.dim) * sizeof(double);
+      LAUNCH(ctx, niw_prepare_kernel, (unsigned)K, 128, smem, f, st->d_hp, st->d_ss, st->d_col2slot, st->d_niwW[d],
+             st->d_niwBias[d], st->d_niwCoef[d]);
+    }
+    st->niw_cols_cap = std::max(st->niw_cols_cap, K);
+  }
+  return MSB_OK;
+}
+
+static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scores) {
+  msb_ctx *ctx = st->ctx;
+  const size_t nrows = row_hi - row_lo;
+  const size_t K = st->h_col2slot.size();
+  const size_t KT = 32 * (size_t)st->V;
+  const size_t ktiles = st->ld / KT;
+  if (st->has_scalar) {
+    const size_t smem = std::max<size_t>(st->max_chunk_rows * KT * sizeof(float), 16);
+    if (smem > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "parameter chunk does not fit in shared memory");
+    if (st->V == 1) {
+      dim3 grid(cdiv(nrows, SCORE_WARPS * 32), (unsigned)ktiles);
+      LAUNCH(ctx, (score_kernel<1, 32>), grid, SCORE_WARPS * 32, smem, st->d_feats, (int)st->D, st->d_params, st->region_rows, st->d_base, scores, st->ld, row_lo, row_hi);
+    } else if (st->V == 2) {
+      dim3 grid(cdiv(nrows, SCORE_WARPS * 32), (unsigned)ktiles);
+      LAUNCH(ctx, (score_kernel<2, 32>), grid, SCORE_WARPS * 32, smem, st->d_feats, (int)st->D, st->d_params, st->region_rows, st->d_base, scores, st->ld, row_lo, row_hi);
+    } else {
+      dim3 grid(cdiv(nrows, SCORE_WARPS * 16), (unsigned)ktiles);
+      LAUNCH(ctx, (score_kernel<4, 16>), grid, SCORE_WARPS * 32, smem, st->d_feats, (int)st->D, st->d_params, st->region_rows, st->d_base, scores, st->ld, row_lo, row_hi);
+    }
+  } else {
+    // no scalar feature: scores start from the CRP term
+    for (size_t r0 = 0; r0 < nrows; r0 += 65535) {
+      const size_t nr = std::min<size_t>(65535, nrows - r0);
+      CU_TRY(cudaMemcpy2DAsync(scores + r0 * st->ld, sizeof(float) * st->ld, st->d_base, 0, sizeof(float) * st->ld, nr, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  for (size_t d = 0; d < st->D; d++) {
+    const FeatDev &f = st->feats[d];
+    if (f.kind != KIND_NIW) continue;
+    bool done = false;
+    MSB_TRY(niw_tc_score(ctx->stream, &ctx->launches, (const float *)f.col, f.dim, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
+                         st->d_niwB[d], K, scores, st->ld, row_lo, row_hi, ctx->sm_count, &done, g_last_error));
+    if (!done) {
+      const size_t smem = ((size_t)f.dim * f.dim + f.dim) * sizeof(float);
+      dim3 grid(cdiv(nrows, 128), (unsigned)K);
+      LAUNCH(ctx, niw_score_simt_kernel, grid, 128, smem, (const float *)f.col, (int)f.dim, st->d_niwW[d], st->d_niwBias[d],
+             st->d_niwCoef[d], scores, st->ld, row_lo, row_hi);
+    }
+  }
+  return MSB_OK;
+}
+
+static int refresh_counts(msb_state *st) {
+  CU_TRY(cudaMemcpyAsync(st->h_counts.data(), st->d_ss, sizeof(double) * st->kmax, cudaMemcpyDeviceToHost, st->ctx->stream));
+  CU_TRY(cudaStreamSynchronize(st->ctx->stream));
+  return MSB_OK;
+}
+
+static int launch_update(msb_state *st, size_t row_lo, size_t row_hi) {  // old = d_assign, new = d_newslot
+  msb_ctx *ctx = st->ctx;
+  const size_t nrows = row_hi - row_lo;
+  if (st->has_scalar) {
+    dim3 grid(cdiv(nrows, 256), (unsigned)st->D);
+    LAUNCH(ctx, update_kernel, grid, 256, 0, st->d_feats, (int)st->D, st->d_assign, st->d_newslot, row_lo, row_hi, st->d_delta);
+  }
+  for (size_t d = 0; d < st->D; d++) {
+    const FeatDev &f = st->feats[d];
+    if (f.kind != KIND_NIW) continue;
+    LAUNCH(ctx, update_niw_kernel, cdiv(nrows, 8), 256, 0, f, st->d_assign, st->d_newslot, row_lo, row_hi, st->d_delta);
+  }
+  LAUNCH(ctx, commit_assign_kernel, cdiv(nrows, 256), 256, 0, st->d_assign, st->d_newslot, row_lo, row_hi, st->d_delta, st->d_counter);
+  return MSB_OK;
+}
+
+static int apply_deltas(msb_state *st) {
+  LAUNCH(st->ctx, apply_delta_kernel, cdiv(st->SS, 256), 256, 0, st->d_ss, st->d_delta, st->SS);
+  return refresh_counts(st);
+}
+
+extern "C" MSB_API int msb_state_delta_buffer(msb_state *st, double **dev_ptr, size_t *count) {
+  REQUIRE(st && dev_ptr && count, "NULL argument");
+  *dev_ptr = st->d_delta; *count = st->SS;
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_state_apply_deltas(msb_state *st) {
+  REQUIRE(st, "NULL argument");
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  return apply_deltas(st);
+}
+
+// ---- assignments -------------------------------------------------------------
+extern "C" MSB_API int msb_state_assignments(msb_state *st, int64_t *out, size_t n) {
+  REQUIRE(st && out, "NULL argument");
+  REQUIRE(st->dv, "no dataview bound");
+  REQUIRE(n == st->n, "wrong length");
+  if (!n) return MSB_OK;
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  int64_t *d_out = nullptr;
+  CU_TRY(cudaMalloc(&d_out, sizeof(int64_t) * n));
+  CU_TRY(cudaMemcpyAsync(st->d_slot2gid, st->slot2gid.data(), sizeof(int64_t) * st->kmax, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, map_i32_to_i64_kernel, cdiv(n, 256), 256, 0, st->d_assign, st->d_slot2gid, n, d_out);
+  CU_TRY(cudaMemcpyAsync(out, d_out, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_out);
+  return MSB_OK;
+}
+
+static int read_assign(msb_state *st, size_t eid, int32_t *slot) {
+  CU_TRY(cudaMemcpyAsync(slot, st->d_assign + eid, sizeof(int32_t), cudaMemcpyDeviceToHost, st->ctx->stream));
+  CU_TRY(cudaStreamSynchronize(st->ctx->stream));
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_state_add_values(msb_state *st, const int64_t *gids, size_t n) {
+  REQUIRE(st && gids, "NULL argument");
+  REQUIRE(st->dv, "no dataview bound");
+  REQUIRE(n == st->n, "wrong length");
+  if (!n) return MSB_OK;
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  std::vector<int32_t> cur(n), req(n);
+  CU_TRY(cudaMemcpyAsync(cur.data(), st->d_assign, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < n; i++) {
+    if (gids[i] < 0) { req[i] = cur[i]; continue; }
+    if (cur[i] >= 0) return fail(MSB_ERR_STATE, "entity already assigned");  // group_manager.hpp:221
+    auto it = st->gid2slot.find((size_t)gids[i]);
+    if (it == st->gid2slot.end()) return fail(MSB_ERR_INVALID, "invalid gid");
+    req[i] = it->second;
+  }
+  MSB_TRY(ensure_rows(st, n));
+  MSB_TRY(sync_small(st));
+  CU_TRY(cudaMemcpyAsync(st->d_newslot, req.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned long long), ctx->stream));
+  MSB_TRY(launch_update(st, 0, n));
+  return apply_deltas(st);
+}
+
+extern "C" MSB_API int msb_state_add_value(msb_state *st, size_t gid, size_t eid) {
+  REQUIRE(st, "NULL argument");
+  REQUIRE(st->dv, "no dataview bound");
+  REQUIRE(eid < st->n, "invalid eid");
+  int slot; int32_t cur;
+  MSB_TRY(slot_of(st, gid, &slot));
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  MSB_TRY(read_assign(st, eid, &cur));
+  if (cur != -1) return fail(MSB_ERR_STATE, "entity already assigned");
+  MSB_TRY(ensure_rows(st, 1));
+  MSB_TRY(sync_small(st));
+  const int32_t s32 = slot;
+  CU_TRY(cudaMemcpyAsync(st->d_newslot, &s32, sizeof(int32_t), cudaMemcpyHostToDevice, st->ctx->stream));
+  MSB_TRY(launch_update(st, eid, eid + 1));
+  return apply_deltas(st);
+}
+
+extern "C" MSB_API int msb_state_remove_value(msb_state *st, size_t eid, size_t *gid) {
+  REQUIRE(st, "NULL argument");
+  REQUIRE(st->dv, "no dataview bound");
+  REQUIRE(eid < st->n, "invalid eid");
+  int32_t cur;
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  MSB_TRY(read_assign(st, eid, &cur));
+  if (cur == -1) return fail(MSB_ERR_STATE, "entity not assigned");  // group_manager.hpp:238
+  if (gid) *gid = (size_t)st->slot2gid[cur];
+  MSB_TRY(ensure_rows(st, 1));
+  MSB_TRY(sync_small(st));
+  const int32_t s32 = -1;
+  CU_TRY(cudaMemcpyAsync(st->d_newslot, &s32, sizeof(int32_t), cudaMemcpyHostToDevice, st->ctx->stream));
+  MSB_TRY(launch_update(st, eid, eid + 1));
+  return apply_deltas(st);
+}
+
+// ---- scoring -------------------------------------------------------------------
+static int ensure_scores(msb_state *st, size_t nrows) { return ensure(&st->d_scores, &st->scores_cap, nrows * st->ld + 64); }
+
+extern "C" MSB_API int msb_state_score_value(msb_state *st, size_t eid, size_t *gids, float *scores, size_t cap, size_t *n) {
+  REQUIRE(st && n, "NULL argument");
+  REQUIRE(st->dv, "no dataview bound");
+  REQUIRE(eid < st->n, "invalid eid");
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  MSB_TRY(prepare_columns(st));
+  const size_t K = st->h_col2slot.size();
+  *n = K;
+  if (!scores && !gids) return MSB_OK;
+  REQUIRE(cap >= K, "buffer too small");
+  MSB_TRY(ensure_scores(st, 1));
+  if (!st->has_niw) {
+    MSB_TRY(sync_small(st));
+    LAUNCH(ctx, score_direct_kernel, 1, 128, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot, (int)K,
+           st->d_base, st->d_scores, st->ld, eid, eid + 1);
+  } else {
+    MSB_TRY(build_params(st));
+    MSB_TRY(launch_score(st, eid, eid + 1, st->d_scores));
+  }
+  st->last_rows = 1; st->last_cols = K;
+  if (scores) CU_TRY(cudaMemcpyAsync(scores, st->d_scores, sizeof(float) * K, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  if (gids) for (size_t c = 0; c < K; c++) gids[c] = st->h_colgid[c];
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_state_score_rows(msb_state *st, size_t row_lo, size_t row_hi, float *scores, size_t ld,
+                                    int on_device, size_t *gids, size_t cap, size_t *ncols) {
+  REQUIRE(st && ncols, "NULL argument");
+  REQUIRE(st->dv, "no dataview bound");
+  REQUIRE(row_lo <= row_hi && row_hi <= st->n, "bad row range");
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  MSB_TRY(prepare_columns(st));
+  const size_t K = st->h_col2slot.size();
+  *ncols = K;
+  if (gids) { REQUIRE(cap >= K, "buffer too small"); for (size_t c = 0; c < K; c++) gids[c] = st->h_colgid[c]; }
+  const size_t nrows = row_hi - row_lo;
+  if (!nrows) return MSB_OK;
+  const bool direct = getenv("MSB_FORCE_DIRECT") && !st->has_niw;
+  // a device destination with the internal leading dimension is written in place
+  float *dst = (on_device && scores && ld == st->ld) ? scores : nullptr;
+  if (!dst) { MSB_TRY(ensure_scores(st, nrows)); dst = st->d_scores; }
+  if (direct) {
+    MSB_TRY(sync_small(st));
+    LAUNCH(ctx, score_direct_kernel, (unsigned)nrows, 128, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot,
+           (int)K, st->d_base, dst, st->ld, row_lo, row_hi);
+  } else {
+    MSB_TRY(build_params(st));
+    MSB_TRY(launch_score(st, row_lo, row_hi, dst));
+  }
+  st->last_rows = nrows; st->last_cols = K;
+  if (scores && dst != scores) {
+    REQUIRE(ld >= K, "ld smaller than the number of groups");
+    CU_TRY(cudaMemcpy2DAsync(scores, sizeof(float) * ld, dst, sizeof(float) * st->ld, sizeof(float) * K, nrows,
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (!on_device) CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_state_last_scores(msb_state *st, float **dev_ptr, size_t *ld, size_t *nrows, size_t *ncols) {
+  REQUIRE(st, "NULL argument");
+  if (dev_ptr) *dev_ptr = st->d_scores;
+  if (ld) *ld = st->ld;
+  if (nrows) *nrows = st->last_rows;
+  if (ncols) *ncols = st->last_cols;
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_state_last_timings(msb_state *st, float *ms, size_t count) {
+  REQUIRE(st && ms, "NULL argument");
+  for (size_t i = 0; i < count && i < 5; i++) ms[i] = st->last_ms[i];
+  return MSB_OK;
+}
+
+// ---- sampler ---------------------------------------------------------------------
+extern "C" MSB_API int msb_sample_discrete_log(msb_ctx *ctx, const float *scores, size_t nrows, size_t k, size_t ld,
+                                       const float *uniforms, int32_t *out) {
+  REQUIRE(ctx && scores && uniforms && out, "NULL argument");
+  REQUIRE(k > 0 && ld >= k && k < (1u << 30), "bad shape");
+  if (!nrows) return MSB_OK;
+  CU_TRY(cudaSetDevice(ctx->device));
+  float *d_s = nullptr, *d_u = nullptr; int32_t *d_o = nullptr;
+  CU_TRY(cudaMalloc(&d_s, sizeof(float) * nrows * ld));
+  CU_TRY(cudaMalloc(&d_u, sizeof(float) * nrows));
+  CU_TRY(cudaMalloc(&d_o, sizeof(int32_t) * nrows));
+  CU_TRY(cudaMemcpyAsync(d_s, scores, sizeof(float) * nrows * ld, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(d_u, uniforms, sizeof(float) * nrows, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, sample_kernel, cdiv(nrows, 128), 128, 0, d_s, ld, (int)k, nrows, d_u, 0ull, 0ull, 0ull, (const int32_t *)nullptr, d_o, (int32_t *)nullptr);
+  CU_TRY(cudaMemcpyAsync(out, d_o, sizeof(int32_t) * nrows, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_s); cudaFree(d_u); cudaFree(d_o);
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_philox_uniforms(msb_ctx *ctx, uint64_t seed, uint64_t sweep, uint64_t row_lo, size_t n, float *out) {
+  REQUIRE(ctx && out, "NULL argument");
+  if (!n) return MSB_OK;
+  CU_TRY(cudaSetDevice(ctx->device));
+  float *d_u = nullptr;
+  CU_TRY(cudaMalloc(&d_u, sizeof(float) * n));
+  LAUNCH(ctx, philox_fill_kernel, cdiv(n, 256), 256, 0, seed, sweep, row_lo, n, d_u);
+  CU_TRY(cudaMemcpyAsync(out, d_u, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_u);
+  return MSB_OK;
+}
+
+// ---- sweep -------------------------------------------------------------------------
+extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_hi, const msb_sweep_opts *opts,
+                               msb_sweep_result *res) {
+  REQUIRE(st && opts, "NULL argument");
+  REQUIRE(st->dv, "no dataview bound");
+  REQUIRE(row_lo <= row_hi && row_hi <= st->n, "bad row range");
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  MSB_TRY(prepare_columns(st));
+  const size_t K = st->h_col2slot.size();
+  const size_t nrows = row_hi - row_lo;
+  if (res) { res->rows = nrows; res->moved = 0; res->units = (uint64_t)nrows * K * st->D; }
+  if (!nrows) return MSB_OK;
+  size_t budget_mb = 4096;
+  if (const char *e = getenv("MSB_SCORES_MB")) budget_mb = std::max(1, atoi(e));
+  const size_t chunk = std::max<size_t>(1, std::min(nrows, budget_mb * 1024 * 1024 / (st->ld * sizeof(float))));
+  const size_t nchunks = (nrows + chunk - 1) / chunk;
+  MSB_TRY(ensure_scores(st, chunk));
+  MSB_TRY(ensure_rows(st, chunk));
+  while (st->events.size() < nchunks + 1) {
+    PhaseEvents pe;
+    for (auto &e : pe.e) CU_TRY(cudaEventCreate(&e));
+    st->events.push_back(pe);
+  }
+  CU_TRY(cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned long long), ctx->stream));
+  CU_TRY(cudaEventRecord(st->events[0].e[0], ctx->stream));
+  MSB_TRY(build_params(st));
+  CU_TRY(cudaEventRecord(st->events[0].e[1], ctx->stream));
+  for (size_t c = 0; c < nchunks; c++) {
+    const size_t lo = row_lo + c * chunk, hi = std::min(row_hi, lo + chunk);
+    PhaseEvents &pe = st->events[c + 1];
+    CU_TRY(cudaEventRecord(pe.e[0], ctx->stream));
+    MSB_TRY(launch_score(st, lo, hi, st->d_scores));
+    CU_TRY(cudaEventRecord(pe.e[1], ctx->stream));
+    const float *d_u = nullptr;
+    if (opts->uniforms) {
+      CU_TRY(cudaMemcpyAsync(st->d_uniforms, opts->uniforms + (lo - row_lo), sizeof(float) * (hi - lo), cudaMemcpyHostToDevice, ctx->stream));
+      d_u = st->d_uniforms;
+    }
+    LAUNCH(ctx, sample_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores, st->ld, (int)K, hi - lo, d_u, opts->seed, opts->sweep,
+           opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
+    CU_TRY(cudaEventRecord(pe.e[2], ctx->stream));
+    MSB_TRY(launch_update(st, lo, hi));
+    CU_TRY(cudaEventRecord(pe.e[3], ctx->stream));
+  }
+  st->last_rows = std::min(chunk, nrows); st->last_cols = K;
+  CU_TRY(cudaEventRecord(st->events[0].e[2], ctx->stream));
+  if (!opts->defer_apply) LAUNCH(ctx, apply_delta_kernel, cdiv(st->SS, 256), 256, 0, st->d_ss, st->d_delta, st->SS);
+  CU_TRY(cudaEventRecord(st->events[0].e[3], ctx->stream));
+  unsigned long long moved = 0;
+  CU_TRY(cudaMemcpyAsync(&moved, st->d_counter, sizeof(moved), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!opts->defer_apply) MSB_TRY(refresh_counts(st));
+  else CU_TRY(cudaStreamSynchronize(ctx->stream));
+  if (res) res->moved = moved;
+  float ms = 0.f;
+  for (float &m : st->last_ms) m = 0.f;
+  cudaEventElapsedTime(&ms, st->events[0].e[0], st->events[0].e[1]); st->last_ms[0] = ms;
+  for (size_t c = 0; c < nchunks; c++) {
+    PhaseEvents &pe = st->events[c + 1];
+    for (int p = 0; p < 3; p++) { cudaEventElapsedTime(&ms, pe.e[p], pe.e[p + 1]); st->last_ms[1 + p] += ms; }
+  }
+  cudaEventElapsedTime(&ms, st->events[0].e[2], st->events[0].e[3]); st->last_ms[4] = ms;
+  return MSB_OK;
+}
+
+// ---- single-value plugin calls (models/base.hpp:25-27) -------------------------------
+static int value_to_doubles(const void *value, const msb_runtime_type *vt, std::vector<double> &x) {
+  REQUIRE(value && vt, "NULL argument");
+  REQUIRE(vt->prim >= 0 && vt->prim < MSB_TYPE_NELEMS && vt->n > 0, "bad runtime type");
+  x.resize(vt->n);
+  const uint8_t *p = (const uint8_t *)value;
+  for (uint32_t i = 0; i < vt->n; i++, p += k_prim_size[vt->prim]) {
+    switch (vt->prim) {
+      case MSB_TYPE_B: x[i] = *p != 0; break;
+      case MSB_TYPE_I8: x[i] = *(const int8_t *)p; break;
+      case MSB_TYPE_U8: x[i] = *p; break;
+      case MSB_TYPE_I16: { int16_t v; memcpy(&v, p, 2); x[i] = v; } break;
+      case MSB_TYPE_U16: { uint16_t v; memcpy(&v, p, 2); x[i] = v; } break;
+      case MSB_TYPE_I32: { int32_t v; memcpy(&v, p, 4); x[i] = v; } break;
+      case MSB_TYPE_U32: { uint32_t v; memcpy(&v, p, 4); x[i] = v; } break;
+      case MSB_TYPE_I64: { int64_t v; memcpy(&v, p, 8); x[i] = (double)v; } break;
+      case MSB_TYPE_U64: { uint64_t v; memcpy(&v, p, 8); x[i] = (double)v; } break;
+      case MSB_TYPE_F32: { float v; memcpy(&v, p, 4); x[i] = v; } break;
+      default: { double v; memcpy(&v, p, 8); x[i] = v; } break;
+    }
+  }
+  return MSB_OK;
+}
+
+static int value_op(msb_ctx *ctx, const msb_model_desc *model, int op, const double *hp, size_t nhp, double *ss,
+                    size_t nss, const void *value, const msb_runtime_type *vtype, float *score) {
+  REQUIRE(ctx && model && hp && ss, "NULL argument");
+  MSB_TRY(check_model(*model, 0));
+  REQUIRE(nhp == hp_size(*model) && nss == ss_size(*model), "wrong dimension");
+  std::vector<double> x;
+  MSB_TRY(value_to_doubles(value, vtype, x));
+  REQUIRE(x.size() == (model->family == MSB_FAMILY_NIW ? model->dim : 1u), "shapes do not match");
+  CU_TRY(cudaSetDevice(ctx->device));
+  double *d_buf = nullptr; float *d_score = nullptr;
+  const size_t total = nhp + nss + x.size();
+  CU_TRY(cudaMalloc(&d_buf, sizeof(double) * total));
+  CU_TRY(cudaMalloc(&d_score, sizeof(float) * 64));
+  double *d_hp = d_buf, *d_ss = d_buf + nhp, *d_x = d_ss + nss;
+  CU_TRY(cudaMemcpyAsync(d_hp, hp, sizeof(double) * nhp, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(d_ss, ss, sizeof(double) * nss, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(d_x, x.data(), sizeof(double) * x.size(), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = MSB_OK;
+  if (model->family == MSB_FAMILY_NIW && op == 0) {
+    // one group, one row: the batched NIW kernels with K = 1, N = 1
+    const uint32_t d = model->dim;
+    FeatDev f; memset(&f, 0, sizeof(f));
+    f.family = FAM_NIW; f.kind = KIND_NIW; f.dim = d; f.hp_off = 0; f.ss_off = 0; f.ss_w = (uint32_t)nss;
+    float *d_W = nullptr, *d_x32 = nullptr; int32_t *d_c2s = nullptr;
+    std::vector<float> x32(x.begin(), x.end());
+    CU_TRY(cudaMalloc(&d_W, sizeof(float) * ((size_t)d * d + d + 4)));
+    CU_TRY(cudaMalloc(&d_x32, sizeof(float) * d));
+    CU_TRY(cudaMalloc(&d_c2s, sizeof(int32_t)));
+    CU_TRY(cudaMemsetAsync(d_c2s, 0, sizeof(int32_t), ctx->stream));
+    CU_TRY(cudaMemsetAsync(d_score, 0, sizeof(float), ctx->stream));
+    CU_TRY(cudaMemcpyAsync(d_x32, x32.data(), sizeof(float) * d, cudaMemcpyHostToDevice, ctx->stream));
+    float *d_bias = d_W + (size_t)d * d, *d_coef = d_bias + d;
+    LAUNCH(ctx, niw_prepare_kernel, 1, 128, (2 * (size_t)d * d + d) * sizeof(double), f, d_hp, d_ss, d_c2s, d_W, d_bias, d_coef);
+    LAUNCH(ctx, niw_score_simt_kernel, dim3(1, 1), 128, ((size_t)d * d + d) * sizeof(float), d_x32, (int)d, d_W, d_bias, d_coef,
+           d_score, (size_t)1, (size_t)0, (size_t)1);
+    CU_TRY(cudaMemcpyAsync(score, d_score, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_W); cudaFree(d_x32); cudaFree(d_c2s);
+  } else {
+    LAUNCH(ctx, value_op_kernel, 1, 32, 0, model->family, model->dim, op, d_hp, d_ss, d_x, d_score);
+    if (op == 0) CU_TRY(cudaMemcpyAsync(score, d_score, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    else CU_TRY(cudaMemcpyAsync(ss, d_ss, sizeof(double) * nss, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  cudaFree(d_buf); cudaFree(d_score);
+  return rc;
+}
+
+extern "C" MSB_API int msb_value_score(msb_ctx *ctx, const msb_model_desc *model, const double *hp, size_t nhp, const double *ss,
+                               size_t nss, const void *value, const msb_runtime_type *vtype, float *score) {
+  REQUIRE(score, "NULL argument");
+  return value_op(ctx, model, 0, hp, nhp, const_cast<double *>(ss), nss, value, vtype, score);
+}
+extern "C" MSB_API int msb_value_add(msb_ctx *ctx, const msb_model_desc *model, const double *hp, size_t nhp, double *ss,
+                             size_t nss, const void *value, const msb_runtime_type *vtype) {
+  return value_op(ctx, model, 1, hp, nhp, ss, nss, value, vtype, nullptr);
+}
+extern "C" MSB_API int msb_value_remove(msb_ctx *ctx, const msb_model_desc *model, const double *hp, size_t nhp, double *ss,
+                                size_t nss, const void *value, const msb_runtime_type *vtype) {
+  return value_op(ctx, model, 2, hp, nhp, ss, nss, value, vtype, nullptr);
+}

@@ -1,0 +1,234 @@
+"""Mixture-model state on the device -- the caller side of the hot path.
+
+Method names and meaning follow the reference's entity_based_state_object
+(include/microscopes/common/entity_state.hpp:25-90) and group_manager
+(include/microscopes/common/group_manager.hpp:48-306); the batched calls
+(score_rows, sweep) are the data-parallel form of the same loop.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _dbl(values):
+    a = np.ascontiguousarray(np.asarray(values, dtype=np.float64).ravel())
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class state(object):
+    def __init__(self, ctx, models, max_groups=64, cluster_hp=None):
+        self._ctx = ctx
+        self._models = [m() for m in models]
+        descs = (_lib.ModelDesc * len(self._models))(*[m.c_desc() for m in self._models])
+        h = C.c_void_p()
+        _lib.check(_lib.load().msb_state_create(ctx.handle, descs, len(self._models), int(max_groups), C.byref(h)))
+        self._h = h
+        self._view = None
+        if cluster_hp is not None:
+            self.set_cluster_hp(cluster_hp)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def models(self):
+        return list(self._models)
+
+    # ---- data ---------------------------------------------------------------
+    def bind(self, view):
+        dev = view.to_device(self._ctx) if hasattr(view, "to_device") else view
+        _lib.check(_lib.load().msb_state_bind(self._h, dev.handle))
+        self._view = dev
+
+    # ---- hyperparameters (entity_state.hpp:41-49) -----------------------------
+    def set_cluster_hp(self, hp):
+        _lib.check(_lib.load().msb_state_set_cluster_hp(self._h, b"alpha", float(hp["alpha"])))
+
+    def get_cluster_hp(self):
+        v = C.c_double()
+        _lib.check(_lib.load().msb_state_get_cluster_hp(self._h, b"alpha", C.byref(v)))
+        return {"alpha": v.value}
+
+    def set_component_hp(self, component, hp):
+        for key, val in hp.items():
+            a, p = _dbl(val)
+            _lib.check(_lib.load().msb_state_set_hp(self._h, component, key.encode(), p, a.size))
+
+    def get_component_hp(self, component):
+        out = {}
+        for key, default in self._models[component].default_hyperparams().items():
+            shape = np.shape(default)
+            a = np.zeros(int(np.prod(shape)) if shape else 1, np.float64)
+            _lib.check(_lib.load().msb_state_get_hp(self._h, component, key.encode(),
+                                                    a.ctypes.data_as(C.POINTER(C.c_double)), a.size))
+            out[key] = a.reshape(shape) if shape else float(a[0])
+        return out
+
+    def set_hp_raw(self, component, key, values):
+        a, p = _dbl(values)
+        _lib.check(_lib.load().msb_state_set_hp(self._h, component, key.encode(), p, a.size))
+
+    # ---- suffstats (entity_state.hpp:51-54) --------------------------------------
+    def get_suffstats(self, component, gid, key, count=1):
+        a = np.zeros(count, np.float64)
+        _lib.check(_lib.load().msb_state_get_ss(self._h, component, gid, key.encode(),
+                                                a.ctypes.data_as(C.POINTER(C.c_double)), count))
+        return a
+
+    def set_suffstats(self, component, gid, key, values):
+        a, p = _dbl(values)
+        _lib.check(_lib.load().msb_state_set_ss(self._h, component, gid, key.encode(), p, a.size))
+
+    # ---- groups (entity_state.hpp:30-38,87-89) -------------------------------------
+    def nentities(self):
+        v = C.c_size_t()
+        _lib.check(_lib.load().msb_state_nentities(self._h, C.byref(v)))
+        return v.value
+
+    def ngroups(self):
+        v = C.c_size_t()
+        _lib.check(_lib.load().msb_state_ngroups(self._h, C.byref(v)))
+        return v.value
+
+    def ncomponents(self):
+        return len(self._models)
+
+    def groups(self):
+        n = self.ngroups()
+        buf = (C.c_size_t * max(n, 1))()
+        out = C.c_size_t()
+        _lib.check(_lib.load().msb_state_groups(self._h, buf, n, C.byref(out)))
+        return [int(buf[i]) for i in range(out.value)]
+
+    def empty_groups(self):
+        n = self.ngroups()
+        buf = (C.c_size_t * max(n, 1))()
+        out = C.c_size_t()
+        _lib.check(_lib.load().msb_state_empty_groups(self._h, buf, n, C.byref(out)))
+        return [int(buf[i]) for i in range(out.value)]
+
+    def groupsize(self, gid):
+        v = C.c_size_t()
+        _lib.check(_lib.load().msb_state_groupsize(self._h, gid, C.byref(v)))
+        return v.value
+
+    def create_group(self, rng=None):
+        v = C.c_size_t()
+        _lib.check(_lib.load().msb_state_create_group(self._h, C.byref(v)))
+        return v.value
+
+    def delete_group(self, gid):
+        _lib.check(_lib.load().msb_state_delete_group(self._h, gid))
+
+    def assignments(self):
+        n = self.nentities()
+        a = np.zeros(n, np.int64)
+        _lib.check(_lib.load().msb_state_assignments(self._h, a.ctypes.data, n))
+        return a
+
+    # ---- membership (entity_state.hpp:57-72) ------------------------------------------
+    def add_value(self, gid, eid, rng=None):
+        _lib.check(_lib.load().msb_state_add_value(self._h, gid, eid))
+
+    def remove_value(self, eid, rng=None):
+        v = C.c_size_t()
+        _lib.check(_lib.load().msb_state_remove_value(self._h, eid, C.byref(v)))
+        return v.value
+
+    def add_values(self, gids):
+        a = np.ascontiguousarray(gids, dtype=np.int64)
+        _lib.check(_lib.load().msb_state_add_values(self._h, a.ctypes.data, a.size))
+
+    def score_value(self, eid, rng=None):
+        k = self.ngroups()
+        gids = (C.c_size_t * max(k, 1))()
+        scores = np.zeros(max(k, 1), np.float32)
+        n = C.c_size_t()
+        _lib.check(_lib.load().msb_state_score_value(self._h, eid, gids, scores.ctypes.data_as(C.POINTER(C.c_float)),
+                                                     k, C.byref(n)))
+        return [int(gids[i]) for i in range(n.value)], scores[:n.value]
+
+    # ---- batched ---------------------------------------------------------------------
+    def score_rows(self, row_lo=0, row_hi=None, out=None):
+        """(gids, scores[nrows, K]): log(pseudocount) + sum_d score_value for every row"""
+        row_hi = self.nentities() if row_hi is None else row_hi
+        k = self.ngroups()
+        gids = (C.c_size_t * max(k, 1))()
+        n = C.c_size_t()
+        if out is None:
+            out = np.empty((row_hi - row_lo, k), np.float32)
+        _lib.check(_lib.load().msb_state_score_rows(self._h, row_lo, row_hi, out.ctypes.data, out.strides[0] // 4 if out.size else k,
+                                                    0, gids, k, C.byref(n)))
+        return [int(gids[i]) for i in range(n.value)], out
+
+    def score_rows_device(self, row_lo=0, row_hi=None):
+        """scores stay on the device; returns (gids, device pointer, ld)"""
+        row_hi = self.nentities() if row_hi is None else row_hi
+        k = self.ngroups()
+        gids = (C.c_size_t * max(k, 1))()
+        n = C.c_size_t()
+        _lib.check(_lib.load().msb_state_score_rows(self._h, row_lo, row_hi, None, 0, 1, gids, k, C.byref(n)))
+        ptr, ld = C.c_void_p(), C.c_size_t()
+        _lib.check(_lib.load().msb_state_last_scores(self._h, C.byref(ptr), C.byref(ld), None, None))
+        return [int(gids[i]) for i in range(n.value)], ptr.value, ld.value
+
+    def sweep(self, row_lo=0, row_hi=None, seed=0, sweep=0, uniforms=None, row_id_offset=0, defer_apply=False):
+        row_hi = self.nentities() if row_hi is None else row_hi
+        opts = _lib.SweepOpts(int(seed), int(sweep), int(row_id_offset), None, 1 if defer_apply else 0, 0)
+        keep = None
+        if uniforms is not None:
+            keep = np.ascontiguousarray(uniforms, dtype=np.float32)
+            assert keep.size == row_hi - row_lo
+            opts.uniforms = keep.ctypes.data
+        res = _lib.SweepResult()
+        _lib.check(_lib.load().msb_state_sweep(self._h, row_lo, row_hi, C.byref(opts), C.byref(res)))
+        return {"rows": res.rows, "moved": res.moved, "units": res.units}
+
+    def last_scores(self):
+        """copy of the score matrix the last score/sweep call left on the device"""
+        import ctypes
+        ptr, ld, nr, nc = C.c_void_p(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _lib.check(_lib.load().msb_state_last_scores(self._h, C.byref(ptr), C.byref(ld), C.byref(nr), C.byref(nc)))
+        return ptr.value, ld.value, nr.value, nc.value
+
+    def last_timings(self):
+        a = (C.c_float * 5)()
+        _lib.check(_lib.load().msb_state_last_timings(self._h, a, 5))
+        return dict(zip(("build", "score", "sample", "update", "apply"), [float(x) for x in a]))
+
+    def delta_buffer(self):
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _lib.check(_lib.load().msb_state_delta_buffer(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def apply_deltas(self):
+        _lib.check(_lib.load().msb_state_apply_deltas(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.load().msb_state_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sample_discrete_log(ctx, scores, uniforms):
+    """util.hpp:138-143 for every row of ``scores`` with one uniform each, on the device"""
+    s = np.ascontiguousarray(scores, dtype=np.float32)
+    u = np.ascontiguousarray(uniforms, dtype=np.float32)
+    out = np.zeros(s.shape[0], np.int32)
+    _lib.check(_lib.load().msb_sample_discrete_log(ctx.handle, s.ctypes.data, s.shape[0], s.shape[1], s.shape[1],
+                                                   u.ctypes.data, out.ctypes.data))
+    return out
+
+
+def philox_uniforms(ctx, seed, sweep, row_lo, n):
+    out = np.zeros(n, np.float32)
+    _lib.check(_lib.load().msb_philox_uniforms(ctx.handle, seed, sweep, row_lo, n, out.ctypes.data))
+    return out

@@ -1,0 +1,222 @@
+/*
+ * mscope_b200.h -- C ABI of the B200-native hot path of microscopes-common.
+ *
+ * One shared library (common_b200/csrc/libmscope_b200.so) exports exactly the
+ * symbols declared here.  No C++ or torch types cross this boundary: plain
+ * pointers, sizes, opaque handles, int status codes + msb_last_error().
+ *
+ * What each entry point replaces in the reference (paths relative to the
+ * reference tree, datamicroscopes/common):
+ *
+ *   msb_dataview_*        include/microscopes/common/recarray/dataview.hpp:194-217
+ *                         (row_major_dataview ctor: data, mask, n, types) and
+ *                         src/common/recarray/dataview.cpp:81-139 (row addressing)
+ *   msb_runtime_type      include/microscopes/common/runtime_type.hpp:65-141
+ *   msb_prim              include/microscopes/common/type_info.h:10-44
+ *   msb_state_set/get_hp  models/distributions.hpp:128-144,165-181 (get_hp_mutator keys)
+ *   msb_state_set/get_ss  models/distributions.hpp:146-160,183-199 (get_ss_mutator keys)
+ *   msb_state_create_group / delete_group / groups / groupsize / empty_groups
+ *                         common/group_manager.hpp:133-216
+ *   msb_state_add_value / remove_value / score_value
+ *                         common/entity_state.hpp:57-72 (which loop over
+ *                         models/base.hpp:25-27 group::add_value/remove_value/score_value)
+ *   msb_state_score_rows  the same K x D loop of base.hpp:27 for a whole row range
+ *   msb_sample_discrete_log
+ *                         common/util.hpp:125-156 (scores_to_probs + sample_discrete)
+ *   msb_state_sweep       one batched Gibbs reassignment pass: remove/score/sample/add
+ *                          against frozen suffstats
+ *   msb_value_*           single-value group::score_value/add_value/remove_value
+ *                         (models/base.hpp:25-27), executed on the device
+ *
+ * Semantics notes
+ *  - A masked (row, feature) cell contributes 0 to every score and nothing to
+ *    the suffstats (the reference leaves this to the caller and asserts
+ *    !anymasked, distributions.hpp:269,276,283).
+ *  - Values cross the ABI as double (integers are exact); device storage is
+ *    described in DESIGN.md.
+ *  - All calls on one msb_ctx are ordered on its CUDA stream; calls returning
+ *    host data synchronise that stream before returning.
+ *  - There is no CPU fallback: without a usable CUDA device msb_ctx_create
+ *    fails with MSB_ERR_CUDA.
+ */
+#ifndef MSCOPE_B200_H
+#define MSCOPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MSB_API __attribute__((visibility("default")))
+#else
+#define MSB_API
+#endif
+
+typedef struct msb_ctx msb_ctx;           /* device + stream */
+typedef struct msb_dataview msb_dataview; /* device copy of a row_major_dataview */
+typedef struct msb_state msb_state;       /* K groups x D features of suffstats + hypers + assignments */
+
+enum msb_status {
+  MSB_OK = 0,
+  MSB_ERR_INVALID = 1,     /* bad argument (the reference throws std::runtime_error) */
+  MSB_ERR_CUDA = 2,        /* CUDA runtime error, see msb_last_error() */
+  MSB_ERR_NOMEM = 3,
+  MSB_ERR_UNSUPPORTED = 4,
+  MSB_ERR_KEY = 5,         /* unknown hp/ss key: distributions.hpp:140,152 */
+  MSB_ERR_STATE = 6        /* call not valid in the current state (e.g. entity already assigned) */
+};
+
+/* type_info.h:10-34, same order, same values */
+enum msb_prim {
+  MSB_TYPE_B = 0, MSB_TYPE_I8, MSB_TYPE_U8, MSB_TYPE_I16, MSB_TYPE_U16,
+  MSB_TYPE_I32, MSB_TYPE_U32, MSB_TYPE_I64, MSB_TYPE_U64, MSB_TYPE_F32, MSB_TYPE_F64,
+  MSB_TYPE_NELEMS
+};
+
+/* runtime_type.hpp:65-141: (primitive, n, vec) */
+typedef struct msb_runtime_type {
+  int32_t prim;  /* enum msb_prim */
+  uint32_t n;    /* number of elements (1 for scalars) */
+  int32_t vec;   /* 0 scalar, 1 vector */
+} msb_runtime_type;
+
+/* DISTRIB_FOR_EACH_DISTRIBUTION, distributions.hpp:58-64 (bnb reserved, not built yet) */
+enum msb_family {
+  MSB_FAMILY_BB = 0,   /* BetaBernoulli             hp: alpha beta            ss: heads tails */
+  MSB_FAMILY_BNB = 1,  /* reserved */
+  MSB_FAMILY_GP = 2,   /* GammaPoisson              hp: alpha inv_beta        ss: count sum log_prod */
+  MSB_FAMILY_NICH = 3, /* NormalInverseChiSq        hp: mu kappa sigmasq nu   ss: count mean count_times_variance */
+  MSB_FAMILY_DD = 4,   /* DirichletDiscrete(dim)    hp: alphas[dim]           ss: count_sum counts[dim] */
+  MSB_FAMILY_NIW = 5   /* NormalInverseWishart(dim) hp: mu[dim] kappa psi[dim*dim] nu
+                                                    ss: count sum_x[dim] sum_xxT[dim*dim] */
+};
+
+typedef struct msb_model_desc {
+  int32_t family; /* enum msb_family */
+  uint32_t dim;   /* dd: number of categories (runtime, not capped at 128); niw: dimension; else 0 */
+} msb_model_desc;
+
+MSB_API const char *msb_last_error(void);
+MSB_API int msb_abi_version(void);
+
+/* ---- context ------------------------------------------------------------ */
+/* stream: a cudaStream_t owned by the caller, or NULL to create a private one */
+MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out);
+MSB_API int msb_ctx_destroy(msb_ctx *ctx);
+MSB_API int msb_ctx_synchronize(msb_ctx *ctx);
+MSB_API void *msb_ctx_stream(msb_ctx *ctx);
+/* number of kernels this library has launched on ctx since creation */
+MSB_API int msb_ctx_launch_count(msb_ctx *ctx, uint64_t *out);
+
+/* ---- dataview (recarray/dataview.hpp:194-217) --------------------------- */
+/* data: n records, AoS, field offsets = running sum of type sizes
+ *       (runtime_type.hpp:123-134); mask: n x sum(type.n) bytes of bool or NULL.
+ * on_device != 0: data/mask are device pointers (no host copy). */
+MSB_API int msb_dataview_create(msb_ctx *ctx, const void *data, const void *mask, size_t n,
+                        const msb_runtime_type *types, size_t nfeatures, int on_device,
+                        msb_dataview **out);
+MSB_API int msb_dataview_destroy(msb_dataview *dv);
+MSB_API int msb_dataview_size(const msb_dataview *dv, size_t *n);
+MSB_API int msb_dataview_nfeatures(const msb_dataview *dv, size_t *d);
+MSB_API int msb_dataview_rowsize(const msb_dataview *dv, size_t *rowsize, size_t *maskrowsize);
+/* copy record idx (and its mask row, may be NULL) back to the host: dataview::get(idx) */
+MSB_API int msb_dataview_get_row(msb_dataview *dv, size_t idx, void *row_out, void *mask_out);
+
+/* ---- state -------------------------------------------------------------- */
+MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *models, size_t nfeatures,
+                     size_t max_groups, msb_state **out);
+MSB_API int msb_state_destroy(msb_state *st);
+/* converts the AoS records to columnar Value-typed device columns (the
+ * runtime_cast of runtime_type.hpp:145-166 applied once per cell) and sizes the
+ * assignment vector (all -1, group_manager.hpp:64-69). */
+MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv);
+
+MSB_API int msb_state_set_hp(msb_state *st, size_t feature, const char *key, const double *v, size_t count);
+MSB_API int msb_state_get_hp(msb_state *st, size_t feature, const char *key, double *v, size_t count);
+MSB_API int msb_state_set_ss(msb_state *st, size_t feature, size_t gid, const char *key, const double *v, size_t count);
+MSB_API int msb_state_get_ss(msb_state *st, size_t feature, size_t gid, const char *key, double *v, size_t count);
+/* CRP hyperparameter "alpha": group_manager.hpp:107-131 */
+MSB_API int msb_state_set_cluster_hp(msb_state *st, const char *key, double v);
+MSB_API int msb_state_get_cluster_hp(msb_state *st, const char *key, double *v);
+
+MSB_API int msb_state_nentities(msb_state *st, size_t *n);
+MSB_API int msb_state_ngroups(msb_state *st, size_t *n);
+MSB_API int msb_state_groups(msb_state *st, size_t *gids, size_t cap, size_t *n); /* ascending gid */
+MSB_API int msb_state_empty_groups(msb_state *st, size_t *gids, size_t cap, size_t *n);
+MSB_API int msb_state_groupsize(msb_state *st, size_t gid, size_t *count);
+MSB_API int msb_state_create_group(msb_state *st, size_t *gid);
+MSB_API int msb_state_delete_group(msb_state *st, size_t gid); /* must be empty */
+
+/* assignments: gid per entity, -1 = unassigned (group_manager.hpp:133-137) */
+MSB_API int msb_state_assignments(msb_state *st, int64_t *out, size_t n);
+/* bulk add_value of every currently unassigned entity whose gids[i] != -1 */
+MSB_API int msb_state_add_values(msb_state *st, const int64_t *gids, size_t n);
+
+/* single-entity calls, entity_state.hpp:57-72 */
+MSB_API int msb_state_add_value(msb_state *st, size_t gid, size_t eid);
+MSB_API int msb_state_remove_value(msb_state *st, size_t eid, size_t *gid);
+MSB_API int msb_state_score_value(msb_state *st, size_t eid, size_t *gids, float *scores, size_t cap, size_t *n);
+
+/* batched scoring: scores[(i - row_lo) * ld + c] for column c <-> gids[c]
+ * (all groups, ascending gid), = log(pseudocount) + sum_d score_value.
+ * on_device != 0: scores is a device pointer. */
+MSB_API int msb_state_score_rows(msb_state *st, size_t row_lo, size_t row_hi, float *scores, size_t ld,
+                         int on_device, size_t *gids, size_t cap, size_t *ncols);
+
+/* util.hpp:125-156 on the device, one uniform per row; host pointers */
+MSB_API int msb_sample_discrete_log(msb_ctx *ctx, const float *scores, size_t nrows, size_t k, size_t ld,
+                            const float *uniforms, int32_t *out);
+/* the uniform the sweep draws for (seed, global row id, sweep): Philox4x32-10 */
+MSB_API int msb_philox_uniforms(msb_ctx *ctx, uint64_t seed, uint64_t sweep, uint64_t row_lo, size_t n, float *out);
+
+typedef struct msb_sweep_opts {
+  uint64_t seed;          /* Philox key */
+  uint64_t sweep;         /* Philox counter word 2 */
+  uint64_t row_id_offset; /* global id of local row 0 (multi-GPU row sharding) */
+  const float *uniforms;  /* host array, one per row of [row_lo,row_hi), or NULL -> Philox */
+  int32_t defer_apply;    /* 1: leave the suffstat deltas unapplied (all-reduce them, then msb_state_apply_deltas) */
+  int32_t reserved;
+} msb_sweep_opts;
+
+typedef struct msb_sweep_result {
+  uint64_t rows;   /* rows processed */
+  uint64_t moved;  /* rows whose group changed (local) */
+  uint64_t units;  /* rows x groups x features scored */
+} msb_sweep_result;
+
+/* score rows [row_lo,row_hi) against the frozen suffstats, draw a group per row,
+ * then apply remove_value(old)/add_value(new) for every row that moved. */
+MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_hi, const msb_sweep_opts *opts,
+                    msb_sweep_result *res);
+
+/* multi-GPU: flat fp64 buffer [group counts | per-feature suffstat deltas] on the device */
+MSB_API int msb_state_delta_buffer(msb_state *st, double **dev_ptr, size_t *count);
+MSB_API int msb_state_apply_deltas(msb_state *st);
+
+/* device pointer + leading dimension of the scores the last sweep/score wrote (diagnostics, tests) */
+MSB_API int msb_state_last_scores(msb_state *st, float **dev_ptr, size_t *ld, size_t *nrows, size_t *ncols);
+/* events recorded around the kernels of the last sweep; ms per phase:
+ * [0] table build, [1] score, [2] sample, [3] update, [4] apply */
+MSB_API int msb_state_last_timings(msb_state *st, float *ms, size_t count);
+
+/* ---- single-value plugin calls (models/base.hpp:25-27), run on the device -- */
+/* hp/ss are the flat field vectors in the order listed at enum msb_family */
+MSB_API int msb_value_score(msb_ctx *ctx, const msb_model_desc *model, const double *hp, size_t nhp,
+                    const double *ss, size_t nss, const void *value, const msb_runtime_type *vtype,
+                    float *score);
+MSB_API int msb_value_add(msb_ctx *ctx, const msb_model_desc *model, const double *hp, size_t nhp,
+                  double *ss, size_t nss, const void *value, const msb_runtime_type *vtype);
+MSB_API int msb_value_remove(msb_ctx *ctx, const msb_model_desc *model, const double *hp, size_t nhp,
+                     double *ss, size_t nss, const void *value, const msb_runtime_type *vtype);
+MSB_API size_t msb_model_hp_size(const msb_model_desc *model);
+MSB_API size_t msb_model_ss_size(const msb_model_desc *model);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSCOPE_B200_H */

@@ -1,0 +1,62 @@
+"""CPU: the C-ABI library loads and exports every symbol include/mscope_b200.h declares;
+without a GPU it fails loudly instead of falling back."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import common_b200 as cb
+from common_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "mscope_b200.h")).read()
+    return sorted(set(re.findall(r"^MSB_API [^;(]*?\b(msb_\w+)\(", text, re.M)))
+
+
+def test_header_and_binding_agree():
+    assert _header_symbols() == list(_lib.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _header_symbols():
+        assert hasattr(lib, name), name
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH]).decode()
+    exported = sorted(set(re.findall(r" T (msb_\w+)", out)))
+    assert exported == _header_symbols()  # nothing undeclared leaks out either
+    assert _lib.load().msb_abi_version() == 1
+
+
+def test_library_is_sm100a_native():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in out.stdout
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(cb.MsbError) as e:
+        cb.Context(0)
+    assert e.value.status == _lib.MSB_ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    # the oracle is test infrastructure: nothing under common_b200/ may reference it
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "common_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".sh")):
+                text = open(os.path.join(dirpath, fn), errors="replace").read()
+                assert "oracle" not in text.lower(), os.path.join(dirpath, fn)
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        assert "oracle" not in open(os.path.join(ROOT, "include", fn)).read().lower()
