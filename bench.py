@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- row x group x feature scores/sec of the hot path on N B200s of one node.
+
+A "step" is one full pass of the hot path over one batch of synthetic rows:
+parameter build -> score (N x K matrix materialised) -> categorical draw ->
+suffstat update (-> one all-reduce of the suffstat deltas when N > 1).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      # the CPU path, all host threads
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "row_x_group_x_feature_scores_per_sec"
+UNIT = "scores/s"
+
+# per-unit byte sizes of SURVEY.md section 8(d) / BASELINE.md section 5
+B_X = {"bb": 1, "dd": 1, "gp": 4, "nich": 4}
+B_SS = {"bb": 8, "gp": 12, "nich": 12}
+B_HP = {"bb": 8, "gp": 8, "nich": 16}
+
+
+def algorithmic_bytes_score(descs, storage, n, k):
+    """B = N sum b_x + K sum b_ss + sum b_hp + 4 N K   (score mode)"""
+    bx = bss = bhp = 0
+    for d, desc in enumerate(descs):
+        m = desc()
+        nm = m.name()
+        if nm == "dd":
+            C = m._param()
+            bx += np.dtype(storage[d]).itemsize if storage and storage[d] is not None else 4
+            bss += 4 * (C + 1); bhp += 4 * C
+        elif nm == "niw":
+            dim = m._param()
+            bx += 4 * dim; bss += 4 * (1 + dim + dim * dim); bhp += 4 * (2 + dim + dim * dim)
+        else:
+            bx += B_X[nm]; bss += B_SS[nm]; bhp += B_HP[nm]
+    return n * bx + k * bss + bhp + 4 * n * k
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(args, rank, world):
+    import common_b200 as cb
+    cfg = cb.synth.config(args.workload)
+    n = args.rows or cfg["n"]
+    k = args.groups or cfg["k"]
+    descs = cfg["models"]
+    storage = cfg.get("storage")
+    # weak scaling: every rank holds its own n rows of the same planted mixture (stream id = rank)
+    arr, z = cb.synth.make_dataset(descs, n, k, seed=73, stream=rank, storage=storage)
+    return cfg, descs, storage, n, k, arr, z
+
+
+def cpu_reference_rate(descs, hp_by_feature, arr, z, k, budget_s, nthreads, f32=True):
+    """times the CPU path (the reference's per-(row, group, feature) loop) on a bounded row sample.
+    Uses oracle/_ref (the reference's own headers) when it was built, else the C port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common_b200 as cb
+    import oracle_lib as ol
+    import ref_lib
+    orc = ol.load()
+    hp = np.concatenate([orc.flat_hp(d, hp_by_feature) for d in descs])
+    n_build = min(arr.shape[0], 200_000)
+    view_all = cb.numpy_dataview(arr[:n_build])
+    ss, counts = ol.build_suffstats(orc, descs, hp, view_all, z[:n_build], k)
+    lp = ol.logprior(counts, 1.0)
+    ref = ref_lib.load()
+    kind = "reference-api" if ref is not None else "port"
+    D = len(descs)
+
+    def run(rows):
+        view = cb.numpy_dataview(arr[:rows])
+        t0 = time.perf_counter()
+        if ref is not None:
+            ref.score_rows(descs, hp, ss, lp, view, nthreads)
+        else:
+            orc.score_rows(descs, hp, ss, lp, view, nthreads=nthreads, f32=f32)
+        return time.perf_counter() - t0
+
+    rows = max(8, min(256, arr.shape[0]))
+    t = run(rows)
+    # grow the sample until it fills the budget (bounded by the data we have)
+    while t < budget_s / 4 and rows < arr.shape[0]:
+        rows = int(min(arr.shape[0], max(rows * 2, rows * (budget_s / 2) / max(t, 1e-6))))
+        t = run(rows)
+    return {"value": rows * k * D / t, "seconds": t, "rows": rows, "kind": kind, "cores": nthreads,
+            "sample": "%d of the workload's rows x K=%d groups x D=%d features, %s" % (
+                rows, k, D, "reference headers (models/base.hpp, recarray/dataview.hpp) + restated family maths, libm logf/lgammaf"
+                if ref is not None else "C port of the reference loop, libm logf/lgammaf")}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--groups", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    import common_b200 as cb
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cfg, descs, storage, n, k, arr, z = build_workload(args, 0, 1)
+        n = min(n, 200_000)
+        arr, z = arr[:n], z[:n]
+        ncores = os.cpu_count() or 1
+        hpx = cfg.get("hp")
+        rates = []
+        for i in range(args.warmup + args.steps):
+            r = cpu_reference_rate(descs, hpx, arr, z, k, max(2.0, args.cpu_seconds / max(1, args.steps)), ncores)
+            if i >= args.warmup:
+                rates.append(r)
+        val = float(np.mean([r["value"] for r in rates]))
+        ms = float(np.mean([r["seconds"] for r in rates]) * 1e3)
+        line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args, cfg, descs, n, k), "rows_per_step": rates[-1]["rows"], "groups": k,
+                           "features": len(descs)},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": rates[-1]["cores"], "kind": "port", "api": rates[-1]["kind"], "sample": rates[-1]["sample"]},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from common_b200 import dist as cbd
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    cfg, descs, storage, n, k, arr, z = build_workload(args, rank, world)
+    D = len(descs)
+
+    stream = torch.cuda.current_stream(device)
+    ctx = cb.Context(local_rank, stream=stream.cuda_stream)
+    view = cb.numpy_dataview(arr)
+    st = cb.state(ctx, descs, max_groups=k + 8, cluster_hp={"alpha": 1.0})
+    if cfg.get("hp"):
+        for d in range(D):
+            st.set_component_hp(d, cfg["hp"])
+    st.bind(view)
+    gids = np.asarray([st.create_group() for _ in range(k)])
+    st.add_values(gids[z])
+    if world > 1:
+        cbd.allreduce_suffstats(st, device)
+
+    def step(i):
+        if world > 1:
+            r = st.sweep(seed=73, sweep=i, row_id_offset=rank * n, defer_apply=True)
+            cbd.allreduce_deltas(st, device)
+        else:
+            r = st.sweep(seed=73, sweep=i)
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for i in range(warmup):
+        step(i)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase = {"build": 0.0, "score": 0.0, "sample": 0.0, "update": 0.0, "apply": 0.0}
+    units = 0
+    e0.record(stream)
+    for i in range(args.steps):
+        r = step(warmup + i)
+        units += r["units"]
+        for kk, v in st.last_timings().items():
+            phase[kk] += v
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+    u = torch.tensor([float(units)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    ms_total = float(t.item()); units_all = float(u.item())
+    value = units_all / (ms_total * 1e-3)
+
+    # ---- e2e: the same step through the public API from HOST buffers -------------------
+    e2e = None
+    if not args.no_e2e:
+        raw, _ = view.raw()
+        pinned = torch.from_numpy(raw).pin_memory()
+        assign_host = torch.from_numpy(gids[z].astype(np.int64)).pin_memory()
+        types = view.types()
+        from common_b200.dataview import device_dataview
+
+        def e2e_step(i):
+            dv = device_dataview(ctx, data=pinned.data_ptr(), n=n, types=types)      # H2D of the records
+            s2 = cb.state(ctx, descs, max_groups=k + 8, cluster_hp={"alpha": 1.0})
+            if cfg.get("hp"):
+                for d in range(D):
+                    s2.set_component_hp(d, cfg["hp"])
+            s2.bind(dv)                                                             # AoS -> SoA on the device
+            g2 = np.asarray([s2.create_group() for _ in range(k)])
+            s2.add_values(assign_host.numpy())                                      # H2D assignments, suffstats built on device
+            if world > 1:
+                cbd.allreduce_suffstats(s2, device)
+                rr = s2.sweep(seed=73, sweep=i, row_id_offset=rank * n, defer_apply=True)
+                cbd.allreduce_deltas(s2, device)
+            else:
+                rr = s2.sweep(seed=73, sweep=i)
+            out = s2.assignments()                                                  # D2H of the result
+            sizes = [s2.groupsize(int(g)) for g in g2[:4]]
+            s2.close(); dv.close()
+            return rr["units"], out, sizes
+
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        eu = 0
+        esteps = max(2, min(args.steps, 5))
+        for i in range(esteps):
+            eu += e2e_step(i)[0]
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=device, dtype=torch.float64)
+        uu = torch.tensor([float(eu)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(uu, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(uu.item()) / float(tt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(raw.nbytes + n * 8), "d2h_bytes_per_step": int(n * 8 + 4 * 8),
+               "ms_per_step": float(tt.item()) * 1e3 / esteps,
+               "what": "host AoS records (pinned) -> device dataview -> bind/pack -> add_values -> sweep -> assignments to host"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        score_ms = phase["score"] / args.steps
+        abytes = algorithmic_bytes_score(descs, storage, n, k)
+        achieved = abytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args, cfg, descs, n, k), "rows_per_gpu": n, "groups": k, "features": D,
+                           "step": "param build + score (N x K fp32 materialised) + sample + suffstat update" + (" + all-reduce" if world > 1 else ""),
+                           "l2": "no explicit flush: each step streams the %.0f MB score matrix (> 126 MB L2)" % (4.0 * n * st.last_scores()[1] / 1e6)},
+                "phase_ms_per_step": {kk: v / args.steps for kk, v in phase.items()},
+                "roofline": {"kernel": "score_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": abytes,
+                             "launch_ms": score_ms, "peak_source": peak_src,
+                             "note": "score kernels reuse every loaded value K times: the binding roof is shared-memory lookup / FP32 issue rate, see DESIGN.md"},
+                "gpu_launches": int(launches), "clocks": clk}
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu and world == 1:
+            c = cpu_reference_rate(descs, cfg.get("hp"), arr, z, k, args.cpu_seconds, 1)
+            line["cpu_baseline"] = {"value": c["value"], "unit": UNIT, "cores": c["cores"],
+                                    "kind": "port", "api": c["kind"], "sample": c["sample"]}
+        print(json.dumps(line))
+    st.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def workload_name(args, cfg, descs, n, k):
+    names = {}
+    for d in descs:
+        m = d()
+        key = m.name() + ("(%d)" % m._param() if m._param() else "")
+        names[key] = names.get(key, 0) + 1
+    return "%s: %s, N=%d rows x K=%d groups x D=%d features" % (
+        args.workload.upper(), " + ".join("%d x %s" % (c, nm) for nm, c in names.items()), n, k, len(descs))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -90,7 +90,9 @@ _PROTOS = {
     "msb_state_sweep": (C.c_int, [_P, _SZ, _SZ, C.POINTER(SweepOpts), C.POINTER(SweepResult)]),
     "msb_state_delta_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ)]),
     "msb_state_apply_deltas": (C.c_int, [_P]),
+    "msb_state_suffstat_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ)]),
     "msb_state_last_scores": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ), C.POINTER(_SZ), C.POINTER(_SZ)]),
+    "msb_state_read_last_scores": (C.c_int, [_P, _P, _SZ]),
     "msb_state_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), _SZ]),
     "msb_value_score": (C.c_int, [_P, C.POINTER(ModelDesc), C.POINTER(C.c_double), _SZ, C.POINTER(C.c_double), _SZ,
                                   _P, C.POINTER(RuntimeType), C.POINTER(C.c_float)]),

@@ -853,6 +853,11 @@ extern "C" MSB_API int msb_state_delta_buffer(msb_state *st, double **dev_ptr, s
   *dev_ptr = st->d_delta; *count = st->SS;
   return MSB_OK;
 }
+extern "C" MSB_API int msb_state_suffstat_buffer(msb_state *st, double **dev_ptr, size_t *count) {
+  REQUIRE(st && dev_ptr && count, "NULL argument");
+  *dev_ptr = st->d_ss; *count = st->SS;
+  return MSB_OK;
+}
 extern "C" MSB_API int msb_state_apply_deltas(msb_state *st) {
   REQUIRE(st, "NULL argument");
   CU_TRY(cudaSetDevice(st->ctx->device));
@@ -1013,6 +1018,16 @@ extern "C" MSB_API int msb_state_last_scores(msb_state *st, float **dev_ptr, siz
   if (ld) *ld = st->ld;
   if (nrows) *nrows = st->last_rows;
   if (ncols) *ncols = st->last_cols;
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_state_read_last_scores(msb_state *st, float *out, size_t ld_out) {
+  REQUIRE(st && out, "NULL argument");
+  REQUIRE(ld_out >= st->last_cols, "ld smaller than the number of groups");
+  if (!st->last_rows || !st->last_cols) return MSB_OK;
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  CU_TRY(cudaMemcpy2DAsync(out, sizeof(float) * ld_out, st->d_scores, sizeof(float) * st->ld, sizeof(float) * st->last_cols,
+                           st->last_rows, cudaMemcpyDeviceToHost, st->ctx->stream));
+  CU_TRY(cudaStreamSynchronize(st->ctx->stream));
   return MSB_OK;
 }
 extern "C" MSB_API int msb_state_last_timings(msb_state *st, float *ms, size_t count) {

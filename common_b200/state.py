@@ -187,11 +187,18 @@ class state(object):
         return {"rows": res.rows, "moved": res.moved, "units": res.units}
 
     def last_scores(self):
-        """copy of the score matrix the last score/sweep call left on the device"""
-        import ctypes
+        """(device pointer, ld, nrows, ncols) of the score matrix the last score/sweep call wrote"""
         ptr, ld, nr, nc = C.c_void_p(), C.c_size_t(), C.c_size_t(), C.c_size_t()
         _lib.check(_lib.load().msb_state_last_scores(self._h, C.byref(ptr), C.byref(ld), C.byref(nr), C.byref(nc)))
         return ptr.value, ld.value, nr.value, nc.value
+
+    def read_last_scores(self):
+        """host copy of the score matrix the last score/sweep call left on the device"""
+        _, _, nr, nc = self.last_scores()
+        out = np.empty((nr, nc), np.float32)
+        if out.size:
+            _lib.check(_lib.load().msb_state_read_last_scores(self._h, out.ctypes.data, nc))
+        return out
 
     def last_timings(self):
         a = (C.c_float * 5)()
@@ -201,6 +208,11 @@ class state(object):
     def delta_buffer(self):
         ptr, n = C.c_void_p(), C.c_size_t()
         _lib.check(_lib.load().msb_state_delta_buffer(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def suffstat_buffer(self):
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _lib.check(_lib.load().msb_state_suffstat_buffer(self._h, C.byref(ptr), C.byref(n)))
         return ptr.value, n.value
 
     def apply_deltas(self):

@@ -197,9 +197,13 @@ MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_hi, const m
 /* multi-GPU: flat fp64 buffer [group counts | per-feature suffstat deltas] on the device */
 MSB_API int msb_state_delta_buffer(msb_state *st, double **dev_ptr, size_t *count);
 MSB_API int msb_state_apply_deltas(msb_state *st);
+/* the resident suffstats themselves, same layout (replica initialisation: all-reduce, then apply_deltas) */
+MSB_API int msb_state_suffstat_buffer(msb_state *st, double **dev_ptr, size_t *count);
 
 /* device pointer + leading dimension of the scores the last sweep/score wrote (diagnostics, tests) */
 MSB_API int msb_state_last_scores(msb_state *st, float **dev_ptr, size_t *ld, size_t *nrows, size_t *ncols);
+/* host copy of that matrix: out[r * ld_out + c], r < nrows, c < ncols */
+MSB_API int msb_state_read_last_scores(msb_state *st, float *out, size_t ld_out);
 /* events recorded around the kernels of the last sweep; ms per phase:
  * [0] table build, [1] score, [2] sample, [3] update, [4] apply */
 MSB_API int msb_state_last_timings(msb_state *st, float *ms, size_t count);

@@ -1,0 +1,360 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the CPU oracle.
+
+Bars (BASELINE.json north_star): log-probabilities within 1e-5 relative of the
+fp64 closed form; assignments and integer suffstat counts bit-exact when both
+sides are fed the same score bits and the same uniforms.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import common_b200 as cb
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-5  # relative tolerance on a log-probability, stated by north_star for fp32
+
+
+def rel_err(got, want):
+    want = np.asarray(want, np.float64)
+    return np.abs(np.asarray(got, np.float64) - want) / np.maximum(1.0, np.abs(want))
+
+
+def make_state(ctx, oracle, descs, n, k, seed=1, mask_frac=0.0, storage=None, hp=None, max_groups=None, extra_empty=0):
+    arr, z = cb.synth.make_dataset(descs, n, k, seed=seed, mask_frac=mask_frac, storage=storage)
+    view = cb.numpy_dataview(arr)
+    st = cb.state(ctx, descs, max_groups=max_groups or (k + extra_empty + 4), cluster_hp={"alpha": 1.0})
+    hps = []
+    for d, desc in enumerate(descs):
+        h = dict(desc().default_hyperparams(), **((hp or {}).get(d, {})))
+        st.set_component_hp(d, h)
+        hps.append(oracle.flat_hp(desc, h))
+    st.bind(view)
+    gids = [st.create_group() for _ in range(k + extra_empty)]
+    st.add_values(np.asarray(gids)[z])
+    hp_flat = np.concatenate(hps)
+    ss, counts = ol.build_suffstats(oracle, descs, hp_flat, view, z, k + extra_empty)
+    return st, view, z, gids, hp_flat, ss, counts
+
+
+FAMILIES = {
+    "bb": [cb.bb] * 5,
+    "dd": [cb.dd(7), cb.dd(256), cb.dd(128)],
+    "gp": [cb.gp] * 3,
+    "nich": [cb.nich] * 4,
+    "mixed": [cb.bb, cb.gp, cb.nich, cb.dd(16), cb.bb, cb.nich],
+}
+
+
+@pytest.mark.parametrize("name", sorted(FAMILIES))
+@pytest.mark.parametrize("mask_frac", [0.0, 0.05])
+def test_score_rows_matches_oracle(ctx, oracle, name, mask_frac):
+    descs = FAMILIES[name]
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 700, 9, seed=3, mask_frac=mask_frac, extra_empty=2)
+    got_gids, S = st.score_rows()
+    assert got_gids == gids
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
+    assert S.shape == want.shape == (700, 11)
+    assert np.max(rel_err(S, want)) < RTOL
+    st.close()
+
+
+@pytest.mark.parametrize("v", ["1", "2", "4"])
+def test_all_kernel_widths_agree(ctx, oracle, v, monkeypatch):
+    monkeypatch.setenv("MSB_SCORE_V", v)
+    descs = FAMILIES["mixed"]
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 333, 37, seed=5, mask_frac=0.03)
+    _, S = st.score_rows()
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
+    assert np.max(rel_err(S, want)) < RTOL
+    _, S2 = st.score_rows(100, 101)  # a one-row range inside the table path
+    assert np.array_equal(S2[0], S[100])
+    st.close()
+
+
+def test_direct_and_table_paths_agree(ctx, oracle, monkeypatch):
+    descs = FAMILIES["mixed"]
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 200, 6, seed=8, mask_frac=0.1)
+    _, S = st.score_rows()
+    monkeypatch.setenv("MSB_FORCE_DIRECT", "1")
+    _, Sd = st.score_rows()
+    assert np.max(rel_err(S, Sd)) < 2e-6
+    st.close()
+
+
+@pytest.mark.parametrize("storage", [np.uint8, np.int16, np.int64, np.float64, np.uint32])
+def test_any_primitive_type_may_back_a_field(ctx, oracle, storage):
+    # runtime_cast (runtime_type.hpp:145-166): any of the 11 storage types -> the model's Value
+    descs = [cb.dd(9), cb.gp, cb.nich, cb.bb]
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 150, 4, seed=11, storage=[storage] * 4)
+    _, S = st.score_rows()
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
+    assert np.max(rel_err(S, want)) < RTOL
+    st.close()
+
+
+def test_suffstats_after_bulk_add_are_exact(ctx, oracle):
+    descs = FAMILIES["mixed"]
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 900, 5, seed=2, mask_frac=0.05)
+    off = 0
+    for d, desc in enumerate(descs):
+        m = oracle.model(desc)
+        w = oracle.ss_size(m)
+        for k, g in enumerate(gids):
+            ref = ss[k, off:off + w]
+            name = desc().name()
+            if name == "bb":
+                assert st.get_suffstats(d, g, "heads")[0] == ref[0] and st.get_suffstats(d, g, "tails")[0] == ref[1]
+            elif name == "dd":
+                assert st.get_suffstats(d, g, "count_sum")[0] == ref[0]
+                assert np.array_equal(st.get_suffstats(d, g, "counts", w - 1), ref[1:])
+            elif name == "gp":
+                assert st.get_suffstats(d, g, "count")[0] == ref[0] and st.get_suffstats(d, g, "sum")[0] == ref[1]
+                assert abs(st.get_suffstats(d, g, "log_prod")[0] - ref[2]) <= 1e-9 * max(1, abs(ref[2]))
+            elif name == "nich":
+                assert st.get_suffstats(d, g, "count")[0] == ref[0]
+                assert abs(st.get_suffstats(d, g, "mean")[0] - ref[1]) <= 1e-9 * max(1, abs(ref[1]))
+                assert abs(st.get_suffstats(d, g, "count_times_variance")[0] - ref[2]) <= 1e-8 * max(1, abs(ref[2]))
+        off += w
+    for k, g in enumerate(gids):
+        assert st.groupsize(g) == counts[k]
+    assert np.array_equal(st.assignments(), np.asarray(gids)[z])
+    st.close()
+
+
+def test_single_entity_calls_follow_entity_state(ctx, oracle):
+    # entity_state.hpp:57-72 on the device: remove_value / score_value / add_value of one entity
+    descs = [cb.bb, cb.nich, cb.dd(4), cb.gp]
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 60, 3, seed=4, extra_empty=1)
+    eid = 17
+    old = st.remove_value(eid)
+    assert old == gids[z[eid]] and st.assignments()[eid] == -1
+    with pytest.raises(cb.MsbError):
+        st.remove_value(eid)  # "entity not assigned", group_manager.hpp:238
+    zz = z.astype(np.int32).copy()
+    o = zz.copy(); nw = zz.copy(); nw[eid] = -1
+    oracle.update_rows(descs, hp, ss, counts, view, o, nw)
+    got_gids, s = st.score_value(eid)
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, eid, eid + 1)[0]
+    assert got_gids == gids and np.max(rel_err(s, want)) < RTOL
+    st.add_value(gids[3], eid)  # into the empty group
+    with pytest.raises(cb.MsbError):
+        st.add_value(gids[0], eid)  # "entity already assigned", group_manager.hpp:221
+    assert st.groupsize(gids[3]) == 1 and st.empty_groups() == []
+    o2 = nw.copy(); n2 = nw.copy(); n2[eid] = 3
+    oracle.update_rows(descs, hp, ss, counts, view, o2, n2)
+    _, S = st.score_rows()
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
+    assert np.max(rel_err(S, want)) < RTOL
+    st.close()
+
+
+def test_group_manager_bookkeeping(ctx):
+    # test/cxx/test_group_manager.cpp:22-47: create 7, delete gid 3, ids keep growing
+    st = cb.state(ctx, [cb.bb], max_groups=8, cluster_hp={"alpha": 2.0})
+    Y = np.zeros(10, dtype=[("", bool)])
+    st.bind(cb.numpy_dataview(Y))
+    gids = [st.create_group() for _ in range(7)]
+    assert gids == list(range(7)) and st.ngroups() == 7
+    st.delete_group(3)
+    assert st.groups() == [0, 1, 2, 4, 5, 6] and st.empty_groups() == [0, 1, 2, 4, 5, 6]
+    st.add_value(2, 0); st.add_value(2, 1); st.add_value(5, 2)
+    assert st.groupsize(2) == 2 and st.groupsize(5) == 1 and st.empty_groups() == [0, 1, 4, 6]
+    assert st.assignments().tolist() == [2, 2, 5] + [-1] * 7
+    with pytest.raises(cb.MsbError):
+        st.delete_group(2)  # "group not empty", group_manager.hpp:211
+    with pytest.raises(cb.MsbError):
+        st.groupsize(3)  # "invalid gid"
+    assert st.create_group() == 7  # gcount_ keeps counting (group_manager.hpp:199)
+    assert abs(st.get_cluster_hp()["alpha"] - 2.0) < 1e-12
+    with pytest.raises(cb.MsbError):
+        st.set_suffstats(0, 0, "nope", [1.0])  # unknown key, distributions.hpp:152
+    st.close()
+
+
+def test_sampler_bit_exact_given_same_scores_and_uniforms(ctx, oracle):
+    with open(os.path.join(GOLD, "sample_discrete_log.json")) as f:
+        for c in json.load(f)["cases"]:
+            got = cb.sample_discrete_log(ctx, np.asarray([c["scores"]], np.float32), [c["u"]])
+            assert got[0] == c["expect"]
+    rng = np.random.default_rng(0)
+    for K in (1, 2, 31, 200, 1000):
+        sc = (rng.normal(0, 4, size=(4096, K)) - rng.exponential(30, size=(4096, 1)) * (rng.random((4096, K)) < 0.1)).astype(np.float32)
+        sc[::7, K // 2] = -np.inf
+        u = rng.random(4096).astype(np.float32)
+        u[:3] = [0.0, np.float32(1.0) - np.float32(2 ** -24), 0.5]
+        assert np.array_equal(cb.sample_discrete_log(ctx, sc, u), oracle.sample_rows(sc, u)), K
+
+
+def test_philox_stream_matches_oracle(ctx, oracle):
+    u = cb.philox_uniforms(ctx, 73, 5, 1 << 33, 1000)
+    want = np.array([oracle.philox_u01(73, (1 << 33) + i, 5) for i in range(1000)], np.float32)
+    assert np.array_equal(u, want)
+
+
+@pytest.mark.parametrize("mask_frac", [0.0, 0.05])
+def test_sweep_assignments_and_counts_bit_exact(ctx, oracle, mask_frac):
+    descs = FAMILIES["mixed"]
+    n, k = 2000, 12
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=6, mask_frac=mask_frac, extra_empty=1)
+    for sweep in range(3):
+        old = (np.searchsorted(gids, st.assignments())).astype(np.int32)
+        res = st.sweep(seed=73, sweep=sweep)
+        assert res["rows"] == n and res["units"] == n * (k + 1) * len(descs)
+        new_gpu = np.searchsorted(gids, st.assignments()).astype(np.int32)
+        # checker: oracle scores (fp64 truth) are within tolerance of the GPU's, and the GPU's own
+        # score bits + the same Philox uniforms reproduce the draw exactly on the CPU
+        u = np.array([oracle.philox_u01(73, i, sweep) for i in range(n)], np.float32)
+        want_scores = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
+        gpu_scores = _last_sweep_scores(st, n, k + 1)
+        assert np.max(rel_err(gpu_scores, want_scores)) < RTOL
+        assert np.array_equal(new_gpu, oracle.sample_rows(gpu_scores, u))
+        assert res["moved"] == int((new_gpu != old).sum())
+        oracle.update_rows(descs, hp, ss, counts, view, old, new_gpu)
+        for c, g in enumerate(gids):
+            assert st.groupsize(g) == counts[c]
+        off = 0
+        for d, desc in enumerate(descs):
+            w = oracle.ss_size(oracle.model(desc))
+            nm = desc().name()
+            for c, g in enumerate(gids):
+                if nm == "bb":
+                    assert st.get_suffstats(d, g, "heads")[0] == ss[c, off] and st.get_suffstats(d, g, "tails")[0] == ss[c, off + 1]
+                elif nm == "dd":
+                    assert np.array_equal(st.get_suffstats(d, g, "counts", w - 1), ss[c, off + 1:off + w])
+                elif nm == "gp":
+                    assert st.get_suffstats(d, g, "count")[0] == ss[c, off] and st.get_suffstats(d, g, "sum")[0] == ss[c, off + 1]
+                elif nm == "nich":
+                    assert st.get_suffstats(d, g, "count")[0] == ss[c, off]
+                    assert abs(st.get_suffstats(d, g, "mean")[0] - ss[c, off + 1]) <= 1e-7 * max(1, abs(ss[c, off + 1]))
+            off += w
+    st.close()
+
+
+def _last_sweep_scores(st, n, k):
+    """host copy of the score matrix the last sweep sampled from"""
+    S = st.read_last_scores()
+    assert S.shape == (n, k)
+    return S
+
+
+def test_golden_vectors_through_the_value_abi(ctx):
+    # single-value plugin calls (models/base.hpp:27) against the committed golden vectors
+    import ctypes as C
+    from common_b200 import _lib
+    lib = _lib.load()
+    fam = {"bb": _lib.FAMILY_BB, "dd": _lib.FAMILY_DD, "gp": _lib.FAMILY_GP, "nich": _lib.FAMILY_NICH, "niw": _lib.FAMILY_NIW}
+    with open(os.path.join(GOLD, "score_value.json")) as f:
+        cases = json.load(f)["cases"]
+    for c in cases:
+        md = _lib.ModelDesc(fam[c["family"]], c["dim"])
+        hp = np.asarray(c["hp"], np.float64); ss = np.asarray(c["ss"], np.float64)
+        if c["family"] == "nich":
+            pass  # (count, mean, ctv) is the ABI representation for single values
+        x = np.asarray(c["x"], np.float64)
+        vt = _lib.RuntimeType(_lib.TYPE_F64, len(x), 1 if len(x) > 1 else 0)
+        out = C.c_float()
+        _lib.check(lib.msb_value_score(ctx.handle, C.byref(md), hp.ctypes.data_as(C.POINTER(C.c_double)), hp.size,
+                                       ss.ctypes.data_as(C.POINTER(C.c_double)), ss.size, x.ctypes.data, C.byref(vt), C.byref(out)))
+        tol = RTOL * (4 if c["family"] == "niw" else 1)
+        assert abs(out.value - c["expect"]) <= tol * max(1.0, abs(c["expect"])), (c["family"], c["source"], out.value, c["expect"])
+
+
+def test_value_add_remove_roundtrip(ctx, oracle):
+    import ctypes as C
+    from common_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    for desc, draw in [(cb.bb, lambda: [float(rng.integers(0, 2))]), (cb.dd(6), lambda: [float(rng.integers(0, 6))]),
+                       (cb.gp, lambda: [float(rng.poisson(5))]), (cb.nich, lambda: [float(rng.normal())]),
+                       (cb.niw(3), lambda: rng.normal(size=3).tolist())]:
+        md = desc().c_desc()
+        m = oracle.model(desc)
+        hp = oracle.flat_hp(desc)
+        ss = np.zeros(oracle.ss_size(m)); ref = ss.copy()
+        xs = [draw() for _ in range(12)]
+        for x in xs:
+            xa = np.asarray(x, np.float64)
+            vt = _lib.RuntimeType(_lib.TYPE_F64, len(x), 1 if len(x) > 1 else 0)
+            _lib.check(lib.msb_value_add(ctx.handle, C.byref(md), hp.ctypes.data_as(C.POINTER(C.c_double)), hp.size,
+                                         ss.ctypes.data_as(C.POINTER(C.c_double)), ss.size, xa.ctypes.data, C.byref(vt)))
+            oracle.add_value(m, hp, ref, x)
+        np.testing.assert_allclose(ss, ref, rtol=1e-9, atol=1e-9)
+        for x in reversed(xs):
+            xa = np.asarray(x, np.float64)
+            vt = _lib.RuntimeType(_lib.TYPE_F64, len(x), 1 if len(x) > 1 else 0)
+            _lib.check(lib.msb_value_remove(ctx.handle, C.byref(md), hp.ctypes.data_as(C.POINTER(C.c_double)), hp.size,
+                                            ss.ctypes.data_as(C.POINTER(C.c_double)), ss.size, xa.ctypes.data, C.byref(vt)))
+        assert ss[0] == 0
+        np.testing.assert_allclose(ss, 0, atol=1e-9)
+
+
+@pytest.mark.parametrize("dim,n,k", [(3, 300, 4), (8, 500, 5), (64, 600, 6)])
+def test_niw_scores_match_oracle(ctx, oracle, dim, n, k):
+    descs = [cb.niw(dim)]
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=9, extra_empty=1)
+    _, S = st.score_rows()
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
+    assert np.max(rel_err(S, want)) < 4 * RTOL
+    st.close()
+
+
+def test_niw_mixed_with_scalars_and_masks(ctx, oracle):
+    descs = [cb.nich, cb.niw(4), cb.bb]
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 400, 5, seed=10, mask_frac=0.1)
+    _, S = st.score_rows()
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
+    assert np.max(rel_err(S, want)) < 4 * RTOL
+    res = st.sweep(seed=1, sweep=0)
+    assert res["rows"] == 400
+    st.close()
+
+
+def test_dataview_roundtrip_on_device(ctx):
+    # test/test_dataview.py:31-46 through the device copy: dataview::get(idx) returns the same record
+    Y = np.array([(True, 2, 3.5, [1.0, 2.0]), (False, 7, -1.0, [3.0, 4.0])],
+                 dtype=[("", bool), ("", np.int32), ("", np.float32), ("", np.float64, (2,))])
+    view = cb.numpy_dataview(Y)
+    dev = view.to_device(ctx)
+    assert dev.size() == 2 and dev.rowsize() == (1 + 4 + 4 + 16, 5)
+    for i in range(2):
+        row, msk = dev.get_row_bytes(i)
+        assert row.tobytes() == Y[i].tobytes() and not msk.any()
+    with pytest.raises(cb.MsbError):
+        dev.get_row_bytes(2)  # "invalid position", dataview.cpp:131
+
+
+def test_empty_and_ragged_inputs(ctx, oracle):
+    st = cb.state(ctx, [cb.bb, cb.nich], max_groups=4)
+    empty = np.zeros(0, dtype=[("", bool), ("", np.float32)])
+    st.bind(cb.numpy_dataview(empty))
+    st.create_group()
+    assert st.nentities() == 0 and st.assignments().size == 0
+    assert st.sweep()["rows"] == 0
+    gids, S = st.score_rows()
+    assert S.shape == (0, 1)
+    st.close()
+    # sizes that are not multiples of any tile: 1 row, 33 groups, 1 feature
+    descs = [cb.dd(3)]
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 33, 33, seed=12)
+    _, S = st.score_rows(32, 33)
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, 32, 33)
+    assert np.max(rel_err(S, want)) < RTOL
+    st.close()
+    with pytest.raises(cb.MsbError):
+        cb.state(ctx, [cb.nich], max_groups=2).bind(cb.numpy_dataview(np.zeros(3, dtype=[("", np.float32, (2,))])))
+
+
+def test_large_group_counts_stay_accurate(ctx, oracle):
+    # 8000 rows per group (the BASELINE C3 regime): float log(1+z) would lose 1e-3 per feature here
+    descs = [cb.nich] * 8 + [cb.gp] * 4
+    n, k = 40000, 5
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=13)
+    _, S = st.score_rows(0, 512)
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, 0, 512)
+    assert np.max(rel_err(S, want)) < RTOL
+    st.close()
