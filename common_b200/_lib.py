@@ -9,6 +9,7 @@ There is no fallback: if the CUDA library is missing this module raises.
 """
 import ctypes as C
 import os
+import weakref
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmscope_b200.so")
@@ -142,10 +143,16 @@ class Context:
         check(lib.msb_ctx_create(int(device), _P(stream) if stream else None, C.byref(h)))
         self._h = h
         self.device = int(device)
+        self._children = weakref.WeakSet()  # states / dataviews that must be released before the context
 
     @property
     def handle(self):
+        if not self._h:
+            raise MsbError(MSB_ERR_STATE, "context is closed")
         return self._h
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     def synchronize(self):
         check(load().msb_ctx_synchronize(self._h))
@@ -160,6 +167,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for child in list(self._children):
+                child.close()
             load().msb_ctx_destroy(self._h)
             self._h = None
 

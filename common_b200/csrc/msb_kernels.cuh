@@ -544,6 +544,12 @@ __global__ void apply_delta_kernel(double *__restrict__ ss, double *__restrict__
   if (i < n) { ss[i] += delta[i]; delta[i] = 0.0; }
 }
 
+// scores[r][c] = base[c]: the CRP term, when no scalar feature kernel initialises the matrix
+__global__ void fill_rows_kernel(float *__restrict__ scores, size_t ld, const float *__restrict__ base, size_t nrows) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nrows * ld) scores[i] = base[i % ld];
+}
+
 // gid <-> slot translation of the assignment vector
 __global__ void map_i32_to_i64_kernel(const int32_t *__restrict__ in, const int64_t *__restrict__ table, size_t n,
                                       int64_t *__restrict__ out) {

@@ -149,8 +149,8 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   CU_TRY(opt_in_smem(score_kernel<1, 32>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<2, 32>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<4, 16>, c->smem_optin));
-  CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin));
-  CU_TRY(opt_in_smem(niw_score_simt_kernel, c->smem_optin));
+  CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin - 1024));  // it also has a few bytes of static shared memory
+  CU_TRY(opt_in_smem(niw_score_simt_kernel, c->smem_optin - 1024));
   MSB_TRY(niw_tc_init(c->smem_optin, g_last_error));
   *out = c;
   return MSB_OK;
@@ -800,10 +800,7 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
     }
   } else {
     // no scalar feature: scores start from the CRP term
-    for (size_t r0 = 0; r0 < nrows; r0 += 65535) {
-      const size_t nr = std::min<size_t>(65535, nrows - r0);
-      CU_TRY(cudaMemcpy2DAsync(scores + r0 * st->ld, sizeof(float) * st->ld, st->d_base, 0, sizeof(float) * st->ld, nr, cudaMemcpyDeviceToDevice, ctx->stream));
-    }
+    LAUNCH(ctx, fill_rows_kernel, cdiv(nrows * st->ld, 256), 256, 0, scores, st->ld, st->d_base, nrows);
   }
   for (size_t d = 0; d < st->D; d++) {
     const FeatDev &f = st->feats[d];

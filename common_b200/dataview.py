@@ -150,6 +150,7 @@ class device_dataview(object):
         self._h = h
         self._n = n
         self._types = list(types)
+        ctx._adopt(self)
 
     @property
     def handle(self):

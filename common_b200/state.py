@@ -26,6 +26,7 @@ class state(object):
         _lib.check(_lib.load().msb_state_create(ctx.handle, descs, len(self._models), int(max_groups), C.byref(h)))
         self._h = h
         self._view = None
+        ctx._adopt(self)
         if cluster_hp is not None:
             self.set_cluster_hp(cluster_hp)
 
