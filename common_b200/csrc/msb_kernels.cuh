@@ -143,134 +143,6 @@ __global__ void build_params_kernel(const FeatDev *__restrict__ feats, int nfeat
 }
 
 // ---------------------------------------------------------------------------
-// Score kernel.  One warp owns RW rows; lane l owns V consecutive groups of the
-// block's k-tile (KT = 32 V), so a (row, feature) lookup is one conflict-free
-// shared-memory read of 128 V bytes per warp and the value x is warp-uniform
-// (broadcast from the lane that loaded it).  Accumulators acc[RW][V] stay in
-// registers across all features; the N x K result is written once, coalesced.
-// ---------------------------------------------------------------------------
-template <int V> struct VecF;
-template <> struct VecF<1> { float v[1]; __device__ void load(const float *p) { v[0] = *p; } };
-template <> struct VecF<2> { float v[2]; __device__ void load(const float *p) { const float2 t = *(const float2 *)p; v[0] = t.x; v[1] = t.y; } };
-template <> struct VecF<4> { float v[4]; __device__ void load(const float *p) { const float4 t = *(const float4 *)p; v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
-
-template <int V>
-__device__ __forceinline__ void store_vec(float *p, const float *a) {
-  if constexpr (V == 1) *p = a[0];
-  else if constexpr (V == 2) *(float2 *)p = make_float2(a[0], a[1]);
-  else *(float4 *)p = make_float4(a[0], a[1], a[2], a[3]);
-}
-
-constexpr int SCORE_WARPS = 8;
-
-template <int V, int RW>
-__global__ void __launch_bounds__(SCORE_WARPS * 32)
-score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restrict__ params, size_t region_rows,
-             const float *__restrict__ base, float *__restrict__ scores, size_t ld, size_t row_lo, size_t row_hi) {
-  constexpr int KT = 32 * V;
-  extern __shared__ float4 smem4[];
-  float *smem = reinterpret_cast<float *>(smem4);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t row0 = row_lo + ((size_t)blockIdx.x * SCORE_WARPS + warp) * RW;
-  const int kt = blockIdx.y;
-  const float *region = params + (size_t)kt * region_rows * KT;
-  const size_t myrow = row0 + lane;
-  const bool valid = lane < RW && myrow < row_hi;
-
-  float acc[RW][V];
-#pragma unroll
-  for (int r = 0; r < RW; r++)
-#pragma unroll
-    for (int v = 0; v < V; v++) acc[r][v] = 0.f;
-
-  for (int d = 0; d < nfeat; d++) {
-    const FeatDev f = feats[d];
-    if (f.rows == 0) continue;
-    // this lane's row value for feature d (global load issued before the chunk copy)
-    uint32_t xi = f.ncat;
-    float xf = CUDART_NAN_F;
-    if (valid) {
-      if (f.coltype == COL_U8) xi = ((const uint8_t *)f.col)[myrow];
-      else if (f.coltype == COL_U16) xi = ((const uint16_t *)f.col)[myrow];
-      else if (f.coltype == COL_U32) xi = ((const uint32_t *)f.col)[myrow];
-      else xf = ((const float *)f.col)[myrow];
-    } else if (f.kind == KIND_GP) {
-      xi = GP_SENTINEL;
-    }
-    __syncthreads();  // previous chunk fully consumed
-    {
-      const float4 *src = reinterpret_cast<const float4 *>(region + (size_t)f.rowoff * KT);
-      const int n4 = (int)f.rows * (KT / 4);
-      for (int i = threadIdx.x; i < n4; i += SCORE_WARPS * 32) smem4[i] = src[i];
-    }
-    __syncthreads();
-    if (f.kind == KIND_TABLE) {
-#pragma unroll
-      for (int r = 0; r < RW; r++) {
-        const uint32_t x = __shfl_sync(0xffffffffu, xi, r);
-        VecF<V> t;
-        t.load(smem + (size_t)x * KT + lane * V);
-#pragma unroll
-        for (int v = 0; v < V; v++) acc[r][v] += t.v[v];
-      }
-    } else if (f.kind == KIND_GP) {
-      const uint32_t cap = f.ncat;
-      const uint32_t xrow = xi == GP_SENTINEL ? cap : (xi < cap ? xi : cap + 1);
-#pragma unroll
-      for (int r = 0; r < RW; r++) {
-        const uint32_t x = __shfl_sync(0xffffffffu, xrow, r);
-        if (x <= cap) {
-          VecF<V> t;
-          t.load(smem + (size_t)x * KT + lane * V);
-#pragma unroll
-          for (int v = 0; v < V; v++) acc[r][v] += t.v[v];
-        } else {  // count beyond the table: evaluate the closed form (rare)
-          const float xv = (float)__shfl_sync(0xffffffffu, xi, r);
-          const float lgx1 = lgammaf(xv + 1.f);
-#pragma unroll
-          for (int v = 0; v < V; v++) {
-            const float a = smem[(size_t)(cap + 1) * KT + lane * V + v];
-            const float ca = smem[(size_t)(cap + 2) * KT + lane * V + v];
-            const float l1pb = smem[(size_t)(cap + 3) * KT + lane * V + v];
-            acc[r][v] += lgammaf(a + xv) - lgx1 + ca - xv * l1pb;
-          }
-        }
-      }
-    } else {  // KIND_NICH
-      VecF<V> mu, s, c1, c0;
-      mu.load(smem + 0 * KT + lane * V);
-      s.load(smem + 1 * KT + lane * V);
-      c1.load(smem + 2 * KT + lane * V);
-      c0.load(smem + 3 * KT + lane * V);
-#pragma unroll
-      for (int r = 0; r < RW; r++) {
-        const float x = __shfl_sync(0xffffffffu, xf, r);
-        if (x == x) {
-#pragma unroll
-          for (int v = 0; v < V; v++) {
-            const float t = (x - mu.v[v]) * s.v[v];
-            acc[r][v] += fmaf(c1.v[v], log1p_pos(t * t), c0.v[v]);
-          }
-        }
-      }
-    }
-  }
-  // epilogue: + log(pseudocount) (group_manager.hpp:274-283), coalesced 128 V-byte stores
-  VecF<V> b;
-  b.load(base + (size_t)kt * KT + lane * V);
-#pragma unroll
-  for (int r = 0; r < RW; r++) {
-    const size_t row = row0 + r;
-    if (row < row_hi) {
-      float o[V];
-#pragma unroll
-      for (int v = 0; v < V; v++) o[v] = acc[r][v] + b.v[v];
-      store_vec<V>(scores + (row - row_lo) * ld + (size_t)kt * KT + lane * V, o);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
 // Direct scorer: closed forms straight from the suffstats in fp64, no tables.
 // Used for single-entity score_value (entity_state.hpp:60-72) and as an
 // independent on-device cross-check of the table path.  Scalar families only.

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "msb_kernels.cuh"
+#include "msb_score.cuh"
 #include "msb_niw_tc.cuh"
 
 using namespace msb;
@@ -70,6 +71,8 @@ struct msb_state {
   std::vector<msb_model_desc> models;
   std::vector<FeatDev> feats;
   FeatDev *d_feats = nullptr;
+  FeatDev *d_feats_scalar = nullptr;  // the features the score kernel walks (chunk rows > 0), same order
+  size_t n_scalar = 0;
   bool feats_dirty = true;
   // hypers
   std::vector<double> h_hp;
@@ -104,7 +107,7 @@ struct msb_state {
   std::vector<float *> d_niwW, d_niwBias, d_niwCoef, d_niwB;
   size_t niw_cols_cap = 0;
   // last score
-  int V = 2; size_t ld = 0, last_rows = 0, last_cols = 0;
+  int cfg = 1, V = 2; size_t ld = 0, last_rows = 0, last_cols = 0;
   std::vector<int32_t> h_col2slot;
   std::vector<size_t> h_colgid;
   std::vector<PhaseEvents> events;
@@ -146,9 +149,10 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   c->smem_optin = prop.sharedMemPerBlockOptin;
   if (stream) c->stream = (cudaStream_t)stream;
   else { CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-  CU_TRY(opt_in_smem(score_kernel<1, 32>, c->smem_optin));
-  CU_TRY(opt_in_smem(score_kernel<2, 32>, c->smem_optin));
-  CU_TRY(opt_in_smem(score_kernel<4, 16>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 64, 16>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<2, 32, 16>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<4, 32, 8>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 32, 8>, c->smem_optin));
   CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin - 1024));  // it also has a few bytes of static shared memory
   CU_TRY(opt_in_smem(niw_score_simt_kernel, c->smem_optin - 1024));
   MSB_TRY(niw_tc_init(c->smem_optin, g_last_error));
@@ -402,6 +406,7 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
     }
   }
   CU_TRY(cudaMalloc(&st->d_feats, sizeof(FeatDev) * nfeatures));
+  CU_TRY(cudaMalloc(&st->d_feats_scalar, sizeof(FeatDev) * nfeatures));
   CU_TRY(cudaMalloc(&st->d_hp, sizeof(double) * std::max<size_t>(hpo, 1)));
   CU_TRY(cudaMalloc(&st->d_ss, sizeof(double) * st->SS));
   CU_TRY(cudaMalloc(&st->d_delta, sizeof(double) * st->SS));
@@ -425,7 +430,7 @@ extern "C" MSB_API int msb_state_destroy(msb_state *st) {
   cudaStreamSynchronize(st->ctx->stream);
   for (void *c : st->cols) cudaFree(c);
   for (size_t d = 0; d < st->D; d++) { cudaFree(st->d_niwW[d]); cudaFree(st->d_niwBias[d]); cudaFree(st->d_niwCoef[d]); cudaFree(st->d_niwB[d]); }
-  cudaFree(st->d_feats); cudaFree(st->d_hp); cudaFree(st->d_ss); cudaFree(st->d_delta); cudaFree(st->d_counter);
+  cudaFree(st->d_feats); cudaFree(st->d_feats_scalar); cudaFree(st->d_hp); cudaFree(st->d_ss); cudaFree(st->d_delta); cudaFree(st->d_counter);
   cudaFree(st->d_slot2gid); cudaFree(st->d_assign); cudaFree(st->d_params); cudaFree(st->d_scores);
   cudaFree(st->d_base); cudaFree(st->d_col2slot); cudaFree(st->d_newslot); cudaFree(st->d_newcol); cudaFree(st->d_uniforms);
   for (auto &pe : st->events) for (auto &e : pe.e) cudaEventDestroy(e);
@@ -440,6 +445,11 @@ static int sync_small(msb_state *st) {  // upload hypers / feature descriptors i
   }
   if (st->feats_dirty) {
     CU_TRY(cudaMemcpyAsync(st->d_feats, st->feats.data(), sizeof(FeatDev) * st->D, cudaMemcpyHostToDevice, st->ctx->stream));
+    std::vector<FeatDev> sc;
+    for (const auto &f : st->feats) if (f.rows > 0) sc.push_back(f);
+    st->n_scalar = sc.size();
+    if (!sc.empty())
+      CU_TRY(cudaMemcpy(st->d_feats_scalar, sc.data(), sizeof(FeatDev) * sc.size(), cudaMemcpyHostToDevice));
     st->feats_dirty = false;
   }
   // the host vectors are pageable: the copies above have completed on return
@@ -704,16 +714,23 @@ static int ensure_rows(msb_state *st, size_t nrows) {
   return MSB_OK;
 }
 
-static int choose_v(const msb_state *st, size_t ncols) {
-  if (const char *e = getenv("MSB_SCORE_V")) {
-    const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4) return v;
+// Score-kernel shapes (V groups per lane, RW rows per warp, NW warps per block):
+//   0: V=1 RW=64 NW=16  1024 rows x 32 groups  -- big tables (dd with many categories): the table chunk is
+//                                                 re-read from L2 once per block, so maximise rows per block
+//   1: V=2 RW=32 NW=16   512 rows x 64 groups
+//   2: V=4 RW=32 NW=8    256 rows x 128 groups -- small chunks, many groups: fewest instructions per lookup
+//   3: V=1 RW=32 NW=8    256 rows x 32 groups  -- K <= 32
+struct ScoreCfg { int V, RW, NW; };
+static const ScoreCfg k_score_cfgs[4] = {{1, 64, 16}, {2, 32, 16}, {4, 32, 8}, {1, 32, 8}};
+
+static int choose_cfg(const msb_state *st, size_t ncols) {
+  if (const char *e = getenv("MSB_SCORE_CFG")) {
+    const int c = atoi(e);
+    if (c >= 0 && c < 4) return c;
   }
-  const size_t budget = 96 * 1024;  // per-chunk shared memory we are willing to spend
-  auto fits = [&](int v) { return st->max_chunk_rows * 32 * v * sizeof(float) <= budget; };
-  if (ncols <= 32) return 1;
-  if (ncols >= 256 && fits(4)) return 4;
-  if (fits(2)) return 2;
+  if (ncols <= 32) return 3;
+  if (st->max_chunk_rows >= 128) return 0;
+  if (ncols >= 256) return 2;
   return 1;
 }
 
@@ -723,7 +740,8 @@ static int prepare_columns(msb_state *st) {
   msb_ctx *ctx = st->ctx;
   const size_t K = st->gid2slot.size();
   REQUIRE(K > 0, "no groups");
-  st->V = choose_v(st, K);
+  st->cfg = choose_cfg(st, K);
+  st->V = k_score_cfgs[st->cfg].V;
   const size_t KT = 32 * (size_t)st->V;
   st->ld = (K + KT - 1) / KT * KT;
   st->h_col2slot.resize(K); st->h_colgid.resize(K);
@@ -786,18 +804,23 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
   const size_t KT = 32 * (size_t)st->V;
   const size_t ktiles = st->ld / KT;
   if (st->has_scalar) {
-    const size_t smem = std::max<size_t>(st->max_chunk_rows * KT * sizeof(float), 16);
-    if (smem > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "parameter chunk does not fit in shared memory");
-    if (st->V == 1) {
-      dim3 grid(cdiv(nrows, SCORE_WARPS * 32), (unsigned)ktiles);
-      LAUNCH(ctx, (score_kernel<1, 32>), grid, SCORE_WARPS * 32, smem, st->d_feats, (int)st->D, st->d_params, st->region_rows, st->d_base, scores, st->ld, row_lo, row_hi);
-    } else if (st->V == 2) {
-      dim3 grid(cdiv(nrows, SCORE_WARPS * 32), (unsigned)ktiles);
-      LAUNCH(ctx, (score_kernel<2, 32>), grid, SCORE_WARPS * 32, smem, st->d_feats, (int)st->D, st->d_params, st->region_rows, st->d_base, scores, st->ld, row_lo, row_hi);
-    } else {
-      dim3 grid(cdiv(nrows, SCORE_WARPS * 16), (unsigned)ktiles);
-      LAUNCH(ctx, (score_kernel<4, 16>), grid, SCORE_WARPS * 32, smem, st->d_feats, (int)st->D, st->d_params, st->region_rows, st->d_base, scores, st->ld, row_lo, row_hi);
+    const ScoreCfg c = k_score_cfgs[st->cfg];
+    const size_t stage = (st->max_chunk_rows * KT * sizeof(float) + 127) / 128 * 128;
+    const size_t fixed = st->D * sizeof(FeatS) + 2 * 8 * sizeof(uint64_t) + (size_t)c.NW * c.RW * sizeof(uint32_t) + 256;
+    if (stage + fixed > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "parameter chunk does not fit in shared memory");
+    const int S = (int)std::max<size_t>(1, std::min<size_t>(4, (ctx->smem_optin - fixed) / stage));
+    const size_t smem = (size_t)S * stage + fixed;
+    dim3 grid(cdiv(nrows, (size_t)c.NW * c.RW), (unsigned)ktiles);
+#define MSB_SCORE_LAUNCH(V_, RW_, NW_)                                                                              \
+    LAUNCH(ctx, (score_kernel<V_, RW_, NW_>), grid, NW_ * 32, smem, st->d_feats_scalar, (int)st->n_scalar, st->d_params, \
+           st->region_rows, (uint32_t)stage, S, st->d_base, scores, st->ld, row_lo, row_hi)
+    switch (st->cfg) {
+      case 0: MSB_SCORE_LAUNCH(1, 64, 16); break;
+      case 1: MSB_SCORE_LAUNCH(2, 32, 16); break;
+      case 2: MSB_SCORE_LAUNCH(4, 32, 8); break;
+      default: MSB_SCORE_LAUNCH(1, 32, 8); break;
     }
+#undef MSB_SCORE_LAUNCH
   } else {
     // no scalar feature: scores start from the CRP term
     LAUNCH(ctx, fill_rows_kernel, cdiv(nrows * st->ld, 256), 256, 0, scores, st->ld, st->d_base, nrows);

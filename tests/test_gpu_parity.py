@@ -63,11 +63,11 @@ def test_score_rows_matches_oracle(ctx, oracle, name, mask_frac):
     st.close()
 
 
-@pytest.mark.parametrize("v", ["1", "2", "4"])
-def test_all_kernel_widths_agree(ctx, oracle, v, monkeypatch):
-    monkeypatch.setenv("MSB_SCORE_V", v)
+@pytest.mark.parametrize("v", ["0", "1", "2", "3"])
+def test_all_kernel_shapes_agree(ctx, oracle, v, monkeypatch):
+    monkeypatch.setenv("MSB_SCORE_CFG", v)
     descs = FAMILIES["mixed"]
-    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 333, 37, seed=5, mask_frac=0.03)
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 1333, 37, seed=5, mask_frac=0.03)
     _, S = st.score_rows()
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
     assert np.max(rel_err(S, want)) < RTOL
