@@ -318,6 +318,41 @@ __global__ void sample_kernel(const float *__restrict__ scores, size_t ld, int K
   if (out_slot) out_slot[i] = col2slot ? col2slot[pick] : pick;
 }
 
+// The same walk over the blocked layout the sweep's score kernel writes (msb_score.cuh): thread =
+// row, element k of the row at s[k * 32]; every load is a fully coalesced 128-byte warp access.
+__global__ void sample_blocked_kernel(const float *__restrict__ scores, size_t ld, int K, size_t nrows,
+                                      const float *__restrict__ uniforms, uint64_t seed, uint64_t sweep,
+                                      uint64_t row_id0, const int32_t *__restrict__ col2slot,
+                                      int32_t *__restrict__ out_col, int32_t *__restrict__ out_slot) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const float *s = scores + (i / 32) * ld * 32 + (i % 32);
+  float m = s[0];
+#pragma unroll 8
+  for (int k = 1; k < K; k++) m = fmaxf(m, s[(size_t)k * 32]);
+  double acc_d = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < K; k++) acc_d = __dadd_rn(acc_d, (double)msb_expf(__fsub_rn(s[(size_t)k * 32], m)));
+  const float acc = __double2float_rn(acc_d);
+  float dart = uniforms ? uniforms[i] : philox_u01(seed, row_id0 + i, sweep);
+  int pick = K - 1;
+  for (int k = 0; k < K; k++) {
+    const float p = __fdiv_rn(msb_expf(__fsub_rn(s[(size_t)k * 32], m)), acc);
+    dart = __fsub_rn(dart, p);
+    if (dart <= 0.f) { pick = k; break; }
+  }
+  if (out_col) out_col[i] = pick;
+  if (out_slot) out_slot[i] = col2slot ? col2slot[pick] : pick;
+}
+
+// blocked -> row-major copy of a score matrix (diagnostics / tests)
+__global__ void unblock_kernel(const float *__restrict__ blocked, size_t ld, size_t nrows, int K, float *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows * (size_t)K) return;
+  const size_t row = i / K, col = i % K;
+  out[i] = blocked[((row / 32) * ld + col) * 32 + (row % 32)];
+}
+
 __global__ void philox_fill_kernel(uint64_t seed, uint64_t sweep, uint64_t row0, size_t n, float *out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = philox_u01(seed, row0 + i, sweep);

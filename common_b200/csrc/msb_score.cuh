@@ -74,19 +74,31 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                : "memory");
 }
 
-template <int V, int RW, int NW>
+// gp count beyond the lookup table: fp64 closed form straight from the suffstats.  Kept out of line so
+// that its fp64 register pressure stays off the hot loop.
+__device__ __noinline__ float gp_overflow_score(const FeatDev *f, const double *hp, const double *ss, int slot, double xv) {
+  return (float)gp_score(gp_post(hp + f->hp_off, ss + f->ss_off + (size_t)slot * f->ss_w), xv);
+}
+
+// Output layouts of the N x K score matrix:
+//   row-major   scores[(row - row_lo) * ld + col]                     (the API's observable output)
+//   blocked     scores[((row - row_lo) / 32 * ld + col) * 32 + (row - row_lo) % 32]
+//               32-row blocks, group-major inside a block: the sampler walks one row per thread and
+//               reads it fully coalesced.  Internal to the sweep.
+template <int V, int RW, int NW, bool BLOCKED>
 __global__ void __launch_bounds__(NW * 32, 1)
 score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restrict__ params, size_t region_rows,
              uint32_t stage_bytes, int S, const float *__restrict__ base, float *__restrict__ scores, size_t ld,
-             size_t row_lo, size_t row_hi) {
+             size_t row_lo, size_t row_hi, const double *__restrict__ hp, const double *__restrict__ ss,
+             const int32_t *__restrict__ col2slot, int ncols) {
   constexpr int KT = 32 * V;
   constexpr int RL = RW / 32;  // rows per lane whose x this lane loads
   static_assert(RW % 32 == 0, "RW must be a multiple of 32");
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [S stages | per-warp exchange buffers (double) | mbarriers full[S], empty[S] | feature table]
   unsigned char *stages = smem_raw;
-  // layout: [S stages | per-warp exchange buffers | mbarriers full[S], empty[S] | feature table]
   uint32_t *xbuf_all = reinterpret_cast<uint32_t *>(smem_raw + (size_t)S * stage_bytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(xbuf_all + NW * RW);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(xbuf_all + 2 * NW * RW);
   FeatS *ftab = reinterpret_cast<FeatS *>(bars + 2 * S);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kt = blockIdx.y;
@@ -109,29 +121,48 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
   }
   __syncthreads();
 
-  auto issue = [&](int d) {  // thread 0 only: chunk of feature d -> stage d % S
+  auto issue = [&](int d, int s) {  // thread 0 only: chunk of feature d -> stage s
     const FeatS t = ftab[d];
     const uint32_t bytes = t.rows * (uint32_t)(KT * sizeof(float));
-    const uint32_t bar = smem_u32(&bars[d % S]);
+    const uint32_t bar = smem_u32(&bars[s]);
     mbar_expect_tx(bar, bytes);
-    bulk_g2s(smem_u32(stages + (size_t)(d % S) * stage_bytes), region + (size_t)t.rowoff * KT, bytes, bar);
+    bulk_g2s(smem_u32(stages + (size_t)s * stage_bytes), region + (size_t)t.rowoff * KT, bytes, bar);
   };
   if (tid == 0)
-    for (int d = 0; d < S && d < nfeat; d++) issue(d);
+    for (int d = 0; d < S && d < nfeat; d++) issue(d, d);
 
-  auto load_x = [&](int d, uint32_t (&xi)[RL], float (&xf)[RL]) {
+  // raw value of this lane's rows for feature d (bit pattern: table index, count, or float)
+  auto load_x = [&](int d, uint32_t (&x)[RL]) {
     const FeatS t = ftab[d];
 #pragma unroll
     for (int j = 0; j < RL; j++) {
       const size_t row = row0 + j * 32 + lane;
-      xi[j] = t.kind == KIND_GP ? GP_SENTINEL : t.ncat;
-      xf[j] = CUDART_NAN_F;
+      x[j] = t.kind == KIND_GP ? GP_SENTINEL : (t.kind == KIND_NICH ? 0x7fc00000u : t.ncat);
       if (row < row_hi) {
-        if (t.coltype == COL_U8) xi[j] = ((const uint8_t *)t.col)[row];
-        else if (t.coltype == COL_U16) xi[j] = ((const uint16_t *)t.col)[row];
-        else if (t.coltype == COL_U32) xi[j] = ((const uint32_t *)t.col)[row];
-        else xf[j] = ((const float *)t.col)[row];
+        if (t.coltype == COL_U8) x[j] = ((const uint8_t *)t.col)[row];
+        else if (t.coltype == COL_U16) x[j] = ((const uint16_t *)t.col)[row];
+        else x[j] = ((const uint32_t *)t.col)[row];  // u32 counts and f32 values alike
       }
+    }
+  };
+  // Per-warp exchange buffer: each lane publishes the table offset (x * KT, in floats) or the float
+  // value of the rows it loaded; every lane then reads all RW of them back as broadcast 128-bit
+  // shared loads (4 rows per wavefront).  Published one feature ahead, into the other half.
+  uint32_t *xbuf = xbuf_all + warp * 2 * RW;
+  // (gp counts beyond the table publish the zero row and are flagged in a per-32-row ballot mask)
+  auto publish = [&](int d, const uint32_t (&x)[RL], uint32_t (&ovf)[RL]) {
+    const FeatS t = ftab[d];
+#pragma unroll
+    for (int j = 0; j < RL; j++) {
+      uint32_t pub = x[j];
+      bool over = false;
+      if (t.kind == KIND_GP) {
+        const uint32_t cap = t.ncat;
+        over = x[j] != GP_SENTINEL && x[j] >= cap;
+        pub = (x[j] < cap ? x[j] : cap) * KT;
+      } else if (t.kind == KIND_TABLE) pub = x[j] * KT;
+      xbuf[(d & 1) * RW + j * 32 + lane] = pub;
+      ovf[j] = t.kind == KIND_GP ? __ballot_sync(0xffffffffu, over) : 0u;
     }
   };
 
@@ -141,41 +172,26 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
 #pragma unroll
     for (int v = 0; v < V; v++) acc[r][v] = 0.f;
 
-  // Per-warp exchange buffer: each lane publishes the table offset (x * KT, in floats) or the float
-  // value of the rows it loaded; every lane then reads all RW of them back as broadcast 128-bit
-  // shared loads (4 rows per wavefront).  A per-row warp shuffle would cost one crossbar
-  // wavefront per row -- as much as the lookup itself.
-  uint32_t *xbuf = xbuf_all + warp * RW;
-
-  uint32_t xi[RL], xi_next[RL];
-  float xf[RL], xf_next[RL];
-  if (nfeat > 0) load_x(0, xi, xf);
+  uint32_t xa[RL], xb[RL];  // xa: feature d+1 (to publish this iteration), xb: feature d+2 (in flight)
+  uint32_t ovf_cur[RL], ovf_next[RL];
+#pragma unroll
+  for (int j = 0; j < RL; j++) ovf_cur[j] = ovf_next[j] = 0u;
+  if (nfeat > 0) { load_x(0, xa); publish(0, xa, ovf_cur); }
+  if (nfeat > 1) load_x(1, xa);
+  int s = 0;
+  uint32_t parity = 0;
 
   for (int d = 0; d < nfeat; d++) {
-    if (d + 1 < nfeat) load_x(d + 1, xi_next, xf_next);  // prefetch the next feature's values
+    if (d + 2 < nfeat) load_x(d + 2, xb);               // global loads two features ahead
+    if (d + 1 < nfeat) publish(d + 1, xa, ovf_next);    // shared-memory publish one feature ahead
     const FeatS t = ftab[d];
-    const int s = d % S;
-    const uint32_t parity = (uint32_t)(d / S) & 1u;
-    bool overflow = false;
-    __syncwarp();  // the previous feature's reads of xbuf are done
-#pragma unroll
-    for (int j = 0; j < RL; j++) {
-      uint32_t pub;
-      if (t.kind == KIND_NICH) pub = __float_as_uint(xf[j]);
-      else if (t.kind == KIND_GP) {
-        const uint32_t cap = t.ncat;
-        const uint32_t xr = xi[j] == GP_SENTINEL ? cap : (xi[j] < cap ? xi[j] : cap + 1);
-        overflow |= xr > cap;
-        pub = xr * KT;
-      } else pub = xi[j] * KT;
-      xbuf[j * 32 + lane] = pub;
-    }
-    __syncwarp();
+    __syncwarp();  // feature d's publish (previous iteration) is visible to the whole warp
     mbar_wait(smem_u32(&bars[s]), parity);
     const float *chunk = reinterpret_cast<const float *>(stages + (size_t)s * stage_bytes) + lane * V;
-    const uint4 *xq = reinterpret_cast<const uint4 *>(xbuf);
+    const uint32_t *xcur = xbuf + (d & 1) * RW;
+    const uint4 *xq = reinterpret_cast<const uint4 *>(xcur);
 
-    if (t.kind == KIND_TABLE || (t.kind == KIND_GP && !__any_sync(0xffffffffu, overflow))) {
+    if (t.kind != KIND_NICH) {
 #pragma unroll
       for (int r4 = 0; r4 < RW / 4; r4++) {
         const uint4 q = xq[r4];
@@ -188,25 +204,27 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
           for (int v = 0; v < V; v++) acc[r4 * 4 + e][v] += tv.v[v];
         }
       }
-    } else if (t.kind == KIND_GP) {  // some row of this warp has a count beyond the table (rare)
-      const uint32_t cap = t.ncat;
+      if (t.kind == KIND_GP) {  // counts beyond the table: the fp64 closed form from the suffstats (rare)
+        const uint32_t *raw = reinterpret_cast<const uint32_t *>(t.col);
 #pragma unroll
-      for (int r = 0; r < RW; r++) {
-        const uint32_t off = xbuf[r];
-        if (off <= cap * KT) {
-          VecF<V> tv;
-          tv.load(chunk + off);
+        for (int j = 0; j < RL; j++) {
+          uint32_t m = ovf_cur[j];
+          while (m) {
+            const int rr = j * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            const double xv = (double)raw[row0 + rr];
+            float add[V];
 #pragma unroll
-          for (int v = 0; v < V; v++) acc[r][v] += tv.v[v];
-        } else {  // evaluate the closed form
-          const float xv = (float)__shfl_sync(0xffffffffu, xi[r >> 5], r & 31);
-          const float lgx1 = lgammaf(xv + 1.f);
+            for (int v = 0; v < V; v++) {
+              const int col = kt * KT + lane * V + v;
+              add[v] = 0.f;
+              if (col < ncols) add[v] = gp_overflow_score(feats + d, hp, ss, col2slot[col], xv);
+            }
 #pragma unroll
-          for (int v = 0; v < V; v++) {
-            const float a = chunk[(size_t)(cap + 1) * KT + v];
-            const float ca = chunk[(size_t)(cap + 2) * KT + v];
-            const float l1pb = chunk[(size_t)(cap + 3) * KT + v];
-            acc[r][v] += lgammaf(a + xv) - lgx1 + ca - xv * l1pb;
+            for (int r = 0; r < RW; r++)  // static register indexing: acc must not spill to local memory
+              if (r == rr)
+#pragma unroll
+                for (int v = 0; v < V; v++) acc[r][v] += add[v];
           }
         }
       }
@@ -238,23 +256,46 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
     if (lane == 0) mbar_arrive(smem_u32(&bars[S + s]));
     if (tid == 0 && d + S < nfeat) {
       mbar_wait(smem_u32(&bars[S + s]), parity);
-      issue(d + S);
+      issue(d + S, s);
     }
+    if (++s == S) { s = 0; parity ^= 1u; }
 #pragma unroll
-    for (int j = 0; j < RL; j++) { xi[j] = xi_next[j]; xf[j] = xf_next[j]; }
+    for (int j = 0; j < RL; j++) { xa[j] = xb[j]; ovf_cur[j] = ovf_next[j]; }
   }
 
-  // epilogue: + log(pseudocount) (group_manager.hpp:274-283), coalesced 128 V-byte stores
+  // epilogue: + log(pseudocount) (group_manager.hpp:274-283)
   VecF<V> b;
   b.load(base + (size_t)kt * KT + lane * V);
+  if constexpr (!BLOCKED) {  // 128 V-byte coalesced row-major stores
 #pragma unroll
-  for (int r = 0; r < RW; r++) {
-    const size_t row = row0 + r;
-    if (row < row_hi) {
-      float o[V];
+    for (int r = 0; r < RW; r++) {
+      const size_t row = row0 + r;
+      if (row < row_hi) {
+        float o[V];
 #pragma unroll
-      for (int v = 0; v < V; v++) o[v] = acc[r][v] + b.v[v];
-      store_vec<V>(scores + (row - row_lo) * ld + (size_t)kt * KT + lane * V, o);
+        for (int v = 0; v < V; v++) o[v] = acc[r][v] + b.v[v];
+        store_vec<V>(scores + (row - row_lo) * ld + (size_t)kt * KT + lane * V, o);
+      }
+    }
+  } else {
+    // transpose each 32-row x KT-group tile through shared memory (the drained stage ring) so that
+    // lane = row and every store instruction writes 32 consecutive floats of one group
+    __syncthreads();  // every warp has finished reading the stages
+    float *tile = reinterpret_cast<float *>(stages) + (size_t)warp * 32 * (KT + 1);
+#pragma unroll
+    for (int j = 0; j < RL; j++) {
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 32; r++)
+#pragma unroll
+        for (int v = 0; v < V; v++) tile[r * (KT + 1) + lane * V + v] = acc[j * 32 + r][v] + b.v[v];
+      __syncwarp();
+      const size_t rb = (row0 - row_lo) / 32 + j;  // row0 - row_lo is a multiple of 32
+      if (row0 + (size_t)j * 32 < row_hi) {
+        float *dst = scores + (rb * ld + (size_t)kt * KT) * 32 + lane;
+#pragma unroll 8
+        for (int c = 0; c < KT; c++) dst[(size_t)c * 32] = tile[lane * (KT + 1) + c];
+      }
     }
   }
 }

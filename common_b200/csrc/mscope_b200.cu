@@ -108,6 +108,7 @@ struct msb_state {
   size_t niw_cols_cap = 0;
   // last score
   int cfg = 1, V = 2; size_t ld = 0, last_rows = 0, last_cols = 0;
+  bool last_blocked = false;
   std::vector<int32_t> h_col2slot;
   std::vector<size_t> h_colgid;
   std::vector<PhaseEvents> events;
@@ -149,10 +150,14 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   c->smem_optin = prop.sharedMemPerBlockOptin;
   if (stream) c->stream = (cudaStream_t)stream;
   else { CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-  CU_TRY(opt_in_smem(score_kernel<1, 64, 16>, c->smem_optin));
-  CU_TRY(opt_in_smem(score_kernel<2, 32, 16>, c->smem_optin));
-  CU_TRY(opt_in_smem(score_kernel<4, 32, 8>, c->smem_optin));
-  CU_TRY(opt_in_smem(score_kernel<1, 32, 8>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 64, 16, false>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<2, 32, 16, false>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<4, 32, 8, false>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 32, 8, false>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 64, 16, true>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<2, 32, 16, true>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<4, 32, 8, true>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 32, 8, true>, c->smem_optin));
   CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin - 1024));  // it also has a few bytes of static shared memory
   CU_TRY(opt_in_smem(niw_score_simt_kernel, c->smem_optin - 1024));
   MSB_TRY(niw_tc_init(c->smem_optin, g_last_error));
@@ -797,7 +802,7 @@ static int build_params(msb_state *st) {
   return MSB_OK;
 }
 
-static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scores) {
+static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scores, bool blocked = false) {
   msb_ctx *ctx = st->ctx;
   const size_t nrows = row_hi - row_lo;
   const size_t K = st->h_col2slot.size();
@@ -805,15 +810,28 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
   const size_t ktiles = st->ld / KT;
   if (st->has_scalar) {
     const ScoreCfg c = k_score_cfgs[st->cfg];
-    const size_t stage = (st->max_chunk_rows * KT * sizeof(float) + 127) / 128 * 128;
-    const size_t fixed = st->D * sizeof(FeatS) + 2 * 8 * sizeof(uint64_t) + (size_t)c.NW * c.RW * sizeof(uint32_t) + 256;
+    const size_t xbytes = 2 * (size_t)c.NW * c.RW * sizeof(uint32_t);
+    const size_t fixed = st->n_scalar * sizeof(FeatS) + 2 * 8 * sizeof(uint64_t) + xbytes + 256;
+    size_t stage = (st->max_chunk_rows * KT * sizeof(float) + 127) / 128 * 128;
     if (stage + fixed > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "parameter chunk does not fit in shared memory");
     const int S = (int)std::max<size_t>(1, std::min<size_t>(4, (ctx->smem_optin - fixed) / stage));
+    // the blocked epilogue transposes 32 x KT tiles through the (drained) stage ring
+    const size_t tile = (size_t)c.NW * 32 * (KT + 1) * sizeof(float);
+    if (blocked && (size_t)S * stage < tile) stage = ((tile + S - 1) / S + 127) / 128 * 128;
     const size_t smem = (size_t)S * stage + fixed;
+    if (smem > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "score kernel shared memory does not fit");
     dim3 grid(cdiv(nrows, (size_t)c.NW * c.RW), (unsigned)ktiles);
-#define MSB_SCORE_LAUNCH(V_, RW_, NW_)                                                                              \
-    LAUNCH(ctx, (score_kernel<V_, RW_, NW_>), grid, NW_ * 32, smem, st->d_feats_scalar, (int)st->n_scalar, st->d_params, \
-           st->region_rows, (uint32_t)stage, S, st->d_base, scores, st->ld, row_lo, row_hi)
+#define MSB_SCORE_LAUNCH(V_, RW_, NW_)                                                                                   \
+    do {                                                                                                                 \
+      if (blocked)                                                                                                       \
+        LAUNCH(ctx, (score_kernel<V_, RW_, NW_, true>), grid, NW_ * 32, smem, st->d_feats_scalar, (int)st->n_scalar,     \
+               st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base, scores, st->ld, row_lo, row_hi, st->d_hp, \
+               st->d_ss, st->d_col2slot, (int)K);                                                                        \
+      else                                                                                                               \
+        LAUNCH(ctx, (score_kernel<V_, RW_, NW_, false>), grid, NW_ * 32, smem, st->d_feats_scalar, (int)st->n_scalar,    \
+               st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base, scores, st->ld, row_lo, row_hi, st->d_hp, \
+               st->d_ss, st->d_col2slot, (int)K);                                                                        \
+    } while (0)
     switch (st->cfg) {
       case 0: MSB_SCORE_LAUNCH(1, 64, 16); break;
       case 1: MSB_SCORE_LAUNCH(2, 32, 16); break;
@@ -968,7 +986,9 @@ extern "C" MSB_API int msb_state_remove_value(msb_state *st, size_t eid, size_t 
 }
 
 // ---- scoring -------------------------------------------------------------------
-static int ensure_scores(msb_state *st, size_t nrows) { return ensure(&st->d_scores, &st->scores_cap, nrows * st->ld + 64); }
+static int ensure_scores(msb_state *st, size_t nrows) {  // rows padded to the 32-row blocks of the blocked layout
+  return ensure(&st->d_scores, &st->scores_cap, (nrows + 31) / 32 * 32 * st->ld + 64);
+}
 
 extern "C" MSB_API int msb_state_score_value(msb_state *st, size_t eid, size_t *gids, float *scores, size_t cap, size_t *n) {
   REQUIRE(st && n, "NULL argument");
@@ -990,7 +1010,7 @@ extern "C" MSB_API int msb_state_score_value(msb_state *st, size_t eid, size_t *
     MSB_TRY(build_params(st));
     MSB_TRY(launch_score(st, eid, eid + 1, st->d_scores));
   }
-  st->last_rows = 1; st->last_cols = K;
+  st->last_rows = 1; st->last_cols = K; st->last_blocked = false;
   if (scores) CU_TRY(cudaMemcpyAsync(scores, st->d_scores, sizeof(float) * K, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
   if (gids) for (size_t c = 0; c < K; c++) gids[c] = st->h_colgid[c];
@@ -1022,7 +1042,7 @@ extern "C" MSB_API int msb_state_score_rows(msb_state *st, size_t row_lo, size_t
     MSB_TRY(build_params(st));
     MSB_TRY(launch_score(st, row_lo, row_hi, dst));
   }
-  st->last_rows = nrows; st->last_cols = K;
+  st->last_rows = nrows; st->last_cols = K; st->last_blocked = false;
   if (scores && dst != scores) {
     REQUIRE(ld >= K, "ld smaller than the number of groups");
     CU_TRY(cudaMemcpy2DAsync(scores, sizeof(float) * ld, dst, sizeof(float) * st->ld, sizeof(float) * K, nrows,
@@ -1045,6 +1065,17 @@ extern "C" MSB_API int msb_state_read_last_scores(msb_state *st, float *out, siz
   REQUIRE(ld_out >= st->last_cols, "ld smaller than the number of groups");
   if (!st->last_rows || !st->last_cols) return MSB_OK;
   CU_TRY(cudaSetDevice(st->ctx->device));
+  if (st->last_blocked) {
+    float *tmp = nullptr;
+    CU_TRY(cudaMalloc(&tmp, sizeof(float) * st->last_rows * st->last_cols));
+    LAUNCH(st->ctx, unblock_kernel, cdiv(st->last_rows * st->last_cols, 256), 256, 0, st->d_scores, st->ld, st->last_rows,
+           (int)st->last_cols, tmp);
+    CU_TRY(cudaMemcpy2DAsync(out, sizeof(float) * ld_out, tmp, sizeof(float) * st->last_cols, sizeof(float) * st->last_cols,
+                             st->last_rows, cudaMemcpyDeviceToHost, st->ctx->stream));
+    CU_TRY(cudaStreamSynchronize(st->ctx->stream));
+    cudaFree(tmp);
+    return MSB_OK;
+  }
   CU_TRY(cudaMemcpy2DAsync(out, sizeof(float) * ld_out, st->d_scores, sizeof(float) * st->ld, sizeof(float) * st->last_cols,
                            st->last_rows, cudaMemcpyDeviceToHost, st->ctx->stream));
   CU_TRY(cudaStreamSynchronize(st->ctx->stream));
@@ -1113,6 +1144,8 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
     for (auto &e : pe.e) CU_TRY(cudaEventCreate(&e));
     st->events.push_back(pe);
   }
+  // the sweep keeps the scores in the sampler-friendly blocked layout (NIW kernels accumulate row-major)
+  const bool blocked = !st->has_niw && !getenv("MSB_NO_BLOCKED");
   CU_TRY(cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned long long), ctx->stream));
   CU_TRY(cudaEventRecord(st->events[0].e[0], ctx->stream));
   MSB_TRY(build_params(st));
@@ -1121,20 +1154,25 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
     const size_t lo = row_lo + c * chunk, hi = std::min(row_hi, lo + chunk);
     PhaseEvents &pe = st->events[c + 1];
     CU_TRY(cudaEventRecord(pe.e[0], ctx->stream));
-    MSB_TRY(launch_score(st, lo, hi, st->d_scores));
+    MSB_TRY(launch_score(st, lo, hi, st->d_scores, blocked));
     CU_TRY(cudaEventRecord(pe.e[1], ctx->stream));
     const float *d_u = nullptr;
     if (opts->uniforms) {
       CU_TRY(cudaMemcpyAsync(st->d_uniforms, opts->uniforms + (lo - row_lo), sizeof(float) * (hi - lo), cudaMemcpyHostToDevice, ctx->stream));
       d_u = st->d_uniforms;
     }
-    LAUNCH(ctx, sample_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores, st->ld, (int)K, hi - lo, d_u, opts->seed, opts->sweep,
-           opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
+    if (blocked)
+      LAUNCH(ctx, sample_blocked_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores, st->ld, (int)K, hi - lo, d_u, opts->seed,
+             opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
+    else
+      LAUNCH(ctx, sample_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores, st->ld, (int)K, hi - lo, d_u, opts->seed,
+             opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
     CU_TRY(cudaEventRecord(pe.e[2], ctx->stream));
     MSB_TRY(launch_update(st, lo, hi));
     CU_TRY(cudaEventRecord(pe.e[3], ctx->stream));
   }
-  st->last_rows = std::min(chunk, nrows); st->last_cols = K;
+  st->last_rows = nchunks == 1 ? nrows : (nrows - (nchunks - 1) * chunk); st->last_cols = K;
+  st->last_blocked = blocked;
   CU_TRY(cudaEventRecord(st->events[0].e[2], ctx->stream));
   if (!opts->defer_apply) LAUNCH(ctx, apply_delta_kernel, cdiv(st->SS, 256), 256, 0, st->d_ss, st->d_delta, st->SS);
   CU_TRY(cudaEventRecord(st->events[0].e[3], ctx->stream));

@@ -358,3 +358,29 @@ def test_large_group_counts_stay_accurate(ctx, oracle):
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, 0, 512)
     assert np.max(rel_err(S, want)) < RTOL
     st.close()
+
+
+def test_gp_counts_beyond_the_lookup_table(ctx, oracle):
+    # counts above the 252-row table take the closed-form path inside the score kernel
+    rng = np.random.default_rng(21)
+    n, k = 500, 4
+    z = np.arange(n) % k
+    arr = np.zeros(n, dtype=[("f0", np.uint32), ("f1", np.uint32), ("f2", np.bool_)])
+    arr["f0"] = rng.poisson(np.array([3.0, 40.0, 400.0, 900.0])[z])
+    arr["f1"] = rng.poisson(5.0, size=n)
+    arr["f1"][::50] = 5000
+    arr["f2"] = rng.random(n) < 0.5
+    descs = [cb.gp, cb.gp, cb.bb]
+    view = cb.numpy_dataview(arr)
+    st = cb.state(ctx, descs, max_groups=8, cluster_hp={"alpha": 1.0})
+    st.bind(view)
+    gids = [st.create_group() for _ in range(k)]
+    st.add_values(np.asarray(gids)[z])
+    hp = np.concatenate([oracle.flat_hp(d) for d in descs])
+    ss, counts = ol.build_suffstats(oracle, descs, hp, view, z, k)
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
+    _, S = st.score_rows()
+    assert np.max(rel_err(S, want)) < 3 * RTOL  # lgammaf(a + x) - lgammaf(x + 1) in float at x ~ 5000
+    res = st.sweep(seed=5, sweep=1)
+    assert np.max(rel_err(st.read_last_scores(), want)) < 3 * RTOL
+    st.close()
