@@ -85,7 +85,8 @@ __device__ __noinline__ float gp_overflow_score(const FeatDev *f, const double *
 //   blocked     scores[((row - row_lo) / 32 * ld + col) * 32 + (row - row_lo) % 32]
 //               32-row blocks, group-major inside a block: the sampler walks one row per thread and
 //               reads it fully coalesced.  Internal to the sweep.
-template <int V, int RW, int NW, bool BLOCKED>
+// TABLES_ONLY: every feature is a lookup table (bb / dd): no kind dispatch, no gp / nich code.
+template <int V, int RW, int NW, bool BLOCKED, bool TABLES_ONLY>
 __global__ void __launch_bounds__(NW * 32, 1)
 score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restrict__ params, size_t region_rows,
              uint32_t stage_bytes, int S, const float *__restrict__ base, float *__restrict__ scores, size_t ld,
@@ -132,16 +133,24 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
     for (int d = 0; d < S && d < nfeat; d++) issue(d, d);
 
   // raw value of this lane's rows for feature d (bit pattern: table index, count, or float)
+  uint32_t valid = 0;
+#pragma unroll
+  for (int j = 0; j < RL; j++) valid |= (row0 + j * 32 + lane < row_hi ? 1u : 0u) << j;
+  const size_t myrow = row0 + lane;
   auto load_x = [&](int d, uint32_t (&x)[RL]) {
     const FeatS t = ftab[d];
+    const size_t gcol = __cvta_generic_to_global(t.col);
 #pragma unroll
     for (int j = 0; j < RL; j++) {
-      const size_t row = row0 + j * 32 + lane;
-      x[j] = t.kind == KIND_GP ? GP_SENTINEL : (t.kind == KIND_NICH ? 0x7fc00000u : t.ncat);
-      if (row < row_hi) {
-        if (t.coltype == COL_U8) x[j] = ((const uint8_t *)t.col)[row];
-        else if (t.coltype == COL_U16) x[j] = ((const uint16_t *)t.col)[row];
-        else x[j] = ((const uint32_t *)t.col)[row];  // u32 counts and f32 values alike
+      if (TABLES_ONLY) x[j] = t.ncat;
+      else x[j] = t.kind == KIND_GP ? GP_SENTINEL : (t.kind == KIND_NICH ? 0x7fc00000u : t.ncat);
+      if (valid & (1u << j)) {
+        const size_t r = myrow + j * 32;
+        uint32_t v;
+        if (t.coltype == COL_U8) asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(gcol + r));
+        else if (t.coltype == COL_U16) asm("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(gcol + 2 * r));
+        else asm("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(gcol + 4 * r));  // u32 counts and f32 values alike
+        x[j] = v;
       }
     }
   };
@@ -156,13 +165,14 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
     for (int j = 0; j < RL; j++) {
       uint32_t pub = x[j];
       bool over = false;
-      if (t.kind == KIND_GP) {
+      if (TABLES_ONLY) pub = x[j] * KT;
+      else if (t.kind == KIND_GP) {
         const uint32_t cap = t.ncat;
         over = x[j] != GP_SENTINEL && x[j] >= cap;
         pub = (x[j] < cap ? x[j] : cap) * KT;
       } else if (t.kind == KIND_TABLE) pub = x[j] * KT;
       xbuf[(d & 1) * RW + j * 32 + lane] = pub;
-      ovf[j] = t.kind == KIND_GP ? __ballot_sync(0xffffffffu, over) : 0u;
+      if (!TABLES_ONLY) ovf[j] = t.kind == KIND_GP ? __ballot_sync(0xffffffffu, over) : 0u;
     }
   };
 
@@ -191,7 +201,7 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
     const uint32_t *xcur = xbuf + (d & 1) * RW;
     const uint4 *xq = reinterpret_cast<const uint4 *>(xcur);
 
-    if (t.kind != KIND_NICH) {
+    if (TABLES_ONLY || t.kind != KIND_NICH) {
 #pragma unroll
       for (int r4 = 0; r4 < RW / 4; r4++) {
         const uint4 q = xq[r4];
@@ -204,7 +214,7 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
           for (int v = 0; v < V; v++) acc[r4 * 4 + e][v] += tv.v[v];
         }
       }
-      if (t.kind == KIND_GP) {  // counts beyond the table: the fp64 closed form from the suffstats (rare)
+      if (!TABLES_ONLY && t.kind == KIND_GP) {  // counts beyond the table: the fp64 closed form from the suffstats (rare)
         const uint32_t *raw = reinterpret_cast<const uint32_t *>(t.col);
 #pragma unroll
         for (int j = 0; j < RL; j++) {
@@ -228,7 +238,7 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
           }
         }
       }
-    } else {  // KIND_NICH
+    } else if (!TABLES_ONLY) {  // KIND_NICH
       VecF<V> mu, sc, c1, c0;
       mu.load(chunk + 0 * KT);
       sc.load(chunk + 1 * KT);

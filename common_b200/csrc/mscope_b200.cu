@@ -94,7 +94,7 @@ struct msb_state {
   std::vector<void *> cols;
   int32_t *d_assign = nullptr;
   size_t region_rows = 0, max_chunk_rows = 0;
-  bool has_niw = false, has_scalar = false;
+  bool has_niw = false, has_scalar = false, tables_only = false;
   // workspaces
   float *d_params = nullptr; size_t params_cap = 0;
   float *d_scores = nullptr; size_t scores_cap = 0;
@@ -150,14 +150,22 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   c->smem_optin = prop.sharedMemPerBlockOptin;
   if (stream) c->stream = (cudaStream_t)stream;
   else { CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-  CU_TRY(opt_in_smem(score_kernel<1, 64, 16, false>, c->smem_optin));
-  CU_TRY(opt_in_smem(score_kernel<2, 32, 16, false>, c->smem_optin));
-  CU_TRY(opt_in_smem(score_kernel<4, 32, 8, false>, c->smem_optin));
-  CU_TRY(opt_in_smem(score_kernel<1, 32, 8, false>, c->smem_optin));
-  CU_TRY(opt_in_smem(score_kernel<1, 64, 16, true>, c->smem_optin));
-  CU_TRY(opt_in_smem(score_kernel<2, 32, 16, true>, c->smem_optin));
-  CU_TRY(opt_in_smem(score_kernel<4, 32, 8, true>, c->smem_optin));
-  CU_TRY(opt_in_smem(score_kernel<1, 32, 8, true>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 64, 16, false, false>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<2, 32, 16, false, false>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<4, 32, 8, false, false>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 32, 8, false, false>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 64, 16, false, true>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<2, 32, 16, false, true>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<4, 32, 8, false, true>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 32, 8, false, true>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 64, 16, true, false>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<2, 32, 16, true, false>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<4, 32, 8, true, false>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 32, 8, true, false>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 64, 16, true, true>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<2, 32, 16, true, true>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<4, 32, 8, true, true>, c->smem_optin));
+  CU_TRY(opt_in_smem(score_kernel<1, 32, 8, true, true>, c->smem_optin));
   CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin - 1024));  // it also has a few bytes of static shared memory
   CU_TRY(opt_in_smem(niw_score_simt_kernel, c->smem_optin - 1024));
   MSB_TRY(niw_tc_init(c->smem_optin, g_last_error));
@@ -476,6 +484,9 @@ static void layout_chunks(msb_state *st) {
   }
   st->region_rows = ro;
   st->max_chunk_rows = mx;
+  st->tables_only = true;
+  for (auto &f : st->feats) if (f.rows > 0 && f.kind != KIND_TABLE) st->tables_only = false;
+  if (getenv("MSB_NO_TABLES_ONLY")) st->tables_only = false;
   st->feats_dirty = true;
 }
 
@@ -821,16 +832,14 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
     const size_t smem = (size_t)S * stage + fixed;
     if (smem > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "score kernel shared memory does not fit");
     dim3 grid(cdiv(nrows, (size_t)c.NW * c.RW), (unsigned)ktiles);
-#define MSB_SCORE_LAUNCH(V_, RW_, NW_)                                                                                   \
-    do {                                                                                                                 \
-      if (blocked)                                                                                                       \
-        LAUNCH(ctx, (score_kernel<V_, RW_, NW_, true>), grid, NW_ * 32, smem, st->d_feats_scalar, (int)st->n_scalar,     \
-               st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base, scores, st->ld, row_lo, row_hi, st->d_hp, \
-               st->d_ss, st->d_col2slot, (int)K);                                                                        \
-      else                                                                                                               \
-        LAUNCH(ctx, (score_kernel<V_, RW_, NW_, false>), grid, NW_ * 32, smem, st->d_feats_scalar, (int)st->n_scalar,    \
-               st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base, scores, st->ld, row_lo, row_hi, st->d_hp, \
-               st->d_ss, st->d_col2slot, (int)K);                                                                        \
+#define MSB_SCORE_ARGS st->d_feats_scalar, (int)st->n_scalar, st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base, \
+                       scores, st->ld, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K
+#define MSB_SCORE_LAUNCH(V_, RW_, NW_)                                                                         \
+    do {                                                                                                       \
+      if (blocked && st->tables_only) LAUNCH(ctx, (score_kernel<V_, RW_, NW_, true, true>), grid, NW_ * 32, smem, MSB_SCORE_ARGS);        \
+      else if (blocked) LAUNCH(ctx, (score_kernel<V_, RW_, NW_, true, false>), grid, NW_ * 32, smem, MSB_SCORE_ARGS);                     \
+      else if (st->tables_only) LAUNCH(ctx, (score_kernel<V_, RW_, NW_, false, true>), grid, NW_ * 32, smem, MSB_SCORE_ARGS);             \
+      else LAUNCH(ctx, (score_kernel<V_, RW_, NW_, false, false>), grid, NW_ * 32, smem, MSB_SCORE_ARGS);                                 \
     } while (0)
     switch (st->cfg) {
       case 0: MSB_SCORE_LAUNCH(1, 64, 16); break;
@@ -839,6 +848,7 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
       default: MSB_SCORE_LAUNCH(1, 32, 8); break;
     }
 #undef MSB_SCORE_LAUNCH
+#undef MSB_SCORE_ARGS
   } else {
     // no scalar feature: scores start from the CRP term
     LAUNCH(ctx, fill_rows_kernel, cdiv(nrows * st->ld, 256), 256, 0, scores, st->ld, st->d_base, nrows);

@@ -1,0 +1,146 @@
+// test_adapter.cpp -- the reference's own driver loop (bin/perf_group.cpp:76-125) on the GPU adapters,
+// plus the batched form.  Compiles against include/microscopes_b200/plugin_api.hpp, or, with
+// -DMSB_USE_REFERENCE_HEADERS -I<reference>/include, against the reference's real models/base.hpp.
+//
+//   test_adapter compile-only   -> exits 0 without touching the GPU
+//   test_adapter                -> runs on cuda:0, prints "ok" lines, exits non-zero on mismatch
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+
+#include "microscopes_b200/gpu_models.hpp"
+
+using namespace microscopes;
+using namespace microscopes::common;
+using namespace microscopes::models;
+
+static int fails = 0;
+#define EXPECT_NEAR(a, b, tol)                                                                   \
+  do {                                                                                           \
+    const double _a = (a), _b = (b);                                                             \
+    if (!(std::fabs(_a - _b) <= (tol) * std::fmax(1.0, std::fabs(_b)))) {                        \
+      std::printf("FAIL %s:%d %s = %.9g, expected %.9g\n", __FILE__, __LINE__, #a, _a, _b);      \
+      fails++;                                                                                   \
+    }                                                                                            \
+  } while (0)
+
+int main(int argc, char **argv) {
+  if (argc > 1 && std::strcmp(argv[1], "compile-only") == 0) return 0;
+  rng_t r(73);
+
+  // ---- perf_group.cpp loop: D bb features, 1 row, add -> remove -> score -----------------------
+  const size_t D = 16;
+  bool data[D];
+  for (size_t i = 0; i < D; i++) data[i] = std::bernoulli_distribution(0.5)(r);
+  std::vector<runtime_type> types(D, runtime_type(TYPE_B));
+  std::vector<std::shared_ptr<hypers>> shares;
+  std::vector<std::shared_ptr<group>> groups;
+  for (size_t i = 0; i < D; i++) {
+    shares.emplace_back(gpu_model(MSB_FAMILY_BB).create_hypers());
+    shares.back()->get_hp_mutator("alpha").set<float>(2.0);
+    shares.back()->get_hp_mutator("beta").set<float>(2.0);
+    groups.emplace_back(shares.back()->create_group(r));
+  }
+  float score = 0.f;
+  for (size_t i = 0; i < D; i++) {
+    value_accessor v(reinterpret_cast<const uint8_t *>(&data[i]), nullptr, types[i]);
+    groups[i]->add_value(*shares[i], v, r);
+    groups[i]->add_value(*shares[i], v, r);
+    groups[i]->remove_value(*shares[i], v, r);
+    score += groups[i]->score_value(*shares[i], v, r);
+  }
+  // after one add of x: P(x) = (2 + 1) / (4 + 1)
+  EXPECT_NEAR(score, D * std::log(3.0 / 5.0), 1e-5);
+  std::printf("ok perf_group loop on gpu_group: score %.6f\n", score);
+
+  // ---- the other families through the same interface ---------------------------------------------
+  {
+    auto h = gpu_model(MSB_FAMILY_NICH).create_hypers();
+    h->get_hp_mutator("mu").set<float>(0.5f);
+    h->get_hp_mutator("kappa").set<float>(2.0f);
+    h->get_hp_mutator("sigmasq").set<float>(1.5f);
+    h->get_hp_mutator("nu").set<float>(3.0f);
+    auto g = h->create_group(r);
+    const float xs[4] = {1.0f, 2.5f, -0.5f, 1.25f};
+    for (float x : xs) g->add_value(*h, value_accessor(&x), r);
+    const double n = 4, mean = (1.0 + 2.5 - 0.5 + 1.25) / 4;
+    double ctv = 0;
+    for (float x : xs) ctv += (x - mean) * (x - mean);
+    const double kn = 2 + n, nun = 3 + n, mun = (2 * 0.5 + n * mean) / kn;
+    const double sn = (3 * 1.5 + ctv + n * 2 * (0.5 - mean) * (0.5 - mean) / kn) / nun;
+    const double lam = kn / ((kn + 1) * sn), x = 0.75;
+    const double want = std::lgamma(0.5 * nun + 0.5) - std::lgamma(0.5 * nun) + 0.5 * std::log(lam / (M_PI * nun)) -
+                        (0.5 * nun + 0.5) * std::log1p(lam * (x - mun) * (x - mun) / nun);
+    const float xf = (float)x;
+    EXPECT_NEAR(g->score_value(*h, value_accessor(&xf), r), want, 1e-5);
+    double cnt = g->get_ss_mutator("count").accessor().get<double>(0);
+    EXPECT_NEAR(cnt, 4.0, 0);
+    EXPECT_NEAR(g->get_ss_mutator("mean").accessor().get<double>(0), mean, 1e-12);
+    std::printf("ok nich through base.hpp interface\n");
+  }
+  {
+    auto m = gpu_model(MSB_FAMILY_DD, 300);  // beyond the reference's DirichletDiscrete<128> (distributions.hpp:80-81)
+    auto h = m.create_hypers();
+    auto g = h->create_group(r);
+    const int32_t x = 299;
+    for (int i = 0; i < 3; i++) g->add_value(*h, value_accessor(&x), r);
+    EXPECT_NEAR(g->score_value(*h, value_accessor(&x), r), std::log(4.0 / 303.0), 1e-5);
+    const int64_t y = 7;  // any primitive type may back the value (runtime_cast)
+    EXPECT_NEAR(g->score_value(*h, value_accessor(&y), r), std::log(1.0 / 303.0), 1e-5);
+    bool threw = false;
+    try { h->get_hp_mutator("nope"); } catch (const std::runtime_error &) { threw = true; }
+    if (!threw) { std::printf("FAIL unknown key did not throw\n"); fails++; }
+    std::printf("ok dd(300) through base.hpp interface\n");
+  }
+
+  // ---- batched: same numbers as the per-value loop --------------------------------------------------
+  {
+    const size_t N = 257, K = 3;
+    struct __attribute__((packed)) rec { bool b; uint32_t c; float f; };
+    std::vector<rec> rows(N);
+    for (size_t i = 0; i < N; i++) {
+      rows[i].b = std::bernoulli_distribution(0.3 + 0.2 * (i % K))(r);
+      rows[i].c = std::poisson_distribution<uint32_t>(2.0 + 3.0 * (i % K))(r);
+      rows[i].f = std::normal_distribution<float>(1.0f * (i % K), 1.0f)(r);
+    }
+    std::vector<runtime_type> t = {runtime_type(TYPE_B), runtime_type(TYPE_U32), runtime_type(TYPE_F32)};
+    std::vector<std::shared_ptr<gpu_model>> ms = {std::make_shared<gpu_model>(MSB_FAMILY_BB), std::make_shared<gpu_model>(MSB_FAMILY_GP),
+                                                 std::make_shared<gpu_model>(MSB_FAMILY_NICH)};
+    batch_scorer bs(ms, reinterpret_cast<const uint8_t *>(rows.data()), nullptr, N, t, K + 1);
+    bs.set_alpha(1.0);
+    std::vector<int64_t> z(N);
+    for (size_t k = 0; k < K; k++) bs.create_group();
+    for (size_t i = 0; i < N; i++) z[i] = (int64_t)(i % K);
+    bs.add_values(z);
+    std::vector<float> S = bs.score_rows();
+    // per-value loop over the same data
+    std::vector<std::shared_ptr<hypers>> hs;
+    std::vector<std::vector<std::shared_ptr<group>>> gs(K);
+    for (auto &m : ms) hs.push_back(m->create_hypers());
+    for (size_t k = 0; k < K; k++) for (auto &h : hs) gs[k].push_back(h->create_group(r));
+    for (size_t i = 0; i < N; i++) {
+      const uint8_t *p = reinterpret_cast<const uint8_t *>(&rows[i]);
+      gs[i % K][0]->add_value(*hs[0], value_accessor(p, nullptr, t[0]), r);
+      gs[i % K][1]->add_value(*hs[1], value_accessor(p + 1, nullptr, t[1]), r);
+      gs[i % K][2]->add_value(*hs[2], value_accessor(p + 5, nullptr, t[2]), r);
+    }
+    for (size_t i : {size_t(0), size_t(100), N - 1}) {
+      const uint8_t *p = reinterpret_cast<const uint8_t *>(&rows[i]);
+      for (size_t k = 0; k < K; k++) {
+        const double cnt = (double)((N - k + K - 1) / K);
+        double s = std::log(cnt);
+        s += gs[k][0]->score_value(*hs[0], value_accessor(p, nullptr, t[0]), r);
+        s += gs[k][1]->score_value(*hs[1], value_accessor(p + 1, nullptr, t[1]), r);
+        s += gs[k][2]->score_value(*hs[2], value_accessor(p + 5, nullptr, t[2]), r);
+        EXPECT_NEAR(S[i * K + k], s, 2e-5);
+      }
+    }
+    msb_sweep_result res = bs.sweep(73, 0);
+    if (res.rows != N || res.units != N * K * 3) { std::printf("FAIL sweep result\n"); fails++; }
+    std::printf("ok batch_scorer matches the per-value loop (%zu rows, %llu moved)\n", N, (unsigned long long)res.moved);
+  }
+  if (fails) { std::printf("%d failure(s)\n", fails); return 1; }
+  std::printf("all ok\n");
+  return 0;
+}

@@ -58,5 +58,6 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".sh")):
                 text = open(os.path.join(dirpath, fn), errors="replace").read()
                 assert "oracle" not in text.lower(), os.path.join(dirpath, fn)
-    for fn in os.listdir(os.path.join(ROOT, "include")):
-        assert "oracle" not in open(os.path.join(ROOT, "include", fn)).read().lower()
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "include")):
+        for fn in files:
+            assert "oracle" not in open(os.path.join(dirpath, fn)).read().lower(), fn
