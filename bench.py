@@ -254,7 +254,18 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count() - launches0
-    clk = clocks.stop() if rank == 0 else None
+    clk = None
+    if rank == 0:
+        # nvidia-smi cannot sample faster than ~100 ms: when the timed region is shorter than that,
+        # keep the same step running (untimed) until the sampler has seen the GPU under this load
+        extra_t0 = time.perf_counter()
+        extra = 0
+        while len(clocks.rows) < 5 and time.perf_counter() - extra_t0 < 3.0 and world == 1:
+            step(warmup + args.steps + extra)
+            extra += 1
+        torch.cuda.synchronize(device)
+        clk = clocks.stop()
+        clk["sampled_over"] = "timed region" if extra == 0 else "timed region + %d more untimed steps of the same workload" % extra
     t = torch.tensor([ms_total], device=device, dtype=torch.float64)
     u = torch.tensor([float(units)], device=device, dtype=torch.float64)
     if world > 1:
@@ -312,6 +323,20 @@ def main():
                "ms_per_step": float(tt.item()) * 1e3 / esteps,
                "what": "host AoS records (pinned) -> device dataview -> bind/pack -> add_values -> sweep -> assignments to host"}
 
+    tf32_peak = None
+    if rank == 0 and any(d().name() == "niw" for d in descs):
+        # TF32 dense peak is not in MEASURED_PEAKS.json: measure it here with a library GEMM (8192^3)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(8192, 8192, device=device); b = torch.randn(8192, 8192, device=device)
+        for _ in range(3):
+            a @ b
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e9
+        for _ in range(5):
+            t0.record(); a @ b; t1.record(); torch.cuda.synchronize(device)
+            best = min(best, t0.elapsed_time(t1))
+        tf32_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del a, b
     if rank == 0:
         peaks = {}
         try:
@@ -323,6 +348,18 @@ def main():
         score_ms = phase["score"] / args.steps
         abytes = algorithmic_bytes_score(descs, storage, n, k)
         achieved = abytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
+        roof = {"kernel": "score_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": abytes,
+                "launch_ms": score_ms, "peak_source": peak_src,
+                "note": "score kernels reuse every loaded value K times: the binding roof is shared-memory lookup / FP32 issue rate, see DESIGN.md"}
+        if tf32_peak:
+            dims = [d()._param() for d in descs if d().name() == "niw"]
+            flops = sum(2.0 * dd_ * dd_ * n * k for dd_ in dims)   # whitened-GEMM form, SURVEY.md section 8(d)
+            ach = flops / (score_ms * 1e-3) / 1e12
+            roof = {"kernel": "niw_tc_kernel (+ pack, fill)", "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": ach / tf32_peak, "traffic": None, "algorithmic_flops_per_launch": flops, "launch_ms": score_ms,
+                    "peak_source": "torch.matmul TF32 8192^3 measured in this run (no TF32 figure in MEASURED_PEAKS.json)",
+                    "note": "the kernel issues 3 tf32 products per algorithmic product (hi*hi + hi*lo + lo*hi) for fp32-class accuracy: tensor-pipe work is 3x the algorithmic FLOPs"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
@@ -330,10 +367,7 @@ def main():
                            "step": "param build + score (N x K fp32 materialised) + sample + suffstat update" + (" + all-reduce" if world > 1 else ""),
                            "l2": "no explicit flush: each step streams the %.0f MB score matrix (> 126 MB L2)" % (4.0 * n * st.last_scores()[1] / 1e6)},
                 "phase_ms_per_step": {kk: v / args.steps for kk, v in phase.items()},
-                "roofline": {"kernel": "score_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": abytes,
-                             "launch_ms": score_ms, "peak_source": peak_src,
-                             "note": "score kernels reuse every loaded value K times: the binding roof is shared-memory lookup / FP32 issue rate, see DESIGN.md"},
+                "roofline": roof,
                 "gpu_launches": int(launches), "clocks": clk}
         if e2e:
             line["e2e"] = e2e

@@ -386,9 +386,10 @@ __global__ void update_kernel(const FeatDev *__restrict__ feats, int nfeat, cons
       const int j = x ? 0 : 1;
       if (a >= 0) atomic_add_f64(blk + (size_t)a * 2 + j, -1.0);
       if (b >= 0) atomic_add_f64(blk + (size_t)b * 2 + j, 1.0);
-    } else {  // ss = [count_sum, counts[dim]]
-      if (a >= 0) { atomic_add_f64(blk + (size_t)a * f.ss_w, -1.0); atomic_add_f64(blk + (size_t)a * f.ss_w + 1 + x, -1.0); }
-      if (b >= 0) { atomic_add_f64(blk + (size_t)b * f.ss_w, 1.0); atomic_add_f64(blk + (size_t)b * f.ss_w + 1 + x, 1.0); }
+    } else {  // ss = [count_sum, counts[dim]]; count_sum is re-derived from counts (dd_count_sum_kernel):
+              // a RED per cell on only K addresses per feature would serialise in L2
+      if (a >= 0) atomic_add_f64(blk + (size_t)a * f.ss_w + 1 + x, -1.0);
+      if (b >= 0) atomic_add_f64(blk + (size_t)b * f.ss_w + 1 + x, 1.0);
     }
   } else if (f.kind == KIND_GP) {  // ss = [count, sum, log_prod]
     const uint32_t x = ((const uint32_t *)f.col)[row];
@@ -434,16 +435,52 @@ __global__ void update_niw_kernel(FeatDev f, const int32_t *__restrict__ old_slo
 // CRP bookkeeping (group_manager.hpp:218-248): per-group entity counts,
 // assignment vector, number of moved rows.
 __global__ void commit_assign_kernel(int32_t *__restrict__ assign, const int32_t *__restrict__ new_slot,
-                                     size_t row_lo, size_t row_hi, double *__restrict__ delta_counts,
+                                     size_t row_lo, size_t row_hi, double *__restrict__ delta_counts, int kmax,
                                      unsigned long long *__restrict__ moved) {
+  // per-block histogram of count changes in shared memory (when it fits), one RED per touched group per block
+  extern __shared__ int hist[];
+  const bool use_hist = kmax <= 8192;
+  if (use_hist) {
+    for (int i = threadIdx.x; i < kmax; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+  }
   const size_t row = row_lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= row_hi) return;
-  const int a = assign[row], b = new_slot[row - row_lo];
-  if (a == b) return;
-  if (a >= 0) atomic_add_f64(delta_counts + a, -1.0);
-  if (b >= 0) atomic_add_f64(delta_counts + b, 1.0);
-  assign[row] = b;
-  atomicAdd(moved, 1ull);
+  bool did = false;
+  if (row < row_hi) {
+    const int a = assign[row], b = new_slot[row - row_lo];
+    if (a != b) {
+      if (use_hist) {
+        if (a >= 0) atomicSub(&hist[a], 1);
+        if (b >= 0) atomicAdd(&hist[b], 1);
+      } else {
+        if (a >= 0) atomic_add_f64(delta_counts + a, -1.0);
+        if (b >= 0) atomic_add_f64(delta_counts + b, 1.0);
+      }
+      assign[row] = b;
+      did = true;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, did);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(moved, (unsigned long long)__popc(m));
+  if (use_hist) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kmax; i += blockDim.x)
+      if (hist[i] != 0) atomic_add_f64(delta_counts + i, (double)hist[i]);
+  }
+}
+
+// dd: count_sum[slot] = sum of counts[slot][:] (kept consistent after every apply)
+__global__ void dd_count_sum_kernel(const FeatDev *__restrict__ feats, int nfeat, int kmax, double *__restrict__ ss) {
+  const int d = blockIdx.y;
+  const FeatDev f = feats[d];
+  if (f.family != FAM_DD) return;
+  const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (slot >= kmax) return;
+  double *p = ss + f.ss_off + (size_t)slot * f.ss_w;
+  double s = 0.0;
+  for (uint32_t i = lane; i < f.dim; i += 32) s += p[1 + i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) p[0] = s;
 }
 
 __global__ void apply_delta_kernel(double *__restrict__ ss, double *__restrict__ delta, size_t n) {

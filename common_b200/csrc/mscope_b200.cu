@@ -88,13 +88,16 @@ struct msb_state {
   std::vector<int64_t> slot2gid;
   std::vector<int> free_slots;
   std::vector<double> h_counts;
+  std::vector<char> slot_dirty;   // suffstats of the slot may be non-zero (set by any update / set_ss)
+  bool all_unassigned = true;     // no entity has been assigned since bind
+  void *col_slab = nullptr;       // one allocation backing every column
   // data
   msb_dataview *dv = nullptr;
   size_t n = 0;
   std::vector<void *> cols;
   int32_t *d_assign = nullptr;
   size_t region_rows = 0, max_chunk_rows = 0;
-  bool has_niw = false, has_scalar = false, tables_only = false;
+  bool has_niw = false, has_scalar = false, tables_only = false, has_dd = false;
   // workspaces
   float *d_params = nullptr; size_t params_cap = 0;
   float *d_scores = nullptr; size_t scores_cap = 0;
@@ -393,7 +396,7 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
     switch (m.family) {
       case MSB_FAMILY_BB: f.kind = KIND_TABLE; f.coltype = COL_U8; f.ncat = 2; f.dim = 2; st->has_scalar = true; break;
       case MSB_FAMILY_DD:
-        f.kind = KIND_TABLE; f.ncat = m.dim; st->has_scalar = true;
+        f.kind = KIND_TABLE; f.ncat = m.dim; st->has_scalar = true; st->has_dd = true;
         f.coltype = m.dim + 1 <= 256 ? COL_U8 : (m.dim + 1 <= 65536 ? COL_U16 : COL_U32);
         break;
       case MSB_FAMILY_GP: f.kind = KIND_GP; f.coltype = COL_U32; f.ncat = 1; st->has_scalar = true; break;
@@ -429,6 +432,7 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
   CU_TRY(cudaMalloc(&st->d_slot2gid, sizeof(int64_t) * max_groups));
   st->slot2gid.assign(max_groups, -1);
   st->h_counts.assign(max_groups, 0.0);
+  st->slot_dirty.assign(max_groups, 0);
   for (int s = (int)max_groups - 1; s >= 0; s--) st->free_slots.push_back(s);
   st->cols.assign(nfeatures, nullptr);
   st->d_niwW.assign(nfeatures, nullptr); st->d_niwBias.assign(nfeatures, nullptr);
@@ -441,7 +445,7 @@ extern "C" MSB_API int msb_state_destroy(msb_state *st) {
   if (!st) return MSB_OK;
   cudaSetDevice(st->ctx->device);
   cudaStreamSynchronize(st->ctx->stream);
-  for (void *c : st->cols) cudaFree(c);
+  cudaFree(st->col_slab);
   for (size_t d = 0; d < st->D; d++) { cudaFree(st->d_niwW[d]); cudaFree(st->d_niwBias[d]); cudaFree(st->d_niwCoef[d]); cudaFree(st->d_niwB[d]); }
   cudaFree(st->d_feats); cudaFree(st->d_feats_scalar); cudaFree(st->d_hp); cudaFree(st->d_ss); cudaFree(st->d_delta); cudaFree(st->d_counter);
   cudaFree(st->d_slot2gid); cudaFree(st->d_assign); cudaFree(st->d_params); cudaFree(st->d_scores);
@@ -502,16 +506,22 @@ extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
     if (m.family == MSB_FAMILY_NIW) REQUIRE(t.n == m.dim, "shapes do not match");  // distributions.hpp:218
     else REQUIRE(t.n == 1, "scalar model bound to a vector field");               // distributions.hpp:209
   }
-  for (void *&c : st->cols) { cudaFree(c); c = nullptr; }
+  cudaFree(st->col_slab); st->col_slab = nullptr;
   cudaFree(st->d_assign); st->d_assign = nullptr;
   st->dv = dv; st->n = dv->n;
   const size_t n = std::max<size_t>(dv->n, 1);
+  std::vector<size_t> coff(st->D);
+  size_t slab = 0;
+  for (size_t d = 0; d < st->D; d++) {
+    const FeatDev &f = st->feats[d];
+    const size_t bytes = f.kind == KIND_NIW ? n * f.dim * sizeof(float) : n * (f.coltype == COL_U8 ? 1 : f.coltype == COL_U16 ? 2 : 4);
+    coff[d] = slab;
+    slab += (bytes + 4096 + 255) / 256 * 256;  // padded: tile-granular kernels may read past the last row
+  }
+  CU_TRY(cudaMalloc(&st->col_slab, slab));
   for (size_t d = 0; d < st->D; d++) {
     FeatDev &f = st->feats[d];
-    size_t bytes;
-    if (f.kind == KIND_NIW) bytes = n * f.dim * sizeof(float);
-    else bytes = n * (f.coltype == COL_U8 ? 1 : f.coltype == COL_U16 ? 2 : 4);
-    CU_TRY(cudaMalloc(&st->cols[d], bytes + 16));
+    st->cols[d] = (char *)st->col_slab + coff[d];
     f.col = st->cols[d];
     f.src_off = dv->off[d]; f.msk_off = dv->moff[d];
     f.src_prim = (uint32_t)dv->types[d].prim; f.src_n = dv->types[d].n;
@@ -543,6 +553,7 @@ extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
   layout_chunks(st);
   CU_TRY(cudaMalloc(&st->d_assign, sizeof(int32_t) * n));
   CU_TRY(cudaMemsetAsync(st->d_assign, 0xFF, sizeof(int32_t) * n, ctx->stream));  // all -1
+  st->all_unassigned = true;
   return MSB_OK;
 }
 
@@ -643,6 +654,7 @@ extern "C" MSB_API int msb_state_set_ss(msb_state *st, size_t feature, size_t gi
   ss_to_ref(st->models[feature], s);
   for (size_t i = 0; i < cnt; i++) s[off + i] = v[i];
   ss_from_ref(st->models[feature], s);
+  st->slot_dirty[slot] = 1;
   CU_TRY(cudaMemcpyAsync(dst, s.data(), sizeof(double) * f.ss_w, cudaMemcpyHostToDevice, st->ctx->stream));
   CU_TRY(cudaStreamSynchronize(st->ctx->stream));
   return MSB_OK;
@@ -689,10 +701,14 @@ extern "C" MSB_API int msb_state_create_group(msb_state *st, size_t *gid) {
   st->gid2slot[g] = slot;
   st->slot2gid[slot] = (int64_t)g;
   st->h_counts[slot] = 0.0;
-  // Group::init: zero suffstats (distributions.hpp:351)
-  CU_TRY(cudaMemsetAsync(st->d_ss + slot, 0, sizeof(double), st->ctx->stream));
-  for (auto &f : st->feats)
-    CU_TRY(cudaMemsetAsync(st->d_ss + f.ss_off + (size_t)slot * f.ss_w, 0, sizeof(double) * f.ss_w, st->ctx->stream));
+  // Group::init: zero suffstats (distributions.hpp:351); a slot nobody has written since the state was
+  // created is still zero from the initial memset
+  if (st->slot_dirty[slot]) {
+    CU_TRY(cudaMemsetAsync(st->d_ss + slot, 0, sizeof(double), st->ctx->stream));
+    for (auto &f : st->feats)
+      CU_TRY(cudaMemsetAsync(st->d_ss + f.ss_off + (size_t)slot * f.ss_w, 0, sizeof(double) * f.ss_w, st->ctx->stream));
+    st->slot_dirty[slot] = 0;
+  }
   *gid = g;
   return MSB_OK;
 }
@@ -869,7 +885,11 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
   return MSB_OK;
 }
 
+static void mark_dirty(msb_state *st) {
+  for (auto &p : st->gid2slot) st->slot_dirty[p.second] = 1;
+}
 static int refresh_counts(msb_state *st) {
+  mark_dirty(st);
   CU_TRY(cudaMemcpyAsync(st->h_counts.data(), st->d_ss, sizeof(double) * st->kmax, cudaMemcpyDeviceToHost, st->ctx->stream));
   CU_TRY(cudaStreamSynchronize(st->ctx->stream));
   return MSB_OK;
@@ -887,12 +907,21 @@ static int launch_update(msb_state *st, size_t row_lo, size_t row_hi) {  // old 
     if (f.kind != KIND_NIW) continue;
     LAUNCH(ctx, update_niw_kernel, cdiv(nrows, 8), 256, 0, f, st->d_assign, st->d_newslot, row_lo, row_hi, st->d_delta);
   }
-  LAUNCH(ctx, commit_assign_kernel, cdiv(nrows, 256), 256, 0, st->d_assign, st->d_newslot, row_lo, row_hi, st->d_delta, st->d_counter);
+  LAUNCH(ctx, commit_assign_kernel, cdiv(nrows, 256), 256, st->kmax <= 8192 ? st->kmax * sizeof(int) : 0, st->d_assign,
+         st->d_newslot, row_lo, row_hi, st->d_delta, (int)st->kmax, st->d_counter);
   return MSB_OK;
 }
 
-static int apply_deltas(msb_state *st) {
+static int launch_apply(msb_state *st) {
   LAUNCH(st->ctx, apply_delta_kernel, cdiv(st->SS, 256), 256, 0, st->d_ss, st->d_delta, st->SS);
+  if (st->has_dd) {
+    dim3 grid(cdiv(st->kmax, 8), (unsigned)st->D);
+    LAUNCH(st->ctx, dd_count_sum_kernel, grid, 256, 0, st->d_feats, (int)st->D, (int)st->kmax, st->d_ss);
+  }
+  return MSB_OK;
+}
+static int apply_deltas(msb_state *st) {
+  MSB_TRY(launch_apply(st));
   return refresh_counts(st);
 }
 
@@ -943,16 +972,25 @@ extern "C" MSB_API int msb_state_add_values(msb_state *st, const int64_t *gids, 
   if (!n) return MSB_OK;
   msb_ctx *ctx = st->ctx;
   CU_TRY(cudaSetDevice(ctx->device));
-  std::vector<int32_t> cur(n), req(n);
-  CU_TRY(cudaMemcpyAsync(cur.data(), st->d_assign, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  std::vector<int32_t> cur, req(n);
+  if (st->all_unassigned) cur.assign(n, -1);
+  else {
+    cur.resize(n);
+    CU_TRY(cudaMemcpyAsync(cur.data(), st->d_assign, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  std::vector<int> g2s;  // dense gid -> slot table: one lookup per entity instead of a map search
+  if (!st->gid2slot.empty()) {
+    g2s.assign(st->gid2slot.rbegin()->first + 1, -1);
+    for (auto &p : st->gid2slot) g2s[p.first] = p.second;
+  }
   for (size_t i = 0; i < n; i++) {
     if (gids[i] < 0) { req[i] = cur[i]; continue; }
     if (cur[i] >= 0) return fail(MSB_ERR_STATE, "entity already assigned");  // group_manager.hpp:221
-    auto it = st->gid2slot.find((size_t)gids[i]);
-    if (it == st->gid2slot.end()) return fail(MSB_ERR_INVALID, "invalid gid");
-    req[i] = it->second;
+    if ((size_t)gids[i] >= g2s.size() || g2s[(size_t)gids[i]] < 0) return fail(MSB_ERR_INVALID, "invalid gid");
+    req[i] = g2s[(size_t)gids[i]];
   }
+  st->all_unassigned = false;
   MSB_TRY(ensure_rows(st, n));
   MSB_TRY(sync_small(st));
   CU_TRY(cudaMemcpyAsync(st->d_newslot, req.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -970,6 +1008,7 @@ extern "C" MSB_API int msb_state_add_value(msb_state *st, size_t gid, size_t eid
   CU_TRY(cudaSetDevice(st->ctx->device));
   MSB_TRY(read_assign(st, eid, &cur));
   if (cur != -1) return fail(MSB_ERR_STATE, "entity already assigned");
+  st->all_unassigned = false;
   MSB_TRY(ensure_rows(st, 1));
   MSB_TRY(sync_small(st));
   const int32_t s32 = slot;
@@ -1184,7 +1223,7 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
   st->last_rows = nchunks == 1 ? nrows : (nrows - (nchunks - 1) * chunk); st->last_cols = K;
   st->last_blocked = blocked;
   CU_TRY(cudaEventRecord(st->events[0].e[2], ctx->stream));
-  if (!opts->defer_apply) LAUNCH(ctx, apply_delta_kernel, cdiv(st->SS, 256), 256, 0, st->d_ss, st->d_delta, st->SS);
+  if (!opts->defer_apply) MSB_TRY(launch_apply(st));
   CU_TRY(cudaEventRecord(st->events[0].e[3], ctx->stream));
   unsigned long long moved = 0;
   CU_TRY(cudaMemcpyAsync(&moved, st->d_counter, sizeof(moved), cudaMemcpyDeviceToHost, ctx->stream));

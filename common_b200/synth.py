@@ -31,6 +31,9 @@ def make_dataset(models, n, k_true, seed=73, stream=0, mask_frac=0.0, storage=No
     storage: optional list of numpy dtypes overriding each model's Value dtype
     (any of the 11 primitive types may back a field, runtime_type.hpp:145-166).
     """
+    # the planted mixture (group parameters) depends on the seed only; `stream` selects which rows
+    # of that mixture are drawn, so that every rank of a row-sharded run sees the same model
+    prng = _rng(seed, 1_000_003)
     rng = _rng(seed, stream)
     z = (np.arange(n) % k_true).astype(np.int64)
     cols, fields = [], []
@@ -38,27 +41,27 @@ def make_dataset(models, n, k_true, seed=73, stream=0, mask_frac=0.0, storage=No
         m = m()
         name = m.name()
         if name == "bb":
-            p = rng.beta(0.5, 0.5, size=k_true)
+            p = prng.beta(0.5, 0.5, size=k_true)
             x = rng.random(n) < p[z]
             dt = np.bool_
         elif name == "dd":
             C = m._param()
-            theta = rng.dirichlet(np.full(C, 0.5), size=k_true)
+            theta = prng.dirichlet(np.full(C, 0.5), size=k_true)
             x = _categorical(rng, theta, z)
             dt = np.int32
         elif name == "gp":
-            lam = rng.gamma(2.0, 4.0, size=k_true)
+            lam = prng.gamma(2.0, 4.0, size=k_true)
             x = rng.poisson(lam[z])
             dt = np.uint32
         elif name == "nich":
-            mu = rng.normal(0.0, 3.0, size=k_true)
-            sg = rng.uniform(0.5, 2.0, size=k_true)
+            mu = prng.normal(0.0, 3.0, size=k_true)
+            sg = prng.uniform(0.5, 2.0, size=k_true)
             x = mu[z] + sg[z] * rng.standard_normal(n)
             dt = np.float32
         elif name == "niw":
             dim = m._param()
-            mu = rng.normal(0.0, 2.0, size=(k_true, dim))
-            A = rng.standard_normal((k_true, dim, dim))
+            mu = prng.normal(0.0, 2.0, size=(k_true, dim))
+            A = prng.standard_normal((k_true, dim, dim))
             L = np.linalg.cholesky(A @ A.transpose(0, 2, 1) / dim + 0.1 * np.eye(dim))
             e = rng.standard_normal((n, dim))
             x = mu[z] + np.einsum("nij,nj->ni", L[z], e)

@@ -384,3 +384,21 @@ def test_gp_counts_beyond_the_lookup_table(ctx, oracle):
     res = st.sweep(seed=5, sweep=1)
     assert np.max(rel_err(st.read_last_scores(), want)) < 3 * RTOL
     st.close()
+
+
+def test_niw_tensor_core_path_many_tiles_and_group_blocks(ctx, oracle, monkeypatch):
+    # 157 row tiles x 10 group blocks over <=148 persistent CTAs: exercises every mbarrier phase, the
+    # resident-B reload, a ragged last row tile, a ragged last group block (37 = 9*4 + 1) and masked rows
+    descs = [cb.niw(64)]
+    n, k = 20001, 36
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=14, mask_frac=0.02, extra_empty=1)
+    _, S = st.score_rows()
+    rows = np.r_[0:300, 9990:10300, n - 200:n]
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), cb.numpy_dataview(view._data[rows] if view._mask is None else
+                                                                                          np.ma.array(view._data[rows], mask=view._mask[rows])))
+    assert np.max(rel_err(S[rows], want)) < 4 * RTOL
+    monkeypatch.setenv("MSB_NO_TENSOR", "1")   # the CUDA-core kernel on the same state
+    _, S2 = st.score_rows()
+    assert np.max(rel_err(S2[rows], want)) < 4 * RTOL
+    assert np.max(rel_err(S, S2)) < 4 * RTOL
+    st.close()
