@@ -135,7 +135,8 @@ __global__ void build_params_kernel(const FeatDev *__restrict__ feats, int nfeat
         else v = (float)p.l1pb;
       } else if (f.kind == KIND_NICH) {
         const NichPost p = nich_post(fhp, gss);
-        v = xr == 0 ? (float)p.mu : xr == 1 ? (float)p.s : xr == 2 ? (float)p.c1 : (float)p.c0;
+        // rows: mu', s, c1 ln2 (the score kernel evaluates log2(1+z)), c0
+        v = xr == 0 ? (float)p.mu : xr == 1 ? (float)p.s : xr == 2 ? (float)(p.c1 * 0.6931471805599453) : (float)p.c0;
       }
     }
     chunk[i] = v;
@@ -486,6 +487,22 @@ __global__ void dd_count_sum_kernel(const FeatDev *__restrict__ feats, int nfeat
 __global__ void apply_delta_kernel(double *__restrict__ ss, double *__restrict__ delta, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { ss[i] += delta[i]; delta[i] = 0.0; }
+}
+
+// base[col] += sum over nich features of c0[col]: the row-independent part of the nich term is added once
+// per (row, group) in the score kernel's epilogue instead of once per unit
+__global__ void nich_c0_sum_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restrict__ params,
+                                   size_t region_rows, int KT, int ncols_padded, float *__restrict__ base) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols_padded) return;
+  const int kt = col / KT, kl = col - kt * KT;
+  float s = 0.f;
+  for (int d = 0; d < nfeat; d++) {
+    const FeatDev f = feats[d];
+    if (f.kind != KIND_NICH) continue;
+    s += params[((size_t)kt * region_rows + f.rowoff + 3) * KT + kl];
+  }
+  base[col] += s;
 }
 
 // scores[r][c] = base[c]: the CRP term, when no scalar feature kernel initialises the matrix

@@ -113,18 +113,20 @@ __device__ __forceinline__ double nich_score(const NichPost &p, double x) {
   return p.c0 + p.c1 * log1p(t * t);
 }
 
-// fp32 log1p(z), z >= 0, for the nich inner loop: relative error ~1e-7 for
-// z < 1/16 (degree-5 polynomial, FMA pipe) and MUFU.LG2 above (relative error
-// <= 2^-22 / log2(1.0625) = 2.7e-6 in the worst case just above the switch).
-__device__ __forceinline__ float log1p_pos(float z) {
-  float p = -1.0f / 6.0f;
-  p = fmaf(p, z, 0.2f);
-  p = fmaf(p, z, -0.25f);
-  p = fmaf(p, z, 1.0f / 3.0f);
-  p = fmaf(p, z, -0.5f);
-  p = fmaf(p, z, 1.0f);
+// fp32 log2(1 + z), z >= 0, for the nich inner loop (the natural-log factor ln 2 is folded into the
+// per-(group, feature) coefficient c1 by build_params_kernel).  z < 1/16: degree-5 polynomial on the
+// FMA pipe (relative error ~1e-8); above: MUFU.LG2(1 + z), whose absolute error 2^-22 is at most
+// 2.7e-6 relative just above the switch.  Branch-free: both are evaluated and selected.
+__device__ __forceinline__ float log2_1p_pos(float z) {
+  constexpr float L2E = 1.4426950408889634f;
+  float p = -L2E / 6.0f;
+  p = fmaf(p, z, L2E / 5.0f);
+  p = fmaf(p, z, -L2E / 4.0f);
+  p = fmaf(p, z, L2E / 3.0f);
+  p = fmaf(p, z, -L2E / 2.0f);
+  p = fmaf(p, z, L2E);
   const float small = p * z;
-  const float big = __log2f(1.0f + z) * 0.693147180559945f;
+  const float big = __log2f(1.0f + z);
   return z < 0.0625f ? small : big;
 }
 

@@ -171,8 +171,12 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
         over = x[j] != GP_SENTINEL && x[j] >= cap;
         pub = (x[j] < cap ? x[j] : cap) * KT;
       } else if (t.kind == KIND_TABLE) pub = x[j] * KT;
+      else {  // nich: a masked cell (NaN) is scored as x = 0 in the branch-free loop and undone afterwards
+        over = pub == 0x7fc00000u || __uint_as_float(pub) != __uint_as_float(pub);
+        if (over) pub = 0u;
+      }
       xbuf[(d & 1) * RW + j * 32 + lane] = pub;
-      if (!TABLES_ONLY) ovf[j] = t.kind == KIND_GP ? __ballot_sync(0xffffffffu, over) : 0u;
+      if (!TABLES_ONLY) ovf[j] = t.kind != KIND_TABLE ? __ballot_sync(0xffffffffu, over) : 0u;
     }
   };
 
@@ -238,25 +242,44 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
           }
         }
       }
-    } else if (!TABLES_ONLY) {  // KIND_NICH
-      VecF<V> mu, sc, c1, c0;
+    } else if (!TABLES_ONLY) {  // KIND_NICH: c1' log2(1 + ((x - mu) s)^2); sum_d c0 is already in base[]
+      VecF<V> mu, sc, c1;
       mu.load(chunk + 0 * KT);
       sc.load(chunk + 1 * KT);
       c1.load(chunk + 2 * KT);
-      c0.load(chunk + 3 * KT);
 #pragma unroll
       for (int r4 = 0; r4 < RW / 4; r4++) {
         const uint4 q = xq[r4];
         const float xs[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const float x = xs[e];
-          if (x == x) {
+        for (int e = 0; e < 4; e++)
 #pragma unroll
-            for (int v = 0; v < V; v++) {
-              const float tt = (x - mu.v[v]) * sc.v[v];
-              acc[r4 * 4 + e][v] += fmaf(c1.v[v], log1p_pos(tt * tt), c0.v[v]);
-            }
+          for (int v = 0; v < V; v++) {
+            const float tt = (xs[e] - mu.v[v]) * sc.v[v];
+            acc[r4 * 4 + e][v] = fmaf(c1.v[v], log2_1p_pos(tt * tt), acc[r4 * 4 + e][v]);
+          }
+      }
+      // masked cells: undo the x = 0 term and the c0 that base[] carries for this feature (rare)
+#pragma unroll
+      for (int j = 0; j < RL; j++) {
+        uint32_t m = ovf_cur[j];
+        if (m) {
+          VecF<V> c0;
+          c0.load(chunk + 3 * KT);
+          float undo[V];
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const float tt = (0.f - mu.v[v]) * sc.v[v];
+            undo[v] = -fmaf(c1.v[v], log2_1p_pos(tt * tt), c0.v[v]);
+          }
+          while (m) {
+            const int rr = j * 32 + __ffs(m) - 1;
+            m &= m - 1;
+#pragma unroll
+            for (int r = 0; r < RW; r++)
+              if (r == rr)
+#pragma unroll
+                for (int v = 0; v < V; v++) acc[r][v] += undo[v];
           }
         }
       }

@@ -97,11 +97,12 @@ struct msb_state {
   std::vector<void *> cols;
   int32_t *d_assign = nullptr;
   size_t region_rows = 0, max_chunk_rows = 0;
-  bool has_niw = false, has_scalar = false, tables_only = false, has_dd = false;
+  bool has_niw = false, has_scalar = false, tables_only = false, has_dd = false, has_nich = false;
   // workspaces
   float *d_params = nullptr; size_t params_cap = 0;
   float *d_scores = nullptr; size_t scores_cap = 0;
   float *d_base = nullptr; size_t base_cap = 0;
+  float *d_base_score = nullptr; size_t base_score_cap = 0;  // base + row-independent nich terms, for the score kernel
   int32_t *d_col2slot = nullptr; size_t col_cap = 0;
   int64_t *d_slot2gid = nullptr;
   int32_t *d_newslot = nullptr, *d_newcol = nullptr; size_t row_cap = 0;
@@ -400,7 +401,7 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
         f.coltype = m.dim + 1 <= 256 ? COL_U8 : (m.dim + 1 <= 65536 ? COL_U16 : COL_U32);
         break;
       case MSB_FAMILY_GP: f.kind = KIND_GP; f.coltype = COL_U32; f.ncat = 1; st->has_scalar = true; break;
-      case MSB_FAMILY_NICH: f.kind = KIND_NICH; f.coltype = COL_F32; st->has_scalar = true; break;
+      case MSB_FAMILY_NICH: f.kind = KIND_NICH; f.coltype = COL_F32; st->has_scalar = true; st->has_nich = true; break;
       case MSB_FAMILY_NIW: f.kind = KIND_NIW; f.coltype = COL_F32; st->has_niw = true; break;
     }
   }
@@ -449,7 +450,7 @@ extern "C" MSB_API int msb_state_destroy(msb_state *st) {
   for (size_t d = 0; d < st->D; d++) { cudaFree(st->d_niwW[d]); cudaFree(st->d_niwBias[d]); cudaFree(st->d_niwCoef[d]); cudaFree(st->d_niwB[d]); }
   cudaFree(st->d_feats); cudaFree(st->d_feats_scalar); cudaFree(st->d_hp); cudaFree(st->d_ss); cudaFree(st->d_delta); cudaFree(st->d_counter);
   cudaFree(st->d_slot2gid); cudaFree(st->d_assign); cudaFree(st->d_params); cudaFree(st->d_scores);
-  cudaFree(st->d_base); cudaFree(st->d_col2slot); cudaFree(st->d_newslot); cudaFree(st->d_newcol); cudaFree(st->d_uniforms);
+  cudaFree(st->d_base); cudaFree(st->d_base_score); cudaFree(st->d_col2slot); cudaFree(st->d_newslot); cudaFree(st->d_newcol); cudaFree(st->d_uniforms);
   for (auto &pe : st->events) for (auto &e : pe.e) cudaEventDestroy(e);
   delete st;
   return MSB_OK;
@@ -807,6 +808,12 @@ static int build_params(msb_state *st) {
     dim3 grid((unsigned)st->D, (unsigned)ktiles);
     LAUNCH(ctx, build_params_kernel, grid, 256, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot, (int)K,
            (int)KT, st->region_rows, st->d_params);
+    MSB_TRY(ensure(&st->d_base_score, &st->base_score_cap, st->ld));
+    CU_TRY(cudaMemcpyAsync(st->d_base_score, st->d_base, sizeof(float) * st->ld, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (st->has_nich) {  // fold sum_d c0 of the nich features into the score kernel's base[]
+      LAUNCH(ctx, nich_c0_sum_kernel, cdiv(st->ld, 128), 128, 0, st->d_feats, (int)st->D, st->d_params, st->region_rows,
+             (int)KT, (int)st->ld, st->d_base_score);
+    }
   }
   if (st->has_niw) {
     for (size_t d = 0; d < st->D; d++) {
@@ -848,7 +855,7 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
     const size_t smem = (size_t)S * stage + fixed;
     if (smem > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "score kernel shared memory does not fit");
     dim3 grid(cdiv(nrows, (size_t)c.NW * c.RW), (unsigned)ktiles);
-#define MSB_SCORE_ARGS st->d_feats_scalar, (int)st->n_scalar, st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base, \
+#define MSB_SCORE_ARGS st->d_feats_scalar, (int)st->n_scalar, st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base_score, \
                        scores, st->ld, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K
 #define MSB_SCORE_LAUNCH(V_, RW_, NW_)                                                                         \
     do {                                                                                                       \
