@@ -21,6 +21,10 @@ struct FeatDev {
   uint32_t rowoff;    // first row of the chunk inside a k-tile region
   uint32_t ss_w;      // doubles per group slot
   const void *col;    // Value-typed column, n elements (niw: n x dim floats)
+  const uint32_t *scol;     // score column: u32 table row index (always a valid chunk row) or f32 value (masked -> 0)
+  const uint32_t *slowmask; // per 32-row block: rows that need the score kernel's slow path (gp overflow, nich masked)
+  uint32_t has_slow;        // any bit set in slowmask
+  uint32_t pad_;
   uint64_t hp_off;    // into hp[]
   uint64_t ss_off;    // into ss[] / delta[]: block[slot * ss_w + j]
   double asum;        // dd: sum of alphas
@@ -89,6 +93,42 @@ __global__ void pack_kernel(const uint8_t *__restrict__ data, const uint8_t *__r
     if (f.coltype == COL_U8) ((uint8_t *)f.col)[row] = (uint8_t)x;
     else if (f.coltype == COL_U16) ((uint16_t *)f.col)[row] = (uint16_t)x;
     else ((uint32_t *)f.col)[row] = x;
+  }
+}
+
+// Score columns: what the score kernel streams.  One u32 per (row, feature): the chunk row to look up
+// (masked cells and gp counts beyond the table point at the all-zero row) or the f32 value (masked -> 0),
+// plus a bitmask per 32-row block of the cells that need the slow path.  Rows [n, n_pad) are padding.
+__global__ void scorecol_kernel(const FeatDev *__restrict__ feats, int nfeat, size_t n, size_t n_pad,
+                                uint32_t *__restrict__ any_slow) {
+  const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // n_pad is a multiple of the block size
+  const int d = blockIdx.y;
+  const FeatDev f = feats[d];
+  if (f.kind == KIND_NIW) return;
+  uint32_t out;
+  bool slow = false;
+  if (f.kind == KIND_NICH) {
+    const float x = row < n ? ((const float *)f.col)[row] : 0.f;
+    slow = x != x;
+    out = slow ? 0u : __float_as_uint(x);
+  } else if (f.kind == KIND_GP) {
+    const uint32_t x = row < n ? ((const uint32_t *)f.col)[row] : GP_SENTINEL;
+    slow = x != GP_SENTINEL && x >= f.ncat;
+    out = x < f.ncat ? x : f.ncat;
+  } else {
+    uint32_t x = f.ncat;
+    if (row < n) {
+      if (f.coltype == COL_U8) x = ((const uint8_t *)f.col)[row];
+      else if (f.coltype == COL_U16) x = ((const uint16_t *)f.col)[row];
+      else x = ((const uint32_t *)f.col)[row];
+    }
+    out = x < f.ncat ? x : f.ncat;
+  }
+  const_cast<uint32_t *>(f.scol)[row] = out;
+  const uint32_t m = __ballot_sync(0xffffffffu, slow);
+  if ((threadIdx.x & 31) == 0) {
+    const_cast<uint32_t *>(f.slowmask)[row >> 5] = m;
+    if (m) any_slow[d] = 1u;
   }
 }
 
@@ -321,13 +361,14 @@ __global__ void sample_kernel(const float *__restrict__ scores, size_t ld, int K
 
 // The same walk over the blocked layout the sweep's score kernel writes (msb_score.cuh): thread =
 // row, element k of the row at s[k * 32]; every load is a fully coalesced 128-byte warp access.
-__global__ void sample_blocked_kernel(const float *__restrict__ scores, size_t ld, int K, size_t nrows,
+__global__ void sample_blocked_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int K, size_t nrows,
                                       const float *__restrict__ uniforms, uint64_t seed, uint64_t sweep,
                                       uint64_t row_id0, const int32_t *__restrict__ col2slot,
                                       int32_t *__restrict__ out_col, int32_t *__restrict__ out_slot) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
-  const float *s = scores + (i / 32) * ld * 32 + (i % 32);
+  const size_t loc = i + skip;  // position in the buffer, whose origin is a multiple of 128 rows
+  const float *s = scores + (loc / 32) * ld * 32 + (loc % 32);
   float m = s[0];
 #pragma unroll 8
   for (int k = 1; k < K; k++) m = fmaxf(m, s[(size_t)k * 32]);
@@ -347,10 +388,11 @@ __global__ void sample_blocked_kernel(const float *__restrict__ scores, size_t l
 }
 
 // blocked -> row-major copy of a score matrix (diagnostics / tests)
-__global__ void unblock_kernel(const float *__restrict__ blocked, size_t ld, size_t nrows, int K, float *__restrict__ out) {
+__global__ void unblock_kernel(const float *__restrict__ blocked, size_t ld, size_t skip, size_t nrows, int K,
+                               float *__restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows * (size_t)K) return;
-  const size_t row = i / K, col = i % K;
+  const size_t row = i / K + skip, col = i % K;
   out[i] = blocked[((row / 32) * ld + col) * 32 + (row % 32)];
 }
 

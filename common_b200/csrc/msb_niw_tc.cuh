@@ -103,7 +103,7 @@ __global__ void niw_pack_b_kernel(const float *__restrict__ W, int ncols, float 
 __global__ void __launch_bounds__(niwtc::THREADS, 1)
 niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const float *__restrict__ bias,
               const float *__restrict__ coef, int ncols, float *__restrict__ scores, size_t ld, size_t row_lo,
-              size_t row_hi) {
+              size_t row_hi, int num_gb_lanes) {
   using namespace niwtc;
   extern __shared__ __align__(1024) unsigned char niw_smem[];
   unsigned char *sm = niw_smem;
@@ -117,8 +117,14 @@ niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const 
   const size_t nrows = row_hi - row_lo;
   const int nRT = (int)((nrows + TM - 1) / TM);
   const int nGB = (ncols + GB - 1) / GB;
-  const long long total = (long long)nRT * nGB;
-  const long long w_lo = total * blockIdx.x / gridDim.x, w_hi = total * (blockIdx.x + 1) / gridDim.x;
+  // Schedule: the grid is G x P CTAs.  CTA (g, p) keeps group block g (then g + G, ...) resident and sweeps
+  // the p-th slice of the row tiles, so the G CTAs of a slice read the same X tiles at about the same time:
+  // X streams from HBM once per sweep and is shared through L2 instead of being re-read once per group block.
+  // (lanes with a smaller index get the leftover CTAs: P_g = number of CTAs c with c % G == g.)
+  const int G = (int)num_gb_lanes;
+  const int g0 = (int)blockIdx.x % G, part = (int)blockIdx.x / G;
+  const int P = ((int)gridDim.x - g0 + G - 1) / G;
+  const int rt_lo = (int)((long long)nRT * part / P), rt_hi = (int)((long long)nRT * (part + 1) / P);
 
   if (tid == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
@@ -142,33 +148,45 @@ niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const 
 
   if (warp < 4) {
     // ===== producers: X tile (fp32) -> tf32 hi / lo halves in core-matrix layout =====
-    long long h = 0;  // half-tile counter
-    for (long long w = w_lo; w < w_hi; w++) {
-      const int rt = (int)(w % nRT);
+    // The A operand does not depend on the group block: the producers just cycle through this CTA's row
+    // tiles.  Global loads for half-tile h + 1 are issued before waiting for the buffer of half-tile h, so
+    // their latency hides behind the MMAs instead of serialising with them.
+    const int n_mine = rt_hi - rt_lo;
+    const int ngb_mine = (nGB - g0 + G - 1) / G;
+    const long long total_h = 2ll * n_mine * ngb_mine;
+    auto load_half = [&](long long h, float4 (&v)[8]) {
+      const int rt = rt_lo + (int)((h >> 1) % n_mine), half = (int)(h & 1);
       const size_t row = row_lo + (size_t)rt * TM + tid;  // tid in [0,128): one row per thread
+      const float4 *src = reinterpret_cast<const float4 *>(X + row * D) + half * 8;
       const bool ok = row < row_hi;
-      const float4 *src = reinterpret_cast<const float4 *>(X + row * D);
-      for (int half = 0; half < 2; half++, h++) {
-        const int buf = (int)(h & 1);
-        if (h >= 2) mbar_wait(smem_u32(&bars[4 + buf]), (uint32_t)(((h >> 1) - 1) & 1));  // MMAs that read this buffer are done
-        unsigned char *hi_base = sA + (size_t)buf * 2 * A_HALF_BYTES;
-        unsigned char *lo_base = hi_base + A_HALF_BYTES;
 #pragma unroll
-        for (int c = 0; c < 8; c++) {  // 8 chunks of 4 k
-          float4 v = ok ? __ldg(src + half * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 vh, vl;
-          vh.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); vl.x = v.x - vh.x;
-          vh.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); vl.y = v.y - vh.y;
-          vh.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); vl.z = v.z - vh.z;
-          vh.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); vl.w = v.w - vh.w;
-          const uint32_t off = core_off((uint32_t)tid, (uint32_t)c * 4, TM / 8);
-          *reinterpret_cast<float4 *>(hi_base + off) = vh;
-          *reinterpret_cast<float4 *>(lo_base + off) = vl;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars[2 + buf]));
+      for (int c = 0; c < 8; c++) v[c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 cur[8], nxt[8];
+    if (total_h > 0) load_half(0, cur);
+    for (long long h = 0; h < total_h; h++) {
+      if (h + 1 < total_h) load_half(h + 1, nxt);
+      const int buf = (int)(h & 1);
+      if (h >= 2) mbar_wait(smem_u32(&bars[4 + buf]), (uint32_t)(((h >> 1) - 1) & 1));  // MMAs that read this buffer are done
+      unsigned char *hi_base = sA + (size_t)buf * 2 * A_HALF_BYTES;
+      unsigned char *lo_base = hi_base + A_HALF_BYTES;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {  // 8 chunks of 4 k
+        const float4 v = cur[c];
+        float4 vh, vl;
+        vh.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); vl.x = v.x - vh.x;
+        vh.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); vl.y = v.y - vh.y;
+        vh.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); vl.z = v.z - vh.z;
+        vh.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); vl.w = v.w - vh.w;
+        const uint32_t off = core_off((uint32_t)tid, (uint32_t)c * 4, TM / 8);
+        *reinterpret_cast<float4 *>(hi_base + off) = vh;
+        *reinterpret_cast<float4 *>(lo_base + off) = vl;
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[2 + buf]));
+#pragma unroll
+      for (int c = 0; c < 8; c++) cur[c] = nxt[c];
     }
   } else if (warp == 8) {
     // ===== MMA issuer (one elected lane) =====
@@ -176,8 +194,8 @@ niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const 
       long long h = 0, t = 0;
       int cur_gb = -1;
       uint32_t b_loads = 0;
-      for (long long w = w_lo; w < w_hi; w++, t++) {
-        const int gb = (int)(w / nRT);
+      for (int gb = g0; gb < nGB; gb += G)
+      for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
         if (gb != cur_gb) {  // (re)load the resident B operand
           if (cur_gb >= 0) {
             mma_commit(smem_u32(&bars[1]));
@@ -220,8 +238,8 @@ niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const 
     const int ew = warp & 3;
     const int etid = tid - 128;  // 0..127
     long long t = 0;
-    for (long long w = w_lo; w < w_hi; w++, t++) {
-      const int gb = (int)(w / nRT), rt = (int)(w % nRT);
+    for (int gb = g0; gb < nGB; gb += G)
+    for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
       const int acc = (int)(t & 1);
       float *sb = sBias + (size_t)acc * (TN + 16);
       // stage this block's bias and coefficients (the previous use of this buffer ended two tiles ago)
@@ -293,10 +311,11 @@ static inline int niw_tc_score(cudaStream_t stream, uint64_t *launches, const fl
   niw_pack_b_kernel<<<nGB, 256, 0, stream>>>(W, (int)ncols, Bop);
   (*launches)++;
   const long long nRT = (long long)((row_hi - row_lo + niwtc::TM - 1) / niwtc::TM);
-  const long long total = nRT * nGB;
-  const int grid = (int)std::min<long long>(total, sm_count);
-  niw_tc_kernel<<<grid, niwtc::THREADS, niwtc::SMEM_BYTES, stream>>>(X + row_lo * 0, Bop, bias, coef, (int)ncols, scores, ld,
-                                                                      row_lo, row_hi);
+  const int G = std::min(nGB, sm_count);
+  // as many CTAs as SMs, but never more than one per (group block, row tile)
+  const int grid = (int)std::max<long long>(G, std::min<long long>(sm_count, (long long)G * nRT));
+  niw_tc_kernel<<<grid, niwtc::THREADS, niwtc::SMEM_BYTES, stream>>>(X, Bop, bias, coef, (int)ncols, scores, ld, row_lo,
+                                                                      row_hi, G);
   (*launches)++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { err = std::string("niw_tc_kernel launch: ") + cudaGetErrorString(e); return MSB_ERR_CUDA; }

@@ -32,12 +32,14 @@ __device__ __forceinline__ void store_vec(float *p, const float *a) {
 
 // compact per-feature record kept in shared memory by the score kernel
 struct FeatS {
-  const void *col;
-  uint32_t rowoff;  // first chunk row inside the k-tile region
-  uint32_t rows;    // chunk rows
+  const uint32_t *scol;      // score column (u32 chunk-row index, or f32 value)
+  const uint32_t *slowmask;  // per 32-row block bitmask of slow-path cells
+  const void *col;           // value column (raw gp counts for the slow path)
+  uint32_t rowoff;           // first chunk row inside the k-tile region
+  uint32_t rows;             // chunk rows
   uint32_t ncat;
   uint16_t kind;
-  uint16_t coltype;
+  uint16_t has_slow;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,36 +83,43 @@ __device__ __noinline__ float gp_overflow_score(const FeatDev *f, const double *
 }
 
 // Output layouts of the N x K score matrix:
-//   row-major   scores[(row - row_lo) * ld + col]                     (the API's observable output)
-//   blocked     scores[((row - row_lo) / 32 * ld + col) * 32 + (row - row_lo) % 32]
+//   row-major   scores[(row - row_org) * ld + col]                     (the API's observable output)
+//   blocked     scores[((row - row_org) / 32 * ld + col) * 32 + (row - row_org) % 32]
 //               32-row blocks, group-major inside a block: the sampler walks one row per thread and
 //               reads it fully coalesced.  Internal to the sweep.
-// TABLES_ONLY: every feature is a lookup table (bb / dd): no kind dispatch, no gp / nich code.
+// row_org (a multiple of 128, <= row_lo) is the first row the grid covers; rows < row_lo are not written.
+// TABLES_ONLY: every feature is a lookup table without slow-path cells: no kind dispatch at all.
+//
+// Stage layout (one per feature in flight): [row values: NW*RW u32][slow masks: NW*RW/32 u32][pad to 128][chunk]
 template <int V, int RW, int NW, bool BLOCKED, bool TABLES_ONLY>
 __global__ void __launch_bounds__(NW * 32, 1)
 score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restrict__ params, size_t region_rows,
              uint32_t stage_bytes, int S, const float *__restrict__ base, float *__restrict__ scores, size_t ld,
-             size_t row_lo, size_t row_hi, const double *__restrict__ hp, const double *__restrict__ ss,
-             const int32_t *__restrict__ col2slot, int ncols) {
+             size_t row_org, size_t row_lo, size_t row_hi, const double *__restrict__ hp,
+             const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols) {
   constexpr int KT = 32 * V;
-  constexpr int RL = RW / 32;  // rows per lane whose x this lane loads
-  static_assert(RW % 32 == 0, "RW must be a multiple of 32");
+  constexpr int RL = RW / 32;
+  constexpr int RB = NW * RW;                                   // rows per block
+  constexpr uint32_t X_BYTES = RB * 4, M_BYTES = RB / 8;        // row values, slow masks
+  constexpr uint32_t CHUNK_OFF = (X_BYTES + M_BYTES + 127) / 128 * 128;
+  static_assert(RW % 32 == 0 && M_BYTES % 16 == 0, "tile sizes must keep the bulk copies 16-byte granular");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [S stages | per-warp exchange buffers (double) | mbarriers full[S], empty[S] | feature table]
+  // layout: [S stages | mbarriers full[S], empty[S] | feature table]
   unsigned char *stages = smem_raw;
-  uint32_t *xbuf_all = reinterpret_cast<uint32_t *>(smem_raw + (size_t)S * stage_bytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(xbuf_all + 2 * NW * RW);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * stage_bytes);
   FeatS *ftab = reinterpret_cast<FeatS *>(bars + 2 * S);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kt = blockIdx.y;
   const float *region = params + (size_t)kt * region_rows * KT;
-  const size_t row0 = row_lo + ((size_t)blockIdx.x * NW + warp) * RW;
+  const size_t blk_row0 = row_org + (size_t)blockIdx.x * RB;   // multiple of 128
+  const size_t row0 = blk_row0 + (size_t)warp * RW;
 
   for (int i = tid; i < nfeat; i += NW * 32) {
     const FeatDev f = feats[i];
     FeatS t;
-    t.col = f.col; t.rowoff = f.rowoff; t.rows = f.rows; t.ncat = f.ncat;
-    t.kind = (uint16_t)f.kind; t.coltype = (uint16_t)f.coltype;
+    t.scol = f.scol; t.slowmask = f.slowmask; t.col = f.col;
+    t.rowoff = f.rowoff; t.rows = f.rows; t.ncat = f.ncat;
+    t.kind = (uint16_t)f.kind; t.has_slow = (uint16_t)(f.has_slow != 0);
     ftab[i] = t;
   }
   if (tid == 0) {
@@ -122,63 +131,20 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
   }
   __syncthreads();
 
-  auto issue = [&](int d, int s) {  // thread 0 only: chunk of feature d -> stage s
+  // thread 0 only: everything feature d needs -> stage s (row values, slow masks, parameter chunk)
+  auto issue = [&](int d, int s) {
     const FeatS t = ftab[d];
-    const uint32_t bytes = t.rows * (uint32_t)(KT * sizeof(float));
+    const uint32_t cbytes = t.rows * (uint32_t)(KT * sizeof(float));
     const uint32_t bar = smem_u32(&bars[s]);
-    mbar_expect_tx(bar, bytes);
-    bulk_g2s(smem_u32(stages + (size_t)s * stage_bytes), region + (size_t)t.rowoff * KT, bytes, bar);
+    const uint32_t dst = smem_u32(stages + (size_t)s * stage_bytes);
+    const bool slow = !TABLES_ONLY && t.has_slow;
+    mbar_expect_tx(bar, cbytes + X_BYTES + (slow ? M_BYTES : 0u));
+    bulk_g2s(dst, t.scol + blk_row0, X_BYTES, bar);
+    if (slow) bulk_g2s(dst + X_BYTES, t.slowmask + (blk_row0 >> 5), M_BYTES, bar);
+    bulk_g2s(dst + CHUNK_OFF, region + (size_t)t.rowoff * KT, cbytes, bar);
   };
   if (tid == 0)
     for (int d = 0; d < S && d < nfeat; d++) issue(d, d);
-
-  // raw value of this lane's rows for feature d (bit pattern: table index, count, or float)
-  uint32_t valid = 0;
-#pragma unroll
-  for (int j = 0; j < RL; j++) valid |= (row0 + j * 32 + lane < row_hi ? 1u : 0u) << j;
-  const size_t myrow = row0 + lane;
-  auto load_x = [&](int d, uint32_t (&x)[RL]) {
-    const FeatS t = ftab[d];
-    const size_t gcol = __cvta_generic_to_global(t.col);
-#pragma unroll
-    for (int j = 0; j < RL; j++) {
-      if (TABLES_ONLY) x[j] = t.ncat;
-      else x[j] = t.kind == KIND_GP ? GP_SENTINEL : (t.kind == KIND_NICH ? 0x7fc00000u : t.ncat);
-      if (valid & (1u << j)) {
-        const size_t r = myrow + j * 32;
-        uint32_t v;
-        if (t.coltype == COL_U8) asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(gcol + r));
-        else if (t.coltype == COL_U16) asm("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(gcol + 2 * r));
-        else asm("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(gcol + 4 * r));  // u32 counts and f32 values alike
-        x[j] = v;
-      }
-    }
-  };
-  // Per-warp exchange buffer: each lane publishes the table offset (x * KT, in floats) or the float
-  // value of the rows it loaded; every lane then reads all RW of them back as broadcast 128-bit
-  // shared loads (4 rows per wavefront).  Published one feature ahead, into the other half.
-  uint32_t *xbuf = xbuf_all + warp * 2 * RW;
-  // (gp counts beyond the table publish the zero row and are flagged in a per-32-row ballot mask)
-  auto publish = [&](int d, const uint32_t (&x)[RL], uint32_t (&ovf)[RL]) {
-    const FeatS t = ftab[d];
-#pragma unroll
-    for (int j = 0; j < RL; j++) {
-      uint32_t pub = x[j];
-      bool over = false;
-      if (TABLES_ONLY) pub = x[j] * KT;
-      else if (t.kind == KIND_GP) {
-        const uint32_t cap = t.ncat;
-        over = x[j] != GP_SENTINEL && x[j] >= cap;
-        pub = (x[j] < cap ? x[j] : cap) * KT;
-      } else if (t.kind == KIND_TABLE) pub = x[j] * KT;
-      else {  // nich: a masked cell (NaN) is scored as x = 0 in the branch-free loop and undone afterwards
-        over = pub == 0x7fc00000u || __uint_as_float(pub) != __uint_as_float(pub);
-        if (over) pub = 0u;
-      }
-      xbuf[(d & 1) * RW + j * 32 + lane] = pub;
-      if (!TABLES_ONLY) ovf[j] = t.kind != KIND_TABLE ? __ballot_sync(0xffffffffu, over) : 0u;
-    }
-  };
 
   float acc[RW][V];
 #pragma unroll
@@ -186,34 +152,29 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
 #pragma unroll
     for (int v = 0; v < V; v++) acc[r][v] = 0.f;
 
-  uint32_t xa[RL], xb[RL];  // xa: feature d+1 (to publish this iteration), xb: feature d+2 (in flight)
-  uint32_t ovf_cur[RL], ovf_next[RL];
-#pragma unroll
-  for (int j = 0; j < RL; j++) ovf_cur[j] = ovf_next[j] = 0u;
-  if (nfeat > 0) { load_x(0, xa); publish(0, xa, ovf_cur); }
-  if (nfeat > 1) load_x(1, xa);
   int s = 0;
   uint32_t parity = 0;
-
   for (int d = 0; d < nfeat; d++) {
-    if (d + 2 < nfeat) load_x(d + 2, xb);               // global loads two features ahead
-    if (d + 1 < nfeat) publish(d + 1, xa, ovf_next);    // shared-memory publish one feature ahead
     const FeatS t = ftab[d];
-    __syncwarp();  // feature d's publish (previous iteration) is visible to the whole warp
     mbar_wait(smem_u32(&bars[s]), parity);
-    const float *chunk = reinterpret_cast<const float *>(stages + (size_t)s * stage_bytes) + lane * V;
-    const uint32_t *xcur = xbuf + (d & 1) * RW;
-    const uint4 *xq = reinterpret_cast<const uint4 *>(xcur);
+    const unsigned char *st = stages + (size_t)s * stage_bytes;
+    // this warp's RW row values, read as broadcast 128-bit loads (4 rows per shared-memory wavefront)
+    const uint4 *xq = reinterpret_cast<const uint4 *>(st) + warp * (RW / 4);
+    const float *chunk = reinterpret_cast<const float *>(st + CHUNK_OFF) + lane * V;
+    uint32_t slow[RL];
+#pragma unroll
+    for (int j = 0; j < RL; j++)
+      slow[j] = (!TABLES_ONLY && t.has_slow) ? reinterpret_cast<const uint32_t *>(st + X_BYTES)[warp * RL + j] : 0u;
 
     if (TABLES_ONLY || t.kind != KIND_NICH) {
 #pragma unroll
       for (int r4 = 0; r4 < RW / 4; r4++) {
         const uint4 q = xq[r4];
-        const uint32_t off[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t idx[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           VecF<V> tv;
-          tv.load(chunk + off[e]);
+          tv.load(chunk + (size_t)idx[e] * KT);
 #pragma unroll
           for (int v = 0; v < V; v++) acc[r4 * 4 + e][v] += tv.v[v];
         }
@@ -222,7 +183,7 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
         const uint32_t *raw = reinterpret_cast<const uint32_t *>(t.col);
 #pragma unroll
         for (int j = 0; j < RL; j++) {
-          uint32_t m = ovf_cur[j];
+          uint32_t m = slow[j];
           while (m) {
             const int rr = j * 32 + __ffs(m) - 1;
             m &= m - 1;
@@ -242,7 +203,7 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
           }
         }
       }
-    } else if (!TABLES_ONLY) {  // KIND_NICH: c1' log2(1 + ((x - mu) s)^2); sum_d c0 is already in base[]
+    } else {  // KIND_NICH: c1' log2(1 + ((x - mu) s)^2); sum_d c0 is already in base[]
       VecF<V> mu, sc, c1;
       mu.load(chunk + 0 * KT);
       sc.load(chunk + 1 * KT);
@@ -259,10 +220,10 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
             acc[r4 * 4 + e][v] = fmaf(c1.v[v], log2_1p_pos(tt * tt), acc[r4 * 4 + e][v]);
           }
       }
-      // masked cells: undo the x = 0 term and the c0 that base[] carries for this feature (rare)
+      // masked cells were scored as x = 0: undo that term and the c0 that base[] carries for this feature (rare)
 #pragma unroll
       for (int j = 0; j < RL; j++) {
-        uint32_t m = ovf_cur[j];
+        uint32_t m = slow[j];
         if (m) {
           VecF<V> c0;
           c0.load(chunk + 3 * KT);
@@ -284,7 +245,7 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
         }
       }
     }
-    // release the stage; thread 0 refills it with chunk d + S once every warp has released it
+    // release the stage; thread 0 refills it with feature d + S once every warp has released it
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&bars[S + s]));
     if (tid == 0 && d + S < nfeat) {
@@ -292,8 +253,6 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
       issue(d + S, s);
     }
     if (++s == S) { s = 0; parity ^= 1u; }
-#pragma unroll
-    for (int j = 0; j < RL; j++) { xa[j] = xb[j]; ovf_cur[j] = ovf_next[j]; }
   }
 
   // epilogue: + log(pseudocount) (group_manager.hpp:274-283)
@@ -303,11 +262,11 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
 #pragma unroll
     for (int r = 0; r < RW; r++) {
       const size_t row = row0 + r;
-      if (row < row_hi) {
+      if (row >= row_lo && row < row_hi) {
         float o[V];
 #pragma unroll
         for (int v = 0; v < V; v++) o[v] = acc[r][v] + b.v[v];
-        store_vec<V>(scores + (row - row_lo) * ld + (size_t)kt * KT + lane * V, o);
+        store_vec<V>(scores + (row - row_org) * ld + (size_t)kt * KT + lane * V, o);
       }
     }
   } else {
@@ -323,7 +282,7 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
 #pragma unroll
         for (int v = 0; v < V; v++) tile[r * (KT + 1) + lane * V + v] = acc[j * 32 + r][v] + b.v[v];
       __syncwarp();
-      const size_t rb = (row0 - row_lo) / 32 + j;  // row0 - row_lo is a multiple of 32
+      const size_t rb = (row0 - row_org) / 32 + j;
       if (row0 + (size_t)j * 32 < row_hi) {
         float *dst = scores + (rb * ld + (size_t)kt * KT) * 32 + lane;
 #pragma unroll 8

@@ -91,6 +91,7 @@ struct msb_state {
   std::vector<char> slot_dirty;   // suffstats of the slot may be non-zero (set by any update / set_ss)
   bool all_unassigned = true;     // no entity has been assigned since bind
   void *col_slab = nullptr;       // one allocation backing every column
+  size_t n_pad = 0;               // rows of the (padded) score columns
   // data
   msb_dataview *dv = nullptr;
   size_t n = 0;
@@ -113,6 +114,7 @@ struct msb_state {
   // last score
   int cfg = 1, V = 2; size_t ld = 0, last_rows = 0, last_cols = 0;
   bool last_blocked = false;
+  size_t last_skip = 0;  // rows between the score buffer's origin (row_origin) and the first valid row
   std::vector<int32_t> h_col2slot;
   std::vector<size_t> h_colgid;
   std::vector<PhaseEvents> events;
@@ -489,9 +491,7 @@ static void layout_chunks(msb_state *st) {
   }
   st->region_rows = ro;
   st->max_chunk_rows = mx;
-  st->tables_only = true;
-  for (auto &f : st->feats) if (f.rows > 0 && f.kind != KIND_TABLE) st->tables_only = false;
-  if (getenv("MSB_NO_TABLES_ONLY")) st->tables_only = false;
+  st->tables_only = false;  // decided at the end of bind, once the slow-path masks are known
   st->feats_dirty = true;
 }
 
@@ -511,19 +511,28 @@ extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
   cudaFree(st->d_assign); st->d_assign = nullptr;
   st->dv = dv; st->n = dv->n;
   const size_t n = std::max<size_t>(dv->n, 1);
-  std::vector<size_t> coff(st->D);
+  std::vector<size_t> coff(st->D), soff(st->D), moff(st->D);
   size_t slab = 0;
+  const size_t n_pad = (n + 1024 + 1023) / 1024 * 1024;  // tile-granular kernels read whole 1024-row tiles
+  st->n_pad = n_pad;
   for (size_t d = 0; d < st->D; d++) {
     const FeatDev &f = st->feats[d];
     const size_t bytes = f.kind == KIND_NIW ? n * f.dim * sizeof(float) : n * (f.coltype == COL_U8 ? 1 : f.coltype == COL_U16 ? 2 : 4);
     coff[d] = slab;
-    slab += (bytes + 4096 + 255) / 256 * 256;  // padded: tile-granular kernels may read past the last row
+    slab += (bytes + 4096 + 255) / 256 * 256;
+    if (f.kind != KIND_NIW) {
+      soff[d] = slab; slab += n_pad * sizeof(uint32_t);
+      moff[d] = slab; slab += n_pad / 32 * sizeof(uint32_t);
+    }
   }
   CU_TRY(cudaMalloc(&st->col_slab, slab));
   for (size_t d = 0; d < st->D; d++) {
     FeatDev &f = st->feats[d];
     st->cols[d] = (char *)st->col_slab + coff[d];
     f.col = st->cols[d];
+    f.scol = f.kind != KIND_NIW ? (const uint32_t *)((char *)st->col_slab + soff[d]) : nullptr;
+    f.slowmask = f.kind != KIND_NIW ? (const uint32_t *)((char *)st->col_slab + moff[d]) : nullptr;
+    f.has_slow = 0;
     f.src_off = dv->off[d]; f.msk_off = dv->moff[d];
     f.src_prim = (uint32_t)dv->types[d].prim; f.src_n = dv->types[d].n;
   }
@@ -552,6 +561,23 @@ extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
     for (size_t i = 0; i < gp.size(); i++) st->feats[gp[i]].ncat = std::min<uint32_t>(h_max[i] + 1, cap_limit);
   }
   layout_chunks(st);
+  if (st->has_scalar) {  // score columns + slow-path masks (the gp table sizes are known now)
+    MSB_TRY(sync_small(st));
+    uint32_t *d_any = nullptr;
+    CU_TRY(cudaMalloc(&d_any, sizeof(uint32_t) * st->D));
+    CU_TRY(cudaMemsetAsync(d_any, 0, sizeof(uint32_t) * st->D, ctx->stream));
+    dim3 grid((unsigned)(st->n_pad / 256), (unsigned)st->D);
+    LAUNCH(ctx, scorecol_kernel, grid, 256, 0, st->d_feats, (int)st->D, dv->n, st->n_pad, d_any);
+    std::vector<uint32_t> h_any(st->D);
+    CU_TRY(cudaMemcpyAsync(h_any.data(), d_any, sizeof(uint32_t) * st->D, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_any);
+    bool any = false;
+    for (size_t d = 0; d < st->D; d++) { st->feats[d].has_slow = h_any[d]; any |= h_any[d] != 0; }
+    // the tables-only kernel has no slow path and no nich code: gp features qualify when no count exceeds their table
+    st->tables_only = !any && !st->has_nich && !getenv("MSB_NO_TABLES_ONLY");
+    st->feats_dirty = true;
+  }
   CU_TRY(cudaMalloc(&st->d_assign, sizeof(int32_t) * n));
   CU_TRY(cudaMemsetAsync(st->d_assign, 0xFF, sizeof(int32_t) * n, ctx->stream));  // all -1
   st->all_unassigned = true;
@@ -836,27 +862,33 @@ static int build_params(msb_state *st) {
   return MSB_OK;
 }
 
+// first row the score kernel's grid covers: bulk copies of the row-value tiles need 16-byte aligned sources
+static inline size_t row_origin(size_t row_lo) { return row_lo & ~(size_t)127; }
+
+// scores is indexed from row_origin(row_lo): element (row, col) at (row - org) * ld + col (or blocked)
 static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scores, bool blocked = false) {
   msb_ctx *ctx = st->ctx;
-  const size_t nrows = row_hi - row_lo;
+  const size_t org = row_origin(row_lo);
+  const size_t nrows = row_hi - org;
   const size_t K = st->h_col2slot.size();
   const size_t KT = 32 * (size_t)st->V;
   const size_t ktiles = st->ld / KT;
   if (st->has_scalar) {
     const ScoreCfg c = k_score_cfgs[st->cfg];
-    const size_t xbytes = 2 * (size_t)c.NW * c.RW * sizeof(uint32_t);
-    const size_t fixed = st->n_scalar * sizeof(FeatS) + 2 * 8 * sizeof(uint64_t) + xbytes + 256;
-    size_t stage = (st->max_chunk_rows * KT * sizeof(float) + 127) / 128 * 128;
+    const size_t RB = (size_t)c.NW * c.RW;
+    const size_t chunk_off = (RB * 4 + RB / 8 + 127) / 128 * 128;
+    const size_t fixed = st->n_scalar * sizeof(FeatS) + 2 * 8 * sizeof(uint64_t) + 256;
+    size_t stage = (chunk_off + st->max_chunk_rows * KT * sizeof(float) + 127) / 128 * 128;
     if (stage + fixed > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "parameter chunk does not fit in shared memory");
-    const int S = (int)std::max<size_t>(1, std::min<size_t>(4, (ctx->smem_optin - fixed) / stage));
+    const int S = (int)std::max<size_t>(1, std::min<size_t>(8, (ctx->smem_optin - fixed) / stage));
     // the blocked epilogue transposes 32 x KT tiles through the (drained) stage ring
     const size_t tile = (size_t)c.NW * 32 * (KT + 1) * sizeof(float);
     if (blocked && (size_t)S * stage < tile) stage = ((tile + S - 1) / S + 127) / 128 * 128;
     const size_t smem = (size_t)S * stage + fixed;
     if (smem > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "score kernel shared memory does not fit");
-    dim3 grid(cdiv(nrows, (size_t)c.NW * c.RW), (unsigned)ktiles);
+    dim3 grid(cdiv(nrows, RB), (unsigned)ktiles);
 #define MSB_SCORE_ARGS st->d_feats_scalar, (int)st->n_scalar, st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base_score, \
-                       scores, st->ld, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K
+                       scores, st->ld, org, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K
 #define MSB_SCORE_LAUNCH(V_, RW_, NW_)                                                                         \
     do {                                                                                                       \
       if (blocked && st->tables_only) LAUNCH(ctx, (score_kernel<V_, RW_, NW_, true, true>), grid, NW_ * 32, smem, MSB_SCORE_ARGS);        \
@@ -876,6 +908,7 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
     // no scalar feature: scores start from the CRP term
     LAUNCH(ctx, fill_rows_kernel, cdiv(nrows * st->ld, 256), 256, 0, scores, st->ld, st->d_base, nrows);
   }
+  row_lo = org;  // the NIW kernels below index the score matrix from the same origin
   for (size_t d = 0; d < st->D; d++) {
     const FeatDev &f = st->feats[d];
     if (f.kind != KIND_NIW) continue;
@@ -1057,17 +1090,20 @@ extern "C" MSB_API int msb_state_score_value(msb_state *st, size_t eid, size_t *
   *n = K;
   if (!scores && !gids) return MSB_OK;
   REQUIRE(cap >= K, "buffer too small");
-  MSB_TRY(ensure_scores(st, 1));
+  size_t skip = 0;
   if (!st->has_niw) {
+    MSB_TRY(ensure_scores(st, 1));
     MSB_TRY(sync_small(st));
     LAUNCH(ctx, score_direct_kernel, 1, 128, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot, (int)K,
            st->d_base, st->d_scores, st->ld, eid, eid + 1);
   } else {
+    skip = eid - row_origin(eid);
+    MSB_TRY(ensure_scores(st, skip + 1));
     MSB_TRY(build_params(st));
     MSB_TRY(launch_score(st, eid, eid + 1, st->d_scores));
   }
-  st->last_rows = 1; st->last_cols = K; st->last_blocked = false;
-  if (scores) CU_TRY(cudaMemcpyAsync(scores, st->d_scores, sizeof(float) * K, cudaMemcpyDeviceToHost, ctx->stream));
+  st->last_rows = 1; st->last_cols = K; st->last_blocked = false; st->last_skip = skip;
+  if (scores) CU_TRY(cudaMemcpyAsync(scores, st->d_scores + skip * st->ld, sizeof(float) * K, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
   if (gids) for (size_t c = 0; c < K; c++) gids[c] = st->h_colgid[c];
   return MSB_OK;
@@ -1087,9 +1123,10 @@ extern "C" MSB_API int msb_state_score_rows(msb_state *st, size_t row_lo, size_t
   const size_t nrows = row_hi - row_lo;
   if (!nrows) return MSB_OK;
   const bool direct = getenv("MSB_FORCE_DIRECT") && !st->has_niw;
+  const size_t skip = direct ? 0 : row_lo - row_origin(row_lo);
   // a device destination with the internal leading dimension is written in place
-  float *dst = (on_device && scores && ld == st->ld) ? scores : nullptr;
-  if (!dst) { MSB_TRY(ensure_scores(st, nrows)); dst = st->d_scores; }
+  float *dst = (on_device && scores && ld == st->ld && skip == 0) ? scores : nullptr;
+  if (!dst) { MSB_TRY(ensure_scores(st, nrows + skip)); dst = st->d_scores; }
   if (direct) {
     MSB_TRY(sync_small(st));
     LAUNCH(ctx, score_direct_kernel, (unsigned)nrows, 128, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot,
@@ -1098,10 +1135,10 @@ extern "C" MSB_API int msb_state_score_rows(msb_state *st, size_t row_lo, size_t
     MSB_TRY(build_params(st));
     MSB_TRY(launch_score(st, row_lo, row_hi, dst));
   }
-  st->last_rows = nrows; st->last_cols = K; st->last_blocked = false;
+  st->last_rows = nrows; st->last_cols = K; st->last_blocked = false; st->last_skip = dst == st->d_scores ? skip : 0;
   if (scores && dst != scores) {
     REQUIRE(ld >= K, "ld smaller than the number of groups");
-    CU_TRY(cudaMemcpy2DAsync(scores, sizeof(float) * ld, dst, sizeof(float) * st->ld, sizeof(float) * K, nrows,
+    CU_TRY(cudaMemcpy2DAsync(scores, sizeof(float) * ld, dst + skip * st->ld, sizeof(float) * st->ld, sizeof(float) * K, nrows,
                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (!on_device) CU_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1110,7 +1147,7 @@ extern "C" MSB_API int msb_state_score_rows(msb_state *st, size_t row_lo, size_t
 
 extern "C" MSB_API int msb_state_last_scores(msb_state *st, float **dev_ptr, size_t *ld, size_t *nrows, size_t *ncols) {
   REQUIRE(st, "NULL argument");
-  if (dev_ptr) *dev_ptr = st->d_scores;
+  if (dev_ptr) *dev_ptr = st->d_scores + (st->last_blocked ? 0 : st->last_skip * st->ld);
   if (ld) *ld = st->ld;
   if (nrows) *nrows = st->last_rows;
   if (ncols) *ncols = st->last_cols;
@@ -1124,16 +1161,16 @@ extern "C" MSB_API int msb_state_read_last_scores(msb_state *st, float *out, siz
   if (st->last_blocked) {
     float *tmp = nullptr;
     CU_TRY(cudaMalloc(&tmp, sizeof(float) * st->last_rows * st->last_cols));
-    LAUNCH(st->ctx, unblock_kernel, cdiv(st->last_rows * st->last_cols, 256), 256, 0, st->d_scores, st->ld, st->last_rows,
-           (int)st->last_cols, tmp);
+    LAUNCH(st->ctx, unblock_kernel, cdiv(st->last_rows * st->last_cols, 256), 256, 0, st->d_scores, st->ld, st->last_skip,
+           st->last_rows, (int)st->last_cols, tmp);
     CU_TRY(cudaMemcpy2DAsync(out, sizeof(float) * ld_out, tmp, sizeof(float) * st->last_cols, sizeof(float) * st->last_cols,
                              st->last_rows, cudaMemcpyDeviceToHost, st->ctx->stream));
     CU_TRY(cudaStreamSynchronize(st->ctx->stream));
     cudaFree(tmp);
     return MSB_OK;
   }
-  CU_TRY(cudaMemcpy2DAsync(out, sizeof(float) * ld_out, st->d_scores, sizeof(float) * st->ld, sizeof(float) * st->last_cols,
-                           st->last_rows, cudaMemcpyDeviceToHost, st->ctx->stream));
+  CU_TRY(cudaMemcpy2DAsync(out, sizeof(float) * ld_out, st->d_scores + st->last_skip * st->ld, sizeof(float) * st->ld,
+                           sizeof(float) * st->last_cols, st->last_rows, cudaMemcpyDeviceToHost, st->ctx->stream));
   CU_TRY(cudaStreamSynchronize(st->ctx->stream));
   return MSB_OK;
 }
@@ -1191,9 +1228,10 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
   if (!nrows) return MSB_OK;
   size_t budget_mb = 4096;
   if (const char *e = getenv("MSB_SCORES_MB")) budget_mb = std::max(1, atoi(e));
-  const size_t chunk = std::max<size_t>(1, std::min(nrows, budget_mb * 1024 * 1024 / (st->ld * sizeof(float))));
+  size_t chunk = std::max<size_t>(1, std::min(nrows, budget_mb * 1024 * 1024 / (st->ld * sizeof(float))));
+  if (chunk < nrows) chunk = std::max<size_t>(1024, chunk / 1024 * 1024);
   const size_t nchunks = (nrows + chunk - 1) / chunk;
-  MSB_TRY(ensure_scores(st, chunk));
+  MSB_TRY(ensure_scores(st, chunk + 128));
   MSB_TRY(ensure_rows(st, chunk));
   while (st->events.size() < nchunks + 1) {
     PhaseEvents pe;
@@ -1210,7 +1248,9 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
     const size_t lo = row_lo + c * chunk, hi = std::min(row_hi, lo + chunk);
     PhaseEvents &pe = st->events[c + 1];
     CU_TRY(cudaEventRecord(pe.e[0], ctx->stream));
+    const size_t skip = lo - row_origin(lo);
     MSB_TRY(launch_score(st, lo, hi, st->d_scores, blocked));
+    st->last_skip = skip;
     CU_TRY(cudaEventRecord(pe.e[1], ctx->stream));
     const float *d_u = nullptr;
     if (opts->uniforms) {
@@ -1218,10 +1258,10 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
       d_u = st->d_uniforms;
     }
     if (blocked)
-      LAUNCH(ctx, sample_blocked_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores, st->ld, (int)K, hi - lo, d_u, opts->seed,
+      LAUNCH(ctx, sample_blocked_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores, st->ld, skip, (int)K, hi - lo, d_u, opts->seed,
              opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
     else
-      LAUNCH(ctx, sample_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores, st->ld, (int)K, hi - lo, d_u, opts->seed,
+      LAUNCH(ctx, sample_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores + skip * st->ld, st->ld, (int)K, hi - lo, d_u, opts->seed,
              opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
     CU_TRY(cudaEventRecord(pe.e[2], ctx->stream));
     MSB_TRY(launch_update(st, lo, hi));
