@@ -904,18 +904,29 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
     }
 #undef MSB_SCORE_LAUNCH
 #undef MSB_SCORE_ARGS
-  } else {
-    // no scalar feature: scores start from the CRP term
-    LAUNCH(ctx, fill_rows_kernel, cdiv(nrows * st->ld, 256), 256, 0, scores, st->ld, st->d_base, nrows);
   }
   row_lo = org;  // the NIW kernels below index the score matrix from the same origin
+  // without scalar features the first NIW feature initialises the matrix: the tensor-core kernel writes
+  // base[k] + term directly; the CUDA-core kernel accumulates onto a base-filled matrix
+  bool need_init = !st->has_scalar;
   for (size_t d = 0; d < st->D; d++) {
     const FeatDev &f = st->feats[d];
     if (f.kind != KIND_NIW) continue;
     bool done = false;
+    const bool tc_ok = f.dim == 64 && !getenv("MSB_NO_TENSOR");
+    if (need_init && !tc_ok) {
+      LAUNCH(ctx, fill_rows_kernel, cdiv(nrows * st->ld, 256), 256, 0, scores, st->ld, st->d_base, nrows);
+      need_init = false;
+    }
     MSB_TRY(niw_tc_score(ctx->stream, &ctx->launches, (const float *)f.col, f.dim, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
-                         st->d_niwB[d], K, scores, st->ld, row_lo, row_hi, ctx->sm_count, &done, g_last_error));
+                         st->d_niwB[d], K, scores, st->ld, row_lo, row_hi, ctx->sm_count, need_init ? st->d_base : nullptr,
+                         &done, g_last_error));
+    if (done) need_init = false;
     if (!done) {
+      if (need_init) {
+        LAUNCH(ctx, fill_rows_kernel, cdiv(nrows * st->ld, 256), 256, 0, scores, st->ld, st->d_base, nrows);
+        need_init = false;
+      }
       const size_t smem = ((size_t)f.dim * f.dim + f.dim) * sizeof(float);
       dim3 grid(cdiv(nrows, 128), (unsigned)K);
       LAUNCH(ctx, niw_score_simt_kernel, grid, 128, smem, (const float *)f.col, (int)f.dim, st->d_niwW[d], st->d_niwBias[d],
