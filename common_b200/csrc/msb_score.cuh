@@ -76,6 +76,68 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Sampler over the blocked score layout with the 32-row tile staged in shared memory: the tile
+// ([K][32] floats, contiguous in global memory) is bulk-copied once and the three order-sensitive
+// passes of util.hpp:125-156 (max / exp + double sum / dart scan) run from shared memory, lane = row,
+// conflict-free.  exp(s - m) is computed once (pass 2 overwrites the tile with it).  HBM traffic: the
+// score matrix is read exactly once.  Used when a tile fits (K * 128 bytes per warp).
+// ---------------------------------------------------------------------------------------------------
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+sample_tile_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int K, size_t nrows,
+                   const float *__restrict__ uniforms, uint64_t seed, uint64_t sweep, uint64_t row_id0,
+                   const int32_t *__restrict__ col2slot, int32_t *__restrict__ out_col, int32_t *__restrict__ out_slot) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tile_bytes = (uint32_t)K * 128u;
+  float *tile = reinterpret_cast<float *>(smem_raw + (size_t)warp * tile_bytes);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * tile_bytes) + warp;
+  if (lane == 0) {
+    mbar_init(smem_u32(bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const size_t blk_lo = skip / 32, blk_hi = (skip + nrows + 31) / 32;
+  uint32_t parity = 0;
+  for (size_t blk = blk_lo + (size_t)blockIdx.x * WARPS + warp; blk < blk_hi; blk += (size_t)gridDim.x * WARPS) {
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(bar), tile_bytes);
+      bulk_g2s(smem_u32(tile), scores + blk * ld * 32, tile_bytes, smem_u32(bar));
+    }
+    mbar_wait(smem_u32(bar), parity);
+    parity ^= 1u;
+    const long long i = (long long)(blk * 32 + lane) - (long long)skip;  // row of this lane, relative to the first valid row
+    const bool valid = i >= 0 && (size_t)i < nrows;
+    float *s = tile + lane;
+    float m = s[0];
+#pragma unroll 8
+    for (int k = 1; k < K; k++) m = fmaxf(m, s[k * 32]);
+    double acc_d = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < K; k++) {
+      const float p = msb_expf(__fsub_rn(s[k * 32], m));
+      s[k * 32] = p;
+      acc_d = __dadd_rn(acc_d, (double)p);
+    }
+    const float acc = __double2float_rn(acc_d);
+    float dart = 0.f;
+    if (valid) dart = uniforms ? uniforms[i] : philox_u01(seed, row_id0 + (uint64_t)i, sweep);
+    int pick = K - 1;
+    for (int k = 0; k < K; k++) {
+      dart = __fsub_rn(dart, __fdiv_rn(s[k * 32], acc));
+      if (dart <= 0.f) { pick = k; break; }
+    }
+    if (valid) {
+      if (out_col) out_col[i] = pick;
+      if (out_slot) out_slot[i] = col2slot ? col2slot[pick] : pick;
+    }
+    // the next bulk copy (async proxy) overwrites the tile this warp has just read and written (generic proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+  }
+}
+
 // gp count beyond the lookup table: fp64 closed form straight from the suffstats.  Kept out of line so
 // that its fp64 register pressure stays off the hot loop.
 __device__ __noinline__ float gp_overflow_score(const FeatDev *f, const double *hp, const double *ss, int slot, double xv) {

@@ -172,6 +172,7 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   CU_TRY(opt_in_smem(score_kernel<2, 32, 16, true, true>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<4, 32, 8, true, true>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<1, 32, 8, true, true>, c->smem_optin));
+  CU_TRY(opt_in_smem(sample_tile_kernel<4>, c->smem_optin));
   CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin - 1024));  // it also has a few bytes of static shared memory
   CU_TRY(opt_in_smem(niw_score_simt_kernel, c->smem_optin - 1024));
   MSB_TRY(niw_tc_init(c->smem_optin, g_last_error));
@@ -1268,7 +1269,16 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
       CU_TRY(cudaMemcpyAsync(st->d_uniforms, opts->uniforms + (lo - row_lo), sizeof(float) * (hi - lo), cudaMemcpyHostToDevice, ctx->stream));
       d_u = st->d_uniforms;
     }
-    if (blocked)
+    if (blocked && K * 128 <= 48 * 1024 && !getenv("MSB_NO_TILE_SAMPLER")) {
+      // tile staged in shared memory: scores read from HBM exactly once
+      constexpr int SW = 4;
+      const size_t smem = (size_t)SW * K * 128 + SW * sizeof(uint64_t) + 64;
+      const size_t nblk = (skip + (hi - lo) + 31) / 32 - skip / 32;
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ctx->smem_optin / smem));
+      const unsigned grid = (unsigned)std::min<size_t>((nblk + SW - 1) / SW, (size_t)ctx->sm_count * per_sm);
+      LAUNCH(ctx, sample_tile_kernel<SW>, grid, SW * 32, smem, st->d_scores, st->ld, skip, (int)K, hi - lo, d_u, opts->seed,
+             opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
+    } else if (blocked)
       LAUNCH(ctx, sample_blocked_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores, st->ld, skip, (int)K, hi - lo, d_u, opts->seed,
              opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
     else
