@@ -40,7 +40,10 @@ class ModelDesc(C.Structure):
 
 class SweepOpts(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("sweep", C.c_uint64), ("row_id_offset", C.c_uint64),
-                ("uniforms", C.c_void_p), ("defer_apply", C.c_int32), ("reserved", C.c_int32)]
+                ("uniforms", C.c_void_p), ("defer_apply", C.c_int32), ("flags", C.c_int32)]
+
+
+SWEEP_ASYNC = 1
 
 
 class SweepResult(C.Structure):
@@ -59,6 +62,7 @@ _PROTOS = {
     "msb_ctx_stream": (_P, [_P]),
     "msb_ctx_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "msb_dataview_create": (C.c_int, [_P, _P, _P, _SZ, C.POINTER(RuntimeType), _SZ, C.c_int, C.POINTER(_P)]),
+    "msb_dataview_upload": (C.c_int, [_P, _P, _P]),
     "msb_dataview_destroy": (C.c_int, [_P]),
     "msb_dataview_size": (C.c_int, [_P, C.POINTER(_SZ)]),
     "msb_dataview_nfeatures": (C.c_int, [_P, C.POINTER(_SZ)]),
@@ -67,6 +71,7 @@ _PROTOS = {
     "msb_state_create": (C.c_int, [_P, C.POINTER(ModelDesc), _SZ, _SZ, C.POINTER(_P)]),
     "msb_state_destroy": (C.c_int, [_P]),
     "msb_state_bind": (C.c_int, [_P, _P]),
+    "msb_state_refresh": (C.c_int, [_P]),
     "msb_state_set_hp": (C.c_int, [_P, _SZ, C.c_char_p, C.POINTER(C.c_double), _SZ]),
     "msb_state_get_hp": (C.c_int, [_P, _SZ, C.c_char_p, C.POINTER(C.c_double), _SZ]),
     "msb_state_set_ss": (C.c_int, [_P, _SZ, _SZ, C.c_char_p, C.POINTER(C.c_double), _SZ]),
@@ -88,13 +93,16 @@ _PROTOS = {
     "msb_state_score_rows": (C.c_int, [_P, _SZ, _SZ, _P, _SZ, C.c_int, C.POINTER(_SZ), _SZ, C.POINTER(_SZ)]),
     "msb_sample_discrete_log": (C.c_int, [_P, _P, _SZ, _SZ, _SZ, _P, _P]),
     "msb_philox_uniforms": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _SZ, _P]),
+    "msb_selftest_division": (C.c_int, [_P, C.c_uint64, _SZ, C.POINTER(C.c_uint64)]),
     "msb_state_sweep": (C.c_int, [_P, _SZ, _SZ, C.POINTER(SweepOpts), C.POINTER(SweepResult)]),
+    "msb_state_sweep_wait": (C.c_int, [_P, C.POINTER(SweepResult)]),
     "msb_state_delta_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ)]),
     "msb_state_apply_deltas": (C.c_int, [_P]),
     "msb_state_suffstat_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ)]),
     "msb_state_last_scores": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ), C.POINTER(_SZ), C.POINTER(_SZ)]),
     "msb_state_read_last_scores": (C.c_int, [_P, _P, _SZ]),
     "msb_state_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), _SZ]),
+    "msb_state_timings": (C.c_int, [_P, _SZ, C.POINTER(C.c_float), _SZ]),
     "msb_value_score": (C.c_int, [_P, C.POINTER(ModelDesc), C.POINTER(C.c_double), _SZ, C.POINTER(C.c_double), _SZ,
                                   _P, C.POINTER(RuntimeType), C.POINTER(C.c_float)]),
     "msb_value_add": (C.c_int, [_P, C.POINTER(ModelDesc), C.POINTER(C.c_double), _SZ, C.POINTER(C.c_double), _SZ,

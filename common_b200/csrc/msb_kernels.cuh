@@ -336,25 +336,78 @@ __global__ void niw_score_simt_kernel(const float *__restrict__ X, int d, const 
 // The order of the floating-point operations is part of the contract (the
 // checker must reproduce the draw bit for bit), so one thread walks one row.
 // ---------------------------------------------------------------------------
+//
+// The inverse-CDF walk `dart -= p / acc; if (dart <= 0) return k` is the only serial part.  dart_walk does it
+// eight elements at a time: the eight quotients are independent (computed first), then eight FSUB/compare
+// steps; the warp leaves once every lane has crossed zero.  The quotient RN(p / acc) is computed by Markstein's
+// sequence with the correctly rounded reciprocal y = RN(1 / acc):
+//     q0 = RN(p y),  r = RN(p - acc q0) (exact, FMA),  q = RN(q0 + r y)
+// which equals the IEEE division whenever no intermediate underflows: p >= 2^-100 or p == 0, acc in [1, 2^24]
+// (checked against exact rational arithmetic in tests/test_division_sequence.py and against __fdiv_rn on the
+// device by msb_selftest_division).  A smaller non-zero p gives q < 2^-100, which cannot change a dart >= 2^-60;
+// a batch in which a lane meets such a p with a smaller dart (or an acc outside the range) is redone with
+// __fdiv_rn.  __fdiv_rn on every element would take its out-of-line slow path for every zero / subnormal p,
+// i.e. on most elements of a well-separated mixture.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float div_markstein(float p, float acc, float y) {
+  const float q0 = __fmul_rn(p, y);
+  const float r = __fmaf_rn(-acc, q0, p);
+  return __fmaf_rn(r, y, q0);
+}
+
+// all 32 lanes of the warp must call this (lanes without a row pass found = true)
+template <typename F>
+__device__ __forceinline__ void dart_walk(int K, float acc, float dart, bool found, int &pick, F p_of) {
+  const float y = __frcp_rn(acc);
+  const bool odd = !(acc >= 1.0f && acc <= 16777216.0f);
+  pick = K - 1;
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    float p[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) p[j] = k0 + j < K ? p_of(k0 + j) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) q[j] = div_markstein(p[j], acc, y);
+    const float dart0 = dart;
+    const int pick0 = pick;
+    const bool found0 = found;
+    bool suspect = odd && !found;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      suspect |= !found && dart < 0x1p-60f && p[j] < 0x1p-100f && p[j] > 0.f;
+      dart = __fsub_rn(dart, q[j]);
+      if (!found && dart <= 0.f && k0 + j < K) { pick = k0 + j; found = true; }
+    }
+    if (__any_sync(0xffffffffu, suspect)) {  // rare: redo the batch with the IEEE division
+      dart = dart0; pick = pick0; found = found0;
+#pragma unroll 1
+      for (int j = 0; j < 8; j++) {
+        if (k0 + j >= K) break;
+        dart = __fsub_rn(dart, __fdiv_rn(p_of(k0 + j), acc));
+        if (!found && dart <= 0.f) { pick = k0 + j; found = true; }
+      }
+    }
+    if (__all_sync(0xffffffffu, found)) break;
+  }
+}
+
 __global__ void sample_kernel(const float *__restrict__ scores, size_t ld, int K, size_t nrows,
                               const float *__restrict__ uniforms, uint64_t seed, uint64_t sweep, uint64_t row_id0,
                               const int32_t *__restrict__ col2slot, int32_t *__restrict__ out_col,
                               int32_t *__restrict__ out_slot) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nrows) return;
-  const float *s = scores + i * ld;
+  const bool valid = i < nrows;
+  const float *s = scores + (valid ? i : 0) * ld;
   float m = s[0];
   for (int k = 1; k < K; k++) m = fmaxf(m, s[k]);
   double acc_d = 0.0;
+#pragma unroll 4
   for (int k = 0; k < K; k++) acc_d = __dadd_rn(acc_d, (double)msb_expf(__fsub_rn(s[k], m)));
   const float acc = __double2float_rn(acc_d);
-  float dart = uniforms ? uniforms[i] : philox_u01(seed, row_id0 + i, sweep);
-  int pick = K - 1;
-  for (int k = 0; k < K; k++) {
-    const float p = __fdiv_rn(msb_expf(__fsub_rn(s[k], m)), acc);
-    dart = __fsub_rn(dart, p);
-    if (dart <= 0.f) { pick = k; break; }
-  }
+  float dart = 0.f;
+  if (valid) dart = uniforms ? uniforms[i] : philox_u01(seed, row_id0 + i, sweep);
+  int pick;
+  dart_walk(K, acc, dart, !valid, pick, [&](int k) { return msb_expf(__fsub_rn(s[k], m)); });
+  if (!valid) return;
   if (out_col) out_col[i] = pick;
   if (out_slot) out_slot[i] = col2slot ? col2slot[pick] : pick;
 }
@@ -366,25 +419,47 @@ __global__ void sample_blocked_kernel(const float *__restrict__ scores, size_t l
                                       uint64_t row_id0, const int32_t *__restrict__ col2slot,
                                       int32_t *__restrict__ out_col, int32_t *__restrict__ out_slot) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nrows) return;
-  const size_t loc = i + skip;  // position in the buffer, whose origin is a multiple of 128 rows
+  const bool valid = i < nrows;
+  const size_t loc = (valid ? i : 0) + skip;  // position in the buffer, whose origin is a multiple of 128 rows
   const float *s = scores + (loc / 32) * ld * 32 + (loc % 32);
-  float m = s[0];
-#pragma unroll 8
-  for (int k = 1; k < K; k++) m = fmaxf(m, s[(size_t)k * 32]);
-  double acc_d = 0.0;
-#pragma unroll 4
-  for (int k = 0; k < K; k++) acc_d = __dadd_rn(acc_d, (double)msb_expf(__fsub_rn(s[(size_t)k * 32], m)));
-  const float acc = __double2float_rn(acc_d);
-  float dart = uniforms ? uniforms[i] : philox_u01(seed, row_id0 + i, sweep);
-  int pick = K - 1;
-  for (int k = 0; k < K; k++) {
-    const float p = __fdiv_rn(msb_expf(__fsub_rn(s[(size_t)k * 32], m)), acc);
-    dart = __fsub_rn(dart, p);
-    if (dart <= 0.f) { pick = k; break; }
+  float m0 = s[0], m1 = m0, m2 = m0, m3 = m0;
+  int k = 1;
+  for (; k + 3 < K; k += 4) {
+    m0 = fmaxf(m0, s[(size_t)k * 32]); m1 = fmaxf(m1, s[(size_t)(k + 1) * 32]);
+    m2 = fmaxf(m2, s[(size_t)(k + 2) * 32]); m3 = fmaxf(m3, s[(size_t)(k + 3) * 32]);
   }
+  for (; k < K; k++) m0 = fmaxf(m0, s[(size_t)k * 32]);
+  const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  double acc_d = 0.0;
+#pragma unroll 8
+  for (k = 0; k < K; k++) acc_d = __dadd_rn(acc_d, (double)msb_expf(__fsub_rn(s[(size_t)k * 32], m)));
+  const float acc = __double2float_rn(acc_d);
+  float dart = 0.f;
+  if (valid) dart = uniforms ? uniforms[i] : philox_u01(seed, row_id0 + i, sweep);
+  int pick;
+  dart_walk(K, acc, dart, !valid, pick, [&](int kk) { return msb_expf(__fsub_rn(s[(size_t)kk * 32], m)); });
+  if (!valid) return;
   if (out_col) out_col[i] = pick;
   if (out_slot) out_slot[i] = col2slot ? col2slot[pick] : pick;
+}
+
+// q[i] = (a[i] / b[i] by Markstein's sequence) != __fdiv_rn(a[i], b[i]) counted: device self-test of dart_walk's
+// division on pseudo-random operands p in [2^-100, 1], acc in [1, 2^24) (plus exact zeros)
+__global__ void selftest_division_kernel(uint64_t seed, size_t n, unsigned long long *mismatches) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t r[4];
+  philox4x32_10(seed, i, 0x5e1f7e57ull, r);
+  // p: random mantissa, exponent in [-100, 0]; every 64th operand is an exact zero
+  const uint32_t pe = 127 - (r[2] % 101);
+  float p = __uint_as_float((pe << 23) | (r[0] & 0x7fffffu));
+  if (p > 1.0f) p = 1.0f;
+  if ((r[3] & 63u) == 0) p = 0.f;
+  const uint32_t ae = 127 + ((r[2] >> 8) % 24);
+  const float acc = __uint_as_float((ae << 23) | (r[1] & 0x7fffffu));
+  const float got = div_markstein(p, acc, __frcp_rn(acc));
+  const float want = __fdiv_rn(p, acc);
+  if (__float_as_uint(got) != __float_as_uint(want)) atomicAdd(mismatches, 1ull);
 }
 
 // blocked -> row-major copy of a score matrix (diagnostics / tests)
@@ -529,6 +604,30 @@ __global__ void dd_count_sum_kernel(const FeatDev *__restrict__ feats, int nfeat
 __global__ void apply_delta_kernel(double *__restrict__ ss, double *__restrict__ delta, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { ss[i] += delta[i]; delta[i] = 0.0; }
+}
+
+// base[c] = log(pseudocount(group of column c)) (group_manager.hpp:274-283): the group's entity count, or
+// alpha / #empty groups for an empty one; columns [ncols, ld) are padding (-inf).  Computed on the device from
+// the resident counts so that a sweep never needs the host copy.  One block.
+__global__ void base_kernel(const double *__restrict__ counts, const int32_t *__restrict__ col2slot, int ncols, int ld,
+                            float alpha, float *__restrict__ base) {
+  __shared__ int s_empty;
+  if (threadIdx.x == 0) s_empty = 0;
+  __syncthreads();
+  int e = 0;
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) e += counts[col2slot[c]] == 0.0;
+  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+  if ((threadIdx.x & 31) == 0 && e) atomicAdd(&s_empty, e);
+  __syncthreads();
+  const float per_empty = __fdiv_rn(alpha, (float)s_empty);
+  for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+    float v = -CUDART_INF_F;
+    if (c < ncols) {
+      const double cnt = counts[col2slot[c]];
+      v = (float)log((double)(cnt != 0.0 ? (float)cnt : per_empty));
+    }
+    base[c] = v;
+  }
 }
 
 // base[col] += sum over nich features of c0[col]: the row-independent part of the nich term is added once

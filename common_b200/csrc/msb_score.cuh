@@ -110,12 +110,19 @@ sample_tile_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int
     const long long i = (long long)(blk * 32 + lane) - (long long)skip;  // row of this lane, relative to the first valid row
     const bool valid = i >= 0 && (size_t)i < nrows;
     float *s = tile + lane;
-    float m = s[0];
-#pragma unroll 8
-    for (int k = 1; k < K; k++) m = fmaxf(m, s[k * 32]);
+    // pass 1: max (exact and order-independent: four partial maxima for instruction-level parallelism)
+    float m0 = s[0], m1 = m0, m2 = m0, m3 = m0;
+    int k = 1;
+    for (; k + 3 < K; k += 4) {
+      m0 = fmaxf(m0, s[k * 32]); m1 = fmaxf(m1, s[(k + 1) * 32]);
+      m2 = fmaxf(m2, s[(k + 2) * 32]); m3 = fmaxf(m3, s[(k + 3) * 32]);
+    }
+    for (; k < K; k++) m0 = fmaxf(m0, s[k * 32]);
+    const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    // pass 2: p = exp(s - m) (independent per k, kept in the tile) and the in-order double sum (the only chain)
     double acc_d = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < K; k++) {
+#pragma unroll 8
+    for (k = 0; k < K; k++) {
       const float p = msb_expf(__fsub_rn(s[k * 32], m));
       s[k * 32] = p;
       acc_d = __dadd_rn(acc_d, (double)p);
@@ -123,11 +130,9 @@ sample_tile_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int
     const float acc = __double2float_rn(acc_d);
     float dart = 0.f;
     if (valid) dart = uniforms ? uniforms[i] : philox_u01(seed, row_id0 + (uint64_t)i, sweep);
-    int pick = K - 1;
-    for (int k = 0; k < K; k++) {
-      dart = __fsub_rn(dart, __fdiv_rn(s[k * 32], acc));
-      if (dart <= 0.f) { pick = k; break; }
-    }
+    // pass 3: the dart walk (msb_kernels.cuh), quotients from the tile
+    int pick;
+    dart_walk(K, acc, dart, !valid, pick, [&](int kk) { return s[kk * 32]; });
     if (valid) {
       if (out_col) out_col[i] = pick;
       if (out_slot) out_slot[i] = col2slot ? col2slot[pick] : pick;
@@ -158,7 +163,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
 score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restrict__ params, size_t region_rows,
              uint32_t stage_bytes, int S, const float *__restrict__ base, float *__restrict__ scores, size_t ld,
              size_t row_org, size_t row_lo, size_t row_hi, const double *__restrict__ hp,
-             const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols) {
+             const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols, int ktiles) {
   constexpr int KT = 32 * V;
   constexpr int RL = RW / 32;
   constexpr int RB = NW * RW;                                   // rows per block
@@ -171,9 +176,11 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * stage_bytes);
   FeatS *ftab = reinterpret_cast<FeatS *>(bars + 2 * S);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kt = blockIdx.y;
+  // 1-D grid, k-tile fastest: the blocks that share a row tile run together, so its row values come
+  // from DRAM once and from L2 for the other k-tiles
+  const int kt = (int)(blockIdx.x % (unsigned)ktiles);
   const float *region = params + (size_t)kt * region_rows * KT;
-  const size_t blk_row0 = row_org + (size_t)blockIdx.x * RB;   // multiple of 128
+  const size_t blk_row0 = row_org + (size_t)(blockIdx.x / (unsigned)ktiles) * RB;   // multiple of 128
   const size_t row0 = blk_row0 + (size_t)warp * RW;
 
   for (int i = tid; i < nfeat; i += NW * 32) {

@@ -88,6 +88,14 @@ struct msb_state {
   std::vector<int64_t> slot2gid;
   std::vector<int> free_slots;
   std::vector<double> h_counts;
+  bool counts_stale = false;      // the device counts (d_ss[0..kmax)) are newer than h_counts
+  bool cols_dirty = true;         // groups were created / deleted since the column tables were uploaded
+  unsigned long long *h_moved = nullptr;  // pinned: the moved-row counter of the last sweep lands here
+  uint32_t *h_flags = nullptr;    // pinned scratch for the bind-time device -> host flags
+  uint32_t *d_flags = nullptr;
+  int64_t *d_assign64 = nullptr; size_t assign64_cap = 0;
+  bool slot2gid_dirty = true;
+  msb_sweep_result last_res = {0, 0, 0};
   std::vector<char> slot_dirty;   // suffstats of the slot may be non-zero (set by any update / set_ss)
   bool all_unassigned = true;     // no entity has been assigned since bind
   void *col_slab = nullptr;       // one allocation backing every column
@@ -117,8 +125,11 @@ struct msb_state {
   size_t last_skip = 0;  // rows between the score buffer's origin (row_origin) and the first valid row
   std::vector<int32_t> h_col2slot;
   std::vector<size_t> h_colgid;
-  std::vector<PhaseEvents> events;
-  float last_ms[5] = {0, 0, 0, 0, 0};
+  // phase events of the last TIMING_RING sweeps (read on demand by msb_state_timings, never inside a sweep)
+  static constexpr size_t TIMING_RING = 64;
+  std::vector<PhaseEvents> events[TIMING_RING];
+  size_t ring_nchunks[TIMING_RING] = {0};
+  uint64_t sweep_seq = 0;  // sweeps enqueued so far
 };
 
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
@@ -240,6 +251,17 @@ extern "C" MSB_API int msb_dataview_create(msb_ctx *ctx, const void *data, const
     }
   }
   *out = dv;
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_dataview_upload(msb_dataview *dv, const void *data, const void *mask) {
+  REQUIRE(dv && (data || dv->n == 0), "msb_dataview_upload: NULL argument");
+  REQUIRE(dv->owns, "msb_dataview_upload: the dataview borrows device memory");
+  REQUIRE((mask != nullptr) == (dv->d_mask != nullptr) || dv->n == 0, "msb_dataview_upload: mask presence must match the dataview");
+  if (!dv->n) return MSB_OK;
+  CU_TRY(cudaSetDevice(dv->ctx->device));
+  CU_TRY(cudaMemcpyAsync(dv->d_data, data, dv->n * dv->rowsize, cudaMemcpyHostToDevice, dv->ctx->stream));
+  if (mask) CU_TRY(cudaMemcpyAsync(dv->d_mask, mask, dv->n * dv->maskrowsize, cudaMemcpyHostToDevice, dv->ctx->stream));
   return MSB_OK;
 }
 
@@ -434,6 +456,10 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
   CU_TRY(cudaMemsetAsync(st->d_delta, 0, sizeof(double) * st->SS, ctx->stream));
   CU_TRY(cudaMalloc(&st->d_counter, sizeof(unsigned long long) * 4));
   CU_TRY(cudaMalloc(&st->d_slot2gid, sizeof(int64_t) * max_groups));
+  CU_TRY(cudaMalloc(&st->d_flags, sizeof(uint32_t) * 2 * nfeatures));
+  CU_TRY(cudaHostAlloc(&st->h_flags, sizeof(uint32_t) * 2 * nfeatures, cudaHostAllocDefault));
+  CU_TRY(cudaHostAlloc(&st->h_moved, sizeof(unsigned long long), cudaHostAllocDefault));
+  *st->h_moved = 0;
   st->slot2gid.assign(max_groups, -1);
   st->h_counts.assign(max_groups, 0.0);
   st->slot_dirty.assign(max_groups, 0);
@@ -452,9 +478,9 @@ extern "C" MSB_API int msb_state_destroy(msb_state *st) {
   cudaFree(st->col_slab);
   for (size_t d = 0; d < st->D; d++) { cudaFree(st->d_niwW[d]); cudaFree(st->d_niwBias[d]); cudaFree(st->d_niwCoef[d]); cudaFree(st->d_niwB[d]); }
   cudaFree(st->d_feats); cudaFree(st->d_feats_scalar); cudaFree(st->d_hp); cudaFree(st->d_ss); cudaFree(st->d_delta); cudaFree(st->d_counter);
-  cudaFree(st->d_slot2gid); cudaFree(st->d_assign); cudaFree(st->d_params); cudaFree(st->d_scores);
+  cudaFree(st->d_slot2gid); cudaFree(st->d_assign64); cudaFree(st->d_flags); cudaFreeHost(st->h_moved); cudaFreeHost(st->h_flags); cudaFree(st->d_assign); cudaFree(st->d_params); cudaFree(st->d_scores);
   cudaFree(st->d_base); cudaFree(st->d_base_score); cudaFree(st->d_col2slot); cudaFree(st->d_newslot); cudaFree(st->d_newcol); cudaFree(st->d_uniforms);
-  for (auto &pe : st->events) for (auto &e : pe.e) cudaEventDestroy(e);
+  for (auto &ring : st->events) for (auto &pe : ring) for (auto &e : pe.e) cudaEventDestroy(e);
   delete st;
   return MSB_OK;
 }
@@ -496,6 +522,55 @@ static void layout_chunks(msb_state *st) {
   st->feats_dirty = true;
 }
 
+// Reads the bound dataview into the Value-typed columns (pack_kernel) and the score columns + slow-path
+// masks (scorecol_kernel).  size_tables: also size the gp lookup tables from the column maxima (bind);
+// a refresh keeps the table sizes, counts beyond them take the score kernel's closed-form path.
+static int ingest(msb_state *st, bool size_tables) {
+  msb_ctx *ctx = st->ctx;
+  msb_dataview *dv = st->dv;
+  const size_t D = st->D;
+  MSB_TRY(sync_small(st));
+  if (dv->n) {
+    dim3 grid(cdiv(dv->n, 256), (unsigned)D);
+    LAUNCH(ctx, pack_kernel, grid, 256, 0, dv->d_data, dv->d_mask, dv->n, dv->rowsize, dv->maskrowsize, st->d_feats, (int)D);
+  }
+  if (size_tables) {
+    std::vector<size_t> gp;
+    for (size_t d = 0; d < D; d++) if (st->feats[d].kind == KIND_GP) gp.push_back(d);
+    if (!gp.empty()) {
+      uint32_t *d_max = st->d_flags + D;
+      CU_TRY(cudaMemsetAsync(d_max, 0, sizeof(uint32_t) * gp.size(), ctx->stream));
+      if (dv->n)
+        for (size_t i = 0; i < gp.size(); i++)
+          LAUNCH(ctx, colmax_u32_kernel, std::min<unsigned>(cdiv(dv->n, 256), 1024), 256, 0,
+                 (const uint32_t *)st->cols[gp[i]], dv->n, d_max + i);
+      CU_TRY(cudaMemcpyAsync(st->h_flags + D, d_max, sizeof(uint32_t) * gp.size(), cudaMemcpyDeviceToHost, ctx->stream));
+      CU_TRY(cudaStreamSynchronize(ctx->stream));
+      const uint32_t cap_limit = 252;  // chunk rows = cap + 4 <= 256
+      for (size_t i = 0; i < gp.size(); i++) st->feats[gp[i]].ncat = std::min<uint32_t>(st->h_flags[D + i] + 1, cap_limit);
+    }
+    layout_chunks(st);
+  }
+  if (st->has_scalar) {  // score columns + slow-path masks (the gp table sizes are known now)
+    MSB_TRY(sync_small(st));
+    CU_TRY(cudaMemsetAsync(st->d_flags, 0, sizeof(uint32_t) * D, ctx->stream));
+    dim3 grid((unsigned)(st->n_pad / 256), (unsigned)D);
+    LAUNCH(ctx, scorecol_kernel, grid, 256, 0, st->d_feats, (int)D, dv->n, st->n_pad, st->d_flags);
+    CU_TRY(cudaMemcpyAsync(st->h_flags, st->d_flags, sizeof(uint32_t) * D, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    bool any = false, changed = false;
+    for (size_t d = 0; d < D; d++) {
+      changed |= st->feats[d].has_slow != st->h_flags[d];
+      st->feats[d].has_slow = st->h_flags[d];
+      any |= st->h_flags[d] != 0;
+    }
+    // the tables-only kernel has no slow path and no nich code: gp features qualify when no count exceeds their table
+    st->tables_only = !any && !st->has_nich && !getenv("MSB_NO_TABLES_ONLY");
+    if (changed || size_tables) st->feats_dirty = true;
+  }
+  return MSB_OK;
+}
+
 extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
   REQUIRE(st && dv, "msb_state_bind: NULL argument");
   REQUIRE(dv->ctx == st->ctx, "msb_state_bind: dataview belongs to another context");
@@ -508,81 +583,56 @@ extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
     if (m.family == MSB_FAMILY_NIW) REQUIRE(t.n == m.dim, "shapes do not match");  // distributions.hpp:218
     else REQUIRE(t.n == 1, "scalar model bound to a vector field");               // distributions.hpp:209
   }
-  cudaFree(st->col_slab); st->col_slab = nullptr;
-  cudaFree(st->d_assign); st->d_assign = nullptr;
-  st->dv = dv; st->n = dv->n;
   const size_t n = std::max<size_t>(dv->n, 1);
-  std::vector<size_t> coff(st->D), soff(st->D), moff(st->D);
-  size_t slab = 0;
-  const size_t n_pad = (n + 1024 + 1023) / 1024 * 1024;  // tile-granular kernels read whole 1024-row tiles
-  st->n_pad = n_pad;
-  for (size_t d = 0; d < st->D; d++) {
-    const FeatDev &f = st->feats[d];
-    const size_t bytes = f.kind == KIND_NIW ? n * f.dim * sizeof(float) : n * (f.coltype == COL_U8 ? 1 : f.coltype == COL_U16 ? 2 : 4);
-    coff[d] = slab;
-    slab += (bytes + 4096 + 255) / 256 * 256;
-    if (f.kind != KIND_NIW) {
-      soff[d] = slab; slab += n_pad * sizeof(uint32_t);
-      moff[d] = slab; slab += n_pad / 32 * sizeof(uint32_t);
+  const bool same_shape = st->col_slab && st->d_assign && st->n == dv->n;  // the column slab depends on n only
+  st->dv = dv; st->n = dv->n;
+  if (!same_shape) {
+    cudaFree(st->col_slab); st->col_slab = nullptr;
+    cudaFree(st->d_assign); st->d_assign = nullptr;
+    std::vector<size_t> coff(st->D), soff(st->D), moff(st->D);
+    size_t slab = 0;
+    const size_t n_pad = (n + 1024 + 1023) / 1024 * 1024;  // tile-granular kernels read whole 1024-row tiles
+    st->n_pad = n_pad;
+    for (size_t d = 0; d < st->D; d++) {
+      const FeatDev &f = st->feats[d];
+      const size_t bytes = f.kind == KIND_NIW ? n * f.dim * sizeof(float) : n * (f.coltype == COL_U8 ? 1 : f.coltype == COL_U16 ? 2 : 4);
+      coff[d] = slab;
+      slab += (bytes + 4096 + 255) / 256 * 256;
+      if (f.kind != KIND_NIW) {
+        soff[d] = slab; slab += n_pad * sizeof(uint32_t);
+        moff[d] = slab; slab += n_pad / 32 * sizeof(uint32_t);
+      }
     }
+    CU_TRY(cudaMalloc(&st->col_slab, slab));
+    for (size_t d = 0; d < st->D; d++) {
+      FeatDev &f = st->feats[d];
+      st->cols[d] = (char *)st->col_slab + coff[d];
+      f.col = st->cols[d];
+      f.scol = f.kind != KIND_NIW ? (const uint32_t *)((char *)st->col_slab + soff[d]) : nullptr;
+      f.slowmask = f.kind != KIND_NIW ? (const uint32_t *)((char *)st->col_slab + moff[d]) : nullptr;
+    }
+    CU_TRY(cudaMalloc(&st->d_assign, sizeof(int32_t) * n));
   }
-  CU_TRY(cudaMalloc(&st->col_slab, slab));
   for (size_t d = 0; d < st->D; d++) {
     FeatDev &f = st->feats[d];
-    st->cols[d] = (char *)st->col_slab + coff[d];
-    f.col = st->cols[d];
-    f.scol = f.kind != KIND_NIW ? (const uint32_t *)((char *)st->col_slab + soff[d]) : nullptr;
-    f.slowmask = f.kind != KIND_NIW ? (const uint32_t *)((char *)st->col_slab + moff[d]) : nullptr;
     f.has_slow = 0;
     f.src_off = dv->off[d]; f.msk_off = dv->moff[d];
     f.src_prim = (uint32_t)dv->types[d].prim; f.src_n = dv->types[d].n;
   }
   st->feats_dirty = true;
-  MSB_TRY(sync_small(st));
-  if (dv->n) {
-    dim3 grid(cdiv(dv->n, 256), (unsigned)st->D);
-    LAUNCH(ctx, pack_kernel, grid, 256, 0, dv->d_data, dv->d_mask, dv->n, dv->rowsize, dv->maskrowsize, st->d_feats, (int)st->D);
-  }
-  // size the gp lookup tables from the column maxima
-  std::vector<size_t> gp;
-  for (size_t d = 0; d < st->D; d++) if (st->feats[d].kind == KIND_GP) gp.push_back(d);
-  if (!gp.empty()) {
-    uint32_t *d_max = nullptr;
-    CU_TRY(cudaMalloc(&d_max, sizeof(uint32_t) * gp.size()));
-    CU_TRY(cudaMemsetAsync(d_max, 0, sizeof(uint32_t) * gp.size(), ctx->stream));
-    if (dv->n)
-      for (size_t i = 0; i < gp.size(); i++)
-        LAUNCH(ctx, colmax_u32_kernel, std::min<unsigned>(cdiv(dv->n, 256), 1024), 256, 0,
-               (const uint32_t *)st->cols[gp[i]], dv->n, d_max + i);
-    std::vector<uint32_t> h_max(gp.size());
-    CU_TRY(cudaMemcpyAsync(h_max.data(), d_max, sizeof(uint32_t) * gp.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_max);
-    const uint32_t cap_limit = 252;  // chunk rows = cap + 4 <= 256
-    for (size_t i = 0; i < gp.size(); i++) st->feats[gp[i]].ncat = std::min<uint32_t>(h_max[i] + 1, cap_limit);
-  }
-  layout_chunks(st);
-  if (st->has_scalar) {  // score columns + slow-path masks (the gp table sizes are known now)
-    MSB_TRY(sync_small(st));
-    uint32_t *d_any = nullptr;
-    CU_TRY(cudaMalloc(&d_any, sizeof(uint32_t) * st->D));
-    CU_TRY(cudaMemsetAsync(d_any, 0, sizeof(uint32_t) * st->D, ctx->stream));
-    dim3 grid((unsigned)(st->n_pad / 256), (unsigned)st->D);
-    LAUNCH(ctx, scorecol_kernel, grid, 256, 0, st->d_feats, (int)st->D, dv->n, st->n_pad, d_any);
-    std::vector<uint32_t> h_any(st->D);
-    CU_TRY(cudaMemcpyAsync(h_any.data(), d_any, sizeof(uint32_t) * st->D, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_any);
-    bool any = false;
-    for (size_t d = 0; d < st->D; d++) { st->feats[d].has_slow = h_any[d]; any |= h_any[d] != 0; }
-    // the tables-only kernel has no slow path and no nich code: gp features qualify when no count exceeds their table
-    st->tables_only = !any && !st->has_nich && !getenv("MSB_NO_TABLES_ONLY");
-    st->feats_dirty = true;
-  }
-  CU_TRY(cudaMalloc(&st->d_assign, sizeof(int32_t) * n));
+  MSB_TRY(ingest(st, true));
   CU_TRY(cudaMemsetAsync(st->d_assign, 0xFF, sizeof(int32_t) * n, ctx->stream));  // all -1
   st->all_unassigned = true;
   return MSB_OK;
+}
+
+// The bound dataview's records were replaced in place (msb_dataview_upload): convert them again.
+// Assignments and suffstats are kept -- the rows are the same entities, streamed from the host again.
+extern "C" MSB_API int msb_state_refresh(msb_state *st) {
+  REQUIRE(st, "NULL argument");
+  REQUIRE(st->dv, "no dataview bound");
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  return ingest(st, false);
 }
 
 // ---- hypers / suffstats ------------------------------------------------------
@@ -689,6 +739,16 @@ extern "C" MSB_API int msb_state_set_ss(msb_state *st, size_t feature, size_t gi
 }
 
 // ---- groups (group_manager.hpp:133-216) -------------------------------------
+// The per-group entity counts live on the device (d_ss[0..kmax)); the host copy is refreshed lazily,
+// only when a host-side question needs it, so that sweeps never wait for the stream.
+static int host_counts(msb_state *st) {
+  if (!st->counts_stale) return MSB_OK;
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  CU_TRY(cudaMemcpyAsync(st->h_counts.data(), st->d_ss, sizeof(double) * st->kmax, cudaMemcpyDeviceToHost, st->ctx->stream));
+  CU_TRY(cudaStreamSynchronize(st->ctx->stream));
+  st->counts_stale = false;
+  return MSB_OK;
+}
 extern "C" MSB_API int msb_state_nentities(msb_state *st, size_t *n) { REQUIRE(st && n, "NULL argument"); *n = st->n; return MSB_OK; }
 extern "C" MSB_API int msb_state_ngroups(msb_state *st, size_t *n) { REQUIRE(st && n, "NULL argument"); *n = st->gid2slot.size(); return MSB_OK; }
 extern "C" MSB_API int msb_state_groups(msb_state *st, size_t *gids, size_t cap, size_t *n) {
@@ -703,6 +763,7 @@ extern "C" MSB_API int msb_state_groups(msb_state *st, size_t *gids, size_t cap,
 }
 extern "C" MSB_API int msb_state_empty_groups(msb_state *st, size_t *gids, size_t cap, size_t *n) {
   REQUIRE(st && n, "NULL argument");
+  MSB_TRY(host_counts(st));
   size_t c = 0;
   for (auto &p : st->gid2slot)
     if (st->h_counts[p.second] == 0.0) {
@@ -716,6 +777,7 @@ extern "C" MSB_API int msb_state_groupsize(msb_state *st, size_t gid, size_t *co
   REQUIRE(st && count, "NULL argument");
   int slot;
   MSB_TRY(slot_of(st, gid, &slot));
+  MSB_TRY(host_counts(st));
   *count = (size_t)st->h_counts[slot];
   return MSB_OK;
 }
@@ -728,6 +790,8 @@ extern "C" MSB_API int msb_state_create_group(msb_state *st, size_t *gid) {
   const size_t g = st->gcount++;  // group_manager.hpp:199
   st->gid2slot[g] = slot;
   st->slot2gid[slot] = (int64_t)g;
+  st->cols_dirty = st->slot2gid_dirty = true;
+  MSB_TRY(host_counts(st));
   st->h_counts[slot] = 0.0;
   // Group::init: zero suffstats (distributions.hpp:351); a slot nobody has written since the state was
   // created is still zero from the initial memset
@@ -744,9 +808,11 @@ extern "C" MSB_API int msb_state_delete_group(msb_state *st, size_t gid) {
   REQUIRE(st, "NULL argument");
   int slot;
   MSB_TRY(slot_of(st, gid, &slot));
+  MSB_TRY(host_counts(st));
   if (st->h_counts[slot] != 0.0) return fail(MSB_ERR_STATE, "group not empty");  // group_manager.hpp:211
   st->gid2slot.erase(gid);
   st->slot2gid[slot] = -1;
+  st->cols_dirty = st->slot2gid_dirty = true;
   st->free_slots.push_back(slot);
   return MSB_OK;
 }
@@ -800,27 +866,22 @@ static int prepare_columns(msb_state *st) {
   msb_ctx *ctx = st->ctx;
   const size_t K = st->gid2slot.size();
   REQUIRE(K > 0, "no groups");
-  st->cfg = choose_cfg(st, K);
-  st->V = k_score_cfgs[st->cfg].V;
+  const int cfg = choose_cfg(st, K);
+  st->cfg = cfg;
+  st->V = k_score_cfgs[cfg].V;
   const size_t KT = 32 * (size_t)st->V;
   st->ld = (K + KT - 1) / KT * KT;
-  st->h_col2slot.resize(K); st->h_colgid.resize(K);
-  size_t nempty = 0;
-  for (auto &p : st->gid2slot) if (st->h_counts[p.second] == 0.0) nempty++;
-  std::vector<float> base(st->ld, -INFINITY);
-  size_t c = 0;
-  for (auto &p : st->gid2slot) {
-    st->h_col2slot[c] = p.second; st->h_colgid[c] = p.first;
-    const double cnt = st->h_counts[p.second];
-    const float pseudo = cnt != 0.0 ? (float)cnt : (float)st->alpha / (float)nempty;
-    base[c] = (float)std::log((double)pseudo);
-    c++;
+  if (st->cols_dirty) {  // groups were created / deleted: rebuild and upload the column tables
+    st->h_col2slot.resize(K); st->h_colgid.resize(K);
+    size_t c = 0;
+    for (auto &p : st->gid2slot) { st->h_col2slot[c] = p.second; st->h_colgid[c] = p.first; c++; }
+    MSB_TRY(ensure(&st->d_col2slot, &st->col_cap, K));
+    CU_TRY(cudaMemcpyAsync(st->d_col2slot, st->h_col2slot.data(), sizeof(int32_t) * K, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));  // pageable source, reused next time
+    st->cols_dirty = false;
   }
   MSB_TRY(ensure(&st->d_base, &st->base_cap, st->ld));
-  MSB_TRY(ensure(&st->d_col2slot, &st->col_cap, K));
-  CU_TRY(cudaMemcpyAsync(st->d_base, base.data(), sizeof(float) * st->ld, cudaMemcpyHostToDevice, ctx->stream));
-  CU_TRY(cudaMemcpyAsync(st->d_col2slot, st->h_col2slot.data(), sizeof(int32_t) * K, cudaMemcpyHostToDevice, ctx->stream));
-  CU_TRY(cudaMemcpyAsync(st->d_slot2gid, st->slot2gid.data(), sizeof(int64_t) * st->kmax, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, base_kernel, 1, 256, 0, st->d_ss, st->d_col2slot, (int)K, (int)st->ld, (float)st->alpha, st->d_base);
   return MSB_OK;
 }
 
@@ -887,15 +948,16 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
     if (blocked && (size_t)S * stage < tile) stage = ((tile + S - 1) / S + 127) / 128 * 128;
     const size_t smem = (size_t)S * stage + fixed;
     if (smem > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "score kernel shared memory does not fit");
-    dim3 grid(cdiv(nrows, RB), (unsigned)ktiles);
+    const size_t grid = (size_t)cdiv(nrows, RB) * ktiles;
+    if (grid >= (1ull << 31)) return fail(MSB_ERR_UNSUPPORTED, "score grid too large: sweep a smaller row range");
 #define MSB_SCORE_ARGS st->d_feats_scalar, (int)st->n_scalar, st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base_score, \
-                       scores, st->ld, org, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K
+                       scores, st->ld, org, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K, (int)ktiles
 #define MSB_SCORE_LAUNCH(V_, RW_, NW_)                                                                         \
     do {                                                                                                       \
-      if (blocked && st->tables_only) LAUNCH(ctx, (score_kernel<V_, RW_, NW_, true, true>), grid, NW_ * 32, smem, MSB_SCORE_ARGS);        \
-      else if (blocked) LAUNCH(ctx, (score_kernel<V_, RW_, NW_, true, false>), grid, NW_ * 32, smem, MSB_SCORE_ARGS);                     \
-      else if (st->tables_only) LAUNCH(ctx, (score_kernel<V_, RW_, NW_, false, true>), grid, NW_ * 32, smem, MSB_SCORE_ARGS);             \
-      else LAUNCH(ctx, (score_kernel<V_, RW_, NW_, false, false>), grid, NW_ * 32, smem, MSB_SCORE_ARGS);                                 \
+      if (blocked && st->tables_only) LAUNCH(ctx, (score_kernel<V_, RW_, NW_, true, true>), (unsigned)grid, NW_ * 32, smem, MSB_SCORE_ARGS);        \
+      else if (blocked) LAUNCH(ctx, (score_kernel<V_, RW_, NW_, true, false>), (unsigned)grid, NW_ * 32, smem, MSB_SCORE_ARGS);                     \
+      else if (st->tables_only) LAUNCH(ctx, (score_kernel<V_, RW_, NW_, false, true>), (unsigned)grid, NW_ * 32, smem, MSB_SCORE_ARGS);             \
+      else LAUNCH(ctx, (score_kernel<V_, RW_, NW_, false, false>), (unsigned)grid, NW_ * 32, smem, MSB_SCORE_ARGS);                                 \
     } while (0)
     switch (st->cfg) {
       case 0: MSB_SCORE_LAUNCH(1, 64, 16); break;
@@ -940,10 +1002,9 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
 static void mark_dirty(msb_state *st) {
   for (auto &p : st->gid2slot) st->slot_dirty[p.second] = 1;
 }
-static int refresh_counts(msb_state *st) {
+static int refresh_counts(msb_state *st) {  // the device counts changed: the host copy is re-read on demand (host_counts)
   mark_dirty(st);
-  CU_TRY(cudaMemcpyAsync(st->h_counts.data(), st->d_ss, sizeof(double) * st->kmax, cudaMemcpyDeviceToHost, st->ctx->stream));
-  CU_TRY(cudaStreamSynchronize(st->ctx->stream));
+  st->counts_stale = true;
   return MSB_OK;
 }
 
@@ -1001,13 +1062,14 @@ extern "C" MSB_API int msb_state_assignments(msb_state *st, int64_t *out, size_t
   if (!n) return MSB_OK;
   msb_ctx *ctx = st->ctx;
   CU_TRY(cudaSetDevice(ctx->device));
-  int64_t *d_out = nullptr;
-  CU_TRY(cudaMalloc(&d_out, sizeof(int64_t) * n));
-  CU_TRY(cudaMemcpyAsync(st->d_slot2gid, st->slot2gid.data(), sizeof(int64_t) * st->kmax, cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(ctx, map_i32_to_i64_kernel, cdiv(n, 256), 256, 0, st->d_assign, st->d_slot2gid, n, d_out);
-  CU_TRY(cudaMemcpyAsync(out, d_out, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  MSB_TRY(ensure(&st->d_assign64, &st->assign64_cap, n));
+  if (st->slot2gid_dirty) {
+    CU_TRY(cudaMemcpyAsync(st->d_slot2gid, st->slot2gid.data(), sizeof(int64_t) * st->kmax, cudaMemcpyHostToDevice, ctx->stream));
+    st->slot2gid_dirty = false;  // pageable source: the copy has been staged on return
+  }
+  LAUNCH(ctx, map_i32_to_i64_kernel, cdiv(n, 256), 256, 0, st->d_assign, st->d_slot2gid, n, st->d_assign64);
+  CU_TRY(cudaMemcpyAsync(out, st->d_assign64, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_out);
   return MSB_OK;
 }
 
@@ -1186,10 +1248,28 @@ extern "C" MSB_API int msb_state_read_last_scores(msb_state *st, float *out, siz
   CU_TRY(cudaStreamSynchronize(st->ctx->stream));
   return MSB_OK;
 }
+// back = 0: the last sweep, 1: the one before it, ... (up to TIMING_RING - 1 sweeps back)
+extern "C" MSB_API int msb_state_timings(msb_state *st, size_t back, float *ms, size_t count) {
+  REQUIRE(st && ms, "NULL argument");
+  for (size_t i = 0; i < count; i++) ms[i] = 0.f;
+  REQUIRE(back < msb_state::TIMING_RING && back < st->sweep_seq, "no such sweep in the timing ring");
+  const size_t slot = (st->sweep_seq - 1 - back) % msb_state::TIMING_RING;
+  std::vector<PhaseEvents> &ev = st->events[slot];
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  CU_TRY(cudaEventSynchronize(ev[0].e[3]));
+  float out[5] = {0, 0, 0, 0, 0}, t = 0.f;
+  CU_TRY(cudaEventElapsedTime(&t, ev[0].e[0], ev[0].e[1])); out[0] = t;
+  for (size_t c = 0; c < st->ring_nchunks[slot]; c++)
+    for (int p = 0; p < 3; p++) { CU_TRY(cudaEventElapsedTime(&t, ev[c + 1].e[p], ev[c + 1].e[p + 1])); out[1 + p] += t; }
+  CU_TRY(cudaEventElapsedTime(&t, ev[0].e[2], ev[0].e[3])); out[4] = t;
+  for (size_t i = 0; i < count && i < 5; i++) ms[i] = out[i];
+  return MSB_OK;
+}
 extern "C" MSB_API int msb_state_last_timings(msb_state *st, float *ms, size_t count) {
   REQUIRE(st && ms, "NULL argument");
-  for (size_t i = 0; i < count && i < 5; i++) ms[i] = st->last_ms[i];
-  return MSB_OK;
+  for (size_t i = 0; i < count; i++) ms[i] = 0.f;
+  if (!st->sweep_seq) return MSB_OK;
+  return msb_state_timings(st, 0, ms, count);
 }
 
 // ---- sampler ---------------------------------------------------------------------
@@ -1225,6 +1305,21 @@ extern "C" MSB_API int msb_philox_uniforms(msb_ctx *ctx, uint64_t seed, uint64_t
   return MSB_OK;
 }
 
+extern "C" MSB_API int msb_selftest_division(msb_ctx *ctx, uint64_t seed, size_t n, uint64_t *mismatches) {
+  REQUIRE(ctx && mismatches, "NULL argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  unsigned long long *d = nullptr;
+  CU_TRY(cudaMalloc(&d, sizeof(unsigned long long)));
+  CU_TRY(cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+  if (n) LAUNCH(ctx, selftest_division_kernel, cdiv(n, 256), 256, 0, seed, n, d);
+  unsigned long long h = 0;
+  CU_TRY(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  *mismatches = h;
+  return MSB_OK;
+}
+
 // ---- sweep -------------------------------------------------------------------------
 extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_hi, const msb_sweep_opts *opts,
                                msb_sweep_result *res) {
@@ -1245,20 +1340,24 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
   const size_t nchunks = (nrows + chunk - 1) / chunk;
   MSB_TRY(ensure_scores(st, chunk + 128));
   MSB_TRY(ensure_rows(st, chunk));
-  while (st->events.size() < nchunks + 1) {
+  const size_t ring = st->sweep_seq % msb_state::TIMING_RING;
+  std::vector<PhaseEvents> &ev = st->events[ring];
+  while (ev.size() < nchunks + 1) {
     PhaseEvents pe;
     for (auto &e : pe.e) CU_TRY(cudaEventCreate(&e));
-    st->events.push_back(pe);
+    ev.push_back(pe);
   }
+  st->ring_nchunks[ring] = nchunks;
+  st->sweep_seq++;
   // the sweep keeps the scores in the sampler-friendly blocked layout (NIW kernels accumulate row-major)
   const bool blocked = !st->has_niw && !getenv("MSB_NO_BLOCKED");
   CU_TRY(cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned long long), ctx->stream));
-  CU_TRY(cudaEventRecord(st->events[0].e[0], ctx->stream));
+  CU_TRY(cudaEventRecord(ev[0].e[0], ctx->stream));
   MSB_TRY(build_params(st));
-  CU_TRY(cudaEventRecord(st->events[0].e[1], ctx->stream));
+  CU_TRY(cudaEventRecord(ev[0].e[1], ctx->stream));
   for (size_t c = 0; c < nchunks; c++) {
     const size_t lo = row_lo + c * chunk, hi = std::min(row_hi, lo + chunk);
-    PhaseEvents &pe = st->events[c + 1];
+    PhaseEvents &pe = ev[c + 1];
     CU_TRY(cudaEventRecord(pe.e[0], ctx->stream));
     const size_t skip = lo - row_origin(lo);
     MSB_TRY(launch_score(st, lo, hi, st->d_scores, blocked));
@@ -1290,22 +1389,28 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
   }
   st->last_rows = nchunks == 1 ? nrows : (nrows - (nchunks - 1) * chunk); st->last_cols = K;
   st->last_blocked = blocked;
-  CU_TRY(cudaEventRecord(st->events[0].e[2], ctx->stream));
+  CU_TRY(cudaEventRecord(ev[0].e[2], ctx->stream));
   if (!opts->defer_apply) MSB_TRY(launch_apply(st));
-  CU_TRY(cudaEventRecord(st->events[0].e[3], ctx->stream));
-  unsigned long long moved = 0;
-  CU_TRY(cudaMemcpyAsync(&moved, st->d_counter, sizeof(moved), cudaMemcpyDeviceToHost, ctx->stream));
-  if (!opts->defer_apply) MSB_TRY(refresh_counts(st));
-  else CU_TRY(cudaStreamSynchronize(ctx->stream));
-  if (res) res->moved = moved;
-  float ms = 0.f;
-  for (float &m : st->last_ms) m = 0.f;
-  cudaEventElapsedTime(&ms, st->events[0].e[0], st->events[0].e[1]); st->last_ms[0] = ms;
-  for (size_t c = 0; c < nchunks; c++) {
-    PhaseEvents &pe = st->events[c + 1];
-    for (int p = 0; p < 3; p++) { cudaEventElapsedTime(&ms, pe.e[p], pe.e[p + 1]); st->last_ms[1 + p] += ms; }
+  CU_TRY(cudaEventRecord(ev[0].e[3], ctx->stream));
+  CU_TRY(cudaMemcpyAsync(st->h_moved, st->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  MSB_TRY(refresh_counts(st));  // marks the host copy of the group counts stale; no synchronisation
+  st->last_res.rows = nrows; st->last_res.units = (uint64_t)nrows * K * st->D; st->last_res.moved = 0;
+  if (opts->flags & MSB_SWEEP_ASYNC) {  // everything is enqueued; msb_state_sweep_wait collects the result
+    if (res) res->moved = 0;
+    return MSB_OK;
   }
-  cudaEventElapsedTime(&ms, st->events[0].e[2], st->events[0].e[3]); st->last_ms[4] = ms;
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  st->last_res.moved = *st->h_moved;
+  if (res) res->moved = *st->h_moved;
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_state_sweep_wait(msb_state *st, msb_sweep_result *res) {
+  REQUIRE(st, "NULL argument");
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  CU_TRY(cudaStreamSynchronize(st->ctx->stream));
+  st->last_res.moved = *st->h_moved;
+  if (res) *res = st->last_res;
   return MSB_OK;
 }
 

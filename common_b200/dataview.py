@@ -164,6 +164,12 @@ class device_dataview(object):
         _lib.check(_lib.load().msb_dataview_rowsize(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def upload(self, data, mask=None):
+        """replace the records in place from host memory (address or uint8 array); same n, same types"""
+        dptr = data.ctypes.data if hasattr(data, "ctypes") else data
+        mptr = mask.ctypes.data if hasattr(mask, "ctypes") else mask
+        _lib.check(_lib.load().msb_dataview_upload(self._h, dptr, mptr))
+
     def get_row_bytes(self, idx):
         rs, ms = self.rowsize()
         row = np.zeros(rs, np.uint8)

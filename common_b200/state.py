@@ -43,6 +43,11 @@ class state(object):
         _lib.check(_lib.load().msb_state_bind(self._h, dev.handle))
         self._view = dev
 
+    def refresh(self):
+        """the bound device dataview was re-uploaded in place: convert its records again
+        (assignments and suffstats are kept)"""
+        _lib.check(_lib.load().msb_state_refresh(self._h))
+
     # ---- hyperparameters (entity_state.hpp:41-49) -----------------------------
     def set_cluster_hp(self, hp):
         _lib.check(_lib.load().msb_state_set_cluster_hp(self._h, b"alpha", float(hp["alpha"])))
@@ -123,9 +128,11 @@ class state(object):
     def delete_group(self, gid):
         _lib.check(_lib.load().msb_state_delete_group(self._h, gid))
 
-    def assignments(self):
+    def assignments(self, out=None):
+        """gid per entity (-1 = unassigned); ``out``: optional int64 array (e.g. over pinned memory)"""
         n = self.nentities()
-        a = np.zeros(n, np.int64)
+        a = np.empty(n, np.int64) if out is None else out
+        assert a.dtype == np.int64 and a.size == n and a.flags.c_contiguous
         _lib.check(_lib.load().msb_state_assignments(self._h, a.ctypes.data, n))
         return a
 
@@ -175,9 +182,12 @@ class state(object):
         _lib.check(_lib.load().msb_state_last_scores(self._h, C.byref(ptr), C.byref(ld), None, None))
         return [int(gids[i]) for i in range(n.value)], ptr.value, ld.value
 
-    def sweep(self, row_lo=0, row_hi=None, seed=0, sweep=0, uniforms=None, row_id_offset=0, defer_apply=False):
+    def sweep(self, row_lo=0, row_hi=None, seed=0, sweep=0, uniforms=None, row_id_offset=0, defer_apply=False,
+              wait=True):
+        """one batched reassignment pass; wait=False only enqueues it (sweep_wait() collects ``moved``)"""
         row_hi = self.nentities() if row_hi is None else row_hi
-        opts = _lib.SweepOpts(int(seed), int(sweep), int(row_id_offset), None, 1 if defer_apply else 0, 0)
+        opts = _lib.SweepOpts(int(seed), int(sweep), int(row_id_offset), None, 1 if defer_apply else 0,
+                              0 if wait else _lib.SWEEP_ASYNC)
         keep = None
         if uniforms is not None:
             keep = np.ascontiguousarray(uniforms, dtype=np.float32)
@@ -185,6 +195,11 @@ class state(object):
             opts.uniforms = keep.ctypes.data
         res = _lib.SweepResult()
         _lib.check(_lib.load().msb_state_sweep(self._h, row_lo, row_hi, C.byref(opts), C.byref(res)))
+        return {"rows": res.rows, "moved": res.moved, "units": res.units}
+
+    def sweep_wait(self):
+        res = _lib.SweepResult()
+        _lib.check(_lib.load().msb_state_sweep_wait(self._h, C.byref(res)))
         return {"rows": res.rows, "moved": res.moved, "units": res.units}
 
     def last_scores(self):
@@ -201,9 +216,10 @@ class state(object):
             _lib.check(_lib.load().msb_state_read_last_scores(self._h, out.ctypes.data, nc))
         return out
 
-    def last_timings(self):
+    def last_timings(self, back=0):
+        """ms per phase of the last sweep (back=0) or of an earlier one (ring of 64 sweeps)"""
         a = (C.c_float * 5)()
-        _lib.check(_lib.load().msb_state_last_timings(self._h, a, 5))
+        _lib.check(_lib.load().msb_state_timings(self._h, int(back), a, 5))
         return dict(zip(("build", "score", "sample", "update", "apply"), [float(x) for x in a]))
 
     def delta_buffer(self):

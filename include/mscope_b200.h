@@ -120,6 +120,9 @@ MSB_API int msb_ctx_launch_count(msb_ctx *ctx, uint64_t *out);
 MSB_API int msb_dataview_create(msb_ctx *ctx, const void *data, const void *mask, size_t n,
                         const msb_runtime_type *types, size_t nfeatures, int on_device,
                         msb_dataview **out);
+/* replace the records (and mask) of a host-created dataview in place: same n, same types.  Asynchronous on the
+ * context's stream when the host buffers are pinned.  Follow with msb_state_refresh on the states bound to it. */
+MSB_API int msb_dataview_upload(msb_dataview *dv, const void *data, const void *mask);
 MSB_API int msb_dataview_destroy(msb_dataview *dv);
 MSB_API int msb_dataview_size(const msb_dataview *dv, size_t *n);
 MSB_API int msb_dataview_nfeatures(const msb_dataview *dv, size_t *d);
@@ -135,6 +138,10 @@ MSB_API int msb_state_destroy(msb_state *st);
  * runtime_cast of runtime_type.hpp:145-166 applied once per cell) and sizes the
  * assignment vector (all -1, group_manager.hpp:64-69). */
 MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv);
+/* the bound dataview was re-uploaded (msb_dataview_upload): convert its records again, keeping the
+ * assignments and the suffstats (the reference re-reads its borrowed host rows on every pass,
+ * recarray/dataview.hpp:194-217; here the pass over host rows is upload + refresh + sweep). */
+MSB_API int msb_state_refresh(msb_state *st);
 
 MSB_API int msb_state_set_hp(msb_state *st, size_t feature, const char *key, const double *v, size_t count);
 MSB_API int msb_state_get_hp(msb_state *st, size_t feature, const char *key, double *v, size_t count);
@@ -174,14 +181,22 @@ MSB_API int msb_sample_discrete_log(msb_ctx *ctx, const float *scores, size_t nr
 /* the uniform the sweep draws for (seed, global row id, sweep): Philox4x32-10 */
 MSB_API int msb_philox_uniforms(msb_ctx *ctx, uint64_t seed, uint64_t sweep, uint64_t row_lo, size_t n, float *out);
 
+/* device self-test of the sampler's division sequence (sampler contract): n pseudo-random operand
+ * pairs, counts the results that differ from the IEEE division.  Must report 0. */
+MSB_API int msb_selftest_division(msb_ctx *ctx, uint64_t seed, size_t n, uint64_t *mismatches);
+
 typedef struct msb_sweep_opts {
   uint64_t seed;          /* Philox key */
   uint64_t sweep;         /* Philox counter word 2 */
   uint64_t row_id_offset; /* global id of local row 0 (multi-GPU row sharding) */
   const float *uniforms;  /* host array, one per row of [row_lo,row_hi), or NULL -> Philox */
   int32_t defer_apply;    /* 1: leave the suffstat deltas unapplied (all-reduce them, then msb_state_apply_deltas) */
-  int32_t reserved;
+  int32_t flags;          /* MSB_SWEEP_* */
 } msb_sweep_opts;
+
+/* enqueue the sweep on the context's stream and return without waiting; res->moved is then reported by
+ * msb_state_sweep_wait (or read as 0).  Uniforms passed with an asynchronous sweep must stay valid until then. */
+#define MSB_SWEEP_ASYNC 1
 
 typedef struct msb_sweep_result {
   uint64_t rows;   /* rows processed */
@@ -193,6 +208,9 @@ typedef struct msb_sweep_result {
  * then apply remove_value(old)/add_value(new) for every row that moved. */
 MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_hi, const msb_sweep_opts *opts,
                     msb_sweep_result *res);
+
+/* waits for the stream and reports the last sweep (rows, moved, units) */
+MSB_API int msb_state_sweep_wait(msb_state *st, msb_sweep_result *res);
 
 /* multi-GPU: flat fp64 buffer [group counts | per-feature suffstat deltas] on the device */
 MSB_API int msb_state_delta_buffer(msb_state *st, double **dev_ptr, size_t *count);
@@ -207,6 +225,9 @@ MSB_API int msb_state_read_last_scores(msb_state *st, float *out, size_t ld_out)
 /* events recorded around the kernels of the last sweep; ms per phase:
  * [0] table build, [1] score, [2] sample, [3] update, [4] apply */
 MSB_API int msb_state_last_timings(msb_state *st, float *ms, size_t count);
+/* the same for an earlier sweep: back = 0 is the last one, 1 the one before ... (a ring of 64 sweeps), so a
+ * caller can enqueue many asynchronous sweeps and read every one's phase times afterwards */
+MSB_API int msb_state_timings(msb_state *st, size_t back, float *ms, size_t count);
 
 /* ---- single-value plugin calls (models/base.hpp:25-27), run on the device -- */
 /* hp/ss are the flat field vectors in the order listed at enum msb_family */

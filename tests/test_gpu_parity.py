@@ -402,3 +402,61 @@ def test_niw_tensor_core_path_many_tiles_and_group_blocks(ctx, oracle, monkeypat
     assert np.max(rel_err(S2[rows], want)) < 4 * RTOL
     assert np.max(rel_err(S, S2)) < 4 * RTOL
     st.close()
+
+
+def test_upload_refresh_keeps_state_and_async_sweep_matches_blocking(ctx, oracle):
+    # a pass over HOST rows = upload + refresh + sweep: the re-ingested columns, the kept assignments
+    # and suffstats must give the same scores and draws as a state that never re-read its rows
+    descs = FAMILIES["mixed"]
+    n, k = 3000, 10
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=21, mask_frac=0.04, extra_empty=1)
+    st2, _, _, gids2, _, _, _ = make_state(ctx, oracle, descs, n, k, seed=21, mask_frac=0.04, extra_empty=1)
+    raw, mraw = view.raw()
+    dev = view.to_device(ctx)
+    for sweep in range(3):
+        dev.upload(np.ascontiguousarray(raw), np.ascontiguousarray(mraw))
+        st.refresh()
+        r = st.sweep(seed=5, sweep=sweep, wait=False)          # enqueued only
+        assert r["rows"] == n
+        got = st.sweep_wait()
+        want = st2.sweep(seed=5, sweep=sweep)                   # blocking
+        assert got["moved"] == want["moved"] and got["units"] == want["units"]
+        assert np.array_equal(st.assignments(), st2.assignments())
+        for g, g2 in zip(gids, gids2):
+            assert st.groupsize(g) == st2.groupsize(g2)
+        t = st.last_timings()
+        assert set(t) == {"build", "score", "sample", "update", "apply"} and t["score"] > 0.0
+    t_prev = st.last_timings(back=2)
+    assert t_prev["score"] > 0.0
+    with pytest.raises(cb.MsbError):
+        st.last_timings(back=3)       # only three sweeps were run
+    st.close(); st2.close()
+
+
+@pytest.mark.parametrize("k", [3, 33, 200, 390])
+def test_tile_and_blocked_samplers_draw_identically(ctx, oracle, k, monkeypatch):
+    # the shared-memory tile sampler (default when a [K][32] tile fits) and the global-memory walk must both
+    # reproduce util.hpp:125-156 bit for bit from the same score bits
+    descs = [cb.dd(5), cb.bb, cb.nich]
+    n = 4099
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=31, extra_empty=1)
+    st.sweep(seed=9, sweep=0)
+    a = np.searchsorted(gids, st.assignments()).astype(np.int32)
+    S = st.read_last_scores()
+    u = np.array([oracle.philox_u01(9, i, 0) for i in range(n)], np.float32)
+    assert np.array_equal(a, oracle.sample_rows(S, u))
+    st.close()
+    monkeypatch.setenv("MSB_NO_TILE_SAMPLER", "1")
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=31, extra_empty=1)
+    st.sweep(seed=9, sweep=0)
+    b = np.searchsorted(gids, st.assignments()).astype(np.int32)
+    assert np.array_equal(a, b)
+    st.close()
+
+
+def test_sampler_division_sequence_equals_ieee_division_on_device(ctx):
+    import ctypes as C
+    from common_b200 import _lib
+    bad = C.c_uint64(1)
+    _lib.check(_lib.load().msb_selftest_division(ctx.handle, 12345, 200_000_000, C.byref(bad)))
+    assert bad.value == 0
