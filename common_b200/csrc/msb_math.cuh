@@ -122,6 +122,12 @@ __device__ __forceinline__ double nich_score(const NichPost &p, double x) {
 // per-(group, feature) coefficient c1 by build_params_kernel).  z < 1/16: degree-5 polynomial on the
 // FMA pipe (relative error ~1e-8); above: MUFU.LG2(1 + z), whose absolute error 2^-22 is at most
 // 2.7e-6 relative just above the switch.  Branch-free: both are evaluated and selected.
+// MUFU.LG2 without the subnormal-input fix-up __log2f carries (the argument here is 1 + z >= 1)
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float log2_1p_pos(float z) {
   constexpr float L2E = 1.4426950408889634f;
   float p = -L2E / 6.0f;
@@ -131,8 +137,23 @@ __device__ __forceinline__ float log2_1p_pos(float z) {
   p = fmaf(p, z, -L2E / 2.0f);
   p = fmaf(p, z, L2E);
   const float small = p * z;
-  const float big = __log2f(1.0f + z);
+  const float big = lg2_ftz(1.0f + z);
   return z < 0.0625f ? small : big;
+}
+
+// The same for two groups at once with the packed fp32 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: one issue
+// slot per pair): the nich loop is bound by instruction issue, not by the FMA lanes.  Bit-identical to two
+// calls of log2_1p_pos.
+__device__ __forceinline__ float2 log2_1p_pos2(float2 z) {
+  constexpr float L2E = 1.4426950408889634f;
+  float2 p = __ffma2_rn(make_float2(-L2E / 6.0f, -L2E / 6.0f), z, make_float2(L2E / 5.0f, L2E / 5.0f));
+  p = __ffma2_rn(p, z, make_float2(-L2E / 4.0f, -L2E / 4.0f));
+  p = __ffma2_rn(p, z, make_float2(L2E / 3.0f, L2E / 3.0f));
+  p = __ffma2_rn(p, z, make_float2(-L2E / 2.0f, -L2E / 2.0f));
+  p = __ffma2_rn(p, z, make_float2(L2E, L2E));
+  const float2 small = __fmul2_rn(p, z);
+  const float2 w = __fadd2_rn(z, make_float2(1.0f, 1.0f));
+  return make_float2(z.x < 0.0625f ? small.x : lg2_ftz(w.x), z.y < 0.0625f ? small.y : lg2_ftz(w.y));
 }
 
 }  // namespace msb

@@ -244,8 +244,18 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
         for (int e = 0; e < 4; e++) {
           VecF<V> tv;
           tv.load(chunk + (size_t)idx[e] * KT);
+          if constexpr (V % 2 == 0) {
 #pragma unroll
-          for (int v = 0; v < V; v++) acc[r4 * 4 + e][v] += tv.v[v];
+            for (int h = 0; h < V / 2; h++) {
+              const float2 a = __fadd2_rn(make_float2(acc[r4 * 4 + e][2 * h], acc[r4 * 4 + e][2 * h + 1]),
+                                          make_float2(tv.v[2 * h], tv.v[2 * h + 1]));
+              acc[r4 * 4 + e][2 * h] = a.x;
+              acc[r4 * 4 + e][2 * h + 1] = a.y;
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; v++) acc[r4 * 4 + e][v] += tv.v[v];
+          }
         }
       }
       if (!TABLES_ONLY && t.kind == KIND_GP) {  // counts beyond the table: the fp64 closed form from the suffstats (rare)
@@ -277,17 +287,44 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
       mu.load(chunk + 0 * KT);
       sc.load(chunk + 1 * KT);
       c1.load(chunk + 2 * KT);
+      if constexpr (V % 2 == 0) {  // two groups per instruction (FADD2 / FMUL2 / FFMA2)
+        float2 nmu2[V / 2], sc2[V / 2], c12[V / 2];
 #pragma unroll
-      for (int r4 = 0; r4 < RW / 4; r4++) {
-        const uint4 q = xq[r4];
-        const float xs[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+        for (int h = 0; h < V / 2; h++) {
+          nmu2[h] = make_float2(-mu.v[2 * h], -mu.v[2 * h + 1]);
+          sc2[h] = make_float2(sc.v[2 * h], sc.v[2 * h + 1]);
+          c12[h] = make_float2(c1.v[2 * h], c1.v[2 * h + 1]);
+        }
 #pragma unroll
-        for (int e = 0; e < 4; e++)
+        for (int r4 = 0; r4 < RW / 4; r4++) {
+          const uint4 q = xq[r4];
+          const float xs[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
 #pragma unroll
-          for (int v = 0; v < V; v++) {
-            const float tt = (xs[e] - mu.v[v]) * sc.v[v];
-            acc[r4 * 4 + e][v] = fmaf(c1.v[v], log2_1p_pos(tt * tt), acc[r4 * 4 + e][v]);
+          for (int e = 0; e < 4; e++) {
+            const float2 x2 = make_float2(xs[e], xs[e]);
+#pragma unroll
+            for (int h = 0; h < V / 2; h++) {
+              const float2 tt = __fmul2_rn(__fadd2_rn(x2, nmu2[h]), sc2[h]);
+              const float2 a = __ffma2_rn(c12[h], log2_1p_pos2(__fmul2_rn(tt, tt)),
+                                          make_float2(acc[r4 * 4 + e][2 * h], acc[r4 * 4 + e][2 * h + 1]));
+              acc[r4 * 4 + e][2 * h] = a.x;
+              acc[r4 * 4 + e][2 * h + 1] = a.y;
+            }
           }
+        }
+      } else {
+#pragma unroll
+        for (int r4 = 0; r4 < RW / 4; r4++) {
+          const uint4 q = xq[r4];
+          const float xs[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+              const float tt = (xs[e] - mu.v[v]) * sc.v[v];
+              acc[r4 * 4 + e][v] = fmaf(c1.v[v], log2_1p_pos(tt * tt), acc[r4 * 4 + e][v]);
+            }
+        }
       }
       // masked cells were scored as x = 0: undo that term and the c0 that base[] carries for this feature (rare)
 #pragma unroll
