@@ -359,10 +359,30 @@ def main():
         score_ms = phase["score"] / args.steps
         abytes = algorithmic_bytes_score(descs, storage, n, k)
         achieved = abytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
+        traffic, wf = None, None
+        ctx_sm_count = torch.cuda.get_device_properties(device).multi_processor_count
+        try:  # DRAM bytes per launch of this kernel from the committed ncu capture (same workload, same size)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload.upper())
+            if tr and tr.get("rows") == n and world >= 1:
+                traffic = tr["dram_bytes_per_launch"]
+                wf = tr.get("smem_wavefronts_per_launch")
+        except Exception:
+            pass
+        binding = None
+        try:
+            if wf and score_ms > 0 and clk and clk.get("sm_mhz"):
+                # the pipe that really binds this kernel: one 128-byte shared-memory wavefront per SM per clock
+                per_clk = wf / (score_ms * 1e-3 * clk["sm_mhz"] * 1e6 * ctx_sm_count)
+                binding = {"resource": "shared-memory wavefronts (LSU data pipe, 1 per SM per clock)",
+                           "wavefronts_per_launch": wf, "frac": per_clk, "source": tr["capture"]}
+        except Exception:
+            pass
         roof = {"kernel": "score_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": abytes,
+                "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": abytes,
                 "launch_ms": score_ms, "peak_source": peak_src,
                 "note": "score kernels reuse every loaded value K times: the binding roof is shared-memory lookup / FP32 issue rate, see DESIGN.md"}
+        if binding:
+            roof["binding"] = binding
         if tf32_peak:
             dims = [d()._param() for d in descs if d().name() == "niw"]
             flops = sum(2.0 * dd_ * dd_ * n * k for dd_ in dims)   # whitened-GEMM form, SURVEY.md section 8(d)

@@ -23,6 +23,15 @@ template <> struct VecF<1> { float v[1]; __device__ __forceinline__ void load(co
 template <> struct VecF<2> { float v[2]; __device__ __forceinline__ void load(const float *p) { const float2 t = *(const float2 *)p; v[0] = t.x; v[1] = t.y; } };
 template <> struct VecF<4> { float v[4]; __device__ __forceinline__ void load(const float *p) { const float4 t = *(const float4 *)p; v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
 
+// the same loads from a 32-bit shared-memory address: the lookup address is then ONE integer multiply-add
+// (per-lane chunk base + row index * row bytes) instead of the two the generic-pointer form compiles to
+template <int V>
+__device__ __forceinline__ void lds_vec(float *v, uint32_t addr) {
+  if constexpr (V == 1) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(addr));
+  else if constexpr (V == 2) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr));
+  else asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+
 template <int V>
 __device__ __forceinline__ void store_vec(float *p, const float *a) {
   if constexpr (V == 1) *p = a[0];
@@ -237,13 +246,14 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
 
     if (TABLES_ONLY || t.kind != KIND_NICH) {
 #pragma unroll
+      const uint32_t chunk_s = smem_u32(chunk);
       for (int r4 = 0; r4 < RW / 4; r4++) {
         const uint4 q = xq[r4];
         const uint32_t idx[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           VecF<V> tv;
-          tv.load(chunk + (size_t)idx[e] * KT);
+          lds_vec<V>(tv.v, chunk_s + idx[e] * (uint32_t)(KT * sizeof(float)));
           if constexpr (V % 2 == 0) {
 #pragma unroll
             for (int h = 0; h < V / 2; h++) {
