@@ -132,6 +132,87 @@ __global__ void scorecol_kernel(const FeatDev *__restrict__ feats, int nfeat, si
   }
 }
 
+// pack_kernel + scorecol_kernel in one pass with the AoS records staged in shared memory: a block copies TR
+// consecutive records (and their mask rows) with coalesced 4-byte loads into a padded tile (pitch = record
+// words + 1: thread = row reads of one field are bank-conflict free), then thread r converts every field of
+// row r and writes the Value-typed column, the score column and (by ballot) the slow-path mask.  The records
+// are read from HBM exactly once.  Needs the gp table sizes (refresh path; bind sizes them first).
+// rowsize and maskrowsize are multiples of 4 here (the host falls back to the two-kernel path otherwise).
+template <int TR>
+__global__ void __launch_bounds__(TR)
+ingest_tile_kernel(const uint8_t *__restrict__ data, const uint8_t *__restrict__ mask, size_t n, size_t n_pad,
+                   uint32_t rowwords, uint32_t maskwords, const FeatDev *__restrict__ feats, int nfeat,
+                   uint32_t *__restrict__ any_slow) {
+  extern __shared__ uint32_t tile[];
+  const uint32_t pitch = rowwords + 1, mpitch = maskwords + 1;
+  uint32_t *mtile = tile + (size_t)TR * pitch;
+  const size_t row0 = (size_t)blockIdx.x * TR;
+  const size_t rows_here = row0 < n ? min((size_t)TR, n - row0) : 0;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(data) + row0 * rowwords;
+    const uint32_t total = (uint32_t)rows_here * rowwords;
+    for (uint32_t g = threadIdx.x; g < total; g += TR) tile[(g / rowwords) * pitch + g % rowwords] = src[g];
+    if (mask) {
+      const uint32_t *msrc = reinterpret_cast<const uint32_t *>(mask) + row0 * maskwords;
+      const uint32_t mtotal = (uint32_t)rows_here * maskwords;
+      for (uint32_t g = threadIdx.x; g < mtotal; g += TR) mtile[(g / maskwords) * mpitch + g % maskwords] = msrc[g];
+    }
+  }
+  __syncthreads();
+  const size_t row = row0 + threadIdx.x;   // n_pad is a multiple of TR: every thread owns a (possibly padding) row
+  const bool live = row < n;
+  const uint8_t *rec = reinterpret_cast<const uint8_t *>(tile + (size_t)threadIdx.x * pitch);
+  const uint8_t *mrec = reinterpret_cast<const uint8_t *>(mtile + (size_t)threadIdx.x * mpitch);
+  for (int d = 0; d < nfeat; d++) {
+    const FeatDev f = feats[d];
+    bool masked = false;
+    if (mask && live)
+      for (uint32_t i = 0; i < f.src_n; i++) masked |= (mrec[f.msk_off + i] != 0);
+    const uint32_t ps = prim_size(f.src_prim);
+    if (f.kind == KIND_NIW) {
+      if (live) {
+        float *dst = (float *)f.col + row * (size_t)f.dim;
+        for (uint32_t i = 0; i < f.dim; i++) dst[i] = (float)load_prim(rec + f.src_off + i * ps, f.src_prim);
+        if (masked) dst[0] = CUDART_NAN_F;
+      }
+      continue;
+    }
+    const double v = live ? load_prim(rec + f.src_off, f.src_prim) : 0.0;
+    uint32_t out;
+    bool slow = false;
+    if (f.kind == KIND_NICH) {
+      const float x = masked ? CUDART_NAN_F : (float)v;
+      if (live) ((float *)f.col)[row] = x;
+      slow = live && masked;
+      out = (slow || !live) ? 0u : __float_as_uint(x);
+    } else if (f.kind == KIND_GP) {
+      uint32_t x = v < 0.0 ? 0u : (v >= 4294967294.0 ? 4294967294u : (uint32_t)v);
+      if (masked || !live) x = GP_SENTINEL;
+      if (live) ((uint32_t *)f.col)[row] = x;
+      slow = x != GP_SENTINEL && x >= f.ncat;
+      out = x < f.ncat ? x : f.ncat;
+    } else {
+      uint32_t x = f.ncat;
+      if (live && !masked) {
+        if (f.family == FAM_BB) x = (v != 0.0) ? 1u : 0u;
+        else if (v >= 0.0 && v < (double)f.ncat) x = (uint32_t)v;
+      }
+      if (live) {
+        if (f.coltype == COL_U8) ((uint8_t *)f.col)[row] = (uint8_t)x;
+        else if (f.coltype == COL_U16) ((uint16_t *)f.col)[row] = (uint16_t)x;
+        else ((uint32_t *)f.col)[row] = x;
+      }
+      out = x;
+    }
+    if (row < n_pad) const_cast<uint32_t *>(f.scol)[row] = out;
+    const uint32_t m = __ballot_sync(0xffffffffu, slow);
+    if ((threadIdx.x & 31) == 0 && row < n_pad) {
+      const_cast<uint32_t *>(f.slowmask)[row >> 5] = m;
+      if (m) any_slow[d] = 1u;
+    }
+  }
+}
+
 // max over a gp column (ignoring masked cells): sizes the lookup table
 __global__ void colmax_u32_kernel(const uint32_t *__restrict__ col, size_t n, uint32_t *out) {
   uint32_t m = 0;

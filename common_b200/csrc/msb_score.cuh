@@ -245,8 +245,8 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
       slow[j] = (!TABLES_ONLY && t.has_slow) ? reinterpret_cast<const uint32_t *>(st + X_BYTES)[warp * RL + j] : 0u;
 
     if (TABLES_ONLY || t.kind != KIND_NICH) {
-#pragma unroll
       const uint32_t chunk_s = smem_u32(chunk);
+#pragma unroll
       for (int r4 = 0; r4 < RW / 4; r4++) {
         const uint4 q = xq[r4];
         const uint32_t idx[4] = {q.x, q.y, q.z, q.w};

@@ -49,6 +49,7 @@ struct msb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;  // host -> device record uploads run here, overlapping the kernels on `stream`
   uint64_t launches = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
@@ -61,7 +62,23 @@ struct msb_dataview {
   std::vector<size_t> off, moff;
   uint8_t *d_data = nullptr, *d_mask = nullptr;
   bool owns = false;
+  // ordering between the copy stream (msb_dataview_upload) and the compute stream (kernels that read the records)
+  cudaEvent_t ev_uploaded = nullptr, ev_consumed = nullptr;
+  bool upload_pending = false, consumed_recorded = false;
 };
+
+// the compute stream is about to read dv's records: wait for an upload still in flight on the copy stream
+static cudaError_t dv_acquire(msb_dataview *dv) {
+  if (!dv->upload_pending) return cudaSuccess;
+  dv->upload_pending = false;
+  return cudaStreamWaitEvent(dv->ctx->stream, dv->ev_uploaded, 0);
+}
+// the compute stream has enqueued its last read of dv's records: the next upload may overwrite them after this point
+static cudaError_t dv_release(msb_dataview *dv) {
+  if (!dv->ev_consumed) return cudaSuccess;
+  dv->consumed_recorded = true;
+  return cudaEventRecord(dv->ev_consumed, dv->ctx->stream);
+}
 
 struct PhaseEvents { cudaEvent_t e[6]; };
 
@@ -167,6 +184,7 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   c->smem_optin = prop.sharedMemPerBlockOptin;
   if (stream) c->stream = (cudaStream_t)stream;
   else { CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CU_TRY(opt_in_smem(score_kernel<1, 64, 16, false, false>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<2, 32, 16, false, false>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<4, 32, 8, false, false>, c->smem_optin));
@@ -184,6 +202,7 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   CU_TRY(opt_in_smem(score_kernel<4, 32, 8, true, true>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<1, 32, 8, true, true>, c->smem_optin));
   CU_TRY(opt_in_smem(sample_tile_kernel<4>, c->smem_optin));
+  CU_TRY(opt_in_smem(ingest_tile_kernel<128>, c->smem_optin));
   CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin - 1024));  // it also has a few bytes of static shared memory
   CU_TRY(opt_in_smem(niw_score_simt_kernel, c->smem_optin - 1024));
   MSB_TRY(niw_tc_init(c->smem_optin, g_last_error));
@@ -195,12 +214,15 @@ extern "C" MSB_API int msb_ctx_destroy(msb_ctx *ctx) {
   if (!ctx) return MSB_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return MSB_OK;
 }
 extern "C" MSB_API int msb_ctx_synchronize(msb_ctx *ctx) {
   REQUIRE(ctx, "ctx is NULL");
+  CU_TRY(cudaStreamSynchronize(ctx->copy_stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
   return MSB_OK;
 }
@@ -241,6 +263,8 @@ extern "C" MSB_API int msb_dataview_create(msb_ctx *ctx, const void *data, const
     dv->d_data = (uint8_t *)data; dv->d_mask = (uint8_t *)mask; dv->owns = false;
   } else {
     dv->owns = true;
+    CU_TRY(cudaEventCreateWithFlags(&dv->ev_uploaded, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&dv->ev_consumed, cudaEventDisableTiming));
     if (n) {
       CU_TRY(cudaMalloc(&dv->d_data, n * dv->rowsize));
       CU_TRY(cudaMemcpyAsync(dv->d_data, data, n * dv->rowsize, cudaMemcpyHostToDevice, ctx->stream));
@@ -259,17 +283,31 @@ extern "C" MSB_API int msb_dataview_upload(msb_dataview *dv, const void *data, c
   REQUIRE(dv->owns, "msb_dataview_upload: the dataview borrows device memory");
   REQUIRE((mask != nullptr) == (dv->d_mask != nullptr) || dv->n == 0, "msb_dataview_upload: mask presence must match the dataview");
   if (!dv->n) return MSB_OK;
-  CU_TRY(cudaSetDevice(dv->ctx->device));
-  CU_TRY(cudaMemcpyAsync(dv->d_data, data, dv->n * dv->rowsize, cudaMemcpyHostToDevice, dv->ctx->stream));
-  if (mask) CU_TRY(cudaMemcpyAsync(dv->d_mask, mask, dv->n * dv->maskrowsize, cudaMemcpyHostToDevice, dv->ctx->stream));
+  msb_ctx *ctx = dv->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  // The copy runs on the context's copy stream, after the last kernel that reads the old records
+  // (ev_consumed) and concurrently with everything enqueued on the compute stream since; the next
+  // msb_state_refresh / msb_state_bind / msb_dataview_get_row makes the compute stream wait for it.
+  if (dv->consumed_recorded) CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, dv->ev_consumed, 0));
+  else {  // nothing recorded yet: order after everything enqueued so far (the creating copy included)
+    CU_TRY(cudaEventRecord(dv->ev_consumed, ctx->stream));
+    CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, dv->ev_consumed, 0));
+  }
+  CU_TRY(cudaMemcpyAsync(dv->d_data, data, dv->n * dv->rowsize, cudaMemcpyHostToDevice, ctx->copy_stream));
+  if (mask) CU_TRY(cudaMemcpyAsync(dv->d_mask, mask, dv->n * dv->maskrowsize, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CU_TRY(cudaEventRecord(dv->ev_uploaded, ctx->copy_stream));
+  dv->upload_pending = true;
   return MSB_OK;
 }
 
 extern "C" MSB_API int msb_dataview_destroy(msb_dataview *dv) {
   if (!dv) return MSB_OK;
   cudaSetDevice(dv->ctx->device);
+  cudaStreamSynchronize(dv->ctx->copy_stream);
   cudaStreamSynchronize(dv->ctx->stream);
   if (dv->owns) { cudaFree(dv->d_data); cudaFree(dv->d_mask); }
+  if (dv->ev_uploaded) cudaEventDestroy(dv->ev_uploaded);
+  if (dv->ev_consumed) cudaEventDestroy(dv->ev_consumed);
   delete dv;
   return MSB_OK;
 }
@@ -285,6 +323,7 @@ extern "C" MSB_API int msb_dataview_get_row(msb_dataview *dv, size_t idx, void *
   REQUIRE(dv && row_out, "NULL argument");
   REQUIRE(idx < dv->n, "invalid position");  // dataview.cpp:131
   CU_TRY(cudaSetDevice(dv->ctx->device));
+  CU_TRY(dv_acquire(dv));
   CU_TRY(cudaMemcpyAsync(row_out, dv->d_data + idx * dv->rowsize, dv->rowsize, cudaMemcpyDeviceToHost, dv->ctx->stream));
   if (mask_out) {
     if (dv->d_mask) CU_TRY(cudaMemcpyAsync(mask_out, dv->d_mask + idx * dv->maskrowsize, dv->maskrowsize, cudaMemcpyDeviceToHost, dv->ctx->stream));
@@ -539,6 +578,24 @@ static void layout_chunks(msb_state *st) {
   st->feats_dirty = true;
 }
 
+// per-feature "some cell needs the slow path" flags -> host; decides the tables-only kernel variant
+static int ingest_flags(msb_state *st, bool force_dirty) {
+  msb_ctx *ctx = st->ctx;
+  const size_t D = st->D;
+  CU_TRY(cudaMemcpyAsync(st->h_flags, st->d_flags, sizeof(uint32_t) * D, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  bool any = false, changed = false;
+  for (size_t d = 0; d < D; d++) {
+    changed |= st->feats[d].has_slow != st->h_flags[d];
+    st->feats[d].has_slow = st->h_flags[d];
+    any |= st->h_flags[d] != 0;
+  }
+  // the tables-only kernel has no slow path and no nich code: gp features qualify when no count exceeds their table
+  st->tables_only = !any && !st->has_nich && !getenv("MSB_NO_TABLES_ONLY");
+  if (changed || force_dirty) st->feats_dirty = true;
+  return MSB_OK;
+}
+
 // Reads the bound dataview into the Value-typed columns (pack_kernel) and the score columns + slow-path
 // masks (scorecol_kernel).  size_tables: also size the gp lookup tables from the column maxima (bind);
 // a refresh keeps the table sizes, counts beyond them take the score kernel's closed-form path.
@@ -547,10 +604,23 @@ static int ingest(msb_state *st, bool size_tables) {
   msb_dataview *dv = st->dv;
   const size_t D = st->D;
   MSB_TRY(sync_small(st));
+  CU_TRY(dv_acquire(dv));
+  // refresh path: one fused pass over the records staged in shared memory (they are read from HBM once)
+  constexpr int TR = 128;
+  const size_t tile_bytes = ((size_t)TR * (dv->rowsize / 4 + 1) + (dv->d_mask ? (size_t)TR * (dv->maskrowsize / 4 + 1) : 0)) * 4;
+  if (!size_tables && dv->n && st->has_scalar && dv->rowsize % 4 == 0 && (!dv->d_mask || dv->maskrowsize % 4 == 0) &&
+      tile_bytes <= ctx->smem_optin && !getenv("MSB_NO_FUSED_INGEST")) {
+    CU_TRY(cudaMemsetAsync(st->d_flags, 0, sizeof(uint32_t) * D, ctx->stream));
+    LAUNCH(ctx, ingest_tile_kernel<TR>, (unsigned)(st->n_pad / TR), TR, tile_bytes, dv->d_data, dv->d_mask, dv->n, st->n_pad,
+           (uint32_t)(dv->rowsize / 4), (uint32_t)(dv->maskrowsize / 4), st->d_feats, (int)D, st->d_flags);
+    CU_TRY(dv_release(dv));
+    return ingest_flags(st, false);
+  }
   if (dv->n) {
     dim3 grid(cdiv(dv->n, 256), (unsigned)D);
     LAUNCH(ctx, pack_kernel, grid, 256, 0, dv->d_data, dv->d_mask, dv->n, dv->rowsize, dv->maskrowsize, st->d_feats, (int)D);
   }
+  CU_TRY(dv_release(dv));
   if (size_tables) {
     std::vector<size_t> gp;
     for (size_t d = 0; d < D; d++) if (st->feats[d].kind == KIND_GP) gp.push_back(d);
@@ -573,17 +643,7 @@ static int ingest(msb_state *st, bool size_tables) {
     CU_TRY(cudaMemsetAsync(st->d_flags, 0, sizeof(uint32_t) * D, ctx->stream));
     dim3 grid((unsigned)(st->n_pad / 256), (unsigned)D);
     LAUNCH(ctx, scorecol_kernel, grid, 256, 0, st->d_feats, (int)D, dv->n, st->n_pad, st->d_flags);
-    CU_TRY(cudaMemcpyAsync(st->h_flags, st->d_flags, sizeof(uint32_t) * D, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
-    bool any = false, changed = false;
-    for (size_t d = 0; d < D; d++) {
-      changed |= st->feats[d].has_slow != st->h_flags[d];
-      st->feats[d].has_slow = st->h_flags[d];
-      any |= st->h_flags[d] != 0;
-    }
-    // the tables-only kernel has no slow path and no nich code: gp features qualify when no count exceeds their table
-    st->tables_only = !any && !st->has_nich && !getenv("MSB_NO_TABLES_ONLY");
-    if (changed || size_tables) st->feats_dirty = true;
+    return ingest_flags(st, size_tables);
   }
   return MSB_OK;
 }

@@ -460,3 +460,27 @@ def test_sampler_division_sequence_equals_ieee_division_on_device(ctx):
     bad = C.c_uint64(1)
     _lib.check(_lib.load().msb_selftest_division(ctx.handle, 12345, 200_000_000, C.byref(bad)))
     assert bad.value == 0
+
+
+def test_uploads_on_the_copy_stream_are_ordered_with_the_kernels(ctx, oracle):
+    # upload(B) is enqueued while the sweep over A is still running: the conversion of A must have finished
+    # reading before B lands, and the next refresh must see all of B
+    descs = FAMILIES["mixed"]
+    n, k = 50000, 6
+    st, view_a, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=41)
+    arr_b, _ = cb.synth.make_dataset(descs, n, k, seed=42)
+    view_b = cb.numpy_dataview(arr_b)
+    raw_a, _ = view_a.raw()
+    raw_b, _ = view_b.raw()
+    raw_a, raw_b = np.ascontiguousarray(raw_a), np.ascontiguousarray(raw_b)
+    dev = view_a.to_device(ctx)
+    lp = ol.logprior(counts, 1.0)
+    want = {"a": oracle.score_rows(descs, hp, ss, lp, view_a), "b": oracle.score_rows(descs, hp, ss, lp, view_b)}
+    for which, nxt in [("a", raw_b), ("b", raw_a), ("a", raw_b), ("b", raw_a)]:
+        st.refresh()
+        dev.upload(nxt)                       # next pass's records, concurrent with the scoring below
+        _, S = st.score_rows()
+        assert np.max(rel_err(S, want[which])) < RTOL
+        row, _ = dev.get_row_bytes(n - 1)     # reads the NEW records (waits for the upload)
+        assert np.array_equal(row, nxt[n - 1])
+    st.close()
