@@ -384,6 +384,139 @@ __global__ void niw_prepare_kernel(FeatDev f, const double *__restrict__ hp, con
   }
 }
 
+// ---------------------------------------------------------------------------
+// group::score_data (models/base.hpp:28, forwarded at distributions.hpp:287-291): log marginal likelihood of the
+// data a group holds, per (group column, feature), fp64 closed forms from the resident suffstats.
+// out[col * nfeat + d].  K x D evaluations: not a hot kernel.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double lbeta_d(double a, double b) { return lgamma(a) + lgamma(b) - lgamma(a + b); }
+
+__global__ void score_data_kernel(const FeatDev *__restrict__ feats, int nfeat, const double *__restrict__ hp,
+                                  const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols,
+                                  double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncols * nfeat) return;
+  const int col = i / nfeat, d = i - col * nfeat;
+  const FeatDev f = feats[d];
+  if (f.kind == KIND_NIW) return;  // niw_score_data_kernel
+  const double *h = hp + f.hp_off;
+  const double *g = ss + f.ss_off + (size_t)col2slot[col] * f.ss_w;
+  double r;
+  if (f.family == FAM_BB) {
+    r = lbeta_d(h[0] + g[0], h[1] + g[1]) - lbeta_d(h[0], h[1]);
+  } else if (f.family == FAM_DD) {
+    r = lgamma(f.asum) - lgamma(f.asum + g[0]);
+    for (uint32_t c = 0; c < f.dim; c++) r += lgamma(h[c] + g[1 + c]) - lgamma(h[c]);
+  } else if (f.kind == KIND_GP) {  // prior Gamma(alpha, rate inv_beta); ss = count, sum, sum log x!
+    const double a = h[0] + g[1], b = h[1] + g[0];
+    r = lgamma(a) - lgamma(h[0]) + h[0] * log(h[1]) - a * log(b) - g[2];
+  } else {  // nich; device ss = (count, sum x, sum x^2)
+    const double n = g[0];
+    const double mean = n > 0.0 ? g[1] / n : 0.0;
+    double ctv = n > 0.0 ? g[2] - g[1] * mean : 0.0;
+    if (ctv < 0.0) ctv = 0.0;
+    const double mu1 = h[0] - mean;
+    const double kappa = h[1] + n, nu = h[3] + n;
+    const double sigmasq = (h[3] * h[2] + ctv + (n * h[1] * mu1 * mu1) / kappa) / nu;
+    r = lgamma(0.5 * nu) - lgamma(0.5 * h[3]) + 0.5 * log(h[1] / kappa) + 0.5 * h[3] * log(h[3] * h[2]) -
+        0.5 * nu * log(nu * sigmasq) - 0.5 * n * log(CUDART_PI);
+  }
+  out[i] = r;
+}
+
+// In-place lower Cholesky of the d x d matrix A in shared memory by the whole block (right-looking, as in
+// niw_prepare_kernel); returns log |A| = 2 sum log L_ii, NaN if A is not positive definite.
+__device__ double block_chol_logdet(double *A, int d, int *s_fail, double *s_acc) {
+  if (threadIdx.x == 0) { *s_fail = 0; *s_acc = 0.0; }
+  __syncthreads();
+  for (int j = 0; j < d; j++) {
+    if (threadIdx.x == 0) {
+      const double v = A[j * d + j];
+      if (!(v > 0.0)) *s_fail = 1;
+      A[j * d + j] = sqrt(v > 0.0 ? v : 1.0);
+      *s_acc += 2.0 * log(A[j * d + j]);
+    }
+    __syncthreads();
+    const double ljj = A[j * d + j];
+    for (int i = j + 1 + threadIdx.x; i < d; i += blockDim.x) A[i * d + j] /= ljj;
+    __syncthreads();
+    const int rem = d - j - 1;
+    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
+      const int a = j + 1 + e / rem, b = j + 1 + e % rem;
+      if (b <= a) A[a * d + b] -= A[a * d + j] * A[b * d + j];
+    }
+    __syncthreads();
+  }
+  return *s_fail ? CUDART_NAN : *s_acc;
+}
+
+// NIW marginal likelihood, one block per group column:
+//   -n d/2 log pi + lgamma_d(nu'/2) - lgamma_d(nu/2) + nu/2 log|psi| - nu'/2 log|psi'| + d/2 log(kappa/kappa')
+__global__ void niw_score_data_kernel(FeatDev f, int feat_index, int nfeat, const double *__restrict__ hp,
+                                      const double *__restrict__ ss, const int32_t *__restrict__ col2slot,
+                                      double *__restrict__ out) {
+  extern __shared__ double sm[];
+  const int d = (int)f.dim;
+  double *A = sm;          // d*d
+  double *mu = A + d * d;  // d
+  __shared__ int s_fail;
+  __shared__ double s_acc;
+  const int k = blockIdx.x;
+  const double *fhp = hp + f.hp_off;
+  const double *gss = ss + f.ss_off + (size_t)col2slot[k] * f.ss_w;
+  const double *mu0 = fhp, kappa0 = fhp[d], *psi0 = fhp + d + 1, nu0 = fhp[d + 1 + (size_t)d * d];
+  const double n = gss[0];
+  const double *sx = gss + 1, *sxx = gss + 1 + d;
+  const double kn = kappa0 + n, nun = nu0 + n;
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) A[e] = psi0[e];
+  __syncthreads();
+  const double ld0 = block_chol_logdet(A, d, &s_fail, &s_acc);
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) mu[i] = (kappa0 * mu0[i] + sx[i]) / kn;
+  __syncthreads();
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int i = e / d, j = e - i * d;
+    A[e] = psi0[e] + sxx[e] + kappa0 * mu0[i] * mu0[j] - kn * mu[i] * mu[j];
+  }
+  __syncthreads();
+  const double ldn = block_chol_logdet(A, d, &s_fail, &s_acc);
+  if (threadIdx.x == 0) {
+    double lg = 0.0;  // lgamma_d(nu'/2) - lgamma_d(nu/2): the pi^(d(d-1)/4) factors cancel
+    for (int j = 0; j < d; j++) lg += lgamma(0.5 * (nun - j)) - lgamma(0.5 * (nu0 - j));
+    out[(size_t)k * nfeat + feat_index] = -0.5 * n * d * log(CUDART_PI) + lg + 0.5 * nu0 * ld0 - 0.5 * nun * ldn +
+                                          0.5 * d * log(kappa0 / kn);
+  }
+}
+
+// group_manager::score_assignment (group_manager.hpp:250-272) in closed form from the resident counts: the CRP
+// probability of a partition depends only on the group sizes and on which group holds entity 0:
+//   sum_g [log alpha (unless g holds entity 0) + lgamma(n_g)] - (lgamma(n + alpha) - lgamma(1 + alpha)).
+// out[0] = the score, out[1] = number of assigned entities (the caller checks it equals n).  One block.
+__global__ void score_assignment_kernel(const double *__restrict__ counts, const int32_t *__restrict__ col2slot,
+                                        int ncols, const int32_t *__restrict__ assign, double alpha,
+                                        double *__restrict__ out) {
+  __shared__ double s_sum, s_n;
+  if (threadIdx.x == 0) { s_sum = 0.0; s_n = 0.0; }
+  __syncthreads();
+  const int first = assign[0];
+  double s = 0.0, n = 0.0;
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+    const int slot = col2slot[c];
+    const double cnt = counts[slot];
+    if (cnt > 0.0) {
+      s += (slot == first ? 0.0 : log(alpha)) + lgamma(cnt);
+      n += cnt;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); n += __shfl_xor_sync(0xffffffffu, n, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&s_sum, s); atomicAdd(&s_n, n); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out[0] = s_sum - (lgamma(s_n + alpha) - lgamma(1.0 + alpha));
+    out[1] = s_n;
+  }
+}
+
 // CUDA-core NIW scorer (any dim): thread per row, W_k staged in shared memory.
 // scores[row][k] += c0 + c1 log1p(q / dof).  The tcgen05 path replaces this
 // for dim == 64 (msb_niw_tc.cuh).

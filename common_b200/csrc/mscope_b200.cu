@@ -203,6 +203,7 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   CU_TRY(opt_in_smem(score_kernel<1, 32, 8, true, true>, c->smem_optin));
   CU_TRY(opt_in_smem(sample_tile_kernel<4>, c->smem_optin));
   CU_TRY(opt_in_smem(ingest_tile_kernel<128>, c->smem_optin));
+  CU_TRY(opt_in_smem(niw_score_data_kernel, c->smem_optin - 1024));
   CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin - 1024));  // it also has a few bytes of static shared memory
   CU_TRY(opt_in_smem(niw_score_simt_kernel, c->smem_optin - 1024));
   MSB_TRY(niw_tc_init(c->smem_optin, g_last_error));
@@ -1347,6 +1348,77 @@ extern "C" MSB_API int msb_state_last_timings(msb_state *st, float *ms, size_t c
   for (size_t i = 0; i < count; i++) ms[i] = 0.f;
   if (!st->sweep_seq) return MSB_OK;
   return msb_state_timings(st, 0, ms, count);
+}
+
+// ---- marginal likelihoods (entity_state.hpp:74-86, group_manager.hpp:250-272) -------------------------------
+// out[c * D + d] = group::score_data of (group column c, feature d), columns in ascending gid order
+static int score_data_matrix(msb_state *st, std::vector<double> &h) {
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  MSB_TRY(prepare_columns(st));
+  MSB_TRY(sync_small(st));
+  const size_t K = st->h_col2slot.size(), D = st->D;
+  double *d_out = nullptr;
+  CU_TRY(cudaMalloc(&d_out, sizeof(double) * K * D));
+  LAUNCH(ctx, score_data_kernel, cdiv(K * D, 128), 128, 0, st->d_feats, (int)D, st->d_hp, st->d_ss, st->d_col2slot, (int)K, d_out);
+  for (size_t d = 0; d < D; d++) {
+    const FeatDev &f = st->feats[d];
+    if (f.kind != KIND_NIW) continue;
+    const size_t smem = ((size_t)f.dim * f.dim + f.dim) * sizeof(double);
+    LAUNCH(ctx, niw_score_data_kernel, (unsigned)K, 128, smem, f, (int)d, (int)D, st->d_hp, st->d_ss, st->d_col2slot, d_out);
+  }
+  h.resize(K * D);
+  CU_TRY(cudaMemcpyAsync(h.data(), d_out, sizeof(double) * K * D, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_out);
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_state_score_likelihood(msb_state *st, size_t feature, size_t gid, float *out) {
+  REQUIRE(st && out, "NULL argument");
+  REQUIRE(feature < st->D, "bad feature index");
+  int slot;
+  MSB_TRY(slot_of(st, gid, &slot));
+  std::vector<double> h;
+  MSB_TRY(score_data_matrix(st, h));
+  for (size_t c = 0; c < st->h_col2slot.size(); c++)
+    if (st->h_col2slot[c] == slot) { *out = (float)h[c * st->D + feature]; return MSB_OK; }
+  return fail(MSB_ERR_INVALID, "invalid gid");
+}
+
+// per_feature[d] = sum over groups of score_data (entity_state.hpp:78-86), total = sum over features
+extern "C" MSB_API int msb_state_score_likelihood_all(msb_state *st, float *per_feature, size_t nfeatures, float *total) {
+  REQUIRE(st, "NULL argument");
+  REQUIRE(!per_feature || nfeatures == st->D, "wrong length");
+  std::vector<double> h;
+  MSB_TRY(score_data_matrix(st, h));
+  double tot = 0.0;
+  for (size_t d = 0; d < st->D; d++) {
+    float s = 0.f;  // the reference accumulates the per-group floats in a float (entity_state.hpp:81-84)
+    for (size_t c = 0; c < st->h_col2slot.size(); c++) s += (float)h[c * st->D + d];
+    if (per_feature) per_feature[d] = s;
+    tot += s;
+  }
+  if (total) *total = (float)tot;
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_state_score_assignment(msb_state *st, float *out) {
+  REQUIRE(st && out, "NULL argument");
+  REQUIRE(st->dv && st->n > 0, "no entities");
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  MSB_TRY(prepare_columns(st));
+  double *d_out = nullptr;
+  CU_TRY(cudaMalloc(&d_out, sizeof(double) * 2));
+  LAUNCH(ctx, score_assignment_kernel, 1, 256, 0, st->d_ss, st->d_col2slot, (int)st->h_col2slot.size(), st->d_assign, st->alpha, d_out);
+  double h[2] = {0, 0};
+  CU_TRY(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_out);
+  if ((size_t)h[1] != st->n) return fail(MSB_ERR_STATE, "not assigned");  // group_manager.hpp:255,260
+  *out = (float)h[0];
+  return MSB_OK;
 }
 
 // ---- sampler ---------------------------------------------------------------------

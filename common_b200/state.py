@@ -158,6 +158,28 @@ class state(object):
                                                      k, C.byref(n)))
         return [int(gids[i]) for i in range(n.value)], scores[:n.value]
 
+    # ---- marginal likelihoods (entity_state.hpp:74-86) ------------------------------------
+    def score_assignment(self):
+        v = C.c_float()
+        _lib.check(_lib.load().msb_state_score_assignment(self._h, C.byref(v)))
+        return v.value
+
+    def score_likelihood(self, component=None, gid=None, rng=None):
+        """score_likelihood(component, gid): one group's score_data; score_likelihood(component): summed over
+        the groups; score_likelihood(): summed over components too"""
+        if component is not None and gid is not None:
+            v = C.c_float()
+            _lib.check(_lib.load().msb_state_score_likelihood(self._h, component, gid, C.byref(v)))
+            return v.value
+        per = (C.c_float * len(self._models))()
+        tot = C.c_float()
+        _lib.check(_lib.load().msb_state_score_likelihood_all(self._h, per, len(self._models), C.byref(tot)))
+        return tot.value if component is None else float(per[component])
+
+    def score_joint(self):
+        """score_assignment() + score_likelihood() (the quantity the reference's testutil compares)"""
+        return self.score_assignment() + self.score_likelihood()
+
     # ---- batched ---------------------------------------------------------------------
     def score_rows(self, row_lo=0, row_hi=None, out=None):
         """(gids, scores[nrows, K]): log(pseudocount) + sum_d score_value for every row"""

@@ -20,6 +20,8 @@
  *   msb_state_add_value / remove_value / score_value
  *                         common/entity_state.hpp:57-72 (which loop over
  *                         models/base.hpp:25-27 group::add_value/remove_value/score_value)
+ *   msb_state_score_likelihood / score_assignment
+ *                         common/entity_state.hpp:74-86, common/group_manager.hpp:250-272
  *   msb_state_score_rows  the same K x D loop of base.hpp:27 for a whole row range
  *   msb_sample_discrete_log
  *                         common/util.hpp:125-156 (scores_to_probs + sample_discrete)
@@ -174,6 +176,15 @@ MSB_API int msb_state_score_value(msb_state *st, size_t eid, size_t *gids, float
  * on_device != 0: scores is a device pointer. */
 MSB_API int msb_state_score_rows(msb_state *st, size_t row_lo, size_t row_hi, float *scores, size_t ld,
                          int on_device, size_t *gids, size_t cap, size_t *ncols);
+
+/* entity_state.hpp:74-86: score_likelihood(component, gid) = group::score_data (models/base.hpp:28), the log
+ * marginal likelihood of the group's data under the component's hypers; and its sum over the groups per
+ * component (per_feature[nfeatures], may be NULL) and over everything (total, may be NULL).  fp64 closed forms
+ * on the device from the resident suffstats. */
+MSB_API int msb_state_score_likelihood(msb_state *st, size_t feature, size_t gid, float *out);
+MSB_API int msb_state_score_likelihood_all(msb_state *st, float *per_feature, size_t nfeatures, float *total);
+/* group_manager.hpp:250-272: log CRP probability of the current partition; every entity must be assigned */
+MSB_API int msb_state_score_assignment(msb_state *st, float *out);
 
 /* util.hpp:125-156 on the device, one uniform per row; host pointers */
 MSB_API int msb_sample_discrete_log(msb_ctx *ctx, const float *scores, size_t nrows, size_t k, size_t ld,

@@ -175,6 +175,103 @@ static double niw_score64(unsigned d, const double *hp, const double *ss, const 
   return s;
 }
 
+/* ---- marginal likelihood of a group's data: group::score_data (models/base.hpp:28, forwarded at
+ * models/distributions.hpp:287-291).  Closed forms of the conjugate families; by the chain rule each equals
+ * the sum of the sequential predictives score_value(x_i | x_<i), which is how tests/test_oracle.py pins them
+ * against the (golden-pinned) predictive. ------------------------------------------------------------- */
+static double lbeta(double a, double b) { return lgamma(a) + lgamma(b) - lgamma(a + b); }
+static double lmvgamma(double a, unsigned d) { /* log of the multivariate gamma function Gamma_d(a) */
+  double s = 0.25 * d * (d - 1.0) * log(M_PI);
+  for (unsigned j = 0; j < d; j++) s += lgamma(a - 0.5 * j);
+  return s;
+}
+static double logdet_spd(const double *A, unsigned d) { /* log |A| by Cholesky; NAN if not positive definite */
+  double *L = (double *)malloc(sizeof(double) * d * d);
+  memcpy(L, A, sizeof(double) * d * d);
+  double s = NAN;
+  if (chol_lower(L, d) == 0) {
+    s = 0.0;
+    for (unsigned i = 0; i < d; i++) s += 2.0 * log(L[i * d + i]);
+  }
+  free(L);
+  return s;
+}
+double orc_score_data(const orc_model *m, const double *hp, const double *ss) {
+  switch (m->family) {
+    case ORC_BB: return lbeta(hp[0] + ss[0], hp[1] + ss[1]) - lbeta(hp[0], hp[1]);
+    case ORC_DD: {
+      double asum = 0.0, s = 0.0;
+      for (unsigned i = 0; i < m->dim; i++) { asum += hp[i]; s += lgamma(hp[i] + ss[1 + i]) - lgamma(hp[i]); }
+      return s + lgamma(asum) - lgamma(asum + ss[0]);
+    }
+    case ORC_GP: { /* prior Gamma(alpha, rate inv_beta); ss = count, sum, log_prod = sum log x! */
+      double a = hp[0] + ss[1], b = hp[1] + ss[0];
+      return lgamma(a) - lgamma(hp[0]) + hp[0] * log(hp[1]) - a * log(b) - ss[2];
+    }
+    case ORC_NICH: {
+      double mu, kappa, sigmasq, nu, n = ss[0];
+      nich_post64(hp, ss, &mu, &kappa, &sigmasq, &nu);
+      return lgamma(0.5 * nu) - lgamma(0.5 * hp[3]) + 0.5 * log(hp[1] / kappa) + 0.5 * hp[3] * log(hp[3] * hp[2]) -
+             0.5 * nu * log(nu * sigmasq) - 0.5 * n * log(M_PI);
+    }
+    case ORC_NIW: {
+      unsigned d = m->dim;
+      const double *mu0 = hp, kappa0 = hp[d], *psi0 = hp + d + 1, nu0 = hp[d + 1 + (size_t)d * d];
+      double n = ss[0];
+      const double *sx = ss + 1, *sxx = ss + 1 + d;
+      double kn = kappa0 + n, nun = nu0 + n;
+      double *psin = (double *)malloc(sizeof(double) * d * d);
+      for (unsigned i = 0; i < d; i++)
+        for (unsigned j = 0; j < d; j++) {
+          double mi = (kappa0 * mu0[i] + sx[i]) / kn, mj = (kappa0 * mu0[j] + sx[j]) / kn;
+          psin[i * d + j] = psi0[i * d + j] + sxx[i * d + j] + kappa0 * mu0[i] * mu0[j] - kn * mi * mj;
+        }
+      double r = -0.5 * n * d * log(M_PI) + lmvgamma(0.5 * nun, d) - lmvgamma(0.5 * nu0, d) +
+                 0.5 * nu0 * logdet_spd(psi0, d) - 0.5 * nun * logdet_spd(psin, d) + 0.5 * d * log(kappa0 / kn);
+      free(psin);
+      return r;
+    }
+    default: return NAN;
+  }
+}
+
+/* group_manager<T>::score_assignment, include/microscopes/common/group_manager.hpp:250-272, statement by
+ * statement in float (libm logf where upstream has fast_log): the CRP probability of the partition in entity
+ * order.  assign[i] >= 0 for all i. */
+float orc_score_assignment(const int64_t *assign, size_t n, float alpha) {
+  if (n == 0) return 0.f;
+  int64_t maxg = 0;
+  for (size_t i = 0; i < n; i++) if (assign[i] > maxg) maxg = assign[i];
+  size_t *counts = (size_t *)calloc((size_t)maxg + 1, sizeof(size_t));
+  counts[assign[0]] = 1;
+  float sum = 0.f;
+  for (size_t i = 1; i < n; i++) {
+    const int64_t gid = assign[i];
+    const int found = counts[gid] != 0;
+    const float numer = !found ? alpha : (float)counts[gid];
+    const float denom = (float)i + alpha;
+    sum += logf(numer / denom);
+    counts[gid]++;
+  }
+  free(counts);
+  return sum;
+}
+/* the same quantity in closed form, double: depends on the partition only through the group sizes and on
+ * which group holds entity 0 -- sum_g [log alpha (unless g holds entity 0) + lgamma(n_g)] - sum_{i=1}^{n-1} log(i + alpha) */
+double orc_score_assignment64(const int64_t *assign, size_t n, double alpha) {
+  if (n == 0) return 0.0;
+  int64_t maxg = 0;
+  for (size_t i = 0; i < n; i++) if (assign[i] > maxg) maxg = assign[i];
+  size_t *counts = (size_t *)calloc((size_t)maxg + 1, sizeof(size_t));
+  for (size_t i = 0; i < n; i++) counts[assign[i]]++;
+  double s = 0.0;
+  for (int64_t g = 0; g <= maxg; g++)
+    if (counts[g]) s += (g == assign[0] ? 0.0 : log(alpha)) + lgamma((double)counts[g]);
+  s -= lgamma((double)n + alpha) - lgamma(1.0 + alpha);
+  free(counts);
+  return s;
+}
+
 /* ---- fp32 restatements: float arithmetic, libm logf/lgammaf.  Upstream uses
  * table-driven fast_log / fast_lgamma whose error is not reproducible here. -- */
 static float bb_score32(const double *hp, const double *ss, double x) {

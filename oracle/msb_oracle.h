@@ -52,6 +52,12 @@ double orc_score_value(const orc_model *m, const double *hp, const double *ss, c
 void orc_add_value(const orc_model *m, const double *hp, double *ss, const double *x, int prec);
 void orc_remove_value(const orc_model *m, const double *hp, double *ss, const double *x, int prec);
 
+/* group::score_data (models/base.hpp:28): log marginal likelihood of the data summarised by ss, fp64 closed form */
+double orc_score_data(const orc_model *m, const double *hp, const double *ss);
+/* group_manager::score_assignment (group_manager.hpp:250-272): float loop in entity order / fp64 closed form */
+float orc_score_assignment(const int64_t *assign, size_t n, float alpha);
+double orc_score_assignment64(const int64_t *assign, size_t n, double alpha);
+
 /* batched K x D loop (entity_state.hpp:57-72 semantics, frozen suffstats).
  * hp: concatenation over features; ss: K blocks of the concatenation over features.
  * out[(i-row_lo)*K + k] = logprior[k] + sum over unmasked features. */

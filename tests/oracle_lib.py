@@ -89,6 +89,23 @@ class Oracle(object):
         x = np.ascontiguousarray(np.atleast_1d(x), np.float64)
         self.lib.orc_remove_value(C.byref(m), hp.ctypes.data, ss.ctypes.data, x.ctypes.data, prec)
 
+    # -- marginal likelihoods ----------------------------------------------------
+    def score_data(self, m, hp, ss):
+        hp = np.ascontiguousarray(hp, np.float64); ss = np.ascontiguousarray(ss, np.float64)
+        self.lib.orc_score_data.restype = _D
+        self.lib.orc_score_data.argtypes = [C.POINTER(OrcModel), _P, _P]
+        return self.lib.orc_score_data(C.byref(m), hp.ctypes.data, ss.ctypes.data)
+
+    def score_assignment(self, assign, alpha, prec=32):
+        a = np.ascontiguousarray(assign, np.int64)
+        if prec == 32:
+            self.lib.orc_score_assignment.restype = C.c_float
+            self.lib.orc_score_assignment.argtypes = [_P, _SZ, C.c_float]
+            return self.lib.orc_score_assignment(a.ctypes.data, a.size, float(alpha))
+        self.lib.orc_score_assignment64.restype = _D
+        self.lib.orc_score_assignment64.argtypes = [_P, _SZ, _D]
+        return self.lib.orc_score_assignment64(a.ctypes.data, a.size, float(alpha))
+
     # -- batched ---------------------------------------------------------------
     def _pack(self, descs, view):
         models = (OrcModel * len(descs))(*[self.model(d) for d in descs])

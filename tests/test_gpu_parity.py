@@ -484,3 +484,40 @@ def test_uploads_on_the_copy_stream_are_ordered_with_the_kernels(ctx, oracle):
         row, _ = dev.get_row_bytes(n - 1)     # reads the NEW records (waits for the upload)
         assert np.array_equal(row, nxt[n - 1])
     st.close()
+
+
+def test_score_likelihood_and_score_assignment_match_oracle(ctx, oracle):
+    # entity_state.hpp:74-86 / group_manager.hpp:250-272 through the ABI, against the fp64 closed forms
+    descs = [cb.bb, cb.gp, cb.nich, cb.dd(16), cb.niw(3), cb.dd(256)]
+    n, k = 1500, 7
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=51, mask_frac=0.03, extra_empty=1)
+    for it in range(2):
+        total, off, hoff = 0.0, 0, 0
+        for d, desc in enumerate(descs):
+            m = oracle.model(desc)
+            w, hw = oracle.ss_size(m), oracle.hp_size(m)
+            per = 0.0
+            for c, g in enumerate(gids):
+                want = oracle.score_data(m, hp[hoff:hoff + hw], ss[c, off:off + w])
+                got = st.score_likelihood(d, g)
+                assert abs(got - want) <= 2e-6 * max(1.0, abs(want)), (desc().name(), c, got, want)
+                per += want
+            assert abs(st.score_likelihood(d) - per) <= 1e-5 * max(1.0, abs(per))
+            total += per
+            off += w; hoff += hw
+        assert abs(st.score_likelihood() - total) <= 1e-5 * max(1.0, abs(total))
+        assign = np.searchsorted(gids, st.assignments())
+        want_a = oracle.score_assignment(assign, 1.0, prec=64)
+        got_a = st.score_assignment()
+        assert abs(got_a - want_a) <= 1e-6 * max(1.0, abs(want_a))
+        assert abs(got_a - oracle.score_assignment(assign, 1.0, prec=32)) <= 2e-4 * max(1.0, abs(want_a))  # the float loop
+        assert abs(st.score_joint() - (want_a + total)) <= 1e-5 * max(1.0, abs(want_a + total))
+        # move the entities with one sweep and check again against the updated suffstats
+        old = assign.astype(np.int32)
+        st.sweep(seed=3, sweep=it)
+        new = np.searchsorted(gids, st.assignments()).astype(np.int32)
+        oracle.update_rows(descs, hp, ss, counts, view, old, new)
+    st.remove_value(0)
+    with pytest.raises(cb.MsbError):
+        st.score_assignment()       # "not assigned", group_manager.hpp:255,260
+    st.close()

@@ -182,3 +182,51 @@ def test_batched_scores_match_single_calls(oracle):
             tot += oracle.score_value(m, hp[hoff:hoff + nh], ss[k, soff:soff + ns], [float(arr.data["f%d" % d][i])])
         hoff += nh; soff += ns
     assert abs(S[i, k] - tot) < 1e-12
+
+
+# ---- marginal likelihoods: group::score_data (base.hpp:28), group_manager::score_assignment (:250-272) ----
+def _marginal_cases():
+    with open(os.path.join(GOLD, "score_data.json")) as f:
+        return json.load(f)
+
+
+def test_golden_score_data(oracle):
+    cases = _marginal_cases()["cases"]
+    assert len(cases) >= 18
+    for c in cases:
+        m = ol.OrcModel(FAM[c["family"]], c["dim"])
+        got = oracle.score_data(m, c["hp"], c["ss"])
+        tol = 1e-11 * max(1.0, abs(c["expect"])) * (50.0 if c["family"] == "niw" else 1.0)
+        assert abs(got - c["expect"]) <= tol, (c["family"], c["source"], got, c["expect"])
+        if "ref_vendor" in c:  # the reference's own in-tree inverse-Wishart partition function
+            assert abs(got - c["ref_vendor"]) <= 1e-9 * max(1.0, abs(c["ref_vendor"]))
+
+
+@pytest.mark.parametrize("desc", [cb.bb, cb.gp, cb.nich, cb.dd(7), cb.niw(3)])
+def test_score_data_is_the_chain_of_predictives(oracle, desc):
+    # log p(x_1..x_n) = sum_i log p(x_i | x_<i): pins score_data on the (golden-pinned) score_value / add_value
+    rng = np.random.default_rng(11)
+    m = oracle.model(desc)
+    hp = oracle.flat_hp(desc)
+    ss = np.zeros(oracle.ss_size(m))
+    name = desc().name()
+    chain = 0.0
+    for _ in range(40):
+        if name == "bb": x = float(rng.integers(0, 2))
+        elif name == "dd": x = float(rng.integers(0, 7))
+        elif name == "gp": x = float(rng.poisson(5.0))
+        elif name == "nich": x = float(rng.normal(0.7, 1.1))
+        else: x = rng.normal(0.2, 1.0, size=3)
+        chain += oracle.score_value(m, hp, ss, x, 64)
+        oracle.add_value(m, hp, ss, x, 64)
+    got = oracle.score_data(m, hp, ss)
+    assert abs(got - chain) <= 1e-10 * max(1.0, abs(chain)), (name, got, chain)
+    assert oracle.score_data(m, hp, np.zeros_like(ss)) == pytest.approx(0.0, abs=1e-12)  # an empty group
+
+
+def test_golden_score_assignment(oracle):
+    for c in _marginal_cases()["crp"]:
+        f32 = oracle.score_assignment(c["assign"], c["alpha"], prec=32)   # the reference's float loop
+        f64 = oracle.score_assignment(c["assign"], c["alpha"], prec=64)   # closed form
+        assert abs(f64 - c["expect"]) <= 1e-11 * max(1.0, abs(c["expect"]))
+        assert abs(f32 - c["expect"]) <= 2e-6 * len(c["assign"]) ** 0.5 * max(1.0, abs(c["expect"]))
