@@ -569,13 +569,21 @@ __device__ __forceinline__ float div_markstein(float p, float acc, float y) {
   return __fmaf_rn(r, y, q0);
 }
 
+// Sparsity: exp(s - max) underflows to exactly 0 below -104, which in a mixture is the case for most groups of
+// most rows.  A batch of eight groups whose p is exactly 0 in every lane of the warp leaves every live dart
+// unchanged (dart - 0), so it is skipped as a whole (dead8(k0), warp-uniform); the same test lets the exp pass
+// skip the polynomial (exp_is_zero).  Results are bit-identical, only the work drops.
+__device__ __forceinline__ bool exp_is_zero(float x) { return x < -104.0f; }  // false for NaN, like msb_expf
+
 // all 32 lanes of the warp must call this (lanes without a row pass found = true)
-template <typename F>
-__device__ __forceinline__ void dart_walk(int K, float acc, float dart, bool found, int &pick, F p_of) {
+template <typename F, typename G>
+__device__ __forceinline__ void dart_walk(int K, float acc, float dart, bool found, int &pick, F p_of, G dead8) {
   const float y = __frcp_rn(acc);
   const bool odd = !(acc >= 1.0f && acc <= 16777216.0f);
   pick = K - 1;
   for (int k0 = 0; k0 < K; k0 += 8) {
+    // every p of the batch is +0 in every lane: q = +0 and dart - 0 = dart, unless a lane sits exactly on dart <= 0
+    if (dead8(k0) && __all_sync(0xffffffffu, found || dart > 0.f)) continue;
     float p[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) p[j] = k0 + j < K ? p_of(k0 + j) : 0.f;
@@ -613,14 +621,24 @@ __global__ void sample_kernel(const float *__restrict__ scores, size_t ld, int K
   const float *s = scores + (valid ? i : 0) * ld;
   float m = s[0];
   for (int k = 1; k < K; k++) m = fmaxf(m, s[k]);
+  auto dead8 = [&](int k0) {
+    bool live = false;
+#pragma unroll
+    for (int j = 0; j < 8; j++) live |= k0 + j < K && !exp_is_zero(__fsub_rn(s[k0 + j], m));
+    return !__any_sync(0xffffffffu, live);
+  };
   double acc_d = 0.0;
-#pragma unroll 4
-  for (int k = 0; k < K; k++) acc_d = __dadd_rn(acc_d, (double)msb_expf(__fsub_rn(s[k], m)));
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    if (dead8(k0)) continue;  // acc + 0 = acc
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (k0 + j < K) acc_d = __dadd_rn(acc_d, (double)msb_expf(__fsub_rn(s[k0 + j], m)));
+  }
   const float acc = __double2float_rn(acc_d);
   float dart = 0.f;
   if (valid) dart = uniforms ? uniforms[i] : philox_u01(seed, row_id0 + i, sweep);
   int pick;
-  dart_walk(K, acc, dart, !valid, pick, [&](int k) { return msb_expf(__fsub_rn(s[k], m)); });
+  dart_walk(K, acc, dart, !valid, pick, [&](int k) { return msb_expf(__fsub_rn(s[k], m)); }, dead8);
   if (!valid) return;
   if (out_col) out_col[i] = pick;
   if (out_slot) out_slot[i] = col2slot ? col2slot[pick] : pick;
@@ -644,14 +662,24 @@ __global__ void sample_blocked_kernel(const float *__restrict__ scores, size_t l
   }
   for (; k < K; k++) m0 = fmaxf(m0, s[(size_t)k * 32]);
   const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  auto dead8 = [&](int k0) {
+    bool live = false;
+#pragma unroll
+    for (int j = 0; j < 8; j++) live |= k0 + j < K && !exp_is_zero(__fsub_rn(s[(size_t)(k0 + j) * 32], m));
+    return !__any_sync(0xffffffffu, live);
+  };
   double acc_d = 0.0;
-#pragma unroll 8
-  for (k = 0; k < K; k++) acc_d = __dadd_rn(acc_d, (double)msb_expf(__fsub_rn(s[(size_t)k * 32], m)));
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    if (dead8(k0)) continue;  // acc + 0 = acc
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (k0 + j < K) acc_d = __dadd_rn(acc_d, (double)msb_expf(__fsub_rn(s[(size_t)(k0 + j) * 32], m)));
+  }
   const float acc = __double2float_rn(acc_d);
   float dart = 0.f;
   if (valid) dart = uniforms ? uniforms[i] : philox_u01(seed, row_id0 + i, sweep);
   int pick;
-  dart_walk(K, acc, dart, !valid, pick, [&](int kk) { return msb_expf(__fsub_rn(s[(size_t)kk * 32], m)); });
+  dart_walk(K, acc, dart, !valid, pick, [&](int kk) { return msb_expf(__fsub_rn(s[(size_t)kk * 32], m)); }, dead8);
   if (!valid) return;
   if (out_col) out_col[i] = pick;
   if (out_slot) out_slot[i] = col2slot ? col2slot[pick] : pick;

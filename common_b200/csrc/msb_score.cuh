@@ -120,28 +120,61 @@ sample_tile_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int
     const bool valid = i >= 0 && (size_t)i < nrows;
     float *s = tile + lane;
     // pass 1: max (exact and order-independent: four partial maxima for instruction-level parallelism)
-    float m0 = s[0], m1 = m0, m2 = m0, m3 = m0;
+    float m0 = s[0], m1 = m0, m2 = m0, m3 = m0, lo0 = m0, lo1 = m0;
     int k = 1;
     for (; k + 3 < K; k += 4) {
-      m0 = fmaxf(m0, s[k * 32]); m1 = fmaxf(m1, s[(k + 1) * 32]);
-      m2 = fmaxf(m2, s[(k + 2) * 32]); m3 = fmaxf(m3, s[(k + 3) * 32]);
+      const float a0 = s[k * 32], a1 = s[(k + 1) * 32], a2 = s[(k + 2) * 32], a3 = s[(k + 3) * 32];
+      m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); m2 = fmaxf(m2, a2); m3 = fmaxf(m3, a3);
+      lo0 = fminf(lo0, fminf(a0, a1)); lo1 = fminf(lo1, fminf(a2, a3));
     }
-    for (; k < K; k++) m0 = fmaxf(m0, s[k * 32]);
+    for (; k < K; k++) { m0 = fmaxf(m0, s[k * 32]); lo0 = fminf(lo0, s[k * 32]); }
     const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    // A row whose smallest score is still within exp's range keeps every batch of eight groups alive: the
+    // batch-skipping passes below would only add their votes.  Then take the dense passes (same results).
+    const bool dense = __any_sync(0xffffffffu, valid && !exp_is_zero(__fsub_rn(fminf(lo0, lo1), m)));
     // pass 2: p = exp(s - m) (independent per k, kept in the tile) and the in-order double sum (the only chain)
+    // Batches of eight groups whose exp underflows to 0 in every lane are only recorded (bit kb of `live`):
+    // nothing to add to the sum, nothing to store, and the walk below skips them too (K <= 512 here).
     double acc_d = 0.0;
+    uint64_t live = 0;
+    if (dense) {
+      live = ~0ull;
 #pragma unroll 8
-    for (k = 0; k < K; k++) {
-      const float p = msb_expf(__fsub_rn(s[k * 32], m));
-      s[k * 32] = p;
-      acc_d = __dadd_rn(acc_d, (double)p);
+      for (k = 0; k < K; k++) {
+        const float p = msb_expf(__fsub_rn(s[k * 32], m));
+        s[k * 32] = p;
+        acc_d = __dadd_rn(acc_d, (double)p);
+      }
+    } else
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      float x[8];
+      bool any = false;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        x[j] = k0 + j < K ? __fsub_rn(s[(k0 + j) * 32], m) : -CUDART_INF_F;
+        any |= !exp_is_zero(x[j]);
+      }
+      if (!__any_sync(0xffffffffu, any)) continue;
+      live |= 1ull << (k0 >> 3);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (k0 + j < K) {
+          const float p = msb_expf(x[j]);
+          s[(k0 + j) * 32] = p;
+          acc_d = __dadd_rn(acc_d, (double)p);
+        }
+      }
     }
     const float acc = __double2float_rn(acc_d);
     float dart = 0.f;
     if (valid) dart = uniforms ? uniforms[i] : philox_u01(seed, row_id0 + (uint64_t)i, sweep);
     // pass 3: the dart walk (msb_kernels.cuh), quotients from the tile
     int pick;
-    dart_walk(K, acc, dart, !valid, pick, [&](int kk) { return s[kk * 32]; });
+    if (dense)
+      dart_walk(K, acc, dart, !valid, pick, [&](int kk) { return s[kk * 32]; }, [](int) { return false; });
+    else
+      dart_walk(K, acc, dart, !valid, pick, [&](int kk) { return ((live >> (kk >> 3)) & 1ull) ? s[kk * 32] : 0.f; },
+                [&](int k0) { return !((live >> (k0 >> 3)) & 1ull); });
     if (valid) {
       if (out_col) out_col[i] = pick;
       if (out_slot) out_slot[i] = col2slot ? col2slot[pick] : pick;

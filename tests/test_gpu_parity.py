@@ -521,3 +521,32 @@ def test_score_likelihood_and_score_assignment_match_oracle(ctx, oracle):
     with pytest.raises(cb.MsbError):
         st.score_assignment()       # "not assigned", group_manager.hpp:255,260
     st.close()
+
+
+@pytest.mark.parametrize("k", [40, 300, 700])
+def test_samplers_with_zero_uniforms_and_dead_batches(ctx, oracle, k, monkeypatch):
+    # well-separated groups: exp underflows to exactly 0 for most (row, group) pairs, so the samplers skip whole
+    # batches of eight groups; a uniform of exactly 0 must still pick column 0 (dart - 0 <= 0 at the first step)
+    descs = [cb.nich] * 56 + [cb.dd(5)] * 8
+    n = 4000
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=61)
+    u = np.array([oracle.philox_u01(5, i, 0) for i in range(n)], np.float32)
+    u[::7] = 0.0
+    u[3::11] = np.float32(1.0 - 2.0 ** -24)
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("MSB_NO_TILE_SAMPLER", env)
+        st.sweep(seed=5, sweep=0, uniforms=u)
+        S = st.read_last_scores()
+        dead = np.mean(S - S.max(1, keepdims=True) < -104.0)
+        assert dead > 0.3                      # the case the test is about
+        got = np.searchsorted(gids, st.assignments()).astype(np.int32)
+        want = oracle.sample_rows(S, u)
+        assert np.array_equal(got, want)
+        assert np.all(got[u == 0.0] == 0)
+    st.close()
+    # crafted scores through the row-major kernel: a dead leading batch, then live values
+    s = np.full((64, 24), -1000.0, np.float32)
+    s[:, 9] = 0.0; s[:, 17] = -1.0; s[:, 23] = -200.0
+    uu = np.linspace(0, 0.999, 64).astype(np.float32)
+    assert np.array_equal(cb.sample_discrete_log(ctx, s, uu), oracle.sample_rows(s, uu))
