@@ -725,44 +725,49 @@ __global__ void philox_fill_kernel(uint64_t seed, uint64_t sweep, uint64_t row0,
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
 
+constexpr int UPDATE_SLAB = 16;
 __global__ void update_kernel(const FeatDev *__restrict__ feats, int nfeat, const int32_t *__restrict__ old_slot,
                               const int32_t *__restrict__ new_slot, size_t row_lo, size_t row_hi,
                               double *__restrict__ delta) {
+  // thread = row; blockIdx.y = a slab of UPDATE_SLAB features: the two assignment loads are shared by the slab,
+  // a row that did not move costs nothing more, and for a fixed feature the column loads of a warp are coalesced
   const size_t row = row_lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int d = blockIdx.y;
   if (row >= row_hi) return;
   const int a = old_slot ? old_slot[row] : -1;
   const int b = new_slot ? new_slot[row - row_lo] : -1;
   if (a == b) return;
-  const FeatDev f = feats[d];
-  double *blk = delta + f.ss_off;
-  if (f.kind == KIND_TABLE) {
-    uint32_t x;
-    if (f.coltype == COL_U8) x = ((const uint8_t *)f.col)[row];
-    else if (f.coltype == COL_U16) x = ((const uint16_t *)f.col)[row];
-    else x = ((const uint32_t *)f.col)[row];
-    if (x >= f.ncat) return;
-    if (f.family == FAM_BB) {  // ss = [heads, tails]
-      const int j = x ? 0 : 1;
-      if (a >= 0) atomic_add_f64(blk + (size_t)a * 2 + j, -1.0);
-      if (b >= 0) atomic_add_f64(blk + (size_t)b * 2 + j, 1.0);
-    } else {  // ss = [count_sum, counts[dim]]; count_sum is re-derived from counts (dd_count_sum_kernel):
-              // a RED per cell on only K addresses per feature would serialise in L2
-      if (a >= 0) atomic_add_f64(blk + (size_t)a * f.ss_w + 1 + x, -1.0);
-      if (b >= 0) atomic_add_f64(blk + (size_t)b * f.ss_w + 1 + x, 1.0);
+  const int d_hi = min(nfeat, (int)(blockIdx.y + 1) * UPDATE_SLAB);
+  for (int d = blockIdx.y * UPDATE_SLAB; d < d_hi; d++) {
+    const FeatDev &f = feats[d];
+    double *blk = delta + f.ss_off;
+    if (f.kind == KIND_TABLE) {
+      uint32_t x;
+      if (f.coltype == COL_U8) x = ((const uint8_t *)f.col)[row];
+      else if (f.coltype == COL_U16) x = ((const uint16_t *)f.col)[row];
+      else x = ((const uint32_t *)f.col)[row];
+      if (x >= f.ncat) continue;
+      if (f.family == FAM_BB) {  // ss = [heads, tails]
+        const int j = x ? 0 : 1;
+        if (a >= 0) atomic_add_f64(blk + (size_t)a * 2 + j, -1.0);
+        if (b >= 0) atomic_add_f64(blk + (size_t)b * 2 + j, 1.0);
+      } else {  // ss = [count_sum, counts[dim]]; count_sum is re-derived from counts (dd_count_sum_kernel):
+                // a RED per cell on only K addresses per feature would serialise in L2
+        if (a >= 0) atomic_add_f64(blk + (size_t)a * f.ss_w + 1 + x, -1.0);
+        if (b >= 0) atomic_add_f64(blk + (size_t)b * f.ss_w + 1 + x, 1.0);
+      }
+    } else if (f.kind == KIND_GP) {  // ss = [count, sum, log_prod]
+      const uint32_t x = ((const uint32_t *)f.col)[row];
+      if (x == GP_SENTINEL) continue;
+      const double xd = (double)x, lf = lgamma(xd + 1.0);
+      if (a >= 0) { double *p = blk + (size_t)a * 3; atomic_add_f64(p, -1.0); atomic_add_f64(p + 1, -xd); atomic_add_f64(p + 2, -lf); }
+      if (b >= 0) { double *p = blk + (size_t)b * 3; atomic_add_f64(p, 1.0); atomic_add_f64(p + 1, xd); atomic_add_f64(p + 2, lf); }
+    } else if (f.kind == KIND_NICH) {  // ss = [count, sum x, sum x^2]
+      const float xf = ((const float *)f.col)[row];
+      if (xf != xf) continue;
+      const double xd = (double)xf, x2 = xd * xd;
+      if (a >= 0) { double *p = blk + (size_t)a * 3; atomic_add_f64(p, -1.0); atomic_add_f64(p + 1, -xd); atomic_add_f64(p + 2, -x2); }
+      if (b >= 0) { double *p = blk + (size_t)b * 3; atomic_add_f64(p, 1.0); atomic_add_f64(p + 1, xd); atomic_add_f64(p + 2, x2); }
     }
-  } else if (f.kind == KIND_GP) {  // ss = [count, sum, log_prod]
-    const uint32_t x = ((const uint32_t *)f.col)[row];
-    if (x == GP_SENTINEL) return;
-    const double xd = (double)x, lf = lgamma(xd + 1.0);
-    if (a >= 0) { double *p = blk + (size_t)a * 3; atomic_add_f64(p, -1.0); atomic_add_f64(p + 1, -xd); atomic_add_f64(p + 2, -lf); }
-    if (b >= 0) { double *p = blk + (size_t)b * 3; atomic_add_f64(p, 1.0); atomic_add_f64(p + 1, xd); atomic_add_f64(p + 2, lf); }
-  } else if (f.kind == KIND_NICH) {  // ss = [count, sum x, sum x^2]
-    const float xf = ((const float *)f.col)[row];
-    if (xf != xf) return;
-    const double xd = (double)xf, x2 = xd * xd;
-    if (a >= 0) { double *p = blk + (size_t)a * 3; atomic_add_f64(p, -1.0); atomic_add_f64(p + 1, -xd); atomic_add_f64(p + 2, -x2); }
-    if (b >= 0) { double *p = blk + (size_t)b * 3; atomic_add_f64(p, 1.0); atomic_add_f64(p + 1, xd); atomic_add_f64(p + 2, x2); }
   }
 }
 

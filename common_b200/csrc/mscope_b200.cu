@@ -1090,7 +1090,7 @@ static int launch_update(msb_state *st, size_t row_lo, size_t row_hi) {  // old 
   msb_ctx *ctx = st->ctx;
   const size_t nrows = row_hi - row_lo;
   if (st->has_scalar) {
-    dim3 grid(cdiv(nrows, 256), (unsigned)st->D);
+    dim3 grid(cdiv(nrows, 256), cdiv(st->D, UPDATE_SLAB));
     LAUNCH(ctx, update_kernel, grid, 256, 0, st->d_feats, (int)st->D, st->d_assign, st->d_newslot, row_lo, row_hi, st->d_delta);
   }
   for (size_t d = 0; d < st->D; d++) {
