@@ -103,7 +103,7 @@ __global__ void niw_pack_b_kernel(const float *__restrict__ W, int ncols, float 
 __global__ void __launch_bounds__(niwtc::THREADS, 1)
 niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const float *__restrict__ bias,
               const float *__restrict__ coef, int ncols, float *__restrict__ scores, size_t ld, size_t row_lo,
-              size_t row_hi, int num_gb_lanes, const float *__restrict__ base) {
+              size_t row_hi, int num_gb_lanes, const float *__restrict__ base, int blocked) {
   // base != nullptr: this kernel is the only writer of the score matrix: scores = base[k] + term (no read);
   // base == nullptr: scores += term (the scalar-feature kernel has already written them)
   using namespace niwtc;
@@ -256,8 +256,15 @@ niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const 
       // the accumulator so that the global-load latency hides behind the MMAs
       const size_t row = row_lo + (size_t)rt * TM + ew * 32 + lane;
       float4 *dst = reinterpret_cast<float4 *>(scores + (row - row_lo) * ld + (size_t)gb * GB);
+      // blocked layout (the sweep's, msb_score.cuh): this warp's 32 rows are one 32-row block, lane = row, so the
+      // GB values of a thread go to GB different 128-byte lines, each written by the whole warp at once
+      float *dstb = scores + (((size_t)rt * (TM / 32) + ew) * ld + (size_t)gb * GB) * 32 + lane;
       float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < row_hi) old = base ? __ldg(reinterpret_cast<const float4 *>(base + (size_t)gb * GB)) : *dst;
+      if (row < row_hi) {
+        if (base) old = __ldg(reinterpret_cast<const float4 *>(base + (size_t)gb * GB));
+        else if (blocked) old = make_float4(dstb[0], dstb[32], dstb[64], dstb[96]);
+        else old = *dst;
+      }
       mbar_wait(smem_u32(&bars[6 + acc]), (uint32_t)((t >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float q[GB];
@@ -286,7 +293,12 @@ niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const 
             o[g] += c0 + c1 * log1pf(q[g] * idof);
           }
         }
-        *dst = make_float4(o[0], o[1], o[2], o[3]);
+        if (blocked) {
+#pragma unroll
+          for (int g = 0; g < GB; g++) dstb[g * 32] = o[g];
+        } else {
+          *dst = make_float4(o[0], o[1], o[2], o[3]);
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // nobody still reads sb when the next-but-one tile restages it
     }
@@ -312,8 +324,8 @@ static inline size_t niw_tc_operand_bytes(size_t ncols, uint32_t dim) {
 // scores[row][k] += NIW term for rows [row_lo,row_hi), all ncols groups.  *done = false when this path does not apply.
 static inline int niw_tc_score(cudaStream_t stream, uint64_t *launches, const float *X, uint32_t dim, const float *W,
                                const float *bias, const float *coef, float *Bop, size_t ncols, float *scores,
-                               size_t ld, size_t row_lo, size_t row_hi, int sm_count, const float *base, bool *done,
-                               std::string &err) {
+                               size_t ld, size_t row_lo, size_t row_hi, int sm_count, const float *base, bool blocked,
+                               bool *done, std::string &err) {
   *done = false;
   if (dim != niwtc::D || getenv("MSB_NO_TENSOR") || row_hi <= row_lo) return MSB_OK;
   const int nGB = (int)((ncols + niwtc::GB - 1) / niwtc::GB);
@@ -324,7 +336,7 @@ static inline int niw_tc_score(cudaStream_t stream, uint64_t *launches, const fl
   // as many CTAs as SMs, but never more than one per (group block, row tile)
   const int grid = (int)std::max<long long>(G, std::min<long long>(sm_count, (long long)G * nRT));
   niw_tc_kernel<<<grid, niwtc::THREADS, niwtc::SMEM_BYTES, stream>>>(X, Bop, bias, coef, (int)ncols, scores, ld, row_lo,
-                                                                      row_hi, G, base);
+                                                                      row_hi, G, base, blocked ? 1 : 0);
   (*launches)++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { err = std::string("niw_tc_kernel launch: ") + cudaGetErrorString(e); return MSB_ERR_CUDA; }

@@ -92,14 +92,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 // conflict-free.  exp(s - m) is computed once (pass 2 overwrites the tile with it).  HBM traffic: the
 // score matrix is read exactly once.  Used when a tile fits (K * 128 bytes per warp).
 // ---------------------------------------------------------------------------------------------------
-template <int WARPS>
+// ROWMAJOR: the scores are row-major [row][ld] (the NIW kernels accumulate into that layout): the tile is filled
+// by coalesced loads (lane = group) and stored transposed with pitch 33, conflict-free both ways.
+template <int WARPS, bool ROWMAJOR>
 __global__ void __launch_bounds__(WARPS * 32)
 sample_tile_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int K, size_t nrows,
                    const float *__restrict__ uniforms, uint64_t seed, uint64_t sweep, uint64_t row_id0,
                    const int32_t *__restrict__ col2slot, int32_t *__restrict__ out_col, int32_t *__restrict__ out_slot) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tile_bytes = (uint32_t)K * 128u;
+  constexpr int P = ROWMAJOR ? 33 : 32;  // tile pitch in floats: element (group k, row r) at tile[k * P + r]
+  const uint32_t tile_bytes = ((uint32_t)K * P * 4u + 127u) / 128u * 128u;
   float *tile = reinterpret_cast<float *>(smem_raw + (size_t)warp * tile_bytes);
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * tile_bytes) + warp;
   if (lane == 0) {
@@ -110,12 +113,23 @@ sample_tile_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int
   const size_t blk_lo = skip / 32, blk_hi = (skip + nrows + 31) / 32;
   uint32_t parity = 0;
   for (size_t blk = blk_lo + (size_t)blockIdx.x * WARPS + warp; blk < blk_hi; blk += (size_t)gridDim.x * WARPS) {
-    if (lane == 0) {
-      mbar_expect_tx(smem_u32(bar), tile_bytes);
-      bulk_g2s(smem_u32(tile), scores + blk * ld * 32, tile_bytes, smem_u32(bar));
+    if constexpr (ROWMAJOR) {
+      __syncwarp();
+      for (int r = 0; r < 32; r++) {
+        const long long ri = (long long)(blk * 32 + r) - (long long)skip;
+        if (ri < 0 || (size_t)ri >= nrows) continue;
+        const float *src = scores + (size_t)ri * ld;  // scores already points at the first valid row
+        for (int kk = lane; kk < K; kk += 32) tile[kk * P + r] = src[kk];
+      }
+      __syncwarp();
+    } else {
+      if (lane == 0) {
+        mbar_expect_tx(smem_u32(bar), tile_bytes);
+        bulk_g2s(smem_u32(tile), scores + blk * ld * 32, tile_bytes, smem_u32(bar));
+      }
+      mbar_wait(smem_u32(bar), parity);
+      parity ^= 1u;
     }
-    mbar_wait(smem_u32(bar), parity);
-    parity ^= 1u;
     const long long i = (long long)(blk * 32 + lane) - (long long)skip;  // row of this lane, relative to the first valid row
     const bool valid = i >= 0 && (size_t)i < nrows;
     float *s = tile + lane;
@@ -123,11 +137,11 @@ sample_tile_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int
     float m0 = s[0], m1 = m0, m2 = m0, m3 = m0, lo0 = m0, lo1 = m0;
     int k = 1;
     for (; k + 3 < K; k += 4) {
-      const float a0 = s[k * 32], a1 = s[(k + 1) * 32], a2 = s[(k + 2) * 32], a3 = s[(k + 3) * 32];
+      const float a0 = s[k * P], a1 = s[(k + 1) * P], a2 = s[(k + 2) * P], a3 = s[(k + 3) * P];
       m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); m2 = fmaxf(m2, a2); m3 = fmaxf(m3, a3);
       lo0 = fminf(lo0, fminf(a0, a1)); lo1 = fminf(lo1, fminf(a2, a3));
     }
-    for (; k < K; k++) { m0 = fmaxf(m0, s[k * 32]); lo0 = fminf(lo0, s[k * 32]); }
+    for (; k < K; k++) { m0 = fmaxf(m0, s[k * P]); lo0 = fminf(lo0, s[k * P]); }
     const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
     // A row whose smallest score is still within exp's range keeps every batch of eight groups alive: the
     // batch-skipping passes below would only add their votes.  Then take the dense passes (same results).
@@ -141,8 +155,8 @@ sample_tile_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int
       live = ~0ull;
 #pragma unroll 8
       for (k = 0; k < K; k++) {
-        const float p = msb_expf(__fsub_rn(s[k * 32], m));
-        s[k * 32] = p;
+        const float p = msb_expf(__fsub_rn(s[k * P], m));
+        s[k * P] = p;
         acc_d = __dadd_rn(acc_d, (double)p);
       }
     } else
@@ -151,7 +165,7 @@ sample_tile_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int
       bool any = false;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        x[j] = k0 + j < K ? __fsub_rn(s[(k0 + j) * 32], m) : -CUDART_INF_F;
+        x[j] = k0 + j < K ? __fsub_rn(s[(k0 + j) * P], m) : -CUDART_INF_F;
         any |= !exp_is_zero(x[j]);
       }
       if (!__any_sync(0xffffffffu, any)) continue;
@@ -160,7 +174,7 @@ sample_tile_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int
       for (int j = 0; j < 8; j++) {
         if (k0 + j < K) {
           const float p = msb_expf(x[j]);
-          s[(k0 + j) * 32] = p;
+          s[(k0 + j) * P] = p;
           acc_d = __dadd_rn(acc_d, (double)p);
         }
       }
@@ -171,16 +185,16 @@ sample_tile_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int
     // pass 3: the dart walk (msb_kernels.cuh), quotients from the tile
     int pick;
     if (dense)
-      dart_walk(K, acc, dart, !valid, pick, [&](int kk) { return s[kk * 32]; }, [](int) { return false; });
+      dart_walk(K, acc, dart, !valid, pick, [&](int kk) { return s[kk * P]; }, [](int) { return false; });
     else
-      dart_walk(K, acc, dart, !valid, pick, [&](int kk) { return ((live >> (kk >> 3)) & 1ull) ? s[kk * 32] : 0.f; },
+      dart_walk(K, acc, dart, !valid, pick, [&](int kk) { return ((live >> (kk >> 3)) & 1ull) ? s[kk * P] : 0.f; },
                 [&](int k0) { return !((live >> (k0 >> 3)) & 1ull); });
     if (valid) {
       if (out_col) out_col[i] = pick;
       if (out_slot) out_slot[i] = col2slot ? col2slot[pick] : pick;
     }
     // the next bulk copy (async proxy) overwrites the tile this warp has just read and written (generic proxy)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if constexpr (!ROWMAJOR) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
   }
 }

@@ -201,7 +201,8 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   CU_TRY(opt_in_smem(score_kernel<2, 32, 16, true, true>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<4, 32, 8, true, true>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<1, 32, 8, true, true>, c->smem_optin));
-  CU_TRY(opt_in_smem(sample_tile_kernel<4>, c->smem_optin));
+  CU_TRY(opt_in_smem((sample_tile_kernel<4, false>), c->smem_optin));
+  CU_TRY(opt_in_smem((sample_tile_kernel<4, true>), c->smem_optin));
   CU_TRY(opt_in_smem(ingest_tile_kernel<128>, c->smem_optin));
   CU_TRY(opt_in_smem(niw_score_data_kernel, c->smem_optin - 1024));
   CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin - 1024));  // it also has a few bytes of static shared memory
@@ -1061,7 +1062,8 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
     }
     MSB_TRY(niw_tc_score(ctx->stream, &ctx->launches, (const float *)f.col, f.dim, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
                          st->d_niwB[d], K, scores, st->ld, row_lo, row_hi, ctx->sm_count, need_init ? st->d_base : nullptr,
-                         &done, g_last_error));
+                         blocked, &done, g_last_error));
+    if (blocked && !done) return fail(MSB_ERR_STATE, "internal: blocked score layout without the tensor-core NIW path");
     if (done) need_init = false;
     if (!done) {
       if (need_init) {
@@ -1498,8 +1500,11 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
   }
   st->ring_nchunks[ring] = nchunks;
   st->sweep_seq++;
-  // the sweep keeps the scores in the sampler-friendly blocked layout (NIW kernels accumulate row-major)
-  const bool blocked = !st->has_niw && !getenv("MSB_NO_BLOCKED");
+  // the sweep keeps the scores in the sampler-friendly blocked layout; the CUDA-core NIW kernel (dim != 64)
+  // accumulates row-major only
+  bool niw_tc_only = true;
+  for (const auto &f : st->feats) if (f.kind == KIND_NIW && (f.dim != 64 || getenv("MSB_NO_TENSOR"))) niw_tc_only = false;
+  const bool blocked = niw_tc_only && !getenv("MSB_NO_BLOCKED");
   CU_TRY(cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned long long), ctx->stream));
   CU_TRY(cudaEventRecord(ev[0].e[0], ctx->stream));
   MSB_TRY(build_params(st));
@@ -1517,15 +1522,23 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
       CU_TRY(cudaMemcpyAsync(st->d_uniforms, opts->uniforms + (lo - row_lo), sizeof(float) * (hi - lo), cudaMemcpyHostToDevice, ctx->stream));
       d_u = st->d_uniforms;
     }
-    if (blocked && K * 128 <= 48 * 1024 && !getenv("MSB_NO_TILE_SAMPLER")) {
-      // tile staged in shared memory: scores read from HBM exactly once
+    const bool tile_fits = K * 33 * 4 <= 48 * 1024 && !getenv("MSB_NO_TILE_SAMPLER");
+    if (tile_fits) {
+      // 32-row tile staged in shared memory: scores read from HBM exactly once (bulk copy of the blocked layout,
+      // or coalesced transposing loads of the row-major one the NIW kernels write)
       constexpr int SW = 4;
-      const size_t smem = (size_t)SW * K * 128 + SW * sizeof(uint64_t) + 64;
-      const size_t nblk = (skip + (hi - lo) + 31) / 32 - skip / 32;
+      const size_t tile_bytes = (K * (blocked ? 32 : 33) * 4 + 127) / 128 * 128;
+      const size_t smem = (size_t)SW * tile_bytes + SW * sizeof(uint64_t) + 64;
+      const size_t skip_t = blocked ? skip : 0;  // the row-major pointer below already starts at the first valid row
+      const size_t nblk = (skip_t + (hi - lo) + 31) / 32 - skip_t / 32;
       const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ctx->smem_optin / smem));
       const unsigned grid = (unsigned)std::min<size_t>((nblk + SW - 1) / SW, (size_t)ctx->sm_count * per_sm);
-      LAUNCH(ctx, sample_tile_kernel<SW>, grid, SW * 32, smem, st->d_scores, st->ld, skip, (int)K, hi - lo, d_u, opts->seed,
-             opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
+      if (blocked)
+        LAUNCH(ctx, (sample_tile_kernel<SW, false>), grid, SW * 32, smem, st->d_scores, st->ld, skip, (int)K, hi - lo, d_u, opts->seed,
+               opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
+      else
+        LAUNCH(ctx, (sample_tile_kernel<SW, true>), grid, SW * 32, smem, st->d_scores + skip * st->ld, st->ld, (size_t)0, (int)K, hi - lo,
+               d_u, opts->seed, opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
     } else if (blocked)
       LAUNCH(ctx, sample_blocked_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores, st->ld, skip, (int)K, hi - lo, d_u, opts->seed,
              opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);

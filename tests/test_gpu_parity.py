@@ -550,3 +550,26 @@ def test_samplers_with_zero_uniforms_and_dead_batches(ctx, oracle, k, monkeypatc
     s[:, 9] = 0.0; s[:, 17] = -1.0; s[:, 23] = -200.0
     uu = np.linspace(0, 0.999, 64).astype(np.float32)
     assert np.array_equal(cb.sample_discrete_log(ctx, s, uu), oracle.sample_rows(s, uu))
+
+
+@pytest.mark.parametrize("descs", [[cb.niw(64)], [cb.niw(64), cb.nich, cb.dd(9)], [cb.niw(3), cb.bb]],
+                         ids=["niw64", "niw64+scalars", "niw3+bb"])
+def test_sweep_with_niw_features_draws_bit_exactly(ctx, oracle, descs):
+    # dim 64: tensor-core kernel writing the blocked layout + tile sampler; dim 3: CUDA-core kernel, row-major
+    # scores + the transposing tile sampler.  Same contract: the GPU's score bits + the uniforms give the draw.
+    n, k = 3001, 21
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=71, mask_frac=0.02, extra_empty=1)
+    for sweep in range(2):
+        old = np.searchsorted(gids, st.assignments()).astype(np.int32)
+        res = st.sweep(seed=11, sweep=sweep)
+        S = st.read_last_scores()
+        want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
+        assert np.max(rel_err(S, want)) < 4 * RTOL
+        u = np.array([oracle.philox_u01(11, i, sweep) for i in range(n)], np.float32)
+        new = np.searchsorted(gids, st.assignments()).astype(np.int32)
+        assert np.array_equal(new, oracle.sample_rows(S, u))
+        assert res["moved"] == int((new != old).sum())
+        oracle.update_rows(descs, hp, ss, counts, view, old, new)
+        for c, g in enumerate(gids):
+            assert st.groupsize(g) == counts[c]
+    st.close()
