@@ -30,6 +30,7 @@ namespace niwtc {
 constexpr int D = 64;            // dimension this path is built for
 constexpr int TM = 128;          // rows per tile (UMMA M)
 constexpr int GB = 4;            // groups per block
+constexpr bool TRIANGULAR = true;  // skip the structurally zero part of the lower-triangular W_k (see the MMA loop)
 constexpr int TN = GB * D;       // UMMA N = 256
 constexpr int A_HALF_BYTES = TM * 32 * 4;   // one k-half (32 k) of one part (hi or lo): 16 KB
 constexpr int A_BYTES = 4 * A_HALF_BYTES;   // [half][part]: 64 KB
@@ -47,13 +48,15 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor, kind::tf32: D=F32 (bits 4-5 = 1), A=B=TF32 (bits 7-9, 10-12 = 2), K-major both,
 // N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+__device__ __forceinline__ constexpr uint32_t idesc_n(uint32_t n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
 
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
@@ -76,6 +79,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // byte offset of element (row, k) inside one part of an operand tile with `rowgroups` 8-row groups:
 // [k/4][row/8][row%8][k%4]  (core matrix = 8 rows x 16 bytes, contiguous)
 __device__ __host__ __forceinline__ uint32_t core_off(uint32_t row, uint32_t k, uint32_t rowgroups) {
@@ -90,11 +107,14 @@ __global__ void niw_pack_b_kernel(const float *__restrict__ W, int ncols, float 
   float *dst = Bop + (size_t)gb * (B_BYTES / 4);
   for (int e = threadIdx.x; e < TN * D; e += blockDim.x) {
     const int nn = e / D, j = e % D;
-    const int k = gb * GB + nn / D, i = nn % D;
+    const int g = nn / D, i = nn % D;
+    const int k = gb * GB + g;
     const float w = k < ncols ? W[((size_t)k * D + i) * D + j] : 0.f;
     const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
     const float lo = w - hi;
-    const uint32_t off = core_off(nn, j, TN / 8) / 4;
+    // operand row n' = (i / 8) * 32 + g * 8 + i % 8: the outputs i >= 8 s that contraction step s (j in [8 s, 8 s + 8))
+    // can reach -- W is lower triangular -- are then the contiguous rows [32 s, 256)
+    const uint32_t off = core_off((uint32_t)((i >> 3) * (GB * 8) + g * 8 + (i & 7)), j, TN / 8) / 4;
     dst[off] = hi;
     dst[B_PART_BYTES / 4 + off] = lo;
   }
@@ -222,12 +242,19 @@ niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const 
           const uint32_t b_hi = smem_u32(sB) + (uint32_t)half * (32 / 4) * (TN / 8) * 128u, b_lo = b_hi + B_PART_BYTES;
 #pragma unroll
           for (int ks = 0; ks < 4; ks++) {  // K = 8 per instruction: 2 core-matrix columns
-            const uint32_t ao = (uint32_t)ks * 2u * (TM / 8) * 128u, bo = (uint32_t)ks * 2u * (TN / 8) * 128u;
+            // W is lower triangular: contraction step s = 4 half + ks (j in [8 s, 8 s + 8)) only reaches the outputs
+            // i >= 8 s, i.e. the operand rows / accumulator columns [32 s, 256): N shrinks by 32 per step
+            // (sum over the 8 steps: 1152 instead of 2048 columns of tensor work)
+            const uint32_t st8 = (uint32_t)(half * 4 + ks);
+            const uint32_t n0 = (blocked & 4) ? st8 * (GB * 8) : (blocked & 2) ? (uint32_t)half * (TN / 2) : 0u;
+            const uint32_t idesc = idesc_n(TN - n0);
+            const uint32_t ao = (uint32_t)ks * 2u * (TM / 8) * 128u;
+            const uint32_t bo = (uint32_t)ks * 2u * (TN / 8) * 128u + (n0 / 8u) * 128u;
             const uint64_t dah = smem_desc(a_hi + ao, (TM / 8) * 128u, 128u), dal = smem_desc(a_lo + ao, (TM / 8) * 128u, 128u);
             const uint64_t dbh = smem_desc(b_hi + bo, (TN / 8) * 128u, 128u), dbl = smem_desc(b_lo + bo, (TN / 8) * 128u, 128u);
-            mma_tf32(d_tmem, dah, dbh, (half | ks) ? 1u : 0u);
-            mma_tf32(d_tmem, dah, dbl, 1u);
-            mma_tf32(d_tmem, dal, dbh, 1u);
+            mma_tf32(d_tmem + n0, dah, dbh, idesc, (half | ks) ? 1u : 0u);
+            mma_tf32(d_tmem + n0, dah, dbl, idesc, 1u);
+            mma_tf32(d_tmem + n0, dal, dbh, idesc, 1u);
           }
           mma_commit(smem_u32(&bars[4 + buf]));            // A half-buffer free once these MMAs complete
           if (half == 1) mma_commit(smem_u32(&bars[6 + acc]));  // accumulator ready for the epilogue
@@ -262,23 +289,41 @@ niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const 
       float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < row_hi) {
         if (base) old = __ldg(reinterpret_cast<const float4 *>(base + (size_t)gb * GB));
-        else if (blocked) old = make_float4(dstb[0], dstb[32], dstb[64], dstb[96]);
+        else if (blocked & 1) old = make_float4(dstb[0], dstb[32], dstb[64], dstb[96]);
         else old = *dst;
       }
       mbar_wait(smem_u32(&bars[6 + acc]), (uint32_t)((t >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // accumulator column n' = (i / 8) * 32 + g * 8 + i % 8 (niw_pack_b_kernel): one 32-column load holds the
+      // outputs i in [8 ib, 8 ib + 8) of all four groups
+      // The load of the next 32 columns is in flight while the current ones are reduced; two outputs per
+      // instruction (FADD2 / FFMA2), even and odd outputs in separate partial sums.
       float q[GB];
+      {
+        float2 q2[GB];
 #pragma unroll
-      for (int g = 0; g < GB; g++) {
-        float s = 0.f;
+        for (int g = 0; g < GB; g++) q2[g] = make_float2(0.f, 0.f);
+        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN);
+        uint32_t r[2][32];
+        tmem_ld32_issue(tbase, r[0]);
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-          float v[32];
-          tmem_ld32(tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN + g * D + c * 32), v);
+        for (int ib = 0; ib < D / 8; ib++) {
+          tmem_ld_wait();
+          if (ib + 1 < D / 8) tmem_ld32_issue(tbase + (uint32_t)(ib + 1) * 32u, r[(ib + 1) & 1]);
 #pragma unroll
-          for (int i = 0; i < 32; i++) { const float y = v[i] - sb[g * D + c * 32 + i]; s = fmaf(y, y, s); }
+          for (int g = 0; g < GB; g++) {
+            const float4 b0 = *reinterpret_cast<const float4 *>(sb + g * D + ib * 8);
+            const float4 b1 = *reinterpret_cast<const float4 *>(sb + g * D + ib * 8 + 4);
+            const uint32_t *v = r[ib & 1] + g * 8;
+            float2 y;
+            y = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(-b0.x, -b0.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
+            y = __fadd2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(-b0.z, -b0.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
+            y = __fadd2_rn(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(-b1.x, -b1.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
+            y = __fadd2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(-b1.z, -b1.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
+          }
         }
-        q[g] = s;
+#pragma unroll
+        for (int g = 0; g < GB; g++) q[g] = q2[g].x + q2[g].y;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -293,7 +338,7 @@ niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const 
             o[g] += c0 + c1 * log1pf(q[g] * idof);
           }
         }
-        if (blocked) {
+        if (blocked & 1) {
 #pragma unroll
           for (int g = 0; g < GB; g++) dstb[g * 32] = o[g];
         } else {
@@ -336,7 +381,7 @@ static inline int niw_tc_score(cudaStream_t stream, uint64_t *launches, const fl
   // as many CTAs as SMs, but never more than one per (group block, row tile)
   const int grid = (int)std::max<long long>(G, std::min<long long>(sm_count, (long long)G * nRT));
   niw_tc_kernel<<<grid, niwtc::THREADS, niwtc::SMEM_BYTES, stream>>>(X, Bop, bias, coef, (int)ncols, scores, ld, row_lo,
-                                                                      row_hi, G, base, blocked ? 1 : 0);
+                                                                      row_hi, G, base, (blocked ? 1 : 0) | (getenv("MSB_NIW_TRI2") ? 2 : 0) | (getenv("MSB_NIW_TRI8") ? 4 : 0));
   (*launches)++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { err = std::string("niw_tc_kernel launch: ") + cudaGetErrorString(e); return MSB_ERR_CUDA; }
