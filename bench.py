@@ -100,6 +100,29 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def usable_cores():
+    """host threads this process may really use: the affinity mask, capped by the cgroup CPU quota
+    (os.cpu_count() reports the machine, not the container)"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def build_workload(args, rank, world):
     import common_b200 as cb
     cfg = cb.synth.config(args.workload)
@@ -177,7 +200,7 @@ def main():
         cfg, descs, storage, n, k, arr, z = build_workload(args, 0, 1)
         n = min(n, 200_000)
         arr, z = arr[:n], z[:n]
-        ncores = os.cpu_count() or 1
+        ncores = usable_cores()
         hpx = cfg.get("hp")
         rates = []
         for i in range(args.warmup + args.steps):
