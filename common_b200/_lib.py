@@ -91,6 +91,7 @@ _PROTOS = {
     "msb_state_remove_value": (C.c_int, [_P, _SZ, C.POINTER(_SZ)]),
     "msb_state_score_value": (C.c_int, [_P, _SZ, C.POINTER(_SZ), C.POINTER(C.c_float), _SZ, C.POINTER(_SZ)]),
     "msb_state_score_rows": (C.c_int, [_P, _SZ, _SZ, _P, _SZ, C.c_int, C.POINTER(_SZ), _SZ, C.POINTER(_SZ)]),
+    "msb_state_score_rows_f64": (C.c_int, [_P, _SZ, _SZ, _P, _SZ, C.POINTER(_SZ), _SZ, C.POINTER(_SZ)]),
     "msb_state_score_likelihood": (C.c_int, [_P, _SZ, _SZ, C.POINTER(C.c_float)]),
     "msb_state_score_likelihood_all": (C.c_int, [_P, C.POINTER(C.c_float), _SZ, C.POINTER(C.c_float)]),
     "msb_state_score_assignment": (C.c_int, [_P, C.POINTER(C.c_float)]),

@@ -269,9 +269,11 @@ __global__ void build_params_kernel(const FeatDev *__restrict__ feats, int nfeat
 // Used for single-entity score_value (entity_state.hpp:60-72) and as an
 // independent on-device cross-check of the table path.  Scalar families only.
 // ---------------------------------------------------------------------------
+// OUT = float: the API's fp32 scores; OUT = double: the fp64 result itself (msb_state_score_rows_f64, held to 1e-12).
+template <typename OUT>
 __global__ void score_direct_kernel(const FeatDev *__restrict__ feats, int nfeat, const double *__restrict__ hp,
                                     const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols,
-                                    const float *__restrict__ base, float *__restrict__ scores, size_t ld,
+                                    const float *__restrict__ base, OUT *__restrict__ scores, size_t ld,
                                     size_t row_lo, size_t row_hi) {
   const size_t row = row_lo + blockIdx.x;
   if (row >= row_hi) return;
@@ -299,7 +301,7 @@ __global__ void score_direct_kernel(const FeatDev *__restrict__ feats, int nfeat
         s += nich_score(nich_post(fhp, gss), (double)x);
       }
     }
-    scores[(row - row_lo) * ld + col] = (float)(s + (double)base[col]);
+    scores[(row - row_lo) * ld + col] = (OUT)(s + (double)base[col]);
   }
 }
 
@@ -514,6 +516,51 @@ __global__ void score_assignment_kernel(const double *__restrict__ counts, const
   if (threadIdx.x == 0) {
     out[0] = s_sum - (lgamma(s_n + alpha) - lgamma(1.0 + alpha));
     out[1] = s_n;
+  }
+}
+
+// fp64 NIW scorer (verification path, any dim): one block per group column; the block factors the scale matrix
+// (as niw_prepare_kernel does), then each thread scores rows by forward substitution in fp64.
+// scores[(row - row_lo) * ld + k] += c0 - (dof + d)/2 log1p(|L^-1 (x - mu')|^2 / dof)
+__global__ void niw_score_f64_kernel(FeatDev f, const double *__restrict__ hp, const double *__restrict__ ss,
+                                     const int32_t *__restrict__ col2slot, double *__restrict__ scores, size_t ld,
+                                     size_t row_lo, size_t row_hi) {
+  extern __shared__ double sm[];
+  const int d = (int)f.dim;
+  double *A = sm;          // d*d: scale matrix, then its lower Cholesky factor
+  double *mu = A + d * d;  // d
+  __shared__ int s_fail;
+  __shared__ double s_acc;
+  const int k = blockIdx.x;
+  const double *fhp = hp + f.hp_off;
+  const double *gss = ss + f.ss_off + (size_t)col2slot[k] * f.ss_w;
+  const double *mu0 = fhp, kappa0 = fhp[d], *psi0 = fhp + d + 1, nu0 = fhp[d + 1 + (size_t)d * d];
+  const double n = gss[0];
+  const double *sx = gss + 1, *sxx = gss + 1 + d;
+  const double kn = kappa0 + n, nun = nu0 + n;
+  const double dof = nun - (double)d + 1.0;
+  const double scale = (kn + 1.0) / (kn * dof);
+  for (int i = threadIdx.x; i < d; i += blockDim.x) mu[i] = (kappa0 * mu0[i] + sx[i]) / kn;
+  __syncthreads();
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int i = e / d, j = e - i * d;
+    A[e] = (psi0[e] + sxx[e] + kappa0 * mu0[i] * mu0[j] - kn * mu[i] * mu[j]) * scale;
+  }
+  __syncthreads();
+  const double logdet = block_chol_logdet(A, d, &s_fail, &s_acc);  // = 2 sum log L_ii
+  const double c0 = lgamma(0.5 * (dof + d)) - lgamma(0.5 * dof) - 0.5 * d * log(dof * CUDART_PI) - 0.5 * logdet;
+  for (size_t row = row_lo + threadIdx.x; row < row_hi; row += blockDim.x) {
+    const float *x = (const float *)f.col + row * (size_t)d;
+    if (x[0] != x[0]) continue;  // masked
+    double q = 0.0;
+    double y[96];
+    for (int i = 0; i < d; i++) {
+      double t = (double)x[i] - mu[i];
+      for (int m = 0; m < i; m++) t -= A[i * d + m] * y[m];
+      y[i] = t / A[i * d + i];
+      q += y[i] * y[i];
+    }
+    scores[(row - row_lo) * ld + k] += c0 - 0.5 * (dof + d) * log1p(q / dof);
   }
 }
 

@@ -205,6 +205,7 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   CU_TRY(opt_in_smem((sample_tile_kernel<4, true>), c->smem_optin));
   CU_TRY(opt_in_smem(ingest_tile_kernel<128>, c->smem_optin));
   CU_TRY(opt_in_smem(niw_score_data_kernel, c->smem_optin - 1024));
+  CU_TRY(opt_in_smem(niw_score_f64_kernel, c->smem_optin - 1024));
   CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin - 1024));  // it also has a few bytes of static shared memory
   CU_TRY(opt_in_smem(niw_score_simt_kernel, c->smem_optin - 1024));
   MSB_TRY(niw_tc_init(c->smem_optin, g_last_error));
@@ -1248,7 +1249,7 @@ extern "C" MSB_API int msb_state_score_value(msb_state *st, size_t eid, size_t *
   if (!st->has_niw) {
     MSB_TRY(ensure_scores(st, 1));
     MSB_TRY(sync_small(st));
-    LAUNCH(ctx, score_direct_kernel, 1, 128, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot, (int)K,
+    LAUNCH(ctx, score_direct_kernel<float>, 1, 128, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot, (int)K,
            st->d_base, st->d_scores, st->ld, eid, eid + 1);
   } else {
     skip = eid - row_origin(eid);
@@ -1283,7 +1284,7 @@ extern "C" MSB_API int msb_state_score_rows(msb_state *st, size_t row_lo, size_t
   if (!dst) { MSB_TRY(ensure_scores(st, nrows + skip)); dst = st->d_scores; }
   if (direct) {
     MSB_TRY(sync_small(st));
-    LAUNCH(ctx, score_direct_kernel, (unsigned)nrows, 128, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot,
+    LAUNCH(ctx, score_direct_kernel<float>, (unsigned)nrows, 128, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot,
            (int)K, st->d_base, dst, st->ld, row_lo, row_hi);
   } else {
     MSB_TRY(build_params(st));
@@ -1296,6 +1297,40 @@ extern "C" MSB_API int msb_state_score_rows(msb_state *st, size_t row_lo, size_t
                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (!on_device) CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return MSB_OK;
+}
+
+// fp64 scores: the closed forms evaluated in double straight from the resident suffstats (no tables, no fp32
+// anywhere but the stored values themselves).  The verification path for the 1e-12 tolerance; host output.
+extern "C" MSB_API int msb_state_score_rows_f64(msb_state *st, size_t row_lo, size_t row_hi, double *scores, size_t ld,
+                                        size_t *gids, size_t cap, size_t *ncols) {
+  REQUIRE(st && ncols, "NULL argument");
+  REQUIRE(st->dv, "no dataview bound");
+  REQUIRE(row_lo <= row_hi && row_hi <= st->n, "bad row range");
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  MSB_TRY(prepare_columns(st));
+  MSB_TRY(sync_small(st));
+  const size_t K = st->h_col2slot.size();
+  *ncols = K;
+  if (gids) { REQUIRE(cap >= K, "buffer too small"); for (size_t c = 0; c < K; c++) gids[c] = st->h_colgid[c]; }
+  const size_t nrows = row_hi - row_lo;
+  if (!nrows || !scores) return MSB_OK;
+  REQUIRE(ld >= K, "ld smaller than the number of groups");
+  double *d_out = nullptr;
+  CU_TRY(cudaMalloc(&d_out, sizeof(double) * nrows * K));
+  LAUNCH(ctx, score_direct_kernel<double>, (unsigned)nrows, 128, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot,
+         (int)K, st->d_base, d_out, K, row_lo, row_hi);
+  for (size_t d = 0; d < st->D; d++) {
+    const FeatDev &f = st->feats[d];
+    if (f.kind != KIND_NIW) continue;
+    const size_t smem = ((size_t)f.dim * f.dim + f.dim) * sizeof(double);
+    LAUNCH(ctx, niw_score_f64_kernel, (unsigned)K, 128, smem, f, st->d_hp, st->d_ss, st->d_col2slot, d_out, K, row_lo, row_hi);
+  }
+  CU_TRY(cudaMemcpy2DAsync(scores, sizeof(double) * ld, d_out, sizeof(double) * K, sizeof(double) * K, nrows,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_out);
   return MSB_OK;
 }
 

@@ -193,6 +193,16 @@ class state(object):
                                                     0, gids, k, C.byref(n)))
         return [int(gids[i]) for i in range(n.value)], out
 
+    def score_rows_f64(self, row_lo=0, row_hi=None):
+        """(gids, float64 scores[nrows, K]) from the fp64 closed-form path"""
+        row_hi = self.nentities() if row_hi is None else row_hi
+        k = self.ngroups()
+        gids = (C.c_size_t * max(k, 1))()
+        n = C.c_size_t()
+        out = np.zeros((row_hi - row_lo, k), np.float64)
+        _lib.check(_lib.load().msb_state_score_rows_f64(self._h, row_lo, row_hi, out.ctypes.data, k, gids, k, C.byref(n)))
+        return [int(gids[i]) for i in range(n.value)], out
+
     def score_rows_device(self, row_lo=0, row_hi=None):
         """scores stay on the device; returns (gids, device pointer, ld)"""
         row_hi = self.nentities() if row_hi is None else row_hi

@@ -177,6 +177,11 @@ MSB_API int msb_state_score_value(msb_state *st, size_t eid, size_t *gids, float
 MSB_API int msb_state_score_rows(msb_state *st, size_t row_lo, size_t row_hi, float *scores, size_t ld,
                          int on_device, size_t *gids, size_t cap, size_t *ncols);
 
+/* the same matrix in fp64 (host output): the closed forms in double straight from the resident suffstats,
+ * no tables and no tensor cores -- the path the 1e-12 fp64 tolerance is checked on */
+MSB_API int msb_state_score_rows_f64(msb_state *st, size_t row_lo, size_t row_hi, double *scores, size_t ld,
+                             size_t *gids, size_t cap, size_t *ncols);
+
 /* entity_state.hpp:74-86: score_likelihood(component, gid) = group::score_data (models/base.hpp:28), the log
  * marginal likelihood of the group's data under the component's hypers; and its sum over the groups per
  * component (per_feature[nfeatures], may be NULL) and over everything (total, may be NULL).  fp64 closed forms

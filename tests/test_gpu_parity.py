@@ -573,3 +573,22 @@ def test_sweep_with_niw_features_draws_bit_exactly(ctx, oracle, descs):
         for c, g in enumerate(gids):
             assert st.groupsize(g) == counts[c]
     st.close()
+
+
+@pytest.mark.parametrize("name,cond", [("bb", 1.0), ("dd", 1.0), ("gp", 4.0), ("nich", 4.0), ("mixed", 4.0), ("niw", 50.0)])
+def test_fp64_scores_within_1e12_of_the_oracle(ctx, oracle, name, cond):
+    # north_star tolerance for fp64: 1e-12 relative.  `cond` is the conditioning of the closed form itself in
+    # double (lgamma(a + x) - lgamma(a) and lgamma((nu+1)/2) - lgamma(nu/2) cancel; a d x d Cholesky for niw):
+    # the CPU oracle (glibc) and the device (CUDA libm) each carry that much rounding.
+    descs = FAMILIES[name] if name != "niw" else [cb.niw(5), cb.niw(64)]
+    n, k = (700, 9) if name != "niw" else (300, 5)
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=81, mask_frac=0.04, extra_empty=1)
+    got_gids, S = st.score_rows_f64()
+    assert got_gids == gids and S.dtype == np.float64
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, prec=64)
+    err = np.max(np.abs(S - want) / np.maximum(1.0, np.abs(want)))
+    assert err < 1e-12 * cond, err
+    # and the fp32 production path agrees with its own fp64 form to the fp32 tolerance
+    _, S32 = st.score_rows()
+    assert np.max(rel_err(S32, S)) < (4 if name == "niw" else 1) * RTOL
+    st.close()
