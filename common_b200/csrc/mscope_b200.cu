@@ -111,6 +111,8 @@ struct msb_state {
   uint32_t *h_flags = nullptr;    // pinned scratch for the bind-time device -> host flags
   uint32_t *d_flags = nullptr;
   int64_t *d_assign64 = nullptr; size_t assign64_cap = 0;
+  cudaEvent_t ev_mapped = nullptr, ev_assign_copied = nullptr;  // msb_state_assignments_async
+  bool assign_copy_pending = false;
   bool slot2gid_dirty = true;
   msb_sweep_result last_res = {0, 0, 0};
   std::vector<char> slot_dirty;   // suffstats of the slot may be non-zero (set by any update / set_ss)
@@ -516,7 +518,9 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
 extern "C" MSB_API int msb_state_destroy(msb_state *st) {
   if (!st) return MSB_OK;
   cudaSetDevice(st->ctx->device);
+  cudaStreamSynchronize(st->ctx->copy_stream);
   cudaStreamSynchronize(st->ctx->stream);
+  if (st->ev_mapped) { cudaEventDestroy(st->ev_mapped); cudaEventDestroy(st->ev_assign_copied); }
   cudaFree(st->col_slab);
   for (size_t d = 0; d < st->D; d++) { cudaFree(st->d_niwW[d]); cudaFree(st->d_niwBias[d]); cudaFree(st->d_niwCoef[d]); cudaFree(st->d_niwB[d]); }
   cudaFree(st->d_feats); cudaFree(st->d_feats_scalar); cudaFree(st->d_hp); cudaFree(st->d_ss); cudaFree(st->d_delta); cudaFree(st->d_counter);
@@ -1151,6 +1155,45 @@ extern "C" MSB_API int msb_state_assignments(msb_state *st, int64_t *out, size_t
   LAUNCH(ctx, map_i32_to_i64_kernel, cdiv(n, 256), 256, 0, st->d_assign, st->d_slot2gid, n, st->d_assign64);
   CU_TRY(cudaMemcpyAsync(out, st->d_assign64, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return MSB_OK;
+}
+
+// The same, without waiting: the gid translation runs on the compute stream, the device -> host copy on the
+// copy stream (so it overlaps whatever the compute stream does next, e.g. the next sweep).  `out` should be
+// pinned and must not be read before msb_state_assignments_wait returns.  One copy in flight per state.
+extern "C" MSB_API int msb_state_assignments_async(msb_state *st, int64_t *out, size_t n) {
+  REQUIRE(st && out, "NULL argument");
+  REQUIRE(st->dv, "no dataview bound");
+  REQUIRE(n == st->n, "wrong length");
+  if (!n) return MSB_OK;
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (!st->ev_mapped) {
+    CU_TRY(cudaEventCreateWithFlags(&st->ev_mapped, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&st->ev_assign_copied, cudaEventDisableTiming));
+  }
+  if (st->assign_copy_pending) {  // d_assign64 is still being read by the previous copy
+    CU_TRY(cudaStreamWaitEvent(ctx->stream, st->ev_assign_copied, 0));
+  }
+  MSB_TRY(ensure(&st->d_assign64, &st->assign64_cap, n));
+  if (st->slot2gid_dirty) {
+    CU_TRY(cudaMemcpyAsync(st->d_slot2gid, st->slot2gid.data(), sizeof(int64_t) * st->kmax, cudaMemcpyHostToDevice, ctx->stream));
+    st->slot2gid_dirty = false;
+  }
+  LAUNCH(ctx, map_i32_to_i64_kernel, cdiv(n, 256), 256, 0, st->d_assign, st->d_slot2gid, n, st->d_assign64);
+  CU_TRY(cudaEventRecord(st->ev_mapped, ctx->stream));
+  CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, st->ev_mapped, 0));
+  CU_TRY(cudaMemcpyAsync(out, st->d_assign64, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CU_TRY(cudaEventRecord(st->ev_assign_copied, ctx->copy_stream));
+  st->assign_copy_pending = true;
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_state_assignments_wait(msb_state *st) {
+  REQUIRE(st, "NULL argument");
+  if (!st->assign_copy_pending) return MSB_OK;
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  CU_TRY(cudaEventSynchronize(st->ev_assign_copied));
+  st->assign_copy_pending = false;
   return MSB_OK;
 }
 

@@ -136,6 +136,14 @@ class state(object):
         _lib.check(_lib.load().msb_state_assignments(self._h, a.ctypes.data, n))
         return a
 
+    def assignments_async(self, out):
+        """enqueue the copy of the assignments into ``out`` (int64, pinned); valid after assignments_wait()"""
+        assert out.dtype == np.int64 and out.size == self.nentities() and out.flags.c_contiguous
+        _lib.check(_lib.load().msb_state_assignments_async(self._h, out.ctypes.data, out.size))
+
+    def assignments_wait(self):
+        _lib.check(_lib.load().msb_state_assignments_wait(self._h))
+
     # ---- membership (entity_state.hpp:57-72) ------------------------------------------
     def add_value(self, gid, eid, rng=None):
         _lib.check(_lib.load().msb_state_add_value(self._h, gid, eid))

@@ -163,6 +163,10 @@ MSB_API int msb_state_delete_group(msb_state *st, size_t gid); /* must be empty 
 
 /* assignments: gid per entity, -1 = unassigned (group_manager.hpp:133-137) */
 MSB_API int msb_state_assignments(msb_state *st, int64_t *out, size_t n);
+/* the same without waiting: gid translation on the compute stream, device -> host copy on the copy stream (it
+ * overlaps the next sweep).  `out` (pinned) is valid once msb_state_assignments_wait returns. */
+MSB_API int msb_state_assignments_async(msb_state *st, int64_t *out, size_t n);
+MSB_API int msb_state_assignments_wait(msb_state *st);
 /* bulk add_value of every currently unassigned entity whose gids[i] != -1 */
 MSB_API int msb_state_add_values(msb_state *st, const int64_t *gids, size_t n);
 

@@ -592,3 +592,22 @@ def test_fp64_scores_within_1e12_of_the_oracle(ctx, oracle, name, cond):
     _, S32 = st.score_rows()
     assert np.max(rel_err(S32, S)) < (4 if name == "niw" else 1) * RTOL
     st.close()
+
+
+def test_async_assignments_copy_matches_blocking(ctx, oracle):
+    import torch
+    descs = FAMILIES["mixed"]
+    n, k = 20000, 8
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=91)
+    bufs = [torch.empty(n, dtype=torch.int64).pin_memory().numpy() for _ in range(2)]
+    prev = None
+    for it in range(4):
+        st.sweep(seed=2, sweep=it, wait=False)
+        st.assignments_wait()
+        if prev is not None:
+            assert np.array_equal(bufs[(it - 1) & 1], prev)      # landed while this sweep was being enqueued
+        st.assignments_async(bufs[it & 1])
+        prev = st.assignments()                                  # blocking read of the same state
+    st.assignments_wait()
+    assert np.array_equal(bufs[3 & 1], prev)
+    st.close()
