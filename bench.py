@@ -329,11 +329,12 @@ def main():
             cbd.allreduce_suffstats(s2, device)
 
         dv2.upload(pinned.data_ptr())                # the first pass's records
+        s2.prefetch()
 
         def e2e_step(i):
-            s2.refresh()                             # waits for this pass's records, AoS -> SoA on the device
-            dv2.upload(pinned.data_ptr())            # H2D of the NEXT pass's records on the copy stream: it starts once
-                                                     # the conversion above has read the old ones and overlaps the sweep
+            s2.refresh()                             # this pass's columns (converted on the copy stream) become current
+            dv2.upload(pinned.data_ptr())            # H2D of the NEXT pass's records and their AoS -> SoA conversion into
+            s2.prefetch()                            # the second column buffer: copy stream, under this pass's sweep
             rr = step(i, s2)
             s2.assignments_wait()                    # the previous pass's result has landed in pinned memory
             s2.assignments_async(out_np[i & 1])      # D2H of this pass's result, on the copy stream
@@ -358,7 +359,7 @@ def main():
         e2e = {"value": float(uu.item()) / float(tt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(raw.nbytes), "d2h_bytes_per_step": int(n * 8),
                "ms_per_step": float(tt.item()) * 1e3 / esteps, "steps": esteps,
-               "what": "per pass: one H2D of the host AoS records (pinned; the next pass's upload runs on a copy stream under this pass's sweep) -> AoS->SoA conversion -> sweep (score, draw, suffstat update"
+               "what": "per pass: one H2D of the host AoS records (pinned) + AoS->SoA conversion, both for the NEXT pass on a copy stream under this pass's sweep (double-buffered columns) -> sweep (score, draw, suffstat update"
                        + (", all-reduce" if world > 1 else "") + ") -> int64 assignments to pinned host memory (copied on the copy stream, waited for during the next pass; the last one inside the timed region); groups/hypers/suffstats resident in HBM"}
         s2.close(); dv2.close()
 

@@ -72,6 +72,7 @@ _PROTOS = {
     "msb_state_destroy": (C.c_int, [_P]),
     "msb_state_bind": (C.c_int, [_P, _P]),
     "msb_state_refresh": (C.c_int, [_P]),
+    "msb_state_prefetch": (C.c_int, [_P]),
     "msb_state_set_hp": (C.c_int, [_P, _SZ, C.c_char_p, C.POINTER(C.c_double), _SZ]),
     "msb_state_get_hp": (C.c_int, [_P, _SZ, C.c_char_p, C.POINTER(C.c_double), _SZ]),
     "msb_state_set_ss": (C.c_int, [_P, _SZ, _SZ, C.c_char_p, C.POINTER(C.c_double), _SZ]),

@@ -118,6 +118,16 @@ struct msb_state {
   std::vector<char> slot_dirty;   // suffstats of the slot may be non-zero (set by any update / set_ss)
   bool all_unassigned = true;     // no entity has been assigned since bind
   void *col_slab = nullptr;       // one allocation backing every column
+  size_t slab_bytes = 0;
+  // Second column buffer (msb_state_prefetch): the next pass's records are converted on the copy stream into the
+  // buffer the running sweep does not read; msb_state_refresh then only swaps the two.
+  void *col_slab_b = nullptr;
+  std::vector<FeatDev> feats_b;
+  std::vector<void *> cols_b;
+  FeatDev *d_feats_b = nullptr, *d_feats_scalar_b = nullptr;
+  uint32_t *d_flags_b = nullptr, *h_flags_b = nullptr;
+  cudaEvent_t ev_swap = nullptr, ev_prefetched = nullptr;
+  bool prefetch_pending = false, swap_recorded = false, feats_b_dirty = false;
   size_t n_pad = 0;               // rows of the (padded) score columns
   // data
   msb_dataview *dv = nullptr;
@@ -521,6 +531,8 @@ extern "C" MSB_API int msb_state_destroy(msb_state *st) {
   cudaStreamSynchronize(st->ctx->copy_stream);
   cudaStreamSynchronize(st->ctx->stream);
   if (st->ev_mapped) { cudaEventDestroy(st->ev_mapped); cudaEventDestroy(st->ev_assign_copied); }
+  if (st->ev_swap) { cudaEventDestroy(st->ev_swap); cudaEventDestroy(st->ev_prefetched); }
+  cudaFree(st->col_slab_b); cudaFree(st->d_feats_b); cudaFree(st->d_feats_scalar_b); cudaFree(st->d_flags_b); cudaFreeHost(st->h_flags_b);
   cudaFree(st->col_slab);
   for (size_t d = 0; d < st->D; d++) { cudaFree(st->d_niwW[d]); cudaFree(st->d_niwBias[d]); cudaFree(st->d_niwCoef[d]); cudaFree(st->d_niwB[d]); }
   cudaFree(st->d_feats); cudaFree(st->d_feats_scalar); cudaFree(st->d_hp); cudaFree(st->d_ss); cudaFree(st->d_delta); cudaFree(st->d_counter);
@@ -688,6 +700,9 @@ extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
       }
     }
     CU_TRY(cudaMalloc(&st->col_slab, slab));
+    st->slab_bytes = slab;
+    CU_TRY(cudaStreamSynchronize(ctx->copy_stream));  // a prefetch into the old shadow buffer may still be running
+    cudaFree(st->col_slab_b); st->col_slab_b = nullptr;
     for (size_t d = 0; d < st->D; d++) {
       FeatDev &f = st->feats[d];
       st->cols[d] = (char *)st->col_slab + coff[d];
@@ -704,6 +719,8 @@ extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
     f.src_prim = (uint32_t)dv->types[d].prim; f.src_n = dv->types[d].n;
   }
   st->feats_dirty = true;
+  if (st->prefetch_pending) { CU_TRY(cudaStreamSynchronize(ctx->copy_stream)); st->prefetch_pending = false; }
+  st->feats_b.clear();  // the shadow descriptors are rebuilt from the new layout by the next msb_state_prefetch
   MSB_TRY(ingest(st, true));
   CU_TRY(cudaMemsetAsync(st->d_assign, 0xFF, sizeof(int32_t) * n, ctx->stream));  // all -1
   st->all_unassigned = true;
@@ -715,8 +732,90 @@ extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
 extern "C" MSB_API int msb_state_refresh(msb_state *st) {
   REQUIRE(st, "NULL argument");
   REQUIRE(st->dv, "no dataview bound");
-  CU_TRY(cudaSetDevice(st->ctx->device));
-  return ingest(st, false);
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (!st->prefetch_pending) return ingest(st, false);
+  // the conversion already ran on the copy stream (msb_state_prefetch): make the two column buffers change places
+  CU_TRY(cudaEventSynchronize(st->ev_prefetched));                  // its flags are on the host now
+  CU_TRY(cudaStreamWaitEvent(ctx->stream, st->ev_prefetched, 0));   // kernels enqueued from here on see the new columns
+  st->prefetch_pending = false;
+  std::swap(st->col_slab, st->col_slab_b);
+  std::swap(st->feats, st->feats_b);
+  std::swap(st->cols, st->cols_b);
+  std::swap(st->d_feats, st->d_feats_b);
+  std::swap(st->d_feats_scalar, st->d_feats_scalar_b);
+  bool any = false, changed = st->feats_b_dirty;
+  for (size_t d = 0; d < st->D; d++) {
+    // fields that are not per buffer follow the buffer that was active until now
+    st->feats[d].asum = st->feats_b[d].asum; st->feats[d].ncat = st->feats_b[d].ncat;
+    st->feats[d].rows = st->feats_b[d].rows; st->feats[d].rowoff = st->feats_b[d].rowoff;
+    changed |= st->feats[d].has_slow != st->h_flags_b[d];
+    st->feats[d].has_slow = st->h_flags_b[d];
+    any |= st->h_flags_b[d] != 0;
+  }
+  st->feats_b_dirty = false;
+  st->tables_only = !any && !st->has_nich && !getenv("MSB_NO_TABLES_ONLY");
+  // the device descriptors of this buffer were last used two passes ago (the prefetch waited for ev_swap), so
+  // re-uploading them cannot race with a kernel; needed only when a flag or a shared field changed
+  if (changed) st->feats_dirty = true;
+  else {  // the feature walk order and count are unchanged: n_scalar stays valid
+  }
+  CU_TRY(cudaEventRecord(st->ev_swap, ctx->stream));
+  st->swap_recorded = true;
+  return MSB_OK;
+}
+
+// Converts the bound dataview's (re-uploaded) records into the column buffer that the running sweep does not
+// read, on the copy stream, right behind the upload.  The following msb_state_refresh swaps the buffers.
+extern "C" MSB_API int msb_state_prefetch(msb_state *st) {
+  REQUIRE(st, "NULL argument");
+  REQUIRE(st->dv, "no dataview bound");
+  msb_ctx *ctx = st->ctx;
+  msb_dataview *dv = st->dv;
+  CU_TRY(cudaSetDevice(ctx->device));
+  constexpr int TR = 128;
+  const size_t D = st->D;
+  const size_t tile_bytes = ((size_t)TR * (dv->rowsize / 4 + 1) + (dv->d_mask ? (size_t)TR * (dv->maskrowsize / 4 + 1) : 0)) * 4;
+  const bool fused_ok = dv->n && dv->owns && st->has_scalar && dv->rowsize % 4 == 0 && (!dv->d_mask || dv->maskrowsize % 4 == 0) &&
+                        tile_bytes <= ctx->smem_optin && st->col_slab;
+  if (!fused_ok || st->prefetch_pending) return MSB_OK;  // msb_state_refresh converts on the compute stream instead
+  if (!st->ev_swap) {
+    CU_TRY(cudaEventCreateWithFlags(&st->ev_swap, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&st->ev_prefetched, cudaEventDisableTiming));
+    CU_TRY(cudaMalloc(&st->d_feats_b, sizeof(FeatDev) * D));
+    CU_TRY(cudaMalloc(&st->d_feats_scalar_b, sizeof(FeatDev) * D));
+    CU_TRY(cudaMalloc(&st->d_flags_b, sizeof(uint32_t) * 2 * D));
+    CU_TRY(cudaHostAlloc(&st->h_flags_b, sizeof(uint32_t) * 2 * D, cudaHostAllocDefault));
+  }
+  if (!st->col_slab_b) CU_TRY(cudaMalloc(&st->col_slab_b, st->slab_bytes));
+  if (st->feats_b.empty()) {  // shadow descriptors: the same layout, pointers into the second slab
+    MSB_TRY(sync_small(st));
+    st->feats_b = st->feats;
+    st->cols_b = st->cols;
+    const ptrdiff_t shift = (char *)st->col_slab_b - (char *)st->col_slab;
+    for (size_t d = 0; d < D; d++) {
+      FeatDev &f = st->feats_b[d];
+      f.col = (char *)f.col + shift;
+      st->cols_b[d] = (char *)st->cols_b[d] + shift;
+      if (f.scol) f.scol = (const uint32_t *)((const char *)f.scol + shift);
+      if (f.slowmask) f.slowmask = (const uint32_t *)((const char *)f.slowmask + shift);
+    }
+    CU_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    CU_TRY(cudaMemcpy(st->d_feats_b, st->feats_b.data(), sizeof(FeatDev) * D, cudaMemcpyHostToDevice));
+    st->feats_b_dirty = true;  // its walk-order list (d_feats_scalar_b) is built at the first swap
+  }
+  if (st->swap_recorded) CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, st->ev_swap, 0));  // the last readers of that buffer are done
+  CU_TRY(cudaMemsetAsync(st->d_flags_b, 0, sizeof(uint32_t) * D, ctx->copy_stream));
+  ingest_tile_kernel<TR><<<(unsigned)(st->n_pad / TR), TR, tile_bytes, ctx->copy_stream>>>(
+      dv->d_data, dv->d_mask, dv->n, st->n_pad, (uint32_t)(dv->rowsize / 4), (uint32_t)(dv->maskrowsize / 4), st->d_feats_b,
+      (int)D, st->d_flags_b);
+  ctx->launches++;
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaMemcpyAsync(st->h_flags_b, st->d_flags_b, sizeof(uint32_t) * D, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CU_TRY(cudaEventRecord(st->ev_prefetched, ctx->copy_stream));
+  dv->upload_pending = false;  // the copy stream itself consumed the upload; later uploads queue behind this kernel
+  st->prefetch_pending = true;
+  return MSB_OK;
 }
 
 // ---- hypers / suffstats ------------------------------------------------------
@@ -732,6 +831,7 @@ extern "C" MSB_API int msb_state_set_hp(msb_state *st, size_t feature, const cha
     double a = 0.0;
     for (uint32_t i = 0; i < st->models[feature].dim; i++) a += h[i];
     st->feats[feature].asum = a;
+    if (!st->feats_b.empty()) { st->feats_b[feature].asum = a; st->feats_b_dirty = true; }
     st->feats_dirty = true;
   }
   st->hp_dirty = true;

@@ -48,6 +48,11 @@ class state(object):
         (assignments and suffstats are kept)"""
         _lib.check(_lib.load().msb_state_refresh(self._h))
 
+    def prefetch(self):
+        """after an upload: convert the new records on the copy stream into the second column buffer;
+        the next refresh() only swaps buffers"""
+        _lib.check(_lib.load().msb_state_prefetch(self._h))
+
     # ---- hyperparameters (entity_state.hpp:41-49) -----------------------------
     def set_cluster_hp(self, hp):
         _lib.check(_lib.load().msb_state_set_cluster_hp(self._h, b"alpha", float(hp["alpha"])))

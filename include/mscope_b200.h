@@ -144,6 +144,10 @@ MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv);
  * assignments and the suffstats (the reference re-reads its borrowed host rows on every pass,
  * recarray/dataview.hpp:194-217; here the pass over host rows is upload + refresh + sweep). */
 MSB_API int msb_state_refresh(msb_state *st);
+/* optional, right after msb_dataview_upload: convert the new records on the copy stream into a second column
+ * buffer while the compute stream is still sweeping the current one; the next msb_state_refresh then only swaps
+ * the buffers (no conversion, no wait on the compute stream).  A no-op when the fused conversion does not apply. */
+MSB_API int msb_state_prefetch(msb_state *st);
 
 MSB_API int msb_state_set_hp(msb_state *st, size_t feature, const char *key, const double *v, size_t count);
 MSB_API int msb_state_get_hp(msb_state *st, size_t feature, const char *key, double *v, size_t count);

@@ -611,3 +611,41 @@ def test_async_assignments_copy_matches_blocking(ctx, oracle):
     st.assignments_wait()
     assert np.array_equal(bufs[3 & 1], prev)
     st.close()
+
+
+@pytest.mark.parametrize("mask_frac", [0.0, 0.05])
+def test_prefetched_conversion_swaps_column_buffers_correctly(ctx, oracle, mask_frac):
+    # upload + prefetch of the next dataset run on the copy stream while the compute stream still scores the
+    # current one; refresh then swaps the two column buffers (masks included: the tables-only kernel choice can
+    # change between buffers).  Scores must follow the data that is current in each pass.
+    descs = FAMILIES["mixed"]
+    n, k = 30000, 6
+    st, view_a, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=43, mask_frac=mask_frac)
+    arr_b, _ = cb.synth.make_dataset(descs, n, k, seed=44, mask_frac=0.0)   # B is never masked
+    view_b = cb.numpy_dataview(arr_b)
+    raws = {"a": [np.ascontiguousarray(x) if x is not None else None for x in view_a.raw()],
+            "b": [np.ascontiguousarray(x) if x is not None else None for x in view_b.raw()]}
+    if raws["a"][1] is not None:
+        raws["b"][1] = np.zeros_like(raws["a"][1])
+    views = {"a": view_a, "b": view_b}
+    dev = view_a.to_device(ctx)
+    lp = ol.logprior(counts, 1.0)
+    want = {c: oracle.score_rows(descs, hp, ss, lp, views[c]) for c in "ab"}
+    cur = "a"
+    for nxt in ["b", "a", "b", "b", "a"]:
+        dev.upload(*raws[nxt]); st.prefetch()              # next pass's data, concurrent with what follows
+        _, S = st.score_rows()                             # still the CURRENT data
+        assert np.max(rel_err(S, want[cur])) < RTOL
+        st.refresh()                                       # swap: nxt becomes current
+        cur = nxt
+    # sweeps through the prefetch path on unchanged data: identical to a state that never re-read its rows
+    st2, _, _, gids2, _, _, _ = make_state(ctx, oracle, descs, n, k, seed=43, mask_frac=mask_frac)
+    for it in range(3):
+        dev.upload(*raws["a"]); st.prefetch()
+        st.refresh()
+        st.sweep(seed=8, sweep=it, wait=False)
+        st2.sweep(seed=8, sweep=it)
+        assert np.array_equal(st.assignments(), st2.assignments())
+        for g, g2 in zip(gids, gids2):
+            assert st.groupsize(g) == st2.groupsize(g2)
+    st.close(); st2.close()
