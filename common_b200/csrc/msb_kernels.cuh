@@ -231,8 +231,10 @@ __global__ void colmax_u32_kernel(const uint32_t *__restrict__ col, size_t n, ui
 // ---------------------------------------------------------------------------
 __global__ void build_params_kernel(const FeatDev *__restrict__ feats, int nfeat, const double *__restrict__ hp,
                                     const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols,
-                                    int KT, size_t region_rows, float *__restrict__ params) {
+                                    int KT, size_t region_rows, float *__restrict__ params, int tail_g) {
+  // tail_g > 0: the columns of the last k-tile are replicated every tail_g floats (score kernel, ragged last tile)
   const int d = blockIdx.x, kt = blockIdx.y;
+  const bool rep = tail_g > 0 && kt == (int)gridDim.y - 1;
   const FeatDev f = feats[d];
   if (f.rows == 0) return;
   float *chunk = params + ((size_t)kt * region_rows + f.rowoff) * KT;
@@ -240,7 +242,7 @@ __global__ void build_params_kernel(const FeatDev *__restrict__ feats, int nfeat
   const int total = (int)f.rows * KT;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int xr = i / KT, kl = i - xr * KT;
-    const int col = kt * KT + kl;
+    const int col = kt * KT + (rep ? kl % tail_g : kl);
     float v = 0.f;
     if (col < ncols) {
       const double *gss = ss + f.ss_off + (size_t)col2slot[col] * f.ss_w;

@@ -14,6 +14,8 @@
 //     in the feature loop;
 //   * the N x K result is written once with 128*V-byte coalesced stores.
 #pragma once
+#include <type_traits>
+
 #include "msb_kernels.cuh"
 
 namespace msb {
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
 score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restrict__ params, size_t region_rows,
              uint32_t stage_bytes, int S, const float *__restrict__ base, float *__restrict__ scores, size_t ld,
              size_t row_org, size_t row_lo, size_t row_hi, const double *__restrict__ hp,
-             const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols, int ktiles) {
+             const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols, int ktiles, int tail_g) {
   constexpr int KT = 32 * V;
   constexpr int RL = RW / 32;
   constexpr int RB = NW * RW;                                   // rows per block
@@ -271,6 +273,12 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
   if (tid == 0)
     for (int d = 0; d < S && d < nfeat; d++) issue(d, d);
 
+  // Ragged last k-tile (V = 1, tables only): when it holds tail_g <= 16 groups, build_params_kernel replicates its
+  // table columns 32 / tail_g times across the 32-float chunk row, and lane l owns group l % tail_g of the rows
+  // r = l / tail_g (mod 32 / tail_g): one conflict-free wavefront then serves 32 / tail_g rows instead of one
+  // (C2: K = 200 = 6 x 32 + 8, the 7th tile costs ~45 % of a full one).  acc[s][0] holds row (32 / tail_g) s + l / tail_g.
+  const bool tail = V == 1 && TABLES_ONLY && tail_g > 0 && kt == ktiles - 1;
+
   float acc[RW][V];
 #pragma unroll
   for (int r = 0; r < RW; r++)
@@ -291,7 +299,21 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
     for (int j = 0; j < RL; j++)
       slow[j] = (!TABLES_ONLY && t.has_slow) ? reinterpret_cast<const uint32_t *>(st + X_BYTES)[warp * RL + j] : 0u;
 
-    if (TABLES_ONLY || t.kind != KIND_NICH) {
+    if (V == 1 && TABLES_ONLY && tail) {
+      const uint32_t chunk_s = smem_u32(chunk);
+      auto tail_lookup = [&](auto rtag) {
+        constexpr int R = decltype(rtag)::value;  // rows per wavefront
+        const uint32_t *xw = reinterpret_cast<const uint32_t *>(st) + warp * RW + lane / (32 / R);
+#pragma unroll
+        for (int q = 0; q < RW / R; q++) {
+          float tv[1];
+          lds_vec<1>(tv, chunk_s + xw[q * R] * (uint32_t)(KT * sizeof(float)));
+          acc[q][0] += tv[0];
+        }
+      };
+      if (tail_g == 8) tail_lookup(std::integral_constant<int, 4>{});
+      else tail_lookup(std::integral_constant<int, 2>{});
+    } else if (TABLES_ONLY || t.kind != KIND_NICH) {
       const uint32_t chunk_s = smem_u32(chunk);
 #pragma unroll
       for (int r4 = 0; r4 < RW / 4; r4++) {
@@ -419,6 +441,40 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
   }
 
   // epilogue: + log(pseudocount) (group_manager.hpp:274-283)
+  if (V == 1 && TABLES_ONLY && tail) {
+    auto tail_epilogue = [&](auto rtag) {
+      constexpr int R = decltype(rtag)::value;  // rows per wavefront; this lane: rows R q + sub, group g
+      constexpr int G = 32 / R;
+      const int sub = lane / G, g = lane % G;
+      const float bg = base[(size_t)kt * KT + g];
+      if constexpr (!BLOCKED) {
+#pragma unroll
+        for (int q = 0; q < RW / R; q++) {
+          const size_t row = row0 + (size_t)q * R + sub;
+          if (row >= row_lo && row < row_hi) scores[(row - row_org) * ld + (size_t)kt * KT + g] = acc[q][0] + bg;
+        }
+      } else {
+        __syncthreads();  // every warp has finished reading the stages
+        float *tile = reinterpret_cast<float *>(stages) + (size_t)warp * 32 * (KT + 1);
+#pragma unroll
+        for (int j = 0; j < RL; j++) {
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < G; q++) tile[(q * R + sub) * (KT + 1) + g] = acc[j * G + q][0] + bg;
+          __syncwarp();
+          const size_t rb = (row0 - row_org) / 32 + j;
+          if (row0 + (size_t)j * 32 < row_hi) {
+            float *dst = scores + (rb * ld + (size_t)kt * KT) * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < G; c++) dst[(size_t)c * 32] = tile[lane * (KT + 1) + c];
+          }
+        }
+      }
+    };
+    if (tail_g == 8) tail_epilogue(std::integral_constant<int, 4>{});
+    else tail_epilogue(std::integral_constant<int, 2>{});
+    return;
+  }
   VecF<V> b;
   b.load(base + (size_t)kt * KT + lane * V);
   if constexpr (!BLOCKED) {  // 128 V-byte coalesced row-major stores

@@ -149,6 +149,7 @@ struct msb_state {
   std::vector<float *> d_niwW, d_niwBias, d_niwCoef, d_niwB;
   size_t niw_cols_cap = 0;
   // last score
+  int tail_g = 0;  // replication width of the last k-tile's table columns (build_params), 0 = none
   int cfg = 1, V = 2; size_t ld = 0, last_rows = 0, last_cols = 0;
   bool last_blocked = false;
   size_t last_skip = 0;  // rows between the score buffer's origin (row_origin) and the first valid row
@@ -1078,8 +1079,11 @@ static int build_params(msb_state *st) {
   if (st->has_scalar) {
     MSB_TRY(ensure(&st->d_params, &st->params_cap, ktiles * st->region_rows * KT));
     dim3 grid((unsigned)st->D, (unsigned)ktiles);
+    // ragged last k-tile with at most 16 groups (V = 1, tables only): replicated columns, several rows per lookup
+    const size_t tail_cols = K - (ktiles - 1) * KT;
+    st->tail_g = (st->V == 1 && st->tables_only && tail_cols <= 16 && !getenv("MSB_NO_TAIL_TILE")) ? (tail_cols <= 8 ? 8 : 16) : 0;
     LAUNCH(ctx, build_params_kernel, grid, 256, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot, (int)K,
-           (int)KT, st->region_rows, st->d_params);
+           (int)KT, st->region_rows, st->d_params, st->tail_g);
     MSB_TRY(ensure(&st->d_base_score, &st->base_score_cap, st->ld));
     CU_TRY(cudaMemcpyAsync(st->d_base_score, st->d_base, sizeof(float) * st->ld, cudaMemcpyDeviceToDevice, ctx->stream));
     if (st->has_nich) {  // fold sum_d c0 of the nich features into the score kernel's base[]
@@ -1135,7 +1139,7 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
     const size_t grid = (size_t)cdiv(nrows, RB) * ktiles;
     if (grid >= (1ull << 31)) return fail(MSB_ERR_UNSUPPORTED, "score grid too large: sweep a smaller row range");
 #define MSB_SCORE_ARGS st->d_feats_scalar, (int)st->n_scalar, st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base_score, \
-                       scores, st->ld, org, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K, (int)ktiles
+                       scores, st->ld, org, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K, (int)ktiles, st->tail_g
 #define MSB_SCORE_LAUNCH(V_, RW_, NW_)                                                                         \
     do {                                                                                                       \
       if (blocked && st->tables_only) LAUNCH(ctx, (score_kernel<V_, RW_, NW_, true, true>), (unsigned)grid, NW_ * 32, smem, MSB_SCORE_ARGS);        \

@@ -649,3 +649,24 @@ def test_prefetched_conversion_swaps_column_buffers_correctly(ctx, oracle, mask_
         for g, g2 in zip(gids, gids2):
             assert st.groupsize(g) == st2.groupsize(g2)
     st.close(); st2.close()
+
+
+@pytest.mark.parametrize("k", [3, 8, 12, 33, 40, 45, 70])
+@pytest.mark.parametrize("big", [False, True])
+def test_ragged_last_group_tile(ctx, oracle, k, big):
+    # tables-only states with V = 1: a last k-tile of <= 8 (<= 16) groups is scored 4 (2) rows per lookup from
+    # replicated table columns; both output layouts (row-major API, blocked sweep)
+    descs = [cb.dd(256), cb.bb, cb.dd(7)] if big else [cb.bb, cb.dd(7), cb.bb]
+    n = 2111
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=101, extra_empty=1)
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
+    _, S = st.score_rows()
+    assert np.max(rel_err(S, want)) < RTOL
+    _, S1 = st.score_rows(517, 1300)
+    assert np.array_equal(S1, S[517:1300])
+    st.sweep(seed=4, sweep=0)
+    Sb = st.read_last_scores()
+    assert np.array_equal(Sb, S)            # the blocked layout holds the same bits
+    u = np.array([oracle.philox_u01(4, i, 0) for i in range(n)], np.float32)
+    assert np.array_equal(np.searchsorted(gids, st.assignments()).astype(np.int32), oracle.sample_rows(Sb, u))
+    st.close()
