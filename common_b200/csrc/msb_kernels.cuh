@@ -249,6 +249,8 @@ __global__ void build_params_kernel(const FeatDev *__restrict__ feats, int nfeat
       if (f.kind == KIND_TABLE) {
         if ((uint32_t)xr < f.ncat)
           v = (float)(f.family == FAM_BB ? bb_score(fhp, gss, xr) : dd_score(fhp, f.asum, gss, (uint32_t)xr));
+      } else if (f.kind == KIND_GP && f.family == FAM_BNB) {
+        if ((uint32_t)xr < f.ncat) v = (float)bnb_score(bnb_post(fhp, gss), (double)xr);
       } else if (f.kind == KIND_GP) {
         const GpPost p = gp_post(fhp, gss);
         if ((uint32_t)xr < f.ncat) v = (float)gp_score(p, (double)xr);
@@ -296,7 +298,7 @@ __global__ void score_direct_kernel(const FeatDev *__restrict__ feats, int nfeat
       } else if (f.kind == KIND_GP) {
         const uint32_t x = ((const uint32_t *)f.col)[row];
         if (x == GP_SENTINEL) continue;
-        s += gp_score(gp_post(fhp, gss), (double)x);
+        s += f.family == FAM_BNB ? bnb_score(bnb_post(fhp, gss), (double)x) : gp_score(gp_post(fhp, gss), (double)x);
       } else if (f.kind == KIND_NICH) {
         const float x = ((const float *)f.col)[row];
         if (x != x) continue;
@@ -411,6 +413,11 @@ __global__ void score_data_kernel(const FeatDev *__restrict__ feats, int nfeat, 
   } else if (f.family == FAM_DD) {
     r = lgamma(f.asum) - lgamma(f.asum + g[0]);
     for (uint32_t c = 0; c < f.dim; c++) r += lgamma(h[c] + g[1 + c]) - lgamma(h[c]);
+  } else if (f.family == FAM_BNB) {
+    // (count, sum) do not determine sum_i [lgamma(r + x_i) - lgamma(r) - lgamma(x_i + 1)]: like the family's own
+    // two-field group this returns the part that depends on the partition and on (alpha, beta)
+    const double a = h[0] + h[2] * g[0], b = h[1] + g[1];
+    r = lbeta_d(a, b) - lbeta_d(h[0], h[1]);
   } else if (f.kind == KIND_GP) {  // prior Gamma(alpha, rate inv_beta); ss = count, sum, sum log x!
     const double a = h[0] + g[1], b = h[1] + g[0];
     r = lgamma(a) - lgamma(h[0]) + h[0] * log(h[1]) - a * log(b) - g[2];
@@ -807,6 +814,12 @@ __global__ void update_kernel(const FeatDev *__restrict__ feats, int nfeat, cons
     } else if (f.kind == KIND_GP) {  // ss = [count, sum, log_prod]
       const uint32_t x = ((const uint32_t *)f.col)[row];
       if (x == GP_SENTINEL) continue;
+      if (f.family == FAM_BNB) {  // ss = [count, sum]
+        const double xb = (double)x;
+        if (a >= 0) { double *p = blk + (size_t)a * 2; atomic_add_f64(p, -1.0); atomic_add_f64(p + 1, -xb); }
+        if (b >= 0) { double *p = blk + (size_t)b * 2; atomic_add_f64(p, 1.0); atomic_add_f64(p + 1, xb); }
+        continue;
+      }
       const double xd = (double)x, lf = lgamma(xd + 1.0);
       if (a >= 0) { double *p = blk + (size_t)a * 3; atomic_add_f64(p, -1.0); atomic_add_f64(p + 1, -xd); atomic_add_f64(p + 2, -lf); }
       if (b >= 0) { double *p = blk + (size_t)b * 3; atomic_add_f64(p, 1.0); atomic_add_f64(p + 1, xd); atomic_add_f64(p + 2, lf); }
@@ -974,6 +987,9 @@ __global__ void value_op_kernel(int family, uint32_t dim, int op, const double *
       for (uint32_t i = 0; i < dim; i++) asum += hp[i];
       *score = xi < dim ? (float)dd_score(hp, asum, ss, xi) : CUDART_NAN_F;
     } else if (xi < dim) { ss[0] += sgn; ss[1 + xi] += sgn; }
+  } else if (family == FAM_BNB) {
+    if (op == 0) *score = (float)bnb_score(bnb_post(hp, ss), x[0]);
+    else { ss[0] += sgn; ss[1] += sgn * x[0]; }
   } else if (family == FAM_GP) {
     if (op == 0) *score = (float)gp_score(gp_post(hp, ss), x[0]);
     else { ss[0] += sgn; ss[1] += sgn * x[0]; ss[2] += sgn * lgamma(x[0] + 1.0); }

@@ -74,6 +74,7 @@ __host__ __device__ __forceinline__ float philox_u01(uint64_t seed, uint64_t row
 //   bb   ss = [heads, tails]                 hp = [alpha, beta]
 //   dd   ss = [count_sum, counts[dim]]       hp = alphas[dim]   (asum passed in)
 //   gp   ss = [count, sum, log_prod]         hp = [alpha, inv_beta]
+//   bnb  ss = [count, sum]                   hp = [alpha, beta, r]
 //   nich ss = [count, sum x, sum x^2]        hp = [mu, kappa, sigmasq, nu]
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double bb_score(const double *hp, const double *ss, int x) {
@@ -94,6 +95,22 @@ __device__ __forceinline__ GpPost gp_post(const double *hp, const double *ss) {
 }
 __device__ __forceinline__ double gp_score(const GpPost &p, double x) {
   return lgamma(p.a + x) - lgamma(x + 1.0) + p.ca - x * p.l1pb;
+}
+// bnb (beta-negative-binomial): hp = [alpha, beta, r], ss = [count, sum]; posterior Beta(a, b) over the success
+// probability with a = alpha + r count, b = beta + sum; predictive
+//   lgamma(r + x) - lgamma(r) - lgamma(x + 1) + lbeta(a + r, b + x) - lbeta(a, b)
+struct BnbPost { double ar, b, r, c; };  // ar = a + r, c = -lgamma(r) - lbeta(a, b) + lgamma(a + r)
+__device__ __forceinline__ BnbPost bnb_post(const double *hp, const double *ss) {
+  BnbPost p;
+  const double a = hp[0] + hp[2] * ss[0];
+  p.b = hp[1] + ss[1];
+  p.r = hp[2];
+  p.ar = a + p.r;
+  p.c = -lgamma(p.r) - (lgamma(a) + lgamma(p.b) - lgamma(a + p.b)) + lgamma(p.ar);
+  return p;
+}
+__device__ __forceinline__ double bnb_score(const BnbPost &p, double x) {
+  return lgamma(p.r + x) - lgamma(x + 1.0) + lgamma(p.b + x) - lgamma(p.ar + p.b + x) + p.c;
 }
 struct NichPost { double mu, s, c1, c0; };  // score = c0 + c1 * log1p(((x - mu) s)^2)
 __device__ __forceinline__ NichPost nich_post(const double *hp, const double *ss) {

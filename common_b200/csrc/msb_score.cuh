@@ -204,7 +204,8 @@ sample_tile_kernel(const float *__restrict__ scores, size_t ld, size_t skip, int
 // gp count beyond the lookup table: fp64 closed form straight from the suffstats.  Kept out of line so
 // that its fp64 register pressure stays off the hot loop.
 __device__ __noinline__ float gp_overflow_score(const FeatDev *f, const double *hp, const double *ss, int slot, double xv) {
-  return (float)gp_score(gp_post(hp + f->hp_off, ss + f->ss_off + (size_t)slot * f->ss_w), xv);
+  const double *h = hp + f->hp_off, *g = ss + f->ss_off + (size_t)slot * f->ss_w;
+  return f->family == FAM_BNB ? (float)bnb_score(bnb_post(h, g), xv) : (float)gp_score(gp_post(h, g), xv);
 }
 
 // Output layouts of the N x K score matrix:

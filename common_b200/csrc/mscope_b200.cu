@@ -355,6 +355,7 @@ extern "C" MSB_API int msb_dataview_get_row(msb_dataview *dv, size_t idx, void *
 static size_t hp_size(const msb_model_desc &m) {
   switch (m.family) {
     case MSB_FAMILY_BB: case MSB_FAMILY_GP: return 2;
+    case MSB_FAMILY_BNB: return 3;
     case MSB_FAMILY_NICH: return 4;
     case MSB_FAMILY_DD: return m.dim;
     case MSB_FAMILY_NIW: return (size_t)m.dim * m.dim + m.dim + 2;
@@ -363,7 +364,7 @@ static size_t hp_size(const msb_model_desc &m) {
 }
 static size_t ss_size(const msb_model_desc &m) {
   switch (m.family) {
-    case MSB_FAMILY_BB: return 2;
+    case MSB_FAMILY_BB: case MSB_FAMILY_BNB: return 2;
     case MSB_FAMILY_GP: case MSB_FAMILY_NICH: return 3;
     case MSB_FAMILY_DD: return (size_t)m.dim + 1;
     case MSB_FAMILY_NIW: return (size_t)m.dim * m.dim + m.dim + 1;
@@ -375,7 +376,7 @@ extern "C" MSB_API size_t msb_model_ss_size(const msb_model_desc *m) { return m 
 
 static int check_model(const msb_model_desc &m, size_t d) {
   switch (m.family) {
-    case MSB_FAMILY_BB: case MSB_FAMILY_GP: case MSB_FAMILY_NICH: return MSB_OK;
+    case MSB_FAMILY_BB: case MSB_FAMILY_BNB: case MSB_FAMILY_GP: case MSB_FAMILY_NICH: return MSB_OK;
     case MSB_FAMILY_DD:
       if (m.dim == 0) return fail(MSB_ERR_INVALID, "no elements");  // distributions.hpp:429
       if (m.dim > 1024) return fail(MSB_ERR_UNSUPPORTED, "dd with more than 1024 categories is not built yet");
@@ -396,6 +397,11 @@ static int hp_field(const msb_model_desc &m, const std::string &key, size_t *off
     case MSB_FAMILY_BB:
       if (key == "alpha") { *off = 0; *cnt = 1; return MSB_OK; }
       if (key == "beta") { *off = 1; *cnt = 1; return MSB_OK; }
+      break;
+    case MSB_FAMILY_BNB:  // distributions.hpp:29-32
+      if (key == "alpha") { *off = 0; *cnt = 1; return MSB_OK; }
+      if (key == "beta") { *off = 1; *cnt = 1; return MSB_OK; }
+      if (key == "r") { *off = 2; *cnt = 1; return MSB_OK; }
       break;
     case MSB_FAMILY_GP:
       if (key == "alpha") { *off = 0; *cnt = 1; return MSB_OK; }
@@ -426,6 +432,10 @@ static int ss_field(const msb_model_desc &m, const std::string &key, size_t *off
     case MSB_FAMILY_BB:
       if (key == "heads") { *off = 0; *cnt = 1; return MSB_OK; }
       if (key == "tails") { *off = 1; *cnt = 1; return MSB_OK; }
+      break;
+    case MSB_FAMILY_BNB:  // distributions.hpp:34-36
+      if (key == "count") { *off = 0; *cnt = 1; return MSB_OK; }
+      if (key == "sum") { *off = 1; *cnt = 1; return MSB_OK; }
       break;
     case MSB_FAMILY_GP:
       if (key == "count") { *off = 0; *cnt = 1; return MSB_OK; }
@@ -480,6 +490,7 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
         f.kind = KIND_TABLE; f.ncat = m.dim; st->has_scalar = true; st->has_dd = true;
         f.coltype = m.dim + 1 <= 256 ? COL_U8 : (m.dim + 1 <= 65536 ? COL_U16 : COL_U32);
         break;
+      case MSB_FAMILY_BNB:  // a count family like gp: same lookup-table machinery, its own closed form
       case MSB_FAMILY_GP: f.kind = KIND_GP; f.coltype = COL_U32; f.ncat = 1; st->has_scalar = true; break;
       case MSB_FAMILY_NICH: f.kind = KIND_NICH; f.coltype = COL_F32; st->has_scalar = true; st->has_nich = true; break;
       case MSB_FAMILY_NIW: f.kind = KIND_NIW; f.coltype = COL_F32; st->has_niw = true; break;
@@ -493,6 +504,7 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
     const msb_model_desc &m = models[d];
     switch (m.family) {
       case MSB_FAMILY_BB: case MSB_FAMILY_GP: h[0] = h[1] = 1.0; break;
+      case MSB_FAMILY_BNB: h[0] = h[1] = h[2] = 1.0; break;  // models.pyx:200
       case MSB_FAMILY_NICH: h[0] = 0.0; h[1] = h[2] = h[3] = 1.0; break;
       case MSB_FAMILY_DD: for (uint32_t i = 0; i < m.dim; i++) h[i] = 1.0; st->feats[d].asum = (double)m.dim; break;
       case MSB_FAMILY_NIW:

@@ -49,6 +49,10 @@ def make_dataset(models, n, k_true, seed=73, stream=0, mask_frac=0.0, storage=No
             theta = prng.dirichlet(np.full(C, 0.5), size=k_true)
             x = _categorical(rng, theta, z)
             dt = np.int32
+        elif name == "bnb":
+            pk = prng.beta(2.0, 2.0, size=k_true) * 0.8 + 0.1
+            x = rng.negative_binomial(1, pk[z])
+            dt = np.uint32
         elif name == "gp":
             lam = prng.gamma(2.0, 4.0, size=k_true)
             x = rng.poisson(lam[z])

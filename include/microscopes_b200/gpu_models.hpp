@@ -47,6 +47,7 @@ inline field hp_field(const msb_model_desc &m, const std::string &key) {
   const size_t d = m.dim;
   switch (m.family) {
     case MSB_FAMILY_BB: if (key == "alpha") return {0, 1}; if (key == "beta") return {1, 1}; break;
+    case MSB_FAMILY_BNB: if (key == "alpha") return {0, 1}; if (key == "beta") return {1, 1}; if (key == "r") return {2, 1}; break;
     case MSB_FAMILY_GP: if (key == "alpha") return {0, 1}; if (key == "inv_beta") return {1, 1}; break;
     case MSB_FAMILY_NICH:
       if (key == "mu") return {0, 1}; if (key == "kappa") return {1, 1};
@@ -62,6 +63,7 @@ inline field ss_field(const msb_model_desc &m, const std::string &key) {
   const size_t d = m.dim;
   switch (m.family) {
     case MSB_FAMILY_BB: if (key == "heads") return {0, 1}; if (key == "tails") return {1, 1}; break;
+    case MSB_FAMILY_BNB: if (key == "count") return {0, 1}; if (key == "sum") return {1, 1}; break;
     case MSB_FAMILY_GP: if (key == "count") return {0, 1}; if (key == "sum") return {1, 1}; if (key == "log_prod") return {2, 1}; break;
     case MSB_FAMILY_NICH: if (key == "count") return {0, 1}; if (key == "mean") return {1, 1}; if (key == "count_times_variance") return {2, 1}; break;
     case MSB_FAMILY_DD: if (key == "count_sum") return {0, 1}; if (key == "counts") return {1, d}; break;
@@ -135,6 +137,7 @@ public:
     // defaults of microscopes/models.pyx:189,211,223,238,264-269
     switch (m.family) {
       case MSB_FAMILY_BB: case MSB_FAMILY_GP: hp_[0] = hp_[1] = 1.0; break;
+      case MSB_FAMILY_BNB: hp_[0] = hp_[1] = hp_[2] = 1.0; break;
       case MSB_FAMILY_NICH: hp_[1] = hp_[2] = hp_[3] = 1.0; break;
       case MSB_FAMILY_DD: for (auto &a : hp_) a = 1.0; break;
       case MSB_FAMILY_NIW:
@@ -196,7 +199,7 @@ public:
   common::runtime_type get_runtime_type() const override {
     switch (desc_.family) {  // the Value types of SURVEY.md section 2a
       case MSB_FAMILY_BB: return common::runtime_type(TYPE_B);
-      case MSB_FAMILY_GP: return common::runtime_type(TYPE_U32);
+      case MSB_FAMILY_BNB: case MSB_FAMILY_GP: return common::runtime_type(TYPE_U32);
       case MSB_FAMILY_NICH: return common::runtime_type(TYPE_F32);
       case MSB_FAMILY_DD: return common::runtime_type(TYPE_I32);
       default: return common::runtime_type(TYPE_F32, desc_.dim);  // distributions.hpp:498-505

@@ -87,10 +87,10 @@ typedef struct msb_runtime_type {
   int32_t vec;   /* 0 scalar, 1 vector */
 } msb_runtime_type;
 
-/* DISTRIB_FOR_EACH_DISTRIBUTION, distributions.hpp:58-64 (bnb reserved, not built yet) */
+/* DISTRIB_FOR_EACH_DISTRIBUTION, distributions.hpp:58-64, + NormalInverseWishart (distributions.hpp:449-509) */
 enum msb_family {
   MSB_FAMILY_BB = 0,   /* BetaBernoulli             hp: alpha beta            ss: heads tails */
-  MSB_FAMILY_BNB = 1,  /* reserved */
+  MSB_FAMILY_BNB = 1,  /* BetaNegativeBinomial      hp: alpha beta r          ss: count sum */
   MSB_FAMILY_GP = 2,   /* GammaPoisson              hp: alpha inv_beta        ss: count sum log_prod */
   MSB_FAMILY_NICH = 3, /* NormalInverseChiSq        hp: mu kappa sigmasq nu   ss: count mean count_times_variance */
   MSB_FAMILY_DD = 4,   /* DirichletDiscrete(dim)    hp: alphas[dim]           ss: count_sum counts[dim] */

@@ -48,6 +48,7 @@ double orc_cast(const uint8_t *px, int prim) {
 size_t orc_hp_size(const orc_model *m) {
   switch (m->family) {
     case ORC_BB: return 2;                                 /* alpha beta */
+    case ORC_BNB: return 3;                                /* alpha beta r */
     case ORC_GP: return 2;                                 /* alpha inv_beta */
     case ORC_NICH: return 4;                               /* mu kappa sigmasq nu */
     case ORC_DD: return m->dim;                            /* alphas[dim] */
@@ -58,6 +59,7 @@ size_t orc_hp_size(const orc_model *m) {
 size_t orc_ss_size(const orc_model *m) {
   switch (m->family) {
     case ORC_BB: return 2;                                 /* heads tails */
+    case ORC_BNB: return 2;                                /* count sum */
     case ORC_GP: return 3;                                 /* count sum log_prod */
     case ORC_NICH: return 3;                               /* count mean count_times_variance */
     case ORC_DD: return (size_t)m->dim + 1;                /* count_sum counts[dim] */
@@ -79,6 +81,13 @@ static double dd_score64(unsigned dim, const double *hp, const double *ss, doubl
   long xi = (long)x;
   if (xi < 0 || xi >= (long)dim) return NAN;
   return log((hp[xi] + ss[1 + xi]) / (asum + ss[0]));
+}
+/* bnb (beta-negative-binomial, hp = alpha beta r, ss = count sum): posterior Beta(a, b), a = alpha + r count,
+ * b = beta + sum; predictive lgamma(r+x) - lgamma(r) - lgamma(x+1) + lbeta(a + r, b + x) - lbeta(a, b) */
+static double bnb_score64(const double *hp, const double *ss, double x) {
+  double a = hp[0] + hp[2] * ss[0], b = hp[1] + ss[1], r = hp[2];
+  return lgamma(r + x) - lgamma(r) - lgamma(x + 1.0) + (lgamma(a + r) + lgamma(b + x) - lgamma(a + r + b + x)) -
+         (lgamma(a) + lgamma(b) - lgamma(a + b));
 }
 /* gp: a = alpha+sum, b = inv_beta+count:
  * lgamma(a+x) - lgamma(a) - lgamma(x+1) + a log b - (a+x) log(1+b) */
@@ -204,6 +213,10 @@ double orc_score_data(const orc_model *m, const double *hp, const double *ss) {
       for (unsigned i = 0; i < m->dim; i++) { asum += hp[i]; s += lgamma(hp[i] + ss[1 + i]) - lgamma(hp[i]); }
       return s + lgamma(asum) - lgamma(asum + ss[0]);
     }
+    case ORC_BNB: { /* the part (count, sum) determine: lbeta(a_n, b_n) - lbeta(alpha, beta) */
+      double a = hp[0] + hp[2] * ss[0], b = hp[1] + ss[1];
+      return lbeta(a, b) - lbeta(hp[0], hp[1]);
+    }
     case ORC_GP: { /* prior Gamma(alpha, rate inv_beta); ss = count, sum, log_prod = sum log x! */
       double a = hp[0] + ss[1], b = hp[1] + ss[0];
       return lgamma(a) - lgamma(hp[0]) + hp[0] * log(hp[1]) - a * log(b) - ss[2];
@@ -285,6 +298,13 @@ static float dd_score32(unsigned dim, const double *hp, const double *ss, double
   if (xi < 0 || xi >= (long)dim) return NAN;
   return logf(((float)hp[xi] + (float)ss[1 + xi]) / (asum + (float)ss[0]));
 }
+static float bnb_score32(const double *hp, const double *ss, double x) {
+  float a = (float)hp[0] + (float)hp[2] * (float)ss[0], b = (float)hp[1] + (float)ss[1], r = (float)hp[2], xf = (float)x;
+  float s = lgammaf(r + xf) - lgammaf(r) - lgammaf(xf + 1.f);
+  s += lgammaf(a + r) + lgammaf(b + xf) - lgammaf(a + r + b + xf);
+  s -= lgammaf(a) + lgammaf(b) - lgammaf(a + b);
+  return s;
+}
 static float gp_score32(const double *hp, const double *ss, double x) {
   float a = (float)hp[0] + (float)ss[1], b = (float)hp[1] + (float)ss[0];
   float xf = (float)x;
@@ -311,6 +331,7 @@ double orc_score_value(const orc_model *m, const double *hp, const double *ss, c
   switch (m->family) {
     case ORC_BB: return prec == 32 ? (double)bb_score32(hp, ss, x[0]) : bb_score64(hp, ss, x[0]);
     case ORC_DD: return prec == 32 ? (double)dd_score32(m->dim, hp, ss, x[0]) : dd_score64(m->dim, hp, ss, x[0]);
+    case ORC_BNB: return prec == 32 ? (double)bnb_score32(hp, ss, x[0]) : bnb_score64(hp, ss, x[0]);
     case ORC_GP: return prec == 32 ? (double)gp_score32(hp, ss, x[0]) : gp_score64(hp, ss, x[0]);
     case ORC_NICH: return prec == 32 ? (double)nich_score32(hp, ss, x[0]) : nich_score64(hp, ss, x[0]);
     case ORC_NIW: {
@@ -332,6 +353,7 @@ void orc_add_value(const orc_model *m, const double *hp, double *ss, const doubl
   switch (m->family) {
     case ORC_BB: ss[x[0] != 0.0 ? 0 : 1] += 1.0; break;
     case ORC_DD: ss[0] += 1.0; ss[1 + (long)x[0]] += 1.0; break;
+    case ORC_BNB: ss[0] += 1.0; ss[1] += x[0]; break;
     case ORC_GP:
       ss[0] += 1.0; ss[1] += x[0];
       ss[2] = rnd(ss[2] + rnd(prec == 32 ? (double)lgammaf((float)x[0] + 1.f) : lgamma(x[0] + 1.0), prec), prec);
@@ -361,6 +383,7 @@ void orc_remove_value(const orc_model *m, const double *hp, double *ss, const do
   switch (m->family) {
     case ORC_BB: ss[x[0] != 0.0 ? 0 : 1] -= 1.0; break;
     case ORC_DD: ss[0] -= 1.0; ss[1 + (long)x[0]] -= 1.0; break;
+    case ORC_BNB: ss[0] -= 1.0; ss[1] -= x[0]; break;
     case ORC_GP:
       ss[0] -= 1.0; ss[1] -= x[0];
       ss[2] = rnd(ss[2] - rnd(prec == 32 ? (double)lgammaf((float)x[0] + 1.f) : lgamma(x[0] + 1.0), prec), prec);

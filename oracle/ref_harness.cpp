@@ -120,6 +120,49 @@ struct gp_group : public models::group {
 };
 std::shared_ptr<models::group> gp_hypers::create_group(rng_t &) const { return std::make_shared<gp_group>(); }
 
+// ---- bnb ----------------------------------------------------------------------
+struct bnb_hypers : public models::hypers {
+  float alpha = 1.f, beta = 1.f;
+  unsigned r = 1;
+  float rf = 1.f;  // get_hp_mutator("r") hands out a float slot like the other fields; r is read from it
+  hyperparam_bag_t get_hp() const override { return ""; }
+  void set_hp(const hyperparam_bag_t &) override {}
+  void set_hp(const models::hypers &s) override { *this = static_cast<const bnb_hypers &>(s); }
+  value_mutator get_hp_mutator(const std::string &key) override {
+    if (key == "alpha") return value_mutator(&alpha);
+    if (key == "beta") return value_mutator(&beta);
+    if (key == "r") return value_mutator(&rf);
+    throw std::runtime_error("Unknown shared HP param key: " + key);
+  }
+  std::shared_ptr<models::group> create_group(rng_t &rng) const override;
+  std::string debug_str() const override { return "bnb"; }
+};
+struct bnb_group : public models::group {
+  unsigned count = 0, sum = 0;
+  void add_value(const models::hypers &, const value_accessor &v, rng_t &) override { ++count; sum += v.get<unsigned>(0); }
+  void remove_value(const models::hypers &, const value_accessor &v, rng_t &) override { --count; sum -= v.get<unsigned>(0); }
+  float score_value(const models::hypers &m, const value_accessor &v, rng_t &) const override {
+    const bnb_hypers &h = static_cast<const bnb_hypers &>(m);
+    const float r = h.rf, a = h.alpha + r * count, b = h.beta + sum, x = v.get<unsigned>(0);
+    float s = lgammaf(r + x) - lgammaf(r) - lgammaf(x + 1.f);
+    s += lgammaf(a + r) + lgammaf(b + x) - lgammaf(a + r + b + x);
+    s -= lgammaf(a) + lgammaf(b) - lgammaf(a + b);
+    return s;
+  }
+  float score_data(const models::hypers &, rng_t &) const override { return 0.f; }
+  void sample_value(const models::hypers &, value_mutator &, rng_t &) const override {}
+  suffstats_bag_t get_ss() const override { return ""; }
+  void set_ss(const suffstats_bag_t &) override {}
+  void set_ss(const models::group &g) override { *this = static_cast<const bnb_group &>(g); }
+  value_mutator get_ss_mutator(const std::string &key) override {
+    if (key == "count") return value_mutator(&count);
+    if (key == "sum") return value_mutator(&sum);
+    throw std::runtime_error("Unknown group SS param key: " + key);
+  }
+  std::string debug_str() const override { return "bnb"; }
+};
+std::shared_ptr<models::group> bnb_hypers::create_group(rng_t &) const { return std::make_shared<bnb_group>(); }
+
 // ---- nich ---------------------------------------------------------------------
 struct nich_hypers : public models::hypers {
   float mu = 0.f, kappa = 1.f, sigmasq = 1.f, nu = 1.f;
@@ -271,6 +314,7 @@ struct ref_model : public models::model {
   std::shared_ptr<models::hypers> create_hypers() const override {
     switch (m.family) {
       case ORC_BB: return std::make_shared<bb_hypers>();
+      case ORC_BNB: return std::make_shared<bnb_hypers>();
       case ORC_GP: return std::make_shared<gp_hypers>();
       case ORC_NICH: return std::make_shared<nich_hypers>();
       case ORC_DD: return std::make_shared<dd_hypers>(m.dim);
@@ -281,7 +325,7 @@ struct ref_model : public models::model {
   runtime_type get_runtime_type() const override {
     switch (m.family) {
       case ORC_BB: return runtime_type(TYPE_B);
-      case ORC_GP: return runtime_type(TYPE_U32);
+      case ORC_BNB: case ORC_GP: return runtime_type(TYPE_U32);
       case ORC_NICH: return runtime_type(TYPE_F32);
       case ORC_DD: return runtime_type(TYPE_I32);
       default: return runtime_type(TYPE_F32, m.dim);
@@ -312,6 +356,7 @@ built_state build(const orc_model *models, size_t D, const double *hp, const dou
     const double *p = hp + hpoff[d];
     switch (models[d].family) {
       case ORC_BB: set_f(h->get_hp_mutator("alpha"), p[0]); set_f(h->get_hp_mutator("beta"), p[1]); break;
+      case ORC_BNB: set_f(h->get_hp_mutator("alpha"), p[0]); set_f(h->get_hp_mutator("beta"), p[1]); set_f(h->get_hp_mutator("r"), p[2]); break;
       case ORC_GP: set_f(h->get_hp_mutator("alpha"), p[0]); set_f(h->get_hp_mutator("inv_beta"), p[1]); break;
       case ORC_NICH:
         set_f(h->get_hp_mutator("mu"), p[0]); set_f(h->get_hp_mutator("kappa"), p[1]);
@@ -335,6 +380,7 @@ built_state build(const orc_model *models, size_t D, const double *hp, const dou
       const double *s = ss + k * SS + ssoff[d];
       switch (models[d].family) {
         case ORC_BB: set_u(g->get_ss_mutator("heads"), s[0]); set_u(g->get_ss_mutator("tails"), s[1]); break;
+        case ORC_BNB: set_u(g->get_ss_mutator("count"), s[0]); set_u(g->get_ss_mutator("sum"), s[1]); break;
         case ORC_GP: set_u(g->get_ss_mutator("count"), s[0]); set_u(g->get_ss_mutator("sum"), s[1]); set_f(g->get_ss_mutator("log_prod"), s[2]); break;
         case ORC_NICH: set_u(g->get_ss_mutator("count"), s[0]); set_f(g->get_ss_mutator("mean"), s[1]); set_f(g->get_ss_mutator("count_times_variance"), s[2]); break;
         case ORC_DD: {

@@ -124,6 +124,16 @@ def main():
                               expect=scv, ref_vendor=refv,
                               source="vendor/stats.py:multivariate_t_loglik + scipy multivariate_t"))
 
+    # ---- bnb: beta-negative-binomial predictive (appended last so that the cases above keep their random draws)
+    for alpha, beta, r, count, total in [(1, 1, 1, 0, 0), (2.0, 3.0, 2, 10, 37), (0.7, 1.3, 5, 400, 2512), (1, 1, 1, 7, 0)]:
+        a, b = alpha + r * count, beta + total
+        for x in (0, 1, 6, 40, 250):
+            exp = float(st.betanbinom.logpmf(x, r, a, b))
+            alt = float(sp.gammaln(r + x) - sp.gammaln(r) - sp.gammaln(x + 1) + sp.betaln(a + r, b + x) - sp.betaln(a, b))
+            assert abs(exp - alt) < 1e-9 * max(1.0, abs(exp))
+            cases.append(dict(family="bnb", dim=0, hp=[alpha, beta, r], ss=[count, total], x=[x],
+                              expect=alt, source="scipy betanbinom.logpmf == gammaln/betaln closed form"))
+
     out = os.path.join(ROOT, "tests", "golden", "score_value.json")
     with open(out, "w") as f:
         json.dump(dict(generator="scripts/make_golden.py", cases=cases), f)

@@ -10,7 +10,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB = os.path.join(ORACLE_DIR, "libmsb_oracle.so")
 
 BB, BNB, GP, NICH, DD, NIW = range(6)
-FAMILY = {"bb": BB, "gp": GP, "nich": NICH, "dd": DD, "niw": NIW}
+FAMILY = {"bb": BB, "bnb": BNB, "gp": GP, "nich": NICH, "dd": DD, "niw": NIW}
 
 
 class OrcModel(C.Structure):
@@ -68,6 +68,7 @@ class Oracle(object):
         hp = dict(d.default_hyperparams(), **(hp or {}))
         n = d.name()
         if n in ("bb",): return np.array([hp["alpha"], hp["beta"]], np.float64)
+        if n == "bnb": return np.array([hp["alpha"], hp["beta"], hp["r"]], np.float64)
         if n == "gp": return np.array([hp["alpha"], hp["inv_beta"]], np.float64)
         if n == "nich": return np.array([hp["mu"], hp["kappa"], hp["sigmasq"], hp["nu"]], np.float64)
         if n == "dd": return np.asarray(hp["alphas"], np.float64)

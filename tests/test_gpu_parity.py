@@ -45,8 +45,9 @@ FAMILIES = {
     "bb": [cb.bb] * 5,
     "dd": [cb.dd(7), cb.dd(256), cb.dd(128)],
     "gp": [cb.gp] * 3,
+    "bnb": [cb.bnb] * 3,
     "nich": [cb.nich] * 4,
-    "mixed": [cb.bb, cb.gp, cb.nich, cb.dd(16), cb.bb, cb.nich],
+    "mixed": [cb.bb, cb.gp, cb.nich, cb.dd(16), cb.bb, cb.nich, cb.bnb],
 }
 
 
@@ -112,6 +113,8 @@ def test_suffstats_after_bulk_add_are_exact(ctx, oracle):
             elif name == "dd":
                 assert st.get_suffstats(d, g, "count_sum")[0] == ref[0]
                 assert np.array_equal(st.get_suffstats(d, g, "counts", w - 1), ref[1:])
+            elif name == "bnb":
+                assert st.get_suffstats(d, g, "count")[0] == ref[0] and st.get_suffstats(d, g, "sum")[0] == ref[1]
             elif name == "gp":
                 assert st.get_suffstats(d, g, "count")[0] == ref[0] and st.get_suffstats(d, g, "sum")[0] == ref[1]
                 assert abs(st.get_suffstats(d, g, "log_prod")[0] - ref[2]) <= 1e-9 * max(1, abs(ref[2]))
@@ -226,7 +229,7 @@ def test_sweep_assignments_and_counts_bit_exact(ctx, oracle, mask_frac):
                     assert st.get_suffstats(d, g, "heads")[0] == ss[c, off] and st.get_suffstats(d, g, "tails")[0] == ss[c, off + 1]
                 elif nm == "dd":
                     assert np.array_equal(st.get_suffstats(d, g, "counts", w - 1), ss[c, off + 1:off + w])
-                elif nm == "gp":
+                elif nm in ("gp", "bnb"):
                     assert st.get_suffstats(d, g, "count")[0] == ss[c, off] and st.get_suffstats(d, g, "sum")[0] == ss[c, off + 1]
                 elif nm == "nich":
                     assert st.get_suffstats(d, g, "count")[0] == ss[c, off]
@@ -247,7 +250,7 @@ def test_golden_vectors_through_the_value_abi(ctx):
     import ctypes as C
     from common_b200 import _lib
     lib = _lib.load()
-    fam = {"bb": _lib.FAMILY_BB, "dd": _lib.FAMILY_DD, "gp": _lib.FAMILY_GP, "nich": _lib.FAMILY_NICH, "niw": _lib.FAMILY_NIW}
+    fam = {"bb": _lib.FAMILY_BB, "bnb": _lib.FAMILY_BNB, "dd": _lib.FAMILY_DD, "gp": _lib.FAMILY_GP, "nich": _lib.FAMILY_NICH, "niw": _lib.FAMILY_NIW}
     with open(os.path.join(GOLD, "score_value.json")) as f:
         cases = json.load(f)["cases"]
     for c in cases:
@@ -575,7 +578,7 @@ def test_sweep_with_niw_features_draws_bit_exactly(ctx, oracle, descs):
     st.close()
 
 
-@pytest.mark.parametrize("name,cond", [("bb", 1.0), ("dd", 1.0), ("gp", 4.0), ("nich", 4.0), ("mixed", 4.0), ("niw", 50.0)])
+@pytest.mark.parametrize("name,cond", [("bb", 1.0), ("dd", 1.0), ("gp", 4.0), ("bnb", 4.0), ("nich", 4.0), ("mixed", 4.0), ("niw", 50.0)])
 def test_fp64_scores_within_1e12_of_the_oracle(ctx, oracle, name, cond):
     # north_star tolerance for fp64: 1e-12 relative.  `cond` is the conditioning of the closed form itself in
     # double (lgamma(a + x) - lgamma(a) and lgamma((nu+1)/2) - lgamma(nu/2) cancel; a d x d Cholesky for niw):

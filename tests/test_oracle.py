@@ -10,7 +10,7 @@ import common_b200 as cb
 import oracle_lib as ol
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-FAM = {"bb": ol.BB, "dd": ol.DD, "gp": ol.GP, "nich": ol.NICH, "niw": ol.NIW}
+FAM = {"bb": ol.BB, "bnb": ol.BNB, "dd": ol.DD, "gp": ol.GP, "nich": ol.NICH, "niw": ol.NIW}
 
 
 def _cases():
@@ -24,7 +24,9 @@ def test_golden_score_value_fp64(oracle):
         m = ol.OrcModel(FAM[c["family"]], c["dim"])
         got = oracle.score_value(m, c["hp"], c["ss"], c["x"], 64)
         # fp64 conditioning: lgamma(a+x) - lgamma(a) at a ~ 7.5e3 cancels ~1e4 (gp); d=64 Cholesky (niw)
-        cond = {"niw": 50.0, "gp": max(1.0, 1e-3 * (c["hp"][0] + c["ss"][1]))}.get(c["family"], 1.0)
+        cond = {"niw": 50.0, "gp": max(1.0, 1e-3 * (c["hp"][0] + c["ss"][1])),
+                "bnb": max(1.0, 1e-3 * (sum(c["hp"][:2]) + c["hp"][-1] * c["ss"][0] + c["ss"][1])) if c["family"] == "bnb" else 1.0
+                }.get(c["family"], 1.0)
         tol = 1e-12 * max(1.0, abs(c["expect"])) * cond
         assert abs(got - c["expect"]) <= tol, (c["family"], c["source"], got, c["expect"])
         if "ref_vendor" in c:  # the reference's own in-tree closed form
@@ -46,11 +48,14 @@ def test_golden_score_value_fp32_restatement(oracle):
         if c["family"] == "gp":
             a = c["hp"][0] + c["ss"][1] + c["x"][0]
             n = a * np.log(a + 2.0)
+        if c["family"] == "bnb":
+            a = c["hp"][0] + c["hp"][1] + c["hp"][2] * (c["ss"][0] + 1) + c["ss"][1] + c["x"][0]
+            n = 3 * a * np.log(a + 2.0)
         tol = 2e-5 * max(1.0, abs(c["expect"])) + 6e-7 * n
         assert abs(got - c["expect"]) <= tol, (c["family"], got, c["expect"])
 
 
-@pytest.mark.parametrize("desc", [cb.bb, cb.gp, cb.nich, cb.dd(7), cb.niw(3)])
+@pytest.mark.parametrize("desc", [cb.bb, cb.bnb, cb.gp, cb.nich, cb.dd(7), cb.niw(3)])
 def test_add_remove_roundtrip_and_direct_suffstats(oracle, desc):
     rng = np.random.default_rng(5)
     m = oracle.model(desc)
@@ -62,6 +67,7 @@ def test_add_remove_roundtrip_and_direct_suffstats(oracle, desc):
         if name == "bb": return [float(rng.integers(0, 2))]
         if name == "dd": return [float(rng.integers(0, 7))]
         if name == "gp": return [float(rng.poisson(6))]
+        if name == "bnb": return [float(rng.negative_binomial(1, 0.3))]
         if name == "nich": return [float(rng.normal(2, 1.5))]
         return rng.normal(0, 1, size=3).tolist()
 
@@ -74,6 +80,8 @@ def test_add_remove_roundtrip_and_direct_suffstats(oracle, desc):
         direct = [X.sum(), len(xs) - X.sum()]
     elif name == "dd":
         direct = [len(xs)] + np.bincount(X[:, 0].astype(int), minlength=7).tolist()
+    elif name == "bnb":
+        direct = [len(xs), X.sum()]
     elif name == "gp":
         from scipy.special import gammaln
         direct = [len(xs), X.sum(), gammaln(X[:, 0] + 1).sum()]
@@ -87,7 +95,7 @@ def test_add_remove_roundtrip_and_direct_suffstats(oracle, desc):
     # (iii) add then remove returns to the initial state (ints exactly, floats within tol)
     for x in reversed(xs):
         oracle.remove_value(m, hp, ss, x)
-    if name in ("bb", "dd"):
+    if name in ("bb", "dd", "bnb"):
         assert np.all(ss == 0)
     else:
         assert ss[0] == 0
@@ -230,3 +238,23 @@ def test_golden_score_assignment(oracle):
         f64 = oracle.score_assignment(c["assign"], c["alpha"], prec=64)   # closed form
         assert abs(f64 - c["expect"]) <= 1e-11 * max(1.0, abs(c["expect"]))
         assert abs(f32 - c["expect"]) <= 2e-6 * len(c["assign"]) ** 0.5 * max(1.0, abs(c["expect"]))
+
+
+def test_bnb_predictive_normalises_and_chains(oracle):
+    # sum_x exp(score) ~ 1 over a long range (heavy tail: Beta(3, 9.x) mixing), and the part of the marginal that
+    # (count, sum) determine equals the chain of predictives minus the data-only term sum_i log C(x_i + r - 1, x_i)
+    from scipy.special import gammaln
+    m = ol.OrcModel(ol.BNB, 0)
+    hp = np.array([2.0, 3.0, 2.0])
+    ss = np.array([4.0, 9.0])
+    tot = sum(np.exp(oracle.score_value(m, hp, ss, float(x))) for x in range(0, 20000))
+    assert abs(tot - 1.0) < 1e-6
+    rng = np.random.default_rng(3)
+    ss = np.zeros(2)
+    chain = data_term = 0.0
+    for _ in range(30):
+        x = float(rng.negative_binomial(2, 0.4))
+        chain += oracle.score_value(m, hp, ss, x)
+        data_term += gammaln(hp[2] + x) - gammaln(hp[2]) - gammaln(x + 1.0)
+        oracle.add_value(m, hp, ss, x)
+    assert abs(oracle.score_data(m, hp, ss) - (chain - data_term)) < 1e-9 * max(1.0, abs(chain))
