@@ -236,7 +236,7 @@ public:
 
   void set_alpha(double a) { b200::check(msb_state_set_cluster_hp(st_, "alpha", a)); }
   void set_hypers(size_t feature, const gpu_hypers &h) {
-    static const char *keys[6][4] = {{"alpha", "beta", 0, 0}, {0, 0, 0, 0}, {"alpha", "inv_beta", 0, 0},
+    static const char *keys[6][4] = {{"alpha", "beta", 0, 0}, {"alpha", "beta", "r", 0}, {"alpha", "inv_beta", 0, 0},
                                      {"mu", "kappa", "sigmasq", "nu"}, {"alphas", 0, 0, 0}, {"mu", "kappa", "psi", "nu"}};
     for (int i = 0; i < 4 && keys[descs_[feature].family][i]; i++) {
       const b200::field f = b200::hp_field(descs_[feature], keys[descs_[feature].family][i]);
@@ -274,6 +274,34 @@ public:
     b200::check(msb_state_assignments(st_, a.data(), n));
     return a;
   }
+  // ---- asynchronous / streaming forms ----------------------------------------------
+  // enqueue a sweep and return; sweep_wait() collects rows / moved / units
+  void sweep_async(uint64_t seed, uint64_t sweep_id, uint64_t row_id_offset = 0, bool defer_apply = false) {
+    msb_sweep_opts o;
+    std::memset(&o, 0, sizeof(o));
+    o.seed = seed; o.sweep = sweep_id; o.row_id_offset = row_id_offset;
+    o.defer_apply = defer_apply ? 1 : 0; o.flags = MSB_SWEEP_ASYNC;
+    size_t n = 0;
+    b200::check(msb_state_nentities(st_, &n));
+    b200::check(msb_state_sweep(st_, 0, n, &o, nullptr));
+  }
+  msb_sweep_result sweep_wait() { msb_sweep_result r; b200::check(msb_state_sweep_wait(st_, &r)); return r; }
+  // a pass over host-resident rows: upload (+ prefetch) on the copy stream, refresh swaps the column buffers
+  void upload(const uint8_t *data, const bool *mask = nullptr, bool prefetch = true) {
+    b200::check(msb_dataview_upload(dv_, data, mask));
+    if (prefetch) b200::check(msb_state_prefetch(st_));
+  }
+  void refresh() { b200::check(msb_state_refresh(st_)); }
+  void assignments_async(int64_t *pinned_out, size_t n) { b200::check(msb_state_assignments_async(st_, pinned_out, n)); }
+  void assignments_wait() { b200::check(msb_state_assignments_wait(st_)); }
+  // entity_state.hpp:74-86, group_manager.hpp:250-272
+  float score_assignment() { float v; b200::check(msb_state_score_assignment(st_, &v)); return v; }
+  float score_likelihood(size_t component, size_t gid) { float v; b200::check(msb_state_score_likelihood(st_, component, gid, &v)); return v; }
+  float score_likelihood() { float v; b200::check(msb_state_score_likelihood_all(st_, nullptr, 0, &v)); return v; }
+  // multi-GPU: flat fp64 delta buffer for ncclAllReduce(sum), then apply_deltas()
+  double *delta_buffer(size_t *count) { double *p; b200::check(msb_state_delta_buffer(st_, &p, count)); return p; }
+  void apply_deltas() { b200::check(msb_state_apply_deltas(st_)); }
+  void *stream() { return msb_ctx_stream(ctx_); }
   msb_state *handle() { return st_; }
 
 private:

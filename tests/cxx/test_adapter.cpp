@@ -139,6 +139,31 @@ int main(int argc, char **argv) {
     msb_sweep_result res = bs.sweep(73, 0);
     if (res.rows != N || res.units != N * K * 3) { std::printf("FAIL sweep result\n"); fails++; }
     std::printf("ok batch_scorer matches the per-value loop (%zu rows, %llu moved)\n", N, (unsigned long long)res.moved);
+
+    // ---- a pass over host rows from C++: upload + prefetch on the copy stream, refresh swaps the column buffers,
+    // the sweep is only enqueued, the assignments come back asynchronously --------------------------------------
+    const std::vector<int64_t> before = bs.assignments();
+    std::vector<int64_t> out(N, -7);
+    for (int pass = 1; pass <= 2; pass++) {
+      bs.upload(reinterpret_cast<const uint8_t *>(rows.data()));
+      bs.refresh();
+      bs.sweep_async(73, (uint64_t)pass);
+      bs.assignments_async(out.data(), N);
+      bs.assignments_wait();
+      const msb_sweep_result r2 = bs.sweep_wait();
+      const std::vector<int64_t> now = bs.assignments();
+      size_t same = 0;
+      for (size_t i = 0; i < N; i++) same += now[i] == out[i];
+      if (same != N || r2.rows != N) { std::printf("FAIL streaming pass %d: %zu of %zu assignments agree\n", pass, same, N); fails++; }
+    }
+    // marginal likelihoods through the adapters (entity_state.hpp:74-86, group_manager.hpp:250-272)
+    const float sa = bs.score_assignment(), sl = bs.score_likelihood();
+    double per = 0.0;
+    for (size_t k = 0; k < K; k++)
+      for (size_t d = 0; d < 3; d++) per += bs.score_likelihood(d, k);
+    EXPECT_NEAR(sl, per, 1e-4);
+    if (!(sa < 0.f) || !(sl < 0.f)) { std::printf("FAIL score_assignment %g score_likelihood %g\n", sa, sl); fails++; }
+    std::printf("ok streaming passes and marginal likelihoods from C++ (score_assignment %.3f, score_likelihood %.3f)\n", sa, sl);
   }
   if (fails) { std::printf("%d failure(s)\n", fails); return 1; }
   std::printf("all ok\n");
