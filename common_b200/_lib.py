@@ -100,6 +100,7 @@ _PROTOS = {
     "msb_state_score_assignment": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "msb_sample_discrete_log": (C.c_int, [_P, _P, _SZ, _SZ, _SZ, _P, _P]),
     "msb_philox_uniforms": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _SZ, _P]),
+    "msb_selftest_expf": (C.c_int, [_P, _P, _SZ, _P]),
     "msb_selftest_division": (C.c_int, [_P, C.c_uint64, _SZ, C.POINTER(C.c_uint64)]),
     "msb_state_sweep": (C.c_int, [_P, _SZ, _SZ, C.POINTER(SweepOpts), C.POINTER(SweepResult)]),
     "msb_state_sweep_wait": (C.c_int, [_P, C.POINTER(SweepResult)]),

@@ -741,6 +741,12 @@ __global__ void sample_blocked_kernel(const float *__restrict__ scores, size_t l
   if (out_slot) out_slot[i] = col2slot ? col2slot[pick] : pick;
 }
 
+// y[i] = msb_expf(x[i]): device self-test against the checker's separately written copy
+__global__ void selftest_expf_kernel(const float *__restrict__ x, size_t n, float *__restrict__ y) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = msb_expf(x[i]);
+}
+
 // q[i] = (a[i] / b[i] by Markstein's sequence) != __fdiv_rn(a[i], b[i]) counted: device self-test of dart_walk's
 // division on pseudo-random operands p in [2^-100, 1], acc in [1, 2^24) (plus exact zeros)
 __global__ void selftest_division_kernel(uint64_t seed, size_t n, unsigned long long *mismatches) {

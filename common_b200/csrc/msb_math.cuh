@@ -40,10 +40,13 @@ __device__ __forceinline__ float msb_expf(float x) {
   p = __fmaf_rn(p, r2, r);
   p = __fadd_rn(p, 1.0f);
   const int k = __float_as_int(kbias) - 0x4B400000;
-  const int k1 = k / 2, k2 = k - k1;
-  const float a = __int_as_float((k1 + 127) << 23);
-  const float b = __int_as_float((k2 + 127) << 23);
-  const float y = __fmul_rn(__fmul_rn(p, a), b);
+  // p * 2^k with a single rounding: p is in (0.5, 2), so for kk = max(k, -125) the product p * 2^kk is a normal
+  // number and adding kk to the exponent field is exact; the remaining factor 2^(k - kk) (!= 1 only for results in
+  // the subnormal range) is one correctly rounded multiply.  Same bits as the checker's (p * 2^(k/2)) * 2^(k - k/2):
+  // both are exact up to that one final rounding.
+  const int kk = max(k, -125);
+  const float pk = __int_as_float(__float_as_int(p) + (kk << 23));
+  const float y = __fmul_rn(pk, __int_as_float((k - kk + 127) << 23));
   return x_in >= -104.0f ? y : (x_in != x_in ? x_in : 0.0f);
 }
 

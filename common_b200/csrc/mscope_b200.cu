@@ -1650,6 +1650,20 @@ extern "C" MSB_API int msb_philox_uniforms(msb_ctx *ctx, uint64_t seed, uint64_t
   return MSB_OK;
 }
 
+extern "C" MSB_API int msb_selftest_expf(msb_ctx *ctx, const float *x, size_t n, float *y) {
+  REQUIRE(ctx && x && y, "NULL argument");
+  if (!n) return MSB_OK;
+  CU_TRY(cudaSetDevice(ctx->device));
+  float *d = nullptr;
+  CU_TRY(cudaMalloc(&d, sizeof(float) * 2 * n));
+  CU_TRY(cudaMemcpyAsync(d, x, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, selftest_expf_kernel, cdiv(n, 256), 256, 0, d, n, d + n);
+  CU_TRY(cudaMemcpyAsync(y, d + n, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  return MSB_OK;
+}
+
 extern "C" MSB_API int msb_selftest_division(msb_ctx *ctx, uint64_t seed, size_t n, uint64_t *mismatches) {
   REQUIRE(ctx && mismatches, "NULL argument");
   CU_TRY(cudaSetDevice(ctx->device));

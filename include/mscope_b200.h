@@ -205,6 +205,9 @@ MSB_API int msb_sample_discrete_log(msb_ctx *ctx, const float *scores, size_t nr
 /* the uniform the sweep draws for (seed, global row id, sweep): Philox4x32-10 */
 MSB_API int msb_philox_uniforms(msb_ctx *ctx, uint64_t seed, uint64_t sweep, uint64_t row_lo, size_t n, float *out);
 
+/* y[i] = the sampler's exp (sampler contract) of x[i], evaluated on the device: the checker's own copy
+ * must give the same bits */
+MSB_API int msb_selftest_expf(msb_ctx *ctx, const float *x, size_t n, float *y);
 /* device self-test of the sampler's division sequence (sampler contract): n pseudo-random operand
  * pairs, counts the results that differ from the IEEE division.  Must report 0. */
 MSB_API int msb_selftest_division(msb_ctx *ctx, uint64_t seed, size_t n, uint64_t *mismatches);

@@ -673,3 +673,17 @@ def test_ragged_last_group_tile(ctx, oracle, k, big):
     u = np.array([oracle.philox_u01(4, i, 0) for i in range(n)], np.float32)
     assert np.array_equal(np.searchsorted(gids, st.assignments()).astype(np.int32), oracle.sample_rows(Sb, u))
     st.close()
+
+
+def test_device_expf_is_bit_identical_to_the_checkers_copy(ctx, oracle):
+    from common_b200 import _lib
+    rng = np.random.default_rng(7)
+    x = np.concatenate([
+        rng.uniform(-104.5, 0.0, 400000), rng.uniform(-88.5, -86.0, 100000),      # the subnormal-result range too
+        rng.uniform(-110, 90, 50000), np.array([0.0, -0.0, -104.0, -103.9999, -87.3365, 88.0, 89.0, -1e30, np.nan, -np.inf]),
+        -np.logspace(-30, 2, 20000)]).astype(np.float32)
+    y = np.zeros_like(x)
+    _lib.check(_lib.load().msb_selftest_expf(ctx.handle, x.ctypes.data, x.size, y.ctypes.data))
+    want = np.array([oracle.expf(float(v)) for v in x], np.float32)
+    same = (y.view(np.uint32) == want.view(np.uint32)) | (np.isnan(y) & np.isnan(want))
+    assert same.all(), (x[~same][:5], y[~same][:5], want[~same][:5])
