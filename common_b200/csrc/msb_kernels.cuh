@@ -240,7 +240,7 @@ __global__ void build_params_kernel(const FeatDev *__restrict__ feats, int nfeat
   float *chunk = params + ((size_t)kt * region_rows + f.rowoff) * KT;
   const double *fhp = hp + f.hp_off;
   const int total = (int)f.rows * KT;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+  for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < total; i += blockDim.x * gridDim.z) {  // z: slices of one chunk
     const int xr = i / KT, kl = i - xr * KT;
     const int col = kt * KT + (rep ? kl % tail_g : kl);
     float v = 0.f;

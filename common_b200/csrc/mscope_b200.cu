@@ -1090,7 +1090,9 @@ static int build_params(msb_state *st) {
   const size_t ktiles = st->ld / KT;
   if (st->has_scalar) {
     MSB_TRY(ensure(&st->d_params, &st->params_cap, ktiles * st->region_rows * KT));
-    dim3 grid((unsigned)st->D, (unsigned)ktiles);
+    // enough blocks for a few waves even when D x ktiles is small: big chunks are sliced along z
+    const unsigned zs = (unsigned)std::max<size_t>(1, std::min<size_t>(8, st->max_chunk_rows * KT / 2048));
+    dim3 grid((unsigned)st->D, (unsigned)ktiles, zs);
     // ragged last k-tile with at most 16 groups (V = 1, tables only): replicated columns, several rows per lookup
     const size_t tail_cols = K - (ktiles - 1) * KT;
     st->tail_g = (st->V == 1 && st->tables_only && tail_cols <= 16 && !getenv("MSB_NO_TAIL_TILE")) ? (tail_cols <= 8 ? 8 : 16) : 0;
