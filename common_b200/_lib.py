@@ -86,6 +86,7 @@ _PROTOS = {
     "msb_state_groupsize": (C.c_int, [_P, _SZ, C.POINTER(_SZ)]),
     "msb_state_create_group": (C.c_int, [_P, C.POINTER(_SZ)]),
     "msb_state_delete_group": (C.c_int, [_P, _SZ]),
+    "msb_state_restore_group": (C.c_int, [_P, _SZ]),
     "msb_state_assignments": (C.c_int, [_P, _P, _SZ]),
     "msb_state_assignments_async": (C.c_int, [_P, _P, _SZ]),
     "msb_state_assignments_wait": (C.c_int, [_P]),

@@ -978,13 +978,18 @@ extern "C" MSB_API int msb_state_groupsize(msb_state *st, size_t gid, size_t *co
   *count = (size_t)st->h_counts[slot];
   return MSB_OK;
 }
-extern "C" MSB_API int msb_state_create_group(msb_state *st, size_t *gid) {
+// restore == true: *gid is the identifier to give the group (deserialisation, group_manager.hpp:92-105:
+// identifiers are preserved and gcount becomes 1 + the largest one seen)
+static int create_group_impl(msb_state *st, size_t *gid, bool restore) {
   REQUIRE(st && gid, "NULL argument");
+  if (restore) REQUIRE(st->gid2slot.find(*gid) == st->gid2slot.end(), "group id already in use");
   if (st->free_slots.empty()) return fail(MSB_ERR_NOMEM, "max_groups reached");
   CU_TRY(cudaSetDevice(st->ctx->device));
   const int slot = st->free_slots.back();
   st->free_slots.pop_back();
-  const size_t g = st->gcount++;  // group_manager.hpp:199
+  size_t g;
+  if (restore) { g = *gid; st->gcount = std::max(st->gcount, g + 1); }
+  else g = st->gcount++;  // group_manager.hpp:199
   st->gid2slot[g] = slot;
   st->slot2gid[slot] = (int64_t)g;
   st->cols_dirty = st->slot2gid_dirty = true;
@@ -1001,6 +1006,8 @@ extern "C" MSB_API int msb_state_create_group(msb_state *st, size_t *gid) {
   *gid = g;
   return MSB_OK;
 }
+extern "C" MSB_API int msb_state_create_group(msb_state *st, size_t *gid) { return create_group_impl(st, gid, false); }
+extern "C" MSB_API int msb_state_restore_group(msb_state *st, size_t gid) { return create_group_impl(st, &gid, true); }
 extern "C" MSB_API int msb_state_delete_group(msb_state *st, size_t gid) {
   REQUIRE(st, "NULL argument");
   int slot;

@@ -280,6 +280,71 @@ class state(object):
     def apply_deltas(self):
         _lib.check(_lib.load().msb_state_apply_deltas(self._h))
 
+    # ---- checkpoint / resume: the reference's wire format (microscopes/io/schema.proto) -----------------
+    _SS_KEYS = {"bb": ("heads", "tails"), "bnb": ("count", "sum"), "gp": ("count", "sum", "log_prod"),
+                "nich": ("count", "mean", "count_times_variance"), "dd": ("counts",), "niw": ("count", "sum_x", "sum_xxT")}
+
+    def _ss_counts(self, m, key):
+        p = m._param() or 0
+        return {"counts": p, "sum_x": p, "sum_xxT": p * p}.get(key, 1)
+
+    def get_component_hp_bag(self, component):
+        """hypers::get_hp (distributions.hpp:355-361): the component's Shared message"""
+        from . import wire
+        m = self._models[component]
+        hp = self.get_component_hp(component)
+        vals = {k: (np.asarray(v).ravel().tolist() if np.ndim(v) else v) for k, v in hp.items()}
+        return wire.encode(m.name() + ".Shared", vals)
+
+    def get_suffstats_bag(self, component, gid):
+        """group::get_ss (distributions.hpp:300-306): one group's Group message"""
+        from . import wire
+        m = self._models[component]
+        vals = {}
+        for key in self._SS_KEYS[m.name()]:
+            n = self._ss_counts(m, key)
+            v = self.get_suffstats(component, gid, key, n)
+            vals[key] = v.tolist() if n > 1 or key in ("counts", "sum_x", "sum_xxT") else float(v[0])
+        return wire.encode(m.name() + ".Group", vals)
+
+    def serialize(self):
+        """MixtureModelState{hypers[], groups = GroupManager{alpha, assignments[], groups[GroupData{id, data =
+        MixtureModelGroup{suffstats[]}}]}} -- group_manager.hpp:285-298 with the mixture model's group payload"""
+        from . import wire
+        D = len(self._models)
+        groups = [{"id": g, "data": wire.encode("MixtureModelGroup", {"suffstats": [self.get_suffstats_bag(d, g) for d in range(D)]})}
+                  for g in self.groups()]
+        gm = wire.encode("GroupManager", {"alpha": self.get_cluster_hp()["alpha"], "assignments": self.assignments().tolist(),
+                                          "groups": groups})
+        return wire.encode("MixtureModelState", {"hypers": [self.get_component_hp_bag(d) for d in range(D)], "groups": gm})
+
+    @classmethod
+    def deserialize(cls, ctx, models, view, blob, max_groups=None):
+        """the inverse: group identifiers, assignments, hypers and suffstats as saved (group_manager.hpp:71-105)"""
+        from . import wire
+        top = wire.decode("MixtureModelState", blob)
+        gm = wire.decode("GroupManager", top["groups"])
+        ngroups = len(gm["groups"])
+        st = cls(ctx, models, max_groups=max_groups or (ngroups + 8), cluster_hp={"alpha": gm["alpha"]})
+        for d, bag in enumerate(top["hypers"]):
+            m = st._models[d]
+            hp = wire.decode(m.name() + ".Shared", bag)
+            st.set_component_hp(d, {k: hp[k] for k in m.default_hyperparams()})
+        st.bind(view)
+        for g in gm["groups"]:
+            _lib.check(_lib.load().msb_state_restore_group(st._h, int(g["id"])))
+        a = np.asarray(gm["assignments"], np.int64)
+        assert a.size == st.nentities(), "the checkpoint holds another number of entities"
+        st.add_values(a)        # membership (and the suffstats the data implies) ...
+        for g in gm["groups"]:  # ... then the suffstats exactly as they were saved
+            bags = wire.decode("MixtureModelGroup", g["data"])["suffstats"]
+            for d, bag in enumerate(bags):
+                m = st._models[d]
+                ss = wire.decode(m.name() + ".Group", bag)
+                for key in cls._SS_KEYS[m.name()]:
+                    st.set_suffstats(d, int(g["id"]), key, ss[key])
+        return st
+
     def close(self):
         if self._h:
             _lib.load().msb_state_destroy(self._h)

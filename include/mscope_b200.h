@@ -164,6 +164,8 @@ MSB_API int msb_state_empty_groups(msb_state *st, size_t *gids, size_t cap, size
 MSB_API int msb_state_groupsize(msb_state *st, size_t gid, size_t *count);
 MSB_API int msb_state_create_group(msb_state *st, size_t *gid);
 MSB_API int msb_state_delete_group(msb_state *st, size_t gid); /* must be empty */
+/* deserialisation (group_manager.hpp:71-105): create the group with the identifier it had when it was saved */
+MSB_API int msb_state_restore_group(msb_state *st, size_t gid);
 
 /* assignments: gid per entity, -1 = unassigned (group_manager.hpp:133-137) */
 MSB_API int msb_state_assignments(msb_state *st, int64_t *out, size_t n);

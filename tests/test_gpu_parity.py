@@ -687,3 +687,28 @@ def test_device_expf_is_bit_identical_to_the_checkers_copy(ctx, oracle):
     want = np.array([oracle.expf(float(v)) for v in x], np.float32)
     same = (y.view(np.uint32) == want.view(np.uint32)) | (np.isnan(y) & np.isnan(want))
     assert same.all(), (x[~same][:5], y[~same][:5], want[~same][:5])
+
+
+def test_checkpoint_round_trip_through_the_wire_format(ctx, oracle):
+    # serialize -> MixtureModelState bytes (schema.proto:3-55 framing) -> a new state: identifiers, assignments,
+    # hypers and suffstats as saved; the restored state scores and sweeps like the original
+    descs = [cb.bb, cb.bnb, cb.gp, cb.nich, cb.dd(9), cb.niw(3)]
+    n, k = 900, 7
+    hp = {3: {"mu": 0.5, "kappa": 2.0, "sigmasq": 1.5, "nu": 3.0}, 4: {"alphas": np.linspace(0.5, 2.5, 9)}}
+    st, view, z, gids, _, _, _ = make_state(ctx, oracle, descs, n, k, seed=111, hp=hp, extra_empty=2)
+    st.sweep(seed=1, sweep=0)
+    st.delete_group(gids[-1])                 # identifiers are no longer contiguous ...
+    g_new = st.create_group()                 # ... and gcount has moved on
+    blob = st.serialize()
+    st2 = cb.state.deserialize(ctx, descs, view, blob)
+    assert st2.groups() == st.groups() and st2.empty_groups() == st.empty_groups()
+    assert np.array_equal(st2.assignments(), st.assignments())
+    assert st2.get_cluster_hp() == st.get_cluster_hp()
+    for g in st.groups():
+        assert st2.groupsize(g) == st.groupsize(g)
+    _, S = st.score_rows()
+    _, S2 = st2.score_rows()
+    assert np.max(rel_err(S2, S)) < 1e-6      # float32 fields on the wire
+    assert st2.create_group() == g_new + 1    # gcount = 1 + the largest identifier seen (group_manager.hpp:102-104)
+    assert st2.serialize()[:40] == blob[:40]
+    st.close(); st2.close()
