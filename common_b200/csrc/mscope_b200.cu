@@ -171,6 +171,17 @@ struct msb_state {
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
+// device scratch of one call: released on every return path (the CU_TRY / MSB_TRY early returns included)
+template <typename T> struct Scratch {
+  T *p = nullptr;
+  Scratch() = default;
+  Scratch(const Scratch &) = delete;
+  Scratch &operator=(const Scratch &) = delete;
+  ~Scratch() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t count) { return cudaMalloc(&p, sizeof(T) * std::max<size_t>(count, 1)); }
+  operator T *() const { return p; }
+};
+
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
@@ -1485,8 +1496,8 @@ extern "C" MSB_API int msb_state_score_rows_f64(msb_state *st, size_t row_lo, si
   const size_t nrows = row_hi - row_lo;
   if (!nrows || !scores) return MSB_OK;
   REQUIRE(ld >= K, "ld smaller than the number of groups");
-  double *d_out = nullptr;
-  CU_TRY(cudaMalloc(&d_out, sizeof(double) * nrows * K));
+  Scratch<double> d_out;
+  CU_TRY(d_out.alloc(nrows * K));
   LAUNCH(ctx, score_direct_kernel<double>, (unsigned)nrows, 128, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot,
          (int)K, st->d_base, d_out, K, row_lo, row_hi);
   for (size_t d = 0; d < st->D; d++) {
@@ -1498,7 +1509,6 @@ extern "C" MSB_API int msb_state_score_rows_f64(msb_state *st, size_t row_lo, si
   CU_TRY(cudaMemcpy2DAsync(scores, sizeof(double) * ld, d_out, sizeof(double) * K, sizeof(double) * K, nrows,
                            cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_out);
   return MSB_OK;
 }
 
@@ -1516,14 +1526,13 @@ extern "C" MSB_API int msb_state_read_last_scores(msb_state *st, float *out, siz
   if (!st->last_rows || !st->last_cols) return MSB_OK;
   CU_TRY(cudaSetDevice(st->ctx->device));
   if (st->last_blocked) {
-    float *tmp = nullptr;
-    CU_TRY(cudaMalloc(&tmp, sizeof(float) * st->last_rows * st->last_cols));
+    Scratch<float> tmp;
+    CU_TRY(tmp.alloc(st->last_rows * st->last_cols));
     LAUNCH(st->ctx, unblock_kernel, cdiv(st->last_rows * st->last_cols, 256), 256, 0, st->d_scores, st->ld, st->last_skip,
            st->last_rows, (int)st->last_cols, tmp);
     CU_TRY(cudaMemcpy2DAsync(out, sizeof(float) * ld_out, tmp, sizeof(float) * st->last_cols, sizeof(float) * st->last_cols,
                              st->last_rows, cudaMemcpyDeviceToHost, st->ctx->stream));
     CU_TRY(cudaStreamSynchronize(st->ctx->stream));
-    cudaFree(tmp);
     return MSB_OK;
   }
   CU_TRY(cudaMemcpy2DAsync(out, sizeof(float) * ld_out, st->d_scores + st->last_skip * st->ld, sizeof(float) * st->ld,
@@ -1563,8 +1572,8 @@ static int score_data_matrix(msb_state *st, std::vector<double> &h) {
   MSB_TRY(prepare_columns(st));
   MSB_TRY(sync_small(st));
   const size_t K = st->h_col2slot.size(), D = st->D;
-  double *d_out = nullptr;
-  CU_TRY(cudaMalloc(&d_out, sizeof(double) * K * D));
+  Scratch<double> d_out;
+  CU_TRY(d_out.alloc(K * D));
   LAUNCH(ctx, score_data_kernel, cdiv(K * D, 128), 128, 0, st->d_feats, (int)D, st->d_hp, st->d_ss, st->d_col2slot, (int)K, d_out);
   for (size_t d = 0; d < D; d++) {
     const FeatDev &f = st->feats[d];
@@ -1575,7 +1584,6 @@ static int score_data_matrix(msb_state *st, std::vector<double> &h) {
   h.resize(K * D);
   CU_TRY(cudaMemcpyAsync(h.data(), d_out, sizeof(double) * K * D, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_out);
   return MSB_OK;
 }
 
@@ -1614,13 +1622,12 @@ extern "C" MSB_API int msb_state_score_assignment(msb_state *st, float *out) {
   msb_ctx *ctx = st->ctx;
   CU_TRY(cudaSetDevice(ctx->device));
   MSB_TRY(prepare_columns(st));
-  double *d_out = nullptr;
-  CU_TRY(cudaMalloc(&d_out, sizeof(double) * 2));
+  Scratch<double> d_out;
+  CU_TRY(d_out.alloc(2));
   LAUNCH(ctx, score_assignment_kernel, 1, 256, 0, st->d_ss, st->d_col2slot, (int)st->h_col2slot.size(), st->d_assign, st->alpha, d_out);
   double h[2] = {0, 0};
   CU_TRY(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_out);
   if ((size_t)h[1] != st->n) return fail(MSB_ERR_STATE, "not assigned");  // group_manager.hpp:255,260
   *out = (float)h[0];
   return MSB_OK;
@@ -1633,16 +1640,16 @@ extern "C" MSB_API int msb_sample_discrete_log(msb_ctx *ctx, const float *scores
   REQUIRE(k > 0 && ld >= k && k < (1u << 30), "bad shape");
   if (!nrows) return MSB_OK;
   CU_TRY(cudaSetDevice(ctx->device));
-  float *d_s = nullptr, *d_u = nullptr; int32_t *d_o = nullptr;
-  CU_TRY(cudaMalloc(&d_s, sizeof(float) * nrows * ld));
-  CU_TRY(cudaMalloc(&d_u, sizeof(float) * nrows));
-  CU_TRY(cudaMalloc(&d_o, sizeof(int32_t) * nrows));
+  Scratch<float> d_s, d_u;
+  Scratch<int32_t> d_o;
+  CU_TRY(d_s.alloc(nrows * ld));
+  CU_TRY(d_u.alloc(nrows));
+  CU_TRY(d_o.alloc(nrows));
   CU_TRY(cudaMemcpyAsync(d_s, scores, sizeof(float) * nrows * ld, cudaMemcpyHostToDevice, ctx->stream));
   CU_TRY(cudaMemcpyAsync(d_u, uniforms, sizeof(float) * nrows, cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(ctx, sample_kernel, cdiv(nrows, 128), 128, 0, d_s, ld, (int)k, nrows, d_u, 0ull, 0ull, 0ull, (const int32_t *)nullptr, d_o, (int32_t *)nullptr);
+  LAUNCH(ctx, sample_kernel, cdiv(nrows, 128), 128, 0, (const float *)d_s, ld, (int)k, nrows, (const float *)d_u, 0ull, 0ull, 0ull, (const int32_t *)nullptr, (int32_t *)d_o, (int32_t *)nullptr);
   CU_TRY(cudaMemcpyAsync(out, d_o, sizeof(int32_t) * nrows, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_s); cudaFree(d_u); cudaFree(d_o);
   return MSB_OK;
 }
 
@@ -1650,12 +1657,11 @@ extern "C" MSB_API int msb_philox_uniforms(msb_ctx *ctx, uint64_t seed, uint64_t
   REQUIRE(ctx && out, "NULL argument");
   if (!n) return MSB_OK;
   CU_TRY(cudaSetDevice(ctx->device));
-  float *d_u = nullptr;
-  CU_TRY(cudaMalloc(&d_u, sizeof(float) * n));
-  LAUNCH(ctx, philox_fill_kernel, cdiv(n, 256), 256, 0, seed, sweep, row_lo, n, d_u);
+  Scratch<float> d_u;
+  CU_TRY(d_u.alloc(n));
+  LAUNCH(ctx, philox_fill_kernel, cdiv(n, 256), 256, 0, seed, sweep, row_lo, n, (float *)d_u);
   CU_TRY(cudaMemcpyAsync(out, d_u, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_u);
   return MSB_OK;
 }
 
@@ -1663,27 +1669,25 @@ extern "C" MSB_API int msb_selftest_expf(msb_ctx *ctx, const float *x, size_t n,
   REQUIRE(ctx && x && y, "NULL argument");
   if (!n) return MSB_OK;
   CU_TRY(cudaSetDevice(ctx->device));
-  float *d = nullptr;
-  CU_TRY(cudaMalloc(&d, sizeof(float) * 2 * n));
+  Scratch<float> d;
+  CU_TRY(d.alloc(2 * n));
   CU_TRY(cudaMemcpyAsync(d, x, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(ctx, selftest_expf_kernel, cdiv(n, 256), 256, 0, d, n, d + n);
-  CU_TRY(cudaMemcpyAsync(y, d + n, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  LAUNCH(ctx, selftest_expf_kernel, cdiv(n, 256), 256, 0, (const float *)d, n, d.p + n);
+  CU_TRY(cudaMemcpyAsync(y, d.p + n, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d);
   return MSB_OK;
 }
 
 extern "C" MSB_API int msb_selftest_division(msb_ctx *ctx, uint64_t seed, size_t n, uint64_t *mismatches) {
   REQUIRE(ctx && mismatches, "NULL argument");
   CU_TRY(cudaSetDevice(ctx->device));
-  unsigned long long *d = nullptr;
-  CU_TRY(cudaMalloc(&d, sizeof(unsigned long long)));
+  Scratch<unsigned long long> d;
+  CU_TRY(d.alloc(1));
   CU_TRY(cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
-  if (n) LAUNCH(ctx, selftest_division_kernel, cdiv(n, 256), 256, 0, seed, n, d);
+  if (n) LAUNCH(ctx, selftest_division_kernel, cdiv(n, 256), 256, 0, seed, n, (unsigned long long *)d);
   unsigned long long h = 0;
   CU_TRY(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d);
   *mismatches = h;
   return MSB_OK;
 }
@@ -1826,11 +1830,12 @@ static int value_op(msb_ctx *ctx, const msb_model_desc *model, int op, const dou
   MSB_TRY(value_to_doubles(value, vtype, x));
   REQUIRE(x.size() == (model->family == MSB_FAMILY_NIW ? model->dim : 1u), "shapes do not match");
   CU_TRY(cudaSetDevice(ctx->device));
-  double *d_buf = nullptr; float *d_score = nullptr;
+  Scratch<double> d_buf;
+  Scratch<float> d_score;
   const size_t total = nhp + nss + x.size();
-  CU_TRY(cudaMalloc(&d_buf, sizeof(double) * total));
-  CU_TRY(cudaMalloc(&d_score, sizeof(float) * 64));
-  double *d_hp = d_buf, *d_ss = d_buf + nhp, *d_x = d_ss + nss;
+  CU_TRY(d_buf.alloc(total));
+  CU_TRY(d_score.alloc(64));
+  double *d_hp = d_buf.p, *d_ss = d_buf.p + nhp, *d_x = d_ss + nss;
   CU_TRY(cudaMemcpyAsync(d_hp, hp, sizeof(double) * nhp, cudaMemcpyHostToDevice, ctx->stream));
   CU_TRY(cudaMemcpyAsync(d_ss, ss, sizeof(double) * nss, cudaMemcpyHostToDevice, ctx->stream));
   CU_TRY(cudaMemcpyAsync(d_x, x.data(), sizeof(double) * x.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1840,28 +1845,27 @@ static int value_op(msb_ctx *ctx, const msb_model_desc *model, int op, const dou
     const uint32_t d = model->dim;
     FeatDev f; memset(&f, 0, sizeof(f));
     f.family = FAM_NIW; f.kind = KIND_NIW; f.dim = d; f.hp_off = 0; f.ss_off = 0; f.ss_w = (uint32_t)nss;
-    float *d_W = nullptr, *d_x32 = nullptr; int32_t *d_c2s = nullptr;
+    Scratch<float> d_W, d_x32;
+    Scratch<int32_t> d_c2s;
     std::vector<float> x32(x.begin(), x.end());
-    CU_TRY(cudaMalloc(&d_W, sizeof(float) * ((size_t)d * d + d + 4)));
-    CU_TRY(cudaMalloc(&d_x32, sizeof(float) * d));
-    CU_TRY(cudaMalloc(&d_c2s, sizeof(int32_t)));
+    CU_TRY(d_W.alloc((size_t)d * d + d + 4));
+    CU_TRY(d_x32.alloc(d));
+    CU_TRY(d_c2s.alloc(1));
     CU_TRY(cudaMemsetAsync(d_c2s, 0, sizeof(int32_t), ctx->stream));
     CU_TRY(cudaMemsetAsync(d_score, 0, sizeof(float), ctx->stream));
     CU_TRY(cudaMemcpyAsync(d_x32, x32.data(), sizeof(float) * d, cudaMemcpyHostToDevice, ctx->stream));
-    float *d_bias = d_W + (size_t)d * d, *d_coef = d_bias + d;
-    LAUNCH(ctx, niw_prepare_kernel, 1, 128, (2 * (size_t)d * d + d) * sizeof(double), f, d_hp, d_ss, d_c2s, d_W, d_bias, d_coef);
-    LAUNCH(ctx, niw_score_simt_kernel, dim3(1, 1), 128, ((size_t)d * d + d) * sizeof(float), d_x32, (int)d, d_W, d_bias, d_coef,
-           d_score, (size_t)1, (size_t)0, (size_t)1);
+    float *d_bias = d_W.p + (size_t)d * d, *d_coef = d_bias + d;
+    LAUNCH(ctx, niw_prepare_kernel, 1, 128, (2 * (size_t)d * d + d) * sizeof(double), f, d_hp, d_ss, (const int32_t *)d_c2s, d_W.p, d_bias, d_coef);
+    LAUNCH(ctx, niw_score_simt_kernel, dim3(1, 1), 128, ((size_t)d * d + d) * sizeof(float), (const float *)d_x32, (int)d, (const float *)d_W,
+           (const float *)d_bias, (const float *)d_coef, d_score.p, (size_t)1, (size_t)0, (size_t)1);
     CU_TRY(cudaMemcpyAsync(score, d_score, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_W); cudaFree(d_x32); cudaFree(d_c2s);
   } else {
-    LAUNCH(ctx, value_op_kernel, 1, 32, 0, model->family, model->dim, op, d_hp, d_ss, d_x, d_score);
+    LAUNCH(ctx, value_op_kernel, 1, 32, 0, model->family, model->dim, op, d_hp, d_ss, d_x, d_score.p);
     if (op == 0) CU_TRY(cudaMemcpyAsync(score, d_score, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     else CU_TRY(cudaMemcpyAsync(ss, d_ss, sizeof(double) * nss, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
   }
-  cudaFree(d_buf); cudaFree(d_score);
   return rc;
 }
 
