@@ -107,6 +107,8 @@ _PROTOS = {
     "msb_state_sweep_wait": (C.c_int, [_P, C.POINTER(SweepResult)]),
     "msb_state_delta_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ)]),
     "msb_state_apply_deltas": (C.c_int, [_P]),
+    "msb_state_delta_buffer_i32": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ)]),
+    "msb_state_delta_from_i32": (C.c_int, [_P]),
     "msb_state_suffstat_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ)]),
     "msb_state_last_scores": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ), C.POINTER(_SZ), C.POINTER(_SZ)]),
     "msb_state_read_last_scores": (C.c_int, [_P, _P, _SZ]),

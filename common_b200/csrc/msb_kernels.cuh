@@ -916,6 +916,16 @@ __global__ void dd_count_sum_kernel(const FeatDev *__restrict__ feats, int nfeat
   if (lane == 0) p[0] = s;
 }
 
+// count-valued states (bb / dd only): the deltas are numbers of rows, exact in int32 -- half the bytes of the fp64 buffer
+__global__ void delta_to_i32_kernel(const double *__restrict__ delta, size_t n, int32_t *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)delta[i];
+}
+__global__ void delta_from_i32_kernel(const int32_t *__restrict__ in, size_t n, double *__restrict__ delta) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) delta[i] = (double)in[i];
+}
+
 __global__ void apply_delta_kernel(double *__restrict__ ss, double *__restrict__ delta, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { ss[i] += delta[i]; delta[i] = 0.0; }

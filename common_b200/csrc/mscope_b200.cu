@@ -98,6 +98,7 @@ struct msb_state {
   // suffstats: [counts kmax | per-feature blocks]
   size_t SS = 0;
   double *d_ss = nullptr, *d_delta = nullptr;
+  int32_t *d_delta_i32 = nullptr;  // msb_state_delta_buffer_i32
   // CRP bookkeeping (group_manager.hpp:48-306)
   double alpha = 1.0;
   size_t gcount = 0;
@@ -559,7 +560,7 @@ extern "C" MSB_API int msb_state_destroy(msb_state *st) {
   cudaFree(st->col_slab_b); cudaFree(st->d_feats_b); cudaFree(st->d_feats_scalar_b); cudaFree(st->d_flags_b); cudaFreeHost(st->h_flags_b);
   cudaFree(st->col_slab);
   for (size_t d = 0; d < st->D; d++) { cudaFree(st->d_niwW[d]); cudaFree(st->d_niwBias[d]); cudaFree(st->d_niwCoef[d]); cudaFree(st->d_niwB[d]); }
-  cudaFree(st->d_feats); cudaFree(st->d_feats_scalar); cudaFree(st->d_hp); cudaFree(st->d_ss); cudaFree(st->d_delta); cudaFree(st->d_counter);
+  cudaFree(st->d_feats); cudaFree(st->d_feats_scalar); cudaFree(st->d_hp); cudaFree(st->d_ss); cudaFree(st->d_delta); cudaFree(st->d_delta_i32); cudaFree(st->d_counter);
   cudaFree(st->d_slot2gid); cudaFree(st->d_assign64); cudaFree(st->d_flags); cudaFreeHost(st->h_moved); cudaFreeHost(st->h_flags); cudaFree(st->d_assign); cudaFree(st->d_params); cudaFree(st->d_scores);
   cudaFree(st->d_base); cudaFree(st->d_base_score); cudaFree(st->d_col2slot); cudaFree(st->d_newslot); cudaFree(st->d_newcol); cudaFree(st->d_uniforms);
   for (auto &ring : st->events) for (auto &pe : ring) for (auto &e : pe.e) cudaEventDestroy(e);
@@ -1262,6 +1263,28 @@ static int apply_deltas(msb_state *st) {
 extern "C" MSB_API int msb_state_delta_buffer(msb_state *st, double **dev_ptr, size_t *count) {
   REQUIRE(st && dev_ptr && count, "NULL argument");
   *dev_ptr = st->d_delta; *count = st->SS;
+  return MSB_OK;
+}
+// Count-valued states only (every feature bb or dd: each delta is a number of rows, |delta| <= N < 2^31): the pending
+// deltas as int32, exact, half the bytes to all-reduce.  *dev_ptr == NULL (and MSB_OK) for any other state (bnb / gp
+// sums of values can exceed int32, nich / niw moments are real).
+extern "C" MSB_API int msb_state_delta_buffer_i32(msb_state *st, int32_t **dev_ptr, size_t *count) {
+  REQUIRE(st && dev_ptr && count, "NULL argument");
+  *dev_ptr = nullptr; *count = st->SS;
+  for (const auto &m : st->models)
+    if (m.family != MSB_FAMILY_BB && m.family != MSB_FAMILY_DD) return MSB_OK;
+  if (st->n >= (1ull << 31) || getenv("MSB_NO_I32_DELTAS")) return MSB_OK;
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  if (!st->d_delta_i32) CU_TRY(cudaMalloc(&st->d_delta_i32, sizeof(int32_t) * st->SS));
+  LAUNCH(st->ctx, delta_to_i32_kernel, cdiv(st->SS, 256), 256, 0, st->d_delta, st->SS, st->d_delta_i32);
+  *dev_ptr = st->d_delta_i32;
+  return MSB_OK;
+}
+// after the all-reduce of that buffer: back into the fp64 delta buffer, then msb_state_apply_deltas as usual
+extern "C" MSB_API int msb_state_delta_from_i32(msb_state *st) {
+  REQUIRE(st && st->d_delta_i32, "msb_state_delta_buffer_i32 was not called");
+  CU_TRY(cudaSetDevice(st->ctx->device));
+  LAUNCH(st->ctx, delta_from_i32_kernel, cdiv(st->SS, 256), 256, 0, st->d_delta_i32, st->SS, st->d_delta);
   return MSB_OK;
 }
 extern "C" MSB_API int msb_state_suffstat_buffer(msb_state *st, double **dev_ptr, size_t *count) {

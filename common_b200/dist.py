@@ -14,9 +14,9 @@ class _DevicePtr(object):
                                          "version": 2, "strides": None}
 
 
-def as_tensor(ptr, n, device):
+def as_tensor(ptr, n, device, typestr="<f8"):
     import torch
-    return torch.as_tensor(_DevicePtr(ptr, n), device=device)
+    return torch.as_tensor(_DevicePtr(ptr, n, typestr), device=device)
 
 
 def shard_rows(n_total, rank, world):
@@ -29,9 +29,15 @@ def shard_rows(n_total, rank, world):
 def allreduce_deltas(st, device):
     """sum the flat fp64 delta buffer over all ranks, then apply it on every replica"""
     import torch.distributed as dist
-    ptr, n = st.delta_buffer()
-    t = as_tensor(ptr, n, device)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    ptr32, n = st.delta_buffer_i32()
+    if ptr32:  # every suffstat is a count of rows: exact int32 deltas, half the bytes on the wire
+        t = as_tensor(ptr32, n, device, "<i4")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        st.delta_from_i32()
+    else:
+        ptr, n = st.delta_buffer()
+        t = as_tensor(ptr, n, device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
     st.apply_deltas()
 
 

@@ -272,6 +272,15 @@ class state(object):
         _lib.check(_lib.load().msb_state_delta_buffer(self._h, C.byref(ptr), C.byref(n)))
         return ptr.value, n.value
 
+    def delta_buffer_i32(self):
+        """(device pointer or None, count): the pending deltas as exact int32 (integer-valued states only)"""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _lib.check(_lib.load().msb_state_delta_buffer_i32(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def delta_from_i32(self):
+        _lib.check(_lib.load().msb_state_delta_from_i32(self._h))
+
     def suffstat_buffer(self):
         ptr, n = C.c_void_p(), C.c_size_t()
         _lib.check(_lib.load().msb_state_suffstat_buffer(self._h, C.byref(ptr), C.byref(n)))

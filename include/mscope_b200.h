@@ -244,6 +244,11 @@ MSB_API int msb_state_sweep_wait(msb_state *st, msb_sweep_result *res);
 /* multi-GPU: flat fp64 buffer [group counts | per-feature suffstat deltas] on the device */
 MSB_API int msb_state_delta_buffer(msb_state *st, double **dev_ptr, size_t *count);
 MSB_API int msb_state_apply_deltas(msb_state *st);
+/* count-valued states (every feature bb or dd): the same deltas as exact int32, half the bytes to all-reduce;
+ * *dev_ptr is NULL for any other state.  After the all-reduce call
+ * msb_state_delta_from_i32, then msb_state_apply_deltas. */
+MSB_API int msb_state_delta_buffer_i32(msb_state *st, int32_t **dev_ptr, size_t *count);
+MSB_API int msb_state_delta_from_i32(msb_state *st);
 /* the resident suffstats themselves, same layout (replica initialisation: all-reduce, then apply_deltas) */
 MSB_API int msb_state_suffstat_buffer(msb_state *st, double **dev_ptr, size_t *count);
 
