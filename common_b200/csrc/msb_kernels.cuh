@@ -27,7 +27,7 @@ struct FeatDev {
   uint32_t pad_;
   uint64_t hp_off;    // into hp[]
   uint64_t ss_off;    // into ss[] / delta[]: block[slot * ss_w + j]
-  double asum;        // dd: sum of alphas
+  double asum;        // dd: sum of alphas.  nich: the centre c of the score column (x' = x - c; 0 unless the whole column is far from 0)
   // AoS source record (row_major_dataview layout, runtime_type.hpp:123-134)
   uint64_t src_off;
   uint64_t msk_off;
@@ -110,7 +110,7 @@ __global__ void scorecol_kernel(const FeatDev *__restrict__ feats, int nfeat, si
   if (f.kind == KIND_NICH) {
     const float x = row < n ? ((const float *)f.col)[row] : 0.f;
     slow = x != x;
-    out = slow ? 0u : __float_as_uint(x);
+    out = (slow || row >= n) ? 0u : __float_as_uint((float)((double)x - f.asum));  // centred, see build_params_kernel
   } else if (f.kind == KIND_GP) {
     const uint32_t x = row < n ? ((const uint32_t *)f.col)[row] : GP_SENTINEL;
     slow = x != GP_SENTINEL && x >= f.ncat;
@@ -184,7 +184,7 @@ ingest_tile_kernel(const uint8_t *__restrict__ data, const uint8_t *__restrict__
       const float x = masked ? CUDART_NAN_F : (float)v;
       if (live) ((float *)f.col)[row] = x;
       slow = live && masked;
-      out = (slow || !live) ? 0u : __float_as_uint(x);
+      out = (slow || !live) ? 0u : __float_as_uint((float)((double)x - f.asum));
     } else if (f.kind == KIND_GP) {
       uint32_t x = v < 0.0 ? 0u : (v >= 4294967294.0 ? 4294967294u : (uint32_t)v);
       if (masked || !live) x = GP_SENTINEL;
@@ -211,6 +211,23 @@ ingest_tile_kernel(const uint8_t *__restrict__ data, const uint8_t *__restrict__
       if (m) any_slow[d] = 1u;
     }
   }
+}
+
+// sum, count, min and max of a nich column (ignoring masked cells): decides the centre of the score column.
+// out = [sum, count] as doubles, then [min, max] kept as order-preserving uint32 keys of the floats
+__device__ __forceinline__ uint32_t f32_key(float v) { const uint32_t b = __float_as_uint(v); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__global__ void colstats_f32_kernel(const float *__restrict__ col, size_t n, double *out, uint32_t *minmax) {
+  double s = 0.0, c = 0.0;
+  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = col[i];
+    if (v == v) { s += (double)v; c += 1.0; const uint32_t k = f32_key(v); lo = min(lo, k); hi = max(hi, k); }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, s); atomicAdd(out + 1, c); atomicMin(minmax, lo); atomicMax(minmax + 1, hi); }
 }
 
 // max over a gp column (ignoring masked cells): sizes the lookup table
@@ -260,8 +277,10 @@ __global__ void build_params_kernel(const FeatDev *__restrict__ feats, int nfeat
         else v = (float)p.l1pb;
       } else if (f.kind == KIND_NICH) {
         const NichPost p = nich_post(fhp, gss);
-        // rows: mu', s, c1 ln2 (the score kernel evaluates log2(1+z)), c0
-        v = xr == 0 ? (float)p.mu : xr == 1 ? (float)p.s : xr == 2 ? (float)(p.c1 * 0.6931471805599453) : (float)p.c0;
+        // rows: mu' - c, s, c1 ln2 (the score kernel evaluates log2(1+z)), c0.  c is the centre of the score column
+        // (msb_state_bind): for a column that sits far from 0 relative to its spread the fp32 table entry of mu'
+        // would otherwise carry ulp(mu') of error into t = (x - mu') s
+        v = xr == 0 ? (float)(p.mu - f.asum) : xr == 1 ? (float)p.s : xr == 2 ? (float)(p.c1 * 0.6931471805599453) : (float)p.c0;
       }
     }
     chunk[i] = v;

@@ -680,6 +680,40 @@ static int ingest(msb_state *st, bool size_tables) {
       const uint32_t cap_limit = 252;  // chunk rows = cap + 4 <= 256
       for (size_t i = 0; i < gp.size(); i++) st->feats[gp[i]].ncat = std::min<uint32_t>(st->h_flags[D + i] + 1, cap_limit);
     }
+    // Centre of every nich score column.  t = (x - mu') s subtracts first, which is exact near a group's own mean,
+    // but the fp32 table entry of mu' carries ulp(mu') of error: for a column that sits far from 0 relative to its
+    // spread (all values within |mean| / 4 of the mean) both x and mu' are stored relative to the column mean.
+    // Any other column keeps c = 0: centring would cost small values their low bits.
+    std::vector<size_t> nc;
+    for (size_t d = 0; d < D; d++) if (st->feats[d].kind == KIND_NICH) nc.push_back(d);
+    if (!nc.empty()) {
+      Scratch<double> d_sum;
+      Scratch<uint32_t> d_mm;
+      CU_TRY(d_sum.alloc(2 * nc.size()));
+      CU_TRY(d_mm.alloc(2 * nc.size()));
+      std::vector<uint32_t> h_mm(2 * nc.size());
+      for (size_t i = 0; i < nc.size(); i++) { h_mm[2 * i] = 0xFFFFFFFFu; h_mm[2 * i + 1] = 0u; }
+      CU_TRY(cudaMemsetAsync(d_sum, 0, sizeof(double) * 2 * nc.size(), ctx->stream));
+      CU_TRY(cudaMemcpyAsync(d_mm, h_mm.data(), sizeof(uint32_t) * h_mm.size(), cudaMemcpyHostToDevice, ctx->stream));
+      if (dv->n)
+        for (size_t i = 0; i < nc.size(); i++)
+          LAUNCH(ctx, colstats_f32_kernel, std::min<unsigned>(cdiv(dv->n, 256), 1024), 256, 0, (const float *)st->cols[nc[i]], dv->n,
+                 d_sum.p + 2 * i, d_mm.p + 2 * i);
+      std::vector<double> h_sum(2 * nc.size());
+      CU_TRY(cudaMemcpyAsync(h_sum.data(), d_sum, sizeof(double) * h_sum.size(), cudaMemcpyDeviceToHost, ctx->stream));
+      CU_TRY(cudaMemcpyAsync(h_mm.data(), d_mm, sizeof(uint32_t) * h_mm.size(), cudaMemcpyDeviceToHost, ctx->stream));
+      CU_TRY(cudaStreamSynchronize(ctx->stream));
+      auto unkey = [](uint32_t k) { const uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k; float f; memcpy(&f, &b, 4); return f; };
+      for (size_t i = 0; i < nc.size(); i++) {
+        double c = 0.0;
+        if (h_sum[2 * i + 1] > 0.0) {
+          const double mean = h_sum[2 * i] / h_sum[2 * i + 1];
+          const double lo = unkey(h_mm[2 * i]), hi = unkey(h_mm[2 * i + 1]);
+          if (std::isfinite(mean) && std::max(hi - mean, mean - lo) <= 0.25 * std::fabs(mean)) c = (double)(float)mean;
+        }
+        st->feats[nc[i]].asum = c;
+      }
+    }
     layout_chunks(st);
   }
   if (st->has_scalar) {  // score columns + slow-path masks (the gp table sizes are known now)

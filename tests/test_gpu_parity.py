@@ -712,3 +712,32 @@ def test_checkpoint_round_trip_through_the_wire_format(ctx, oracle):
     assert st2.create_group() == g_new + 1    # gcount = 1 + the largest identifier seen (group_manager.hpp:102-104)
     assert st2.serialize()[:40] == blob[:40]
     st.close(); st2.close()
+
+
+@pytest.mark.parametrize("offset", [0.0, 1.0e3, -3.0e4])
+def test_nich_columns_far_from_the_origin(ctx, oracle, offset):
+    # t = (x - mu') s subtracts first (exact near the group's own mean, Sterbenz), and a column that sits far from 0
+    # relative to its spread is stored relative to its mean (x and the fp32 table entry of mu' alike), so the
+    # accuracy does not depend on the offset.  (Folding the offset into one FMA, t = x' s + b, saves an instruction
+    # -- C3 107 -> 103 ms -- but loses the first property for columns whose groups sit much further apart than
+    # 2^24 sigma, e.g. test_any_primitive_type_may_back_a_field[uint32]; not kept.)
+    descs = [cb.nich] * 5 + [cb.dd(4)]
+    n, k = 6000, 5
+    arr, z = cb.synth.make_dataset(descs, n, k, seed=121, mask_frac=0.03)
+    data = np.array(arr.data if hasattr(arr, "mask") else arr, copy=True)
+    for name in data.dtype.names[:5]:
+        data[name] = (data[name].astype(np.float64) * 0.2 + offset).astype(np.float32)
+    arr2 = np.ma.array(data, mask=np.ma.getmaskarray(arr)) if hasattr(arr, "mask") else data
+    view = cb.numpy_dataview(arr2)
+    st = cb.state(ctx, descs, max_groups=k + 2, cluster_hp={"alpha": 1.0})
+    st.bind(view)
+    gids = [st.create_group() for _ in range(k)]
+    st.add_values(np.asarray(gids)[z])
+    hp = np.concatenate([oracle.flat_hp(d) for d in descs])
+    ss, counts = ol.build_suffstats(oracle, descs, hp, view, z, k)
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
+    _, S = st.score_rows()
+    assert np.max(rel_err(S, want)) < RTOL
+    _, S64 = st.score_rows_f64()
+    assert np.max(rel_err(S64, want)) < 1e-9      # fp64 path; sum x^2 cancellation grows with offset^2
+    st.close()
