@@ -21,8 +21,10 @@ struct FeatDev {
   uint32_t rowoff;    // first row of the chunk inside a k-tile region
   uint32_t ss_w;      // doubles per group slot
   const void *col;    // Value-typed column, n elements (niw: n x dim floats)
-  const uint32_t *scol;     // score column: u32 table row index (always a valid chunk row) or f32 value (masked -> 0)
-  const uint32_t *slowmask; // per 32-row block: rows that need the score kernel's slow path (gp overflow, nich masked)
+  const uint32_t *scol;     // score column: u32 table row index (always a valid chunk row) or f32 value (masked -> 0);
+                            // niw: the CENTRED rows, f32[n][dim] = x - c (what the fp32 scorers read; col keeps the raw rows)
+  const uint32_t *slowmask; // per 32-row block: rows that need the score kernel's slow path (gp overflow, nich masked);
+                            // niw: the centre c, f32[dim] (0 for coordinates that are not far from the origin)
   uint32_t has_slow;        // any bit set in slowmask
   uint32_t pad_;
   uint64_t hp_off;    // into hp[]
@@ -172,8 +174,14 @@ ingest_tile_kernel(const uint8_t *__restrict__ data, const uint8_t *__restrict__
     if (f.kind == KIND_NIW) {
       if (live) {
         float *dst = (float *)f.col + row * (size_t)f.dim;
-        for (uint32_t i = 0; i < f.dim; i++) dst[i] = (float)load_prim(rec + f.src_off + i * ps, f.src_prim);
-        if (masked) dst[0] = CUDART_NAN_F;
+        float *dsc = (float *)f.scol + row * (size_t)f.dim;
+        const float *cen = (const float *)f.slowmask;
+        for (uint32_t i = 0; i < f.dim; i++) {
+          const double v = load_prim(rec + f.src_off + i * ps, f.src_prim);
+          dst[i] = (float)v;
+          dsc[i] = (float)((double)(float)v - (double)cen[i]);
+        }
+        if (masked) dst[0] = dsc[0] = CUDART_NAN_F;
       }
       continue;
     }
@@ -211,6 +219,35 @@ ingest_tile_kernel(const uint8_t *__restrict__ data, const uint8_t *__restrict__
       if (m) any_slow[d] = 1u;
     }
   }
+}
+
+// per-coordinate sum / count / min / max of a niw column (rows with a NaN first element are masked);
+// blockIdx.y = coordinate.  out[j] = [sum, count], minmax[j] = [min key, max key]
+__global__ void niw_colstats_kernel(const float *__restrict__ X, size_t n, int d, double *out, uint32_t *minmax) {
+  const int j = blockIdx.y;
+  double s = 0.0, c = 0.0;
+  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = X[i * d + j];
+    if (X[i * d] == X[i * d] && v == v) {
+      s += (double)v; c += 1.0;
+      const uint32_t b = __float_as_uint(v), k = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+      lo = min(lo, k); hi = max(hi, k);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out + 2 * j, s); atomicAdd(out + 2 * j + 1, c); atomicMin(minmax + 2 * j, lo); atomicMax(minmax + 2 * j + 1, hi); }
+}
+// xc = x - c, the masked-row marker (NaN in element 0) kept
+__global__ void niw_center_kernel(const float *__restrict__ X, size_t n, int d, const float *__restrict__ cen, float *__restrict__ Xc) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * (size_t)d) return;
+  const int j = (int)(i % d);
+  const float v = X[i];
+  Xc[i] = (j == 0 && v != v) ? v : (float)((double)v - (double)cen[j]);
 }
 
 // sum, count, min and max of a nich column (ignoring masked cells): decides the centre of the score column.
@@ -394,9 +431,11 @@ __global__ void niw_prepare_kernel(FeatDev f, const double *__restrict__ hp, con
     s_logdiag = ld;
   }
   for (int e = threadIdx.x; e < d * d; e += blockDim.x) W[(size_t)k * d * d + e] = (float)Winv[e];
+  // the scorers read the centred rows x - c (FeatDev::scol): bias = W (mu' - c)
+  const float *cen = (const float *)f.slowmask;
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     double b = 0.0;
-    for (int j = 0; j <= i; j++) b += Winv[i * d + j] * mu[j];
+    for (int j = 0; j <= i; j++) b += Winv[i * d + j] * (mu[j] - (cen ? (double)cen[j] : 0.0));
     bias[(size_t)k * d + i] = (float)b;
   }
   __syncthreads();

@@ -665,6 +665,13 @@ static int ingest(msb_state *st, bool size_tables) {
     LAUNCH(ctx, pack_kernel, grid, 256, 0, dv->d_data, dv->d_mask, dv->n, dv->rowsize, dv->maskrowsize, st->d_feats, (int)D);
   }
   CU_TRY(dv_release(dv));
+  if (!size_tables && dv->n)  // refresh without the fused kernel: re-centre the niw rows with the centres chosen at bind
+    for (size_t d = 0; d < D; d++) {
+      const FeatDev &f = st->feats[d];
+      if (f.kind == KIND_NIW)
+        LAUNCH(ctx, niw_center_kernel, cdiv(dv->n * (size_t)f.dim, 256), 256, 0, (const float *)f.col, dv->n, (int)f.dim,
+               (const float *)f.slowmask, (float *)const_cast<uint32_t *>(f.scol));
+    }
   if (size_tables) {
     std::vector<size_t> gp;
     for (size_t d = 0; d < D; d++) if (st->feats[d].kind == KIND_GP) gp.push_back(d);
@@ -679,6 +686,43 @@ static int ingest(msb_state *st, bool size_tables) {
       CU_TRY(cudaStreamSynchronize(ctx->stream));
       const uint32_t cap_limit = 252;  // chunk rows = cap + 4 <= 256
       for (size_t i = 0; i < gp.size(); i++) st->feats[gp[i]].ncat = std::min<uint32_t>(st->h_flags[D + i] + 1, cap_limit);
+    }
+    // Centre of every niw column, coordinate by coordinate, under the same rule as nich below: the GEMM form
+    // |W x - W mu'|^2 never subtracts first, so its fp32 error grows with |x| / sigma (measured: 3e-6 at an offset of
+    // 10 sigma, 2.8e-5 at 100, 2.4e-4 at 1000 -- scripts/niw_offset_accuracy.py); the scorers read x - c instead.
+    for (size_t d = 0; d < D; d++) {
+      const FeatDev &f = st->feats[d];
+      if (f.kind != KIND_NIW) continue;
+      const int dim = (int)f.dim;
+      std::vector<float> cen(dim, 0.f);
+      if (dv->n) {
+        Scratch<double> d_sum;
+        Scratch<uint32_t> d_mm;
+        CU_TRY(d_sum.alloc(2 * dim));
+        CU_TRY(d_mm.alloc(2 * dim));
+        std::vector<uint32_t> h_mm(2 * dim);
+        for (int j = 0; j < dim; j++) { h_mm[2 * j] = 0xFFFFFFFFu; h_mm[2 * j + 1] = 0u; }
+        CU_TRY(cudaMemsetAsync(d_sum, 0, sizeof(double) * 2 * dim, ctx->stream));
+        CU_TRY(cudaMemcpyAsync(d_mm, h_mm.data(), sizeof(uint32_t) * h_mm.size(), cudaMemcpyHostToDevice, ctx->stream));
+        dim3 grid(std::min<unsigned>(cdiv(dv->n, 256), 256), (unsigned)dim);
+        LAUNCH(ctx, niw_colstats_kernel, grid, 256, 0, (const float *)f.col, dv->n, dim, d_sum.p, d_mm.p);
+        std::vector<double> h_sum(2 * dim);
+        CU_TRY(cudaMemcpyAsync(h_sum.data(), d_sum, sizeof(double) * h_sum.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaMemcpyAsync(h_mm.data(), d_mm, sizeof(uint32_t) * h_mm.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        auto unkey = [](uint32_t k) { const uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k; float v; memcpy(&v, &b, 4); return v; };
+        for (int j = 0; j < dim; j++) {
+          if (!(h_sum[2 * j + 1] > 0.0)) continue;
+          const double mean = h_sum[2 * j] / h_sum[2 * j + 1];
+          const double lo = unkey(h_mm[2 * j]), hi = unkey(h_mm[2 * j + 1]);
+          if (std::isfinite(mean) && std::max(hi - mean, mean - lo) <= 0.25 * std::fabs(mean)) cen[j] = (float)mean;
+        }
+      }
+      CU_TRY(cudaMemcpyAsync(const_cast<uint32_t *>(f.slowmask), cen.data(), sizeof(float) * dim, cudaMemcpyHostToDevice, ctx->stream));
+      CU_TRY(cudaStreamSynchronize(ctx->stream));  // cen is a local
+      if (dv->n)
+        LAUNCH(ctx, niw_center_kernel, cdiv(dv->n * (size_t)dim, 256), 256, 0, (const float *)f.col, dv->n, dim, (const float *)f.slowmask,
+               (float *)const_cast<uint32_t *>(f.scol));
     }
     // Centre of every nich score column.  t = (x - mu') s subtracts first, which is exact near a group's own mean,
     // but the fp32 table entry of mu' carries ulp(mu') of error: for a column that sits far from 0 relative to its
@@ -756,6 +800,9 @@ extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
       if (f.kind != KIND_NIW) {
         soff[d] = slab; slab += n_pad * sizeof(uint32_t);
         moff[d] = slab; slab += n_pad / 32 * sizeof(uint32_t);
+      } else {  // niw: the centred rows and the centre (FeatDev::scol / slowmask)
+        soff[d] = slab; slab += (bytes + 4096 + 255) / 256 * 256;
+        moff[d] = slab; slab += ((size_t)f.dim * sizeof(float) + 255) / 256 * 256;
       }
     }
     CU_TRY(cudaMalloc(&st->col_slab, slab));
@@ -766,8 +813,8 @@ extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
       FeatDev &f = st->feats[d];
       st->cols[d] = (char *)st->col_slab + coff[d];
       f.col = st->cols[d];
-      f.scol = f.kind != KIND_NIW ? (const uint32_t *)((char *)st->col_slab + soff[d]) : nullptr;
-      f.slowmask = f.kind != KIND_NIW ? (const uint32_t *)((char *)st->col_slab + moff[d]) : nullptr;
+      f.scol = (const uint32_t *)((char *)st->col_slab + soff[d]);
+      f.slowmask = (const uint32_t *)((char *)st->col_slab + moff[d]);
     }
     CU_TRY(cudaMalloc(&st->d_assign, sizeof(int32_t) * n));
   }
@@ -860,6 +907,11 @@ extern "C" MSB_API int msb_state_prefetch(msb_state *st) {
       if (f.slowmask) f.slowmask = (const uint32_t *)((const char *)f.slowmask + shift);
     }
     CU_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    for (size_t d = 0; d < D; d++)  // the niw centres belong to the layout, not to one buffer
+      if (st->feats[d].kind == KIND_NIW)
+        CU_TRY(cudaMemcpy(const_cast<uint32_t *>(st->feats_b[d].slowmask), st->feats[d].slowmask, sizeof(float) * st->feats[d].dim,
+                          cudaMemcpyDeviceToDevice));
     CU_TRY(cudaMemcpy(st->d_feats_b, st->feats_b.data(), sizeof(FeatDev) * D, cudaMemcpyHostToDevice));
     st->feats_b_dirty = true;  // its walk-order list (d_feats_scalar_b) is built at the first swap
   }
@@ -1236,7 +1288,7 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
       LAUNCH(ctx, fill_rows_kernel, cdiv(nrows * st->ld, 256), 256, 0, scores, st->ld, st->d_base, nrows);
       need_init = false;
     }
-    MSB_TRY(niw_tc_score(ctx->stream, &ctx->launches, (const float *)f.col, f.dim, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
+    MSB_TRY(niw_tc_score(ctx->stream, &ctx->launches, (const float *)f.scol, f.dim, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
                          st->d_niwB[d], K, scores, st->ld, row_lo, row_hi, ctx->sm_count, need_init ? st->d_base : nullptr,
                          blocked, &done, g_last_error));
     if (blocked && !done) return fail(MSB_ERR_STATE, "internal: blocked score layout without the tensor-core NIW path");
@@ -1248,7 +1300,7 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
       }
       const size_t smem = ((size_t)f.dim * f.dim + f.dim) * sizeof(float);
       dim3 grid(cdiv(nrows, 128), (unsigned)K);
-      LAUNCH(ctx, niw_score_simt_kernel, grid, 128, smem, (const float *)f.col, (int)f.dim, st->d_niwW[d], st->d_niwBias[d],
+      LAUNCH(ctx, niw_score_simt_kernel, grid, 128, smem, (const float *)f.scol, (int)f.dim, st->d_niwW[d], st->d_niwBias[d],
              st->d_niwCoef[d], scores, st->ld, row_lo, row_hi);
     }
   }

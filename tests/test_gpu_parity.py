@@ -741,3 +741,35 @@ def test_nich_columns_far_from_the_origin(ctx, oracle, offset):
     _, S64 = st.score_rows_f64()
     assert np.max(rel_err(S64, want)) < 1e-9      # fp64 path; sum x^2 cancellation grows with offset^2
     st.close()
+
+
+@pytest.mark.parametrize("dim", [5, 64])
+@pytest.mark.parametrize("offset", [0.0, 100.0, -1000.0])
+def test_niw_rows_far_from_the_origin(ctx, oracle, dim, offset):
+    # the fp32 NIW scorers (tensor-core GEMM form, CUDA-core kernel) read rows centred at bind: without it the
+    # error of |W x - W mu'|^2 grows with |x| / sigma (2.8e-5 at an offset of 100, 2.4e-4 at 1000)
+    descs = [cb.niw(dim), cb.bb]
+    n, k = 3000, 5
+    arr, z = cb.synth.make_dataset(descs, n, k, seed=131, mask_frac=0.02)
+    data = np.array(arr.data, copy=True)
+    nm = data.dtype.names[0]
+    data[nm] = data[nm] + offset
+    view = cb.numpy_dataview(np.ma.array(data, mask=np.ma.getmaskarray(arr)))
+    st = cb.state(ctx, descs, max_groups=k + 2, cluster_hp={"alpha": 1.0})
+    st.bind(view)
+    gids = [st.create_group() for _ in range(k)]
+    st.add_values(np.asarray(gids)[z])
+    hp = np.concatenate([oracle.flat_hp(d) for d in descs])
+    ss, counts = ol.build_suffstats(oracle, descs, hp, view, z, k)
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
+    _, S = st.score_rows()
+    assert np.max(rel_err(S, want)) < 4 * RTOL
+    # a pass over re-uploaded rows keeps the centring (refresh path)
+    raw, mraw = view.raw()
+    view.to_device(ctx).upload(np.ascontiguousarray(raw), np.ascontiguousarray(mraw))
+    st.refresh()
+    _, S2 = st.score_rows()
+    assert np.array_equal(S2, S)
+    st.sweep(seed=3, sweep=0)
+    assert np.max(rel_err(st.read_last_scores(), want)) < 4 * RTOL
+    st.close()
