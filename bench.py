@@ -167,7 +167,10 @@ def cpu_reference_rate(descs, hp_by_feature, arr, z, k, budget_s, nthreads, f32=
     while t < budget_s / 4 and rows < arr.shape[0]:
         rows = int(min(arr.shape[0], max(rows * 2, rows * (budget_s / 2) / max(t, 1e-6))))
         t = run(rows)
-    return {"value": rows * k * D / t, "seconds": t, "rows": rows, "kind": kind, "cores": nthreads,
+    noop_ns = None
+    if ref is not None and hasattr(ref.lib, "ref_noop_overhead_ns"):
+        noop_ns = ref.noop_overhead_ns()     # the reference's own noop model: what the plugin API costs per call
+    return {"value": rows * k * D / t, "seconds": t, "rows": rows, "kind": kind, "cores": nthreads, "noop_ns": noop_ns,
             "sample": "%d of the workload's rows x K=%d groups x D=%d features, %s" % (
                 rows, k, D, "reference headers (models/base.hpp, recarray/dataview.hpp) + restated family maths, libm logf/lgammaf"
                 if ref is not None else "C port of the reference loop, libm logf/lgammaf")}
@@ -434,7 +437,10 @@ def main():
         if not args.no_cpu and world == 1:
             c = cpu_reference_rate(descs, cfg.get("hp"), arr, z, k, args.cpu_seconds, 1)
             line["cpu_baseline"] = {"value": c["value"], "unit": UNIT, "cores": c["cores"],
-                                    "kind": "port", "api": c["kind"], "sample": c["sample"]}
+                                    "kind": "port", "api": c["kind"], "sample": c["sample"],
+                                    "api_overhead_ns_per_call": c["noop_ns"],
+                                    "api_overhead_note": "the reference's own noop model (models/noop.hpp) in the perf_group.cpp loop: "
+                                                         "the floor the plugin API itself puts under any per-value implementation"}
         print(json.dumps(line))
     st.close()
     if world > 1:

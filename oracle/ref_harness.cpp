@@ -17,6 +17,7 @@
 // entity_state.hpp:60-72 contract (score = log pseudocount + sum over features).
 #include <microscopes/common/recarray/dataview.hpp>
 #include <microscopes/models/base.hpp>
+#include <microscopes/models/noop.hpp>  // the reference's own stub model: API overhead only
 
 #include <chrono>
 #include <cmath>
@@ -432,6 +433,33 @@ __attribute__((visibility("default"))) int ref_score_rows(
   } catch (const std::exception &) {
     return 1;
   }
+}
+
+// The reference's REAL noop model (include/microscopes/models/noop.hpp, compiled where it lies) in the loop of
+// bin/perf_group.cpp:95-105: nothing but the plugin API's own cost per call (virtual dispatch, row_accessor::get /
+// bump, value_accessor construction).  Returns ns per score_value call.
+__attribute__((visibility("default"))) double ref_noop_overhead_ns(size_t D, size_t niters) {
+  rng_t r(73);
+  std::vector<uint8_t> data(D, 1);
+  std::vector<runtime_type> types(D, runtime_type(TYPE_B));
+  row_accessor acc(data.data(), nullptr, &types);
+  models::noop_model m;
+  std::vector<std::shared_ptr<models::hypers>> shares;
+  std::vector<std::shared_ptr<models::group>> groups;
+  for (size_t i = 0; i < D; i++) {
+    shares.emplace_back(m.create_hypers());
+    groups.emplace_back(shares.back()->create_group(r));
+  }
+  float score = 0.f;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (size_t n = 0; n < niters; n++) {
+    acc.reset();
+    for (size_t i = 0; i < D; i++, acc.bump()) score += groups[i]->score_value(*shares[i], acc.get(), r);
+  }
+  const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
+  volatile float sink = score;
+  (void)sink;
+  return ns / (double)(D * niters);
 }
 
 // bin/perf_group.cpp:76-125 itself: D features x 1 row, niters x (add, remove, score); returns ns per call

@@ -35,6 +35,12 @@ class RefHarness(object):
             raise RuntimeError("ref_score_rows failed")
         return out
 
+    def noop_overhead_ns(self, D=1000, niters=20000):
+        """ns per call of the reference's own noop model through its plugin API (models/noop.hpp)"""
+        self.lib.ref_noop_overhead_ns.restype = C.c_double
+        self.lib.ref_noop_overhead_ns.argtypes = [_SZ, _SZ]
+        return self.lib.ref_noop_overhead_ns(D, niters)
+
     def perf_group(self, family=ol.BB, dim=0, D=1000, niters=2000):
         s = C.c_double()
         return self.lib.ref_perf_group(family, dim, D, niters, C.byref(s)), s.value
