@@ -246,9 +246,10 @@ def main():
             st.set_component_hp(d, cfg["hp"])
     st.bind(view)
     gids = np.asarray([st.create_group() for _ in range(k)])
-    st.add_values(gids[z])
     if world > 1:
-        cbd.allreduce_suffstats(st, device)
+        cbd.add_values_sharded(st, gids[z], device)   # local rows -> delta buffer -> all-reduce -> every replica applies the sum
+    else:
+        st.add_values(gids[z])
 
     def step(i, s_=None):
         # everything is enqueued on the stream; nothing in a step waits for the device
@@ -327,9 +328,10 @@ def main():
                 s2.set_component_hp(d, cfg["hp"])
         s2.bind(dv2)
         g2 = np.asarray([s2.create_group() for _ in range(k)])
-        s2.add_values(g2[z])
         if world > 1:
-            cbd.allreduce_suffstats(s2, device)
+            cbd.add_values_sharded(s2, g2[z], device)
+        else:
+            s2.add_values(g2[z])
 
         dv2.upload(pinned.data_ptr())                # the first pass's records
         s2.prefetch()

@@ -19,7 +19,7 @@ MSB_OK, MSB_ERR_INVALID, MSB_ERR_CUDA, MSB_ERR_NOMEM, MSB_ERR_UNSUPPORTED, MSB_E
 # type_info.h:10-34
 TYPE_B, TYPE_I8, TYPE_U8, TYPE_I16, TYPE_U16, TYPE_I32, TYPE_U32, TYPE_I64, TYPE_U64, TYPE_F32, TYPE_F64 = range(11)
 # distributions.hpp:58-64
-FAMILY_BB, FAMILY_BNB, FAMILY_GP, FAMILY_NICH, FAMILY_DD, FAMILY_NIW = range(6)
+FAMILY_BB, FAMILY_BNB, FAMILY_GP, FAMILY_NICH, FAMILY_DD, FAMILY_NIW, FAMILY_BBNC = range(7)
 
 
 class MsbError(RuntimeError):
@@ -91,6 +91,7 @@ _PROTOS = {
     "msb_state_assignments_async": (C.c_int, [_P, _P, _SZ]),
     "msb_state_assignments_wait": (C.c_int, [_P]),
     "msb_state_add_values": (C.c_int, [_P, _P, _SZ]),
+    "msb_state_add_values_deferred": (C.c_int, [_P, _P, _SZ]),
     "msb_state_add_value": (C.c_int, [_P, _SZ, _SZ]),
     "msb_state_remove_value": (C.c_int, [_P, _SZ, C.POINTER(_SZ)]),
     "msb_state_score_value": (C.c_int, [_P, _SZ, C.POINTER(_SZ), C.POINTER(C.c_float), _SZ, C.POINTER(_SZ)]),

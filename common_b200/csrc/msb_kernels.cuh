@@ -302,7 +302,8 @@ __global__ void build_params_kernel(const FeatDev *__restrict__ feats, int nfeat
       const double *gss = ss + f.ss_off + (size_t)col2slot[col] * f.ss_w;
       if (f.kind == KIND_TABLE) {
         if ((uint32_t)xr < f.ncat)
-          v = (float)(f.family == FAM_BB ? bb_score(fhp, gss, xr) : dd_score(fhp, f.asum, gss, (uint32_t)xr));
+          v = (float)(f.family == FAM_BB ? bb_score(fhp, gss, xr) : f.family == FAM_BBNC ? bbnc_score(gss, xr)
+                                                                                    : dd_score(fhp, f.asum, gss, (uint32_t)xr));
       } else if (f.kind == KIND_GP && f.family == FAM_BNB) {
         if ((uint32_t)xr < f.ncat) v = (float)bnb_score(bnb_post(fhp, gss), (double)xr);
       } else if (f.kind == KIND_GP) {
@@ -350,7 +351,7 @@ __global__ void score_direct_kernel(const FeatDev *__restrict__ feats, int nfeat
         else if (f.coltype == COL_U16) x = ((const uint16_t *)f.col)[row];
         else x = ((const uint32_t *)f.col)[row];
         if (x >= f.ncat) continue;
-        s += f.family == FAM_BB ? bb_score(fhp, gss, (int)x) : dd_score(fhp, f.asum, gss, x);
+        s += f.family == FAM_BB ? bb_score(fhp, gss, (int)x) : f.family == FAM_BBNC ? bbnc_score(gss, (int)x) : dd_score(fhp, f.asum, gss, x);
       } else if (f.kind == KIND_GP) {
         const uint32_t x = ((const uint32_t *)f.col)[row];
         if (x == GP_SENTINEL) continue;
@@ -468,6 +469,10 @@ __global__ void score_data_kernel(const FeatDev *__restrict__ feats, int nfeat, 
   double r;
   if (f.family == FAM_BB) {
     r = lbeta_d(h[0] + g[0], h[1] + g[1]) - lbeta_d(h[0], h[1]);
+  } else if (f.family == FAM_BBNC) {  // bbnc.cpp:61-73: Beta prior density of p + Bernoulli likelihood of the counts
+    const double p = g[0];
+    r = (p < 0.0 || p > 1.0) ? -CUDART_INF
+                             : (h[0] - 1.0) * log(p) + (h[1] - 1.0) * log1p(-p) - lbeta_d(h[0], h[1]) + g[1] * log(p) + g[2] * log1p(-p);
   } else if (f.family == FAM_DD) {
     r = lgamma(f.asum) - lgamma(f.asum + g[0]);
     for (uint32_t c = 0; c < f.dim; c++) r += lgamma(h[c] + g[1 + c]) - lgamma(h[c]);
@@ -870,6 +875,10 @@ __global__ void update_kernel(const FeatDev *__restrict__ feats, int nfeat, cons
         const int j = x ? 0 : 1;
         if (a >= 0) atomic_add_f64(blk + (size_t)a * 2 + j, -1.0);
         if (b >= 0) atomic_add_f64(blk + (size_t)b * 2 + j, 1.0);
+      } else if (f.family == FAM_BBNC) {  // ss = [p, heads, tails]: p is the group's parameter, never a delta
+        const int j = x ? 1 : 2;
+        if (a >= 0) atomic_add_f64(blk + (size_t)a * 3 + j, -1.0);
+        if (b >= 0) atomic_add_f64(blk + (size_t)b * 3 + j, 1.0);
       } else {  // ss = [count_sum, counts[dim]]; count_sum is re-derived from counts (dd_count_sum_kernel):
                 // a RED per cell on only K addresses per feature would serialise in L2
         if (a >= 0) atomic_add_f64(blk + (size_t)a * f.ss_w + 1 + x, -1.0);
@@ -1054,6 +1063,9 @@ __global__ void value_op_kernel(int family, uint32_t dim, int op, const double *
   if (family == FAM_BB) {
     if (op == 0) *score = (float)bb_score(hp, ss, x[0] != 0.0);
     else ss[x[0] != 0.0 ? 0 : 1] += sgn;
+  } else if (family == FAM_BBNC) {
+    if (op == 0) *score = (float)bbnc_score(ss, x[0] != 0.0);
+    else ss[x[0] != 0.0 ? 1 : 2] += sgn;
   } else if (family == FAM_DD) {
     const uint32_t xi = (uint32_t)x[0];
     if (op == 0) {

@@ -12,7 +12,7 @@
 
 namespace msb {
 
-enum Family : int { FAM_BB = 0, FAM_BNB = 1, FAM_GP = 2, FAM_NICH = 3, FAM_DD = 4, FAM_NIW = 5 };
+enum Family : int { FAM_BB = 0, FAM_BNB = 1, FAM_GP = 2, FAM_NICH = 3, FAM_DD = 4, FAM_NIW = 5, FAM_BBNC = 6 };
 
 // ---------------------------------------------------------------------------
 // msb_expf: exp() built only from correctly rounded IEEE-754 binary32
@@ -84,6 +84,8 @@ __device__ __forceinline__ double bb_score(const double *hp, const double *ss, i
   const double a = hp[0] + ss[0], b = hp[1] + ss[1];
   return log((x ? a : b) / (a + b));
 }
+// bbnc (src/models/bbnc.cpp:46-53): the group holds its own success probability p; ss = [p, heads, tails]
+__device__ __forceinline__ double bbnc_score(const double *ss, int x) { return x ? log(ss[0]) : log1p(-ss[0]); }
 __device__ __forceinline__ double dd_score(const double *hp, double asum, const double *ss, uint32_t x) {
   return log((hp[x] + ss[1 + x]) / (asum + ss[0]));
 }

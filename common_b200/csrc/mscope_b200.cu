@@ -136,6 +136,8 @@ struct msb_state {
   std::vector<void *> cols;
   int32_t *d_assign = nullptr;
   size_t region_rows = 0, max_chunk_rows = 0;
+  bool has_bbnc = false;
+  uint64_t group_seed = 0x6d73625f62626e63ull;  // Philox key of the per-group parameter draws (bbnc: p ~ Beta(alpha, beta))
   bool has_niw = false, has_scalar = false, tables_only = false, has_dd = false, has_nich = false;
   // workspaces
   float *d_params = nullptr; size_t params_cap = 0;
@@ -366,7 +368,7 @@ extern "C" MSB_API int msb_dataview_get_row(msb_dataview *dv, size_t idx, void *
 // ---------------------------------------------------------------------------
 static size_t hp_size(const msb_model_desc &m) {
   switch (m.family) {
-    case MSB_FAMILY_BB: case MSB_FAMILY_GP: return 2;
+    case MSB_FAMILY_BB: case MSB_FAMILY_GP: case MSB_FAMILY_BBNC: return 2;
     case MSB_FAMILY_BNB: return 3;
     case MSB_FAMILY_NICH: return 4;
     case MSB_FAMILY_DD: return m.dim;
@@ -377,7 +379,7 @@ static size_t hp_size(const msb_model_desc &m) {
 static size_t ss_size(const msb_model_desc &m) {
   switch (m.family) {
     case MSB_FAMILY_BB: case MSB_FAMILY_BNB: return 2;
-    case MSB_FAMILY_GP: case MSB_FAMILY_NICH: return 3;
+    case MSB_FAMILY_GP: case MSB_FAMILY_NICH: case MSB_FAMILY_BBNC: return 3;
     case MSB_FAMILY_DD: return (size_t)m.dim + 1;
     case MSB_FAMILY_NIW: return (size_t)m.dim * m.dim + m.dim + 1;
     default: return 0;
@@ -388,7 +390,7 @@ extern "C" MSB_API size_t msb_model_ss_size(const msb_model_desc *m) { return m 
 
 static int check_model(const msb_model_desc &m, size_t d) {
   switch (m.family) {
-    case MSB_FAMILY_BB: case MSB_FAMILY_BNB: case MSB_FAMILY_GP: case MSB_FAMILY_NICH: return MSB_OK;
+    case MSB_FAMILY_BB: case MSB_FAMILY_BNB: case MSB_FAMILY_GP: case MSB_FAMILY_NICH: case MSB_FAMILY_BBNC: return MSB_OK;
     case MSB_FAMILY_DD:
       if (m.dim == 0) return fail(MSB_ERR_INVALID, "no elements");  // distributions.hpp:429
       if (m.dim > 1024) return fail(MSB_ERR_UNSUPPORTED, "dd with more than 1024 categories is not built yet");
@@ -407,6 +409,10 @@ static int hp_field(const msb_model_desc &m, const std::string &key, size_t *off
   const size_t d = m.dim;
   switch (m.family) {
     case MSB_FAMILY_BB:
+      if (key == "alpha") { *off = 0; *cnt = 1; return MSB_OK; }
+      if (key == "beta") { *off = 1; *cnt = 1; return MSB_OK; }
+      break;
+    case MSB_FAMILY_BBNC:  // bbnc.cpp:159-167
       if (key == "alpha") { *off = 0; *cnt = 1; return MSB_OK; }
       if (key == "beta") { *off = 1; *cnt = 1; return MSB_OK; }
       break;
@@ -444,6 +450,11 @@ static int ss_field(const msb_model_desc &m, const std::string &key, size_t *off
     case MSB_FAMILY_BB:
       if (key == "heads") { *off = 0; *cnt = 1; return MSB_OK; }
       if (key == "tails") { *off = 1; *cnt = 1; return MSB_OK; }
+      break;
+    case MSB_FAMILY_BBNC:  // bbnc.cpp:112-118 exposes "p"; heads / tails are the message's other fields (schema.proto:14-18)
+      if (key == "p") { *off = 0; *cnt = 1; return MSB_OK; }
+      if (key == "heads") { *off = 1; *cnt = 1; return MSB_OK; }
+      if (key == "tails") { *off = 2; *cnt = 1; return MSB_OK; }
       break;
     case MSB_FAMILY_BNB:  // distributions.hpp:34-36
       if (key == "count") { *off = 0; *cnt = 1; return MSB_OK; }
@@ -497,6 +508,7 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
     hpo += hp_size(m);
     sso += max_groups * ss_size(m);
     switch (m.family) {
+      case MSB_FAMILY_BBNC: st->has_bbnc = true;  // fall through: the same two-row table, filled from the group's own p
       case MSB_FAMILY_BB: f.kind = KIND_TABLE; f.coltype = COL_U8; f.ncat = 2; f.dim = 2; st->has_scalar = true; break;
       case MSB_FAMILY_DD:
         f.kind = KIND_TABLE; f.ncat = m.dim; st->has_scalar = true; st->has_dd = true;
@@ -515,7 +527,7 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
     double *h = st->h_hp.data() + st->feats[d].hp_off;
     const msb_model_desc &m = models[d];
     switch (m.family) {
-      case MSB_FAMILY_BB: case MSB_FAMILY_GP: h[0] = h[1] = 1.0; break;
+      case MSB_FAMILY_BB: case MSB_FAMILY_GP: case MSB_FAMILY_BBNC: h[0] = h[1] = 1.0; break;
       case MSB_FAMILY_BNB: h[0] = h[1] = h[2] = 1.0; break;  // models.pyx:200
       case MSB_FAMILY_NICH: h[0] = 0.0; h[1] = h[2] = h[3] = 1.0; break;
       case MSB_FAMILY_DD: for (uint32_t i = 0; i < m.dim; i++) h[i] = 1.0; st->feats[d].asum = (double)m.dim; break;
@@ -1076,6 +1088,34 @@ extern "C" MSB_API int msb_state_groupsize(msb_state *st, size_t gid, size_t *co
   *count = (size_t)st->h_counts[slot];
   return MSB_OK;
 }
+// ---- per-group parameter draws (bbnc: p ~ Beta(alpha, beta), bbnc.cpp:120-125) on the host, from the same
+// counter-based Philox stream as everything else: key = group_seed, counter = (gid, feature, draw index), so
+// every replica of a multi-GPU state draws the same p without communicating.  (The reference draws from its
+// std engine; the stream differs, the distribution does not.)
+struct PhiloxStream {
+  uint64_t seed, a, b;
+  uint32_t i = 0;
+  double u01() {  // 53-bit uniform in (0, 1)
+    uint32_t r[4];
+    philox4x32_10(seed, a, (b << 20) | (i++), r);
+    const uint64_t bits = ((uint64_t)(r[0] >> 5) << 26) | (uint64_t)(r[1] >> 6);  // 27 + 26 = 53 bits
+    return ((double)bits + 0.5) * (1.0 / 9007199254740992.0);
+  }
+  double normal() { return std::sqrt(-2.0 * std::log(u01())) * std::cos(6.283185307179586 * u01()); }
+  double gamma(double k) {  // Marsaglia-Tsang
+    if (k < 1.0) return gamma(k + 1.0) * std::pow(u01(), 1.0 / k);
+    const double d = k - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
+    for (;;) {
+      double x, v;
+      do { x = normal(); v = 1.0 + c * x; } while (v <= 0.0);
+      v = v * v * v;
+      const double u = u01();
+      if (u < 1.0 - 0.0331 * x * x * x * x || std::log(u) < 0.5 * x * x + d * (1.0 - v + std::log(v))) return d * v;
+    }
+  }
+  double beta(double al, double be) { const double x = gamma(al), y = gamma(be); return x / (x + y); }
+};
+
 // restore == true: *gid is the identifier to give the group (deserialisation, group_manager.hpp:92-105:
 // identifiers are preserved and gcount becomes 1 + the largest one seen)
 static int create_group_impl(msb_state *st, size_t *gid, bool restore) {
@@ -1100,6 +1140,18 @@ static int create_group_impl(msb_state *st, size_t *gid, bool restore) {
     for (auto &f : st->feats)
       CU_TRY(cudaMemsetAsync(st->d_ss + f.ss_off + (size_t)slot * f.ss_w, 0, sizeof(double) * f.ss_w, st->ctx->stream));
     st->slot_dirty[slot] = 0;
+  }
+  if (st->has_bbnc) {  // hypers::create_group of bbnc samples the group's p (bbnc.cpp:120-125)
+    for (size_t d = 0; d < st->D; d++) {
+      const FeatDev &f = st->feats[d];
+      if (f.family != FAM_BBNC) continue;
+      PhiloxStream rng{st->group_seed, (uint64_t)g, (uint64_t)d};
+      const double *h = st->h_hp.data() + f.hp_off;
+      const double p = rng.beta(h[0], h[1]);
+      CU_TRY(cudaMemcpyAsync(st->d_ss + f.ss_off + (size_t)slot * f.ss_w, &p, sizeof(double), cudaMemcpyHostToDevice, st->ctx->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(st->ctx->stream));  // p is a local
+    st->slot_dirty[slot] = 1;
   }
   *gid = g;
   return MSB_OK;
@@ -1358,7 +1410,7 @@ extern "C" MSB_API int msb_state_delta_buffer_i32(msb_state *st, int32_t **dev_p
   REQUIRE(st && dev_ptr && count, "NULL argument");
   *dev_ptr = nullptr; *count = st->SS;
   for (const auto &m : st->models)
-    if (m.family != MSB_FAMILY_BB && m.family != MSB_FAMILY_DD) return MSB_OK;
+    if (m.family != MSB_FAMILY_BB && m.family != MSB_FAMILY_DD) return MSB_OK;  // (bbnc's p is not a count)
   if (st->n >= (1ull << 31) || getenv("MSB_NO_I32_DELTAS")) return MSB_OK;
   CU_TRY(cudaSetDevice(st->ctx->device));
   if (!st->d_delta_i32) CU_TRY(cudaMalloc(&st->d_delta_i32, sizeof(int32_t) * st->SS));
@@ -1448,7 +1500,7 @@ static int read_assign(msb_state *st, size_t eid, int32_t *slot) {
   return MSB_OK;
 }
 
-extern "C" MSB_API int msb_state_add_values(msb_state *st, const int64_t *gids, size_t n) {
+static int add_values_impl(msb_state *st, const int64_t *gids, size_t n, bool defer) {
   REQUIRE(st && gids, "NULL argument");
   REQUIRE(st->dv, "no dataview bound");
   REQUIRE(n == st->n, "wrong length");
@@ -1479,9 +1531,15 @@ extern "C" MSB_API int msb_state_add_values(msb_state *st, const int64_t *gids, 
   CU_TRY(cudaMemcpyAsync(st->d_newslot, req.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
   CU_TRY(cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned long long), ctx->stream));
   MSB_TRY(launch_update(st, 0, n));
+  if (defer) return refresh_counts(st);  // the caller all-reduces the delta buffer, then msb_state_apply_deltas
   return apply_deltas(st);
 }
 
+extern "C" MSB_API int msb_state_add_values(msb_state *st, const int64_t *gids, size_t n) { return add_values_impl(st, gids, n, false); }
+// multi-GPU replica initialisation: the local rows' contributions stay in the delta buffer; all-reduce it
+// (msb_state_delta_buffer), then msb_state_apply_deltas -- the same path as a sweep, so per-group parameters that are
+// not sums over rows (bbnc's p) are never touched
+extern "C" MSB_API int msb_state_add_values_deferred(msb_state *st, const int64_t *gids, size_t n) { return add_values_impl(st, gids, n, true); }
 extern "C" MSB_API int msb_state_add_value(msb_state *st, size_t gid, size_t eid) {
   REQUIRE(st, "NULL argument");
   REQUIRE(st->dv, "no dataview bound");

@@ -41,6 +41,14 @@ def allreduce_deltas(st, device):
     st.apply_deltas()
 
 
+def add_values_sharded(st, gids, device):
+    """replica initialisation through the delta buffer: every rank adds its own rows (deferred), the deltas are
+    summed, every replica applies the sum.  Unlike summing the suffstat buffers this never touches per-group
+    parameters that are not sums over rows (bbnc's p)."""
+    st.add_values(gids, defer_apply=True)
+    allreduce_deltas(st, device)
+
+
 def allreduce_suffstats(st, device):
     """replica initialisation: every rank added its own rows; the sum is the global state"""
     import torch.distributed as dist

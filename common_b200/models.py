@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _lib
 
-_FAMILY = {"bb": _lib.FAMILY_BB, "bnb": _lib.FAMILY_BNB, "gp": _lib.FAMILY_GP, "nich": _lib.FAMILY_NICH,
+_FAMILY = {"bbnc": _lib.FAMILY_BBNC, "bb": _lib.FAMILY_BB, "bnb": _lib.FAMILY_BNB, "gp": _lib.FAMILY_GP, "nich": _lib.FAMILY_NICH,
            "dd": _lib.FAMILY_DD, "niw": _lib.FAMILY_NIW}
 
 
@@ -65,6 +65,7 @@ def _reconstruct_model_descriptor(name, param):
 # Value types as seen through get_runtime_type (distributions.hpp:399-403): bb bool,
 # gp uint32, nich float32, dd int32 [R: SURVEY.md section 2a]
 bb = model_descriptor("bb", np.bool_, {"alpha": 1., "beta": 1.})
+bbnc = model_descriptor("bbnc", np.bool_, {"alpha": 1., "beta": 1.})            # models.pyx:248-253, src/models/bbnc.cpp
 bnb = model_descriptor("bnb", np.uint32, {"alpha": 1., "beta": 1., "r": 1.})   # models.pyx:196-205
 gp = model_descriptor("gp", np.uint32, {"alpha": 1., "inv_beta": 1.})
 nich = model_descriptor("nich", np.float32, {"mu": 0., "kappa": 1., "sigmasq": 1., "nu": 1.})

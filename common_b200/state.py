@@ -158,9 +158,11 @@ class state(object):
         _lib.check(_lib.load().msb_state_remove_value(self._h, eid, C.byref(v)))
         return v.value
 
-    def add_values(self, gids):
+    def add_values(self, gids, defer_apply=False):
+        """bulk add_value; defer_apply leaves the suffstat changes in the delta buffer (all-reduce, then apply_deltas)"""
         a = np.ascontiguousarray(gids, dtype=np.int64)
-        _lib.check(_lib.load().msb_state_add_values(self._h, a.ctypes.data, a.size))
+        fn = _lib.load().msb_state_add_values_deferred if defer_apply else _lib.load().msb_state_add_values
+        _lib.check(fn(self._h, a.ctypes.data, a.size))
 
     def score_value(self, eid, rng=None):
         k = self.ngroups()
@@ -290,7 +292,7 @@ class state(object):
         _lib.check(_lib.load().msb_state_apply_deltas(self._h))
 
     # ---- checkpoint / resume: the reference's wire format (microscopes/io/schema.proto) -----------------
-    _SS_KEYS = {"bb": ("heads", "tails"), "bnb": ("count", "sum"), "gp": ("count", "sum", "log_prod"),
+    _SS_KEYS = {"bbnc": ("p", "heads", "tails"), "bb": ("heads", "tails"), "bnb": ("count", "sum"), "gp": ("count", "sum", "log_prod"),
                 "nich": ("count", "mean", "count_times_variance"), "dd": ("counts",), "niw": ("count", "sum_x", "sum_xxT")}
 
     def _ss_counts(self, m, key):

@@ -40,7 +40,7 @@ def make_dataset(models, n, k_true, seed=73, stream=0, mask_frac=0.0, storage=No
     for d, m in enumerate(models):
         m = m()
         name = m.name()
-        if name == "bb":
+        if name in ("bb", "bbnc"):
             p = prng.beta(0.5, 0.5, size=k_true)
             x = rng.random(n) < p[z]
             dt = np.bool_

@@ -22,6 +22,8 @@ SCHEMA = {
     "GroupManager": {1: ("alpha", "float", False), 2: ("assignments", "int", True), 3: ("groups", "GroupData", True)},
     "MixtureModelGroup": {1: ("suffstats", "bytes", True)},
     "MixtureModelState": {1: ("hypers", "bytes", True), 2: ("groups", "bytes", False)},
+    "bbnc.Shared": {1: ("alpha", "float", False), 2: ("beta", "float", False)},                 # schema.proto:8-12
+    "bbnc.Group": {1: ("p", "float", False), 2: ("heads", "uint", False), 3: ("tails", "uint", False)},  # schema.proto:14-18
     # ---- distributions/io/schema.proto [R: unpinned] ----
     "bb.Shared": {1: ("alpha", "float", False), 2: ("beta", "float", False)},
     "bb.Group": {1: ("heads", "uint", False), 2: ("tails", "uint", False)},

@@ -94,8 +94,11 @@ enum msb_family {
   MSB_FAMILY_GP = 2,   /* GammaPoisson              hp: alpha inv_beta        ss: count sum log_prod */
   MSB_FAMILY_NICH = 3, /* NormalInverseChiSq        hp: mu kappa sigmasq nu   ss: count mean count_times_variance */
   MSB_FAMILY_DD = 4,   /* DirichletDiscrete(dim)    hp: alphas[dim]           ss: count_sum counts[dim] */
-  MSB_FAMILY_NIW = 5   /* NormalInverseWishart(dim) hp: mu[dim] kappa psi[dim*dim] nu
+  MSB_FAMILY_NIW = 5,  /* NormalInverseWishart(dim) hp: mu[dim] kappa psi[dim*dim] nu
                                                     ss: count sum_x[dim] sum_xxT[dim*dim] */
+  MSB_FAMILY_BBNC = 6  /* BetaBernoulliNonConj (in-tree model, src/models/bbnc.cpp)
+                                                    hp: alpha beta            ss: p heads tails
+                          p is the group's own parameter, drawn from Beta(alpha, beta) when the group is created */
 };
 
 typedef struct msb_model_desc {
@@ -175,6 +178,9 @@ MSB_API int msb_state_assignments_async(msb_state *st, int64_t *out, size_t n);
 MSB_API int msb_state_assignments_wait(msb_state *st);
 /* bulk add_value of every currently unassigned entity whose gids[i] != -1 */
 MSB_API int msb_state_add_values(msb_state *st, const int64_t *gids, size_t n);
+/* the same, leaving the suffstat changes in the delta buffer (multi-GPU replica initialisation: all-reduce the
+ * buffer of msb_state_delta_buffer, then msb_state_apply_deltas) */
+MSB_API int msb_state_add_values_deferred(msb_state *st, const int64_t *gids, size_t n);
 
 /* single-entity calls, entity_state.hpp:57-72 */
 MSB_API int msb_state_add_value(msb_state *st, size_t gid, size_t eid);

@@ -49,6 +49,7 @@ size_t orc_hp_size(const orc_model *m) {
   switch (m->family) {
     case ORC_BB: return 2;                                 /* alpha beta */
     case ORC_BNB: return 3;                                /* alpha beta r */
+    case ORC_BBNC: return 2;                               /* alpha beta (src/models/bbnc.cpp) */
     case ORC_GP: return 2;                                 /* alpha inv_beta */
     case ORC_NICH: return 4;                               /* mu kappa sigmasq nu */
     case ORC_DD: return m->dim;                            /* alphas[dim] */
@@ -60,6 +61,7 @@ size_t orc_ss_size(const orc_model *m) {
   switch (m->family) {
     case ORC_BB: return 2;                                 /* heads tails */
     case ORC_BNB: return 2;                                /* count sum */
+    case ORC_BBNC: return 3;                               /* p heads tails */
     case ORC_GP: return 3;                                 /* count sum log_prod */
     case ORC_NICH: return 3;                               /* count mean count_times_variance */
     case ORC_DD: return (size_t)m->dim + 1;                /* count_sum counts[dim] */
@@ -213,6 +215,11 @@ double orc_score_data(const orc_model *m, const double *hp, const double *ss) {
       for (unsigned i = 0; i < m->dim; i++) { asum += hp[i]; s += lgamma(hp[i] + ss[1 + i]) - lgamma(hp[i]); }
       return s + lgamma(asum) - lgamma(asum + ss[0]);
     }
+    case ORC_BBNC: { /* bbnc.cpp:61-73: Beta(alpha, beta) density of p + Bernoulli likelihood of (heads, tails) */
+      double p = ss[0];
+      if (p < 0.0 || p > 1.0) return -INFINITY;
+      return (hp[0] - 1.0) * log(p) + (hp[1] - 1.0) * log1p(-p) - lbeta(hp[0], hp[1]) + ss[1] * log(p) + ss[2] * log1p(-p);
+    }
     case ORC_BNB: { /* the part (count, sum) determine: lbeta(a_n, b_n) - lbeta(alpha, beta) */
       double a = hp[0] + hp[2] * ss[0], b = hp[1] + ss[1];
       return lbeta(a, b) - lbeta(hp[0], hp[1]);
@@ -332,6 +339,9 @@ double orc_score_value(const orc_model *m, const double *hp, const double *ss, c
     case ORC_BB: return prec == 32 ? (double)bb_score32(hp, ss, x[0]) : bb_score64(hp, ss, x[0]);
     case ORC_DD: return prec == 32 ? (double)dd_score32(m->dim, hp, ss, x[0]) : dd_score64(m->dim, hp, ss, x[0]);
     case ORC_BNB: return prec == 32 ? (double)bnb_score32(hp, ss, x[0]) : bnb_score64(hp, ss, x[0]);
+    case ORC_BBNC: /* bbnc.cpp:46-53: value ? log(p) : log(1. - p), p a float member */
+      if (prec == 32) { float p = (float)ss[0]; return (double)(x[0] != 0.0 ? logf(p) : logf((float)(1. - p))); }
+      return x[0] != 0.0 ? log(ss[0]) : log1p(-ss[0]);
     case ORC_GP: return prec == 32 ? (double)gp_score32(hp, ss, x[0]) : gp_score64(hp, ss, x[0]);
     case ORC_NICH: return prec == 32 ? (double)nich_score32(hp, ss, x[0]) : nich_score64(hp, ss, x[0]);
     case ORC_NIW: {
@@ -354,6 +364,7 @@ void orc_add_value(const orc_model *m, const double *hp, double *ss, const doubl
     case ORC_BB: ss[x[0] != 0.0 ? 0 : 1] += 1.0; break;
     case ORC_DD: ss[0] += 1.0; ss[1 + (long)x[0]] += 1.0; break;
     case ORC_BNB: ss[0] += 1.0; ss[1] += x[0]; break;
+    case ORC_BBNC: ss[x[0] != 0.0 ? 1 : 2] += 1.0; break;   /* bbnc.cpp:21-30 */
     case ORC_GP:
       ss[0] += 1.0; ss[1] += x[0];
       ss[2] = rnd(ss[2] + rnd(prec == 32 ? (double)lgammaf((float)x[0] + 1.f) : lgamma(x[0] + 1.0), prec), prec);
@@ -384,6 +395,7 @@ void orc_remove_value(const orc_model *m, const double *hp, double *ss, const do
     case ORC_BB: ss[x[0] != 0.0 ? 0 : 1] -= 1.0; break;
     case ORC_DD: ss[0] -= 1.0; ss[1 + (long)x[0]] -= 1.0; break;
     case ORC_BNB: ss[0] -= 1.0; ss[1] -= x[0]; break;
+    case ORC_BBNC: ss[x[0] != 0.0 ? 1 : 2] -= 1.0; break;   /* bbnc.cpp:32-44 */
     case ORC_GP:
       ss[0] -= 1.0; ss[1] -= x[0];
       ss[2] = rnd(ss[2] - rnd(prec == 32 ? (double)lgammaf((float)x[0] + 1.f) : lgamma(x[0] + 1.0), prec), prec);

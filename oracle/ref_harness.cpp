@@ -121,6 +121,43 @@ struct gp_group : public models::group {
 };
 std::shared_ptr<models::group> gp_hypers::create_group(rng_t &) const { return std::make_shared<gp_group>(); }
 
+// ---- bbnc (src/models/bbnc.cpp restated: its translation unit needs protobuf and `distributions`) ------------
+struct bbnc_hypers : public models::hypers {
+  float alpha = 1.f, beta = 1.f;
+  hyperparam_bag_t get_hp() const override { return ""; }
+  void set_hp(const hyperparam_bag_t &) override {}
+  void set_hp(const models::hypers &s) override { *this = static_cast<const bbnc_hypers &>(s); }
+  value_mutator get_hp_mutator(const std::string &key) override {
+    if (key == "alpha") return value_mutator(&alpha);
+    if (key == "beta") return value_mutator(&beta);
+    throw std::runtime_error("unknown key: " + key);
+  }
+  std::shared_ptr<models::group> create_group(rng_t &rng) const override;
+  std::string debug_str() const override { return "bbnc"; }
+};
+struct bbnc_group : public models::group {
+  float p = 0.5f;
+  unsigned heads = 0, tails = 0;
+  void add_value(const models::hypers &, const value_accessor &v, rng_t &) override { if (v.get<bool>(0)) heads++; else tails++; }
+  void remove_value(const models::hypers &, const value_accessor &v, rng_t &) override { if (v.get<bool>(0)) heads--; else tails--; }
+  float score_value(const models::hypers &, const value_accessor &v, rng_t &) const override {
+    return v.get<bool>(0) ? logf(p) : logf(1. - p);
+  }
+  float score_data(const models::hypers &, rng_t &) const override { return 0.f; }
+  void sample_value(const models::hypers &, value_mutator &, rng_t &) const override {}
+  suffstats_bag_t get_ss() const override { return ""; }
+  void set_ss(const suffstats_bag_t &) override {}
+  void set_ss(const models::group &g) override { *this = static_cast<const bbnc_group &>(g); }
+  value_mutator get_ss_mutator(const std::string &key) override {
+    if (key == "p") return value_mutator(&p);
+    if (key == "heads") return value_mutator(&heads);
+    if (key == "tails") return value_mutator(&tails);
+    throw std::runtime_error("unknown key: " + key);
+  }
+  std::string debug_str() const override { return "bbnc"; }
+};
+std::shared_ptr<models::group> bbnc_hypers::create_group(rng_t &) const { return std::make_shared<bbnc_group>(); }
+
 // ---- bnb ----------------------------------------------------------------------
 struct bnb_hypers : public models::hypers {
   float alpha = 1.f, beta = 1.f;
@@ -316,6 +353,7 @@ struct ref_model : public models::model {
     switch (m.family) {
       case ORC_BB: return std::make_shared<bb_hypers>();
       case ORC_BNB: return std::make_shared<bnb_hypers>();
+      case ORC_BBNC: return std::make_shared<bbnc_hypers>();
       case ORC_GP: return std::make_shared<gp_hypers>();
       case ORC_NICH: return std::make_shared<nich_hypers>();
       case ORC_DD: return std::make_shared<dd_hypers>(m.dim);
@@ -325,7 +363,7 @@ struct ref_model : public models::model {
   }
   runtime_type get_runtime_type() const override {
     switch (m.family) {
-      case ORC_BB: return runtime_type(TYPE_B);
+      case ORC_BB: case ORC_BBNC: return runtime_type(TYPE_B);
       case ORC_BNB: case ORC_GP: return runtime_type(TYPE_U32);
       case ORC_NICH: return runtime_type(TYPE_F32);
       case ORC_DD: return runtime_type(TYPE_I32);
@@ -358,6 +396,7 @@ built_state build(const orc_model *models, size_t D, const double *hp, const dou
     switch (models[d].family) {
       case ORC_BB: set_f(h->get_hp_mutator("alpha"), p[0]); set_f(h->get_hp_mutator("beta"), p[1]); break;
       case ORC_BNB: set_f(h->get_hp_mutator("alpha"), p[0]); set_f(h->get_hp_mutator("beta"), p[1]); set_f(h->get_hp_mutator("r"), p[2]); break;
+      case ORC_BBNC: set_f(h->get_hp_mutator("alpha"), p[0]); set_f(h->get_hp_mutator("beta"), p[1]); break;
       case ORC_GP: set_f(h->get_hp_mutator("alpha"), p[0]); set_f(h->get_hp_mutator("inv_beta"), p[1]); break;
       case ORC_NICH:
         set_f(h->get_hp_mutator("mu"), p[0]); set_f(h->get_hp_mutator("kappa"), p[1]);
@@ -382,6 +421,7 @@ built_state build(const orc_model *models, size_t D, const double *hp, const dou
       switch (models[d].family) {
         case ORC_BB: set_u(g->get_ss_mutator("heads"), s[0]); set_u(g->get_ss_mutator("tails"), s[1]); break;
         case ORC_BNB: set_u(g->get_ss_mutator("count"), s[0]); set_u(g->get_ss_mutator("sum"), s[1]); break;
+        case ORC_BBNC: set_f(g->get_ss_mutator("p"), s[0]); set_u(g->get_ss_mutator("heads"), s[1]); set_u(g->get_ss_mutator("tails"), s[2]); break;
         case ORC_GP: set_u(g->get_ss_mutator("count"), s[0]); set_u(g->get_ss_mutator("sum"), s[1]); set_f(g->get_ss_mutator("log_prod"), s[2]); break;
         case ORC_NICH: set_u(g->get_ss_mutator("count"), s[0]); set_f(g->get_ss_mutator("mean"), s[1]); set_f(g->get_ss_mutator("count_times_variance"), s[2]); break;
         case ORC_DD: {

@@ -18,8 +18,7 @@ def run(descs, n, k, rank, world, device, ctx):
     st = cb.state(ctx, descs, max_groups=k + 2, cluster_hp={"alpha": 1.0})
     st.bind(cb.numpy_dataview(arr))
     gids = np.asarray([st.create_group() for _ in range(k)])
-    st.add_values(gids[z])
-    cbd.allreduce_suffstats(st, device)
+    cbd.add_values_sharded(st, gids[z], device)
     for it in range(3):
         st.sweep(seed=9, sweep=it, row_id_offset=rank * n, defer_apply=True, wait=False)
         cbd.allreduce_deltas(st, device)
@@ -43,7 +42,7 @@ def main():
     torch.cuda.set_stream(torch.cuda.ExternalStream(ctx.stream(), device=device))
     ok = True
     for name, descs in (("counts only (int32 deltas)", [cb.dd(40), cb.bb, cb.dd(7), cb.bb]),
-                        ("mixed (fp64 deltas)", [cb.dd(9), cb.nich, cb.gp, cb.bb, cb.bnb])):
+                        ("mixed (fp64 deltas)", [cb.dd(9), cb.nich, cb.gp, cb.bb, cb.bnb, cb.bbnc])):
         same, a, sizes = run(descs, 40000, 12, rank, world, device, ctx)
         os.environ["MSB_NO_I32_DELTAS"] = "1"
         same2, b, sizes2 = run(descs, 40000, 12, rank, world, device, ctx)

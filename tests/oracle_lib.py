@@ -9,8 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB = os.path.join(ORACLE_DIR, "libmsb_oracle.so")
 
-BB, BNB, GP, NICH, DD, NIW = range(6)
-FAMILY = {"bb": BB, "bnb": BNB, "gp": GP, "nich": NICH, "dd": DD, "niw": NIW}
+BB, BNB, GP, NICH, DD, NIW, BBNC = range(7)
+FAMILY = {"bbnc": BBNC, "bb": BB, "bnb": BNB, "gp": GP, "nich": NICH, "dd": DD, "niw": NIW}
 
 
 class OrcModel(C.Structure):
@@ -67,7 +67,7 @@ class Oracle(object):
         d = desc()
         hp = dict(d.default_hyperparams(), **(hp or {}))
         n = d.name()
-        if n in ("bb",): return np.array([hp["alpha"], hp["beta"]], np.float64)
+        if n in ("bb", "bbnc"): return np.array([hp["alpha"], hp["beta"]], np.float64)
         if n == "bnb": return np.array([hp["alpha"], hp["beta"], hp["r"]], np.float64)
         if n == "gp": return np.array([hp["alpha"], hp["inv_beta"]], np.float64)
         if n == "nich": return np.array([hp["mu"], hp["kappa"], hp["sigmasq"], hp["nu"]], np.float64)

@@ -38,6 +38,12 @@ def make_state(ctx, oracle, descs, n, k, seed=1, mask_frac=0.0, storage=None, hp
     st.add_values(np.asarray(gids)[z])
     hp_flat = np.concatenate(hps)
     ss, counts = ol.build_suffstats(oracle, descs, hp_flat, view, z, k + extra_empty)
+    off = 0
+    for d, desc in enumerate(descs):     # per-group parameters that are not sums over rows: bbnc's p, drawn at create_group
+        if desc().name() == "bbnc":
+            for c, g in enumerate(gids):
+                ss[c, off] = st.get_suffstats(d, g, "p")[0]
+        off += oracle.ss_size(oracle.model(desc))
     return st, view, z, gids, hp_flat, ss, counts
 
 
@@ -46,8 +52,9 @@ FAMILIES = {
     "dd": [cb.dd(7), cb.dd(256), cb.dd(128)],
     "gp": [cb.gp] * 3,
     "bnb": [cb.bnb] * 3,
+    "bbnc": [cb.bbnc] * 4,
     "nich": [cb.nich] * 4,
-    "mixed": [cb.bb, cb.gp, cb.nich, cb.dd(16), cb.bb, cb.nich, cb.bnb],
+    "mixed": [cb.bb, cb.gp, cb.nich, cb.dd(16), cb.bb, cb.nich, cb.bnb, cb.bbnc],
 }
 
 
@@ -250,7 +257,7 @@ def test_golden_vectors_through_the_value_abi(ctx):
     import ctypes as C
     from common_b200 import _lib
     lib = _lib.load()
-    fam = {"bb": _lib.FAMILY_BB, "bnb": _lib.FAMILY_BNB, "dd": _lib.FAMILY_DD, "gp": _lib.FAMILY_GP, "nich": _lib.FAMILY_NICH, "niw": _lib.FAMILY_NIW}
+    fam = {"bb": _lib.FAMILY_BB, "bbnc": _lib.FAMILY_BBNC, "bnb": _lib.FAMILY_BNB, "dd": _lib.FAMILY_DD, "gp": _lib.FAMILY_GP, "nich": _lib.FAMILY_NICH, "niw": _lib.FAMILY_NIW}
     with open(os.path.join(GOLD, "score_value.json")) as f:
         cases = json.load(f)["cases"]
     for c in cases:
@@ -578,7 +585,7 @@ def test_sweep_with_niw_features_draws_bit_exactly(ctx, oracle, descs):
     st.close()
 
 
-@pytest.mark.parametrize("name,cond", [("bb", 1.0), ("dd", 1.0), ("gp", 4.0), ("bnb", 4.0), ("nich", 4.0), ("mixed", 4.0), ("niw", 50.0)])
+@pytest.mark.parametrize("name,cond", [("bb", 1.0), ("bbnc", 1.0), ("dd", 1.0), ("gp", 4.0), ("bnb", 4.0), ("nich", 4.0), ("mixed", 4.0), ("niw", 50.0)])
 def test_fp64_scores_within_1e12_of_the_oracle(ctx, oracle, name, cond):
     # north_star tolerance for fp64: 1e-12 relative.  `cond` is the conditioning of the closed form itself in
     # double (lgamma(a + x) - lgamma(a) and lgamma((nu+1)/2) - lgamma(nu/2) cancel; a d x d Cholesky for niw):
@@ -773,3 +780,35 @@ def test_niw_rows_far_from_the_origin(ctx, oracle, dim, offset):
     st.sweep(seed=3, sweep=0)
     assert np.max(rel_err(st.read_last_scores(), want)) < 4 * RTOL
     st.close()
+
+
+def test_bbnc_group_parameter_is_a_beta_draw_and_survives_everything(ctx, oracle):
+    # bbnc (src/models/bbnc.cpp): create_group draws p ~ Beta(alpha, beta) (:120-125); p is exposed through
+    # get_ss_mutator("p") (:112-118); score_value is log p / log(1 - p) (:46-53); score_data (:61-73)
+    descs = [cb.bbnc, cb.bb]
+    n, k = 4000, 30
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=141, hp={0: {"alpha": 2.0, "beta": 5.0}})
+    p = np.array([st.get_suffstats(0, g, "p")[0] for g in gids])
+    assert np.all((p > 0) & (p < 1)) and len(np.unique(p)) == k
+    assert abs(p.mean() - 2.0 / 7.0) < 0.08                          # Beta(2, 5) mean, 30 draws
+    st2, _, _, gids2, _, _, _ = make_state(ctx, oracle, descs, n, k, seed=141, hp={0: {"alpha": 2.0, "beta": 5.0}})
+    assert np.array_equal(p, [st2.get_suffstats(0, g, "p")[0] for g in gids2])   # counter-based: the same draws again
+    # a sweep moves rows but never touches p; heads / tails follow the rows
+    old = np.searchsorted(gids, st.assignments()).astype(np.int32)
+    st.sweep(seed=2, sweep=0)
+    new = np.searchsorted(gids, st.assignments()).astype(np.int32)
+    oracle.update_rows(descs, hp, ss, counts, view, old, new)
+    for c, g in enumerate(gids):
+        assert st.get_suffstats(0, g, "p")[0] == p[c]
+        assert st.get_suffstats(0, g, "heads")[0] == ss[c, 1] and st.get_suffstats(0, g, "tails")[0] == ss[c, 2]
+        want = oracle.score_data(oracle.model(cb.bbnc), hp[:2], ss[c, :3])
+        assert abs(st.score_likelihood(0, g) - want) <= 2e-6 * max(1.0, abs(want))
+    st.set_suffstats(0, gids[3], "p", 0.25)                           # the mutator the reference exposes
+    _, S = st.score_rows(0, 50)
+    ss[3, 0] = 0.25
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, 0, 50)
+    assert np.max(rel_err(S, want)) < RTOL
+    blob = st.serialize()                                             # BetaBernoulliNonConj messages are in-tree (schema.proto:6-19)
+    st3 = cb.state.deserialize(ctx, descs, view, blob)
+    assert abs(st3.get_suffstats(0, gids[3], "p")[0] - 0.25) < 1e-7
+    st.close(); st2.close(); st3.close()

@@ -10,7 +10,7 @@ import common_b200 as cb
 import oracle_lib as ol
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-FAM = {"bb": ol.BB, "bnb": ol.BNB, "dd": ol.DD, "gp": ol.GP, "nich": ol.NICH, "niw": ol.NIW}
+FAM = {"bb": ol.BB, "bbnc": ol.BBNC, "bnb": ol.BNB, "dd": ol.DD, "gp": ol.GP, "nich": ol.NICH, "niw": ol.NIW}
 
 
 def _cases():
@@ -258,3 +258,22 @@ def test_bnb_predictive_normalises_and_chains(oracle):
         data_term += gammaln(hp[2] + x) - gammaln(hp[2]) - gammaln(x + 1.0)
         oracle.add_value(m, hp, ss, x)
     assert abs(oracle.score_data(m, hp, ss) - (chain - data_term)) < 1e-9 * max(1.0, abs(chain))
+
+
+def test_bbnc_follows_the_in_tree_source(oracle):
+    # src/models/bbnc.cpp: score_value :46-53, add / remove :21-44, score_data :61-73 (hand-computed here)
+    m = ol.OrcModel(ol.BBNC, 0)
+    hp = np.array([2.0, 3.0])
+    ss = np.array([0.3, 0.0, 0.0])
+    assert oracle.score_value(m, hp, ss, 1.0) == pytest.approx(np.log(0.3), rel=1e-15)
+    assert oracle.score_value(m, hp, ss, 0.0) == pytest.approx(np.log(0.7), rel=1e-15)
+    assert oracle.score_value(m, hp, ss, 1.0, 32) == pytest.approx(np.log(0.3), rel=3e-7)
+    for x in (1, 1, 0, 1):
+        oracle.add_value(m, hp, ss, float(x))
+    assert ss.tolist() == [0.3, 3.0, 1.0]
+    from scipy.special import betaln
+    want = (2 - 1) * np.log(0.3) + (3 - 1) * np.log(0.7) - betaln(2, 3) + 3 * np.log(0.3) + 1 * np.log(0.7)
+    assert oracle.score_data(m, hp, ss) == pytest.approx(want, rel=1e-13)
+    oracle.remove_value(m, hp, ss, 1.0)
+    assert ss.tolist() == [0.3, 2.0, 1.0]
+    assert oracle.score_data(m, hp, np.array([1.5, 0.0, 0.0])) == -np.inf      # p outside [0, 1]
