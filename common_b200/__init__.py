@@ -9,10 +9,10 @@ Python layer (microscopes/models.pyx, microscopes/common/recarray/dataview.pyx).
 """
 from . import _lib
 from ._lib import Context, MsbError
-from .models import bb, bbnc, bnb, gp, nich, dd, niw, model_descriptor
+from .models import bb, bbnc, bnb, gp, nich, dd, dm, niw, model_descriptor
 from .dataview import numpy_dataview
 from .state import state, sample_discrete_log, philox_uniforms
 from . import synth
 
-__all__ = ["Context", "MsbError", "bb", "bbnc", "bnb", "gp", "nich", "dd", "niw", "model_descriptor",
+__all__ = ["Context", "MsbError", "bb", "bbnc", "bnb", "gp", "nich", "dd", "dm", "niw", "model_descriptor",
            "numpy_dataview", "state", "sample_discrete_log", "philox_uniforms"]

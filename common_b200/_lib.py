@@ -19,7 +19,7 @@ MSB_OK, MSB_ERR_INVALID, MSB_ERR_CUDA, MSB_ERR_NOMEM, MSB_ERR_UNSUPPORTED, MSB_E
 # type_info.h:10-34
 TYPE_B, TYPE_I8, TYPE_U8, TYPE_I16, TYPE_U16, TYPE_I32, TYPE_U32, TYPE_I64, TYPE_U64, TYPE_F32, TYPE_F64 = range(11)
 # distributions.hpp:58-64
-FAMILY_BB, FAMILY_BNB, FAMILY_GP, FAMILY_NICH, FAMILY_DD, FAMILY_NIW, FAMILY_BBNC = range(7)
+FAMILY_BB, FAMILY_BNB, FAMILY_GP, FAMILY_NICH, FAMILY_DD, FAMILY_NIW, FAMILY_BBNC, FAMILY_DM = range(8)
 
 
 class MsbError(RuntimeError):

@@ -5,7 +5,7 @@
 
 namespace msb {
 
-enum Kind : int { KIND_TABLE = 0, KIND_GP = 1, KIND_NICH = 2, KIND_NIW = 3 };
+enum Kind : int { KIND_TABLE = 0, KIND_GP = 1, KIND_NICH = 2, KIND_NIW = 3, KIND_DM = 4 };
 enum ColType : int { COL_U8 = 0, COL_U16 = 1, COL_U32 = 2, COL_F32 = 3 };
 
 constexpr uint32_t GP_SENTINEL = 0xFFFFFFFFu;
@@ -36,6 +36,8 @@ struct FeatDev {
   uint32_t src_prim;
   uint32_t src_n;
 };
+
+__device__ __forceinline__ void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
 
 // ---------------------------------------------------------------------------
 // AoS -> SoA pack: applies runtime_cast (runtime_type.hpp:145-166) once per
@@ -80,6 +82,15 @@ __global__ void pack_kernel(const uint8_t *__restrict__ data, const uint8_t *__r
     if (masked) dst[0] = CUDART_NAN_F;
     return;
   }
+  if (f.kind == KIND_DM) {  // a row of dim counts; masked row: sentinel in element 0
+    uint32_t *dst = (uint32_t *)f.col + row * (size_t)f.dim;
+    for (uint32_t i = 0; i < f.dim; i++) {
+      const double c = load_prim(src + i * ps, f.src_prim);
+      dst[i] = c < 0.0 ? 0u : (c >= 4294967294.0 ? 4294967294u : (uint32_t)c);
+    }
+    if (masked) dst[0] = GP_SENTINEL;
+    return;
+  }
   const double v = load_prim(src, f.src_prim);
   if (f.kind == KIND_NICH) {
     ((float *)f.col)[row] = masked ? CUDART_NAN_F : (float)v;
@@ -106,7 +117,7 @@ __global__ void scorecol_kernel(const FeatDev *__restrict__ feats, int nfeat, si
   const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // n_pad is a multiple of the block size
   const int d = blockIdx.y;
   const FeatDev f = feats[d];
-  if (f.kind == KIND_NIW) return;
+  if (f.kind == KIND_NIW || f.kind == KIND_DM) return;
   uint32_t out;
   bool slow = false;
   if (f.kind == KIND_NICH) {
@@ -182,6 +193,17 @@ ingest_tile_kernel(const uint8_t *__restrict__ data, const uint8_t *__restrict__
           dsc[i] = (float)((double)(float)v - (double)cen[i]);
         }
         if (masked) dst[0] = dsc[0] = CUDART_NAN_F;
+      }
+      continue;
+    }
+    if (f.kind == KIND_DM) {
+      if (live) {
+        uint32_t *dst = (uint32_t *)f.col + row * (size_t)f.dim;
+        for (uint32_t i = 0; i < f.dim; i++) {
+          const double c = load_prim(rec + f.src_off + i * ps, f.src_prim);
+          dst[i] = c < 0.0 ? 0u : (c >= 4294967294.0 ? 4294967294u : (uint32_t)c);
+        }
+        if (masked) dst[0] = GP_SENTINEL;
       }
       continue;
     }
@@ -467,7 +489,12 @@ __global__ void score_data_kernel(const FeatDev *__restrict__ feats, int nfeat, 
   const double *h = hp + f.hp_off;
   const double *g = ss + f.ss_off + (size_t)col2slot[col] * f.ss_w;
   double r;
-  if (f.family == FAM_BB) {
+  if (f.family == FAM_DM) {  // dm.cpp:79-95; ss = [counts[dim], ratio]
+    double asum = 0.0, csum = 0.0;
+    r = g[f.dim];
+    for (uint32_t c = 0; c < f.dim; c++) { asum += h[c]; csum += g[c]; r += lgamma(g[c] + h[c]) - lgamma(h[c]); }
+    r += lgamma(asum) - lgamma(asum + csum);
+  } else if (f.family == FAM_BB) {
     r = lbeta_d(h[0] + g[0], h[1] + g[1]) - lbeta_d(h[0], h[1]);
   } else if (f.family == FAM_BBNC) {  // bbnc.cpp:61-73: Beta prior density of p + Bernoulli likelihood of the counts
     const double p = g[0];
@@ -588,6 +615,72 @@ __global__ void score_assignment_kernel(const double *__restrict__ counts, const
   if (threadIdx.x == 0) {
     out[0] = s_sum - (lgamma(s_n + alpha) - lgamma(1.0 + alpha));
     out[1] = s_n;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dm (Dirichlet-multinomial over count vectors, src/models/dm.cpp:38-76).  One block per group column: the block
+// holds e_i = alpha_i + counts_i in shared memory, each thread scores rows:
+//   sum_i [lgamma(e_i + x_i) - lgamma(e_i) - lgamma(x_i + 1)] + lgamma(X + 1) + lgamma(E) - lgamma(E + X)
+// scores[(row - row_lo) * ld + k] += that (OUT = float: the production path; OUT = double: the fp64 path).
+// ---------------------------------------------------------------------------
+template <typename OUT>
+__global__ void dm_score_kernel(FeatDev f, const double *__restrict__ hp, const double *__restrict__ ss,
+                                const int32_t *__restrict__ col2slot, OUT *__restrict__ scores, size_t ld,
+                                size_t row_lo, size_t row_hi) {
+  extern __shared__ double sm[];
+  const int C = (int)f.dim;
+  double *e = sm;  // C
+  __shared__ double s_E;
+  const int k = blockIdx.y;
+  const double *h = hp + f.hp_off;
+  const double *g = ss + f.ss_off + (size_t)col2slot[k] * f.ss_w;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) e[i] = h[i] + g[i];
+  __syncthreads();
+  if (threadIdx.x == 0) { double E = 0.0; for (int i = 0; i < C; i++) E += e[i]; s_E = E; }
+  __syncthreads();
+  const double E = s_E, lgE = lgamma(E);
+  const size_t row = row_lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= row_hi) return;
+  const uint32_t *x = (const uint32_t *)f.col + row * (size_t)C;
+  if (x[0] == GP_SENTINEL) return;  // masked
+  double s = 0.0, X = 0.0;
+  for (int i = 0; i < C; i++) {
+    const uint32_t xi = x[i];
+    if (xi) { s += lgamma_rise(e[i], xi) - lgamma((double)xi + 1.0); X += (double)xi; }
+  }
+  s += lgamma(X + 1.0) + lgE - lgamma(E + X);
+  scores[(row - row_lo) * ld + k] += (OUT)s;
+}
+
+// dm update: one warp per moved row, lanes over the categories; counts += / -= x, ratio as dm.cpp:9-36
+__global__ void update_dm_kernel(FeatDev f, const int32_t *__restrict__ old_slot, const int32_t *__restrict__ new_slot,
+                                 size_t row_lo, size_t row_hi, double *__restrict__ delta) {
+  const size_t row = row_lo + (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= row_hi) return;
+  const int a = old_slot ? old_slot[row] : -1;
+  const int b = new_slot ? new_slot[row - row_lo] : -1;
+  if (a == b) return;
+  const int C = (int)f.dim;
+  const uint32_t *x = (const uint32_t *)f.col + row * (size_t)C;
+  if (x[0] == GP_SENTINEL) return;
+  double *blk = delta + f.ss_off;
+  double part = 0.0, X = 0.0;  // sum lgamma(x_i + 1), sum x_i over this lane's categories
+  for (int i = lane; i < C; i += 32) {
+    const double xi = (double)x[i];
+    if (xi != 0.0) {
+      if (a >= 0) atomic_add_f64(blk + (size_t)a * f.ss_w + i, -xi);
+      if (b >= 0) atomic_add_f64(blk + (size_t)b * f.ss_w + i, xi);
+      part += lgamma(xi + 1.0);
+      X += xi;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { part += __shfl_xor_sync(0xffffffffu, part, o); X += __shfl_xor_sync(0xffffffffu, X, o); }
+  if (lane == 0) {
+    const double r = lgamma(X + 1.0) - part;  // add_value: ratio += lgamma(X + 1) - sum lgamma(x_i + 1)
+    if (a >= 0) atomic_add_f64(blk + (size_t)a * f.ss_w + C, -r);
+    if (b >= 0) atomic_add_f64(blk + (size_t)b * f.ss_w + C, r);
   }
 }
 
@@ -848,7 +941,6 @@ __global__ void philox_fill_kernel(uint64_t seed, uint64_t sweep, uint64_t row0,
 // (row, feature) cell whose row moved (base.hpp:25-26).  All device suffstats
 // are additive fp64 (integers exact), so the deltas can be summed across GPUs.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
 
 constexpr int UPDATE_SLAB = 16;
 __global__ void update_kernel(const FeatDev *__restrict__ feats, int nfeat, const int32_t *__restrict__ old_slot,
@@ -1088,6 +1180,17 @@ __global__ void value_op_kernel(int family, uint32_t dim, int op, const double *
       ss[1] = add[0] > 0.0 ? add[1] / add[0] : 0.0;
       double ctv = add[0] > 1.0 ? add[2] - add[1] * ss[1] : 0.0;
       ss[2] = ctv > 0.0 ? ctv : 0.0;
+    }
+  } else if (family == FAM_DM) {  // ss = [counts[dim], ratio]; x = dim counts
+    double X = 0.0, part = 0.0;
+    for (uint32_t i = 0; i < dim; i++) { X += x[i]; part += lgamma(x[i] + 1.0); }
+    if (op == 0) {
+      double s = lgamma(X + 1.0) - part, E = 0.0;
+      for (uint32_t i = 0; i < dim; i++) { const double e = hp[i] + ss[i]; E += e; s += lgamma_rise(e, (uint32_t)x[i]); }
+      *score = (float)(s + lgamma(E) - lgamma(E + X));
+    } else {
+      for (uint32_t i = 0; i < dim; i++) ss[i] += sgn * x[i];
+      ss[dim] += sgn * (lgamma(X + 1.0) - part);
     }
   } else if (family == FAM_NIW && op != 0) {
     ss[0] += sgn;

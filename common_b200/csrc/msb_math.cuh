@@ -12,7 +12,7 @@
 
 namespace msb {
 
-enum Family : int { FAM_BB = 0, FAM_BNB = 1, FAM_GP = 2, FAM_NICH = 3, FAM_DD = 4, FAM_NIW = 5, FAM_BBNC = 6 };
+enum Family : int { FAM_BB = 0, FAM_BNB = 1, FAM_GP = 2, FAM_NICH = 3, FAM_DD = 4, FAM_NIW = 5, FAM_BBNC = 6, FAM_DM = 7 };
 
 // ---------------------------------------------------------------------------
 // msb_expf: exp() built only from correctly rounded IEEE-754 binary32
@@ -138,6 +138,17 @@ __device__ __forceinline__ NichPost nich_post(const double *hp, const double *ss
 __device__ __forceinline__ double nich_score(const NichPost &p, double x) {
   const double t = (x - p.mu) * p.s;
   return p.c0 + p.c1 * log1p(t * t);
+}
+
+// dm (src/models/dm.cpp:38-76): lgamma(e + x) - lgamma(e) for a count x; the product form for small x has no
+// cancellation (e can be in the thousands)
+__device__ __forceinline__ double lgamma_rise(double e, uint32_t x) {
+  if (x <= 12u) {
+    double p = 1.0;
+    for (uint32_t j = 0; j < x; j++) p *= e + (double)j;
+    return log(p);
+  }
+  return lgamma(e + (double)x) - lgamma(e);
 }
 
 // fp32 log2(1 + z), z >= 0, for the nich inner loop (the natural-log factor ln 2 is folded into the

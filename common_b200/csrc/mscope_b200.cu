@@ -136,7 +136,7 @@ struct msb_state {
   std::vector<void *> cols;
   int32_t *d_assign = nullptr;
   size_t region_rows = 0, max_chunk_rows = 0;
-  bool has_bbnc = false;
+  bool has_bbnc = false, has_dm = false;  // has_dm: a vector count feature scored by its own kernel after the scalar ones (like niw)
   uint64_t group_seed = 0x6d73625f62626e63ull;  // Philox key of the per-group parameter draws (bbnc: p ~ Beta(alpha, beta))
   bool has_niw = false, has_scalar = false, tables_only = false, has_dd = false, has_nich = false;
   // workspaces
@@ -371,7 +371,7 @@ static size_t hp_size(const msb_model_desc &m) {
     case MSB_FAMILY_BB: case MSB_FAMILY_GP: case MSB_FAMILY_BBNC: return 2;
     case MSB_FAMILY_BNB: return 3;
     case MSB_FAMILY_NICH: return 4;
-    case MSB_FAMILY_DD: return m.dim;
+    case MSB_FAMILY_DD: case MSB_FAMILY_DM: return m.dim;
     case MSB_FAMILY_NIW: return (size_t)m.dim * m.dim + m.dim + 2;
     default: return 0;
   }
@@ -380,7 +380,7 @@ static size_t ss_size(const msb_model_desc &m) {
   switch (m.family) {
     case MSB_FAMILY_BB: case MSB_FAMILY_BNB: return 2;
     case MSB_FAMILY_GP: case MSB_FAMILY_NICH: case MSB_FAMILY_BBNC: return 3;
-    case MSB_FAMILY_DD: return (size_t)m.dim + 1;
+    case MSB_FAMILY_DD: case MSB_FAMILY_DM: return (size_t)m.dim + 1;
     case MSB_FAMILY_NIW: return (size_t)m.dim * m.dim + m.dim + 1;
     default: return 0;
   }
@@ -394,6 +394,10 @@ static int check_model(const msb_model_desc &m, size_t d) {
     case MSB_FAMILY_DD:
       if (m.dim == 0) return fail(MSB_ERR_INVALID, "no elements");  // distributions.hpp:429
       if (m.dim > 1024) return fail(MSB_ERR_UNSUPPORTED, "dd with more than 1024 categories is not built yet");
+      return MSB_OK;
+    case MSB_FAMILY_DM:
+      if (m.dim == 0) return fail(MSB_ERR_INVALID, "no elements");
+      if (m.dim > 1024) return fail(MSB_ERR_UNSUPPORTED, "dm with more than 1024 categories is not built yet");
       return MSB_OK;
     case MSB_FAMILY_NIW:
       if (m.dim == 0) return fail(MSB_ERR_INVALID, "no elements");  // distributions.hpp:478
@@ -431,7 +435,7 @@ static int hp_field(const msb_model_desc &m, const std::string &key, size_t *off
       if (key == "sigmasq") { *off = 2; *cnt = 1; return MSB_OK; }
       if (key == "nu") { *off = 3; *cnt = 1; return MSB_OK; }
       break;
-    case MSB_FAMILY_DD:
+    case MSB_FAMILY_DD: case MSB_FAMILY_DM:  // dm.hpp get_hp_mutator("alphas")
       if (key == "alphas") { *off = 0; *cnt = d; return MSB_OK; }
       break;
     case MSB_FAMILY_NIW:
@@ -469,6 +473,10 @@ static int ss_field(const msb_model_desc &m, const std::string &key, size_t *off
       if (key == "count") { *off = 0; *cnt = 1; return MSB_OK; }
       if (key == "mean") { *off = 1; *cnt = 1; return MSB_OK; }
       if (key == "count_times_variance") { *off = 2; *cnt = 1; return MSB_OK; }
+      break;
+    case MSB_FAMILY_DM:  // the fields of DirichletMultinomial.Group (schema.proto:25-28); dm.hpp itself allows no mutation
+      if (key == "counts") { *off = 0; *cnt = d; return MSB_OK; }
+      if (key == "ratio") { *off = d; *cnt = 1; return MSB_OK; }
       break;
     case MSB_FAMILY_DD:
       if (key == "count_sum") { *off = 0; *cnt = 1; return MSB_OK; }
@@ -518,6 +526,7 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
       case MSB_FAMILY_GP: f.kind = KIND_GP; f.coltype = COL_U32; f.ncat = 1; st->has_scalar = true; break;
       case MSB_FAMILY_NICH: f.kind = KIND_NICH; f.coltype = COL_F32; st->has_scalar = true; st->has_nich = true; break;
       case MSB_FAMILY_NIW: f.kind = KIND_NIW; f.coltype = COL_F32; st->has_niw = true; break;
+      case MSB_FAMILY_DM: f.kind = KIND_DM; f.coltype = COL_U32; st->has_dm = true; break;
     }
   }
   st->SS = sso;
@@ -530,6 +539,7 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
       case MSB_FAMILY_BB: case MSB_FAMILY_GP: case MSB_FAMILY_BBNC: h[0] = h[1] = 1.0; break;
       case MSB_FAMILY_BNB: h[0] = h[1] = h[2] = 1.0; break;  // models.pyx:200
       case MSB_FAMILY_NICH: h[0] = 0.0; h[1] = h[2] = h[3] = 1.0; break;
+      case MSB_FAMILY_DM:
       case MSB_FAMILY_DD: for (uint32_t i = 0; i < m.dim; i++) h[i] = 1.0; st->feats[d].asum = (double)m.dim; break;
       case MSB_FAMILY_NIW:
         h[m.dim] = 1.0;
@@ -791,7 +801,7 @@ extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
   for (size_t d = 0; d < st->D; d++) {
     const msb_runtime_type &t = dv->types[d];
     const msb_model_desc &m = st->models[d];
-    if (m.family == MSB_FAMILY_NIW) REQUIRE(t.n == m.dim, "shapes do not match");  // distributions.hpp:218
+    if (m.family == MSB_FAMILY_NIW || m.family == MSB_FAMILY_DM) REQUIRE(t.n == m.dim, "shapes do not match");  // distributions.hpp:218, dm.cpp:11
     else REQUIRE(t.n == 1, "scalar model bound to a vector field");               // distributions.hpp:209
   }
   const size_t n = std::max<size_t>(dv->n, 1);
@@ -806,10 +816,13 @@ extern "C" MSB_API int msb_state_bind(msb_state *st, msb_dataview *dv) {
     st->n_pad = n_pad;
     for (size_t d = 0; d < st->D; d++) {
       const FeatDev &f = st->feats[d];
-      const size_t bytes = f.kind == KIND_NIW ? n * f.dim * sizeof(float) : n * (f.coltype == COL_U8 ? 1 : f.coltype == COL_U16 ? 2 : 4);
+      const size_t bytes = (f.kind == KIND_NIW || f.kind == KIND_DM) ? n * f.dim * sizeof(float)
+                                                                    : n * (f.coltype == COL_U8 ? 1 : f.coltype == COL_U16 ? 2 : 4);
       coff[d] = slab;
       slab += (bytes + 4096 + 255) / 256 * 256;
-      if (f.kind != KIND_NIW) {
+      if (f.kind == KIND_DM) {  // no score column: dm_score_kernel reads the count rows themselves
+        soff[d] = moff[d] = slab;
+      } else if (f.kind != KIND_NIW) {
         soff[d] = slab; slab += n_pad * sizeof(uint32_t);
         moff[d] = slab; slab += n_pad / 32 * sizeof(uint32_t);
       } else {  // niw: the centred rows and the centre (FeatDev::scol / slowmask)
@@ -1356,6 +1369,18 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
              st->d_niwCoef[d], scores, st->ld, row_lo, row_hi);
     }
   }
+  for (size_t d = 0; d < st->D; d++) {  // dm: one more term per (row, group), accumulated like the CUDA-core niw kernel
+    const FeatDev &f = st->feats[d];
+    if (f.kind != KIND_DM) continue;
+    if (blocked) return fail(MSB_ERR_STATE, "internal: blocked score layout with a dm feature");
+    if (need_init) {
+      LAUNCH(ctx, fill_rows_kernel, cdiv(nrows * st->ld, 256), 256, 0, scores, st->ld, st->d_base, nrows);
+      need_init = false;
+    }
+    dim3 grid(cdiv(nrows, 128), (unsigned)K);
+    LAUNCH(ctx, dm_score_kernel<float>, grid, 128, (size_t)f.dim * sizeof(double), f, st->d_hp, st->d_ss, st->d_col2slot, scores, st->ld,
+           row_lo, row_hi);
+  }
   return MSB_OK;
 }
 
@@ -1379,6 +1404,11 @@ static int launch_update(msb_state *st, size_t row_lo, size_t row_hi) {  // old 
     const FeatDev &f = st->feats[d];
     if (f.kind != KIND_NIW) continue;
     LAUNCH(ctx, update_niw_kernel, cdiv(nrows, 8), 256, 0, f, st->d_assign, st->d_newslot, row_lo, row_hi, st->d_delta);
+  }
+  for (size_t d = 0; d < st->D; d++) {
+    const FeatDev &f = st->feats[d];
+    if (f.kind != KIND_DM) continue;
+    LAUNCH(ctx, update_dm_kernel, cdiv(nrows, 8), 256, 0, f, st->d_assign, st->d_newslot, row_lo, row_hi, st->d_delta);
   }
   LAUNCH(ctx, commit_assign_kernel, cdiv(nrows, 256), 256, st->kmax <= 8192 ? st->kmax * sizeof(int) : 0, st->d_assign,
          st->d_newslot, row_lo, row_hi, st->d_delta, (int)st->kmax, st->d_counter);
@@ -1592,7 +1622,7 @@ extern "C" MSB_API int msb_state_score_value(msb_state *st, size_t eid, size_t *
   if (!scores && !gids) return MSB_OK;
   REQUIRE(cap >= K, "buffer too small");
   size_t skip = 0;
-  if (!st->has_niw) {
+  if (!st->has_niw && !st->has_dm) {
     MSB_TRY(ensure_scores(st, 1));
     MSB_TRY(sync_small(st));
     LAUNCH(ctx, score_direct_kernel<float>, 1, 128, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot, (int)K,
@@ -1623,7 +1653,7 @@ extern "C" MSB_API int msb_state_score_rows(msb_state *st, size_t row_lo, size_t
   if (gids) { REQUIRE(cap >= K, "buffer too small"); for (size_t c = 0; c < K; c++) gids[c] = st->h_colgid[c]; }
   const size_t nrows = row_hi - row_lo;
   if (!nrows) return MSB_OK;
-  const bool direct = getenv("MSB_FORCE_DIRECT") && !st->has_niw;
+  const bool direct = getenv("MSB_FORCE_DIRECT") && !st->has_niw && !st->has_dm;
   const size_t skip = direct ? 0 : row_lo - row_origin(row_lo);
   // a device destination with the internal leading dimension is written in place
   float *dst = (on_device && scores && ld == st->ld && skip == 0) ? scores : nullptr;
@@ -1672,6 +1702,13 @@ extern "C" MSB_API int msb_state_score_rows_f64(msb_state *st, size_t row_lo, si
     if (f.kind != KIND_NIW) continue;
     const size_t smem = ((size_t)f.dim * f.dim + f.dim) * sizeof(double);
     LAUNCH(ctx, niw_score_f64_kernel, (unsigned)K, 128, smem, f, st->d_hp, st->d_ss, st->d_col2slot, d_out, K, row_lo, row_hi);
+  }
+  for (size_t d = 0; d < st->D; d++) {
+    const FeatDev &f = st->feats[d];
+    if (f.kind != KIND_DM) continue;
+    dim3 grid(cdiv(nrows, 128), (unsigned)K);
+    LAUNCH(ctx, dm_score_kernel<double>, grid, 128, (size_t)f.dim * sizeof(double), f, st->d_hp, st->d_ss, st->d_col2slot, d_out.p, K,
+           row_lo, row_hi);
   }
   CU_TRY(cudaMemcpy2DAsync(scores, sizeof(double) * ld, d_out, sizeof(double) * K, sizeof(double) * K, nrows,
                            cudaMemcpyDeviceToHost, ctx->stream));
@@ -1892,6 +1929,7 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
   // accumulates row-major only
   bool niw_tc_only = true;
   for (const auto &f : st->feats) if (f.kind == KIND_NIW && (f.dim != 64 || getenv("MSB_NO_TENSOR"))) niw_tc_only = false;
+  if (st->has_dm) niw_tc_only = false;  // dm_score_kernel accumulates row-major
   const bool blocked = niw_tc_only && !getenv("MSB_NO_BLOCKED");
   CU_TRY(cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned long long), ctx->stream));
   CU_TRY(cudaEventRecord(ev[0].e[0], ctx->stream));
@@ -1995,7 +2033,7 @@ static int value_op(msb_ctx *ctx, const msb_model_desc *model, int op, const dou
   REQUIRE(nhp == hp_size(*model) && nss == ss_size(*model), "wrong dimension");
   std::vector<double> x;
   MSB_TRY(value_to_doubles(value, vtype, x));
-  REQUIRE(x.size() == (model->family == MSB_FAMILY_NIW ? model->dim : 1u), "shapes do not match");
+  REQUIRE(x.size() == ((model->family == MSB_FAMILY_NIW || model->family == MSB_FAMILY_DM) ? model->dim : 1u), "shapes do not match");
   CU_TRY(cudaSetDevice(ctx->device));
   Scratch<double> d_buf;
   Scratch<float> d_score;

@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _lib
 
-_FAMILY = {"bbnc": _lib.FAMILY_BBNC, "bb": _lib.FAMILY_BB, "bnb": _lib.FAMILY_BNB, "gp": _lib.FAMILY_GP, "nich": _lib.FAMILY_NICH,
+_FAMILY = {"dm": _lib.FAMILY_DM, "bbnc": _lib.FAMILY_BBNC, "bb": _lib.FAMILY_BB, "bnb": _lib.FAMILY_BNB, "gp": _lib.FAMILY_GP, "nich": _lib.FAMILY_NICH,
            "dd": _lib.FAMILY_DD, "niw": _lib.FAMILY_NIW}
 
 
@@ -74,6 +74,12 @@ nich = model_descriptor("nich", np.float32, {"mu": 0., "kappa": 1., "sigmasq": 1
 def dd(size):
     _validate_positive(size, "size")
     return model_descriptor("dd", np.int32, {"alphas": [1.] * size}, param=int(size))
+
+
+def dm(categories):
+    """Dirichlet-multinomial over count vectors (models.pyx:279-292, src/models/dm.cpp): one value = categories counts"""
+    _validate_positive(categories, "categories")
+    return model_descriptor("dm", np.dtype((np.uint32, (categories,))), {"alphas": [1.] * categories}, param=int(categories))
 
 
 def niw(dim):

@@ -292,7 +292,7 @@ class state(object):
         _lib.check(_lib.load().msb_state_apply_deltas(self._h))
 
     # ---- checkpoint / resume: the reference's wire format (microscopes/io/schema.proto) -----------------
-    _SS_KEYS = {"bbnc": ("p", "heads", "tails"), "bb": ("heads", "tails"), "bnb": ("count", "sum"), "gp": ("count", "sum", "log_prod"),
+    _SS_KEYS = {"dm": ("counts", "ratio"), "bbnc": ("p", "heads", "tails"), "bb": ("heads", "tails"), "bnb": ("count", "sum"), "gp": ("count", "sum", "log_prod"),
                 "nich": ("count", "mean", "count_times_variance"), "dd": ("counts",), "niw": ("count", "sum_x", "sum_xxT")}
 
     def _ss_counts(self, m, key):

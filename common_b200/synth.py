@@ -62,6 +62,12 @@ def make_dataset(models, n, k_true, seed=73, stream=0, mask_frac=0.0, storage=No
             sg = prng.uniform(0.5, 2.0, size=k_true)
             x = mu[z] + sg[z] * rng.standard_normal(n)
             dt = np.float32
+        elif name == "dm":
+            C = m._param()
+            theta = prng.dirichlet(np.full(C, 0.5), size=k_true)
+            tot = rng.poisson(20.0, size=n)
+            x = np.stack([rng.multinomial(int(tot[i]), theta[z[i]]) for i in range(n)]).astype(np.uint32)
+            dt = np.dtype((np.uint32, (C,)))
         elif name == "niw":
             dim = m._param()
             mu = prng.normal(0.0, 2.0, size=(k_true, dim))

@@ -24,6 +24,8 @@ SCHEMA = {
     "MixtureModelState": {1: ("hypers", "bytes", True), 2: ("groups", "bytes", False)},
     "bbnc.Shared": {1: ("alpha", "float", False), 2: ("beta", "float", False)},                 # schema.proto:8-12
     "bbnc.Group": {1: ("p", "float", False), 2: ("heads", "uint", False), 3: ("tails", "uint", False)},  # schema.proto:14-18
+    "dm.Shared": {1: ("alphas", "float", True)},                                                # schema.proto:21-23
+    "dm.Group": {1: ("counts", "uint", True), 2: ("ratio", "float", False)},                    # schema.proto:25-28
     # ---- distributions/io/schema.proto [R: unpinned] ----
     "bb.Shared": {1: ("alpha", "float", False), 2: ("beta", "float", False)},
     "bb.Group": {1: ("heads", "uint", False), 2: ("tails", "uint", False)},

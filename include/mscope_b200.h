@@ -96,9 +96,11 @@ enum msb_family {
   MSB_FAMILY_DD = 4,   /* DirichletDiscrete(dim)    hp: alphas[dim]           ss: count_sum counts[dim] */
   MSB_FAMILY_NIW = 5,  /* NormalInverseWishart(dim) hp: mu[dim] kappa psi[dim*dim] nu
                                                     ss: count sum_x[dim] sum_xxT[dim*dim] */
-  MSB_FAMILY_BBNC = 6  /* BetaBernoulliNonConj (in-tree model, src/models/bbnc.cpp)
+  MSB_FAMILY_BBNC = 6, /* BetaBernoulliNonConj (in-tree model, src/models/bbnc.cpp)
                                                     hp: alpha beta            ss: p heads tails
                           p is the group's own parameter, drawn from Beta(alpha, beta) when the group is created */
+  MSB_FAMILY_DM = 7    /* DirichletMultinomial(dim) (in-tree model, src/models/dm.cpp): the value is a vector of dim counts
+                                                    hp: alphas[dim]           ss: counts[dim] ratio */
 };
 
 typedef struct msb_model_desc {

@@ -52,7 +52,7 @@ size_t orc_hp_size(const orc_model *m) {
     case ORC_BBNC: return 2;                               /* alpha beta (src/models/bbnc.cpp) */
     case ORC_GP: return 2;                                 /* alpha inv_beta */
     case ORC_NICH: return 4;                               /* mu kappa sigmasq nu */
-    case ORC_DD: return m->dim;                            /* alphas[dim] */
+    case ORC_DD: case ORC_DM: return m->dim;               /* alphas[dim] */
     case ORC_NIW: return (size_t)m->dim * m->dim + m->dim + 2; /* mu[d] kappa psi[d*d] nu */
     default: return 0;
   }
@@ -65,6 +65,7 @@ size_t orc_ss_size(const orc_model *m) {
     case ORC_GP: return 3;                                 /* count sum log_prod */
     case ORC_NICH: return 3;                               /* count mean count_times_variance */
     case ORC_DD: return (size_t)m->dim + 1;                /* count_sum counts[dim] */
+    case ORC_DM: return (size_t)m->dim + 1;                /* counts[dim] ratio (src/models/dm.cpp) */
     case ORC_NIW: return (size_t)m->dim * m->dim + m->dim + 1; /* count sum_x[d] sum_xxT[d*d] */
     default: return 0;
   }
@@ -215,6 +216,11 @@ double orc_score_data(const orc_model *m, const double *hp, const double *ss) {
       for (unsigned i = 0; i < m->dim; i++) { asum += hp[i]; s += lgamma(hp[i] + ss[1 + i]) - lgamma(hp[i]); }
       return s + lgamma(asum) - lgamma(asum + ss[0]);
     }
+    case ORC_DM: { /* dm.cpp:79-95 */
+      double score = ss[m->dim], asum = 0.0, csum = 0.0;
+      for (unsigned i = 0; i < m->dim; i++) { asum += hp[i]; csum += ss[i]; score += lgamma(ss[i] + hp[i]) - lgamma(hp[i]); }
+      return score + lgamma(asum) - lgamma(asum + csum);
+    }
     case ORC_BBNC: { /* bbnc.cpp:61-73: Beta(alpha, beta) density of p + Bernoulli likelihood of (heads, tails) */
       double p = ss[0];
       if (p < 0.0 || p > 1.0) return -INFINITY;
@@ -292,6 +298,42 @@ double orc_score_assignment64(const int64_t *assign, size_t n, double alpha) {
   return s;
 }
 
+/* dm: src/models/dm.cpp:38-76, statement by statement; prec 64 in double, prec 32 in float with lgammaf where
+ * upstream has fast_lgamma.  ss = counts[dim], ratio. */
+static double dm_score64(unsigned dim, const double *hp, const double *ss, const double *x) {
+  double score = 0.0, x_sum = 0.0, a_sum = 0.0, n_sum = 0.0;
+  for (unsigned i = 0; i < dim; i++) {
+    double xi = x[i], ai = hp[i], ni = ss[i];
+    x_sum += xi; a_sum += ai; n_sum += ni;
+    double e = ai + ni;
+    score += lgamma(e + xi) - lgamma(e);
+    score -= lgamma(xi + 1.0);
+  }
+  score += lgamma(x_sum + 1.0);
+  score += lgamma(a_sum + n_sum) - lgamma(a_sum + n_sum + x_sum);
+  return score;
+}
+static float dm_score32(unsigned dim, const double *hp, const double *ss, const double *x) {
+  float score = 0.f, a_sum = 0.f;
+  unsigned x_sum = 0, n_sum = 0;
+  for (unsigned i = 0; i < dim; i++) {
+    unsigned xi = (unsigned)x[i], ni = (unsigned)ss[i];
+    float ai = (float)hp[i];
+    x_sum += xi; a_sum += ai; n_sum += ni;
+    float e = ai + ni;
+    score += lgammaf(e + xi) - lgammaf(e);
+    score -= lgammaf(xi + 1);
+  }
+  score += lgammaf(x_sum + 1);
+  score += lgammaf(a_sum + n_sum) - lgammaf(a_sum + n_sum + x_sum);
+  return score;
+}
+static double dm_ratio_term(unsigned dim, const double *x, int prec) { /* dm.cpp:9-21: lgamma(sum + 1) - sum lgamma(x_i + 1) */
+  double s = 0.0, tot = 0.0;
+  for (unsigned i = 0; i < dim; i++) { tot += x[i]; s -= prec == 32 ? (double)lgammaf((float)x[i] + 1.f) : lgamma(x[i] + 1.0); }
+  return s + (prec == 32 ? (double)lgammaf((float)tot + 1.f) : lgamma(tot + 1.0));
+}
+
 /* ---- fp32 restatements: float arithmetic, libm logf/lgammaf.  Upstream uses
  * table-driven fast_log / fast_lgamma whose error is not reproducible here. -- */
 static float bb_score32(const double *hp, const double *ss, double x) {
@@ -348,6 +390,7 @@ double orc_score_value(const orc_model *m, const double *hp, const double *ss, c
       double s = niw_score64(m->dim, hp, ss, x);
       return prec == 32 ? (double)(float)s : s;
     }
+    case ORC_DM: return prec == 32 ? (double)dm_score32(m->dim, hp, ss, x) : dm_score64(m->dim, hp, ss, x);
     default: return NAN;
   }
 }
@@ -365,6 +408,10 @@ void orc_add_value(const orc_model *m, const double *hp, double *ss, const doubl
     case ORC_DD: ss[0] += 1.0; ss[1 + (long)x[0]] += 1.0; break;
     case ORC_BNB: ss[0] += 1.0; ss[1] += x[0]; break;
     case ORC_BBNC: ss[x[0] != 0.0 ? 1 : 2] += 1.0; break;   /* bbnc.cpp:21-30 */
+    case ORC_DM: /* dm.cpp:9-21 */
+      for (unsigned i = 0; i < m->dim; i++) ss[i] += x[i];
+      ss[m->dim] = rnd(ss[m->dim] + dm_ratio_term(m->dim, x, prec), prec);
+      break;
     case ORC_GP:
       ss[0] += 1.0; ss[1] += x[0];
       ss[2] = rnd(ss[2] + rnd(prec == 32 ? (double)lgammaf((float)x[0] + 1.f) : lgamma(x[0] + 1.0), prec), prec);
@@ -396,6 +443,10 @@ void orc_remove_value(const orc_model *m, const double *hp, double *ss, const do
     case ORC_DD: ss[0] -= 1.0; ss[1 + (long)x[0]] -= 1.0; break;
     case ORC_BNB: ss[0] -= 1.0; ss[1] -= x[0]; break;
     case ORC_BBNC: ss[x[0] != 0.0 ? 1 : 2] -= 1.0; break;   /* bbnc.cpp:32-44 */
+    case ORC_DM: /* dm.cpp:23-36 */
+      for (unsigned i = 0; i < m->dim; i++) ss[i] -= x[i];
+      ss[m->dim] = rnd(ss[m->dim] - dm_ratio_term(m->dim, x, prec), prec);
+      break;
     case ORC_GP:
       ss[0] -= 1.0; ss[1] -= x[0];
       ss[2] = rnd(ss[2] - rnd(prec == 32 ? (double)lgammaf((float)x[0] + 1.f) : lgamma(x[0] + 1.0), prec), prec);

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-enum { ORC_BB = 0, ORC_BNB = 1, ORC_GP = 2, ORC_NICH = 3, ORC_DD = 4, ORC_NIW = 5, ORC_BBNC = 6 };
+enum { ORC_BB = 0, ORC_BNB = 1, ORC_GP = 2, ORC_NICH = 3, ORC_DD = 4, ORC_NIW = 5, ORC_BBNC = 6, ORC_DM = 7 };
 typedef struct orc_model { int32_t family; uint32_t dim; } orc_model;
 typedef struct orc_type { int32_t prim; uint32_t n; int32_t vec; } orc_type;
 

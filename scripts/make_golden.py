@@ -134,6 +134,22 @@ def main():
             cases.append(dict(family="bnb", dim=0, hp=[alpha, beta, r], ss=[count, total], x=[x],
                               expect=alt, source="scipy betanbinom.logpmf == gammaln/betaln closed form"))
 
+    # ---- dm: Dirichlet-multinomial predictive of a count vector (src/models/dm.cpp:38-76), own generator so that
+    # the cases above keep their random draws
+    rng_dm = np.random.default_rng(38_76)
+    for C, scale, total in [(3, 1.0, 0), (3, 1.0, 5), (8, 0.5, 40), (16, 2.0, 300), (64, 1.0, 5000), (5, 0.1, 12)]:
+        alphas = rng_dm.uniform(0.2, 2.0, size=C) * scale
+        counts = rng_dm.multinomial(total, rng_dm.dirichlet(np.ones(C))) if total else np.zeros(C, int)
+        for xt in (0, 1, 7, 60):
+            x = rng_dm.multinomial(xt, rng_dm.dirichlet(np.ones(C)))
+            e = alphas + counts
+            exp = float(st.dirichlet_multinomial.logpmf(x, e, xt))
+            alt = float(sp.gammaln(xt + 1) - sp.gammaln(x + 1).sum() + sp.gammaln(e.sum()) - sp.gammaln(e.sum() + xt)
+                        + (sp.gammaln(e + x) - sp.gammaln(e)).sum())
+            assert abs(exp - alt) < 1e-9 * max(1.0, abs(exp))
+            cases.append(dict(family="dm", dim=C, hp=alphas.tolist(), ss=counts.astype(float).tolist() + [0.0], x=x.tolist(),
+                              expect=alt, source="scipy dirichlet_multinomial.logpmf == dm.cpp:38-76 closed form"))
+
     out = os.path.join(ROOT, "tests", "golden", "score_value.json")
     with open(out, "w") as f:
         json.dump(dict(generator="scripts/make_golden.py", cases=cases), f)

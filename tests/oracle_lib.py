@@ -9,8 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB = os.path.join(ORACLE_DIR, "libmsb_oracle.so")
 
-BB, BNB, GP, NICH, DD, NIW, BBNC = range(7)
-FAMILY = {"bbnc": BBNC, "bb": BB, "bnb": BNB, "gp": GP, "nich": NICH, "dd": DD, "niw": NIW}
+BB, BNB, GP, NICH, DD, NIW, BBNC, DM = range(8)
+FAMILY = {"dm": DM, "bbnc": BBNC, "bb": BB, "bnb": BNB, "gp": GP, "nich": NICH, "dd": DD, "niw": NIW}
 
 
 class OrcModel(C.Structure):
@@ -71,7 +71,7 @@ class Oracle(object):
         if n == "bnb": return np.array([hp["alpha"], hp["beta"], hp["r"]], np.float64)
         if n == "gp": return np.array([hp["alpha"], hp["inv_beta"]], np.float64)
         if n == "nich": return np.array([hp["mu"], hp["kappa"], hp["sigmasq"], hp["nu"]], np.float64)
-        if n == "dd": return np.asarray(hp["alphas"], np.float64)
+        if n in ("dd", "dm"): return np.asarray(hp["alphas"], np.float64)
         if n == "niw":
             return np.concatenate([np.asarray(hp["mu"], np.float64).ravel(), [hp["kappa"]],
                                    np.asarray(hp["psi"], np.float64).ravel(), [hp["nu"]]])

@@ -53,6 +53,8 @@ FAMILIES = {
     "gp": [cb.gp] * 3,
     "bnb": [cb.bnb] * 3,
     "bbnc": [cb.bbnc] * 4,
+    "dm": [cb.dm(5), cb.dm(40), cb.dm(1)],
+    "dm+scalars": [cb.dm(12), cb.bb, cb.nich, cb.dd(16), cb.gp],
     "nich": [cb.nich] * 4,
     "mixed": [cb.bb, cb.gp, cb.nich, cb.dd(16), cb.bb, cb.nich, cb.bnb, cb.bbnc],
 }
@@ -105,8 +107,9 @@ def test_any_primitive_type_may_back_a_field(ctx, oracle, storage):
     st.close()
 
 
-def test_suffstats_after_bulk_add_are_exact(ctx, oracle):
-    descs = FAMILIES["mixed"]
+@pytest.mark.parametrize("name", ["mixed", "dm+scalars"])
+def test_suffstats_after_bulk_add_are_exact(ctx, oracle, name):
+    descs = FAMILIES[name]
     st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 900, 5, seed=2, mask_frac=0.05)
     off = 0
     for d, desc in enumerate(descs):
@@ -122,6 +125,9 @@ def test_suffstats_after_bulk_add_are_exact(ctx, oracle):
                 assert np.array_equal(st.get_suffstats(d, g, "counts", w - 1), ref[1:])
             elif name == "bnb":
                 assert st.get_suffstats(d, g, "count")[0] == ref[0] and st.get_suffstats(d, g, "sum")[0] == ref[1]
+            elif name == "dm":
+                assert np.array_equal(st.get_suffstats(d, g, "counts", w - 1), ref[:-1])
+                assert abs(st.get_suffstats(d, g, "ratio")[0] - ref[-1]) <= 1e-9 * max(1, abs(ref[-1]))
             elif name == "gp":
                 assert st.get_suffstats(d, g, "count")[0] == ref[0] and st.get_suffstats(d, g, "sum")[0] == ref[1]
                 assert abs(st.get_suffstats(d, g, "log_prod")[0] - ref[2]) <= 1e-9 * max(1, abs(ref[2]))
@@ -257,7 +263,7 @@ def test_golden_vectors_through_the_value_abi(ctx):
     import ctypes as C
     from common_b200 import _lib
     lib = _lib.load()
-    fam = {"bb": _lib.FAMILY_BB, "bbnc": _lib.FAMILY_BBNC, "bnb": _lib.FAMILY_BNB, "dd": _lib.FAMILY_DD, "gp": _lib.FAMILY_GP, "nich": _lib.FAMILY_NICH, "niw": _lib.FAMILY_NIW}
+    fam = {"dm": _lib.FAMILY_DM, "bb": _lib.FAMILY_BB, "bbnc": _lib.FAMILY_BBNC, "bnb": _lib.FAMILY_BNB, "dd": _lib.FAMILY_DD, "gp": _lib.FAMILY_GP, "nich": _lib.FAMILY_NICH, "niw": _lib.FAMILY_NIW}
     with open(os.path.join(GOLD, "score_value.json")) as f:
         cases = json.load(f)["cases"]
     for c in cases:
@@ -281,7 +287,8 @@ def test_value_add_remove_roundtrip(ctx, oracle):
     rng = np.random.default_rng(1)
     for desc, draw in [(cb.bb, lambda: [float(rng.integers(0, 2))]), (cb.dd(6), lambda: [float(rng.integers(0, 6))]),
                        (cb.gp, lambda: [float(rng.poisson(5))]), (cb.nich, lambda: [float(rng.normal())]),
-                       (cb.niw(3), lambda: rng.normal(size=3).tolist())]:
+                       (cb.niw(3), lambda: rng.normal(size=3).tolist()),
+                       (cb.dm(4), lambda: rng.multinomial(9, [0.1, 0.2, 0.3, 0.4]).astype(float).tolist())]:
         md = desc().c_desc()
         m = oracle.model(desc)
         hp = oracle.flat_hp(desc)
@@ -585,7 +592,7 @@ def test_sweep_with_niw_features_draws_bit_exactly(ctx, oracle, descs):
     st.close()
 
 
-@pytest.mark.parametrize("name,cond", [("bb", 1.0), ("bbnc", 1.0), ("dd", 1.0), ("gp", 4.0), ("bnb", 4.0), ("nich", 4.0), ("mixed", 4.0), ("niw", 50.0)])
+@pytest.mark.parametrize("name,cond", [("bb", 1.0), ("bbnc", 1.0), ("dd", 1.0), ("dm", 8.0), ("gp", 4.0), ("bnb", 4.0), ("nich", 4.0), ("mixed", 4.0), ("niw", 50.0)])
 def test_fp64_scores_within_1e12_of_the_oracle(ctx, oracle, name, cond):
     # north_star tolerance for fp64: 1e-12 relative.  `cond` is the conditioning of the closed form itself in
     # double (lgamma(a + x) - lgamma(a) and lgamma((nu+1)/2) - lgamma(nu/2) cancel; a d x d Cholesky for niw):
@@ -699,7 +706,7 @@ def test_device_expf_is_bit_identical_to_the_checkers_copy(ctx, oracle):
 def test_checkpoint_round_trip_through_the_wire_format(ctx, oracle):
     # serialize -> MixtureModelState bytes (schema.proto:3-55 framing) -> a new state: identifiers, assignments,
     # hypers and suffstats as saved; the restored state scores and sweeps like the original
-    descs = [cb.bb, cb.bnb, cb.gp, cb.nich, cb.dd(9), cb.niw(3)]
+    descs = [cb.bb, cb.bnb, cb.gp, cb.nich, cb.dd(9), cb.niw(3), cb.dm(6)]
     n, k = 900, 7
     hp = {3: {"mu": 0.5, "kappa": 2.0, "sigmasq": 1.5, "nu": 3.0}, 4: {"alphas": np.linspace(0.5, 2.5, 9)}}
     st, view, z, gids, _, _, _ = make_state(ctx, oracle, descs, n, k, seed=111, hp=hp, extra_empty=2)

@@ -10,7 +10,7 @@ import common_b200 as cb
 import oracle_lib as ol
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-FAM = {"bb": ol.BB, "bbnc": ol.BBNC, "bnb": ol.BNB, "dd": ol.DD, "gp": ol.GP, "nich": ol.NICH, "niw": ol.NIW}
+FAM = {"dm": ol.DM, "bb": ol.BB, "bbnc": ol.BBNC, "bnb": ol.BNB, "dd": ol.DD, "gp": ol.GP, "nich": ol.NICH, "niw": ol.NIW}
 
 
 def _cases():
@@ -25,14 +25,15 @@ def test_golden_score_value_fp64(oracle):
         got = oracle.score_value(m, c["hp"], c["ss"], c["x"], 64)
         # fp64 conditioning: lgamma(a+x) - lgamma(a) at a ~ 7.5e3 cancels ~1e4 (gp); d=64 Cholesky (niw)
         cond = {"niw": 50.0, "gp": max(1.0, 1e-3 * (c["hp"][0] + c["ss"][1])),
-                "bnb": max(1.0, 1e-3 * (sum(c["hp"][:2]) + c["hp"][-1] * c["ss"][0] + c["ss"][1])) if c["family"] == "bnb" else 1.0
+                "bnb": max(1.0, 1e-3 * (sum(c["hp"][:2]) + c["hp"][-1] * c["ss"][0] + c["ss"][1])) if c["family"] == "bnb" else 1.0,
+                "dm": max(4.0, 1e-2 * sum(c["ss"])) if c["family"] == "dm" else 1.0,  # lgamma(E + X) - lgamma(E), E = sum(alpha + counts)
                 }.get(c["family"], 1.0)
         tol = 1e-12 * max(1.0, abs(c["expect"])) * cond
         assert abs(got - c["expect"]) <= tol, (c["family"], c["source"], got, c["expect"])
         if "ref_vendor" in c:  # the reference's own in-tree closed form
             assert abs(got - c["ref_vendor"]) <= 5e-11 * max(1.0, abs(c["ref_vendor"]))
         n += 1
-    assert n >= 70
+    assert n >= 94
 
 
 def test_golden_score_value_fp32_restatement(oracle):
@@ -51,6 +52,9 @@ def test_golden_score_value_fp32_restatement(oracle):
         if c["family"] == "bnb":
             a = c["hp"][0] + c["hp"][1] + c["hp"][2] * (c["ss"][0] + 1) + c["ss"][1] + c["x"][0]
             n = 3 * a * np.log(a + 2.0)
+        if c["family"] == "dm":  # dim + 1 differences lgammaf(e + x) - lgammaf(e), each cancelling terms of size e log e
+            e = np.asarray(c["hp"]) + np.asarray(c["ss"][:-1])
+            n = 3 * (np.sum((e + c["x"]) * np.log(e + np.asarray(c["x"]) + 2.0)) + (e.sum() + sum(c["x"])) * np.log(e.sum() + sum(c["x"]) + 2.0))
         tol = 2e-5 * max(1.0, abs(c["expect"])) + 6e-7 * n
         assert abs(got - c["expect"]) <= tol, (c["family"], got, c["expect"])
 
@@ -277,3 +281,30 @@ def test_bbnc_follows_the_in_tree_source(oracle):
     oracle.remove_value(m, hp, ss, 1.0)
     assert ss.tolist() == [0.3, 2.0, 1.0]
     assert oracle.score_data(m, hp, np.array([1.5, 0.0, 0.0])) == -np.inf      # p outside [0, 1]
+
+
+def test_dm_follows_the_in_tree_source(oracle):
+    # src/models/dm.cpp: add / remove :9-36 (counts += x, ratio += lgamma(sum x + 1) - sum lgamma(x_i + 1)),
+    # score_value :38-76, score_data :79-95 = ratio + the Dirichlet-multinomial evidence of the pooled counts
+    from scipy.special import gammaln
+    rng = np.random.default_rng(12)
+    C = 6
+    m = ol.OrcModel(ol.DM, C)
+    hp = rng.uniform(0.3, 2.0, C)
+    ss = np.zeros(C + 1)
+    xs = [rng.multinomial(int(rng.integers(0, 30)), rng.dirichlet(np.ones(C))).astype(float) for _ in range(25)]
+    chain = 0.0
+    for x in xs:   # chain rule: the marginal likelihood is the product of the predictives
+        chain += oracle.score_value(m, hp, ss, x)
+        oracle.add_value(m, hp, ss, x)
+    X = np.asarray(xs)
+    assert np.array_equal(ss[:C], X.sum(0))
+    ratio = sum(gammaln(x.sum() + 1) - gammaln(x + 1).sum() for x in xs)
+    assert ss[C] == pytest.approx(ratio, rel=1e-12)
+    assert oracle.score_data(m, hp, ss) == pytest.approx(chain, rel=1e-11)
+    # an all-zero row scores log 1 = 0 and the predictive over the C one-count rows sums to 1
+    assert oracle.score_value(m, hp, ss, np.zeros(C)) == pytest.approx(0.0, abs=1e-12)
+    assert sum(np.exp(oracle.score_value(m, hp, ss, np.eye(C)[i])) for i in range(C)) == pytest.approx(1.0, rel=1e-12)
+    for x in reversed(xs):
+        oracle.remove_value(m, hp, ss, x)
+    assert np.all(ss[:C] == 0) and abs(ss[C]) < 1e-9
