@@ -121,6 +121,11 @@ _PROTOS = {
                                 _P, C.POINTER(RuntimeType)]),
     "msb_value_remove": (C.c_int, [_P, C.POINTER(ModelDesc), C.POINTER(C.c_double), _SZ, C.POINTER(C.c_double), _SZ,
                                    _P, C.POINTER(RuntimeType)]),
+    "msb_value_score_data": (C.c_int, [_P, C.POINTER(ModelDesc), C.POINTER(C.c_double), _SZ, C.POINTER(C.c_double), _SZ,
+                                       C.POINTER(C.c_float)]),
+    "msb_value_sample": (C.c_int, [_P, C.POINTER(ModelDesc), C.POINTER(C.c_double), _SZ, C.POINTER(C.c_double), _SZ,
+                                   C.c_uint64, C.c_uint64, _SZ, C.POINTER(C.c_double)]),
+    "msb_state_sample_value": (C.c_int, [_P, _SZ, _SZ, C.c_uint64, C.c_uint64, _SZ, C.POINTER(C.c_double)]),
     "msb_model_hp_size": (_SZ, [C.POINTER(ModelDesc)]),
     "msb_model_ss_size": (_SZ, [C.POINTER(ModelDesc)]),
 }

@@ -16,6 +16,7 @@
 #include "msb_kernels.cuh"
 #include "msb_score.cuh"
 #include "msb_niw_tc.cuh"
+#include "msb_draw.cuh"
 
 using namespace msb;
 
@@ -2086,4 +2087,92 @@ extern "C" MSB_API int msb_value_add(msb_ctx *ctx, const msb_model_desc *model, 
 extern "C" MSB_API int msb_value_remove(msb_ctx *ctx, const msb_model_desc *model, const double *hp, size_t nhp, double *ss,
                                 size_t nss, const void *value, const msb_runtime_type *vtype) {
   return value_op(ctx, model, 2, hp, nhp, ss, nss, value, vtype, nullptr);
+}
+
+// ---- group::score_data of one group (models/base.hpp:28, distributions.hpp:287-291): the kernels of
+// msb_state_score_likelihood on a one-feature, one-group layout
+extern "C" MSB_API int msb_value_score_data(msb_ctx *ctx, const msb_model_desc *model, const double *hp, size_t nhp, const double *ss,
+                                            size_t nss, float *score) {
+  REQUIRE(ctx && model && hp && ss && score, "NULL argument");
+  MSB_TRY(check_model(*model, 0));
+  REQUIRE(nhp == hp_size(*model) && nss == ss_size(*model), "wrong dimension");
+  CU_TRY(cudaSetDevice(ctx->device));
+  std::vector<double> s(ss, ss + nss);
+  ss_from_ref(*model, s);
+  FeatDev f; memset(&f, 0, sizeof(f));
+  f.family = model->family; f.dim = model->dim; f.ss_w = (uint32_t)nss;
+  switch (model->family) {
+    case MSB_FAMILY_GP: case MSB_FAMILY_BNB: f.kind = KIND_GP; break;
+    case MSB_FAMILY_NICH: f.kind = KIND_NICH; break;
+    case MSB_FAMILY_NIW: f.kind = KIND_NIW; break;
+    case MSB_FAMILY_DM: f.kind = KIND_DM; break;
+    default: f.kind = KIND_TABLE; break;
+  }
+  if (model->family == MSB_FAMILY_DD) for (size_t i = 0; i < nhp; i++) f.asum += hp[i];
+  Scratch<double> d_buf;
+  Scratch<FeatDev> d_f;
+  Scratch<int32_t> d_c2s;
+  CU_TRY(d_buf.alloc(nhp + nss + 1));
+  CU_TRY(d_f.alloc(1));
+  CU_TRY(d_c2s.alloc(1));
+  double *d_hp = d_buf.p, *d_ss = d_buf.p + nhp, *d_out = d_ss + nss;
+  CU_TRY(cudaMemcpyAsync(d_hp, hp, sizeof(double) * nhp, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(d_ss, s.data(), sizeof(double) * nss, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(d_f.p, &f, sizeof(FeatDev), cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemsetAsync(d_c2s.p, 0, sizeof(int32_t), ctx->stream));
+  if (model->family == MSB_FAMILY_NIW) {
+    const size_t smem = ((size_t)f.dim * f.dim + f.dim) * sizeof(double);
+    LAUNCH(ctx, niw_score_data_kernel, 1, 128, smem, f, 0, 1, (const double *)d_hp, (const double *)d_ss, (const int32_t *)d_c2s.p, d_out);
+  } else {
+    LAUNCH(ctx, score_data_kernel, 1, 32, 0, (const FeatDev *)d_f.p, 1, (const double *)d_hp, (const double *)d_ss, (const int32_t *)d_c2s.p, 1, d_out);
+  }
+  double r;
+  CU_TRY(cudaMemcpyAsync(&r, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  *score = (float)r;
+  return MSB_OK;
+}
+
+// ---- group::sample_value (models/base.hpp:29, distributions.hpp:293-298) -----------------------------------------
+static int launch_draws(msb_ctx *ctx, const msb_model_desc &m, int abi_repr, const double *d_hp, const double *d_ss, uint64_t seed,
+                        uint64_t counter, size_t n, double *out) {
+  if (m.family == MSB_FAMILY_DM) return fail(MSB_ERR_UNSUPPORTED, "multinomial sampling unimplemented");  // dm.cpp:100-111
+  const size_t width = m.family == MSB_FAMILY_NIW ? m.dim : 1;
+  Scratch<double> d_out;
+  CU_TRY(d_out.alloc(n * width));
+  const size_t smem = m.family == MSB_FAMILY_NIW ? ((size_t)m.dim * m.dim + m.dim) * sizeof(double) : 0;
+  if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(sample_value_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)std::min<size_t>(cdiv(n, 128), 148 * 4);
+  LAUNCH(ctx, sample_value_kernel, grid, 128, smem, (int)m.family, m.dim, abi_repr, d_hp, d_ss, seed, counter, n, d_out.p);
+  CU_TRY(cudaMemcpyAsync(out, d_out, sizeof(double) * n * width, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_value_sample(msb_ctx *ctx, const msb_model_desc *model, const double *hp, size_t nhp, const double *ss,
+                                        size_t nss, uint64_t seed, uint64_t counter, size_t n, double *out) {
+  REQUIRE(ctx && model && hp && ss && out, "NULL argument");
+  MSB_TRY(check_model(*model, 0));
+  REQUIRE(nhp == hp_size(*model) && nss == ss_size(*model), "wrong dimension");
+  if (!n) return MSB_OK;
+  CU_TRY(cudaSetDevice(ctx->device));
+  Scratch<double> d_buf;
+  CU_TRY(d_buf.alloc(nhp + nss));
+  CU_TRY(cudaMemcpyAsync(d_buf.p, hp, sizeof(double) * nhp, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(d_buf.p + nhp, ss, sizeof(double) * nss, cudaMemcpyHostToDevice, ctx->stream));
+  return launch_draws(ctx, *model, 1, d_buf.p, d_buf.p + nhp, seed, counter, n, out);
+}
+
+extern "C" MSB_API int msb_state_sample_value(msb_state *st, size_t feature, size_t gid, uint64_t seed, uint64_t counter, size_t n,
+                                              double *out) {
+  REQUIRE(st && out, "NULL argument");
+  REQUIRE(feature < st->D, "bad feature index");
+  int slot;
+  MSB_TRY(slot_of(st, gid, &slot));
+  if (!n) return MSB_OK;
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  MSB_TRY(sync_small(st));
+  const FeatDev &f = st->feats[feature];
+  return launch_draws(ctx, st->models[feature], 0, st->d_hp + f.hp_off, st->d_ss + f.ss_off + (size_t)slot * f.ss_w, seed, counter, n, out);
 }

@@ -79,7 +79,8 @@ def dd(size):
 def dm(categories):
     """Dirichlet-multinomial over count vectors (models.pyx:279-292, src/models/dm.cpp): one value = categories counts"""
     _validate_positive(categories, "categories")
-    return model_descriptor("dm", np.dtype((np.uint32, (categories,))), {"alphas": [1.] * categories}, param=int(categories))
+    # value type: dm.hpp:186-190
+    return model_descriptor("dm", np.dtype((np.int32, (categories,))), {"alphas": [1.] * categories}, param=int(categories))
 
 
 def niw(dim):

@@ -291,6 +291,16 @@ class state(object):
     def apply_deltas(self):
         _lib.check(_lib.load().msb_state_apply_deltas(self._h))
 
+    def sample_value(self, component, gid, seed, counter=0, n=1):
+        """group::sample_value (models/base.hpp:29) for one (feature, group): ``n`` draws from the posterior predictive,
+        draw i from the Philox stream (seed, counter + i).  Returns an array of n values (n x dim for niw)."""
+        m = self._models[component]
+        width = m._param() if m.name() == "niw" else 1
+        out = np.zeros((n, width), np.float64)
+        _lib.check(_lib.load().msb_state_sample_value(self._h, component, gid, seed, counter, n,
+                                                      out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out if width > 1 else out[:, 0]
+
     # ---- checkpoint / resume: the reference's wire format (microscopes/io/schema.proto) -----------------
     _SS_KEYS = {"dm": ("counts", "ratio"), "bbnc": ("p", "heads", "tails"), "bb": ("heads", "tails"), "bnb": ("count", "sum"), "gp": ("count", "sum", "log_prod"),
                 "nich": ("count", "mean", "count_times_variance"), "dd": ("counts",), "niw": ("count", "sum_x", "sum_xxT")}

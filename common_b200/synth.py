@@ -67,7 +67,7 @@ def make_dataset(models, n, k_true, seed=73, stream=0, mask_frac=0.0, storage=No
             theta = prng.dirichlet(np.full(C, 0.5), size=k_true)
             tot = rng.poisson(20.0, size=n)
             x = np.stack([rng.multinomial(int(tot[i]), theta[z[i]]) for i in range(n)]).astype(np.uint32)
-            dt = np.dtype((np.uint32, (C,)))
+            dt = np.dtype((np.int32, (C,)))
         elif name == "niw":
             dim = m._param()
             mu = prng.normal(0.0, 2.0, size=(k_true, dim))

@@ -52,7 +52,8 @@ inline field hp_field(const msb_model_desc &m, const std::string &key) {
     case MSB_FAMILY_NICH:
       if (key == "mu") return {0, 1}; if (key == "kappa") return {1, 1};
       if (key == "sigmasq") return {2, 1}; if (key == "nu") return {3, 1}; break;
-    case MSB_FAMILY_DD: if (key == "alphas") return {0, d}; break;
+    case MSB_FAMILY_DD: case MSB_FAMILY_DM: if (key == "alphas") return {0, d}; break;  // dm.hpp get_hp_mutator
+    case MSB_FAMILY_BBNC: if (key == "alpha") return {0, 1}; if (key == "beta") return {1, 1}; break;  // bbnc.cpp:143-153
     case MSB_FAMILY_NIW:  // beyond the reference: its generic template throws "not supported" (distributions.hpp:112-118)
       if (key == "mu") return {0, d}; if (key == "kappa") return {d, 1};
       if (key == "psi") return {d + 1, d * d}; if (key == "nu") return {d + 1 + d * d, 1}; break;
@@ -67,6 +68,8 @@ inline field ss_field(const msb_model_desc &m, const std::string &key) {
     case MSB_FAMILY_GP: if (key == "count") return {0, 1}; if (key == "sum") return {1, 1}; if (key == "log_prod") return {2, 1}; break;
     case MSB_FAMILY_NICH: if (key == "count") return {0, 1}; if (key == "mean") return {1, 1}; if (key == "count_times_variance") return {2, 1}; break;
     case MSB_FAMILY_DD: if (key == "count_sum") return {0, 1}; if (key == "counts") return {1, d}; break;
+    case MSB_FAMILY_BBNC: if (key == "p") return {0, 1}; if (key == "heads") return {1, 1}; if (key == "tails") return {2, 1}; break;  // bbnc.cpp:107-118
+    case MSB_FAMILY_DM: if (key == "counts") return {0, d}; if (key == "ratio") return {d, 1}; break;  // schema.proto:25-28
     case MSB_FAMILY_NIW: if (key == "count") return {0, 1}; if (key == "sum_x") return {1, d}; if (key == "sum_xxT") return {1 + d, d * d}; break;
   }
   throw std::runtime_error("Unknown group SS param key: " + key);  // distributions.hpp:152
@@ -102,8 +105,10 @@ public:
   void add_value(const hypers &m, const common::value_accessor &value, common::rng_t &) override;
   void remove_value(const hypers &m, const common::value_accessor &value, common::rng_t &) override;
   float score_value(const hypers &m, const common::value_accessor &value, common::rng_t &) const override;
-  float score_data(const hypers &, common::rng_t &) const override { throw std::runtime_error("Not implemented: score_data"); }
-  void sample_value(const hypers &, common::value_mutator &, common::rng_t &) const override { throw std::runtime_error("Not implemented: sample_value"); }
+  float score_data(const hypers &m, common::rng_t &) const override;
+  // one draw from the posterior predictive (distributions.hpp:293-298); the caller's rng supplies the counter of the
+  // device's Philox stream, so the engine advances as it would upstream.  dm throws, as dm.cpp:100-111 does.
+  void sample_value(const hypers &m, common::value_mutator &value, common::rng_t &rng) const override;
   common::suffstats_bag_t get_ss() const override {  // raw little-endian doubles (the protobuf bag is row f3, not built)
     return common::suffstats_bag_t(reinterpret_cast<const char *>(ss_.data()), ss_.size() * sizeof(double));
   }
@@ -136,10 +141,10 @@ public:
   gpu_hypers(const msb_model_desc &m) : desc_(m), hp_(msb_model_hp_size(&m), 0.0) {
     // defaults of microscopes/models.pyx:189,211,223,238,264-269
     switch (m.family) {
-      case MSB_FAMILY_BB: case MSB_FAMILY_GP: hp_[0] = hp_[1] = 1.0; break;
+      case MSB_FAMILY_BB: case MSB_FAMILY_GP: case MSB_FAMILY_BBNC: hp_[0] = hp_[1] = 1.0; break;
       case MSB_FAMILY_BNB: hp_[0] = hp_[1] = hp_[2] = 1.0; break;
       case MSB_FAMILY_NICH: hp_[1] = hp_[2] = hp_[3] = 1.0; break;
-      case MSB_FAMILY_DD: for (auto &a : hp_) a = 1.0; break;
+      case MSB_FAMILY_DD: case MSB_FAMILY_DM: for (auto &a : hp_) a = 1.0; break;
       case MSB_FAMILY_NIW:
         hp_[m.dim] = 1.0;
         for (unsigned i = 0; i < m.dim; i++) hp_[m.dim + 1 + (size_t)i * m.dim + i] = 1.0;
@@ -188,17 +193,34 @@ inline float gpu_group::score_value(const hypers &m, const common::value_accesso
   return out;
 }
 
+inline float gpu_group::score_data(const hypers &m, common::rng_t &) const {
+  const gpu_hypers &h = static_cast<const gpu_hypers &>(m);
+  float out = 0.f;
+  b200::check(msb_value_score_data(b200::default_ctx(), &desc_, h.hp().data(), h.hp().size(), ss_.data(), ss_.size(), &out));
+  return out;
+}
+inline void gpu_group::sample_value(const hypers &m, common::value_mutator &value, common::rng_t &rng) const {
+  const gpu_hypers &h = static_cast<const gpu_hypers &>(m);
+  const uint64_t hi = (uint64_t)rng(), lo = (uint64_t)rng();
+  std::vector<double> x(desc_.family == MSB_FAMILY_NIW ? desc_.dim : 1u);
+  b200::check(msb_value_sample(b200::default_ctx(), &desc_, h.hp().data(), h.hp().size(), ss_.data(), ss_.size(),
+                               0x6d73625f64726177ull, (hi << 32) ^ lo, 1, x.data()));
+  if (value.shape() != x.size()) throw std::runtime_error("shapes do not match");  // distributions.hpp:243
+  for (size_t i = 0; i < x.size(); i++) value.set<double>(x[i], i);
+}
+
 // model handles: what microscopes/_models.pyx:22-44 constructs (bb, gp, nich, dd(size), niw(dim))
 class gpu_model : public model {
 public:
   gpu_model(int family, unsigned dim = 0) {
     desc_.family = family; desc_.dim = dim;
-    if ((family == MSB_FAMILY_DD || family == MSB_FAMILY_NIW) && dim == 0) throw std::runtime_error("no elements");  // distributions.hpp:429,478
+    if ((family == MSB_FAMILY_DD || family == MSB_FAMILY_NIW || family == MSB_FAMILY_DM) && dim == 0) throw std::runtime_error("no elements");  // distributions.hpp:429,478
   }
   std::shared_ptr<hypers> create_hypers() const override { return std::make_shared<gpu_hypers>(desc_); }
   common::runtime_type get_runtime_type() const override {
     switch (desc_.family) {  // the Value types of SURVEY.md section 2a
-      case MSB_FAMILY_BB: return common::runtime_type(TYPE_B);
+      case MSB_FAMILY_BB: case MSB_FAMILY_BBNC: return common::runtime_type(TYPE_B);  // bbnc.cpp:180-184
+      case MSB_FAMILY_DM: return common::runtime_type(TYPE_I32, desc_.dim);             // dm.hpp:186-190
       case MSB_FAMILY_BNB: case MSB_FAMILY_GP: return common::runtime_type(TYPE_U32);
       case MSB_FAMILY_NICH: return common::runtime_type(TYPE_F32);
       case MSB_FAMILY_DD: return common::runtime_type(TYPE_I32);
@@ -236,8 +258,9 @@ public:
 
   void set_alpha(double a) { b200::check(msb_state_set_cluster_hp(st_, "alpha", a)); }
   void set_hypers(size_t feature, const gpu_hypers &h) {
-    static const char *keys[6][4] = {{"alpha", "beta", 0, 0}, {"alpha", "beta", "r", 0}, {"alpha", "inv_beta", 0, 0},
-                                     {"mu", "kappa", "sigmasq", "nu"}, {"alphas", 0, 0, 0}, {"mu", "kappa", "psi", "nu"}};
+    static const char *keys[8][4] = {{"alpha", "beta", 0, 0}, {"alpha", "beta", "r", 0}, {"alpha", "inv_beta", 0, 0},
+                                     {"mu", "kappa", "sigmasq", "nu"}, {"alphas", 0, 0, 0}, {"mu", "kappa", "psi", "nu"},
+                                     {"alpha", "beta", 0, 0}, {"alphas", 0, 0, 0}};
     for (int i = 0; i < 4 && keys[descs_[feature].family][i]; i++) {
       const b200::field f = b200::hp_field(descs_[feature], keys[descs_[feature].family][i]);
       b200::check(msb_state_set_hp(st_, feature, keys[descs_[feature].family][i], h.hp().data() + f.off, f.cnt));

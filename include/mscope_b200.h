@@ -27,7 +27,7 @@
  *                         common/util.hpp:125-156 (scores_to_probs + sample_discrete)
  *   msb_state_sweep       one batched Gibbs reassignment pass: remove/score/sample/add
  *                          against frozen suffstats
- *   msb_value_*           single-value group::score_value/add_value/remove_value
+ *   msb_value_*           single-value group::score_value/add_value/remove_value/score_data/sample_value
  *                         (models/base.hpp:25-27), executed on the device
  *
  * Semantics notes
@@ -280,6 +280,19 @@ MSB_API int msb_value_add(msb_ctx *ctx, const msb_model_desc *model, const doubl
                   double *ss, size_t nss, const void *value, const msb_runtime_type *vtype);
 MSB_API int msb_value_remove(msb_ctx *ctx, const msb_model_desc *model, const double *hp, size_t nhp,
                      double *ss, size_t nss, const void *value, const msb_runtime_type *vtype);
+/* group::score_data (models/base.hpp:28; distributions.hpp:287-291; src/models/dm.cpp:79-95, bbnc.cpp:61-73): the marginal
+ * likelihood of the data summarised by one group's suffstats */
+MSB_API int msb_value_score_data(msb_ctx *ctx, const msb_model_desc *model, const double *hp, size_t nhp,
+                         const double *ss, size_t nss, float *score);
+/* group::sample_value (models/base.hpp:29; distributions.hpp:293-298; src/models/bbnc.cpp:75-83): n draws from the group's
+ * posterior predictive into out[n * width] (width = dim for niw, else 1).  Draw i reads the Philox stream
+ * (key = seed, counter = counter + i): the same (seed, counter) gives the same value on every device and in the checker.
+ * dm: MSB_ERR_UNSUPPORTED, "multinomial sampling unimplemented", as src/models/dm.cpp:100-111 throws. */
+MSB_API int msb_value_sample(msb_ctx *ctx, const msb_model_desc *model, const double *hp, size_t nhp,
+                     const double *ss, size_t nss, uint64_t seed, uint64_t counter, size_t n, double *out);
+/* the same from the suffstats resident in HBM: feature `feature` of group `gid` */
+MSB_API int msb_state_sample_value(msb_state *st, size_t feature, size_t gid, uint64_t seed, uint64_t counter,
+                           size_t n, double *out);
 MSB_API size_t msb_model_hp_size(const msb_model_desc *model);
 MSB_API size_t msb_model_ss_size(const msb_model_desc *model);
 

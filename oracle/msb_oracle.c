@@ -696,3 +696,104 @@ float orc_philox_u01(uint64_t seed, uint64_t row, uint64_t sweep) {
   orc_philox_raw(seed, row, sweep, r);
   return (float)(r[0] >> 8) * 5.9604644775390625e-8f; /* 2^-24, in [0,1) */
 }
+
+/* ---- group::sample_value (models/base.hpp:29; distributions.hpp:293-298; bbnc.cpp:75-83; dm.cpp:100-111) ----------
+ * Draws from the posterior predictive; upstream draws a parameter from the posterior and a value from the likelihood,
+ * whose marginal law is the same.  Draw i reads the Philox blocks (key = seed, counter = (counter + i, TAG | block)).
+ * bb / bbnc / dd: inverse CDF; gp / bnb: walk of the predictive pmf from 0 by its ratio recurrence;
+ * nich: Student-t from a normal and a gamma draw (Box-Muller, Marsaglia-Tsang); niw: multivariate Student-t through
+ * the Cholesky factor of the scale matrix; dm: not implemented upstream either (returns -1). */
+#define ORC_DRAW_TAG 0x53414d5000000000ull
+#define ORC_DRAW_WALK_CAP (1u << 26)
+typedef struct draw_stream { uint64_t seed, idx; uint32_t blk, buf[4]; int pos; } draw_stream;
+static uint32_t ds_next(draw_stream *r) {
+  if (r->pos == 4) { orc_philox_raw(r->seed, r->idx, ORC_DRAW_TAG | r->blk, r->buf); r->blk++; r->pos = 0; }
+  return r->buf[r->pos++];
+}
+static double ds_u53(draw_stream *r) {
+  uint32_t a = ds_next(r) >> 5, b = ds_next(r) >> 6;
+  return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+}
+static double ds_normal(draw_stream *r) {
+  double u1 = ds_u53(r), u2 = ds_u53(r);
+  return sqrt(-2.0 * log1p(-u1)) * cos(6.283185307179586 * u2);
+}
+static double ds_gamma(draw_stream *r, double k) {
+  double boost = 1.0;
+  if (k < 1.0) { boost = pow(1.0 - ds_u53(r), 1.0 / k); k += 1.0; }
+  double d = k - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (int it = 0; it < 1000; it++) {
+    double z = ds_normal(r);
+    double v = 1.0 + c * z;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    double u = 1.0 - ds_u53(r);
+    if (log(u) < 0.5 * z * z + d - d * v + d * log(v)) return boost * d * v;
+  }
+  return boost * d;
+}
+int orc_sample_value(const orc_model *m, const double *hp, const double *ss, uint64_t seed, uint64_t counter, size_t n,
+                     double *out) {
+  niw_prep prep;
+  unsigned d = m->dim;
+  if (m->family == ORC_DM) return -1;
+  if (m->family == ORC_NIW && niw_prepare(d, hp, ss, &prep) != 0) { niw_free(&prep); return -2; }
+  for (size_t i = 0; i < n; i++) {
+    draw_stream rs = {seed, counter + i, 0, {0, 0, 0, 0}, 4};
+    switch (m->family) {
+      case ORC_BB: out[i] = ds_u53(&rs) < (hp[0] + ss[0]) / (hp[0] + hp[1] + ss[0] + ss[1]) ? 1.0 : 0.0; break;
+      case ORC_BBNC: out[i] = ds_u53(&rs) < ss[0] ? 1.0 : 0.0; break;
+      case ORC_DD: {
+        double tot = 0.0;
+        for (unsigned c = 0; c < d; c++) tot += hp[c] + ss[1 + c];
+        double t = ds_u53(&rs) * tot;
+        unsigned x = d - 1;
+        for (unsigned c = 0; c < d; c++) { t -= hp[c] + ss[1 + c]; if (t < 0.0) { x = c; break; } }
+        out[i] = (double)x;
+      } break;
+      case ORC_GP: case ORC_BNB: {
+        double a, b, r = 0.0, p, ib = 0.0;
+        if (m->family == ORC_GP) {
+          a = hp[0] + ss[1]; b = hp[1] + ss[0];
+          p = exp(a * (log(b) - log1p(b)));
+          ib = 1.0 / (1.0 + b);
+        } else {
+          r = hp[2]; a = hp[0] + r * ss[0]; b = hp[1] + ss[1];
+          p = exp(lgamma(a + r) + lgamma(a + b) - lgamma(a + r + b) - lgamma(a));
+        }
+        double t = ds_u53(&rs);
+        uint32_t x = 0;
+        while (t >= p && x < ORC_DRAW_WALK_CAP) {
+          t -= p;
+          double xd = (double)x;
+          p *= m->family == ORC_GP ? (a + xd) / (xd + 1.0) * ib : (r + xd) / (xd + 1.0) * ((b + xd) / (a + r + b + xd));
+          x++;
+          if (p == 0.0) break;
+        }
+        out[i] = (double)x;
+      } break;
+      case ORC_NICH: {
+        double mu, kappa, sigmasq, nu;
+        nich_post64(hp, ss, &mu, &kappa, &sigmasq, &nu);
+        double lambda = kappa / ((kappa + 1.0) * sigmasq);
+        double g = ds_gamma(&rs, 0.5 * nu);
+        double z = ds_normal(&rs);
+        double tv = z * sqrt(0.5 * nu / g);
+        out[i] = mu + tv / (sqrt(lambda / nu) * sqrt(nu));
+      } break;
+      case ORC_NIW: {
+        double *o = out + i * (size_t)d;
+        double g = ds_gamma(&rs, 0.5 * prep.dof);
+        double s = sqrt(0.5 * prep.dof / g);
+        for (unsigned a = 0; a < d; a++) o[a] = prep.mu[a];
+        for (unsigned j = 0; j < d; j++) {
+          double z = ds_normal(&rs) * s;
+          for (unsigned a = j; a < d; a++) o[a] += prep.L[a * d + j] * z;
+        }
+      } break;
+      default: return -1;
+    }
+  }
+  if (m->family == ORC_NIW) niw_free(&prep);
+  return 0;
+}

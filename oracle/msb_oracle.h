@@ -84,6 +84,11 @@ void orc_update_rows(const orc_model *models, size_t D, const double *hp, double
                      size_t row_lo, size_t row_hi, const int32_t *assign_old, const int32_t *assign_new,
                      int prec);
 
+/* group::sample_value (models/base.hpp:29): n draws from the posterior predictive, draw i from the Philox stream
+ * (seed, counter + i); out[n * width], width = dim for niw.  Returns -1 for dm (unimplemented upstream, dm.cpp:100-111). */
+int orc_sample_value(const orc_model *m, const double *hp, const double *ss, uint64_t seed, uint64_t counter, size_t n,
+                     double *out);
+
 #ifdef __cplusplus
 }
 #endif

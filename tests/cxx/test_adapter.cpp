@@ -94,6 +94,70 @@ int main(int argc, char **argv) {
     std::printf("ok dd(300) through base.hpp interface\n");
   }
 
+  // ---- score_data, sample_value (base.hpp:28-29) and the in-tree models (bbnc, dm) ------------------------------
+  {
+    auto h = gpu_model(MSB_FAMILY_BB).create_hypers();
+    auto g = h->create_group(r);
+    const bool t = true, f = false;
+    for (int i = 0; i < 3; i++) g->add_value(*h, value_accessor(&t), r);
+    g->add_value(*h, value_accessor(&f), r);
+    // Beta-Bernoulli evidence with alpha = beta = 1: B(1 + 3, 1 + 1) / B(1, 1) = 1 / 20
+    EXPECT_NEAR(g->score_data(*h, r), std::log(1.0 / 20.0), 1e-6);
+    int heads = 0;
+    const int draws = 400;
+    for (int i = 0; i < draws; i++) {
+      bool x = false;
+      value_mutator vm(&x);
+      g->sample_value(*h, vm, r);
+      heads += x;
+    }
+    // predictive P(1) = 4 / 6; 400 draws: mean 266.7, sd 9.4
+    if (heads < 210 || heads > 320) { std::printf("FAIL bb sample_value: %d heads of %d\n", heads, draws); fails++; }
+    std::printf("ok score_data / sample_value through base.hpp (bb: %d heads of %d, expected ~267)\n", heads, draws);
+  }
+  {
+    auto h = gpu_model(MSB_FAMILY_NICH).create_hypers();
+    auto g = h->create_group(r);
+    const float xs[3] = {4.0f, 5.0f, 6.0f};
+    for (int rep = 0; rep < 20; rep++) for (float x : xs) g->add_value(*h, value_accessor(&x), r);
+    double sum = 0;
+    for (int i = 0; i < 300; i++) { float x = 0; value_mutator vm(&x); g->sample_value(*h, vm, r); sum += x; }
+    EXPECT_NEAR(sum / 300, 60 * 5.0 / 61, 0.05);  // posterior mean, predictive sd ~0.83 -> se 0.05
+    std::printf("ok nich sample_value mean %.3f\n", sum / 300);
+  }
+  {
+    auto m = gpu_model(MSB_FAMILY_BBNC);
+    auto h = m.create_hypers();
+    auto g = h->create_group(r);
+    g->get_ss_mutator("p").set<float>(0.25f);
+    const bool t = true;
+    EXPECT_NEAR(g->score_value(*h, value_accessor(&t), r), std::log(0.25), 1e-6);  // bbnc.cpp:46-53
+    g->add_value(*h, value_accessor(&t), r);
+    EXPECT_NEAR(g->get_ss_mutator("heads").accessor().get<double>(0), 1.0, 0);
+    // bbnc.cpp:61-73 with alpha = beta = 1: log Beta(p; 1, 1) + heads log p + tails log(1 - p)
+    EXPECT_NEAR(g->score_data(*h, r), std::log(0.25), 1e-6);
+    std::printf("ok bbnc through base.hpp interface\n");
+  }
+  {
+    auto m = gpu_model(MSB_FAMILY_DM, 3);
+    auto h = m.create_hypers();
+    auto g = h->create_group(r);
+    const int32_t a[3] = {2, 0, 1}, b[3] = {1, 1, 0};
+    const runtime_type vt(TYPE_I32, 3);
+    g->add_value(*h, value_accessor(reinterpret_cast<const uint8_t *>(a), nullptr, vt), r);
+    // dm.cpp:38-76: e = (3, 1, 2), E = 6, x = (1, 1, 0): 2!/(1! 1! 0!) * (3 * 1) / (6 * 7)
+    EXPECT_NEAR(g->score_value(*h, value_accessor(reinterpret_cast<const uint8_t *>(b), nullptr, vt), r), std::log(2.0 * 3.0 / 42.0), 1e-5);
+    EXPECT_NEAR(g->get_ss_mutator("ratio").accessor().get<double>(0), std::log(3.0), 1e-12);  // 3! / (2! 0! 1!)
+    // dm.cpp:79-95: ratio + evidence of (2, 0, 1) under alpha = 1: 3 * (1*2 * 1) / (3*4*5)
+    EXPECT_NEAR(g->score_data(*h, r), std::log(3.0 * 2.0 / 60.0), 1e-6);
+    bool threw = false;
+    int32_t out3[3];
+    value_mutator vm(reinterpret_cast<uint8_t *>(out3), vt);
+    try { g->sample_value(*h, vm, r); } catch (const std::runtime_error &e) { threw = std::string(e.what()).find("unimplemented") != std::string::npos; }
+    if (!threw) { std::printf("FAIL dm sample_value did not throw\n"); fails++; }  // dm.cpp:100-111
+    std::printf("ok dm through base.hpp interface\n");
+  }
+
   // ---- batched: same numbers as the per-value loop --------------------------------------------------
   {
     const size_t N = 257, K = 3;

@@ -97,6 +97,18 @@ class Oracle(object):
         self.lib.orc_score_data.argtypes = [C.POINTER(OrcModel), _P, _P]
         return self.lib.orc_score_data(C.byref(m), hp.ctypes.data, ss.ctypes.data)
 
+    # -- posterior-predictive draws (group::sample_value) ----------------------------
+    def sample_value(self, m, hp, ss, seed, counter, n):
+        hp = np.ascontiguousarray(hp, np.float64); ss = np.ascontiguousarray(ss, np.float64)
+        width = m.dim if m.family == NIW else 1
+        out = np.zeros((n, width), np.float64)
+        self.lib.orc_sample_value.restype = C.c_int
+        self.lib.orc_sample_value.argtypes = [C.POINTER(OrcModel), _P, _P, C.c_uint64, C.c_uint64, _SZ, _P]
+        rc = self.lib.orc_sample_value(C.byref(m), hp.ctypes.data, ss.ctypes.data, seed, counter, n, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("multinomial sampling unimplemented" if rc == -1 else "scale matrix is not positive definite")
+        return out if width > 1 else out[:, 0]
+
     def score_assignment(self, assign, alpha, prec=32):
         a = np.ascontiguousarray(assign, np.int64)
         if prec == 32:

@@ -819,3 +819,52 @@ def test_bbnc_group_parameter_is_a_beta_draw_and_survives_everything(ctx, oracle
     st3 = cb.state.deserialize(ctx, descs, view, blob)
     assert abs(st3.get_suffstats(0, gids[3], "p")[0] - 0.25) < 1e-7
     st.close(); st2.close(); st3.close()
+
+
+def test_sample_value_draws_equal_the_checkers(ctx, oracle):
+    # group::sample_value (models/base.hpp:29): device draws from the Philox stream (seed, counter + i) against the CPU
+    # restatement of the same sequence -- counts identical, reals to fp64 rounding; from the resident suffstats
+    # (msb_state_sample_value) and through the single-group plugin call (msb_value_sample)
+    import ctypes as C
+    from common_b200 import _lib
+    lib = _lib.load()
+    descs = [cb.bb, cb.bnb, cb.gp, cb.nich, cb.dd(9), cb.niw(3), cb.bbnc, cb.niw(64), cb.dm(4)]
+    n, k = 1200, 5
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=23, extra_empty=1)
+    off = hoff = 0
+    for d, desc in enumerate(descs):
+        m = oracle.model(desc)
+        w, hw = oracle.ss_size(m), oracle.hp_size(m)
+        name = desc().name()
+        for c in (0, 3, k):                     # two populated groups and the empty one (prior predictive)
+            g = gids[c]
+            if name == "dm":
+                with pytest.raises(cb.MsbError, match="multinomial sampling unimplemented"):
+                    st.sample_value(d, g, 7)
+                continue
+            ndraw = 700 if name != "niw" else 60
+            got = st.sample_value(d, g, seed=7, counter=1000 * c, n=ndraw)
+            want = oracle.sample_value(m, hp[hoff:hoff + hw], ss[c, off:off + w], 7, 1000 * c, ndraw)
+            if name in ("bb", "bbnc", "dd", "gp", "bnb"):
+                assert np.array_equal(got, want), name
+            else:   # the suffstats themselves were accumulated in another order on the device
+                assert np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) < 1e-9, name
+            # the plugin call on the same suffstats
+            md = desc().c_desc()
+            h = np.ascontiguousarray(hp[hoff:hoff + hw]); s = np.ascontiguousarray(ss[c, off:off + w])
+            out = np.zeros(got.shape, np.float64)
+            _lib.check(lib.msb_value_sample(ctx.handle, C.byref(md), h.ctypes.data_as(C.POINTER(C.c_double)), h.size,
+                                            s.ctypes.data_as(C.POINTER(C.c_double)), s.size, 7, 1000 * c, ndraw,
+                                            out.ctypes.data_as(C.POINTER(C.c_double))))
+            if name in ("bb", "bbnc", "dd", "gp", "bnb"):
+                assert np.array_equal(out, want), name
+            else:
+                assert np.max(np.abs(out - want) / np.maximum(1.0, np.abs(want))) < 1e-11, name
+            # group::score_data of one group through the plugin call
+            sc = C.c_float()
+            _lib.check(lib.msb_value_score_data(ctx.handle, C.byref(md), h.ctypes.data_as(C.POINTER(C.c_double)), h.size,
+                                                s.ctypes.data_as(C.POINTER(C.c_double)), s.size, C.byref(sc)))
+            wd = oracle.score_data(m, h, s)
+            assert abs(sc.value - wd) <= 2e-6 * max(1.0, abs(wd)), name
+        off += w; hoff += hw
+    st.close()

@@ -308,3 +308,55 @@ def test_dm_follows_the_in_tree_source(oracle):
     for x in reversed(xs):
         oracle.remove_value(m, hp, ss, x)
     assert np.all(ss[:C] == 0) and abs(ss[C]) < 1e-9
+
+
+def test_sample_value_draws_follow_the_predictive(oracle):
+    # group::sample_value (models/base.hpp:29): the checker's draws against the (golden-pinned) predictive --
+    # chi-square for the discrete families, Kolmogorov-Smirnov for nich, moments for niw
+    from scipy import stats
+    n = 40000
+    for fam, dim, hp, ss, support in [(ol.BB, 0, [0.7, 1.4], [6, 3], 2), (ol.BBNC, 0, [1.0, 1.0], [0.27, 4, 9], 2),
+                                      (ol.DD, 5, [0.5, 1, 2, 0.1, 1], [9, 3, 0, 4, 1, 1], 5),
+                                      (ol.GP, 0, [2.0, 0.5], [6, 31, 0.0], 60), (ol.BNB, 0, [3.0, 2.0, 4.0], [5, 9], 400)]:
+        m = ol.OrcModel(fam, dim)
+        x = oracle.sample_value(m, hp, ss, 99, 0, n)
+        assert np.all(x == np.floor(x)) and x.min() >= 0
+        pmf = np.exp([oracle.score_value(m, hp, ss, [v]) for v in range(support)])
+        obs = np.bincount(np.minimum(x.astype(int), support - 1), minlength=support).astype(float)
+        exp = pmf * n
+        exp[-1] += n - exp.sum()       # the tail beyond the listed support
+        keep = exp > 5
+        chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum() + (obs[~keep].sum() - exp[~keep].sum()) ** 2 / max(exp[~keep].sum(), 1.0)
+        assert chi2 < stats.chi2.ppf(1 - 1e-6, keep.sum()), (fam, chi2)
+    m = ol.OrcModel(ol.NICH, 0)
+    hp, ss = [0.5, 2.0, 1.5, 3.0], [7, 1.2, 9.5]
+    x = oracle.sample_value(m, hp, ss, 5, 1000, n)
+    kappa, nu = 2.0 + 7, 3.0 + 7
+    mu = (2.0 * 0.5 + 7 * 1.2) / kappa
+    sigmasq = (3.0 * 1.5 + 9.5 + 7 * 2.0 * (0.5 - 1.2) ** 2 / kappa) / nu
+    ks = stats.kstest(x, stats.t(df=nu, loc=mu, scale=np.sqrt(sigmasq * (kappa + 1) / kappa)).cdf)
+    assert ks.pvalue > 1e-4, ks
+    # a shape below 1 takes the boosted branch of the gamma sampler: nu' = 0.6
+    x = oracle.sample_value(m, [0.0, 1.0, 1.0, 0.6], [0, 0, 0], 5, 0, n)
+    assert stats.kstest(x, stats.t(df=0.6, loc=0.0, scale=np.sqrt(2.0)).cdf).pvalue > 1e-4
+    d = 3
+    m = ol.OrcModel(ol.NIW, d)
+    rng = np.random.default_rng(3)
+    data = rng.normal(size=(30, d)) @ np.array([[1.0, 0.4, 0.0], [0.0, 1.0, 0.3], [0.0, 0.0, 0.5]]) + [1.0, -2.0, 0.5]
+    hp = np.concatenate([np.zeros(d), [1.0], np.eye(d).ravel(), [d + 2.0]])
+    ss = np.concatenate([[30], data.sum(0), (data.T @ data).ravel()])
+    x = oracle.sample_value(m, hp, ss, 8, 0, n)
+    kn, nun = 31.0, d + 2.0 + 30
+    mun = data.sum(0) / kn
+    psin = np.eye(d) + data.T @ data - kn * np.outer(mun, mun)
+    dof = nun - d + 1
+    scale = psin * (kn + 1) / (kn * dof)
+    assert np.allclose(x.mean(0), mun, atol=5 * np.sqrt(np.diag(scale).max() / n) * 2)
+    assert np.allclose(np.cov(x.T), scale * dof / (dof - 2), rtol=0.05, atol=0.02)
+    # the Mahalanobis radius / d of a multivariate t is F(d, dof)
+    r = np.einsum("ni,ij,nj->n", x - mun, np.linalg.inv(scale), x - mun) / d
+    assert stats.kstest(r, stats.f(d, dof).cdf).pvalue > 1e-4
+    # draws are a pure function of (seed, counter + i)
+    assert np.array_equal(oracle.sample_value(m, hp, ss, 8, 100, 5), x[100:105])
+    with pytest.raises(RuntimeError):
+        oracle.sample_value(ol.OrcModel(ol.DM, 3), [1, 1, 1], [0, 0, 0, 0], 1, 0, 1)   # dm.cpp:100-111
