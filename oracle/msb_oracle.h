@@ -25,7 +25,9 @@
  * add_value / remove_value => at the `distributions`
  * boundary parity is UNPINNED.  What IS pinned: bb and niw predictive against
  * the reference's own Python closed forms (vendor/stats.py, run in the build
- * container, fixtures in tests/golden/), every family against scipy in fp64,
+ * container, fixtures in tests/golden/), bbnc and dm bookkeeping against runs
+ * of the reference's in-tree Python models (microscopes/dbg/models/*.py ->
+ * tests/golden/intree_models.json), every family against scipy in fp64,
  * the dataview layout against the reference's real headers (oracle/_ref).
  */
 #ifndef MSB_ORACLE_H

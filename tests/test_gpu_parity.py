@@ -868,3 +868,53 @@ def test_sample_value_draws_equal_the_checkers(ctx, oracle):
             assert abs(sc.value - wd) <= 2e-6 * max(1.0, abs(wd)), name
         off += w; hoff += hw
     st.close()
+
+
+def test_value_abi_against_runs_of_the_references_own_python_models(ctx):
+    # the single-value plugin calls on the device against tests/golden/intree_models.json (outputs of the reference's
+    # in-tree dbg/models/bbnc.py and dm.py, scripts/make_golden_intree.py)
+    import ctypes as C
+    from common_b200 import _lib
+    lib = _lib.load()
+    with open(os.path.join(GOLD, "intree_models.json")) as f:
+        gold = json.load(f)
+    PD = C.POINTER(C.c_double)
+
+    def op(fn, md, hp, ss, x, *extra):
+        xa = np.ascontiguousarray(np.atleast_1d(x), np.float64)
+        vt = _lib.RuntimeType(_lib.TYPE_F64, xa.size, 1 if xa.size > 1 else 0)
+        _lib.check(fn(ctx.handle, C.byref(md), hp.ctypes.data_as(PD), hp.size, ss.ctypes.data_as(PD), ss.size, xa.ctypes.data,
+                      C.byref(vt), *extra))
+
+    def score_data(md, hp, ss):
+        out = C.c_float()
+        _lib.check(lib.msb_value_score_data(ctx.handle, C.byref(md), hp.ctypes.data_as(PD), hp.size, ss.ctypes.data_as(PD), ss.size,
+                                            C.byref(out)))
+        return out.value
+
+    md = _lib.ModelDesc(_lib.FAMILY_BBNC, 0)
+    for r in gold["bbnc"]:
+        hp = np.array([r["alpha"], r["beta"]]); ss = np.array([r["p"], 0.0, 0.0])
+        for v in r["values"]:
+            op(lib.msb_value_add, md, hp, ss, float(v))
+        assert ss[1:].tolist() == r["after_add"]
+        for x, key in ((1.0, "score_true"), (0.0, "score_false")):
+            out = C.c_float()
+            op(lib.msb_value_score, md, hp, ss, x, C.byref(out))
+            assert abs(out.value - r[key]) <= RTOL * max(1.0, abs(r[key]))
+        assert abs(score_data(md, hp, ss) - r["score_data"]) <= RTOL * max(1.0, abs(r["score_data"]))
+        for v in r["removed"]:
+            op(lib.msb_value_remove, md, hp, ss, float(v))
+        assert ss[1:].tolist() == r["after_remove"]
+    for r in gold["dm"]:
+        Cn = r["dim"]
+        md = _lib.ModelDesc(_lib.FAMILY_DM, Cn)
+        hp = np.ones(Cn); ss = np.zeros(Cn + 1)
+        for x in r["rows"]:
+            op(lib.msb_value_add, md, hp, ss, np.asarray(x, float))
+        assert ss[:Cn].tolist() == r["counts_after_add"]
+        assert abs(ss[Cn] - r["ratio_after_add"]) <= 1e-11 * max(1.0, abs(r["ratio_after_add"]))
+        for x in r["rows"][:r["removed"]]:
+            op(lib.msb_value_remove, md, hp, ss, np.asarray(x, float))
+        assert ss[:Cn].tolist() == r["counts_after_remove"]
+        assert abs(ss[Cn] - r["ratio_after_remove"]) <= 1e-10 * max(1.0, abs(r["ratio_after_add"]))

@@ -360,3 +360,41 @@ def test_sample_value_draws_follow_the_predictive(oracle):
     assert np.array_equal(oracle.sample_value(m, hp, ss, 8, 100, 5), x[100:105])
     with pytest.raises(RuntimeError):
         oracle.sample_value(ol.OrcModel(ol.DM, 3), [1, 1, 1], [0, 0, 0, 0], 1, 0, 1)   # dm.cpp:100-111
+
+
+def _intree():
+    with open(os.path.join(GOLD, "intree_models.json")) as f:
+        return json.load(f)
+
+
+def test_oracle_against_runs_of_the_references_own_python_models(oracle):
+    # tests/golden/intree_models.json = outputs of /root/reference/microscopes/dbg/models/{bbnc,dm}.py run in the
+    # build container (scripts/make_golden_intree.py): the one place the reference tree itself computes this path
+    gold = _intree()
+    m = ol.OrcModel(ol.BBNC, 0)
+    for r in gold["bbnc"]:
+        hp = np.array([r["alpha"], r["beta"]])
+        ss = np.array([r["p"], 0.0, 0.0])
+        for v in r["values"]:
+            oracle.add_value(m, hp, ss, float(v))
+        assert ss[1:].tolist() == r["after_add"]
+        assert oracle.score_value(m, hp, ss, 1.0) == pytest.approx(r["score_true"], rel=1e-14)
+        assert oracle.score_value(m, hp, ss, 0.0) == pytest.approx(r["score_false"], rel=1e-14)
+        assert oracle.score_data(m, hp, ss) == pytest.approx(r["score_data"], rel=1e-12)
+        for v in r["removed"]:
+            oracle.remove_value(m, hp, ss, float(v))
+        assert ss[1:].tolist() == r["after_remove"]
+        assert oracle.score_data(m, hp, ss) == pytest.approx(r["score_data_after_remove"], rel=1e-12)
+    for r in gold["dm"]:
+        C = r["dim"]
+        m = ol.OrcModel(ol.DM, C)
+        hp = np.ones(C)
+        ss = np.zeros(C + 1)
+        for x in r["rows"]:
+            oracle.add_value(m, hp, ss, np.asarray(x, float))
+        assert ss[:C].tolist() == r["counts_after_add"]
+        assert ss[C] == pytest.approx(r["ratio_after_add"], rel=1e-12, abs=1e-12)
+        for x in r["rows"][:r["removed"]]:
+            oracle.remove_value(m, hp, ss, np.asarray(x, float))
+        assert ss[:C].tolist() == r["counts_after_remove"]
+        assert ss[C] == pytest.approx(r["ratio_after_remove"], rel=1e-12, abs=1e-10)
