@@ -201,6 +201,7 @@ def main():
         if rank != 0:
             return 0
         cfg, descs, storage, n, k, arr, z = build_workload(args, 0, 1)
+        name = workload_name(args, cfg, descs, n, k)   # the same workload as the b200 arm; each step times a bounded sample of its rows
         n = min(n, 200_000)
         arr, z = arr[:n], z[:n]
         ncores = usable_cores()
@@ -215,8 +216,8 @@ def main():
         line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args, cfg, descs, n, k), "rows_per_step": rates[-1]["rows"], "groups": k,
-                           "features": len(descs)},
+                "config": {"workload": name, "rows_per_step": rates[-1]["rows"], "groups": k, "features": len(descs),
+                           "sample": "each step scores rows_per_step of the workload's rows against all K groups x D features"},
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": rates[-1]["cores"], "kind": "port", "api": rates[-1]["kind"], "sample": rates[-1]["sample"]},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
