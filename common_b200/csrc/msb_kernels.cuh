@@ -653,6 +653,78 @@ __global__ void dm_score_kernel(FeatDev f, const double *__restrict__ hp, const 
   scores[(row - row_lo) * ld + k] += (OUT)s;
 }
 
+// The batched form: a block owns a tile of 32 group columns (e_i transposed into shared memory, lane = group) and
+// DM_TILE_ROWS rows (one warp per row, the row's counts are warp-uniform loads).  Per (row, group) the predictive is
+//   log [ prod_i (e_i)_(x_i) / (E)_(X) ] + log X! - sum_i log x_i!      ((a)_(n) = a (a + 1) ... (a + n - 1))
+// with the rising factorials multiplied out in fp64 (no lgamma(e + x) - lgamma(e) cancellation, one log per
+// (row, group) instead of one per category) whenever the counts are small; large counts take the lgamma form.
+constexpr int DM_TILE_ROWS = 64;
+__constant__ double c_lfact[21] = {0.0, 0.0, 0.6931471805599453, 1.791759469228055, 3.1780538303479458, 4.787491742782046,
+                                   6.579251212010101, 8.525161361065415, 10.604602902745251, 12.801827480081469,
+                                   15.104412573075516, 17.502307845873887, 19.987214495661885, 22.552163853123425,
+                                   25.19122118273868, 27.89927138384089, 30.671860106080672, 33.50507345013689,
+                                   36.39544520803305, 39.339884187199495, 42.335616460753485};
+__device__ __forceinline__ double lfact(uint32_t n) { return n <= 20u ? c_lfact[n] : lgamma((double)n + 1.0); }
+
+template <typename OUT>
+__global__ void __launch_bounds__(256) dm_score_tile_kernel(FeatDev f, const double *__restrict__ hp, const double *__restrict__ ss,
+                                                            const int32_t *__restrict__ col2slot, int K, OUT *__restrict__ scores,
+                                                            size_t ld, size_t row_lo, size_t row_hi) {
+  extern __shared__ double sm[];
+  const int C = (int)f.dim;
+  double *eT = sm;            // [C][32]
+  double *Es = sm + C * 32;   // [32]: E = sum_i e_i
+  double *lgE = Es + 32;      // [32]
+  const int k0 = blockIdx.y * 32;
+  const double *h = hp + f.hp_off;
+  for (int idx = threadIdx.x; idx < C * 32; idx += blockDim.x) {
+    const int kk = idx / C, i = idx - kk * C;
+    const int k = k0 + kk;
+    eT[i * 32 + kk] = k < K ? h[i] + ss[f.ss_off + (size_t)col2slot[k] * f.ss_w + i] : 1.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double E = 0.0;
+    for (int i = 0; i < C; i++) E += eT[i * 32 + threadIdx.x];
+    Es[threadIdx.x] = E;
+    lgE[threadIdx.x] = lgamma(E);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = k0 + lane;
+  const size_t tile_lo = row_lo + (size_t)blockIdx.x * DM_TILE_ROWS;
+  const size_t tile_hi = tile_lo + DM_TILE_ROWS < row_hi ? tile_lo + DM_TILE_ROWS : row_hi;
+  const double E = Es[lane];
+  for (size_t row = tile_lo + warp; row < tile_hi; row += 8) {
+    const uint32_t *x = (const uint32_t *)f.col + row * (size_t)C;
+    if (x[0] == GP_SENTINEL) continue;  // masked (warp-uniform)
+    double s = 0.0, p = 1.0, rowc = 0.0, X = 0.0;
+    for (int i = 0; i < C; i++) {
+      const uint32_t xi = x[i];
+      if (!xi) continue;
+      rowc -= lfact(xi);
+      X += (double)xi;
+      const double e = eT[i * 32 + lane];
+      if (xi <= 12u) {
+        for (uint32_t j = 0; j < xi; j++) p *= e + (double)j;
+        if (p > 1e100 || p < 1e-100) { s += log(p); p = 1.0; }
+      } else {
+        s += lgamma(e + (double)xi) - lgamma(e);
+      }
+    }
+    if (X <= 16.0) {
+      double q = 1.0;
+      const int n = (int)X;
+      for (int j = 0; j < n; j++) q *= E + (double)j;
+      s += log(p) - log(q);
+    } else {
+      s += log(p) + lgE[lane] - lgamma(E + X);
+    }
+    rowc += X <= 20.0 ? c_lfact[(int)X] : lgamma(X + 1.0);
+    if (k < K) scores[(row - row_lo) * ld + k] += (OUT)(s + rowc);
+  }
+}
+
 // dm update: one warp per moved row, lanes over the categories; counts += / -= x, ratio as dm.cpp:9-36
 __global__ void update_dm_kernel(FeatDev f, const int32_t *__restrict__ old_slot, const int32_t *__restrict__ new_slot,
                                  size_t row_lo, size_t row_hi, double *__restrict__ delta) {

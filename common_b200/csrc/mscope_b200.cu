@@ -1301,6 +1301,24 @@ static int build_params(msb_state *st) {
 static inline size_t row_origin(size_t row_lo) { return row_lo & ~(size_t)127; }
 
 // scores is indexed from row_origin(row_lo): element (row, col) at (row - org) * ld + col (or blocked)
+// dm term of the score matrix: the 32-group tile kernel while its transposed e-tile fits in shared memory, else one block per group
+template <typename OUT>
+static int launch_dm(msb_ctx *ctx, const FeatDev &f, const double *d_hp, const double *d_ss, const int32_t *d_col2slot, size_t K,
+                     OUT *scores, size_t ld, size_t row_lo, size_t row_hi) {
+  const size_t nrows = row_hi - row_lo;
+  const size_t smem = ((size_t)f.dim * 32 + 64) * sizeof(double);
+  if (smem <= 200 * 1024 && !getenv("MSB_DM_NO_TILE")) {
+    if (smem > 48 * 1024)
+      CU_TRY(cudaFuncSetAttribute(dm_score_tile_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(nrows, DM_TILE_ROWS), cdiv(K, 32));
+    LAUNCH(ctx, dm_score_tile_kernel<OUT>, grid, 256, smem, f, d_hp, d_ss, d_col2slot, (int)K, scores, ld, row_lo, row_hi);
+  } else {
+    dim3 grid(cdiv(nrows, 128), (unsigned)K);
+    LAUNCH(ctx, dm_score_kernel<OUT>, grid, 128, (size_t)f.dim * sizeof(double), f, d_hp, d_ss, d_col2slot, scores, ld, row_lo, row_hi);
+  }
+  return MSB_OK;
+}
+
 static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scores, bool blocked = false) {
   msb_ctx *ctx = st->ctx;
   const size_t org = row_origin(row_lo);
@@ -1378,9 +1396,7 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
       LAUNCH(ctx, fill_rows_kernel, cdiv(nrows * st->ld, 256), 256, 0, scores, st->ld, st->d_base, nrows);
       need_init = false;
     }
-    dim3 grid(cdiv(nrows, 128), (unsigned)K);
-    LAUNCH(ctx, dm_score_kernel<float>, grid, 128, (size_t)f.dim * sizeof(double), f, st->d_hp, st->d_ss, st->d_col2slot, scores, st->ld,
-           row_lo, row_hi);
+    MSB_TRY(launch_dm(ctx, f, st->d_hp, st->d_ss, st->d_col2slot, K, scores, st->ld, row_lo, row_hi));
   }
   return MSB_OK;
 }
@@ -1707,9 +1723,7 @@ extern "C" MSB_API int msb_state_score_rows_f64(msb_state *st, size_t row_lo, si
   for (size_t d = 0; d < st->D; d++) {
     const FeatDev &f = st->feats[d];
     if (f.kind != KIND_DM) continue;
-    dim3 grid(cdiv(nrows, 128), (unsigned)K);
-    LAUNCH(ctx, dm_score_kernel<double>, grid, 128, (size_t)f.dim * sizeof(double), f, st->d_hp, st->d_ss, st->d_col2slot, d_out.p, K,
-           row_lo, row_hi);
+    MSB_TRY(launch_dm(ctx, f, st->d_hp, st->d_ss, st->d_col2slot, K, d_out.p, K, row_lo, row_hi));
   }
   CU_TRY(cudaMemcpy2DAsync(scores, sizeof(double) * ld, d_out, sizeof(double) * K, sizeof(double) * K, nrows,
                            cudaMemcpyDeviceToHost, ctx->stream));

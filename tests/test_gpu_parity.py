@@ -918,3 +918,37 @@ def test_value_abi_against_runs_of_the_references_own_python_models(ctx):
             op(lib.msb_value_remove, md, hp, ss, np.asarray(x, float))
         assert ss[:Cn].tolist() == r["counts_after_remove"]
         assert abs(ss[Cn] - r["ratio_after_remove"]) <= 1e-10 * max(1.0, abs(r["ratio_after_add"]))
+
+
+@pytest.mark.parametrize("C,alpha,total", [(3, 1.0, 4), (24, 1e-9, 3), (24, 0.3, 400), (300, 0.5, 60), (1000, 1.0, 30)],
+                         ids=["small-counts", "tiny-alphas", "large-counts", "C300-optin-smem", "C1000-per-group-kernel"])
+def test_dm_score_kernels_over_their_branches(ctx, oracle, C, alpha, total, monkeypatch):
+    # dm_score_tile_kernel: rising-factorial products (counts <= 12, row totals <= 16) against the lgamma form the
+    # checker uses (dm.cpp:38-76), its flush of a product that leaves [1e-100, 1e100], the shared-memory opt-in, and
+    # the one-block-per-group kernel that takes over when the transposed tile does not fit
+    rng = np.random.default_rng(C)
+    n, k = 500, 37
+    descs = [cb.dm(C)]
+    theta = rng.dirichlet(np.full(C, 0.3), size=k)
+    z = np.arange(n) % k
+    x = np.stack([rng.multinomial(int(rng.integers(0, total + 1)), theta[z[i]]) for i in range(n)]).astype(np.int32)
+    arr = np.zeros(n, dtype=[("f0", np.int32, (C,))])
+    arr["f0"] = x
+    view = cb.numpy_dataview(arr)
+    st = cb.state(ctx, descs, max_groups=k + 4, cluster_hp={"alpha": 1.0})
+    alphas = np.full(C, alpha) * rng.uniform(0.5, 2.0, C)
+    st.set_component_hp(0, {"alphas": alphas})
+    st.bind(view)
+    gids = [st.create_group() for _ in range(k + 1)]
+    st.add_values(np.asarray(gids)[z])
+    ss, counts = ol.build_suffstats(oracle, descs, alphas, view, z, k + 1)
+    want = oracle.score_rows(descs, alphas, ss, ol.logprior(counts, 1.0), view, prec=64)
+    _, S64 = st.score_rows_f64()
+    assert np.max(np.abs(S64 - want) / np.maximum(1.0, np.abs(want))) < 2e-11
+    _, S = st.score_rows()
+    assert np.max(rel_err(S, want)) < RTOL
+    if C <= 300:
+        monkeypatch.setenv("MSB_DM_NO_TILE", "1")
+        _, S64b = st.score_rows_f64()
+        assert np.max(np.abs(S64b - S64) / np.maximum(1.0, np.abs(S64))) < 2e-11
+    st.close()
