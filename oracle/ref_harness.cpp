@@ -450,24 +450,32 @@ __attribute__((visibility("default"))) int ref_score_rows(
   try {
     built_state st = build(models, D, hp, ss, K, types);
     if (nthreads < 1) nthreads = 1;
-    auto worker = [&](size_t lo, size_t hi) {
+    // everything the loop reads is captured BY VALUE: captured references would live in this frame, next to the locals
+    // the calling thread writes while it runs its own share, and every other thread would take those cache misses
+    // (measured: 2 threads slower than 1)
+    const built_state *stp = &st;
+    auto worker = [=](size_t lo, size_t hi) {
       rng_t rng(73);
+      const size_t rowsize = stp->rowsize, maskrowsize = stp->maskrowsize;
+      const std::vector<runtime_type> *tys = &stp->types;
       for (size_t i = lo; i < hi; i++) {
-        const bool *mrow = mask ? reinterpret_cast<const bool *>(mask) + st.maskrowsize * i : nullptr;
-        row_accessor acc(data + st.rowsize * i, mrow, &st.types);  // what row_major_dataview::get() builds, dataview.cpp:97-104
+        const bool *mrow = mask ? reinterpret_cast<const bool *>(mask) + maskrowsize * i : nullptr;
+        row_accessor acc(data + rowsize * i, mrow, tys);  // what row_major_dataview::get() builds, dataview.cpp:97-104
         for (size_t k = 0; k < K; k++) {
           float s = (float)logprior[k];
+          const std::shared_ptr<models::group> *gk = stp->groups[k].data();
+          const std::shared_ptr<models::hypers> *hs = stp->hypers.data();
           acc.reset();
           for (size_t d = 0; d < D; d++, acc.bump())
-            if (!acc.anymasked()) s += st.groups[k][d]->score_value(*st.hypers[d], acc.get(), rng);
+            if (!acc.anymasked()) s += gk[d]->score_value(*hs[d], acc.get(), rng);
           out[(i - row_lo) * K + k] = s;
         }
       }
     };
     std::vector<std::thread> th;
     const size_t n = row_hi - row_lo;
-    for (int t = 0; t + 1 < nthreads; t++) th.emplace_back(worker, row_lo + n * t / nthreads, row_lo + n * (t + 1) / nthreads);
-    worker(row_lo + n * (nthreads - 1) / nthreads, row_hi);
+    if (nthreads == 1) worker(row_lo, row_hi);
+    else for (int t = 0; t < nthreads; t++) th.emplace_back(worker, row_lo + n * t / nthreads, row_lo + n * (t + 1) / nthreads);
     for (auto &t : th) t.join();
     return 0;
   } catch (const std::exception &) {
