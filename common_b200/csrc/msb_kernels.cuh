@@ -5,7 +5,8 @@
 
 namespace msb {
 
-enum Kind : int { KIND_TABLE = 0, KIND_GP = 1, KIND_NICH = 2, KIND_NIW = 3, KIND_DM = 4 };
+enum Kind : int { KIND_TABLE = 0, KIND_GP = 1, KIND_NICH = 2, KIND_NIW = 3, KIND_DM = 4,
+                  KIND_BIN = 5 };  // KIND_BIN: score-kernel-local code of a KIND_TABLE feature in binary form (FeatDev::binform)
 enum ColType : int { COL_U8 = 0, COL_U16 = 1, COL_U32 = 2, COL_F32 = 3 };
 
 constexpr uint32_t GP_SENTINEL = 0xFFFFFFFFu;
@@ -26,7 +27,8 @@ struct FeatDev {
   const uint32_t *slowmask; // per 32-row block: rows that need the score kernel's slow path (gp overflow, nich masked);
                             // niw: the centre c, f32[dim] (0 for coordinates that are not far from the origin)
   uint32_t has_slow;        // any bit set in slowmask
-  uint32_t pad_;
+  uint32_t binform;         // bb next to nich features: scored as base + x * (t1 - t0) on the FMA pipe instead of a table lookup
+                            // (chunk rows: t1 - t0, t0; score column: x as 0.0f / 1.0f, masked cells 0 with their slow bit set)
   uint64_t hp_off;    // into hp[]
   uint64_t ss_off;    // into ss[] / delta[]: block[slot * ss_w + j]
   double asum;        // dd: sum of alphas.  nich: the centre c of the score column (x' = x - c; 0 unless the whole column is far from 0)
@@ -136,6 +138,10 @@ __global__ void scorecol_kernel(const FeatDev *__restrict__ feats, int nfeat, si
       else x = ((const uint32_t *)f.col)[row];
     }
     out = x < f.ncat ? x : f.ncat;
+    if (f.binform) {  // binary form: the value itself; masked / out-of-range cells take the slow path
+      slow = row < n && x >= f.ncat;
+      out = __float_as_uint(x == 1u ? 1.0f : 0.0f);
+    }
   }
   const_cast<uint32_t *>(f.scol)[row] = out;
   const uint32_t m = __ballot_sync(0xffffffffu, slow);
@@ -233,6 +239,10 @@ ingest_tile_kernel(const uint8_t *__restrict__ data, const uint8_t *__restrict__
         else ((uint32_t *)f.col)[row] = x;
       }
       out = x;
+      if (f.binform) {
+        slow = live && x >= f.ncat;
+        out = __float_as_uint(x == 1u ? 1.0f : 0.0f);
+      }
     }
     if (row < n_pad) const_cast<uint32_t *>(f.scol)[row] = out;
     const uint32_t m = __ballot_sync(0xffffffffu, slow);
@@ -322,7 +332,10 @@ __global__ void build_params_kernel(const FeatDev *__restrict__ feats, int nfeat
     float v = 0.f;
     if (col < ncols) {
       const double *gss = ss + f.ss_off + (size_t)col2slot[col] * f.ss_w;
-      if (f.kind == KIND_TABLE) {
+      if (f.kind == KIND_TABLE && f.binform) {  // rows: t1 - t0 (difference taken in fp64), t0
+        const double t0 = bb_score(fhp, gss, 0), t1 = bb_score(fhp, gss, 1);
+        v = xr == 0 ? (float)(t1 - t0) : (float)t0;
+      } else if (f.kind == KIND_TABLE) {
         if ((uint32_t)xr < f.ncat)
           v = (float)(f.family == FAM_BB ? bb_score(fhp, gss, xr) : f.family == FAM_BBNC ? bbnc_score(gss, xr)
                                                                                     : dd_score(fhp, f.asum, gss, (uint32_t)xr));
@@ -1186,8 +1199,8 @@ __global__ void base_kernel(const double *__restrict__ counts, const int32_t *__
   }
 }
 
-// base[col] += sum over nich features of c0[col]: the row-independent part of the nich term is added once
-// per (row, group) in the score kernel's epilogue instead of once per unit
+// base[col] += sum over nich features of c0[col] (and over binary-form bb features of t0[col]): the row-independent
+// part of the term is added once per (row, group) in the score kernel's epilogue instead of once per unit
 __global__ void nich_c0_sum_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restrict__ params,
                                    size_t region_rows, int KT, int ncols_padded, float *__restrict__ base) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1196,6 +1209,7 @@ __global__ void nich_c0_sum_kernel(const FeatDev *__restrict__ feats, int nfeat,
   float s = 0.f;
   for (int d = 0; d < nfeat; d++) {
     const FeatDev f = feats[d];
+    if (f.kind == KIND_TABLE && f.binform) s += params[((size_t)kt * region_rows + f.rowoff + 1) * KT + kl];  // t0
     if (f.kind != KIND_NICH) continue;
     s += params[((size_t)kt * region_rows + f.rowoff + 3) * KT + kl];
   }

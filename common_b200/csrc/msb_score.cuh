@@ -247,7 +247,7 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
     FeatS t;
     t.scol = f.scol; t.slowmask = f.slowmask; t.col = f.col;
     t.rowoff = f.rowoff; t.rows = f.rows; t.ncat = f.ncat;
-    t.kind = (uint16_t)f.kind; t.has_slow = (uint16_t)(f.has_slow != 0);
+    t.kind = (uint16_t)((f.kind == KIND_TABLE && f.binform) ? KIND_BIN : f.kind); t.has_slow = (uint16_t)(f.has_slow != 0);
     ftab[i] = t;
   }
   if (tid == 0) {
@@ -314,6 +314,47 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
       };
       if (tail_g == 8) tail_lookup(std::integral_constant<int, 4>{});
       else tail_lookup(std::integral_constant<int, 2>{});
+    } else if (!TABLES_ONLY && t.kind == KIND_BIN) {  // bb in binary form: acc += x (t1 - t0), sum_d t0 is already in base[]
+      VecF<V> df;
+      df.load(chunk + 0 * KT);
+#pragma unroll
+      for (int r4 = 0; r4 < RW / 4; r4++) {
+        const uint4 q = xq[r4];
+        const float xs[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          if constexpr (V % 2 == 0) {
+#pragma unroll
+            for (int h = 0; h < V / 2; h++) {
+              const float2 a = __ffma2_rn(make_float2(xs[e], xs[e]), make_float2(df.v[2 * h], df.v[2 * h + 1]),
+                                          make_float2(acc[r4 * 4 + e][2 * h], acc[r4 * 4 + e][2 * h + 1]));
+              acc[r4 * 4 + e][2 * h] = a.x;
+              acc[r4 * 4 + e][2 * h + 1] = a.y;
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; v++) acc[r4 * 4 + e][v] = fmaf(xs[e], df.v[v], acc[r4 * 4 + e][v]);
+          }
+        }
+      }
+      // masked cells were scored as x = 0: take back the t0 that base[] carries for this feature (rare)
+#pragma unroll
+      for (int j = 0; j < RL; j++) {
+        uint32_t m = slow[j];
+        if (m) {
+          VecF<V> t0;
+          t0.load(chunk + 1 * KT);
+          while (m) {
+            const int rr = j * 32 + __ffs(m) - 1;
+            m &= m - 1;
+#pragma unroll
+            for (int r = 0; r < RW; r++)
+              if (r == rr)
+#pragma unroll
+                for (int v = 0; v < V; v++) acc[r][v] -= t0.v[v];
+          }
+        }
+      }
     } else if (TABLES_ONLY || t.kind != KIND_NICH) {
       const uint32_t chunk_s = smem_u32(chunk);
 #pragma unroll

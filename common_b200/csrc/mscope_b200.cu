@@ -530,6 +530,10 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
       case MSB_FAMILY_DM: f.kind = KIND_DM; f.coltype = COL_U32; st->has_dm = true; break;
     }
   }
+  // bb features that sit next to nich features (the general score kernel runs anyway) are scored in binary form
+  if (st->has_nich && !getenv("MSB_NO_BINFORM"))
+    for (auto &f : st->feats)
+      if (f.family == FAM_BB) f.binform = 1;
   st->SS = sso;
   // default hyperparameters: microscopes/models.pyx:189,211,223,238,264-269
   st->h_hp.assign(hpo, 0.0);
@@ -630,7 +634,7 @@ static void layout_chunks(msb_state *st) {
   uint32_t ro = 0, mx = 0;
   for (auto &f : st->feats) {
     switch (f.kind) {
-      case KIND_TABLE: f.rows = f.ncat + 1; break;
+      case KIND_TABLE: f.rows = f.binform ? 2 : f.ncat + 1; break;
       case KIND_GP: f.rows = f.ncat + 4; break;
       case KIND_NICH: f.rows = 4; break;
       default: f.rows = 0; break;
