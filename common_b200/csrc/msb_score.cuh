@@ -42,6 +42,11 @@ __device__ __forceinline__ void store_vec(float *p, const float *a) {
 }
 
 // compact per-feature record kept in shared memory by the score kernel
+// which kernels keep thread 0 as the producer of the stage ring (see the end of the feature loop)
+#ifndef MSB_FIXED_PRODUCER
+#define MSB_FIXED_PRODUCER(tables_only) (tables_only)
+#endif
+
 struct FeatS {
   const uint32_t *scol;      // score column (u32 chunk-row index, or f32 value)
   const uint32_t *slowmask;  // per 32-row block bitmask of slow-path cells
@@ -253,13 +258,14 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
   if (tid == 0) {
     for (int s = 0; s < S; s++) {
       mbar_init(smem_u32(&bars[s]), 1);
-      mbar_init(smem_u32(&bars[S + s]), NW);
+      if constexpr (MSB_FIXED_PRODUCER(TABLES_ONLY)) mbar_init(smem_u32(&bars[S + s]), NW);
+      else bars[S + s] = 0;  // release counter of the stage (see the end of the feature loop)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // thread 0 only: everything feature d needs -> stage s (row values, slow masks, parameter chunk)
+  // one thread: everything feature d needs -> stage s (row values, slow masks, parameter chunk)
   auto issue = [&](int d, int s) {
     const FeatS t = ftab[d];
     const uint32_t cbytes = t.rows * (uint32_t)(KT * sizeof(float));
@@ -472,12 +478,32 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
         }
       }
     }
-    // release the stage; thread 0 refills it with feature d + S once every warp has released it
+    // Release the stage; the refill with feature d + S is issued once every warp has released it.
     __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&bars[S + s]));
-    if (tid == 0 && d + S < nfeat) {
-      mbar_wait(smem_u32(&bars[S + s]), parity);
-      issue(d + S, s);
+    if constexpr (MSB_FIXED_PRODUCER(TABLES_ONLY)) {
+      // thread 0 is the producer: it waits for the other warps' releases, then issues the copies
+      if (lane == 0) mbar_arrive(smem_u32(&bars[S + s]));
+      if (tid == 0 && d + S < nfeat) {
+        mbar_wait(smem_u32(&bars[S + s]), parity);
+        issue(d + S, s);
+      }
+    } else {
+      // A release counter per stage, and the warp that arrives LAST issues the refill: nobody waits here.  With thread 0
+      // as the fixed producer, warp 0 -- which cannot go on before the slowest warp has finished the feature -- falls
+      // behind by construction; with 8 warps of long arithmetic chains the others then run S features ahead into a
+      // stage that is only just being requested (ncu: 9 % of the samples on the full-barrier spin).  C3 93.7 -> 87.4 ms,
+      // C5 47.5 -> 44.0 ms.  The tables-only kernel keeps the fixed producer: measured, it is the faster of the two there
+      // (C2 1.40 against 1.46 ms).  Also measured and not kept: looking at the counter's return value one feature
+      // later, so that no warp waits for the atomic (C2 1.48, C3 87.3, C5 46.2 ms), and a producer role that rotates
+      // over the warps (C2 1.44, C3 97.1, C5 50.8 ms).
+      if (lane == 0) {
+        unsigned int *rel = reinterpret_cast<unsigned int *>(&bars[S + s]);
+        if (atomicAdd(rel, 1u) == (unsigned)(NW - 1)) {
+          *rel = 0u;  // nobody touches it again before the refill below has landed and been consumed
+          __threadfence_block();
+          if (d + S < nfeat) issue(d + S, s);
+        }
+      }
     }
     if (++s == S) { s = 0; parity ^= 1u; }
   }
