@@ -497,10 +497,14 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
       // later, so that no warp waits for the atomic (C2 1.48, C3 87.3, C5 46.2 ms), and a producer role that rotates
       // over the warps (C2 1.44, C3 97.1, C5 50.8 ms).
       if (lane == 0) {
-        unsigned int *rel = reinterpret_cast<unsigned int *>(&bars[S + s]);
-        if (atomicAdd(rel, 1u) == (unsigned)(NW - 1)) {
-          *rel = 0u;  // nobody touches it again before the refill below has landed and been consumed
-          __threadfence_block();
+        // acq_rel: this warp's reads of the stage (ordered before lane 0 by the __syncwarp above) happen before the
+        // increment, and the last arriver's refill happens after every other warp's increment
+        const uint32_t rel = smem_u32(&bars[S + s]);
+        unsigned int old;
+        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(rel) : "memory");
+        if (old == (unsigned)(NW - 1)) {
+          // nobody touches the counter again before the refill below has landed and been consumed
+          asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(rel), "r"(0u) : "memory");
           if (d + S < nfeat) issue(d + S, s);
         }
       }
