@@ -171,7 +171,7 @@ niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const 
   if (warp < 4) {
     // ===== producers: X tile (fp32) -> tf32 hi / lo halves in core-matrix layout =====
     // The A operand does not depend on the group block: the producers just cycle through this CTA's row
-    // tiles.  Global loads for half-tile h + 1 are issued before waiting for the buffer of half-tile h, so
+    // tiles.  Global loads for half-tile h + 2 are issued before waiting for the buffer of half-tile h, so
     // their latency hides behind the MMAs instead of serialising with them.
     const int n_mine = rt_hi - rt_lo;
     const int ngb_mine = (nGB - g0 + G - 1) / G;
@@ -184,10 +184,11 @@ niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const 
 #pragma unroll
       for (int c = 0; c < 8; c++) v[c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    float4 cur[8], nxt[8];
+    float4 cur[8], nxt[8], nx2[8];  // two half-tiles in flight: one (0.75 us of MMAs) does not cover the HBM latency under load
     if (total_h > 0) load_half(0, cur);
+    if (total_h > 1) load_half(1, nxt);
     for (long long h = 0; h < total_h; h++) {
-      if (h + 1 < total_h) load_half(h + 1, nxt);
+      if (h + 2 < total_h) load_half(h + 2, nx2);
       const int buf = (int)(h & 1);
       if (h >= 2) mbar_wait(smem_u32(&bars[4 + buf]), (uint32_t)(((h >> 1) - 1) & 1));  // MMAs that read this buffer are done
       unsigned char *hi_base = sA + (size_t)buf * 2 * A_HALF_BYTES;
@@ -208,7 +209,7 @@ niw_tc_kernel(const float *__restrict__ X, const float *__restrict__ Bop, const 
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars[2 + buf]));
 #pragma unroll
-      for (int c = 0; c < 8; c++) cur[c] = nxt[c];
+      for (int c = 0; c < 8; c++) { cur[c] = nxt[c]; nxt[c] = nx2[c]; }
     }
   } else if (warp == 8) {
     // ===== MMA issuer (one elected lane) =====
