@@ -1,0 +1,403 @@
+// msb_niw_tc16.cuh -- the NIW Mahalanobis GEMM of msb_niw_tc.cuh on the fp16 tensor-core path (kind::f16, K = 16).
+//
+// Same contraction, same CTA roles, barriers, schedule and epilogue as niw_tc_kernel; what changes is the operand
+// format.  A tf32 operand keeps 11 significand bits, so fp32-class accuracy takes a hi / lo split and three products
+// per k-step (hi*hi + hi*lo + lo*hi).  An fp16 operand keeps 11 bits as well, the same three products give the same
+// 2^-21 -- but kind::f16 runs at twice the tf32 rate and an instruction covers K = 16 instead of 8: half the tensor
+// time and half the operand bytes.  fp16's narrow exponent is handled by exact power-of-two scales:
+//   X'[n][j]      = X[n][j] sx_j,            sx_j   = 2^(9 - e),  max_n |X[n][j]|        in [2^(e-1), 2^e)
+//   W'[k][i][j]   = W[k][i][j] r_ki / sx_j,  r_ki   = 2^(9 - e),  max_j |W[k][i][j]/sx_j| in [2^(e-1), 2^e)
+//   Y'[n][(k,i)]  = sum_j X' W' = r_ki Y,    epilogue: t = Y' (1 / r_ki) - b   (an FFMA2 where the tf32 kernel has an FADD2)
+// so every operand row / column has its largest entry in [256, 512): products accumulate (fp32, TMEM) below 2^24, the
+// hi parts are normal down to 2^-23 of the largest entry and what the subnormal lo parts lose is below 2^-30 of the
+// largest term of the sum.  The scales are recomputed from the rows of the sweep itself (niw_colmax_kernel: one more
+// pass over X, 256 MB at C4), so data uploaded after bind cannot overflow them.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "msb_niw_tc.cuh"
+
+namespace msb {
+
+namespace niwtc16 {
+using niwtc::D;
+using niwtc::GB;
+using niwtc::TM;
+using niwtc::TN;
+using niwtc::THREADS;
+constexpr int A_HALF_BYTES = TM * 32 * 2;   // one k-half (32 k) of one part (hi or lo): 8 KB
+constexpr int NA = 4;                        // A half-tile buffers in the ring (hi + lo each): conversion runs up to two tiles ahead of the MMAs
+constexpr int A_BYTES = NA * 2 * A_HALF_BYTES;   // [buffer][part]: 64 KB
+constexpr int B_PART_BYTES = TN * D * 2;    // 32 KB
+constexpr int B_BYTES = 2 * B_PART_BYTES;   // hi + lo: 64 KB
+constexpr int SB_FLOATS = 2 * TN + 16;      // per accumulator: bias[TN], 1 / r[TN], coef[GB x 4]
+constexpr size_t SMEM_BYTES = (size_t)B_BYTES + A_BYTES + 2 * SB_FLOATS * sizeof(float) + D * sizeof(float) +
+                              16 * sizeof(uint64_t) + 64;
+
+// byte offset of element (row, k) inside one part of an fp16 operand tile with `rowgroups` 8-row groups:
+// [k/8][row/8][row%8][k%8]  (core matrix = 8 rows x 16 bytes, contiguous)
+__device__ __host__ __forceinline__ uint32_t core_off16(uint32_t row, uint32_t k, uint32_t rowgroups) {
+  return (k >> 3) * (rowgroups * 128u) + (row >> 3) * 128u + (row & 7u) * 16u + (k & 7u) * 2u;
+}
+// instruction descriptor, kind::f16: D = F32 (bits 4-5 = 1), A = B = F16 (bits 7-9, 10-12 = 0), K-major both,
+// N >> 3 at [17,23), M >> 4 at [24,29)
+__device__ __forceinline__ constexpr uint32_t idesc_f16(uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the power of two that brings a positive maximum into [256, 512); 1 for an all-zero (or non-finite) row
+__device__ __forceinline__ float pow2_scale(float mx) {
+  if (!(mx > 0.f) || mx > 3.0e38f) return 1.f;
+  int e;
+  frexpf(mx, &e);  // mx = m 2^e, m in [0.5, 1)
+  return ldexpf(1.f, 9 - e);
+}
+// x (already scaled) -> fp16 hi and lo parts, two values at a time
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+}  // namespace niwtc16
+
+// colmax[j] = max over the rows [row_lo, row_hi) of |X[row][j]| as float bits (non-negative floats order like
+// unsigned integers; NaN rows -- masked -- and infinities are skipped).  colmax must be zeroed before.
+__global__ void niw_colmax_kernel(const float *__restrict__ X, size_t row_lo, size_t row_hi, unsigned int *__restrict__ colmax) {
+  constexpr int D = niwtc::D;
+  __shared__ unsigned int sm[D];
+  if (threadIdx.x < D) sm[threadIdx.x] = 0u;
+  __syncthreads();
+  const int j4 = (threadIdx.x & 15) * 4;  // 16 threads cover one row with float4 loads
+  float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (size_t row = row_lo + (size_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); row < row_hi;
+       row += (size_t)gridDim.x * (blockDim.x >> 4)) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(X + row * D + j4));
+    const float a = fabsf(v.x), b = fabsf(v.y), c = fabsf(v.z), d = fabsf(v.w);
+    if (a <= 3.0e38f) m.x = fmaxf(m.x, a);
+    if (b <= 3.0e38f) m.y = fmaxf(m.y, b);
+    if (c <= 3.0e38f) m.z = fmaxf(m.z, c);
+    if (d <= 3.0e38f) m.w = fmaxf(m.w, d);
+  }
+  atomicMax(&sm[j4 + 0], __float_as_uint(m.x));
+  atomicMax(&sm[j4 + 1], __float_as_uint(m.y));
+  atomicMax(&sm[j4 + 2], __float_as_uint(m.z));
+  atomicMax(&sm[j4 + 3], __float_as_uint(m.w));
+  __syncthreads();
+  if (threadIdx.x < D) atomicMax(&colmax[threadIdx.x], sm[threadIdx.x]);
+}
+
+// W[k][i][j] (fp32, row-major per group) -> per group block: [hi | lo] fp16 parts in UMMA layout, scaled; blocks padded
+// with zeros.  rinv[k * D + i] = 1 / r_ki.  sx[j] is derived from colmax[j] here and written out by block 0.
+__global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, const unsigned int *__restrict__ colmax,
+                                    unsigned char *__restrict__ Bop, float *__restrict__ rinv, float *__restrict__ sx_out) {
+  using namespace niwtc16;
+  __shared__ float s_isx[D];   // 1 / sx_j
+  __shared__ float s_r[TN];    // r of operand row (g, i)
+  const int gb = blockIdx.x;
+  if (threadIdx.x < D) {
+    const float sx = pow2_scale(__uint_as_float(colmax[threadIdx.x]));
+    s_isx[threadIdx.x] = 1.f / sx;
+    if (gb == 0) sx_out[threadIdx.x] = sx;
+  }
+  __syncthreads();
+  for (int nn = threadIdx.x; nn < TN; nn += blockDim.x) {  // nn = g * D + i
+    const int g = nn / D, i = nn % D, k = gb * GB + g;
+    float mx = 0.f;
+    if (k < ncols)
+      for (int j = 0; j < D; j++) mx = fmaxf(mx, fabsf(W[((size_t)k * D + i) * D + j] * s_isx[j]));
+    const float r = pow2_scale(mx);
+    s_r[nn] = r;
+    rinv[(size_t)gb * TN + nn] = 1.f / r;
+  }
+  __syncthreads();
+  __half *dst = reinterpret_cast<__half *>(Bop + (size_t)gb * B_BYTES);
+  for (int e = threadIdx.x; e < TN * D; e += blockDim.x) {
+    const int nn = e / D, j = e % D;
+    const int g = nn / D, i = nn % D;
+    const int k = gb * GB + g;
+    const float w = k < ncols ? W[((size_t)k * D + i) * D + j] * s_isx[j] * s_r[nn] : 0.f;   // exact: powers of two
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+    // operand row n' = (i / 8) * 32 + g * 8 + i % 8, as in niw_pack_b_kernel (the epilogue's accumulator order)
+    const uint32_t off = core_off16((uint32_t)((i >> 3) * (GB * 8) + g * 8 + (i & 7)), (uint32_t)j, TN / 8) / 2;
+    dst[off] = hi;
+    dst[B_PART_BYTES / 2 + off] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(niwtc::THREADS, 1)
+niw_tc16_kernel(const float *__restrict__ X, const unsigned char *__restrict__ Bop, const float *__restrict__ rinv,
+                const float *__restrict__ sxg, const float *__restrict__ bias, const float *__restrict__ coef, int ncols,
+                float *__restrict__ scores, size_t ld, size_t row_lo, size_t row_hi, int num_gb_lanes,
+                const float *__restrict__ base, int blocked) {
+  using namespace niwtc16;
+  extern __shared__ __align__(1024) unsigned char niw_smem[];
+  unsigned char *sm = niw_smem;
+  unsigned char *sB = sm;                      // [part][...]
+  unsigned char *sA = sm + B_BYTES;            // [half][part][...]
+  float *sBias = reinterpret_cast<float *>(sA + A_BYTES);            // [2][SB_FLOATS]: bias, 1 / r, coef (GB x 4)
+  float *sSx = sBias + 2 * SB_FLOATS;                                 // [D]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sSx + D);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 15);
+  // barriers: 0 b_full, 1 b_free, A_FULL.. a_full[NA], A_EMPTY.. a_empty[NA], ACC_FULL.. acc_full[2], ACC_EMPTY.. acc_empty[2]
+  constexpr int A_FULL = 2, A_EMPTY = 2 + NA, ACC_FULL = 2 + 2 * NA, ACC_EMPTY = 4 + 2 * NA;
+  static_assert(ACC_EMPTY + 2 <= 15, "barrier slots");
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t nrows = row_hi - row_lo;
+  const int nRT = (int)((nrows + TM - 1) / TM);
+  const int nGB = (ncols + GB - 1) / GB;
+  const int G = (int)num_gb_lanes;
+  const int g0 = (int)blockIdx.x % G, part = (int)blockIdx.x / G;
+  const int P = ((int)gridDim.x - g0 + G - 1) / G;
+  const int rt_lo = (int)((long long)nRT * part / P), rt_hi = (int)((long long)nRT * (part + 1) / P);
+
+  if (tid < D) sSx[tid] = sxg[tid];
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    for (int i = 0; i < NA; i++) {
+      mbar_init(smem_u32(&bars[A_FULL + i]), 4);    // a_full: one arrive per producer warp
+      mbar_init(smem_u32(&bars[A_EMPTY + i]), 1);   // a_empty: tcgen05.commit
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(smem_u32(&bars[ACC_FULL + i]), 1);  // acc_full: tcgen05.commit
+      mbar_init(smem_u32(&bars[ACC_EMPTY + i]), 4); // acc_empty: one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {  // TMEM: all 512 columns (2 accumulators x 256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // ===== producers: X tile (fp32) -> scaled fp16 hi / lo halves in core-matrix layout =====
+    const int n_mine = rt_hi - rt_lo;
+    const int ngb_mine = (nGB - g0 + G - 1) / G;
+    const long long total_h = 2ll * n_mine * ngb_mine;
+    auto load_half = [&](long long h, float4 (&v)[8]) {
+      const int rt = rt_lo + (int)((h >> 1) % n_mine), half = (int)(h & 1);
+      const size_t row = row_lo + (size_t)rt * TM + tid;  // tid in [0,128): one row per thread
+      const float4 *src = reinterpret_cast<const float4 *>(X + row * D) + half * 8;
+      const bool ok = row < row_hi;
+#pragma unroll
+      for (int c = 0; c < 8; c++) v[c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 cur[8], nxt[8], nx2[8];
+    if (total_h > 0) load_half(0, cur);
+    if (total_h > 1) load_half(1, nxt);
+    for (long long h = 0; h < total_h; h++) {
+      if (h + 2 < total_h) load_half(h + 2, nx2);
+      const int buf = (int)(h % NA), half = (int)(h & 1);
+      if (h >= NA) mbar_wait(smem_u32(&bars[A_EMPTY + buf]), (uint32_t)(((h / NA) - 1) & 1));  // MMAs that read this buffer are done
+      unsigned char *hi_base = sA + (size_t)buf * 2 * A_HALF_BYTES;
+      unsigned char *lo_base = hi_base + A_HALF_BYTES;
+      const float *sx = sSx + half * 32;
+#pragma unroll
+      for (int c8 = 0; c8 < 4; c8++) {  // 4 chunks of 8 k: one 16-byte core-matrix row each
+        const float4 a = cur[2 * c8], b = cur[2 * c8 + 1];
+        const float4 s0 = *reinterpret_cast<const float4 *>(sx + c8 * 8), s1 = *reinterpret_cast<const float4 *>(sx + c8 * 8 + 4);
+        uint4 vh, vl;
+        split2(a.x * s0.x, a.y * s0.y, vh.x, vl.x);
+        split2(a.z * s0.z, a.w * s0.w, vh.y, vl.y);
+        split2(b.x * s1.x, b.y * s1.y, vh.z, vl.z);
+        split2(b.z * s1.z, b.w * s1.w, vh.w, vl.w);
+        const uint32_t off = core_off16((uint32_t)tid, (uint32_t)c8 * 8, TM / 8);
+        *reinterpret_cast<uint4 *>(hi_base + off) = vh;
+        *reinterpret_cast<uint4 *>(lo_base + off) = vl;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[A_FULL + buf]));
+#pragma unroll
+      for (int c = 0; c < 8; c++) { cur[c] = nxt[c]; nxt[c] = nx2[c]; }
+    }
+  } else if (warp == 8) {
+    // ===== MMA issuer (one elected lane) =====
+    if (lane == 0) {
+      long long h = 0, t = 0;
+      int cur_gb = -1;
+      uint32_t b_loads = 0;
+      const uint32_t idesc = idesc_f16(TN);
+      for (int gb = g0; gb < nGB; gb += G)
+      for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
+        if (gb != cur_gb) {  // (re)load the resident B operand
+          if (cur_gb >= 0) {
+            niwtc::mma_commit(smem_u32(&bars[1]));
+            mbar_wait(smem_u32(&bars[1]), (b_loads - 1) & 1u);  // every MMA that read the old B has completed
+          }
+          mbar_expect_tx(smem_u32(&bars[0]), B_BYTES);
+          const unsigned char *gsrc = Bop + (size_t)gb * B_BYTES;
+          for (int c = 0; c < 4; c++)
+            bulk_g2s(smem_u32(sB + (size_t)c * (B_BYTES / 4)), gsrc + (size_t)c * (B_BYTES / 4), B_BYTES / 4, smem_u32(&bars[0]));
+          mbar_wait(smem_u32(&bars[0]), b_loads & 1u);
+          b_loads++;
+          cur_gb = gb;
+        }
+        const int acc = (int)(t & 1);
+        if (t >= 2) mbar_wait(smem_u32(&bars[ACC_EMPTY + acc]), (uint32_t)(((t >> 1) - 1) & 1));  // epilogue drained this accumulator
+        const uint32_t d_tmem = tmem + (uint32_t)acc * TN;
+        for (int half = 0; half < 2; half++, h++) {
+          const int buf = (int)(h % NA);
+          mbar_wait(smem_u32(&bars[A_FULL + buf]), (uint32_t)((h / NA) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(sA + (size_t)buf * 2 * A_HALF_BYTES), a_lo = a_hi + A_HALF_BYTES;
+          const uint32_t b_hi = smem_u32(sB) + (uint32_t)half * (32 / 8) * (TN / 8) * 128u, b_lo = b_hi + B_PART_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 2; ks++) {  // K = 16 per instruction: 2 core-matrix columns
+            const uint32_t ao = (uint32_t)ks * 2u * (TM / 8) * 128u;
+            const uint32_t bo = (uint32_t)ks * 2u * (TN / 8) * 128u;
+            const uint64_t dah = niwtc::smem_desc(a_hi + ao, (TM / 8) * 128u, 128u), dal = niwtc::smem_desc(a_lo + ao, (TM / 8) * 128u, 128u);
+            const uint64_t dbh = niwtc::smem_desc(b_hi + bo, (TN / 8) * 128u, 128u), dbl = niwtc::smem_desc(b_lo + bo, (TN / 8) * 128u, 128u);
+            mma_f16(d_tmem, dah, dbh, idesc, (half | ks) ? 1u : 0u);
+            mma_f16(d_tmem, dah, dbl, idesc, 1u);
+            mma_f16(d_tmem, dal, dbh, idesc, 1u);
+          }
+          niwtc::mma_commit(smem_u32(&bars[A_EMPTY + buf]));            // A half-buffer free once these MMAs complete
+          if (half == 1) niwtc::mma_commit(smem_u32(&bars[ACC_FULL + acc]));  // accumulator ready for the epilogue
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps 4..7: TMEM lanes 32*(warp%4) .. +31 =====
+    const int ew = warp & 3;
+    const int etid = tid - 128;  // 0..127
+    long long t = 0;
+    int staged_gb = -1;
+    float *sb = sBias;
+    float *sr = sb + TN, *sc = sb + 2 * TN;
+    for (int gb = g0; gb < nGB; gb += G)
+    for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
+      const int acc = (int)(t & 1);
+      // this group block's bias, 1 / r and coefficients: staged when the block changes, not per tile -- the global
+      // loads and the two barriers around them sat on the epilogue's critical path of every tile
+      if (gb != staged_gb) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // nobody still reads the previous block's values
+        for (int i = etid; i < SB_FLOATS; i += 128) {
+          float v = 0.f;
+          if (i < TN) { const int k = gb * GB + i / D; if (k < ncols) v = bias[(size_t)k * D + (i % D)]; }
+          else if (i < 2 * TN) v = rinv[(size_t)gb * TN + (i - TN)];
+          else { const int k = gb * GB + (i - 2 * TN) / 4; if (k < ncols) v = coef[(size_t)k * 4 + ((i - 2 * TN) & 3)]; }
+          sb[i] = v;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        staged_gb = gb;
+      }
+      const size_t row = row_lo + (size_t)rt * TM + ew * 32 + lane;
+      float4 *dst = reinterpret_cast<float4 *>(scores + (row - row_lo) * ld + (size_t)gb * GB);
+      float *dstb = scores + (((size_t)rt * (TM / 32) + ew) * ld + (size_t)gb * GB) * 32 + lane;
+      float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < row_hi) {
+        if (base) old = __ldg(reinterpret_cast<const float4 *>(base + (size_t)gb * GB));
+        else if (blocked & 1) old = make_float4(dstb[0], dstb[32], dstb[64], dstb[96]);
+        else old = *dst;
+      }
+      mbar_wait(smem_u32(&bars[ACC_FULL + acc]), (uint32_t)((t >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float q[GB];
+      {
+        float2 q2[GB];
+#pragma unroll
+        for (int g = 0; g < GB; g++) q2[g] = make_float2(0.f, 0.f);
+        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN);
+        uint32_t r[2][32];
+        niwtc::tmem_ld32_issue(tbase, r[0]);
+#pragma unroll
+        for (int ib = 0; ib < D / 8; ib++) {
+          niwtc::tmem_ld_wait();
+          if (ib + 1 < D / 8) niwtc::tmem_ld32_issue(tbase + (uint32_t)(ib + 1) * 32u, r[(ib + 1) & 1]);
+#pragma unroll
+          for (int g = 0; g < GB; g++) {
+            const float4 b0 = *reinterpret_cast<const float4 *>(sb + g * D + ib * 8);
+            const float4 b1 = *reinterpret_cast<const float4 *>(sb + g * D + ib * 8 + 4);
+            const float4 r0 = *reinterpret_cast<const float4 *>(sr + g * D + ib * 8);
+            const float4 r1 = *reinterpret_cast<const float4 *>(sr + g * D + ib * 8 + 4);
+            const uint32_t *v = r[ib & 1] + g * 8;
+            float2 y;
+            y = __ffma2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(r0.x, r0.y), make_float2(-b0.x, -b0.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
+            y = __ffma2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(r0.z, r0.w), make_float2(-b0.z, -b0.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
+            y = __ffma2_rn(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(r1.x, r1.y), make_float2(-b1.x, -b1.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
+            y = __ffma2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(r1.z, r1.w), make_float2(-b1.z, -b1.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < GB; g++) q[g] = q2[g].x + q2[g].y;
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
+      if (row < row_hi) {
+        float o[GB] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+        for (int g = 0; g < GB; g++) {
+          const int k = gb * GB + g;
+          if (k < ncols && q[g] == q[g]) {  // NaN = masked row: contributes nothing
+            const float c0 = sc[g * 4 + 0], c1 = sc[g * 4 + 1], idof = sc[g * 4 + 2];
+            o[g] += c0 + c1 * log1pf(q[g] * idof);
+          }
+        }
+        if (blocked & 1) {
+#pragma unroll
+          for (int g = 0; g < GB; g++) dstb[g * 32] = o[g];
+        } else {
+          *dst = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+static inline int niw_tc16_init(size_t smem_optin, std::string &err) {
+  if (niwtc16::SMEM_BYTES > smem_optin) return MSB_OK;
+  cudaError_t e = cudaFuncSetAttribute(niw_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)niwtc16::SMEM_BYTES);
+  if (e != cudaSuccess) { err = std::string("niw_tc16_init: ") + cudaGetErrorString(e); return MSB_ERR_CUDA; }
+  return MSB_OK;
+}
+// operand scratch of the fp16 path inside the buffer niw_tc_operand_bytes() sizes (the tf32 operands are twice as big):
+// [colmax: D u32][sx: D f32][rinv: nGB x TN f32][B blocks: nGB x B_BYTES]
+static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, const float *X, const float *W, const float *bias,
+                                 const float *coef, float *Bop, size_t ncols, float *scores, size_t ld, size_t row_lo,
+                                 size_t row_hi, int sm_count, const float *base, bool blocked, std::string &err) {
+  using namespace niwtc16;
+  const int nGB = (int)((ncols + GB - 1) / GB);
+  unsigned int *colmax = reinterpret_cast<unsigned int *>(Bop);
+  float *sx = Bop + D;
+  float *rinv = Bop + 2 * D;
+  unsigned char *Bblk = reinterpret_cast<unsigned char *>(Bop) + (2 * D + (size_t)nGB * TN) * sizeof(float);  // 512 + nGB KB: 16-byte aligned
+  cudaMemsetAsync(colmax, 0, D * sizeof(unsigned int), stream);
+  const size_t nrows = row_hi - row_lo;
+  const unsigned cm_grid = (unsigned)std::min<size_t>((nrows + 15) / 16, (size_t)sm_count * 8);
+  niw_colmax_kernel<<<cm_grid, 256, 0, stream>>>(X, row_lo, row_hi, colmax);
+  niw_pack_b16_kernel<<<nGB, 256, 0, stream>>>(W, (int)ncols, colmax, Bblk, rinv, sx);
+  (*launches) += 2;
+  const long long nRT = (long long)((nrows + TM - 1) / TM);
+  const int G = std::min(nGB, sm_count);
+  const int grid = (int)std::max<long long>(G, std::min<long long>(sm_count, (long long)G * nRT));
+  niw_tc16_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(X, Bblk, rinv, sx, bias, coef, (int)ncols, scores, ld, row_lo, row_hi, G,
+                                                         base, blocked ? 1 : 0);
+  (*launches)++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { err = std::string("niw_tc16_kernel launch: ") + cudaGetErrorString(e); return MSB_ERR_CUDA; }
+  return MSB_OK;
+}
+
+}  // namespace msb

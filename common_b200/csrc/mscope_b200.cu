@@ -16,6 +16,7 @@
 #include "msb_kernels.cuh"
 #include "msb_score.cuh"
 #include "msb_niw_tc.cuh"
+#include "msb_niw_tc16.cuh"
 #include "msb_draw.cuh"
 
 using namespace msb;
@@ -237,6 +238,7 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin - 1024));  // it also has a few bytes of static shared memory
   CU_TRY(opt_in_smem(niw_score_simt_kernel, c->smem_optin - 1024));
   MSB_TRY(niw_tc_init(c->smem_optin, g_last_error));
+  MSB_TRY(niw_tc16_init(c->smem_optin, g_last_error));
   *out = c;
   return MSB_OK;
 }
@@ -1376,6 +1378,12 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
       LAUNCH(ctx, fill_rows_kernel, cdiv(nrows * st->ld, 256), 256, 0, scores, st->ld, st->d_base, nrows);
       need_init = false;
     }
+    if (tc_ok && !getenv("MSB_NIW_TF32") && row_hi > row_lo) {  // fp16 operands (msb_niw_tc16.cuh): the default
+      MSB_TRY(niw_tc16_score(ctx->stream, &ctx->launches, (const float *)f.scol, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
+                             st->d_niwB[d], K, scores, st->ld, row_lo, row_hi, ctx->sm_count, need_init ? st->d_base : nullptr,
+                             blocked, g_last_error));
+      done = true;
+    } else
     MSB_TRY(niw_tc_score(ctx->stream, &ctx->launches, (const float *)f.scol, f.dim, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
                          st->d_niwB[d], K, scores, st->ld, row_lo, row_hi, ctx->sm_count, need_init ? st->d_base : nullptr,
                          blocked, &done, g_last_error));
