@@ -24,7 +24,7 @@ using niwtc::D;
 using niwtc::GB;
 using niwtc::TM;
 using niwtc::TN;
-using niwtc::THREADS;
+constexpr int THREADS = 13 * 32;            // warps 0-3 producers, 4-7 and 9-12 epilogue, 8 MMA issuer
 constexpr int A_HALF_BYTES = TM * 32 * 2;   // one k-half (32 k) of one part (hi or lo): 8 KB
 constexpr int NA = 4;                        // A half-tile buffers in the ring (hi + lo each): conversion runs up to two tiles ahead of the MMAs
 constexpr int A_BYTES = NA * 2 * A_HALF_BYTES;   // [buffer][part]: 64 KB
@@ -65,6 +65,15 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
   const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
   hi = *reinterpret_cast<const uint32_t *>(&h);
   lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 }  // namespace niwtc16
 
@@ -133,7 +142,7 @@ __global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, cons
   }
 }
 
-__global__ void __launch_bounds__(niwtc::THREADS, 1)
+__global__ void __launch_bounds__(niwtc16::THREADS, 1)
 niw_tc16_kernel(const float *__restrict__ X, const unsigned char *__restrict__ Bop, const float *__restrict__ rinv,
                 const float *__restrict__ sxg, const float *__restrict__ bias, const float *__restrict__ coef, int ncols,
                 float *__restrict__ scores, size_t ld, size_t row_lo, size_t row_hi, int num_gb_lanes,
@@ -169,7 +178,7 @@ niw_tc16_kernel(const float *__restrict__ X, const unsigned char *__restrict__ B
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(smem_u32(&bars[ACC_FULL + i]), 1);  // acc_full: tcgen05.commit
-      mbar_init(smem_u32(&bars[ACC_EMPTY + i]), 4); // acc_empty: one arrive per epilogue warp
+      mbar_init(smem_u32(&bars[ACC_EMPTY + i]), 8); // acc_empty: one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -272,9 +281,13 @@ niw_tc16_kernel(const float *__restrict__ X, const unsigned char *__restrict__ B
     }
     __syncwarp();
   } else {
-    // ===== epilogue warps 4..7: TMEM lanes 32*(warp%4) .. +31 =====
+    // ===== epilogue: warps 4..7 (groups 0, 1 of the block) and 9..12 (groups 2, 3); TMEM lanes 32 * (warp % 4) .. + 31 =====
+    // Two warps per lane quadrant, each reading 16 of the 32 columns of an output block: the epilogue (256 outputs per
+    // row and tile, two packed operations and half a shared-memory load each) was the critical path with four warps.
+    constexpr int HG = GB / 2;  // groups per epilogue warp
     const int ew = warp & 3;
-    const int etid = tid - 128;  // 0..127
+    const int cg = warp >= 9 ? 1 : 0;
+    const int etid = cg * 128 + ew * 32 + lane;  // 0..255
     long long t = 0;
     int staged_gb = -1;
     float *sb = sBias;
@@ -285,75 +298,83 @@ niw_tc16_kernel(const float *__restrict__ X, const unsigned char *__restrict__ B
       // this group block's bias, 1 / r and coefficients: staged when the block changes, not per tile -- the global
       // loads and the two barriers around them sat on the epilogue's critical path of every tile
       if (gb != staged_gb) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // nobody still reads the previous block's values
-        for (int i = etid; i < SB_FLOATS; i += 128) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // nobody still reads the previous block's values
+        for (int i = etid; i < SB_FLOATS; i += 256) {
           float v = 0.f;
           if (i < TN) { const int k = gb * GB + i / D; if (k < ncols) v = bias[(size_t)k * D + (i % D)]; }
           else if (i < 2 * TN) v = rinv[(size_t)gb * TN + (i - TN)];
           else { const int k = gb * GB + (i - 2 * TN) / 4; if (k < ncols) v = coef[(size_t)k * 4 + ((i - 2 * TN) & 3)]; }
           sb[i] = v;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         staged_gb = gb;
       }
       const size_t row = row_lo + (size_t)rt * TM + ew * 32 + lane;
-      float4 *dst = reinterpret_cast<float4 *>(scores + (row - row_lo) * ld + (size_t)gb * GB);
-      float *dstb = scores + (((size_t)rt * (TM / 32) + ew) * ld + (size_t)gb * GB) * 32 + lane;
-      float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+      float2 *dst = reinterpret_cast<float2 *>(scores + (row - row_lo) * ld + (size_t)gb * GB + cg * HG);
+      float *dstb = scores + (((size_t)rt * (TM / 32) + ew) * ld + (size_t)gb * GB + cg * HG) * 32 + lane;
+      float2 old = make_float2(0.f, 0.f);
       if (row < row_hi) {
-        if (base) old = __ldg(reinterpret_cast<const float4 *>(base + (size_t)gb * GB));
-        else if (blocked & 1) old = make_float4(dstb[0], dstb[32], dstb[64], dstb[96]);
+        if (base) old = __ldg(reinterpret_cast<const float2 *>(base + (size_t)gb * GB + cg * HG));
+        else if (blocked & 1) old = make_float2(dstb[0], dstb[32]);
         else old = *dst;
       }
       mbar_wait(smem_u32(&bars[ACC_FULL + acc]), (uint32_t)((t >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float q[GB];
+      float q[HG];
       {
-        float2 q2[GB];
+        float2 q2[HG];
 #pragma unroll
-        for (int g = 0; g < GB; g++) q2[g] = make_float2(0.f, 0.f);
-        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN);
-        uint32_t r[2][32];
-        niwtc::tmem_ld32_issue(tbase, r[0]);
+        for (int g = 0; g < HG; g++) q2[g] = make_float2(0.f, 0.f);
+        // accumulator column n' = (i / 8) * 32 + g * 8 + i % 8: this warp's groups are the 16 columns from cg * 16
+        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN) + (uint32_t)(cg * 16);
+        // four 16-column loads in flight at a time: with one, the TMEM round trip (not the arithmetic) set the pace
+        uint32_t r[4][16];
 #pragma unroll
-        for (int ib = 0; ib < D / 8; ib++) {
+        for (int ib0 = 0; ib0 < D / 8; ib0 += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; u++) tmem_ld16_issue(tbase + (uint32_t)(ib0 + u) * 32u, r[u]);
           niwtc::tmem_ld_wait();
-          if (ib + 1 < D / 8) niwtc::tmem_ld32_issue(tbase + (uint32_t)(ib + 1) * 32u, r[(ib + 1) & 1]);
 #pragma unroll
-          for (int g = 0; g < GB; g++) {
-            const float4 b0 = *reinterpret_cast<const float4 *>(sb + g * D + ib * 8);
-            const float4 b1 = *reinterpret_cast<const float4 *>(sb + g * D + ib * 8 + 4);
-            const float4 r0 = *reinterpret_cast<const float4 *>(sr + g * D + ib * 8);
-            const float4 r1 = *reinterpret_cast<const float4 *>(sr + g * D + ib * 8 + 4);
-            const uint32_t *v = r[ib & 1] + g * 8;
-            float2 y;
-            y = __ffma2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(r0.x, r0.y), make_float2(-b0.x, -b0.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
-            y = __ffma2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(r0.z, r0.w), make_float2(-b0.z, -b0.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
-            y = __ffma2_rn(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(r1.x, r1.y), make_float2(-b1.x, -b1.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
-            y = __ffma2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(r1.z, r1.w), make_float2(-b1.z, -b1.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
+          for (int u = 0; u < 4; u++) {
+            const int ib = ib0 + u;
+#pragma unroll
+            for (int g = 0; g < HG; g++) {
+              const int gg = cg * HG + g;
+              const float4 b0 = *reinterpret_cast<const float4 *>(sb + gg * D + ib * 8);
+              const float4 b1 = *reinterpret_cast<const float4 *>(sb + gg * D + ib * 8 + 4);
+              const float4 r0 = *reinterpret_cast<const float4 *>(sr + gg * D + ib * 8);
+              const float4 r1 = *reinterpret_cast<const float4 *>(sr + gg * D + ib * 8 + 4);
+              const uint32_t *v = r[u] + g * 8;
+              float2 y;
+              y = __ffma2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(r0.x, r0.y), make_float2(-b0.x, -b0.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
+              y = __ffma2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(r0.z, r0.w), make_float2(-b0.z, -b0.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
+              y = __ffma2_rn(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(r1.x, r1.y), make_float2(-b1.x, -b1.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
+              y = __ffma2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(r1.z, r1.w), make_float2(-b1.z, -b1.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
+            }
           }
         }
 #pragma unroll
-        for (int g = 0; g < GB; g++) q[g] = q2[g].x + q2[g].y;
+        for (int g = 0; g < HG; g++) q[g] = q2[g].x + q2[g].y;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
       if (row < row_hi) {
-        float o[GB] = {old.x, old.y, old.z, old.w};
+        float o[HG] = {old.x, old.y};
 #pragma unroll
-        for (int g = 0; g < GB; g++) {
-          const int k = gb * GB + g;
+        for (int g = 0; g < HG; g++) {
+          const int gg = cg * HG + g;
+          const int k = gb * GB + gg;
           if (k < ncols && q[g] == q[g]) {  // NaN = masked row: contributes nothing
-            const float c0 = sc[g * 4 + 0], c1 = sc[g * 4 + 1], idof = sc[g * 4 + 2];
+            const float c0 = sc[gg * 4 + 0], c1 = sc[gg * 4 + 1], idof = sc[gg * 4 + 2];
             o[g] += c0 + c1 * log1pf(q[g] * idof);
           }
         }
         if (blocked & 1) {
 #pragma unroll
-          for (int g = 0; g < GB; g++) dstb[g * 32] = o[g];
+          for (int g = 0; g < HG; g++) dstb[g * 32] = o[g];
         } else {
-          *dst = make_float4(o[0], o[1], o[2], o[3]);
+          *dst = make_float2(o[0], o[1]);
         }
       }
     }
