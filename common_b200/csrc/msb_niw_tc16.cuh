@@ -6,9 +6,9 @@
 // 2^-21 -- but kind::f16 runs at twice the tf32 rate and an instruction covers K = 16 instead of 8: half the tensor
 // time and half the operand bytes.  fp16's narrow exponent is handled by exact power-of-two scales:
 //   X'[n][j]      = X[n][j] sx_j,            sx_j   = 2^(9 - e),  max_n |X[n][j]|        in [2^(e-1), 2^e)
-//   W'[k][i][j]   = W[k][i][j] r_ki / sx_j,  r_ki   = 2^(9 - e),  max_j |W[k][i][j]/sx_j| in [2^(e-1), 2^e)
-//   Y'[n][(k,i)]  = sum_j X' W' = r_ki Y,    epilogue: t = Y' (1 / r_ki) - b   (an FFMA2 where the tf32 kernel has an FADD2)
-// so every operand row / column has its largest entry in [256, 512): products accumulate (fp32, TMEM) below 2^24, the
+//   W'[k][i][j]   = W[k][i][j] r_k / sx_j,   r_k    = 2^(9 - e),  max_ij |W[k][i][j]/sx_j| in [2^(e-1), 2^e)
+//   Y'[n][(k,i)]  = sum_j X' W' = r_k Y,     epilogue: t = Y' - r_k b, q' = sum_i t^2 = r_k^2 q  (1 / r_k^2 folded into 1 / dof)
+// so every column of X' and every W'_k has its largest entry in [256, 512): products accumulate (fp32, TMEM) below 2^24, the
 // hi parts are normal down to 2^-23 of the largest entry and what the subnormal lo parts lose is below 2^-30 of the
 // largest term of the sum.  The scales are recomputed from the rows of the sweep itself (niw_colmax_kernel: one more
 // pass over X, 256 MB at C4), so data uploaded after bind cannot overflow them.
@@ -30,7 +30,7 @@ constexpr int NA = 4;                        // A half-tile buffers in the ring 
 constexpr int A_BYTES = NA * 2 * A_HALF_BYTES;   // [buffer][part]: 64 KB
 constexpr int B_PART_BYTES = TN * D * 2;    // 32 KB
 constexpr int B_BYTES = 2 * B_PART_BYTES;   // hi + lo: 64 KB
-constexpr int SB_FLOATS = 2 * TN + 16;      // per accumulator: bias[TN], 1 / r[TN], coef[GB x 4]
+constexpr int SB_FLOATS = TN + 16;          // bias r_k [TN], coef[GB x 4] (c0, c1, 1 / (dof r_k^2), -)
 constexpr size_t SMEM_BYTES = (size_t)B_BYTES + A_BYTES + 2 * SB_FLOATS * sizeof(float) + D * sizeof(float) +
                               16 * sizeof(uint64_t) + 64;
 
@@ -104,12 +104,12 @@ __global__ void niw_colmax_kernel(const float *__restrict__ X, size_t row_lo, si
 }
 
 // W[k][i][j] (fp32, row-major per group) -> per group block: [hi | lo] fp16 parts in UMMA layout, scaled; blocks padded
-// with zeros.  rinv[k * D + i] = 1 / r_ki.  sx[j] is derived from colmax[j] here and written out by block 0.
+// with zeros.  rinv[2 k] = r_k, rinv[2 k + 1] = 1 / r_k^2.  sx[j] is derived from colmax[j] here and written out by block 0.
 __global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, const unsigned int *__restrict__ colmax,
                                     unsigned char *__restrict__ Bop, float *__restrict__ rinv, float *__restrict__ sx_out) {
   using namespace niwtc16;
   __shared__ float s_isx[D];   // 1 / sx_j
-  __shared__ float s_r[TN];    // r of operand row (g, i)
+  __shared__ float s_r[2 * GB];  // per group: max |W / sx| (as ordered bits), then r_k
   const int gb = blockIdx.x;
   if (threadIdx.x < D) {
     const float sx = pow2_scale(__uint_as_float(colmax[threadIdx.x]));
@@ -117,14 +117,24 @@ __global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, cons
     if (gb == 0) sx_out[threadIdx.x] = sx;
   }
   __syncthreads();
+  // one scale per group: r_k brings max_ij |W[k][i][j] / sx_j| into [256, 512).  (A scale per output row would keep a
+  // few more bits for rows much smaller than the group's largest, but costs the epilogue a second shared-memory
+  // operand per output -- and the kernel is bound by shared-memory traffic.)
+  if (threadIdx.x < GB) s_r[threadIdx.x] = 0.f;
+  __syncthreads();
   for (int nn = threadIdx.x; nn < TN; nn += blockDim.x) {  // nn = g * D + i
     const int g = nn / D, i = nn % D, k = gb * GB + g;
     float mx = 0.f;
     if (k < ncols)
       for (int j = 0; j < D; j++) mx = fmaxf(mx, fabsf(W[((size_t)k * D + i) * D + j] * s_isx[j]));
-    const float r = pow2_scale(mx);
-    s_r[nn] = r;
-    rinv[(size_t)gb * TN + nn] = 1.f / r;
+    atomicMax(reinterpret_cast<unsigned int *>(&s_r[g]), __float_as_uint(mx));
+  }
+  __syncthreads();
+  if (threadIdx.x < GB) {
+    const float r = pow2_scale(s_r[threadIdx.x]);
+    rinv[((size_t)gb * GB + threadIdx.x) * 2 + 0] = r;
+    rinv[((size_t)gb * GB + threadIdx.x) * 2 + 1] = (1.f / r) * (1.f / r);
+    s_r[GB + threadIdx.x] = r;
   }
   __syncthreads();
   __half *dst = reinterpret_cast<__half *>(Bop + (size_t)gb * B_BYTES);
@@ -132,7 +142,7 @@ __global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, cons
     const int nn = e / D, j = e % D;
     const int g = nn / D, i = nn % D;
     const int k = gb * GB + g;
-    const float w = k < ncols ? W[((size_t)k * D + i) * D + j] * s_isx[j] * s_r[nn] : 0.f;   // exact: powers of two
+    const float w = k < ncols ? W[((size_t)k * D + i) * D + j] * s_isx[j] * s_r[GB + g] : 0.f;   // exact: powers of two
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
     // operand row n' = (i / 8) * 32 + g * 8 + i % 8, as in niw_pack_b_kernel (the epilogue's accumulator order)
@@ -291,19 +301,23 @@ niw_tc16_kernel(const float *__restrict__ X, const unsigned char *__restrict__ B
     long long t = 0;
     int staged_gb = -1;
     float *sb = sBias;
-    float *sr = sb + TN, *sc = sb + 2 * TN;
+    float *sc = sb + TN;
     for (int gb = g0; gb < nGB; gb += G)
     for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
       const int acc = (int)(t & 1);
-      // this group block's bias, 1 / r and coefficients: staged when the block changes, not per tile -- the global
+      // this group block's bias and coefficients: staged when the block changes, not per tile -- the global
       // loads and the two barriers around them sat on the epilogue's critical path of every tile
       if (gb != staged_gb) {
         asm volatile("bar.sync 1, 256;" ::: "memory");  // nobody still reads the previous block's values
         for (int i = etid; i < SB_FLOATS; i += 256) {
           float v = 0.f;
-          if (i < TN) { const int k = gb * GB + i / D; if (k < ncols) v = bias[(size_t)k * D + (i % D)]; }
-          else if (i < 2 * TN) v = rinv[(size_t)gb * TN + (i - TN)];
-          else { const int k = gb * GB + (i - 2 * TN) / 4; if (k < ncols) v = coef[(size_t)k * 4 + ((i - 2 * TN) & 3)]; }
+          if (i < TN) {  // bias' = b r_k
+            const int k = gb * GB + i / D;
+            if (k < ncols) v = bias[(size_t)k * D + (i % D)] * rinv[(size_t)k * 2];
+          } else {       // c0, c1, 1 / (dof r_k^2): q' = r_k^2 q
+            const int k = gb * GB + (i - TN) / 4, c = (i - TN) & 3;
+            if (k < ncols) v = coef[(size_t)k * 4 + c] * (c == 2 ? rinv[(size_t)k * 2 + 1] : 1.f);
+          }
           sb[i] = v;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -342,14 +356,12 @@ niw_tc16_kernel(const float *__restrict__ X, const unsigned char *__restrict__ B
               const int gg = cg * HG + g;
               const float4 b0 = *reinterpret_cast<const float4 *>(sb + gg * D + ib * 8);
               const float4 b1 = *reinterpret_cast<const float4 *>(sb + gg * D + ib * 8 + 4);
-              const float4 r0 = *reinterpret_cast<const float4 *>(sr + gg * D + ib * 8);
-              const float4 r1 = *reinterpret_cast<const float4 *>(sr + gg * D + ib * 8 + 4);
               const uint32_t *v = r[u] + g * 8;
               float2 y;
-              y = __ffma2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(r0.x, r0.y), make_float2(-b0.x, -b0.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
-              y = __ffma2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(r0.z, r0.w), make_float2(-b0.z, -b0.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
-              y = __ffma2_rn(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(r1.x, r1.y), make_float2(-b1.x, -b1.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
-              y = __ffma2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(r1.z, r1.w), make_float2(-b1.z, -b1.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
+              y = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(-b0.x, -b0.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
+              y = __fadd2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(-b0.z, -b0.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
+              y = __fadd2_rn(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(-b1.x, -b1.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
+              y = __fadd2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(-b1.z, -b1.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
             }
           }
         }
