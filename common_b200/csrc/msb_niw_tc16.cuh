@@ -26,13 +26,13 @@ using niwtc::TM;
 using niwtc::TN;
 constexpr int THREADS = 13 * 32;            // warps 0-3 producers, 4-7 and 9-12 epilogue, 8 MMA issuer
 constexpr int A_HALF_BYTES = TM * 32 * 2;   // one k-half (32 k) of one part (hi or lo): 8 KB
-constexpr int NA = 4;                        // A half-tile buffers in the ring (hi + lo each): conversion runs up to two tiles ahead of the MMAs
+constexpr int NA = 6;                        // A half-tile buffers in the ring (hi + lo each): the copies run up to three tiles ahead of the MMAs
 constexpr int A_BYTES = NA * 2 * A_HALF_BYTES;   // [buffer][part]: 64 KB
 constexpr int B_PART_BYTES = TN * D * 2;    // 32 KB
 constexpr int B_BYTES = 2 * B_PART_BYTES;   // hi + lo: 64 KB
 constexpr int SB_FLOATS = TN + 16;          // bias r_k [TN], coef[GB x 4] (c0, c1, 1 / (dof r_k^2), -)
 constexpr size_t SMEM_BYTES = (size_t)B_BYTES + A_BYTES + 2 * SB_FLOATS * sizeof(float) + D * sizeof(float) +
-                              16 * sizeof(uint64_t) + 64;
+                              20 * sizeof(uint64_t) + 64;
 
 // byte offset of element (row, k) inside one part of an fp16 operand tile with `rowgroups` 8-row groups:
 // [k/8][row/8][row%8][k%8]  (core matrix = 8 rows x 16 bytes, contiguous)
@@ -103,6 +103,38 @@ __global__ void niw_colmax_kernel(const float *__restrict__ X, size_t row_lo, si
   if (threadIdx.x < D) atomicMax(&colmax[threadIdx.x], sm[threadIdx.x]);
 }
 
+// X rows [row_lo, row_hi) -> the A operand of niw_tc16_kernel: per 128-row tile and k-half, [hi | lo] fp16 parts of
+// X[row][j] sx_j in core-matrix layout (16 KB, the exact bytes of one ring buffer).  Rows past row_hi are zero.
+// thread = (row, 8-k chunk), rows fastest: 32-byte reads (one sector each), coalesced 16-byte writes.
+__global__ void niw_convert_a16_kernel(const float *__restrict__ X, size_t row_lo, size_t row_hi, const unsigned int *__restrict__ colmax,
+                                       unsigned char *__restrict__ A16) {
+  using namespace niwtc16;
+  __shared__ float s_sx[D];
+  if (threadIdx.x < D) s_sx[threadIdx.x] = pow2_scale(__uint_as_float(colmax[threadIdx.x]));
+  __syncthreads();
+  const size_t rt = blockIdx.x;                 // one block per tile: 128 rows x 8 chunks = 1024 items, 256 threads
+  for (int it = threadIdx.x; it < TM * 8; it += blockDim.x) {
+    const int r = it % TM, c8 = it / TM;        // c8 in [0, 8): k = 8 c8 .. 8 c8 + 7
+    const size_t row = row_lo + rt * TM + r;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (row < row_hi) {
+      a = __ldg(reinterpret_cast<const float4 *>(X + row * D + c8 * 8));
+      b = __ldg(reinterpret_cast<const float4 *>(X + row * D + c8 * 8 + 4));
+    }
+    const float *sx = s_sx + c8 * 8;
+    uint4 vh, vl;
+    split2(a.x * sx[0], a.y * sx[1], vh.x, vl.x);
+    split2(a.z * sx[2], a.w * sx[3], vh.y, vl.y);
+    split2(b.x * sx[4], b.y * sx[5], vh.z, vl.z);
+    split2(b.z * sx[6], b.w * sx[7], vh.w, vl.w);
+    const int half = c8 >> 2;
+    unsigned char *hi_base = A16 + (rt * 2 + half) * (size_t)(2 * A_HALF_BYTES);
+    const uint32_t off = core_off16((uint32_t)r, (uint32_t)(c8 & 3) * 8, TM / 8);
+    *reinterpret_cast<uint4 *>(hi_base + off) = vh;
+    *reinterpret_cast<uint4 *>(hi_base + A_HALF_BYTES + off) = vl;
+  }
+}
+
 // W[k][i][j] (fp32, row-major per group) -> per group block: [hi | lo] fp16 parts in UMMA layout, scaled; blocks padded
 // with zeros.  rinv[2 k] = r_k, rinv[2 k + 1] = 1 / r_k^2.  sx[j] is derived from colmax[j] here and written out by block 0.
 __global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, const unsigned int *__restrict__ colmax,
@@ -153,8 +185,8 @@ __global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, cons
 }
 
 __global__ void __launch_bounds__(niwtc16::THREADS, 1)
-niw_tc16_kernel(const float *__restrict__ X, const unsigned char *__restrict__ Bop, const float *__restrict__ rinv,
-                const float *__restrict__ sxg, const float *__restrict__ bias, const float *__restrict__ coef, int ncols,
+niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__restrict__ Bop, const float *__restrict__ rinv,
+                const float *__restrict__ bias, const float *__restrict__ coef, int ncols,
                 float *__restrict__ scores, size_t ld, size_t row_lo, size_t row_hi, int num_gb_lanes,
                 const float *__restrict__ base, int blocked) {
   using namespace niwtc16;
@@ -163,12 +195,11 @@ niw_tc16_kernel(const float *__restrict__ X, const unsigned char *__restrict__ B
   unsigned char *sB = sm;                      // [part][...]
   unsigned char *sA = sm + B_BYTES;            // [half][part][...]
   float *sBias = reinterpret_cast<float *>(sA + A_BYTES);            // [2][SB_FLOATS]: bias, 1 / r, coef (GB x 4)
-  float *sSx = sBias + 2 * SB_FLOATS;                                 // [D]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sSx + D);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 15);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sBias + 2 * SB_FLOATS + D);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 19);
   // barriers: 0 b_full, 1 b_free, A_FULL.. a_full[NA], A_EMPTY.. a_empty[NA], ACC_FULL.. acc_full[2], ACC_EMPTY.. acc_empty[2]
   constexpr int A_FULL = 2, A_EMPTY = 2 + NA, ACC_FULL = 2 + 2 * NA, ACC_EMPTY = 4 + 2 * NA;
-  static_assert(ACC_EMPTY + 2 <= 15, "barrier slots");
+  static_assert(ACC_EMPTY + 2 <= 19, "barrier slots");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t nrows = row_hi - row_lo;
   const int nRT = (int)((nrows + TM - 1) / TM);
@@ -178,12 +209,11 @@ niw_tc16_kernel(const float *__restrict__ X, const unsigned char *__restrict__ B
   const int P = ((int)gridDim.x - g0 + G - 1) / G;
   const int rt_lo = (int)((long long)nRT * part / P), rt_hi = (int)((long long)nRT * (part + 1) / P);
 
-  if (tid < D) sSx[tid] = sxg[tid];
   if (tid == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
     mbar_init(smem_u32(&bars[1]), 1);
     for (int i = 0; i < NA; i++) {
-      mbar_init(smem_u32(&bars[A_FULL + i]), 4);    // a_full: one arrive per producer warp
+      mbar_init(smem_u32(&bars[A_FULL + i]), 1);    // a_full: the producer's expect_tx, completed by the bulk copy
       mbar_init(smem_u32(&bars[A_EMPTY + i]), 1);   // a_empty: tcgen05.commit
     }
     for (int i = 0; i < 2; i++) {
@@ -202,47 +232,24 @@ niw_tc16_kernel(const float *__restrict__ X, const unsigned char *__restrict__ B
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 4) {
-    // ===== producers: X tile (fp32) -> scaled fp16 hi / lo halves in core-matrix layout =====
-    const int n_mine = rt_hi - rt_lo;
-    const int ngb_mine = (nGB - g0 + G - 1) / G;
-    const long long total_h = 2ll * n_mine * ngb_mine;
-    auto load_half = [&](long long h, float4 (&v)[8]) {
-      const int rt = rt_lo + (int)((h >> 1) % n_mine), half = (int)(h & 1);
-      const size_t row = row_lo + (size_t)rt * TM + tid;  // tid in [0,128): one row per thread
-      const float4 *src = reinterpret_cast<const float4 *>(X + row * D) + half * 8;
-      const bool ok = row < row_hi;
-#pragma unroll
-      for (int c = 0; c < 8; c++) v[c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    float4 cur[8], nxt[8], nx2[8];
-    if (total_h > 0) load_half(0, cur);
-    if (total_h > 1) load_half(1, nxt);
-    for (long long h = 0; h < total_h; h++) {
-      if (h + 2 < total_h) load_half(h + 2, nx2);
-      const int buf = (int)(h % NA), half = (int)(h & 1);
-      if (h >= NA) mbar_wait(smem_u32(&bars[A_EMPTY + buf]), (uint32_t)(((h / NA) - 1) & 1));  // MMAs that read this buffer are done
-      unsigned char *hi_base = sA + (size_t)buf * 2 * A_HALF_BYTES;
-      unsigned char *lo_base = hi_base + A_HALF_BYTES;
-      const float *sx = sSx + half * 32;
-#pragma unroll
-      for (int c8 = 0; c8 < 4; c8++) {  // 4 chunks of 8 k: one 16-byte core-matrix row each
-        const float4 a = cur[2 * c8], b = cur[2 * c8 + 1];
-        const float4 s0 = *reinterpret_cast<const float4 *>(sx + c8 * 8), s1 = *reinterpret_cast<const float4 *>(sx + c8 * 8 + 4);
-        uint4 vh, vl;
-        split2(a.x * s0.x, a.y * s0.y, vh.x, vl.x);
-        split2(a.z * s0.z, a.w * s0.w, vh.y, vl.y);
-        split2(b.x * s1.x, b.y * s1.y, vh.z, vl.z);
-        split2(b.z * s1.z, b.w * s1.w, vh.w, vl.w);
-        const uint32_t off = core_off16((uint32_t)tid, (uint32_t)c8 * 8, TM / 8);
-        *reinterpret_cast<uint4 *>(hi_base + off) = vh;
-        *reinterpret_cast<uint4 *>(lo_base + off) = vl;
+    // ===== producer: one thread streams the pre-converted A operand (niw_convert_a16_kernel: scaled fp16 hi / lo parts,
+    // already in core-matrix layout, 16 KB per half-tile) into the ring with bulk copies.  Converting in this kernel,
+    // as the tf32 version does, repeats the conversion once per group block (64 times at C4) and was what the MMAs
+    // waited for.
+    if (tid == 0) {
+      const int n_mine = rt_hi - rt_lo;
+      const int ngb_mine = (nGB - g0 + G - 1) / G;
+      const long long total_h = 2ll * n_mine * ngb_mine;
+      for (long long h = 0; h < total_h; h++) {
+        const int rt = rt_lo + (int)((h >> 1) % n_mine), half = (int)(h & 1);
+        const int buf = (int)(h % NA);
+        if (h >= NA) mbar_wait(smem_u32(&bars[A_EMPTY + buf]), (uint32_t)(((h / NA) - 1) & 1));  // MMAs that read this buffer are done
+        const uint32_t bar = smem_u32(&bars[A_FULL + buf]);
+        mbar_expect_tx(bar, 2 * A_HALF_BYTES);
+        bulk_g2s(smem_u32(sA + (size_t)buf * 2 * A_HALF_BYTES), A16 + ((size_t)rt * 2 + half) * (2 * A_HALF_BYTES), 2 * A_HALF_BYTES, bar);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars[A_FULL + buf]));
-#pragma unroll
-      for (int c = 0; c < 8; c++) { cur[c] = nxt[c]; nxt[c] = nx2[c]; }
     }
+    __syncwarp();
   } else if (warp == 8) {
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0) {
@@ -407,9 +414,10 @@ static inline int niw_tc16_init(size_t smem_optin, std::string &err) {
 }
 // operand scratch of the fp16 path inside the buffer niw_tc_operand_bytes() sizes (the tf32 operands are twice as big):
 // [colmax: D u32][sx: D f32][rinv: nGB x TN f32][B blocks: nGB x B_BYTES]
+static inline size_t niw_tc16_a_bytes(size_t nrows) { return ((nrows + niwtc16::TM - 1) / niwtc16::TM) * (size_t)(4 * niwtc16::A_HALF_BYTES); }
 static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, const float *X, const float *W, const float *bias,
-                                 const float *coef, float *Bop, size_t ncols, float *scores, size_t ld, size_t row_lo,
-                                 size_t row_hi, int sm_count, const float *base, bool blocked, std::string &err) {
+                                 const float *coef, float *Bop, unsigned char *A16, size_t ncols, float *scores, size_t ld,
+                                 size_t row_lo, size_t row_hi, int sm_count, const float *base, bool blocked, std::string &err) {
   using namespace niwtc16;
   const int nGB = (int)((ncols + GB - 1) / GB);
   unsigned int *colmax = reinterpret_cast<unsigned int *>(Bop);
@@ -418,14 +426,15 @@ static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, const 
   unsigned char *Bblk = reinterpret_cast<unsigned char *>(Bop) + (2 * D + (size_t)nGB * TN) * sizeof(float);  // 512 + nGB KB: 16-byte aligned
   cudaMemsetAsync(colmax, 0, D * sizeof(unsigned int), stream);
   const size_t nrows = row_hi - row_lo;
+  const long long nRT = (long long)((nrows + TM - 1) / TM);
   const unsigned cm_grid = (unsigned)std::min<size_t>((nrows + 15) / 16, (size_t)sm_count * 8);
   niw_colmax_kernel<<<cm_grid, 256, 0, stream>>>(X, row_lo, row_hi, colmax);
+  niw_convert_a16_kernel<<<(unsigned)nRT, 256, 0, stream>>>(X, row_lo, row_hi, colmax, A16);
   niw_pack_b16_kernel<<<nGB, 256, 0, stream>>>(W, (int)ncols, colmax, Bblk, rinv, sx);
-  (*launches) += 2;
-  const long long nRT = (long long)((nrows + TM - 1) / TM);
+  (*launches) += 3;
   const int G = std::min(nGB, sm_count);
   const int grid = (int)std::max<long long>(G, std::min<long long>(sm_count, (long long)G * nRT));
-  niw_tc16_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(X, Bblk, rinv, sx, bias, coef, (int)ncols, scores, ld, row_lo, row_hi, G,
+  niw_tc16_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(A16, Bblk, rinv, bias, coef, (int)ncols, scores, ld, row_lo, row_hi, G,
                                                          base, blocked ? 1 : 0);
   (*launches)++;
   cudaError_t e = cudaGetLastError();

@@ -152,6 +152,7 @@ struct msb_state {
   float *d_uniforms = nullptr;
   unsigned long long *d_counter = nullptr;
   std::vector<float *> d_niwW, d_niwBias, d_niwCoef, d_niwB;
+  void *d_niwA16 = nullptr; size_t niw_a16_cap = 0;  // fp16 A operand of the tensor-core NIW kernel (one feature at a time)
   size_t niw_cols_cap = 0;
   // last score
   int tail_g = 0;  // replication width of the last k-tile's table columns (build_params), 0 = none
@@ -589,6 +590,7 @@ extern "C" MSB_API int msb_state_destroy(msb_state *st) {
   cudaFree(st->col_slab_b); cudaFree(st->d_feats_b); cudaFree(st->d_feats_scalar_b); cudaFree(st->d_flags_b); cudaFreeHost(st->h_flags_b);
   cudaFree(st->col_slab);
   for (size_t d = 0; d < st->D; d++) { cudaFree(st->d_niwW[d]); cudaFree(st->d_niwBias[d]); cudaFree(st->d_niwCoef[d]); cudaFree(st->d_niwB[d]); }
+  cudaFree(st->d_niwA16);
   cudaFree(st->d_feats); cudaFree(st->d_feats_scalar); cudaFree(st->d_hp); cudaFree(st->d_ss); cudaFree(st->d_delta); cudaFree(st->d_delta_i32); cudaFree(st->d_counter);
   cudaFree(st->d_slot2gid); cudaFree(st->d_assign64); cudaFree(st->d_flags); cudaFreeHost(st->h_moved); cudaFreeHost(st->h_flags); cudaFree(st->d_assign); cudaFree(st->d_params); cudaFree(st->d_scores);
   cudaFree(st->d_base); cudaFree(st->d_base_score); cudaFree(st->d_col2slot); cudaFree(st->d_newslot); cudaFree(st->d_newcol); cudaFree(st->d_uniforms);
@@ -1379,9 +1381,15 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
       need_init = false;
     }
     if (tc_ok && !getenv("MSB_NIW_TF32") && row_hi > row_lo) {  // fp16 operands (msb_niw_tc16.cuh): the default
+      const size_t a_bytes = niw_tc16_a_bytes(row_hi - row_lo);   // the rows of this call, converted once per sweep
+      if (st->niw_a16_cap < a_bytes) {
+        cudaFree(st->d_niwA16); st->d_niwA16 = nullptr; st->niw_a16_cap = 0;
+        CU_TRY(cudaMalloc(&st->d_niwA16, a_bytes));
+        st->niw_a16_cap = a_bytes;
+      }
       MSB_TRY(niw_tc16_score(ctx->stream, &ctx->launches, (const float *)f.scol, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
-                             st->d_niwB[d], K, scores, st->ld, row_lo, row_hi, ctx->sm_count, need_init ? st->d_base : nullptr,
-                             blocked, g_last_error));
+                             st->d_niwB[d], (unsigned char *)st->d_niwA16, K, scores, st->ld, row_lo, row_hi, ctx->sm_count,
+                             need_init ? st->d_base : nullptr, blocked, g_last_error));
       done = true;
     } else
     MSB_TRY(niw_tc_score(ctx->stream, &ctx->launches, (const float *)f.scol, f.dim, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
