@@ -422,10 +422,18 @@ def main():
             dims = [d()._param() for d in descs if d().name() == "niw"]
             flops = sum(2.0 * dd_ * dd_ * n * k for dd_ in dims)   # whitened-GEMM form, SURVEY.md section 8(d)
             ach = flops / (score_ms * 1e-3) / 1e12
-            roof = {"kernel": "niw_tc_kernel (+ pack, fill)", "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-                    "frac": ach / tf32_peak, "traffic": None, "algorithmic_flops_per_launch": flops, "launch_ms": score_ms,
-                    "peak_source": "torch.matmul TF32 8192^3 measured in this run (no TF32 figure in MEASURED_PEAKS.json)",
-                    "note": "the kernel issues 3 tf32 products per algorithmic product (hi*hi + hi*lo + lo*hi) for fp32-class accuracy: tensor-pipe work is 3x the algorithmic FLOPs"}
+            if os.environ.get("MSB_NIW_TF32"):
+                roof = {"kernel": "niw_tc_kernel (+ pack, fill)", "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": ach / tf32_peak, "traffic": None, "algorithmic_flops_per_launch": flops, "launch_ms": score_ms,
+                        "peak_source": "torch.matmul TF32 8192^3 measured in this run (no TF32 figure in MEASURED_PEAKS.json)",
+                        "note": "the kernel issues 3 tf32 products per algorithmic product (hi*hi + hi*lo + lo*hi) for fp32-class accuracy: tensor-pipe work is 3x the algorithmic FLOPs"}
+            else:
+                f16_peak = float(peaks.get("bf16_tflops", 0.0)) or 2.0 * tf32_peak
+                roof = {"kernel": "niw_tc16_kernel (+ colmax, convert, pack)", "bound": "tensor", "achieved": ach, "peak": f16_peak, "unit": "TFLOP/s",
+                        "frac": ach / f16_peak, "traffic": None, "algorithmic_flops_per_launch": flops, "launch_ms": score_ms,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; fp16 runs at the bf16 rate)" if peaks.get("bf16_tflops") else "2 x the TF32 rate measured in this run",
+                        "tf32_tflops_measured_here": tf32_peak,
+                        "note": "the kernel issues 3 fp16 products per algorithmic product (hi*hi + hi*lo + lo*hi, scaled operands) for fp32-class accuracy: tensor-pipe work is 3x the algorithmic FLOPs, i.e. pipe utilisation = 3 x frac"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

@@ -187,7 +187,7 @@ __global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, cons
 __global__ void __launch_bounds__(niwtc16::THREADS, 1)
 niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__restrict__ Bop, const float *__restrict__ rinv,
                 const float *__restrict__ bias, const float *__restrict__ coef, int ncols,
-                float *__restrict__ scores, size_t ld, size_t row_lo, size_t row_hi, int num_gb_lanes,
+                float *__restrict__ scores, size_t ld, size_t row_lo, size_t row_hi, int slice_tiles,
                 const float *__restrict__ base, int blocked) {
   using namespace niwtc16;
   extern __shared__ __align__(1024) unsigned char niw_smem[];
@@ -204,11 +204,14 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
   const size_t nrows = row_hi - row_lo;
   const int nRT = (int)((nrows + TM - 1) / TM);
   const int nGB = (ncols + GB - 1) / GB;
-  const int G = (int)num_gb_lanes;
-  const int g0 = (int)blockIdx.x % G, part = (int)blockIdx.x / G;
-  const int P = ((int)gridDim.x - g0 + G - 1) / G;
-  const int rt_lo = (int)((long long)nRT * part / P), rt_hi = (int)((long long)nRT * (part + 1) / P);
-
+  // Schedule: the work is cut into items (slice of `slice_tiles` row tiles) x (group block), numbered group block
+  // fastest, and CTA c takes the items c, c + gridDim.x, ...  At any moment the CTAs are therefore all inside two or three
+  // neighbouring slices: their A tiles are shared through L2 (A streams from HBM about once), and every CTA gets the
+  // same number of items to within one -- the earlier split into one lane of CTAs per group block left 44 of the 64
+  // lanes with two CTAs and 20 with three at C4, i.e. finished 13 % later than the average.
+  const int SL = slice_tiles;
+  const int nSL = (nRT + SL - 1) / SL;
+  const long long nItems = (long long)nSL * nGB;
   if (tid == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
     mbar_init(smem_u32(&bars[1]), 1);
@@ -237,16 +240,18 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
     // as the tf32 version does, repeats the conversion once per group block (64 times at C4) and was what the MMAs
     // waited for.
     if (tid == 0) {
-      const int n_mine = rt_hi - rt_lo;
-      const int ngb_mine = (nGB - g0 + G - 1) / G;
-      const long long total_h = 2ll * n_mine * ngb_mine;
-      for (long long h = 0; h < total_h; h++) {
-        const int rt = rt_lo + (int)((h >> 1) % n_mine), half = (int)(h & 1);
+      long long h = 0;
+      for (long long item = blockIdx.x; item < nItems; item += gridDim.x) {
+      const int sl = (int)(item / nGB);
+      const int rt_lo = sl * SL, rt_hi = rt_lo + SL < nRT ? rt_lo + SL : nRT;
+      for (int rt = rt_lo; rt < rt_hi; rt++)
+      for (int half = 0; half < 2; half++, h++) {
         const int buf = (int)(h % NA);
         if (h >= NA) mbar_wait(smem_u32(&bars[A_EMPTY + buf]), (uint32_t)(((h / NA) - 1) & 1));  // MMAs that read this buffer are done
         const uint32_t bar = smem_u32(&bars[A_FULL + buf]);
         mbar_expect_tx(bar, 2 * A_HALF_BYTES);
         bulk_g2s(smem_u32(sA + (size_t)buf * 2 * A_HALF_BYTES), A16 + ((size_t)rt * 2 + half) * (2 * A_HALF_BYTES), 2 * A_HALF_BYTES, bar);
+      }
       }
     }
     __syncwarp();
@@ -257,7 +262,9 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
       int cur_gb = -1;
       uint32_t b_loads = 0;
       const uint32_t idesc = idesc_f16(TN);
-      for (int gb = g0; gb < nGB; gb += G)
+      for (long long item = blockIdx.x; item < nItems; item += gridDim.x) {
+      const int gb = (int)(item % nGB), sl = (int)(item / nGB);
+      const int rt_lo = sl * SL, rt_hi = rt_lo + SL < nRT ? rt_lo + SL : nRT;
       for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
         if (gb != cur_gb) {  // (re)load the resident B operand
           if (cur_gb >= 0) {
@@ -295,6 +302,7 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
           if (half == 1) niwtc::mma_commit(smem_u32(&bars[ACC_FULL + acc]));  // accumulator ready for the epilogue
         }
       }
+      }
     }
     __syncwarp();
   } else {
@@ -309,7 +317,9 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
     int staged_gb = -1;
     float *sb = sBias;
     float *sc = sb + TN;
-    for (int gb = g0; gb < nGB; gb += G)
+    for (long long item = blockIdx.x; item < nItems; item += gridDim.x) {
+    const int gb = (int)(item % nGB), sl = (int)(item / nGB);
+    const int rt_lo = sl * SL, rt_hi = rt_lo + SL < nRT ? rt_lo + SL : nRT;
     for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
       const int acc = (int)(t & 1);
       // this group block's bias and coefficients: staged when the block changes, not per tile -- the global
@@ -397,6 +407,7 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
         }
       }
     }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -432,9 +443,11 @@ static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, const 
   niw_convert_a16_kernel<<<(unsigned)nRT, 256, 0, stream>>>(X, row_lo, row_hi, colmax, A16);
   niw_pack_b16_kernel<<<nGB, 256, 0, stream>>>(W, (int)ncols, colmax, Bblk, rinv, sx);
   (*launches) += 3;
-  const int G = std::min(nGB, sm_count);
-  const int grid = (int)std::max<long long>(G, std::min<long long>(sm_count, (long long)G * nRT));
-  niw_tc16_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(A16, Bblk, rinv, bias, coef, (int)ncols, scores, ld, row_lo, row_hi, G,
+  // about 24 items per CTA (at most 32 tiles per slice): balance to within a few percent, one B reload per item
+  const int SL = (int)std::max<long long>(1, std::min<long long>(32, nRT * nGB / ((long long)sm_count * 24)));
+  const long long nItems = ((nRT + SL - 1) / SL) * nGB;
+  const int grid = (int)std::min<long long>(sm_count, nItems);
+  niw_tc16_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(A16, Bblk, rinv, bias, coef, (int)ncols, scores, ld, row_lo, row_hi, SL,
                                                          base, blocked ? 1 : 0);
   (*launches)++;
   cudaError_t e = cudaGetLastError();
