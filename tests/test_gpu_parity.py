@@ -952,3 +952,34 @@ def test_dm_score_kernels_over_their_branches(ctx, oracle, C, alpha, total, monk
         _, S64b = st.score_rows_f64()
         assert np.max(np.abs(S64b - S64) / np.maximum(1.0, np.abs(S64))) < 2e-11
     st.close()
+
+
+@pytest.mark.parametrize("spread", [1.0, 1.0e3])
+def test_niw_tensor_core_path_with_badly_scaled_and_correlated_columns(ctx, oracle, spread):
+    # the fp16 tensor-core path scales every column of X and every W_k by a power of two: columns whose ranges differ
+    # by 10^6 and strongly correlated coordinates (a whitening matrix with rows of very different size) must still meet
+    # the fp32 tolerance
+    dim, n, k = 64, 1500, 6
+    rng = np.random.default_rng(int(spread))
+    colscale = np.logspace(-np.log10(spread), np.log10(spread), dim)
+    mix = np.eye(dim) + 0.9 * np.tril(rng.normal(size=(dim, dim)), -1) / np.sqrt(dim)   # correlated coordinates
+    z = np.arange(n) % k
+    mu = rng.normal(0, 3, size=(k, dim))
+    x = ((mu[z] + rng.normal(size=(n, dim))) @ mix.T) * colscale
+    arr = np.zeros(n, dtype=[("f0", np.float32, (dim,))])
+    arr["f0"] = x.astype(np.float32)
+    view = cb.numpy_dataview(arr)
+    descs = [cb.niw(dim)]
+    st = cb.state(ctx, descs, max_groups=k + 2, cluster_hp={"alpha": 1.0})
+    hp = {"mu": np.zeros(dim), "kappa": 1.0, "psi": np.diag(colscale ** 2), "nu": float(dim)}
+    st.set_component_hp(0, hp)
+    st.bind(view)
+    gids = [st.create_group() for _ in range(k + 1)]
+    st.add_values(np.asarray(gids)[z])
+    hp_flat = oracle.flat_hp(descs[0], hp)
+    ss, counts = ol.build_suffstats(oracle, descs, hp_flat, view, z, k + 1)
+    want = oracle.score_rows(descs, hp_flat, ss, ol.logprior(counts, 1.0), view, prec=64)
+    res = st.sweep(seed=3, sweep=0)         # the sweep takes the tensor-core kernel (blocked layout)
+    S = st.read_last_scores()
+    assert np.max(rel_err(S, want)) < 4 * RTOL
+    st.close()
