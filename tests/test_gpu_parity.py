@@ -983,3 +983,27 @@ def test_niw_tensor_core_path_with_badly_scaled_and_correlated_columns(ctx, orac
     S = st.read_last_scores()
     assert np.max(rel_err(S, want)) < 4 * RTOL
     st.close()
+
+
+@pytest.mark.parametrize("descs,exact", [([cb.bb, cb.gp, cb.nich, cb.dd(16), cb.dm(6)], True), ([cb.niw(64), cb.nich], False)],
+                         ids=["scalars+dm", "niw64"])
+def test_sweep_in_row_chunks_draws_like_one_pass(ctx, oracle, descs, exact, monkeypatch):
+    # a sweep whose score matrix exceeds the budget (MSB_SCORES_MB) runs in row chunks: same draws as the one-pass sweep
+    # (bit-identical for the scalar kernels; the fp16 NIW kernel rescales per chunk, so a draw may flip where the dart
+    # lands within rounding of a boundary)
+    n, k = 20000, 20
+    out = []
+    for mb in (None, "1"):
+        if mb:
+            monkeypatch.setenv("MSB_SCORES_MB", mb)
+        st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=131, mask_frac=0.02, extra_empty=1)
+        res = st.sweep(seed=17, sweep=0)
+        assert res["rows"] == n
+        out.append((np.searchsorted(gids, st.assignments()), res["moved"], [st.groupsize(g) for g in gids]))
+        st.close()
+    (a0, m0, c0), (a1, m1, c1) = out
+    if exact:
+        assert np.array_equal(a0, a1) and m0 == m1 and c0 == c1
+    else:
+        assert np.mean(a0 != a1) < 1e-3
+    assert sum(c1) == n
