@@ -261,7 +261,6 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
       long long h = 0, t = 0;
       int cur_gb = -1;
       uint32_t b_loads = 0;
-      const uint32_t idesc = idesc_f16(TN);
       for (long long item = blockIdx.x; item < nItems; item += gridDim.x) {
       const int gb = (int)(item % nGB), sl = (int)(item / nGB);
       const int rt_lo = sl * SL, rt_hi = rt_lo + SL < nRT ? rt_lo + SL : nRT;
@@ -290,13 +289,20 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
           const uint32_t b_hi = smem_u32(sB) + (uint32_t)half * (32 / 8) * (TN / 8) * 128u, b_lo = b_hi + B_PART_BYTES;
 #pragma unroll
           for (int ks = 0; ks < 2; ks++) {  // K = 16 per instruction: 2 core-matrix columns
+            // W_k is lower triangular: contraction step st (j in [16 st, 16 st + 16)) only reaches the outputs i >= 16 st,
+            // which the operand row order n' = (i / 8) * 32 + g * 8 + i % 8 makes the contiguous rows / accumulator
+            // columns [64 st, 256): N = 256, 192, 128, 64 over the four steps, 640 instead of 1024 columns of tensor
+            // work per tile.  (The same trick did not pay in the tf32 kernel, which was not bound by the tensor pipe.)
+            const uint32_t st = (uint32_t)(half * 2 + ks);
+            const uint32_t n0 = (blocked & 4) ? 0u : st * 64u;
+            const uint32_t idn = idesc_f16(TN - n0);
             const uint32_t ao = (uint32_t)ks * 2u * (TM / 8) * 128u;
-            const uint32_t bo = (uint32_t)ks * 2u * (TN / 8) * 128u;
+            const uint32_t bo = (uint32_t)ks * 2u * (TN / 8) * 128u + (n0 / 8u) * 128u;
             const uint64_t dah = niwtc::smem_desc(a_hi + ao, (TM / 8) * 128u, 128u), dal = niwtc::smem_desc(a_lo + ao, (TM / 8) * 128u, 128u);
             const uint64_t dbh = niwtc::smem_desc(b_hi + bo, (TN / 8) * 128u, 128u), dbl = niwtc::smem_desc(b_lo + bo, (TN / 8) * 128u, 128u);
-            mma_f16(d_tmem, dah, dbh, idesc, (half | ks) ? 1u : 0u);
-            mma_f16(d_tmem, dah, dbl, idesc, 1u);
-            mma_f16(d_tmem, dal, dbh, idesc, 1u);
+            mma_f16(d_tmem + n0, dah, dbh, idn, st ? 1u : 0u);
+            mma_f16(d_tmem + n0, dah, dbl, idn, 1u);
+            mma_f16(d_tmem + n0, dal, dbh, idn, 1u);
           }
           niwtc::mma_commit(smem_u32(&bars[A_EMPTY + buf]));            // A half-buffer free once these MMAs complete
           if (half == 1) niwtc::mma_commit(smem_u32(&bars[ACC_FULL + acc]));  // accumulator ready for the epilogue
@@ -448,7 +454,7 @@ static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, const 
   const long long nItems = ((nRT + SL - 1) / SL) * nGB;
   const int grid = (int)std::min<long long>(sm_count, nItems);
   niw_tc16_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(A16, Bblk, rinv, bias, coef, (int)ncols, scores, ld, row_lo, row_hi, SL,
-                                                         base, blocked ? 1 : 0);
+                                                         base, (blocked ? 1 : 0) | (getenv("MSB_NIW_NO_TRI") ? 4 : 0));
   (*launches)++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { err = std::string("niw_tc16_kernel launch: ") + cudaGetErrorString(e); return MSB_ERR_CUDA; }
