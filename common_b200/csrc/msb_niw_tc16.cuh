@@ -221,7 +221,7 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(smem_u32(&bars[ACC_FULL + i]), 1);  // acc_full: tcgen05.commit
-      mbar_init(smem_u32(&bars[ACC_EMPTY + i]), 8); // acc_empty: one arrive per epilogue warp
+      mbar_init(smem_u32(&bars[ACC_EMPTY + i]), 4); // acc_empty: one arrive per warp of the set that owns the accumulator
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -312,27 +312,27 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warps 4..7 (groups 0, 1 of the block) and 9..12 (groups 2, 3); TMEM lanes 32 * (warp % 4) .. + 31 =====
-    // Two warps per lane quadrant, each reading 16 of the 32 columns of an output block: the epilogue (256 outputs per
-    // row and tile, two packed operations and half a shared-memory load each) was the critical path with four warps.
-    constexpr int HG = GB / 2;  // groups per epilogue warp
+    // ===== epilogue: warps 4..7 take the even tiles (accumulator 0), warps 9..12 the odd ones (accumulator 1); TMEM lanes
+    // 32 * (warp % 4) .. + 31.  A tile's epilogue is a chain of waits (accumulator ready -> TMEM loads -> arithmetic ->
+    // release): with one set of warps the chains of consecutive tiles run back to back and their latency, not their
+    // instruction count, set the pace; two sets overlap them.
     const int ew = warp & 3;
-    const int cg = warp >= 9 ? 1 : 0;
-    const int etid = cg * 128 + ew * 32 + lane;  // 0..255
+    const int set = warp >= 9 ? 1 : 0;
+    const int etid = ew * 32 + lane;  // 0..127 within the set
     long long t = 0;
     int staged_gb = -1;
-    float *sb = sBias;
+    float *sb = sBias + (size_t)set * SB_FLOATS;
     float *sc = sb + TN;
     for (long long item = blockIdx.x; item < nItems; item += gridDim.x) {
     const int gb = (int)(item % nGB), sl = (int)(item / nGB);
     const int rt_lo = sl * SL, rt_hi = rt_lo + SL < nRT ? rt_lo + SL : nRT;
     for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
-      const int acc = (int)(t & 1);
-      // this group block's bias and coefficients: staged when the block changes, not per tile -- the global
-      // loads and the two barriers around them sat on the epilogue's critical path of every tile
+      if ((int)(t & 1) != set) continue;
+      const int acc = set;
+      // this group block's bias and coefficients (each set keeps its own copy): staged when the block changes, not per tile
       if (gb != staged_gb) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // nobody still reads the previous block's values
-        for (int i = etid; i < SB_FLOATS; i += 256) {
+        if (set == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        for (int i = etid; i < SB_FLOATS; i += 128) {
           float v = 0.f;
           if (i < TN) {  // bias' = b r_k
             const int k = gb * GB + i / D;
@@ -343,73 +343,65 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
           }
           sb[i] = v;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (set == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
         staged_gb = gb;
       }
       const size_t row = row_lo + (size_t)rt * TM + ew * 32 + lane;
-      float2 *dst = reinterpret_cast<float2 *>(scores + (row - row_lo) * ld + (size_t)gb * GB + cg * HG);
-      float *dstb = scores + (((size_t)rt * (TM / 32) + ew) * ld + (size_t)gb * GB + cg * HG) * 32 + lane;
-      float2 old = make_float2(0.f, 0.f);
+      float4 *dst = reinterpret_cast<float4 *>(scores + (row - row_lo) * ld + (size_t)gb * GB);
+      float *dstb = scores + (((size_t)rt * (TM / 32) + ew) * ld + (size_t)gb * GB) * 32 + lane;
+      float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < row_hi) {
-        if (base) old = __ldg(reinterpret_cast<const float2 *>(base + (size_t)gb * GB + cg * HG));
-        else if (blocked & 1) old = make_float2(dstb[0], dstb[32]);
+        if (base) old = __ldg(reinterpret_cast<const float4 *>(base + (size_t)gb * GB));
+        else if (blocked & 1) old = make_float4(dstb[0], dstb[32], dstb[64], dstb[96]);
         else old = *dst;
       }
       mbar_wait(smem_u32(&bars[ACC_FULL + acc]), (uint32_t)((t >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float q[HG];
+      float q[GB];
       {
-        float2 q2[HG];
+        float2 q2[GB];
 #pragma unroll
-        for (int g = 0; g < HG; g++) q2[g] = make_float2(0.f, 0.f);
-        // accumulator column n' = (i / 8) * 32 + g * 8 + i % 8: this warp's groups are the 16 columns from cg * 16
-        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN) + (uint32_t)(cg * 16);
-        // four 16-column loads in flight at a time: with one, the TMEM round trip (not the arithmetic) set the pace
-        uint32_t r[4][16];
+        for (int g = 0; g < GB; g++) q2[g] = make_float2(0.f, 0.f);
+        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN);
+        uint32_t r[2][32];
+        niwtc::tmem_ld32_issue(tbase, r[0]);
 #pragma unroll
-        for (int ib0 = 0; ib0 < D / 8; ib0 += 4) {
-#pragma unroll
-          for (int u = 0; u < 4; u++) tmem_ld16_issue(tbase + (uint32_t)(ib0 + u) * 32u, r[u]);
+        for (int ib = 0; ib < D / 8; ib++) {
           niwtc::tmem_ld_wait();
+          if (ib + 1 < D / 8) niwtc::tmem_ld32_issue(tbase + (uint32_t)(ib + 1) * 32u, r[(ib + 1) & 1]);
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int ib = ib0 + u;
-#pragma unroll
-            for (int g = 0; g < HG; g++) {
-              const int gg = cg * HG + g;
-              const float4 b0 = *reinterpret_cast<const float4 *>(sb + gg * D + ib * 8);
-              const float4 b1 = *reinterpret_cast<const float4 *>(sb + gg * D + ib * 8 + 4);
-              const uint32_t *v = r[u] + g * 8;
-              float2 y;
-              y = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(-b0.x, -b0.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
-              y = __fadd2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(-b0.z, -b0.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
-              y = __fadd2_rn(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(-b1.x, -b1.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
-              y = __fadd2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(-b1.z, -b1.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
-            }
+          for (int g = 0; g < GB; g++) {
+            const float4 b0 = *reinterpret_cast<const float4 *>(sb + g * D + ib * 8);
+            const float4 b1 = *reinterpret_cast<const float4 *>(sb + g * D + ib * 8 + 4);
+            const uint32_t *v = r[ib & 1] + g * 8;
+            float2 y;
+            y = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(-b0.x, -b0.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
+            y = __fadd2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(-b0.z, -b0.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
+            y = __fadd2_rn(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(-b1.x, -b1.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
+            y = __fadd2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(-b1.z, -b1.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
           }
         }
 #pragma unroll
-        for (int g = 0; g < HG; g++) q[g] = q2[g].x + q2[g].y;
+        for (int g = 0; g < GB; g++) q[g] = q2[g].x + q2[g].y;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
       if (row < row_hi) {
-        float o[HG] = {old.x, old.y};
+        float o[GB] = {old.x, old.y, old.z, old.w};
 #pragma unroll
-        for (int g = 0; g < HG; g++) {
-          const int gg = cg * HG + g;
-          const int k = gb * GB + gg;
+        for (int g = 0; g < GB; g++) {
+          const int k = gb * GB + g;
           if (k < ncols && q[g] == q[g]) {  // NaN = masked row: contributes nothing
-            const float c0 = sc[gg * 4 + 0], c1 = sc[gg * 4 + 1], idof = sc[gg * 4 + 2];
+            const float c0 = sc[g * 4 + 0], c1 = sc[g * 4 + 1], idof = sc[g * 4 + 2];
             o[g] += c0 + c1 * log1pf(q[g] * idof);
           }
         }
         if (blocked & 1) {
 #pragma unroll
-          for (int g = 0; g < HG; g++) dstb[g * 32] = o[g];
+          for (int g = 0; g < GB; g++) dstb[g * 32] = o[g];
         } else {
-          *dst = make_float2(o[0], o[1]);
+          *dst = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
     }
