@@ -136,9 +136,9 @@ __global__ void niw_convert_a16_kernel(const float *__restrict__ X, size_t row_l
 }
 
 // W[k][i][j] (fp32, row-major per group) -> per group block: [hi | lo] fp16 parts in UMMA layout, scaled; blocks padded
-// with zeros.  rinv[2 k] = r_k, rinv[2 k + 1] = 1 / r_k^2.  sx[j] is derived from colmax[j] here and written out by block 0.
+// with zeros.  rinv[2 k] = r_k, rinv[2 k + 1] = 1 / r_k^2.  sx[j] is derived from colmax[j] (as niw_convert_a16_kernel does).
 __global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, const unsigned int *__restrict__ colmax,
-                                    unsigned char *__restrict__ Bop, float *__restrict__ rinv, float *__restrict__ sx_out) {
+                                    unsigned char *__restrict__ Bop, float *__restrict__ rinv) {
   using namespace niwtc16;
   __shared__ float s_isx[D];   // 1 / sx_j
   __shared__ float s_r[2 * GB];  // per group: max |W / sx| (as ordered bits), then r_k
@@ -146,7 +146,6 @@ __global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, cons
   if (threadIdx.x < D) {
     const float sx = pow2_scale(__uint_as_float(colmax[threadIdx.x]));
     s_isx[threadIdx.x] = 1.f / sx;
-    if (gb == 0) sx_out[threadIdx.x] = sx;
   }
   __syncthreads();
   // one scale per group: r_k brings max_ij |W[k][i][j] / sx_j| into [256, 512).  (A scale per output row would keep a
@@ -422,7 +421,7 @@ static inline int niw_tc16_init(size_t smem_optin, std::string &err) {
   return MSB_OK;
 }
 // operand scratch of the fp16 path inside the buffer niw_tc_operand_bytes() sizes (the tf32 operands are twice as big):
-// [colmax: D u32][sx: D f32][rinv: nGB x TN f32][B blocks: nGB x B_BYTES]
+// [colmax: D u32][D f32 unused][rinv: nGB x TN f32, 2 used per group][B blocks: nGB x B_BYTES]
 static inline size_t niw_tc16_a_bytes(size_t nrows) { return ((nrows + niwtc16::TM - 1) / niwtc16::TM) * (size_t)(4 * niwtc16::A_HALF_BYTES); }
 static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, const float *X, const float *W, const float *bias,
                                  const float *coef, float *Bop, unsigned char *A16, size_t ncols, float *scores, size_t ld,
@@ -430,7 +429,6 @@ static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, const 
   using namespace niwtc16;
   const int nGB = (int)((ncols + GB - 1) / GB);
   unsigned int *colmax = reinterpret_cast<unsigned int *>(Bop);
-  float *sx = Bop + D;
   float *rinv = Bop + 2 * D;
   unsigned char *Bblk = reinterpret_cast<unsigned char *>(Bop) + (2 * D + (size_t)nGB * TN) * sizeof(float);  // 512 + nGB KB: 16-byte aligned
   cudaMemsetAsync(colmax, 0, D * sizeof(unsigned int), stream);
@@ -439,7 +437,7 @@ static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, const 
   const unsigned cm_grid = (unsigned)std::min<size_t>((nrows + 15) / 16, (size_t)sm_count * 8);
   niw_colmax_kernel<<<cm_grid, 256, 0, stream>>>(X, row_lo, row_hi, colmax);
   niw_convert_a16_kernel<<<(unsigned)nRT, 256, 0, stream>>>(X, row_lo, row_hi, colmax, A16);
-  niw_pack_b16_kernel<<<nGB, 256, 0, stream>>>(W, (int)ncols, colmax, Bblk, rinv, sx);
+  niw_pack_b16_kernel<<<nGB, 256, 0, stream>>>(W, (int)ncols, colmax, Bblk, rinv);
   (*launches) += 3;
   // about 24 items per CTA (at most 32 tiles per slice): balance to within a few percent, one B reload per item
   const int SL = (int)std::max<long long>(1, std::min<long long>(32, nRT * nGB / ((long long)sm_count * 24)));

@@ -954,8 +954,11 @@ def test_dm_score_kernels_over_their_branches(ctx, oracle, C, alpha, total, monk
     st.close()
 
 
+@pytest.mark.parametrize("operands", ["f16", "tf32"])
 @pytest.mark.parametrize("spread", [1.0, 1.0e3])
-def test_niw_tensor_core_path_with_badly_scaled_and_correlated_columns(ctx, oracle, spread):
+def test_niw_tensor_core_path_with_badly_scaled_and_correlated_columns(ctx, oracle, spread, operands, monkeypatch):
+    if operands == "tf32":
+        monkeypatch.setenv("MSB_NIW_TF32", "1")   # the tf32-operand kernel (msb_niw_tc.cuh), kept as the alternative
     # the fp16 tensor-core path scales every column of X and every W_k by a power of two: columns whose ranges differ
     # by 10^6 and strongly correlated coordinates (a whitening matrix with rows of very different size) must still meet
     # the fp32 tolerance
