@@ -79,3 +79,43 @@ def test_packed_repeated_scalars_and_unknown_fields_are_accepted():
     assert wire.decode("dd.Shared", packed_alphas)["alphas"] == [0.5, 1.5]
     msg = wire.encode("nich.Group", {"count": 7, "mean": 0.25, "count_times_variance": 3.5})
     assert wire.decode("nich.Group", msg) == {"count": 7, "mean": 0.25, "count_times_variance": 3.5}
+
+
+def test_in_tree_model_messages_equal_the_protobuf_runtime():
+    # BetaBernoulliNonConj.{Shared, Group} and DirichletMultinomial.{Shared, Group} (schema.proto:7-29): the bytes of
+    # group::get_ss / hypers::get_hp for the two in-tree models
+    fd = descriptor_pb2.FileDescriptorProto()
+    fd.name, fd.package, fd.syntax = "schema_models.proto", "microscopes.io", "proto2"
+    REQ, REP = F.LABEL_REQUIRED, F.LABEL_REPEATED
+
+    def nested(outer, name, fields):
+        m = outer.nested_type.add()
+        m.name = name
+        for fname, num, ftype, label in fields:
+            f = m.field.add()
+            f.name, f.number, f.type, f.label = fname, num, ftype, label
+
+    bbnc = fd.message_type.add(); bbnc.name = "BetaBernoulliNonConj"
+    nested(bbnc, "Shared", [("alpha", 1, F.TYPE_FLOAT, REQ), ("beta", 2, F.TYPE_FLOAT, REQ)])
+    nested(bbnc, "Group", [("p", 1, F.TYPE_FLOAT, REQ), ("heads", 2, F.TYPE_UINT32, REQ), ("tails", 3, F.TYPE_UINT32, REQ)])
+    dm = fd.message_type.add(); dm.name = "DirichletMultinomial"
+    nested(dm, "Shared", [("alphas", 1, F.TYPE_FLOAT, REP)])
+    nested(dm, "Group", [("counts", 1, F.TYPE_UINT32, REP), ("ratio", 2, F.TYPE_FLOAT, REQ)])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+
+    def cls(name):
+        return message_factory.GetMessageClass(pool.FindMessageTypeByName("microscopes.io." + name))
+
+    s = cls("BetaBernoulliNonConj.Shared")(); s.alpha, s.beta = 0.5, 2.0
+    assert wire.encode("bbnc.Shared", {"alpha": 0.5, "beta": 2.0}) == s.SerializeToString()
+    g = cls("BetaBernoulliNonConj.Group")(); g.p, g.heads, g.tails = 0.3125, 7, 300
+    mine = wire.encode("bbnc.Group", {"p": 0.3125, "heads": 7, "tails": 300})
+    assert mine == g.SerializeToString() and wire.decode("bbnc.Group", mine) == {"p": 0.3125, "heads": 7, "tails": 300}
+    s = cls("DirichletMultinomial.Shared")(); s.alphas.extend([1.0, 0.25, 3.5])
+    assert wire.encode("dm.Shared", {"alphas": [1.0, 0.25, 3.5]}) == s.SerializeToString()
+    g = cls("DirichletMultinomial.Group")(); g.counts.extend([0, 12, 70000, 3]); g.ratio = 41.625
+    mine = wire.encode("dm.Group", {"counts": [0, 12, 70000, 3], "ratio": 41.625})
+    assert mine == g.SerializeToString()
+    back = wire.decode("dm.Group", g.SerializeToString())
+    assert back["counts"] == [0, 12, 70000, 3] and back["ratio"] == 41.625
