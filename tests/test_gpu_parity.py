@@ -1010,3 +1010,21 @@ def test_sweep_in_row_chunks_draws_like_one_pass(ctx, oracle, descs, exact, monk
     else:
         assert np.mean(a0 != a1) < 1e-3
     assert sum(c1) == n
+
+
+def test_single_rows_through_the_tensor_core_niw_path(ctx, oracle):
+    # one-row ranges and single-entity score_value (entity_state.hpp:60-72) with a dim-64 NIW feature: one tile, one item
+    descs = [cb.niw(64), cb.bb]
+    n, k = 300, 5
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=9)
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, prec=64)
+    _, S = st.score_rows(137, 138)
+    assert np.max(rel_err(S[0], want[137])) < 4 * RTOL
+    eid = 11
+    st.remove_value(eid)
+    a = z.astype(np.int32).copy(); b = a.copy(); b[eid] = -1
+    oracle.update_rows(descs, hp, ss, counts, view, a, b)
+    _, s = st.score_value(eid)
+    w = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, eid, eid + 1, prec=64)[0]
+    assert np.max(rel_err(s, w)) < 4 * RTOL
+    st.close()
