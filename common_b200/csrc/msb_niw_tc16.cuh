@@ -1,10 +1,11 @@
-// msb_niw_tc16.cuh -- the NIW Mahalanobis GEMM of msb_niw_tc.cuh on the fp16 tensor-core path (kind::f16, K = 16).
+// msb_niw_tc16.cuh -- the NIW Mahalanobis GEMM on the fp16 tensor-core path (tcgen05 kind::f16, M128 N256 K16), dim == 64.
 //
-// Same contraction, same CTA roles, barriers, schedule and epilogue as niw_tc_kernel; what changes is the operand
-// format.  A tf32 operand keeps 11 significand bits, so fp32-class accuracy takes a hi / lo split and three products
-// per k-step (hi*hi + hi*lo + lo*hi).  An fp16 operand keeps 11 bits as well, the same three products give the same
-// 2^-21 -- but kind::f16 runs at twice the tf32 rate and an instruction covers K = 16 instead of 8: half the tensor
-// time and half the operand bytes.  fp16's narrow exponent is handled by exact power-of-two scales:
+//   scores[n][k] += c0_k + c1_k * log1p(|W_k x_n - b_k|^2 / dof_k),     Y[n][(k,i)] = sum_j X[n][j] W_k[i][j]
+//
+// Operands.  A tf32 operand keeps 11 significand bits, so fp32-class accuracy takes a hi / lo split and three products
+// per k-step (hi*hi + hi*lo + lo*hi; msb_niw_tc.cuh).  An fp16 operand keeps 11 bits as well: the same three products
+// give the same 2^-21 at twice the tensor rate, K = 16 per instruction and half the operand bytes.  fp16's narrow
+// exponent is handled by exact power-of-two scales:
 //   X'[n][j]      = X[n][j] sx_j,            sx_j   = 2^(9 - e),  max_n |X[n][j]|        in [2^(e-1), 2^e)
 //   W'[k][i][j]   = W[k][i][j] r_k / sx_j,   r_k    = 2^(9 - e),  max_ij |W[k][i][j]/sx_j| in [2^(e-1), 2^e)
 //   Y'[n][(k,i)]  = sum_j X' W' = r_k Y,     epilogue: t = Y' - r_k b, q' = sum_i t^2 = r_k^2 q  (1 / r_k^2 folded into 1 / dof)
@@ -12,6 +13,19 @@
 // hi parts are normal down to 2^-23 of the largest entry and what the subnormal lo parts lose is below 2^-30 of the
 // largest term of the sum.  The scales are recomputed from the rows of the sweep itself (niw_colmax_kernel: one more
 // pass over X, 256 MB at C4), so data uploaded after bind cannot overflow them.
+//
+// Kernels of one call:  niw_colmax_kernel -> niw_convert_a16_kernel (A: hi | lo parts of every 128-row tile, in the exact
+// core-matrix bytes of a ring buffer, written once per sweep) + niw_pack_b16_kernel (B: the same for every block of 4
+// groups) -> niw_tc16_kernel:
+//   * thread 0 streams A half-tiles (16 KB) into a 6-deep shared-memory ring with bulk copies;
+//   * one lane of warp 8 keeps the current group block's B (64 KB) resident and issues the MMAs: per 128-row tile four
+//     k-steps x three products, N shrinking 256, 192, 128, 64 (W_k is lower triangular), two 256-column TMEM accumulators;
+//   * epilogue warps 4-7 (even tiles, accumulator 0) and 9-12 (odd tiles, accumulator 1): tcgen05.ld of their 32 TMEM
+//     lanes, bias, square-sum per group, log1p, store -- in the sweep's blocked layout a warp's 32 lanes are one 32-row
+//     block, so every store is a full 128-byte line;
+//   * work items = (slice of <= 32 row tiles) x (group block), dealt round-robin to the CTAs, group block fastest: even
+//     load and A shared through L2.
+// Synchronisation is mbarrier-only (bulk-copy complete_tx, tcgen05.commit); every wait is bounded (trap).
 #pragma once
 #include <cuda_fp16.h>
 
