@@ -1028,3 +1028,83 @@ def test_single_rows_through_the_tensor_core_niw_path(ctx, oracle):
     w = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, eid, eid + 1, prec=64)[0]
     assert np.max(rel_err(s, w)) < 4 * RTOL
     st.close()
+
+
+def test_gibbs_chain_over_four_entities_visits_partitions_with_their_posterior_probability(ctx):
+    # the reference validates samplers distributionally: enumerate every clustering of a few entities, compute its
+    # exact posterior, and compare with the chain's visit frequencies (microscopes/common/testutil.py:217-260,
+    # dist_on_all_clusterings / assert_discrete_dist_approx).  Here the chain is the single-entity Gibbs step
+    # (entity_state.hpp:57-72: remove_value -> score_value -> sample -> add_value) driven through the ABI.
+    from math import lgamma
+    data = np.array([[1, 1, 0], [1, 1, 1], [0, 0, 1], [0, 0, 0]], dtype=bool)
+    n, D = data.shape
+    arr = np.zeros(n, dtype=[("f%d" % d, np.bool_) for d in range(D)])
+    for d in range(D):
+        arr["f%d" % d] = data[:, d]
+    alpha = 1.5
+
+    def partitions(items):
+        if not items:
+            yield []
+            return
+        first, rest = items[0], items[1:]
+        for p in partitions(rest):
+            for i in range(len(p)):
+                yield p[:i] + [[first] + p[i]] + p[i + 1:]
+            yield [[first]] + p
+
+    def lbeta(a, b):
+        return lgamma(a) + lgamma(b) - lgamma(a + b)
+
+    def log_joint(p):   # CRP prior (up to the common normaliser) x Beta-Bernoulli evidence, alpha = beta = 1
+        s = 0.0
+        for g in p:
+            s += np.log(alpha) + lgamma(len(g))
+            for d in range(D):
+                h = int(data[g, d].sum())
+                s += lbeta(1 + h, 1 + len(g) - h) - lbeta(1, 1)
+        return s
+
+    def canon(assign):
+        seen = {}
+        return tuple(seen.setdefault(a, len(seen)) for a in assign)
+
+    exact = {}
+    for p in partitions(list(range(n))):
+        a = [0] * n
+        for gi, g in enumerate(p):
+            for e in g:
+                a[e] = gi
+        exact[canon(a)] = log_joint(p)
+    m = max(exact.values())
+    z = sum(np.exp(v - m) for v in exact.values())
+    exact = {k: float(np.exp(v - m) / z) for k, v in exact.items()}
+    assert len(exact) == 15
+
+    view = cb.numpy_dataview(arr)
+    st = cb.state(ctx, [cb.bb] * D, max_groups=8, cluster_hp={"alpha": alpha})
+    st.bind(view)
+    g0 = st.create_group()
+    st.add_values(np.full(n, g0))
+    rng = np.random.default_rng(0)
+    visits = {}
+    sweeps, burn = 2500, 100
+    for it in range(sweeps):
+        for eid in range(n):
+            old = st.remove_value(eid)
+            empties = st.empty_groups()
+            if not empties:
+                st.create_group()
+            elif len(empties) > 1:          # keep exactly one empty group, as the reference's assign kernel does
+                for g in empties[1:]:
+                    st.delete_group(g)
+            gids, s = st.score_value(eid)   # log pseudocount (alpha for the one empty group) + predictive
+            p = np.exp(np.asarray(s, np.float64) - np.max(s))
+            st.add_value(gids[int(rng.choice(len(gids), p=p / p.sum()))], eid)
+        if it >= burn:
+            key = canon(st.assignments().tolist())
+            visits[key] = visits.get(key, 0) + 1
+    st.close()
+    total = sum(visits.values())
+    worst = max(abs(visits.get(k, 0) / total - pk) for k, pk in exact.items())
+    assert worst < 0.04, (worst, {k: (round(visits.get(k, 0) / total, 3), round(pk, 3)) for k, pk in exact.items()})
