@@ -26,7 +26,7 @@
  * boundary parity is UNPINNED.  What IS pinned: bb and niw predictive against
  * the reference's own Python closed forms (vendor/stats.py, run in the build
  * container, fixtures in tests/golden/), bbnc and dm bookkeeping against runs
- * of the reference's in-tree Python models (microscopes/dbg/models/*.py ->
+ * of the reference's in-tree Python models (microscopes/dbg/models/{bbnc,dm}.py ->
  * tests/golden/intree_models.json), every family against scipy in fp64,
  * the dataview layout against the reference's real headers (oracle/_ref).
  */

@@ -158,6 +158,83 @@ struct bbnc_group : public models::group {
 };
 std::shared_ptr<models::group> bbnc_hypers::create_group(rng_t &) const { return std::make_shared<bbnc_group>(); }
 
+// ---- dm (src/models/dm.cpp restated statement by statement: its translation unit needs protobuf and `distributions`;
+// lgammaf where upstream has fast_lgamma) ------------------------------------------------------------------------
+struct dm_hypers : public models::hypers {
+  unsigned dim;
+  std::vector<float> alphas;
+  explicit dm_hypers(unsigned d) : dim(d), alphas(d, 1.f) {}
+  hyperparam_bag_t get_hp() const override { return ""; }
+  void set_hp(const hyperparam_bag_t &) override {}
+  void set_hp(const models::hypers &s) override { *this = static_cast<const dm_hypers &>(s); }
+  value_mutator get_hp_mutator(const std::string &key) override {
+    if (key == "alphas") return value_mutator(reinterpret_cast<uint8_t *>(&alphas[0]), runtime_type(TYPE_F32, dim));
+    throw std::runtime_error("unknown key: " + key);
+  }
+  std::shared_ptr<models::group> create_group(rng_t &rng) const override;
+  std::string debug_str() const override { return "dm"; }
+};
+struct dm_group : public models::group {
+  std::vector<unsigned> counts;
+  float ratio = 0.f;
+  explicit dm_group(unsigned d) : counts(d, 0) {}
+  void add_value(const models::hypers &, const value_accessor &value, rng_t &) override {  // dm.cpp:9-21
+    unsigned count_sum = 0;
+    for (size_t i = 0; i < counts.size(); i++) {
+      const unsigned ni = value.get<unsigned>(i);
+      count_sum += ni;
+      counts[i] += ni;
+      ratio -= lgammaf(ni + 1);
+    }
+    ratio += lgammaf(count_sum + 1);
+  }
+  void remove_value(const models::hypers &, const value_accessor &value, rng_t &) override {  // dm.cpp:23-36
+    unsigned count_sum = 0;
+    for (size_t i = 0; i < counts.size(); i++) {
+      const unsigned ni = value.get<unsigned>(i);
+      count_sum += ni;
+      counts[i] -= ni;
+      ratio += lgammaf(ni + 1);
+    }
+    ratio -= lgammaf(count_sum + 1);
+  }
+  float score_value(const models::hypers &m, const value_accessor &value, rng_t &) const override {  // dm.cpp:38-76
+    const dm_hypers &h = static_cast<const dm_hypers &>(m);
+    float score = 0.;
+    unsigned x_sum = 0;
+    float a_sum = 0.;
+    unsigned n_sum = 0;
+    for (size_t i = 0; i < counts.size(); i++) {
+      const unsigned xi = value.get<unsigned>(i);
+      const float ai = h.alphas[i];
+      const unsigned ni = counts[i];
+      x_sum += xi;
+      a_sum += ai;
+      n_sum += ni;
+      const float effective_ai = ai + ni;
+      score += lgammaf(effective_ai + xi) - lgammaf(effective_ai);
+      score -= lgammaf(xi + 1);
+    }
+    score += lgammaf(x_sum + 1);
+    score += lgammaf(a_sum + n_sum) - lgammaf(a_sum + n_sum + x_sum);
+    return score;
+  }
+  float score_data(const models::hypers &, rng_t &) const override { return 0.f; }
+  void sample_value(const models::hypers &, value_mutator &, rng_t &) const override {
+    throw std::runtime_error("multinomial sampling unimplemented");  // dm.cpp:100-111
+  }
+  suffstats_bag_t get_ss() const override { return ""; }
+  void set_ss(const suffstats_bag_t &) override {}
+  void set_ss(const models::group &g) override { *this = static_cast<const dm_group &>(g); }
+  value_mutator get_ss_mutator(const std::string &key) override {
+    if (key == "counts") return value_mutator(reinterpret_cast<uint8_t *>(&counts[0]), runtime_type(TYPE_U32, (unsigned)counts.size()));
+    if (key == "ratio") return value_mutator(&ratio);
+    throw std::runtime_error("unknown key: " + key);
+  }
+  std::string debug_str() const override { return "dm"; }
+};
+std::shared_ptr<models::group> dm_hypers::create_group(rng_t &) const { return std::make_shared<dm_group>(dim); }
+
 // ---- bnb ----------------------------------------------------------------------
 struct bnb_hypers : public models::hypers {
   float alpha = 1.f, beta = 1.f;
@@ -357,6 +434,7 @@ struct ref_model : public models::model {
       case ORC_GP: return std::make_shared<gp_hypers>();
       case ORC_NICH: return std::make_shared<nich_hypers>();
       case ORC_DD: return std::make_shared<dd_hypers>(m.dim);
+      case ORC_DM: return std::make_shared<dm_hypers>(m.dim);
       case ORC_NIW: return std::make_shared<niw_hypers>(m.dim);
       default: throw std::runtime_error("unknown family");
     }
@@ -367,6 +445,7 @@ struct ref_model : public models::model {
       case ORC_BNB: case ORC_GP: return runtime_type(TYPE_U32);
       case ORC_NICH: return runtime_type(TYPE_F32);
       case ORC_DD: return runtime_type(TYPE_I32);
+      case ORC_DM: return runtime_type(TYPE_I32, m.dim);  // dm.hpp:186-190
       default: return runtime_type(TYPE_F32, m.dim);
     }
   }
@@ -408,6 +487,11 @@ built_state build(const orc_model *models, size_t D, const double *hp, const dou
         break;
       }
       case ORC_NIW: static_cast<niw_hypers &>(*h).hp.assign(p, p + orc_hp_size(&models[d])); break;
+      case ORC_DM: {
+        auto mut = h->get_hp_mutator("alphas");
+        for (unsigned i = 0; i < models[d].dim; i++) mut.set<float>((float)p[i], i);
+        break;
+      }
     }
     st.hypers.push_back(h);
   }
@@ -431,6 +515,12 @@ built_state build(const orc_model *models, size_t D, const double *hp, const dou
           break;
         }
         case ORC_NIW: static_cast<niw_group &>(*g).ss.assign(s, s + orc_ss_size(&models[d])); break;
+        case ORC_DM: {
+          auto mut = g->get_ss_mutator("counts");
+          for (unsigned i = 0; i < models[d].dim; i++) mut.set<unsigned>((unsigned)s[i], i);
+          set_f(g->get_ss_mutator("ratio"), s[models[d].dim]);
+          break;
+        }
       }
       st.groups[k].push_back(g);
     }

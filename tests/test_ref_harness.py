@@ -48,3 +48,21 @@ def test_reference_api_any_storage_type(oracle, ref):
 def test_perf_group_loop_runs(ref):
     ns, score = ref.perf_group(ol.BB, 0, D=1000, niters=200)   # bin/perf_group.cpp:76-125
     assert ns > 0 and np.isfinite(score) and score < 0
+
+
+def test_reference_api_loop_with_count_vector_fields(oracle, ref):
+    # dm (src/models/dm.cpp) behind the reference's real base.hpp: value_accessor::get<unsigned>(i) over a sub-array
+    # field (runtime_value.hpp:46-54), row_accessor::bump over type.n() mask bytes (recarray/dataview.hpp:58-66)
+    descs = [cb.dm(6), cb.bb, cb.dm(3)]
+    for mask_frac in (0.0, 0.1):
+        arr, z = cb.synth.make_dataset(descs, 90, 4, seed=6, mask_frac=mask_frac)
+        view = cb.numpy_dataview(arr)
+        hp = np.concatenate([oracle.flat_hp(d) for d in descs])
+        ss, counts = ol.build_suffstats(oracle, descs, hp, view, z, 4)
+        lp = ol.logprior(counts, 1.0)
+        a = ref.score_rows(descs, hp, ss, lp, view, nthreads=2)
+        b = oracle.score_rows(descs, hp, ss, lp, view, f32=True)
+        c = oracle.score_rows(descs, hp, ss, lp, view)
+        assert np.max(np.abs(a - b) / np.maximum(1, np.abs(b))) < 2e-6   # two float restatements of dm.cpp:38-76
+        # the float formula itself: lgammaf(e + x) - lgammaf(e) cancels terms of size e log e per category (e in the hundreds)
+        assert np.max(np.abs(a - c) / np.maximum(1, np.abs(c))) < 1e-3
