@@ -328,6 +328,27 @@ class state(object):
             vals[key] = v.tolist() if n > 1 or key in ("counts", "sum_x", "sum_xxT") else float(v[0])
         return wire.encode(m.name() + ".Group", vals)
 
+    def suffstats_identifiers(self, component):
+        """entity_state.hpp:52: the identifiers under which the component's suffstats are kept -- the group ids"""
+        if not 0 <= component < len(self._models):
+            raise IndexError("bad component index")
+        return self.groups()
+
+    def set_component_hp_bag(self, component, bag):
+        """entity_state.hpp:47 / hypers::set_hp (distributions.hpp:363-369): from the component's Shared message"""
+        from . import wire
+        m = self._models[component]
+        hp = wire.decode(m.name() + ".Shared", bag)
+        self.set_component_hp(component, {k: hp[k] for k in m.default_hyperparams()})
+
+    def set_suffstats_bag(self, component, gid, bag):
+        """entity_state.hpp:54 / group::set_ss (distributions.hpp:308-314): from one group's Group message"""
+        from . import wire
+        m = self._models[component]
+        ss = wire.decode(m.name() + ".Group", bag)
+        for key in self._SS_KEYS[m.name()]:
+            self.set_suffstats(component, gid, key, ss[key])
+
     def serialize(self):
         """MixtureModelState{hypers[], groups = GroupManager{alpha, assignments[], groups[GroupData{id, data =
         MixtureModelGroup{suffstats[]}}]}} -- group_manager.hpp:285-298 with the mixture model's group payload"""
@@ -348,9 +369,7 @@ class state(object):
         ngroups = len(gm["groups"])
         st = cls(ctx, models, max_groups=max_groups or (ngroups + 8), cluster_hp={"alpha": gm["alpha"]})
         for d, bag in enumerate(top["hypers"]):
-            m = st._models[d]
-            hp = wire.decode(m.name() + ".Shared", bag)
-            st.set_component_hp(d, {k: hp[k] for k in m.default_hyperparams()})
+            st.set_component_hp_bag(d, bag)
         st.bind(view)
         for g in gm["groups"]:
             _lib.check(_lib.load().msb_state_restore_group(st._h, int(g["id"])))
@@ -360,10 +379,7 @@ class state(object):
         for g in gm["groups"]:  # ... then the suffstats exactly as they were saved
             bags = wire.decode("MixtureModelGroup", g["data"])["suffstats"]
             for d, bag in enumerate(bags):
-                m = st._models[d]
-                ss = wire.decode(m.name() + ".Group", bag)
-                for key in cls._SS_KEYS[m.name()]:
-                    st.set_suffstats(d, int(g["id"]), key, ss[key])
+                st.set_suffstats_bag(d, int(g["id"]), bag)
         return st
 
     def close(self):

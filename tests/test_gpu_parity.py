@@ -723,6 +723,12 @@ def test_checkpoint_round_trip_through_the_wire_format(ctx, oracle):
     _, S = st.score_rows()
     _, S2 = st2.score_rows()
     assert np.max(rel_err(S2, S)) < 1e-6      # float32 fields on the wire
+    assert st2.suffstats_identifiers(0) == st2.groups()
+    # one group's bag moved by hand (entity_state.hpp:53-54): get_suffstats -> set_suffstats
+    src, dst = st.groups()[0], st.groups()[1]
+    for d in range(len(descs)):
+        st2.set_suffstats_bag(d, dst, st.get_suffstats_bag(d, src))
+        assert st2.get_suffstats_bag(d, dst) == st.get_suffstats_bag(d, src)
     assert st2.create_group() == g_new + 1    # gcount = 1 + the largest identifier seen (group_manager.hpp:102-104)
     assert st2.serialize()[:40] == blob[:40]
     st.close(); st2.close()
