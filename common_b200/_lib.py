@@ -44,6 +44,12 @@ class SweepOpts(C.Structure):
 
 
 SWEEP_ASYNC = 1
+NCCL_UNIQUE_ID_BYTES = 128
+
+
+class PassOpts(C.Structure):
+    _fields_ = [("sweep", SweepOpts), ("next_data", C.c_void_p), ("next_mask", C.c_void_p), ("assign_out", C.c_void_p),
+                ("nccl_comm", C.c_void_p), ("global_rows", C.c_uint64)]
 
 
 class SweepResult(C.Structure):
@@ -61,6 +67,8 @@ _PROTOS = {
     "msb_ctx_synchronize": (C.c_int, [_P]),
     "msb_ctx_stream": (_P, [_P]),
     "msb_ctx_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "msb_ctx_profile": (C.c_int, [_P, C.c_int]),
+    "msb_ctx_profile_read": (C.c_int, [_P, C.c_char_p, _SZ, C.POINTER(_SZ)]),
     "msb_dataview_create": (C.c_int, [_P, _P, _P, _SZ, C.POINTER(RuntimeType), _SZ, C.c_int, C.POINTER(_P)]),
     "msb_dataview_upload": (C.c_int, [_P, _P, _P]),
     "msb_dataview_destroy": (C.c_int, [_P]),
@@ -111,6 +119,13 @@ _PROTOS = {
     "msb_state_delta_buffer_i32": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ)]),
     "msb_state_delta_from_i32": (C.c_int, [_P]),
     "msb_state_suffstat_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ)]),
+    "msb_nccl_version": (C.c_int, [C.POINTER(C.c_int)]),
+    "msb_nccl_unique_id": (C.c_int, [_P]),
+    "msb_nccl_comm_create": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    "msb_nccl_comm_destroy": (C.c_int, [_P]),
+    "msb_state_allreduce_deltas": (C.c_int, [_P, _P, C.c_uint64]),
+    "msb_state_last_allreduce_bytes": (C.c_int, [_P, C.POINTER(_SZ)]),
+    "msb_state_pass": (C.c_int, [_P, C.POINTER(PassOpts), C.POINTER(SweepResult)]),
     "msb_state_last_scores": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_SZ), C.POINTER(_SZ), C.POINTER(_SZ)]),
     "msb_state_read_last_scores": (C.c_int, [_P, _P, _SZ]),
     "msb_state_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), _SZ]),
@@ -189,6 +204,22 @@ class Context:
         v = C.c_uint64()
         check(load().msb_ctx_launch_count(self._h, C.byref(v)))
         return v.value
+
+    def profile(self, enable=True):
+        """per-kernel CUDA event pairs around every launch from now on (diagnostics; off by default)"""
+        check(load().msb_ctx_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """{kernel name: (launches, total ms)} of the launches recorded since profile(True)"""
+        need = _SZ()
+        check(load().msb_ctx_profile_read(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value + 16)
+        check(load().msb_ctx_profile_read(self._h, buf, len(buf), C.byref(need)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit("\t", 2)
+            out[name.strip("()")] = (int(cnt), float(ms))
+        return out
 
     def close(self):
         if self._h:

@@ -1,9 +1,48 @@
 // msb_kernels.cuh -- sm_100a kernels of the hot path (see DESIGN.md for the
 // data layout, the per-kernel roofline and the algorithmic bytes).
 #pragma once
+#include <string>
+#include <vector>
+
 #include "msb_math.cuh"
 
 namespace msb {
+
+// Optional per-kernel timing (msb_ctx_profile): a CUDA event pair around every launch while it is switched on.
+// Off by default -- nothing is recorded on the hot path.  Used by bench.py for one extra, untimed step so that the
+// bandwidth-bound kernels (ingest, sampler, update, conversions) can each be reported against the HBM roof.
+struct KernelProf {
+  struct Rec { const char *name; cudaEvent_t a, b; };
+  bool on = false;
+  cudaStream_t stream = nullptr;
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t take() {
+    cudaEvent_t e = nullptr;
+    if (!pool.empty()) { e = pool.back(); pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+  }
+  void begin(const char *name, cudaStream_t s) {
+    if (!on) return;
+    Rec r{name, take(), take()};
+    cudaEventRecord(r.a, s);
+    recs.push_back(r);
+  }
+  void end(cudaStream_t s) {
+    if (!on || recs.empty()) return;
+    cudaEventRecord(recs.back().b, s);
+  }
+  void clear() {
+    for (auto &r : recs) { pool.push_back(r.a); pool.push_back(r.b); }
+    recs.clear();
+  }
+  void destroy() {
+    clear();
+    for (auto e : pool) cudaEventDestroy(e);
+    pool.clear();
+  }
+};
 
 enum Kind : int { KIND_TABLE = 0, KIND_GP = 1, KIND_NICH = 2, KIND_NIW = 3, KIND_DM = 4,
                   KIND_BIN = 5 };  // KIND_BIN: score-kernel-local code of a KIND_TABLE feature in binary form (FeatDev::binform)

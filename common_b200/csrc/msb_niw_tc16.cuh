@@ -437,32 +437,46 @@ static inline int niw_tc16_init(size_t smem_optin, std::string &err) {
 // operand scratch of the fp16 path inside the buffer niw_tc_operand_bytes() sizes (the tf32 operands are twice as big):
 // [colmax: D u32][D f32 unused][rinv: nGB x TN f32, 2 used per group][B blocks: nGB x B_BYTES]
 static inline size_t niw_tc16_a_bytes(size_t nrows) { return ((nrows + niwtc16::TM - 1) / niwtc16::TM) * (size_t)(4 * niwtc16::A_HALF_BYTES); }
-static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, const float *X, const float *W, const float *bias,
+static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, KernelProf *prof, const float *X, const float *W, const float *bias,
                                  const float *coef, float *Bop, unsigned char *A16, size_t ncols, float *scores, size_t ld,
                                  size_t row_lo, size_t row_hi, int sm_count, const float *base, bool blocked, std::string &err) {
   using namespace niwtc16;
+  static const bool no_tri = getenv("MSB_NIW_NO_TRI") != nullptr;  // diagnostics switch, read once
   const int nGB = (int)((ncols + GB - 1) / GB);
   unsigned int *colmax = reinterpret_cast<unsigned int *>(Bop);
   float *rinv = Bop + 2 * D;
   unsigned char *Bblk = reinterpret_cast<unsigned char *>(Bop) + (2 * D + (size_t)nGB * TN) * sizeof(float);  // 512 + nGB KB: 16-byte aligned
-  cudaMemsetAsync(colmax, 0, D * sizeof(unsigned int), stream);
+  auto check = [&](const char *what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return MSB_OK;
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return MSB_ERR_CUDA;
+  };
+  if (cudaMemsetAsync(colmax, 0, D * sizeof(unsigned int), stream) != cudaSuccess) return check("niw_tc16_score: cudaMemsetAsync");
   const size_t nrows = row_hi - row_lo;
   const long long nRT = (long long)((nrows + TM - 1) / TM);
   const unsigned cm_grid = (unsigned)std::min<size_t>((nrows + 15) / 16, (size_t)sm_count * 8);
+  prof->begin("niw_colmax_kernel", stream);
   niw_colmax_kernel<<<cm_grid, 256, 0, stream>>>(X, row_lo, row_hi, colmax);
+  prof->end(stream); (*launches)++;
+  if (int s = check("niw_colmax_kernel launch")) return s;
+  prof->begin("niw_convert_a16_kernel", stream);
   niw_convert_a16_kernel<<<(unsigned)nRT, 256, 0, stream>>>(X, row_lo, row_hi, colmax, A16);
+  prof->end(stream); (*launches)++;
+  if (int s = check("niw_convert_a16_kernel launch")) return s;
+  prof->begin("niw_pack_b16_kernel", stream);
   niw_pack_b16_kernel<<<nGB, 256, 0, stream>>>(W, (int)ncols, colmax, Bblk, rinv);
-  (*launches) += 3;
+  prof->end(stream); (*launches)++;
+  if (int s = check("niw_pack_b16_kernel launch")) return s;
   // about 24 items per CTA (at most 32 tiles per slice): balance to within a few percent, one B reload per item
   const int SL = (int)std::max<long long>(1, std::min<long long>(32, nRT * nGB / ((long long)sm_count * 24)));
   const long long nItems = ((nRT + SL - 1) / SL) * nGB;
   const int grid = (int)std::min<long long>(sm_count, nItems);
+  prof->begin("niw_tc16_kernel", stream);
   niw_tc16_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(A16, Bblk, rinv, bias, coef, (int)ncols, scores, ld, row_lo, row_hi, SL,
-                                                         base, (blocked ? 1 : 0) | (getenv("MSB_NIW_NO_TRI") ? 4 : 0));
-  (*launches)++;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { err = std::string("niw_tc16_kernel launch: ") + cudaGetErrorString(e); return MSB_ERR_CUDA; }
-  return MSB_OK;
+                                                         base, (blocked ? 1 : 0) | (no_tri ? 4 : 0));
+  prof->end(stream); (*launches)++;
+  return check("niw_tc16_kernel launch");
 }
 
 }  // namespace msb

@@ -3,6 +3,9 @@
 // msb_kernels.cuh / msb_niw_tc.cuh on the context's CUDA stream.
 #include "../../include/mscope_b200.h"
 
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is resolved at run time (nccl_api below), never linked
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -55,6 +58,7 @@ struct msb_ctx {
   uint64_t launches = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
+  KernelProf prof;  // msb_ctx_profile: per-kernel event pairs, off by default
 };
 
 struct msb_dataview {
@@ -166,11 +170,14 @@ struct msb_state {
   std::vector<PhaseEvents> events[TIMING_RING];
   size_t ring_nchunks[TIMING_RING] = {0};
   uint64_t sweep_seq = 0;  // sweeps enqueued so far
+  size_t last_allreduce_bytes = 0;  // message size of the last msb_state_allreduce_deltas
 };
 
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
   do {                                                                   \
+    (ctx)->prof.begin(#kernel, (ctx)->stream);                           \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);     \
+    (ctx)->prof.end((ctx)->stream);                                      \
     (ctx)->launches++;                                                   \
     CU_TRY(cudaGetLastError());                                          \
   } while (0)
@@ -251,6 +258,7 @@ extern "C" MSB_API int msb_ctx_destroy(msb_ctx *ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->prof.destroy();
   delete ctx;
   return MSB_OK;
 }
@@ -264,6 +272,47 @@ extern "C" MSB_API void *msb_ctx_stream(msb_ctx *ctx) { return ctx ? (void *)ctx
 extern "C" MSB_API int msb_ctx_launch_count(msb_ctx *ctx, uint64_t *out) {
   REQUIRE(ctx && out, "NULL argument");
   *out = ctx->launches;
+  return MSB_OK;
+}
+
+// Per-kernel timing.  enable != 0: forget earlier records and put an event pair around every kernel launched on the
+// context's compute stream from now on; enable == 0: stop recording (the records stay readable).
+extern "C" MSB_API int msb_ctx_profile(msb_ctx *ctx, int enable) {
+  REQUIRE(ctx, "ctx is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (enable) { CU_TRY(cudaStreamSynchronize(ctx->stream)); ctx->prof.clear(); }
+  ctx->prof.on = enable != 0;
+  return MSB_OK;
+}
+// Text, one line per kernel name in first-launch order: "name\tlaunches\ttotal_ms\n".  *needed = bytes including the
+// terminating 0; the text is truncated to cap.
+extern "C" MSB_API int msb_ctx_profile_read(msb_ctx *ctx, char *buf, size_t cap, size_t *needed) {
+  REQUIRE(ctx && needed, "NULL argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<size_t> cnt;
+  for (auto &r : ctx->prof.recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+    size_t i = 0;
+    for (; i < names.size(); i++) if (names[i] == r.name) break;
+    if (i == names.size()) { names.push_back(r.name); ms.push_back(0.0); cnt.push_back(0); }
+    ms[i] += t; cnt[i]++;
+  }
+  std::string out;
+  for (size_t i = 0; i < names.size(); i++) {
+    char line[512];
+    snprintf(line, sizeof line, "%s\t%zu\t%.6f\n", names[i].c_str(), cnt[i], ms[i]);
+    out += line;
+  }
+  *needed = out.size() + 1;
+  if (buf && cap) {
+    const size_t m = std::min(cap - 1, out.size());
+    memcpy(buf, out.data(), m);
+    buf[m] = 0;
+  }
   return MSB_OK;
 }
 
@@ -1289,7 +1338,12 @@ static int build_params(msb_state *st) {
       const FeatDev &f = st->feats[d];
       if (f.kind != KIND_NIW) continue;
       if (st->niw_cols_cap < K || !st->d_niwW[d]) {
-        cudaFree(st->d_niwW[d]); cudaFree(st->d_niwBias[d]); cudaFree(st->d_niwCoef[d]); cudaFree(st->d_niwB[d]);
+        // growing K on the sweep path: the kernels of earlier sweeps may still read the old buffers
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        CU_TRY(cudaFree(st->d_niwW[d])); st->d_niwW[d] = nullptr;
+        CU_TRY(cudaFree(st->d_niwBias[d])); st->d_niwBias[d] = nullptr;
+        CU_TRY(cudaFree(st->d_niwCoef[d])); st->d_niwCoef[d] = nullptr;
+        CU_TRY(cudaFree(st->d_niwB[d])); st->d_niwB[d] = nullptr;
         const size_t cap = st->ld + 64;
         CU_TRY(cudaMalloc(&st->d_niwW[d], sizeof(float) * cap * f.dim * f.dim));
         CU_TRY(cudaMalloc(&st->d_niwBias[d], sizeof(float) * cap * f.dim));
@@ -1387,7 +1441,7 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
         CU_TRY(cudaMalloc(&st->d_niwA16, a_bytes));
         st->niw_a16_cap = a_bytes;
       }
-      MSB_TRY(niw_tc16_score(ctx->stream, &ctx->launches, (const float *)f.scol, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
+      MSB_TRY(niw_tc16_score(ctx->stream, &ctx->launches, &ctx->prof, (const float *)f.scol, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
                              st->d_niwB[d], (unsigned char *)st->d_niwA16, K, scores, st->ld, row_lo, row_hi, ctx->sm_count,
                              need_init ? st->d_base : nullptr, blocked, g_last_error));
       done = true;
@@ -1931,6 +1985,125 @@ extern "C" MSB_API int msb_selftest_division(msb_ctx *ctx, uint64_t seed, size_t
   return MSB_OK;
 }
 
+// ---- NCCL: the one exchange step of the path -------------------------------------------------
+// Rows are sharded, every rank holds a full replica of the suffstats, and one all-reduce(sum) of the flat delta buffer
+// per sweep keeps the replicas identical.  The NCCL library is resolved at run time: a host process that already has
+// one loaded (PyTorch ships its own libnccl.so.2) must keep using that copy, so the library is looked up among the
+// loaded objects first and dlopen'ed only when there is none.
+struct NcclApi {
+  bool ok = false;
+  std::string err;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommCount)(const ncclComm_t, int *) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GetVersion)(int *) = nullptr;
+};
+static NcclApi &nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { api.err = std::string("NCCL is not available: ") + dlerror(); return api; }
+#define MSB_NCCL_SYM(field, name)                                         \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name));      \
+  if (!api.field) { api.err = std::string("NCCL symbol missing: ") + name; return api; }
+  MSB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+  MSB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  MSB_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  MSB_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  MSB_NCCL_SYM(CommCount, "ncclCommCount")
+  MSB_NCCL_SYM(AllReduce, "ncclAllReduce")
+  MSB_NCCL_SYM(GetVersion, "ncclGetVersion")
+#undef MSB_NCCL_SYM
+  api.ok = true;
+  return api;
+}
+#define NCCL_TRY(expr)                                                                                        \
+  do {                                                                                                        \
+    ncclResult_t _r = (expr);                                                                                 \
+    if (_r != ncclSuccess) return fail(MSB_ERR_CUDA, std::string(#expr) + ": " + nccl_api().GetErrorString(_r)); \
+  } while (0)
+
+extern "C" MSB_API int msb_nccl_version(int *version) {
+  REQUIRE(version, "NULL argument");
+  NcclApi &n = nccl_api();
+  if (!n.ok) return fail(MSB_ERR_UNSUPPORTED, n.err);
+  NCCL_TRY(n.GetVersion(version));
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_nccl_unique_id(void *id128) {
+  REQUIRE(id128, "NULL argument");
+  NcclApi &n = nccl_api();
+  if (!n.ok) return fail(MSB_ERR_UNSUPPORTED, n.err);
+  static_assert(sizeof(ncclUniqueId) == MSB_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  NCCL_TRY(n.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_nccl_comm_create(msb_ctx *ctx, int nranks, int rank, const void *id128, void **comm) {
+  REQUIRE(ctx && id128 && comm, "NULL argument");
+  REQUIRE(nranks > 0 && rank >= 0 && rank < nranks, "bad rank");
+  NcclApi &n = nccl_api();
+  if (!n.ok) return fail(MSB_ERR_UNSUPPORTED, n.err);
+  CU_TRY(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  ncclComm_t c = nullptr;
+  NCCL_TRY(n.CommInitRank(&c, nranks, id, rank));
+  *comm = c;
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_nccl_comm_destroy(void *comm) {
+  if (!comm) return MSB_OK;
+  NcclApi &n = nccl_api();
+  if (!n.ok) return fail(MSB_ERR_UNSUPPORTED, n.err);
+  NCCL_TRY(n.CommDestroy((ncclComm_t)comm));
+  return MSB_OK;
+}
+
+// every suffstat of the state is a count of rows (bb heads / tails, dd counts): the deltas are integers bounded by the
+// GLOBAL row count, so they cross the wire as exact int32 when that count fits
+static bool counts_only(const msb_state *st) {
+  for (const auto &m : st->models)
+    if (m.family != MSB_FAMILY_BB && m.family != MSB_FAMILY_DD) return false;  // (bbnc's p is not a count)
+  return true;
+}
+
+// Sum the pending suffstat deltas over the ranks of `comm` on the context's stream and apply the sum to the resident
+// suffstats: afterwards every replica holds the same state.  global_rows = rows over ALL ranks (0 = unknown: fp64
+// deltas).  Every rank must pass the same value -- the element type of the collective depends on it.
+extern "C" MSB_API int msb_state_allreduce_deltas(msb_state *st, void *nccl_comm, uint64_t global_rows) {
+  REQUIRE(st && nccl_comm, "NULL argument");
+  NcclApi &n = nccl_api();
+  if (!n.ok) return fail(MSB_ERR_UNSUPPORTED, n.err);
+  msb_ctx *ctx = st->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  static const bool no_i32 = getenv("MSB_NO_I32_DELTAS") != nullptr;
+  const bool i32 = counts_only(st) && global_rows > 0 && global_rows < (1ull << 31) && !no_i32;
+  if (i32) {
+    if (!st->d_delta_i32) CU_TRY(cudaMalloc(&st->d_delta_i32, sizeof(int32_t) * st->SS));
+    LAUNCH(ctx, delta_to_i32_kernel, cdiv(st->SS, 256), 256, 0, st->d_delta, st->SS, st->d_delta_i32);
+    NCCL_TRY(n.AllReduce(st->d_delta_i32, st->d_delta_i32, st->SS, ncclInt32, ncclSum, (ncclComm_t)nccl_comm, ctx->stream));
+    LAUNCH(ctx, delta_from_i32_kernel, cdiv(st->SS, 256), 256, 0, st->d_delta_i32, st->SS, st->d_delta);
+  } else {
+    NCCL_TRY(n.AllReduce(st->d_delta, st->d_delta, st->SS, ncclFloat64, ncclSum, (ncclComm_t)nccl_comm, ctx->stream));
+  }
+  st->last_allreduce_bytes = st->SS * (i32 ? sizeof(int32_t) : sizeof(double));
+  return apply_deltas(st);
+}
+extern "C" MSB_API int msb_state_last_allreduce_bytes(msb_state *st, size_t *bytes) {
+  REQUIRE(st && bytes, "NULL argument");
+  *bytes = st->last_allreduce_bytes;
+  return MSB_OK;
+}
+
 // ---- sweep -------------------------------------------------------------------------
 extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_hi, const msb_sweep_opts *opts,
                                msb_sweep_result *res) {
@@ -2034,6 +2207,31 @@ extern "C" MSB_API int msb_state_sweep_wait(msb_state *st, msb_sweep_result *res
   CU_TRY(cudaStreamSynchronize(st->ctx->stream));
   st->last_res.moved = *st->h_moved;
   if (res) *res = st->last_res;
+  return MSB_OK;
+}
+
+// ---- one pass over host rows in ONE call ---------------------------------------------------------------------------
+// What a caller that re-reads its host rows on every pass (the reference does: recarray/dataview.hpp:194-217) would
+// otherwise issue as six calls: refresh (this pass's columns become current) -> upload + prefetch of the NEXT pass's
+// records on the copy stream -> sweep (+ the delta all-reduce when a communicator is given) -> wait for the previous
+// pass's assignments -> start the copy of this pass's assignments.  Nothing in it waits for the compute stream.
+extern "C" MSB_API int msb_state_pass(msb_state *st, const msb_pass_opts *opts, msb_sweep_result *res) {
+  REQUIRE(st && opts, "NULL argument");
+  REQUIRE(st->dv, "no dataview bound");
+  MSB_TRY(msb_state_refresh(st));
+  if (opts->next_data) {
+    MSB_TRY(msb_dataview_upload(st->dv, opts->next_data, opts->next_mask));
+    MSB_TRY(msb_state_prefetch(st));
+  }
+  msb_sweep_opts so = opts->sweep;
+  so.flags |= MSB_SWEEP_ASYNC;
+  if (opts->nccl_comm) so.defer_apply = 1;
+  MSB_TRY(msb_state_sweep(st, 0, st->n, &so, res));
+  if (opts->nccl_comm) MSB_TRY(msb_state_allreduce_deltas(st, opts->nccl_comm, opts->global_rows));
+  if (opts->assign_out) {
+    MSB_TRY(msb_state_assignments_wait(st));
+    MSB_TRY(msb_state_assignments_async(st, opts->assign_out, st->n));
+  }
   return MSB_OK;
 }
 

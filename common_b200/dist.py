@@ -26,8 +26,52 @@ def shard_rows(n_total, rank, world):
     return lo, hi
 
 
-def allreduce_deltas(st, device):
-    """sum the flat fp64 delta buffer over all ranks, then apply it on every replica"""
+class NcclComm(object):
+    """an ncclComm_t created through the C ABI (msb_nccl_comm_create): the collective of the path then runs inside the
+    library (msb_state_allreduce_deltas) on the context's stream.  The 128-byte unique id travels from rank 0 to the
+    other ranks through ``exchange`` (default: torch.distributed's object broadcast -- plumbing only)."""
+
+    def __init__(self, ctx, rank, world, exchange=None):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        buf = C.create_string_buffer(_lib.NCCL_UNIQUE_ID_BYTES)
+        if rank == 0:
+            _lib.check(lib.msb_nccl_unique_id(buf))
+        raw = bytes(buf.raw)
+        if exchange is None:
+            import torch.distributed as dist
+            box = [raw]
+            dist.broadcast_object_list(box, src=0)
+            raw = box[0]
+        else:
+            raw = exchange(raw)
+        h = C.c_void_p()
+        _lib.check(lib.msb_nccl_comm_create(ctx.handle, int(world), int(rank), raw, C.byref(h)))
+        self.handle = h
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if self.handle:
+            from . import _lib
+            _lib.load().msb_nccl_comm_destroy(self.handle)
+            self.handle = None
+
+
+def nccl_version():
+    import ctypes as C
+    from . import _lib
+    v = C.c_int()
+    _lib.check(_lib.load().msb_nccl_version(C.byref(v)))
+    return v.value
+
+
+def allreduce_deltas(st, device, comm=None, global_rows=0):
+    """sum the flat delta buffer over all ranks, then apply it on every replica.  With ``comm`` (NcclComm) the
+    collective runs inside the library; without, torch.distributed carries it (gloo in the CPU tests)."""
+    if comm is not None:
+        st.allreduce_deltas(comm, global_rows)
+        return
     import torch.distributed as dist
     ptr32, n = st.delta_buffer_i32()
     if ptr32:  # every suffstat is a count of rows: exact int32 deltas, half the bytes on the wire
@@ -41,12 +85,12 @@ def allreduce_deltas(st, device):
     st.apply_deltas()
 
 
-def add_values_sharded(st, gids, device):
+def add_values_sharded(st, gids, device, comm=None, global_rows=0):
     """replica initialisation through the delta buffer: every rank adds its own rows (deferred), the deltas are
     summed, every replica applies the sum.  Unlike summing the suffstat buffers this never touches per-group
     parameters that are not sums over rows (bbnc's p)."""
     st.add_values(gids, defer_apply=True)
-    allreduce_deltas(st, device)
+    allreduce_deltas(st, device, comm, global_rows)
 
 
 def allreduce_suffstats(st, device):

@@ -291,6 +291,33 @@ class state(object):
     def apply_deltas(self):
         _lib.check(_lib.load().msb_state_apply_deltas(self._h))
 
+    def allreduce_deltas(self, comm, global_rows=0):
+        """ncclAllReduce(sum) of the pending deltas inside the library (comm: dist.NcclComm or a raw ncclComm_t),
+        then apply: every replica ends with the same suffstats"""
+        h = comm.handle if hasattr(comm, "handle") else comm
+        _lib.check(_lib.load().msb_state_allreduce_deltas(self._h, h, int(global_rows)))
+
+    def last_allreduce_bytes(self):
+        v = C.c_size_t()
+        _lib.check(_lib.load().msb_state_last_allreduce_bytes(self._h, C.byref(v)))
+        return v.value
+
+    def run_pass(self, seed=0, sweep=0, row_id_offset=0, next_data=None, next_mask=None, assign_out=None, comm=None,
+                 global_rows=0):
+        """one pass over host rows in one ABI call (msb_state_pass): refresh -> upload + prefetch of the next pass's
+        records -> asynchronous sweep (-> delta all-reduce) -> assignments of this pass on their way to ``assign_out``
+        (a pinned int64 array); next_data / next_mask are host addresses (pinned)"""
+        po = _lib.PassOpts()
+        po.sweep = _lib.SweepOpts(int(seed), int(sweep), int(row_id_offset), None, 0, 0)
+        po.next_data = next_data
+        po.next_mask = next_mask
+        po.assign_out = assign_out.ctypes.data if assign_out is not None else None
+        po.nccl_comm = (comm.handle if hasattr(comm, "handle") else comm) if comm is not None else None
+        po.global_rows = int(global_rows)
+        res = _lib.SweepResult()
+        _lib.check(_lib.load().msb_state_pass(self._h, C.byref(po), C.byref(res)))
+        return {"rows": res.rows, "moved": res.moved, "units": res.units}
+
     def sample_value(self, component, gid, seed, counter=0, n=1):
         """group::sample_value (models/base.hpp:29) for one (feature, group): ``n`` draws from the posterior predictive,
         draw i from the Philox stream (seed, counter + i).  Returns an array of n values (n x dim for niw)."""

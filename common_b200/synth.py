@@ -74,7 +74,9 @@ def make_dataset(models, n, k_true, seed=73, stream=0, mask_frac=0.0, storage=No
             A = prng.standard_normal((k_true, dim, dim))
             L = np.linalg.cholesky(A @ A.transpose(0, 2, 1) / dim + 0.1 * np.eye(dim))
             e = rng.standard_normal((n, dim))
-            x = mu[z] + np.einsum("nij,nj->ni", L[z], e)
+            x = np.empty((n, dim))
+            for g in range(k_true):  # z = row mod K: the rows of group g are g, g + K, ...  (no N x d x d gather of L[z])
+                x[g::k_true] = mu[g] + e[g::k_true] @ L[g].T
             dt = np.dtype((np.float32, (dim,)))
         else:
             raise ValueError(name)

@@ -119,6 +119,11 @@ MSB_API int msb_ctx_synchronize(msb_ctx *ctx);
 MSB_API void *msb_ctx_stream(msb_ctx *ctx);
 /* number of kernels this library has launched on ctx since creation */
 MSB_API int msb_ctx_launch_count(msb_ctx *ctx, uint64_t *out);
+/* diagnostics (the reference's only profiling is common/timer.hpp:20-126 around its loop): enable != 0 puts a CUDA event
+ * pair around every kernel launched on the context's stream from now on (earlier records are dropped); 0 stops.
+ * msb_ctx_profile_read: one text line per kernel, "name\tlaunches\ttotal_ms\n"; *needed = bytes incl. the final 0. */
+MSB_API int msb_ctx_profile(msb_ctx *ctx, int enable);
+MSB_API int msb_ctx_profile_read(msb_ctx *ctx, char *buf, size_t cap, size_t *needed);
 
 /* ---- dataview (recarray/dataview.hpp:194-217) --------------------------- */
 /* data: n records, AoS, field offsets = running sum of type sizes
@@ -259,6 +264,36 @@ MSB_API int msb_state_delta_buffer_i32(msb_state *st, int32_t **dev_ptr, size_t 
 MSB_API int msb_state_delta_from_i32(msb_state *st);
 /* the resident suffstats themselves, same layout (replica initialisation: all-reduce, then apply_deltas) */
 MSB_API int msb_state_suffstat_buffer(msb_state *st, double **dev_ptr, size_t *count);
+
+/* ---- the exchange step (rows sharded over the GPUs of one box, suffstat replicas) ----------
+ * NCCL is resolved at run time (the copy already loaded in the process, else libnccl.so.2); MSB_ERR_UNSUPPORTED
+ * when there is none.  A host that already owns an ncclComm_t passes it as nccl_comm; the helpers below create
+ * one from a 128-byte ncclUniqueId that rank 0 generates and hands to the other ranks by its own means. */
+#define MSB_NCCL_UNIQUE_ID_BYTES 128
+MSB_API int msb_nccl_version(int *version);
+MSB_API int msb_nccl_unique_id(void *id128);
+MSB_API int msb_nccl_comm_create(msb_ctx *ctx, int nranks, int rank, const void *id128, void **nccl_comm);
+MSB_API int msb_nccl_comm_destroy(void *nccl_comm);
+/* ncclAllReduce(sum) of the pending suffstat deltas on the context's stream, then msb_state_apply_deltas: every
+ * replica ends with the same suffstats.  global_rows = rows over ALL ranks (every rank passes the same value);
+ * count-valued states (every feature bb or dd) whose global row count fits int32 exchange exact int32 deltas,
+ * anything else fp64.  nccl_comm is an ncclComm_t. */
+MSB_API int msb_state_allreduce_deltas(msb_state *st, void *nccl_comm, uint64_t global_rows);
+MSB_API int msb_state_last_allreduce_bytes(msb_state *st, size_t *bytes);
+
+/* one pass over host rows in one call: msb_state_refresh -> msb_dataview_upload(next_data, next_mask) +
+ * msb_state_prefetch (skipped when next_data is NULL) -> msb_state_sweep over every row, asynchronous
+ * (-> msb_state_allreduce_deltas when nccl_comm is given) -> msb_state_assignments_wait + _async into assign_out
+ * (pinned, n int64; skipped when NULL).  Returns without waiting for the compute stream. */
+typedef struct msb_pass_opts {
+  msb_sweep_opts sweep;
+  const void *next_data;  /* host records of the NEXT pass (pinned), or NULL */
+  const void *next_mask;
+  int64_t *assign_out;    /* or NULL */
+  void *nccl_comm;        /* ncclComm_t or NULL */
+  uint64_t global_rows;   /* rows over all ranks (see msb_state_allreduce_deltas) */
+} msb_pass_opts;
+MSB_API int msb_state_pass(msb_state *st, const msb_pass_opts *opts, msb_sweep_result *res);
 
 /* device pointer + leading dimension of the scores the last sweep/score wrote (diagnostics, tests) */
 MSB_API int msb_state_last_scores(msb_state *st, float **dev_ptr, size_t *ld, size_t *nrows, size_t *ncols);

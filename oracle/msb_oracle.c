@@ -678,6 +678,29 @@ void orc_sample_rows(const float *scores, size_t nrows, size_t K, size_t ld, con
   for (size_t i = 0; i < nrows; i++) out[i] = (int32_t)orc_sample_discrete_log(scores + i * ld, K, u[i]);
 }
 
+/* The same walk with the C library's expf, i.e. exactly what the reference executes (util.hpp:131 calls expf from
+ * <cmath>).  The device cannot run glibc's expf, so the bit-exact contract is stated against orc_expf above; this
+ * variant exists to MEASURE how often the two exponentials lead to a different draw on given scores (bench.py's
+ * parity record, tests/test_oracle.py). */
+int64_t orc_sample_discrete_log_libm(const float *scores, size_t K, float u) {
+  if (K == 0) return -1;
+  float m = scores[0];
+  for (size_t k = 1; k < K; k++) if (scores[k] > m) m = scores[k];
+  double acc_d = 0.0;
+  for (size_t k = 0; k < K; k++) acc_d += (double)expf(scores[k] - m);
+  const float acc = (float)acc_d;
+  float dart = u;
+  for (size_t k = 0; k < K; k++) {
+    float p = expf(scores[k] - m) / acc;
+    dart -= p;
+    if (dart <= 0.f) return (int64_t)k;
+  }
+  return (int64_t)K - 1;
+}
+void orc_sample_rows_libm(const float *scores, size_t nrows, size_t K, size_t ld, const float *u, int32_t *out) {
+  for (size_t i = 0; i < nrows; i++) out[i] = (int32_t)orc_sample_discrete_log_libm(scores + i * ld, K, u[i]);
+}
+
 /* Philox4x32-10 (Salmon et al., SC'11): key = seed, counter = (row lo, row hi, sweep lo, sweep hi) */
 void orc_philox_raw(uint64_t seed, uint64_t row, uint64_t sweep, uint32_t out[4]) {
   uint32_t c0 = (uint32_t)row, c1 = (uint32_t)(row >> 32), c2 = (uint32_t)sweep, c3 = (uint32_t)(sweep >> 32);
@@ -695,6 +718,9 @@ float orc_philox_u01(uint64_t seed, uint64_t row, uint64_t sweep) {
   uint32_t r[4];
   orc_philox_raw(seed, row, sweep, r);
   return (float)(r[0] >> 8) * 5.9604644775390625e-8f; /* 2^-24, in [0,1) */
+}
+void orc_philox_u01_rows(uint64_t seed, uint64_t row_lo, size_t n, uint64_t sweep, float *out) {
+  for (size_t i = 0; i < n; i++) out[i] = orc_philox_u01(seed, row_lo + i, sweep);
 }
 
 /* ---- group::sample_value (models/base.hpp:29; distributions.hpp:293-298; bbnc.cpp:75-83; dm.cpp:100-111) ----------

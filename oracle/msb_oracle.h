@@ -76,7 +76,11 @@ void orc_score_rows_f32(const orc_model *models, size_t D, const double *hp, con
 float orc_expf(float x);
 int64_t orc_sample_discrete_log(const float *scores, size_t K, float u);
 void orc_sample_rows(const float *scores, size_t nrows, size_t K, size_t ld, const float *u, int32_t *out);
+/* the same with glibc's expf (what util.hpp:131 really calls): to measure how often a draw differs */
+int64_t orc_sample_discrete_log_libm(const float *scores, size_t K, float u);
+void orc_sample_rows_libm(const float *scores, size_t nrows, size_t K, size_t ld, const float *u, int32_t *out);
 float orc_philox_u01(uint64_t seed, uint64_t row, uint64_t sweep);
+void orc_philox_u01_rows(uint64_t seed, uint64_t row_lo, size_t n, uint64_t sweep, float *out);
 void orc_philox_raw(uint64_t seed, uint64_t row, uint64_t sweep, uint32_t out[4]);
 
 /* apply remove(old)/add(new) for every row of [row_lo,row_hi) in row order.

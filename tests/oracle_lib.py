@@ -47,6 +47,10 @@ class Oracle(object):
         lib.orc_sample_rows.restype = None
         lib.orc_sample_rows.argtypes = [_P, _SZ, _SZ, _SZ, _P, _P]
         lib.orc_philox_u01.restype = C.c_float; lib.orc_philox_u01.argtypes = [C.c_uint64] * 3
+        lib.orc_sample_rows_libm.restype = None
+        lib.orc_sample_rows_libm.argtypes = [_P, _SZ, _SZ, _SZ, _P, _P]
+        lib.orc_philox_u01_rows.restype = None
+        lib.orc_philox_u01_rows.argtypes = [C.c_uint64, C.c_uint64, _SZ, C.c_uint64, _P]
         lib.orc_philox_raw.restype = None; lib.orc_philox_raw.argtypes = [C.c_uint64] * 3 + [_P]
 
     # -- models ------------------------------------------------------------
@@ -167,6 +171,18 @@ class Oracle(object):
         s = np.ascontiguousarray(scores, np.float32); u = np.ascontiguousarray(u, np.float32)
         out = np.zeros(s.shape[0], np.int32)
         self.lib.orc_sample_rows(s.ctypes.data, s.shape[0], s.shape[1], s.shape[1], u.ctypes.data, out.ctypes.data)
+        return out
+
+    def sample_rows_libm(self, scores, u):
+        """the same walk with glibc's expf (util.hpp:131): how often does the exponential change a draw?"""
+        s = np.ascontiguousarray(scores, np.float32); u = np.ascontiguousarray(u, np.float32)
+        out = np.zeros(s.shape[0], np.int32)
+        self.lib.orc_sample_rows_libm(s.ctypes.data, s.shape[0], s.shape[1], s.shape[1], u.ctypes.data, out.ctypes.data)
+        return out
+
+    def philox_u01_rows(self, seed, row_lo, n, sweep):
+        out = np.zeros(n, np.float32)
+        self.lib.orc_philox_u01_rows(seed, row_lo, n, sweep, out.ctypes.data)
         return out
 
     def philox_u01(self, seed, row, sweep):
