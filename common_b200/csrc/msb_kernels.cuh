@@ -76,6 +76,12 @@ struct FeatDev {
   uint64_t msk_off;
   uint32_t src_prim;
   uint32_t src_n;
+  // score_bundle_kernel: where the feature sits inside the shared-memory stage of its bundle (laid out by the host for
+  // the tile shape in use), and whether it closes the bundle
+  uint32_t sx_off;
+  uint32_t sc_off;
+  uint32_t bundle_last;
+  uint32_t fuse;      // first feature of a fused quad [bb in binary form, table, table, nich] (all four in one bundle)
 };
 
 __device__ __forceinline__ void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }

@@ -56,6 +56,10 @@ struct FeatS {
   uint32_t ncat;
   uint16_t kind;
   uint16_t has_slow;
+  uint32_t sx_off;           // score_bundle_kernel: offset of this feature's row values inside its stage
+  uint32_t sc_off;           //                      offset of its parameter chunk
+  uint32_t last;             //                      last feature of its bundle
+  uint32_t fuse;             //                      first feature of a fused quad [bin, table, table, nich]
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -253,6 +257,7 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
     t.scol = f.scol; t.slowmask = f.slowmask; t.col = f.col;
     t.rowoff = f.rowoff; t.rows = f.rows; t.ncat = f.ncat;
     t.kind = (uint16_t)((f.kind == KIND_TABLE && f.binform) ? KIND_BIN : f.kind); t.has_slow = (uint16_t)(f.has_slow != 0);
+    t.sx_off = t.sc_off = 0; t.last = 1; t.fuse = 0;
     ftab[i] = t;
   }
   if (tid == 0) {
@@ -572,6 +577,404 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
       for (int r = 0; r < 32; r++)
 #pragma unroll
         for (int v = 0; v < V; v++) tile[r * (KT + 1) + lane * V + v] = acc[j * 32 + r][v] + b.v[v];
+      __syncwarp();
+      const size_t rb = (row0 - row_org) / 32 + j;
+      if (row0 + (size_t)j * 32 < row_hi) {
+        float *dst = scores + (rb * ld + (size_t)kt * KT) * 32 + lane;
+#pragma unroll 8
+        for (int c = 0; c < KT; c++) dst[(size_t)c * 32] = tile[lane * (KT + 1) + c];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// score_bundle_kernel -- the general score kernel (states with nich features, slow-path cells, ...).
+//
+// Same mapping as score_kernel: a block owns NW*RW rows and one k-tile of 32*V groups, lane l owns V consecutive
+// groups, acc[RW][V] lives in registers across all features.  What differs is the stage ring: a stage holds a BUNDLE
+// of consecutive features of the walk order (their row values, slow masks and parameter chunks, packed at the
+// offsets the host laid out: FeatDev::sx_off / sc_off / bundle_last), and the ring is waited for, released and
+// refilled once per bundle instead of once per feature.  ncu on the per-feature ring (profiles/r02_c5_score_src.txt):
+// one third of C5's warp samples sat in the loop head and tail -- the try_wait round trip, the FeatS reload, the kind
+// dispatch, the release atomic whose return value decides who refills -- because a table feature is only ~170
+// instructions of work per warp.  A C5 bundle is one period of the walk order (bb, gp, dd, nich: ~64 KB).
+// ---------------------------------------------------------------------------------------------------
+template <int V, int RW, int NW, bool BLOCKED>
+__global__ void __launch_bounds__(NW * 32, 1)
+score_bundle_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restrict__ params, size_t region_rows,
+                    uint32_t stage_bytes, int S, const float *__restrict__ base, float *__restrict__ scores, size_t ld,
+                    size_t row_org, size_t row_lo, size_t row_hi, const double *__restrict__ hp,
+                    const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols, int ktiles) {
+  constexpr int KT = 32 * V;
+  constexpr int RL = RW / 32;
+  constexpr int RB = NW * RW;                                   // rows per block
+  constexpr uint32_t X_BYTES = RB * 4, M_BYTES = RB / 8;        // row values, slow masks
+  static_assert(RW % 32 == 0 && M_BYTES % 16 == 0, "tile sizes must keep the bulk copies 16-byte granular");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [S stages | full[S], release counters[S] | nb | feature table | bundle starts (nfeat + 1) | bundle bytes (nfeat)]
+  unsigned char *stages = smem_raw;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * stage_bytes);
+  int *nb_slot = reinterpret_cast<int *>(bars + 2 * S);
+  FeatS *ftab = reinterpret_cast<FeatS *>(bars + 2 * S + 1);
+  uint16_t *bfirst = reinterpret_cast<uint16_t *>(ftab + nfeat);
+  uint32_t *bbytes = reinterpret_cast<uint32_t *>(bfirst + ((nfeat + 1 + 1) & ~1));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kt = (int)(blockIdx.x % (unsigned)ktiles);          // k-tile fastest: a row tile's values come from DRAM once
+  const float *region = params + (size_t)kt * region_rows * KT;
+  const size_t blk_row0 = row_org + (size_t)(blockIdx.x / (unsigned)ktiles) * RB;   // multiple of 128
+  const size_t row0 = blk_row0 + (size_t)warp * RW;
+
+  for (int i = tid; i < nfeat; i += NW * 32) {
+    const FeatDev f = feats[i];
+    FeatS t;
+    t.scol = f.scol; t.slowmask = f.slowmask; t.col = f.col;
+    t.rowoff = f.rowoff; t.rows = f.rows; t.ncat = f.ncat;
+    t.kind = (uint16_t)((f.kind == KIND_TABLE && f.binform) ? KIND_BIN : f.kind); t.has_slow = (uint16_t)(f.has_slow != 0);
+    t.sx_off = f.sx_off; t.sc_off = f.sc_off; t.last = f.bundle_last; t.fuse = f.fuse;
+    ftab[i] = t;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) {
+      mbar_init(smem_u32(&bars[s]), 1);
+      bars[S + s] = 0;  // release counter of the stage
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {  // bundle table
+    int nb = 0;
+    uint32_t bytes = 0;
+    bfirst[0] = 0;
+    for (int i = 0; i < nfeat; i++) {
+      const FeatS t = ftab[i];
+      bytes += X_BYTES + (t.has_slow ? M_BYTES : 0u) + t.rows * (uint32_t)(KT * sizeof(float));
+      if (t.last || i == nfeat - 1) { bbytes[nb] = bytes; bytes = 0; bfirst[++nb] = (uint16_t)(i + 1); }
+    }
+    *nb_slot = nb;
+  }
+  __syncthreads();
+  const int nb = *nb_slot;
+
+  // one thread: everything bundle b needs -> stage s
+  auto issue = [&](int b, int s) {
+    const uint32_t bar = smem_u32(&bars[s]);
+    const uint32_t dst0 = smem_u32(stages + (size_t)s * stage_bytes);
+    mbar_expect_tx(bar, bbytes[b]);
+    const int d1 = bfirst[b + 1];
+    for (int d = bfirst[b]; d < d1; d++) {
+      const FeatS t = ftab[d];
+      bulk_g2s(dst0 + t.sx_off, t.scol + blk_row0, X_BYTES, bar);
+      if (t.has_slow) bulk_g2s(dst0 + t.sx_off + X_BYTES, t.slowmask + (blk_row0 >> 5), M_BYTES, bar);
+      bulk_g2s(dst0 + t.sc_off, region + (size_t)t.rowoff * KT, t.rows * (uint32_t)(KT * sizeof(float)), bar);
+    }
+  };
+  if (tid == 0)
+    for (int b = 0; b < S && b < nb; b++) issue(b, b);
+
+  float acc[RW][V];
+#pragma unroll
+  for (int r = 0; r < RW; r++)
+#pragma unroll
+    for (int v = 0; v < V; v++) acc[r][v] = 0.f;
+
+  // ---- rare-path fix-ups, shared by the sequential and the fused walk (static register indexing throughout: acc must
+  // not spill to local memory)
+  auto load_slow = [&](const FeatS &t, const unsigned char *st, uint32_t (&slow)[RL]) {
+#pragma unroll
+    for (int j = 0; j < RL; j++)
+      slow[j] = t.has_slow ? reinterpret_cast<const uint32_t *>(st + X_BYTES)[warp * RL + j] : 0u;
+  };
+  // bb in binary form: masked cells were scored as x = 0: take back the t0 that base[] carries for this feature
+  auto fix_bin = [&](const float *chunk, const uint32_t (&slow)[RL]) {
+#pragma unroll
+    for (int j = 0; j < RL; j++) {
+      uint32_t m = slow[j];
+      if (m) {
+        VecF<V> t0;
+        t0.load(chunk + 1 * KT);
+        while (m) {
+          const int rr = j * 32 + __ffs(m) - 1;
+          m &= m - 1;
+#pragma unroll
+          for (int r = 0; r < RW; r++)
+            if (r == rr)
+#pragma unroll
+              for (int v = 0; v < V; v++) acc[r][v] -= t0.v[v];
+        }
+      }
+    }
+  };
+  // gp / bnb counts beyond the table: the fp64 closed form from the suffstats
+  auto fix_gp = [&](const FeatS &t, int d, const uint32_t (&slow)[RL]) {
+    const uint32_t *raw = reinterpret_cast<const uint32_t *>(t.col);
+#pragma unroll
+    for (int j = 0; j < RL; j++) {
+      uint32_t m = slow[j];
+      while (m) {
+        const int rr = j * 32 + __ffs(m) - 1;
+        m &= m - 1;
+        const double xv = (double)raw[row0 + rr];
+        float add[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          const int col = kt * KT + lane * V + v;
+          add[v] = 0.f;
+          if (col < ncols) add[v] = gp_overflow_score(feats + d, hp, ss, col2slot[col], xv);
+        }
+#pragma unroll
+        for (int r = 0; r < RW; r++)
+          if (r == rr)
+#pragma unroll
+            for (int v = 0; v < V; v++) acc[r][v] += add[v];
+      }
+    }
+  };
+  // nich: masked cells were scored as x = 0: undo that term and the c0 that base[] carries for this feature
+  auto fix_nich = [&](const float *chunk, const VecF<V> &mu, const VecF<V> &sc, const VecF<V> &c1, const uint32_t (&slow)[RL]) {
+#pragma unroll
+    for (int j = 0; j < RL; j++) {
+      uint32_t m = slow[j];
+      if (m) {
+        VecF<V> c0;
+        c0.load(chunk + 3 * KT);
+        float undo[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          const float tt = (0.f - mu.v[v]) * sc.v[v];
+          undo[v] = -fmaf(c1.v[v], log2_1p_pos(tt * tt), c0.v[v]);
+        }
+        while (m) {
+          const int rr = j * 32 + __ffs(m) - 1;
+          m &= m - 1;
+#pragma unroll
+          for (int r = 0; r < RW; r++)
+            if (r == rr)
+#pragma unroll
+              for (int v = 0; v < V; v++) acc[r][v] += undo[v];
+        }
+      }
+    }
+  };
+
+  int s = 0;
+  uint32_t parity = 0;
+  for (int b = 0; b < nb; b++) {
+    mbar_wait(smem_u32(&bars[s]), parity);
+    const unsigned char *stage = stages + (size_t)s * stage_bytes;
+    const int d1 = bfirst[b + 1];
+    for (int d = bfirst[b]; d < d1; d++) {
+      const FeatS t = ftab[d];
+      const unsigned char *st = stage + t.sx_off;
+      // this warp's RW row values, read as broadcast 128-bit loads (4 rows per shared-memory wavefront)
+      const uint4 *xq = reinterpret_cast<const uint4 *>(st) + warp * (RW / 4);
+      const float *chunk = reinterpret_cast<const float *>(stage + t.sc_off) + lane * V;
+      uint32_t slow[RL];
+      load_slow(t, st, slow);
+
+      if constexpr (V == 4) {
+        if (t.fuse) {
+          // Fused quad [bb in binary form, table A, table B, nich] (the host orders the walk so; all four sit in this
+          // stage): every row step issues the two lookups (shared-memory pipe) next to the nich arithmetic (FMA / XU
+          // pipes) and the bb multiply-add, so that inside ONE warp the lookup latency hides under ~30 arithmetic
+          // instructions and both pipes stay busy.  Walking the four features one after the other keeps each pipe idle
+          // while the other works: with 242 registers there are only two warps per scheduler to overlap anything.
+          const FeatS tA = ftab[d + 1], tC = ftab[d + 2], tN = ftab[d + 3];
+          const unsigned char *stA = stage + tA.sx_off, *stC = stage + tC.sx_off, *stN = stage + tN.sx_off;
+          const uint4 *xqA = reinterpret_cast<const uint4 *>(stA) + warp * (RW / 4);
+          const uint4 *xqC = reinterpret_cast<const uint4 *>(stC) + warp * (RW / 4);
+          const uint4 *xqN = reinterpret_cast<const uint4 *>(stN) + warp * (RW / 4);
+          const float *chunkA = reinterpret_cast<const float *>(stage + tA.sc_off) + lane * V;
+          const float *chunkC = reinterpret_cast<const float *>(stage + tC.sc_off) + lane * V;
+          const float *chunkN = reinterpret_cast<const float *>(stage + tN.sc_off) + lane * V;
+          const uint32_t cA = smem_u32(chunkA), cC = smem_u32(chunkC);
+          VecF<V> df, mu, sc, c1;
+          df.load(chunk + 0 * KT);
+          mu.load(chunkN + 0 * KT);
+          sc.load(chunkN + 1 * KT);
+          c1.load(chunkN + 2 * KT);
+          float2 nmu2[2], sc2[2], c12[2], df2[2];
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            nmu2[h] = make_float2(-mu.v[2 * h], -mu.v[2 * h + 1]);
+            sc2[h] = make_float2(sc.v[2 * h], sc.v[2 * h + 1]);
+            c12[h] = make_float2(c1.v[2 * h], c1.v[2 * h + 1]);
+            df2[h] = make_float2(df.v[2 * h], df.v[2 * h + 1]);
+          }
+#pragma unroll
+          for (int r4 = 0; r4 < RW / 4; r4++) {
+            const uint4 qB = xq[r4], qA = xqA[r4], qC = xqC[r4], qN = xqN[r4];
+            const float xb[4] = {__uint_as_float(qB.x), __uint_as_float(qB.y), __uint_as_float(qB.z), __uint_as_float(qB.w)};
+            const float xn[4] = {__uint_as_float(qN.x), __uint_as_float(qN.y), __uint_as_float(qN.z), __uint_as_float(qN.w)};
+            const uint32_t iA[4] = {qA.x, qA.y, qA.z, qA.w}, iC[4] = {qC.x, qC.y, qC.z, qC.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int r = r4 * 4 + e;
+              VecF<V> tvA, tvC;
+              lds_vec<V>(tvA.v, cA + iA[e] * (uint32_t)(KT * sizeof(float)));
+              lds_vec<V>(tvC.v, cC + iC[e] * (uint32_t)(KT * sizeof(float)));
+              const float2 x2 = make_float2(xn[e], xn[e]), b2 = make_float2(xb[e], xb[e]);
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const float2 tt = __fmul2_rn(__fadd2_rn(x2, nmu2[h]), sc2[h]);
+                float2 a = __ffma2_rn(c12[h], log2_1p_pos2(__fmul2_rn(tt, tt)), make_float2(acc[r][2 * h], acc[r][2 * h + 1]));
+                a = __ffma2_rn(b2, df2[h], a);
+                a = __fadd2_rn(a, make_float2(tvA.v[2 * h], tvA.v[2 * h + 1]));
+                a = __fadd2_rn(a, make_float2(tvC.v[2 * h], tvC.v[2 * h + 1]));
+                acc[r][2 * h] = a.x;
+                acc[r][2 * h + 1] = a.y;
+              }
+            }
+          }
+          // rare paths of the four features
+          fix_bin(chunk, slow);
+          uint32_t slowX[RL];
+          if (tA.kind == KIND_GP) { load_slow(tA, stA, slowX); fix_gp(tA, d + 1, slowX); }
+          if (tC.kind == KIND_GP) { load_slow(tC, stC, slowX); fix_gp(tC, d + 2, slowX); }
+          load_slow(tN, stN, slowX);
+          fix_nich(chunkN, mu, sc, c1, slowX);
+          d += 3;
+          continue;
+        }
+      }
+
+      if (t.kind == KIND_BIN) {  // bb in binary form: acc += x (t1 - t0), sum_d t0 is already in base[]
+        VecF<V> df;
+        df.load(chunk + 0 * KT);
+#pragma unroll
+        for (int r4 = 0; r4 < RW / 4; r4++) {
+          const uint4 q = xq[r4];
+          const float xs[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            if constexpr (V % 2 == 0) {
+#pragma unroll
+              for (int h = 0; h < V / 2; h++) {
+                const float2 a = __ffma2_rn(make_float2(xs[e], xs[e]), make_float2(df.v[2 * h], df.v[2 * h + 1]),
+                                            make_float2(acc[r4 * 4 + e][2 * h], acc[r4 * 4 + e][2 * h + 1]));
+                acc[r4 * 4 + e][2 * h] = a.x;
+                acc[r4 * 4 + e][2 * h + 1] = a.y;
+              }
+            } else {
+#pragma unroll
+              for (int v = 0; v < V; v++) acc[r4 * 4 + e][v] = fmaf(xs[e], df.v[v], acc[r4 * 4 + e][v]);
+            }
+          }
+        }
+        fix_bin(chunk, slow);
+      } else if (t.kind != KIND_NICH) {
+        const uint32_t chunk_s = smem_u32(chunk);
+#pragma unroll
+        for (int r4 = 0; r4 < RW / 4; r4++) {
+          const uint4 q = xq[r4];
+          const uint32_t idx[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            VecF<V> tv;
+            lds_vec<V>(tv.v, chunk_s + idx[e] * (uint32_t)(KT * sizeof(float)));
+            if constexpr (V % 2 == 0) {
+#pragma unroll
+              for (int h = 0; h < V / 2; h++) {
+                const float2 a = __fadd2_rn(make_float2(acc[r4 * 4 + e][2 * h], acc[r4 * 4 + e][2 * h + 1]),
+                                            make_float2(tv.v[2 * h], tv.v[2 * h + 1]));
+                acc[r4 * 4 + e][2 * h] = a.x;
+                acc[r4 * 4 + e][2 * h + 1] = a.y;
+              }
+            } else {
+#pragma unroll
+              for (int v = 0; v < V; v++) acc[r4 * 4 + e][v] += tv.v[v];
+            }
+          }
+        }
+        if (t.kind == KIND_GP) fix_gp(t, d, slow);
+      } else {  // KIND_NICH: c1' log2(1 + ((x - mu) s)^2); sum_d c0 is already in base[]
+        VecF<V> mu, sc, c1;
+        mu.load(chunk + 0 * KT);
+        sc.load(chunk + 1 * KT);
+        c1.load(chunk + 2 * KT);
+        if constexpr (V % 2 == 0) {  // two groups per instruction (FADD2 / FMUL2 / FFMA2)
+          float2 nmu2[V / 2], sc2[V / 2], c12[V / 2];
+#pragma unroll
+          for (int h = 0; h < V / 2; h++) {
+            nmu2[h] = make_float2(-mu.v[2 * h], -mu.v[2 * h + 1]);
+            sc2[h] = make_float2(sc.v[2 * h], sc.v[2 * h + 1]);
+            c12[h] = make_float2(c1.v[2 * h], c1.v[2 * h + 1]);
+          }
+#pragma unroll
+          for (int r4 = 0; r4 < RW / 4; r4++) {
+            const uint4 q = xq[r4];
+            const float xs[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const float2 x2 = make_float2(xs[e], xs[e]);
+#pragma unroll
+              for (int h = 0; h < V / 2; h++) {
+                const float2 tt = __fmul2_rn(__fadd2_rn(x2, nmu2[h]), sc2[h]);
+                const float2 a = __ffma2_rn(c12[h], log2_1p_pos2(__fmul2_rn(tt, tt)),
+                                            make_float2(acc[r4 * 4 + e][2 * h], acc[r4 * 4 + e][2 * h + 1]));
+                acc[r4 * 4 + e][2 * h] = a.x;
+                acc[r4 * 4 + e][2 * h + 1] = a.y;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r4 = 0; r4 < RW / 4; r4++) {
+            const uint4 q = xq[r4];
+            const float xs[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+#pragma unroll
+              for (int v = 0; v < V; v++) {
+                const float tt = (xs[e] - mu.v[v]) * sc.v[v];
+                acc[r4 * 4 + e][v] = fmaf(c1.v[v], log2_1p_pos(tt * tt), acc[r4 * 4 + e][v]);
+              }
+          }
+        }
+        fix_nich(chunk, mu, sc, c1, slow);
+      }
+    }
+    // Release the stage: a counter per stage, and the warp that arrives LAST issues the refill with bundle b + S, so
+    // that nobody waits here (see score_kernel for what was measured against a fixed producer thread).
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t rel = smem_u32(&bars[S + s]);
+      unsigned int old;
+      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(rel) : "memory");
+      if (old == (unsigned)(NW - 1)) {
+        asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(rel), "r"(0u) : "memory");
+        if (b + S < nb) issue(b + S, s);
+      }
+    }
+    if (++s == S) { s = 0; parity ^= 1u; }
+  }
+
+  // epilogue: + log(pseudocount) (group_manager.hpp:274-283)
+  VecF<V> bv;
+  bv.load(base + (size_t)kt * KT + lane * V);
+  if constexpr (!BLOCKED) {  // 128 V-byte coalesced row-major stores
+#pragma unroll
+    for (int r = 0; r < RW; r++) {
+      const size_t row = row0 + r;
+      if (row >= row_lo && row < row_hi) {
+        float o[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) o[v] = acc[r][v] + bv.v[v];
+        store_vec<V>(scores + (row - row_org) * ld + (size_t)kt * KT + lane * V, o);
+      }
+    }
+  } else {
+    // transpose each 32-row x KT-group tile through shared memory (the drained stage ring) so that
+    // lane = row and every store instruction writes 32 consecutive floats of one group
+    __syncthreads();  // every warp has finished reading the stages
+    float *tile = reinterpret_cast<float *>(stages) + (size_t)warp * 32 * (KT + 1);
+#pragma unroll
+    for (int j = 0; j < RL; j++) {
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 32; r++)
+#pragma unroll
+        for (int v = 0; v < V; v++) tile[r * (KT + 1) + lane * V + v] = acc[j * 32 + r][v] + bv.v[v];
       __syncwarp();
       const size_t rb = (row0 - row_org) / 32 + j;
       if (row0 + (size_t)j * 32 < row_hi) {

@@ -142,6 +142,8 @@ struct msb_state {
   std::vector<void *> cols;
   int32_t *d_assign = nullptr;
   size_t region_rows = 0, max_chunk_rows = 0;
+  std::vector<FeatDev> sc_host;  // the score kernel's walk order (host copy of d_feats_scalar)
+  uint64_t bundle_key = 0;       // (tile shape, stage bytes) the bundle layout in d_feats_scalar was made for; 0 = none
   bool has_bbnc = false, has_dm = false;  // has_dm: a vector count feature scored by its own kernel after the scalar ones (like niw)
   uint64_t group_seed = 0x6d73625f62626e63ull;  // Philox key of the per-group parameter draws (bbnc: p ~ Beta(alpha, beta))
   bool has_niw = false, has_scalar = false, tables_only = false, has_dd = false, has_nich = false;
@@ -238,6 +240,10 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   CU_TRY(opt_in_smem(score_kernel<2, 32, 16, true, true>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<4, 32, 8, true, true>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<1, 32, 8, true, true>, c->smem_optin));
+  CU_TRY(opt_in_smem((score_bundle_kernel<2, 32, 16, false>), c->smem_optin));
+  CU_TRY(opt_in_smem((score_bundle_kernel<2, 32, 16, true>), c->smem_optin));
+  CU_TRY(opt_in_smem((score_bundle_kernel<4, 32, 8, false>), c->smem_optin));
+  CU_TRY(opt_in_smem((score_bundle_kernel<4, 32, 8, true>), c->smem_optin));
   CU_TRY(opt_in_smem((sample_tile_kernel<4, false>), c->smem_optin));
   CU_TRY(opt_in_smem((sample_tile_kernel<4, true>), c->smem_optin));
   CU_TRY(opt_in_smem(ingest_tile_kernel<128>, c->smem_optin));
@@ -662,19 +668,43 @@ static int sync_small(msb_state *st) {  // upload hypers / feature descriptors i
     // rotated order was measured too and is not kept: with 2 warps per SM sub-partition neither group
     // saturates its pipe (57.8 ms).
     std::vector<FeatDev> sc, light, heavy;
-    for (const auto &f : st->feats)
+    for (auto f : st->feats) {
+      f.fuse = 0; f.bundle_last = 1; f.sx_off = f.sc_off = 0;
       if (f.rows > 0) (f.kind == KIND_NICH ? heavy : light).push_back(f);
-    if (heavy.empty() || light.empty() || getenv("MSB_NO_INTERLEAVE")) {
-      for (const auto &f : st->feats) if (f.rows > 0) sc.push_back(f);
+    }
+    static const bool no_interleave = getenv("MSB_NO_INTERLEAVE") != nullptr, no_fuse = getenv("MSB_NO_FUSE") != nullptr;
+    if (heavy.empty() || light.empty() || no_interleave) {
+      for (const auto &f : st->feats) if (f.rows > 0) { sc.push_back(f); sc.back().fuse = 0; }
     } else {
-      size_t li = 0;
-      for (size_t h = 0; h < heavy.size(); h++) {
-        const size_t upto = light.size() * (h + 1) / heavy.size();
-        while (li < upto) sc.push_back(light[li++]);
-        sc.push_back(heavy[h]);
+      // Fused quads first (score_bundle_kernel): [bb in binary form, table, table, nich] walked together, one row step
+      // doing the two lookups next to the nich arithmetic.  Tables are paired first half with second half of their
+      // list, so that a family with big chunks (gp) meets one with small chunks (dd) and every quad fills about the
+      // same share of a stage.
+      std::vector<FeatDev> bins, tabs, rest;
+      for (const auto &f : light) ((f.kind == KIND_TABLE && f.binform) ? bins : tabs).push_back(f);
+      const size_t Q = no_fuse ? 0 : std::min(bins.size(), std::min(tabs.size() / 2, heavy.size()));
+      const size_t half = tabs.size() / 2;
+      for (size_t q = 0; q < Q; q++) {
+        sc.push_back(bins[q]); sc.back().fuse = 1;
+        sc.push_back(tabs[q]);
+        sc.push_back(tabs[half + q]);
+        sc.push_back(heavy[q]);
       }
+      for (size_t i = Q; i < bins.size(); i++) rest.push_back(bins[i]);
+      for (size_t i = 0; i < tabs.size(); i++) if (!(i < Q || (i >= half && i < half + Q))) rest.push_back(tabs[i]);
+      // the others: nich features spread evenly between the table lookups
+      const size_t nh = heavy.size() - Q;
+      size_t li = 0;
+      for (size_t h = 0; h < nh; h++) {
+        const size_t upto = rest.size() * (h + 1) / nh;
+        while (li < upto) sc.push_back(rest[li++]);
+        sc.push_back(heavy[Q + h]);
+      }
+      while (li < rest.size()) sc.push_back(rest[li++]);
     }
     st->n_scalar = sc.size();
+    st->sc_host = sc;        // kept: launch_score lays the bundles of score_bundle_kernel out for the tile shape in use
+    st->bundle_key = 0;      // ... and uploads the list again when that layout changes
     if (!sc.empty())
       CU_TRY(cudaMemcpy(st->d_feats_scalar, sc.data(), sizeof(FeatDev) * sc.size(), cudaMemcpyHostToDevice));
     st->feats_dirty = false;
@@ -1403,6 +1433,62 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
     if (smem > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "score kernel shared memory does not fit");
     const size_t grid = (size_t)cdiv(nrows, RB) * ktiles;
     if (grid >= (1ull << 31)) return fail(MSB_ERR_UNSUPPORTED, "score grid too large: sweep a smaller row range");
+    static const bool no_bundle = getenv("MSB_NO_BUNDLE") != nullptr;
+    if (!st->tables_only && !no_bundle && (st->cfg == 1 || st->cfg == 2)) {
+      // General kernel, bundled ring (score_bundle_kernel): three stages of a third of the shared memory each, every
+      // stage filled with as many consecutive features of the walk order as fit.
+      const size_t fixed_b = st->n_scalar * (sizeof(FeatS) + 8) + 2 * 8 * sizeof(uint64_t) + 256;
+      const size_t xm = (RB * 4 + RB / 8 + 127) / 128 * 128;
+      const size_t biggest = (xm + st->max_chunk_rows * KT * sizeof(float) + 127) / 128 * 128;
+      static const int want_stages = getenv("MSB_BUNDLE_STAGES") ? atoi(getenv("MSB_BUNDLE_STAGES")) : 3;
+      int Sb = std::max(2, std::min(8, want_stages));
+      size_t stage_b = (ctx->smem_optin - fixed_b) / Sb / 128 * 128;
+      while (Sb > 2 && stage_b < biggest) { Sb--; stage_b = (ctx->smem_optin - fixed_b) / Sb / 128 * 128; }
+      if (stage_b >= biggest && (!blocked || (size_t)Sb * stage_b >= tile)) {
+        const uint64_t key = ((uint64_t)st->cfg + 1) << 32 | (uint64_t)stage_b;
+        if (st->bundle_key != key) {
+          size_t off = 0;
+          auto need_of = [&](const FeatDev &f) { return (xm + (size_t)f.rows * KT * sizeof(float) + 127) / 128 * 128; };
+          for (size_t i = 0; i < st->sc_host.size(); i++) {
+            FeatDev &f = st->sc_host[i];
+            size_t need = need_of(f);
+            if (f.fuse) {  // a fused quad stays inside one bundle; when it cannot, its features are walked one by one
+              size_t quad = 0;
+              for (size_t j = 0; j < 4; j++) quad += need_of(st->sc_host[i + j]);
+              if (quad > stage_b || st->V != 4) f.fuse = 0;
+              else need = quad;
+            }
+            if (off + need > stage_b) { st->sc_host[i - 1].bundle_last = 1; off = 0; }
+            const size_t span = f.fuse ? 4 : 1;
+            for (size_t j = 0; j < span; j++) {
+              FeatDev &g = st->sc_host[i + j];
+              g.sx_off = (uint32_t)off;
+              g.sc_off = (uint32_t)(off + xm);
+              g.bundle_last = 0;
+              off += need_of(g);
+            }
+            i += span - 1;
+          }
+          if (!st->sc_host.empty()) st->sc_host.back().bundle_last = 1;
+          // kernels of earlier sweeps read the list in stream order: the copy is ordered behind them
+          CU_TRY(cudaMemcpyAsync(st->d_feats_scalar, st->sc_host.data(), sizeof(FeatDev) * st->sc_host.size(), cudaMemcpyHostToDevice, ctx->stream));
+          CU_TRY(cudaStreamSynchronize(ctx->stream));
+          st->bundle_key = key;
+        }
+        const size_t smem_b = (size_t)Sb * stage_b + fixed_b;
+#define MSB_BUNDLE_LAUNCH(V_, RW_, NW_)                                                                                   \
+        do {                                                                                                              \
+          if (blocked) LAUNCH(ctx, (score_bundle_kernel<V_, RW_, NW_, true>), (unsigned)grid, NW_ * 32, smem_b, MSB_BUNDLE_ARGS); \
+          else LAUNCH(ctx, (score_bundle_kernel<V_, RW_, NW_, false>), (unsigned)grid, NW_ * 32, smem_b, MSB_BUNDLE_ARGS);        \
+        } while (0)
+#define MSB_BUNDLE_ARGS st->d_feats_scalar, (int)st->n_scalar, st->d_params, st->region_rows, (uint32_t)stage_b, Sb, st->d_base_score, \
+                        scores, st->ld, org, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K, (int)ktiles
+        if (st->cfg == 1) MSB_BUNDLE_LAUNCH(2, 32, 16); else MSB_BUNDLE_LAUNCH(4, 32, 8);
+#undef MSB_BUNDLE_LAUNCH
+#undef MSB_BUNDLE_ARGS
+        goto scalar_done;
+      }
+    }
 #define MSB_SCORE_ARGS st->d_feats_scalar, (int)st->n_scalar, st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base_score, \
                        scores, st->ld, org, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K, (int)ktiles, st->tail_g
 #define MSB_SCORE_LAUNCH(V_, RW_, NW_)                                                                         \
@@ -1421,6 +1507,7 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
 #undef MSB_SCORE_LAUNCH
 #undef MSB_SCORE_ARGS
   }
+scalar_done:
   row_lo = org;  // the NIW kernels below index the score matrix from the same origin
   // without scalar features the first NIW feature initialises the matrix: the tensor-core kernel writes
   // base[k] + term directly; the CUDA-core kernel accumulates onto a base-filled matrix
