@@ -607,10 +607,10 @@ score_bundle_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *_
                     size_t row_org, size_t row_lo, size_t row_hi, const double *__restrict__ hp,
                     const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols, int ktiles) {
   constexpr int KT = 32 * V;
-  constexpr int RL = RW / 32;
+  constexpr int RL = (RW + 31) / 32;                            // slow-mask words per warp (RW = 16: half a word)
   constexpr int RB = NW * RW;                                   // rows per block
   constexpr uint32_t X_BYTES = RB * 4, M_BYTES = RB / 8;        // row values, slow masks
-  static_assert(RW % 32 == 0 && M_BYTES % 16 == 0, "tile sizes must keep the bulk copies 16-byte granular");
+  static_assert((RW % 32 == 0 || RW == 16) && M_BYTES % 16 == 0, "tile sizes must keep the bulk copies 16-byte granular");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // layout: [S stages | full[S], release counters[S] | nb | feature table | bundle starts (nfeat + 1) | bundle bytes (nfeat)]
   unsigned char *stages = smem_raw;
@@ -681,9 +681,14 @@ score_bundle_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *_
   // ---- rare-path fix-ups, shared by the sequential and the fused walk (static register indexing throughout: acc must
   // not spill to local memory)
   auto load_slow = [&](const FeatS &t, const unsigned char *st, uint32_t (&slow)[RL]) {
+    if constexpr (RW == 16) {  // two warps share a 32-row mask word
+      const uint32_t w = t.has_slow ? reinterpret_cast<const uint32_t *>(st + X_BYTES)[warp >> 1] : 0u;
+      slow[0] = (w >> (16 * (warp & 1))) & 0xFFFFu;
+    } else {
 #pragma unroll
-    for (int j = 0; j < RL; j++)
-      slow[j] = t.has_slow ? reinterpret_cast<const uint32_t *>(st + X_BYTES)[warp * RL + j] : 0u;
+      for (int j = 0; j < RL; j++)
+        slow[j] = t.has_slow ? reinterpret_cast<const uint32_t *>(st + X_BYTES)[warp * RL + j] : 0u;
+    }
   };
   // bb in binary form: masked cells were scored as x = 0: take back the t0 that base[] carries for this feature
   auto fix_bin = [&](const float *chunk, const uint32_t (&slow)[RL]) {
@@ -967,6 +972,23 @@ score_bundle_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *_
     // transpose each 32-row x KT-group tile through shared memory (the drained stage ring) so that
     // lane = row and every store instruction writes 32 consecutive floats of one group
     __syncthreads();  // every warp has finished reading the stages
+    if constexpr (RW == 16) {  // a pair of warps owns one 32-row block: each writes its 16 rows, each stores half of the columns
+      float *tile = reinterpret_cast<float *>(stages) + (size_t)(warp >> 1) * 32 * (KT + 1);
+      const int rbase = 16 * (warp & 1);
+#pragma unroll
+      for (int r = 0; r < 16; r++)
+#pragma unroll
+        for (int v = 0; v < V; v++) tile[(rbase + r) * (KT + 1) + lane * V + v] = acc[r][v] + bv.v[v];
+      __syncthreads();
+      const size_t prow0 = blk_row0 + (size_t)(warp >> 1) * 32;
+      if (prow0 < row_hi) {
+        float *dst = scores + (((prow0 - row_org) / 32) * ld + (size_t)kt * KT) * 32 + lane;
+        const int c0 = (warp & 1) * (KT / 2);
+#pragma unroll 8
+        for (int c = c0; c < c0 + KT / 2; c++) dst[(size_t)c * 32] = tile[lane * (KT + 1) + c];
+      }
+      return;
+    }
     float *tile = reinterpret_cast<float *>(stages) + (size_t)warp * 32 * (KT + 1);
 #pragma unroll
     for (int j = 0; j < RL; j++) {

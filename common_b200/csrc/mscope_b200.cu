@@ -244,6 +244,8 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   CU_TRY(opt_in_smem((score_bundle_kernel<2, 32, 16, true>), c->smem_optin));
   CU_TRY(opt_in_smem((score_bundle_kernel<4, 32, 8, false>), c->smem_optin));
   CU_TRY(opt_in_smem((score_bundle_kernel<4, 32, 8, true>), c->smem_optin));
+  CU_TRY(opt_in_smem((score_bundle_kernel<4, 16, 16, false>), c->smem_optin));
+  CU_TRY(opt_in_smem((score_bundle_kernel<4, 16, 16, true>), c->smem_optin));
   CU_TRY(opt_in_smem((sample_tile_kernel<4, false>), c->smem_optin));
   CU_TRY(opt_in_smem((sample_tile_kernel<4, true>), c->smem_optin));
   CU_TRY(opt_in_smem(ingest_tile_kernel<128>, c->smem_optin));
@@ -1139,6 +1141,11 @@ extern "C" MSB_API int msb_state_set_ss(msb_state *st, size_t feature, size_t gi
   CU_TRY(cudaStreamSynchronize(st->ctx->stream));
   ss_to_ref(st->models[feature], s);
   for (size_t i = 0; i < cnt; i++) s[off + i] = v[i];
+  if (st->models[feature].family == MSB_FAMILY_DD && off > 0) {
+    // count_sum is derived: it follows the counts (dd_score and score_data read it before the next apply refreshes it)
+    s[0] = 0.0;
+    for (size_t i = 1; i < s.size(); i++) s[0] += s[i];
+  }
   ss_from_ref(st->models[feature], s);
   st->slot_dirty[slot] = 1;
   CU_TRY(cudaMemcpyAsync(dst, s.data(), sizeof(double) * f.ss_w, cudaMemcpyHostToDevice, st->ctx->stream));
@@ -1301,13 +1308,15 @@ static int ensure_rows(msb_state *st, size_t nrows) {
 //   1: V=2 RW=32 NW=16   512 rows x 64 groups
 //   2: V=4 RW=32 NW=8    256 rows x 128 groups -- small chunks, many groups: fewest instructions per lookup
 //   3: V=1 RW=32 NW=8    256 rows x 32 groups  -- K <= 32
+//   4: V=4 RW=16 NW=16   256 rows x 128 groups on 16 warps (score_bundle_kernel only)
 struct ScoreCfg { int V, RW, NW; };
-static const ScoreCfg k_score_cfgs[4] = {{1, 64, 16}, {2, 32, 16}, {4, 32, 8}, {1, 32, 8}};
+static const ScoreCfg k_score_cfgs[5] = {{1, 64, 16}, {2, 32, 16}, {4, 32, 8}, {1, 32, 8}, {4, 16, 16}};
 
 static int choose_cfg(const msb_state *st, size_t ncols) {
   if (const char *e = getenv("MSB_SCORE_CFG")) {
     const int c = atoi(e);
     if (c >= 0 && c < 4) return c;
+    if (c == 4 && !st->tables_only && st->has_scalar) return c;
   }
   if (ncols <= 32) return 3;
   if (st->max_chunk_rows >= 128) return 0;
@@ -1427,14 +1436,13 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
     if (stage + fixed > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "parameter chunk does not fit in shared memory");
     const int S = (int)std::max<size_t>(1, std::min<size_t>(8, (ctx->smem_optin - fixed) / stage));
     // the blocked epilogue transposes 32 x KT tiles through the (drained) stage ring
-    const size_t tile = (size_t)c.NW * 32 * (KT + 1) * sizeof(float);
+    const size_t tile = RB * (KT + 1) * sizeof(float);   // one 32-row x KT tile per 32 rows of the block
     if (blocked && (size_t)S * stage < tile) stage = ((tile + S - 1) / S + 127) / 128 * 128;
     const size_t smem = (size_t)S * stage + fixed;
-    if (smem > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "score kernel shared memory does not fit");
     const size_t grid = (size_t)cdiv(nrows, RB) * ktiles;
     if (grid >= (1ull << 31)) return fail(MSB_ERR_UNSUPPORTED, "score grid too large: sweep a smaller row range");
     static const bool no_bundle = getenv("MSB_NO_BUNDLE") != nullptr;
-    if (!st->tables_only && !no_bundle && (st->cfg == 1 || st->cfg == 2)) {
+    if (!st->tables_only && !no_bundle && (st->cfg == 1 || st->cfg == 2 || st->cfg == 4)) {
       // General kernel, bundled ring (score_bundle_kernel): three stages of a third of the shared memory each, every
       // stage filled with as many consecutive features of the walk order as fit.
       const size_t fixed_b = st->n_scalar * (sizeof(FeatS) + 8) + 2 * 8 * sizeof(uint64_t) + 256;
@@ -1483,12 +1491,16 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
         } while (0)
 #define MSB_BUNDLE_ARGS st->d_feats_scalar, (int)st->n_scalar, st->d_params, st->region_rows, (uint32_t)stage_b, Sb, st->d_base_score, \
                         scores, st->ld, org, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K, (int)ktiles
-        if (st->cfg == 1) MSB_BUNDLE_LAUNCH(2, 32, 16); else MSB_BUNDLE_LAUNCH(4, 32, 8);
+        if (st->cfg == 1) MSB_BUNDLE_LAUNCH(2, 32, 16);
+        else if (st->cfg == 4) MSB_BUNDLE_LAUNCH(4, 16, 16);
+        else MSB_BUNDLE_LAUNCH(4, 32, 8);
 #undef MSB_BUNDLE_LAUNCH
 #undef MSB_BUNDLE_ARGS
         goto scalar_done;
       }
     }
+    if (st->cfg == 4) return fail(MSB_ERR_UNSUPPORTED, "score shape 4 exists for the bundled general kernel only");
+    if (smem > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "score kernel shared memory does not fit");
 #define MSB_SCORE_ARGS st->d_feats_scalar, (int)st->n_scalar, st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base_score, \
                        scores, st->ld, org, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K, (int)ktiles, st->tail_g
 #define MSB_SCORE_LAUNCH(V_, RW_, NW_)                                                                         \

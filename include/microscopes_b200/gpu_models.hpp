@@ -20,6 +20,7 @@
 
 #include "../mscope_b200.h"
 #include "plugin_api.hpp"
+#include "wire.hpp"
 
 namespace microscopes {
 namespace models {
@@ -109,12 +110,16 @@ public:
   // one draw from the posterior predictive (distributions.hpp:293-298); the caller's rng supplies the counter of the
   // device's Philox stream, so the engine advances as it would upstream.  dm throws, as dm.cpp:100-111 does.
   void sample_value(const hypers &m, common::value_mutator &value, common::rng_t &rng) const override;
-  common::suffstats_bag_t get_ss() const override {  // raw little-endian doubles (the protobuf bag is row f3, not built)
-    return common::suffstats_bag_t(reinterpret_cast<const char *>(ss_.data()), ss_.size() * sizeof(double));
-  }
-  void set_ss(const common::suffstats_bag_t &ss) override {
-    if (ss.size() != ss_.size() * sizeof(double)) throw std::runtime_error("wrong dimension");
-    std::memcpy(ss_.data(), ss.data(), ss.size());
+  // the serialized Group message, as distributions.hpp:300-306 / bbnc.cpp, dm.cpp return it (wire.hpp)
+  common::suffstats_bag_t get_ss() const override { return b200::wire::encode(b200::wire::group_fields(desc_), ss_); }
+  void set_ss(const common::suffstats_bag_t &ss) override {  // distributions.hpp:308-314
+    std::vector<double> s = ss_;
+    b200::wire::decode(b200::wire::group_fields(desc_), ss, s);
+    if (desc_.family == MSB_FAMILY_DD) {  // count_sum is not on the wire: it is the sum of the counts
+      s[0] = 0.0;
+      for (size_t i = 1; i < s.size(); i++) s[0] += s[i];
+    }
+    ss_ = s;
   }
   void set_ss(const group &g) override { ss_ = static_cast<const gpu_group &>(g).ss_; }  // unchecked cast, as distributions.hpp:316-320
   common::value_mutator get_ss_mutator(const std::string &key) override {
@@ -152,12 +157,12 @@ public:
         break;
     }
   }
-  common::hyperparam_bag_t get_hp() const override {
-    return common::hyperparam_bag_t(reinterpret_cast<const char *>(hp_.data()), hp_.size() * sizeof(double));
-  }
+  // the serialized Shared message (distributions.hpp:355-369)
+  common::hyperparam_bag_t get_hp() const override { return b200::wire::encode(b200::wire::shared_fields(desc_), hp_); }
   void set_hp(const common::hyperparam_bag_t &hp) override {
-    if (hp.size() != hp_.size() * sizeof(double)) throw std::runtime_error("wrong dimension");  // distributions.hpp:436
-    std::memcpy(hp_.data(), hp.data(), hp.size());
+    std::vector<double> h = hp_;
+    b200::wire::decode(b200::wire::shared_fields(desc_), hp, h);  // throws "wrong dimension" like distributions.hpp:436
+    hp_ = h;
   }
   void set_hp(const hypers &s) override { hp_ = static_cast<const gpu_hypers &>(s).hp_; }
   common::value_mutator get_hp_mutator(const std::string &key) override {

@@ -25,8 +25,62 @@ static int fails = 0;
     }                                                                                            \
   } while (0)
 
+// "bags": host only (no device).  For every family: fill the hypers and one group through the named mutators with fixed
+// values, print "<family> <dim> <hex of get_hp()> <hex of get_ss()>"; then, for every line "<family> <dim> <hp hex> <ss hex>"
+// on stdin, load the bags into fresh objects with set_hp / set_ss and print what get_hp / get_ss return afterwards.
+static std::string to_hex(const std::string &b) {
+  static const char *d = "0123456789abcdef";
+  std::string o;
+  for (unsigned char c : b) { o.push_back(d[c >> 4]); o.push_back(d[c & 15]); }
+  return o.empty() ? "-" : o;
+}
+static std::string from_hex(const std::string &h) {
+  std::string o;
+  if (h == "-") return o;
+  for (size_t i = 0; i + 1 < h.size(); i += 2) o.push_back((char)std::stoi(h.substr(i, 2), nullptr, 16));
+  return o;
+}
+static void fill(value_mutator m, double base) {
+  for (unsigned i = 0; i < m.shape(); i++) m.set<double>(base + i, i);
+}
+static int bags_mode() {
+  rng_t r(1);
+  struct fam { int family; unsigned dim; std::vector<const char *> hp, ss; };
+  const std::vector<fam> fams = {
+      {MSB_FAMILY_BB, 0, {"alpha", "beta"}, {"heads", "tails"}},
+      {MSB_FAMILY_BNB, 0, {"alpha", "beta", "r"}, {"count", "sum"}},
+      {MSB_FAMILY_GP, 0, {"alpha", "inv_beta"}, {"count", "sum", "log_prod"}},
+      {MSB_FAMILY_NICH, 0, {"mu", "kappa", "sigmasq", "nu"}, {"count", "mean", "count_times_variance"}},
+      {MSB_FAMILY_DD, 5, {"alphas"}, {"counts"}},
+      {MSB_FAMILY_NIW, 3, {"mu", "kappa", "psi", "nu"}, {"count", "sum_x", "sum_xxT"}},
+      {MSB_FAMILY_BBNC, 0, {"alpha", "beta"}, {"p", "heads", "tails"}},
+      {MSB_FAMILY_DM, 4, {"alphas"}, {"counts", "ratio"}}};
+  for (const auto &f : fams) {
+    auto h = gpu_model(f.family, f.dim).create_hypers();
+    double base = 1.5;
+    for (auto k : f.hp) { fill(h->get_hp_mutator(k), std::strcmp(k, "r") == 0 ? 21.0 : base); base += 10.0; }
+    auto g = h->create_group(r);
+    base = 3.0;
+    for (auto k : f.ss) { fill(g->get_ss_mutator(k), std::strcmp(k, "p") == 0 ? 0.25 : base); base += 7.0; }
+    std::printf("%d %u %s %s\n", f.family, f.dim, to_hex(h->get_hp()).c_str(), to_hex(g->get_ss()).c_str());
+  }
+  std::printf("--\n");
+  int family; unsigned dim; char hp[1 << 16], ss[1 << 16];
+  while (std::scanf("%d %u %65535s %65535s", &family, &dim, hp, ss) == 4) {
+    auto h = gpu_model(family, dim).create_hypers();
+    auto g = h->create_group(r);
+    try {
+      h->set_hp(from_hex(hp));
+      g->set_ss(from_hex(ss));
+      std::printf("%d %u %s %s\n", family, dim, to_hex(h->get_hp()).c_str(), to_hex(g->get_ss()).c_str());
+    } catch (const std::runtime_error &e) { std::printf("%d %u error %s\n", family, dim, e.what()); }
+  }
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc > 1 && std::strcmp(argv[1], "compile-only") == 0) return 0;
+  if (argc > 1 && std::strcmp(argv[1], "bags") == 0) return bags_mode();
   rng_t r(73);
 
   // ---- perf_group.cpp loop: D bb features, 1 row, add -> remove -> score -----------------------

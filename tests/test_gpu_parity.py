@@ -24,6 +24,20 @@ def rel_err(got, want):
     return np.abs(np.asarray(got, np.float64) - want) / np.maximum(1.0, np.abs(want))
 
 
+def check(got, want, tol=RTOL):
+    """max relative error below tol; the achieved figure of every check is appended to gpurun_out/parity_achieved.jsonl
+    (one line per check, keyed by the running test) so that DESIGN.md can quote what the kernels really reach"""
+    err = float(np.max(rel_err(got, want))) if np.size(want) else 0.0
+    try:
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_achieved.jsonl"), "a") as f:
+            f.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0], "err": err, "tol": tol}) + "\n")
+    except OSError:
+        pass
+    assert err < tol, "max relative error %.3g (tolerance %.3g)" % (err, tol)
+
+
 def make_state(ctx, oracle, descs, n, k, seed=1, mask_frac=0.0, storage=None, hp=None, max_groups=None, extra_empty=0):
     arr, z = cb.synth.make_dataset(descs, n, k, seed=seed, mask_frac=mask_frac, storage=storage)
     view = cb.numpy_dataview(arr)
@@ -69,7 +83,7 @@ def test_score_rows_matches_oracle(ctx, oracle, name, mask_frac):
     assert got_gids == gids
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
     assert S.shape == want.shape == (700, 11)
-    assert np.max(rel_err(S, want)) < RTOL
+    check(S, want)
     st.close()
 
 
@@ -80,7 +94,7 @@ def test_all_kernel_shapes_agree(ctx, oracle, v, monkeypatch):
     st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 1333, 37, seed=5, mask_frac=0.03)
     _, S = st.score_rows()
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
-    assert np.max(rel_err(S, want)) < RTOL
+    check(S, want)
     _, S2 = st.score_rows(100, 101)  # a one-row range inside the table path
     assert np.array_equal(S2[0], S[100])
     st.close()
@@ -92,7 +106,7 @@ def test_direct_and_table_paths_agree(ctx, oracle, monkeypatch):
     _, S = st.score_rows()
     monkeypatch.setenv("MSB_FORCE_DIRECT", "1")
     _, Sd = st.score_rows()
-    assert np.max(rel_err(S, Sd)) < 2e-6
+    check(S, Sd, 2e-6)
     st.close()
 
 
@@ -103,7 +117,7 @@ def test_any_primitive_type_may_back_a_field(ctx, oracle, storage):
     st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 150, 4, seed=11, storage=[storage] * 4)
     _, S = st.score_rows()
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
-    assert np.max(rel_err(S, want)) < RTOL
+    check(S, want)
     st.close()
 
 
@@ -165,7 +179,7 @@ def test_single_entity_calls_follow_entity_state(ctx, oracle):
     oracle.update_rows(descs, hp, ss, counts, view, o2, n2)
     _, S = st.score_rows()
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
-    assert np.max(rel_err(S, want)) < RTOL
+    check(S, want)
     st.close()
 
 
@@ -227,7 +241,7 @@ def test_sweep_assignments_and_counts_bit_exact(ctx, oracle, mask_frac):
         u = np.array([oracle.philox_u01(73, i, sweep) for i in range(n)], np.float32)
         want_scores = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
         gpu_scores = _last_sweep_scores(st, n, k + 1)
-        assert np.max(rel_err(gpu_scores, want_scores)) < RTOL
+        check(gpu_scores, want_scores)
         assert np.array_equal(new_gpu, oracle.sample_rows(gpu_scores, u))
         assert res["moved"] == int((new_gpu != old).sum())
         oracle.update_rows(descs, hp, ss, counts, view, old, new_gpu)
@@ -276,7 +290,7 @@ def test_golden_vectors_through_the_value_abi(ctx):
         out = C.c_float()
         _lib.check(lib.msb_value_score(ctx.handle, C.byref(md), hp.ctypes.data_as(C.POINTER(C.c_double)), hp.size,
                                        ss.ctypes.data_as(C.POINTER(C.c_double)), ss.size, x.ctypes.data, C.byref(vt), C.byref(out)))
-        tol = RTOL * (4 if c["family"] == "niw" else 1)
+        tol = RTOL
         assert abs(out.value - c["expect"]) <= tol * max(1.0, abs(c["expect"])), (c["family"], c["source"], out.value, c["expect"])
 
 
@@ -316,7 +330,7 @@ def test_niw_scores_match_oracle(ctx, oracle, dim, n, k):
     st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=9, extra_empty=1)
     _, S = st.score_rows()
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
-    assert np.max(rel_err(S, want)) < 4 * RTOL
+    check(S, want)
     st.close()
 
 
@@ -325,7 +339,7 @@ def test_niw_mixed_with_scalars_and_masks(ctx, oracle):
     st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 400, 5, seed=10, mask_frac=0.1)
     _, S = st.score_rows()
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
-    assert np.max(rel_err(S, want)) < 4 * RTOL
+    check(S, want)
     res = st.sweep(seed=1, sweep=0)
     assert res["rows"] == 400
     st.close()
@@ -360,7 +374,7 @@ def test_empty_and_ragged_inputs(ctx, oracle):
     st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 33, 33, seed=12)
     _, S = st.score_rows(32, 33)
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, 32, 33)
-    assert np.max(rel_err(S, want)) < RTOL
+    check(S, want)
     st.close()
     with pytest.raises(cb.MsbError):
         cb.state(ctx, [cb.nich], max_groups=2).bind(cb.numpy_dataview(np.zeros(3, dtype=[("", np.float32, (2,))])))
@@ -373,7 +387,7 @@ def test_large_group_counts_stay_accurate(ctx, oracle):
     st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=13)
     _, S = st.score_rows(0, 512)
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, 0, 512)
-    assert np.max(rel_err(S, want)) < RTOL
+    check(S, want)
     st.close()
 
 
@@ -397,9 +411,9 @@ def test_gp_counts_beyond_the_lookup_table(ctx, oracle):
     ss, counts = ol.build_suffstats(oracle, descs, hp, view, z, k)
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
     _, S = st.score_rows()
-    assert np.max(rel_err(S, want)) < 3 * RTOL  # lgammaf(a + x) - lgammaf(x + 1) in float at x ~ 5000
+    check(S, want)
     res = st.sweep(seed=5, sweep=1)
-    assert np.max(rel_err(st.read_last_scores(), want)) < 3 * RTOL
+    check(st.read_last_scores(), want)
     st.close()
 
 
@@ -413,11 +427,11 @@ def test_niw_tensor_core_path_many_tiles_and_group_blocks(ctx, oracle, monkeypat
     rows = np.r_[0:300, 9990:10300, n - 200:n]
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), cb.numpy_dataview(view._data[rows] if view._mask is None else
                                                                                           np.ma.array(view._data[rows], mask=view._mask[rows])))
-    assert np.max(rel_err(S[rows], want)) < 4 * RTOL
+    check(S[rows], want)
     monkeypatch.setenv("MSB_NO_TENSOR", "1")   # the CUDA-core kernel on the same state
     _, S2 = st.score_rows()
-    assert np.max(rel_err(S2[rows], want)) < 4 * RTOL
-    assert np.max(rel_err(S, S2)) < 4 * RTOL
+    check(S2[rows], want)
+    check(S, S2)
     st.close()
 
 
@@ -497,7 +511,7 @@ def test_uploads_on_the_copy_stream_are_ordered_with_the_kernels(ctx, oracle):
         st.refresh()
         dev.upload(nxt)                       # next pass's records, concurrent with the scoring below
         _, S = st.score_rows()
-        assert np.max(rel_err(S, want[which])) < RTOL
+        check(S, want[which])
         row, _ = dev.get_row_bytes(n - 1)     # reads the NEW records (waits for the upload)
         assert np.array_equal(row, nxt[n - 1])
     st.close()
@@ -581,7 +595,7 @@ def test_sweep_with_niw_features_draws_bit_exactly(ctx, oracle, descs):
         res = st.sweep(seed=11, sweep=sweep)
         S = st.read_last_scores()
         want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
-        assert np.max(rel_err(S, want)) < 4 * RTOL
+        check(S, want)
         u = np.array([oracle.philox_u01(11, i, sweep) for i in range(n)], np.float32)
         new = np.searchsorted(gids, st.assignments()).astype(np.int32)
         assert np.array_equal(new, oracle.sample_rows(S, u))
@@ -592,22 +606,24 @@ def test_sweep_with_niw_features_draws_bit_exactly(ctx, oracle, descs):
     st.close()
 
 
-@pytest.mark.parametrize("name,cond", [("bb", 1.0), ("bbnc", 1.0), ("dd", 1.0), ("dm", 8.0), ("gp", 4.0), ("bnb", 4.0), ("nich", 4.0), ("mixed", 4.0), ("niw", 50.0)])
+@pytest.mark.parametrize("name,cond", [("bb", 1.0), ("bbnc", 1.0), ("dd", 1.0), ("bnb", 1.0), ("nich", 1.0), ("mixed", 1.0), ("niw", 1.0),
+                                       ("dm", 2.0), ("gp", 4.0)])
 def test_fp64_scores_within_1e12_of_the_oracle(ctx, oracle, name, cond):
-    # north_star tolerance for fp64: 1e-12 relative.  `cond` is the conditioning of the closed form itself in
-    # double (lgamma(a + x) - lgamma(a) and lgamma((nu+1)/2) - lgamma(nu/2) cancel; a d x d Cholesky for niw):
-    # the CPU oracle (glibc) and the device (CUDA libm) each carry that much rounding.
+    # north_star tolerance for fp64: 1e-12 relative -- held as stated (cond = 1) by every family but two.  gp and dm
+    # score through lgamma(a + x) - lgamma(a) with a of a few thousand on this data: each lgamma value is ~3e4, one ulp of
+    # it is 3.6e-12, and glibc (the oracle) and the CUDA math library (the device) each round it on their own, so the two
+    # closed forms cannot agree better than an ulp or two of the terms they subtract: 1.5e-12 (dm) and 3.2e-12 (gp)
+    # measured (profiles/r02_parity_achieved.txt), held to 2e-12 and 4e-12.
     descs = FAMILIES[name] if name != "niw" else [cb.niw(5), cb.niw(64)]
     n, k = (700, 9) if name != "niw" else (300, 5)
     st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=81, mask_frac=0.04, extra_empty=1)
     got_gids, S = st.score_rows_f64()
     assert got_gids == gids and S.dtype == np.float64
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, prec=64)
-    err = np.max(np.abs(S - want) / np.maximum(1.0, np.abs(want)))
-    assert err < 1e-12 * cond, err
+    check(S, want, 1e-12 * cond)
     # and the fp32 production path agrees with its own fp64 form to the fp32 tolerance
     _, S32 = st.score_rows()
-    assert np.max(rel_err(S32, S)) < (4 if name == "niw" else 1) * RTOL
+    check(S32, S)
     st.close()
 
 
@@ -652,7 +668,7 @@ def test_prefetched_conversion_swaps_column_buffers_correctly(ctx, oracle, mask_
     for nxt in ["b", "a", "b", "b", "a"]:
         dev.upload(*raws[nxt]); st.prefetch()              # next pass's data, concurrent with what follows
         _, S = st.score_rows()                             # still the CURRENT data
-        assert np.max(rel_err(S, want[cur])) < RTOL
+        check(S, want[cur])
         st.refresh()                                       # swap: nxt becomes current
         cur = nxt
     # sweeps through the prefetch path on unchanged data: identical to a state that never re-read its rows
@@ -678,7 +694,7 @@ def test_ragged_last_group_tile(ctx, oracle, k, big):
     st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=101, extra_empty=1)
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
     _, S = st.score_rows()
-    assert np.max(rel_err(S, want)) < RTOL
+    check(S, want)
     _, S1 = st.score_rows(517, 1300)
     assert np.array_equal(S1, S[517:1300])
     st.sweep(seed=4, sweep=0)
@@ -722,7 +738,7 @@ def test_checkpoint_round_trip_through_the_wire_format(ctx, oracle):
         assert st2.groupsize(g) == st.groupsize(g)
     _, S = st.score_rows()
     _, S2 = st2.score_rows()
-    assert np.max(rel_err(S2, S)) < 1e-6      # float32 fields on the wire
+    check(S2, S, 1e-6)      # float32 fields on the wire
     assert st2.suffstats_identifiers(0) == st2.groups()
     # one group's bag moved by hand (entity_state.hpp:53-54): get_suffstats -> set_suffstats
     src, dst = st.groups()[0], st.groups()[1]
@@ -757,9 +773,9 @@ def test_nich_columns_far_from_the_origin(ctx, oracle, offset):
     ss, counts = ol.build_suffstats(oracle, descs, hp, view, z, k)
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
     _, S = st.score_rows()
-    assert np.max(rel_err(S, want)) < RTOL
+    check(S, want)
     _, S64 = st.score_rows_f64()
-    assert np.max(rel_err(S64, want)) < 1e-9      # fp64 path; sum x^2 cancellation grows with offset^2
+    check(S64, want, 1e-9)      # fp64 path; sum x^2 cancellation grows with offset^2
     st.close()
 
 
@@ -783,7 +799,7 @@ def test_niw_rows_far_from_the_origin(ctx, oracle, dim, offset):
     ss, counts = ol.build_suffstats(oracle, descs, hp, view, z, k)
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view)
     _, S = st.score_rows()
-    assert np.max(rel_err(S, want)) < 4 * RTOL
+    check(S, want)
     # a pass over re-uploaded rows keeps the centring (refresh path)
     raw, mraw = view.raw()
     view.to_device(ctx).upload(np.ascontiguousarray(raw), np.ascontiguousarray(mraw))
@@ -791,7 +807,7 @@ def test_niw_rows_far_from_the_origin(ctx, oracle, dim, offset):
     _, S2 = st.score_rows()
     assert np.array_equal(S2, S)
     st.sweep(seed=3, sweep=0)
-    assert np.max(rel_err(st.read_last_scores(), want)) < 4 * RTOL
+    check(st.read_last_scores(), want)
     st.close()
 
 
@@ -820,7 +836,7 @@ def test_bbnc_group_parameter_is_a_beta_draw_and_survives_everything(ctx, oracle
     _, S = st.score_rows(0, 50)
     ss[3, 0] = 0.25
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, 0, 50)
-    assert np.max(rel_err(S, want)) < RTOL
+    check(S, want)
     blob = st.serialize()                                             # BetaBernoulliNonConj messages are in-tree (schema.proto:6-19)
     st3 = cb.state.deserialize(ctx, descs, view, blob)
     assert abs(st3.get_suffstats(0, gids[3], "p")[0] - 0.25) < 1e-7
@@ -952,7 +968,7 @@ def test_dm_score_kernels_over_their_branches(ctx, oracle, C, alpha, total, monk
     _, S64 = st.score_rows_f64()
     assert np.max(np.abs(S64 - want) / np.maximum(1.0, np.abs(want))) < 2e-11
     _, S = st.score_rows()
-    assert np.max(rel_err(S, want)) < RTOL
+    check(S, want)
     if C <= 300:
         monkeypatch.setenv("MSB_DM_NO_TILE", "1")
         _, S64b = st.score_rows_f64()
@@ -990,7 +1006,7 @@ def test_niw_tensor_core_path_with_badly_scaled_and_correlated_columns(ctx, orac
     want = oracle.score_rows(descs, hp_flat, ss, ol.logprior(counts, 1.0), view, prec=64)
     res = st.sweep(seed=3, sweep=0)         # the sweep takes the tensor-core kernel (blocked layout)
     S = st.read_last_scores()
-    assert np.max(rel_err(S, want)) < 4 * RTOL
+    check(S, want)
     st.close()
 
 
@@ -1025,14 +1041,14 @@ def test_single_rows_through_the_tensor_core_niw_path(ctx, oracle):
     st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=9)
     want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, prec=64)
     _, S = st.score_rows(137, 138)
-    assert np.max(rel_err(S[0], want[137])) < 4 * RTOL
+    check(S[0], want[137])
     eid = 11
     st.remove_value(eid)
     a = z.astype(np.int32).copy(); b = a.copy(); b[eid] = -1
     oracle.update_rows(descs, hp, ss, counts, view, a, b)
     _, s = st.score_value(eid)
     w = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, eid, eid + 1, prec=64)[0]
-    assert np.max(rel_err(s, w)) < 4 * RTOL
+    check(s, w)
     st.close()
 
 
@@ -1114,3 +1130,70 @@ def test_gibbs_chain_over_four_entities_visits_partitions_with_their_posterior_p
     total = sum(visits.values())
     worst = max(abs(visits.get(k, 0) / total - pk) for k, pk in exact.items())
     assert worst < 0.04, (worst, {k: (round(visits.get(k, 0) / total, 3), round(pk, 3)) for k, pk in exact.items()})
+
+
+# ---- the tolerance per (row, group, FEATURE), not on a sum over features ---------------------------------------------
+@pytest.mark.parametrize("fam", ["bb", "dd", "gp", "bnb", "nich", "bbnc"])
+@pytest.mark.parametrize("rows_per_group", [40, 4000])
+def test_one_feature_scores_are_within_tolerance_per_row_group_feature(ctx, oracle, fam, rows_per_group):
+    """D = 1: the score matrix is log(pseudocount) + ONE feature's predictive, so the 1e-5 of north_star is held per
+    (row, group, feature) term -- with small groups (the prior dominates) and with thousands of rows per group (the regime
+    in which the reference's own fp32 formulas lose digits)."""
+    desc = {"bb": cb.bb, "dd": cb.dd(23), "gp": cb.gp, "bnb": cb.bnb, "nich": cb.nich, "bbnc": cb.bbnc}[fam]
+    k = 6
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, [desc], rows_per_group * k, k, seed=17, extra_empty=1)
+    hi = min(512, rows_per_group * k)
+    _, S = st.score_rows(0, hi)
+    want = oracle.score_rows([desc], hp, ss, ol.logprior(counts, 1.0), view, 0, hi)
+    check(S, want)
+    # the feature term itself (the CRP term taken off both sides): relative to the term, floor 1 like everywhere else
+    lp = ol.logprior(counts, 1.0)[None, :]
+    check(S - lp, want - lp)
+    st.close()
+
+
+# ---- the shapes of BASELINE.json: full K and D (they select the tile shapes and k-tile grids the bench runs), rows cut down
+BASELINE_SHAPES = {
+    "C2": ([cb.dd(256)] * 32, 200, [np.uint8] * 32),
+    "C3": ([cb.nich] * 128, 500, None),
+    "C4": ([cb.niw(64)], 256, None),
+    "C5": ([cb.bb] * 64 + [cb.gp] * 64 + [cb.nich] * 64 + [cb.dd(16)] * 64, 1000, None),
+}
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("name", sorted(BASELINE_SHAPES))
+def test_parity_at_the_baseline_shapes(ctx, oracle, name):
+    descs, k, storage = BASELINE_SHAPES[name]
+    n = 8 * k if name != "C4" else 40 * k          # every group populated; niw needs n > dim rows per group to be well conditioned
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=73, storage=storage)
+    lo, hi = 0, min(n, 1536)
+    _, S = st.score_rows(lo, hi)
+    want = oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view, lo, hi, nthreads=8)
+    check(S, want)
+    # and the sweep's own kernels (blocked layout, tile / blocked sampler) on the same shape: draws replayed from its scores
+    old = z.astype(np.int32)
+    res = st.sweep(seed=73, sweep=3)
+    Ssw = st.read_last_scores()
+    check(Ssw[lo:hi], want)
+    u = oracle.philox_u01_rows(73, 0, n, 3)
+    new = np.searchsorted(gids, st.assignments()).astype(np.int32)
+    assert np.array_equal(new, oracle.sample_rows(Ssw, u))
+    assert res["moved"] == int((new != old).sum())
+    oracle.update_rows(descs, hp, ss, counts, view, old, new)
+    assert all(st.groupsize(g) == counts[c] for c, g in enumerate(gids))
+    st.close()
+
+
+def test_dd_counts_set_through_the_abi_are_scored_at_once(ctx, oracle):
+    """set_ss("counts") on a dd feature also moves count_sum (the predictive's denominator): scoring right after the
+    call, with no sweep in between, sees the new group (the stale count_sum)."""
+    descs = [cb.dd(6)]
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, 120, 3, seed=4)
+    new_counts = np.array([5, 0, 7, 1, 0, 30], np.float64)
+    st.set_suffstats(0, gids[1], "counts", new_counts)
+    assert st.get_suffstats(0, gids[1], "count_sum")[0] == new_counts.sum()
+    ss[1, 0] = new_counts.sum(); ss[1, 1:7] = new_counts
+    _, S = st.score_rows()
+    check(S, oracle.score_rows(descs, hp, ss, ol.logprior(counts, 1.0), view))
+    st.close()
