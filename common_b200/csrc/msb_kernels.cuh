@@ -1,6 +1,7 @@
 // msb_kernels.cuh -- sm_100a kernels of the hot path (see DESIGN.md for the
 // data layout, the per-kernel roofline and the algorithmic bytes).
 #pragma once
+#include <cstddef>
 #include <string>
 #include <vector>
 
@@ -106,8 +107,9 @@ __device__ __forceinline__ double load_prim(const uint8_t *p, uint32_t prim) {
   }
 }
 __device__ __forceinline__ uint32_t prim_size(uint32_t prim) {
-  const uint32_t sz[11] = {1, 1, 1, 2, 2, 4, 4, 8, 8, 4, 8};
-  return sz[prim];
+  // sizes {1, 1, 1, 2, 2, 4, 4, 8, 8, 4, 8} of type_info.h:10-34 as nibbles of one constant (an indexed local array costs every
+  // thread eleven local-memory stores per call: 4 % of the ingest kernel's instructions in the round-2 profile)
+  return (uint32_t)((0x84884422111ull >> (4u * prim)) & 0xFull);
 }
 
 __global__ void pack_kernel(const uint8_t *__restrict__ data, const uint8_t *__restrict__ mask, size_t n,
@@ -202,12 +204,19 @@ __global__ void scorecol_kernel(const FeatDev *__restrict__ feats, int nfeat, si
 // row r and writes the Value-typed column, the score column and (by ballot) the slow-path mask.  The records
 // are read from HBM exactly once.  Needs the gp table sizes (refresh path; bind sizes them first).
 // rowsize and maskrowsize are multiples of 4 here (the host falls back to the two-kernel path otherwise).
-template <int TR>
-__global__ void __launch_bounds__(TR)
+// NS slices of TR threads each: thread (r, slice) converts the features d = slice, slice + NS, ... of row r, so a warp is
+// still 32 consecutive rows of one feature (coalesced column stores, one ballot per slow-path word) and a block keeps
+// NS * TR / 32 = 16 warps busy whatever the record size (round 1: one thread per row walked all D features -- 2 warps per
+// scheduler, 7 % of the HBM roof on C5).  TR is chosen by the host so that several blocks fit in an SM's shared memory and
+// one block's tile load overlaps another's conversion.  The per-feature descriptors are read from global memory
+// (warp-uniform, L1-resident).
+template <int TR, int NS>
+__global__ void __launch_bounds__(TR * NS)
 ingest_tile_kernel(const uint8_t *__restrict__ data, const uint8_t *__restrict__ mask, size_t n, size_t n_pad,
                    uint32_t rowwords, uint32_t maskwords, const FeatDev *__restrict__ feats, int nfeat,
                    uint32_t *__restrict__ any_slow) {
   extern __shared__ uint32_t tile[];
+  constexpr int NT = TR * NS;
   const uint32_t pitch = rowwords + 1, mpitch = maskwords + 1;
   uint32_t *mtile = tile + (size_t)TR * pitch;
   const size_t row0 = (size_t)blockIdx.x * TR;
@@ -215,20 +224,40 @@ ingest_tile_kernel(const uint8_t *__restrict__ data, const uint8_t *__restrict__
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(data) + row0 * rowwords;
     const uint32_t total = (uint32_t)rows_here * rowwords;
-    for (uint32_t g = threadIdx.x; g < total; g += TR) tile[(g / rowwords) * pitch + g % rowwords] = src[g];
+    if ((rowwords & 3u) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {  // 16-byte loads, 4-byte padded stores
+      const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
+      for (uint32_t g = threadIdx.x; g < total / 4; g += NT) {
+        const uint4 v = __ldg(src4 + g);
+        const uint32_t w = g * 4, r = w / rowwords, c = w - r * rowwords;
+        uint32_t *dst = tile + r * pitch + c;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+      }
+    } else {
+      for (uint32_t g = threadIdx.x; g < total; g += NT) tile[(g / rowwords) * pitch + g % rowwords] = src[g];
+    }
     if (mask) {
       const uint32_t *msrc = reinterpret_cast<const uint32_t *>(mask) + row0 * maskwords;
       const uint32_t mtotal = (uint32_t)rows_here * maskwords;
-      for (uint32_t g = threadIdx.x; g < mtotal; g += TR) mtile[(g / maskwords) * mpitch + g % maskwords] = msrc[g];
+      for (uint32_t g = threadIdx.x; g < mtotal; g += NT) mtile[(g / maskwords) * mpitch + g % maskwords] = msrc[g];
     }
   }
   __syncthreads();
-  const size_t row = row0 + threadIdx.x;   // n_pad is a multiple of TR: every thread owns a (possibly padding) row
+  const int r = threadIdx.x % TR, slice = threadIdx.x / TR;
+  const size_t row = row0 + r;   // n_pad is a multiple of TR: every thread owns a (possibly padding) row
   const bool live = row < n;
-  const uint8_t *rec = reinterpret_cast<const uint8_t *>(tile + (size_t)threadIdx.x * pitch);
-  const uint8_t *mrec = reinterpret_cast<const uint8_t *>(mtile + (size_t)threadIdx.x * mpitch);
-  for (int d = 0; d < nfeat; d++) {
-    const FeatDev f = feats[d];
+  const uint8_t *rec = reinterpret_cast<const uint8_t *>(tile + (size_t)r * pitch);
+  const uint8_t *mrec = reinterpret_cast<const uint8_t *>(mtile + (size_t)r * mpitch);
+  static_assert(sizeof(FeatDev) % 16 == 0 && offsetof(FeatDev, sx_off) == 112, "the descriptor is fetched as seven 16-byte loads");
+  for (int d = slice; d < nfeat; d += NS) {
+    // the descriptor (warp-uniform, L1-resident) in seven independent 16-byte loads: one wait per feature instead of one
+    // per field (the field-by-field form spent half of the kernel's warp samples on those dependent loads)
+    FeatDev f;
+    {
+      const uint4 *src = reinterpret_cast<const uint4 *>(feats + d);
+      uint4 *dst = reinterpret_cast<uint4 *>(&f);
+#pragma unroll
+      for (int i = 0; i < 7; i++) dst[i] = __ldg(src + i);
+    }
     bool masked = false;
     if (mask && live)
       for (uint32_t i = 0; i < f.src_n; i++) masked |= (mrec[f.msk_off + i] != 0);
@@ -258,35 +287,65 @@ ingest_tile_kernel(const uint8_t *__restrict__ data, const uint8_t *__restrict__
       }
       continue;
     }
-    const double v = live ? load_prim(rec + f.src_off, f.src_prim) : 0.0;
     uint32_t out;
     bool slow = false;
+    const uint8_t *p = rec + f.src_off;
+    // 4-byte sources at 4-byte offsets (the usual record): one aligned shared-memory load instead of four byte loads
+    const bool word = (f.src_off & 3u) == 0;
+    const uint32_t w32 = word ? *reinterpret_cast<const uint32_t *>(p) : 0u;
     if (f.kind == KIND_NICH) {
-      const float x = masked ? CUDART_NAN_F : (float)v;
+      // the cast of runtime_type.hpp:145-166 to the model's float Value: exact for a float source, through double otherwise
+      float x;
+      if (f.src_prim == 9) { if (word) x = __uint_as_float(w32); else memcpy(&x, p, 4); }
+      else x = (float)load_prim(p, f.src_prim);
+      if (masked) x = CUDART_NAN_F;
       if (live) ((float *)f.col)[row] = x;
       slow = live && masked;
       out = (slow || !live) ? 0u : __float_as_uint((float)((double)x - f.asum));
-    } else if (f.kind == KIND_GP) {
-      uint32_t x = v < 0.0 ? 0u : (v >= 4294967294.0 ? 4294967294u : (uint32_t)v);
-      if (masked || !live) x = GP_SENTINEL;
-      if (live) ((uint32_t *)f.col)[row] = x;
-      slow = x != GP_SENTINEL && x >= f.ncat;
-      out = x < f.ncat ? x : f.ncat;
     } else {
-      uint32_t x = f.ncat;
-      if (live && !masked) {
-        if (f.family == FAM_BB) x = (v != 0.0) ? 1u : 0u;
-        else if (v >= 0.0 && v < (double)f.ncat) x = (uint32_t)v;
+      // unsigned integer Values (bool, category, count): the common integer sources convert without a trip through double;
+      // `big` marks values no uint32 Value holds (they saturate like the double path), `neg` negative sources
+      uint32_t xi = 0;
+      bool neg = false, big = false;
+      switch (f.src_prim) {
+        case 0: xi = (*p != 0); break;
+        case 2: xi = *p; break;
+        case 4: { uint16_t v; memcpy(&v, p, 2); xi = v; break; }
+        case 6: if (word) xi = w32; else memcpy(&xi, p, 4); break;
+        case 1: { const int8_t v = *(const int8_t *)p; neg = v < 0; xi = (uint32_t)v; break; }
+        case 3: { int16_t v; memcpy(&v, p, 2); neg = v < 0; xi = (uint32_t)v; break; }
+        case 5: { int32_t v; if (word) v = (int32_t)w32; else memcpy(&v, p, 4); neg = v < 0; xi = (uint32_t)v; break; }
+        default: {
+          const double v = live ? load_prim(p, f.src_prim) : 0.0;
+          neg = v < 0.0; big = v >= 4294967294.0;
+          xi = (neg || big) ? 0u : (uint32_t)v;
+          if (f.kind != KIND_GP && f.family == FAM_BB) xi = (v != 0.0) ? 1u : 0u, neg = big = false;   // any non-zero value is "true"
+          else if (f.kind != KIND_GP && !neg && !big && !(v < (double)f.ncat)) big = true;                // includes fractions >= ncat, NaN
+          break;
+        }
       }
-      if (live) {
-        if (f.coltype == COL_U8) ((uint8_t *)f.col)[row] = (uint8_t)x;
-        else if (f.coltype == COL_U16) ((uint16_t *)f.col)[row] = (uint16_t)x;
-        else ((uint32_t *)f.col)[row] = x;
-      }
-      out = x;
-      if (f.binform) {
-        slow = live && x >= f.ncat;
-        out = __float_as_uint(x == 1u ? 1.0f : 0.0f);
+      if (f.kind == KIND_GP) {
+        uint32_t x = neg ? 0u : (big || xi >= 4294967294u ? 4294967294u : xi);
+        if (masked || !live) x = GP_SENTINEL;
+        if (live) ((uint32_t *)f.col)[row] = x;
+        slow = x != GP_SENTINEL && x >= f.ncat;
+        out = x < f.ncat ? x : f.ncat;
+      } else {
+        uint32_t x = f.ncat;
+        if (live && !masked) {
+          if (f.family == FAM_BB) x = (xi != 0u || neg) ? 1u : 0u;
+          else if (!neg && !big && xi < f.ncat) x = xi;
+        }
+        if (live) {
+          if (f.coltype == COL_U8) ((uint8_t *)f.col)[row] = (uint8_t)x;
+          else if (f.coltype == COL_U16) ((uint16_t *)f.col)[row] = (uint16_t)x;
+          else ((uint32_t *)f.col)[row] = x;
+        }
+        out = x;
+        if (f.binform) {
+          slow = live && x >= f.ncat;
+          out = __float_as_uint(x == 1u ? 1.0f : 0.0f);
+        }
       }
     }
     if (row < n_pad) const_cast<uint32_t *>(f.scol)[row] = out;

@@ -20,9 +20,13 @@
 //   * thread 0 streams A half-tiles (16 KB) into a 6-deep shared-memory ring with bulk copies;
 //   * one lane of warp 8 keeps the current group block's B (64 KB) resident and issues the MMAs: per 128-row tile four
 //     k-steps x three products, N shrinking 256, 192, 128, 64 (W_k is lower triangular), two 256-column TMEM accumulators;
-//   * epilogue warps 4-7 (even tiles, accumulator 0) and 9-12 (odd tiles, accumulator 1): tcgen05.ld of their 32 TMEM
-//     lanes, bias, square-sum per group, log1p, store -- in the sweep's blocked layout a warp's 32 lanes are one 32-row
-//     block, so every store is a full 128-byte line;
+//   * sixteen epilogue warps: even tiles (accumulator 0) and odd tiles (accumulator 1) have their own set of eight, and
+//     inside a set the four groups of the block are split two and two -- per TMEM lane quadrant one warp reads the
+//     columns of groups 0-1 and another those of groups 2-3 (tcgen05.ld 32x32b.x16), bias, square-sum per group,
+//     log1p, store.  What paces the kernel is how long an accumulator stays occupied after its last MMA (the MMAs of
+//     tile t + 2 wait for the readers of tile t): with four warps per accumulator that was ~2800 cycles against ~1000
+//     of MMA work per tile; two readers per quadrant halve it.  In the sweep's blocked layout a warp's 32 lanes are
+//     one 32-row block, so every store is a full 128-byte line;
 //   * work items = (slice of <= 32 row tiles) x (group block), dealt round-robin to the CTAs, group block fastest: even
 //     load and A shared through L2.
 // Synchronisation is mbarrier-only (bulk-copy complete_tx, tcgen05.commit); every wait is bounded (trap).
@@ -38,7 +42,8 @@ using niwtc::D;
 using niwtc::GB;
 using niwtc::TM;
 using niwtc::TN;
-constexpr int THREADS = 13 * 32;            // warps 0-3 producers, 4-7 and 9-12 epilogue, 8 MMA issuer
+constexpr int EPI_WARPS = 16;               // epilogue warps: 2 tile parities x 2 group pairs x 4 TMEM lane quadrants
+constexpr int THREADS = (2 + EPI_WARPS) * 32;   // warp 0 A producer, warp 1 MMA issuer, warps 2-17 epilogue
 constexpr int A_HALF_BYTES = TM * 32 * 2;   // one k-half (32 k) of one part (hi or lo): 8 KB
 constexpr int NA = 6;                        // A half-tile buffers in the ring (hi + lo each): the copies run up to three tiles ahead of the MMAs
 constexpr int A_BYTES = NA * 2 * A_HALF_BYTES;   // [buffer][part]: 64 KB
@@ -234,11 +239,11 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(smem_u32(&bars[ACC_FULL + i]), 1);  // acc_full: tcgen05.commit
-      mbar_init(smem_u32(&bars[ACC_EMPTY + i]), 4); // acc_empty: one arrive per warp of the set that owns the accumulator
+      mbar_init(smem_u32(&bars[ACC_EMPTY + i]), EPI_WARPS / 2); // acc_empty: one arrive per warp of the set that owns the accumulator
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {  // TMEM: all 512 columns (2 accumulators x 256)
+  if (warp == 1) {  // TMEM: all 512 columns (2 accumulators x 256)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -247,7 +252,7 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp == 0) {
     // ===== producer: one thread streams the pre-converted A operand (niw_convert_a16_kernel: scaled fp16 hi / lo parts,
     // already in core-matrix layout, 16 KB per half-tile) into the ring with bulk copies.  Converting in this kernel,
     // as the tf32 version does, repeats the conversion once per group block (64 times at C4) and was what the MMAs
@@ -268,7 +273,7 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
       }
     }
     __syncwarp();
-  } else if (warp == 8) {
+  } else if (warp == 1) {
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0) {
       long long h = 0, t = 0;
@@ -325,13 +330,15 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warps 4..7 take the even tiles (accumulator 0), warps 9..12 the odd ones (accumulator 1); TMEM lanes
-    // 32 * (warp % 4) .. + 31.  A tile's epilogue is a chain of waits (accumulator ready -> TMEM loads -> arithmetic ->
-    // release): with one set of warps the chains of consecutive tiles run back to back and their latency, not their
-    // instruction count, set the pace; two sets overlap them.
-    const int ew = warp & 3;
-    const int set = warp >= 9 ? 1 : 0;
-    const int etid = ew * 32 + lane;  // 0..127 within the set
+    // ===== epilogue: warps 2..17 in four groups of four (one warp per TMEM lane quadrant = warp id % 4): group index
+    // bit 0 = tile parity (accumulator), bit 1 = which two of the block's four groups the warp reduces.  A tile's epilogue
+    // is a chain of waits (accumulator ready -> TMEM loads -> arithmetic -> release), and the MMAs of tile t + 2 cannot
+    // start before the readers of tile t have released the accumulator.
+    const int e = warp - 2;
+    const int ew = warp & 3;                 // TMEM lanes 32 ew .. 32 ew + 31 (fixed by the hardware: warp id % 4)
+    const int set = (e >> 2) & 1;            // tile parity
+    const int gh = e >> 3;                   // groups 2 gh, 2 gh + 1 of the block
+    const int etid = ((gh << 2) | (e & 3)) * 32 + lane;  // 0..255 within the set
     long long t = 0;
     int staged_gb = -1;
     float *sb = sBias + (size_t)set * SB_FLOATS;
@@ -344,8 +351,8 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
       const int acc = set;
       // this group block's bias and coefficients (each set keeps its own copy): staged when the block changes, not per tile
       if (gb != staged_gb) {
-        if (set == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-        for (int i = etid; i < SB_FLOATS; i += 128) {
+        if (set == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
+        for (int i = etid; i < SB_FLOATS; i += 256) {
           float v = 0.f;
           if (i < TN) {  // bias' = b r_k
             const int k = gb * GB + i / D;
@@ -356,36 +363,36 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
           }
           sb[i] = v;
         }
-        if (set == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (set == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
         staged_gb = gb;
       }
       const size_t row = row_lo + (size_t)rt * TM + ew * 32 + lane;
-      float4 *dst = reinterpret_cast<float4 *>(scores + (row - row_lo) * ld + (size_t)gb * GB);
-      float *dstb = scores + (((size_t)rt * (TM / 32) + ew) * ld + (size_t)gb * GB) * 32 + lane;
-      float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int g0 = 2 * gh;
+      float2 *dst = reinterpret_cast<float2 *>(scores + (row - row_lo) * ld + (size_t)gb * GB + g0);
+      float *dstb = scores + (((size_t)rt * (TM / 32) + ew) * ld + (size_t)gb * GB + g0) * 32 + lane;
+      float2 old = make_float2(0.f, 0.f);
       if (row < row_hi) {
-        if (base) old = __ldg(reinterpret_cast<const float4 *>(base + (size_t)gb * GB));
-        else if (blocked & 1) old = make_float4(dstb[0], dstb[32], dstb[64], dstb[96]);
+        if (base) old = __ldg(reinterpret_cast<const float2 *>(base + (size_t)gb * GB + g0));
+        else if (blocked & 1) old = make_float2(dstb[0], dstb[32]);
         else old = *dst;
       }
       mbar_wait(smem_u32(&bars[ACC_FULL + acc]), (uint32_t)((t >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float q[GB];
+      float q[2];
       {
-        float2 q2[GB];
-#pragma unroll
-        for (int g = 0; g < GB; g++) q2[g] = make_float2(0.f, 0.f);
-        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN);
-        uint32_t r[2][32];
-        niwtc::tmem_ld32_issue(tbase, r[0]);
+        float2 q2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        // columns of the accumulator: block ib = i / 8 holds [g][i % 8]; this warp's two groups are 16 contiguous columns of it
+        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN) + (uint32_t)(gh * 16);
+        uint32_t r[2][16];
+        tmem_ld16_issue(tbase, r[0]);
 #pragma unroll
         for (int ib = 0; ib < D / 8; ib++) {
           niwtc::tmem_ld_wait();
-          if (ib + 1 < D / 8) niwtc::tmem_ld32_issue(tbase + (uint32_t)(ib + 1) * 32u, r[(ib + 1) & 1]);
+          if (ib + 1 < D / 8) tmem_ld16_issue(tbase + (uint32_t)(ib + 1) * 32u, r[(ib + 1) & 1]);
 #pragma unroll
-          for (int g = 0; g < GB; g++) {
-            const float4 b0 = *reinterpret_cast<const float4 *>(sb + g * D + ib * 8);
-            const float4 b1 = *reinterpret_cast<const float4 *>(sb + g * D + ib * 8 + 4);
+          for (int g = 0; g < 2; g++) {
+            const float4 b0 = *reinterpret_cast<const float4 *>(sb + (g0 + g) * D + ib * 8);
+            const float4 b1 = *reinterpret_cast<const float4 *>(sb + (g0 + g) * D + ib * 8 + 4);
             const uint32_t *v = r[ib & 1] + g * 8;
             float2 y;
             y = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(-b0.x, -b0.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
@@ -394,27 +401,27 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
             y = __fadd2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(-b1.z, -b1.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
           }
         }
-#pragma unroll
-        for (int g = 0; g < GB; g++) q[g] = q2[g].x + q2[g].y;
+        q[0] = q2[0].x + q2[0].y;
+        q[1] = q2[1].x + q2[1].y;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
       if (row < row_hi) {
-        float o[GB] = {old.x, old.y, old.z, old.w};
+        float o[2] = {old.x, old.y};
 #pragma unroll
-        for (int g = 0; g < GB; g++) {
-          const int k = gb * GB + g;
+        for (int g = 0; g < 2; g++) {
+          const int k = gb * GB + g0 + g;
           if (k < ncols && q[g] == q[g]) {  // NaN = masked row: contributes nothing
-            const float c0 = sc[g * 4 + 0], c1 = sc[g * 4 + 1], idof = sc[g * 4 + 2];
+            const float c0 = sc[(g0 + g) * 4 + 0], c1 = sc[(g0 + g) * 4 + 1], idof = sc[(g0 + g) * 4 + 2];
             o[g] += c0 + c1 * log1pf(q[g] * idof);
           }
         }
         if (blocked & 1) {
-#pragma unroll
-          for (int g = 0; g < GB; g++) dstb[g * 32] = o[g];
+          dstb[0] = o[0];
+          dstb[32] = o[1];
         } else {
-          *dst = make_float4(o[0], o[1], o[2], o[3]);
+          *dst = make_float2(o[0], o[1]);
         }
       }
     }
@@ -422,7 +429,7 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }

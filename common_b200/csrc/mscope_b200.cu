@@ -144,6 +144,8 @@ struct msb_state {
   size_t region_rows = 0, max_chunk_rows = 0;
   std::vector<FeatDev> sc_host;  // the score kernel's walk order (host copy of d_feats_scalar)
   uint64_t bundle_key = 0;       // (tile shape, stage bytes) the bundle layout in d_feats_scalar was made for; 0 = none
+  std::vector<FeatDev> sc_host_b;  // the same pair for the second column buffer (msb_state_prefetch): its descriptors point
+  uint64_t bundle_key_b = 0;       // into the other slab, so each buffer keeps its own list and its own layout state
   bool has_bbnc = false, has_dm = false;  // has_dm: a vector count feature scored by its own kernel after the scalar ones (like niw)
   uint64_t group_seed = 0x6d73625f62626e63ull;  // Philox key of the per-group parameter draws (bbnc: p ~ Beta(alpha, beta))
   bool has_niw = false, has_scalar = false, tables_only = false, has_dd = false, has_nich = false;
@@ -248,7 +250,10 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   CU_TRY(opt_in_smem((score_bundle_kernel<4, 16, 16, true>), c->smem_optin));
   CU_TRY(opt_in_smem((sample_tile_kernel<4, false>), c->smem_optin));
   CU_TRY(opt_in_smem((sample_tile_kernel<4, true>), c->smem_optin));
-  CU_TRY(opt_in_smem(ingest_tile_kernel<128>, c->smem_optin));
+  CU_TRY(opt_in_smem((ingest_tile_kernel<512, 1>), c->smem_optin));
+  CU_TRY(opt_in_smem((ingest_tile_kernel<256, 2>), c->smem_optin));
+  CU_TRY(opt_in_smem((ingest_tile_kernel<128, 4>), c->smem_optin));
+  CU_TRY(opt_in_smem((ingest_tile_kernel<64, 8>), c->smem_optin));
   CU_TRY(opt_in_smem(niw_score_data_kernel, c->smem_optin - 1024));
   CU_TRY(opt_in_smem(niw_score_f64_kernel, c->smem_optin - 1024));
   CU_TRY(opt_in_smem(niw_prepare_kernel, c->smem_optin - 1024));  // it also has a few bytes of static shared memory
@@ -734,6 +739,32 @@ static void layout_chunks(msb_state *st) {
   st->feats_dirty = true;
 }
 
+// Fused AoS -> SoA conversion (ingest_tile_kernel): rows per block chosen so that several blocks share an SM (a tile of at
+// most 56 KB) -- one block's tile load then overlaps another's conversion; 512 threads per block whatever the tile.
+static size_t ingest_tile_bytes(const msb_dataview *dv, size_t TR) {
+  return ((size_t)TR * (dv->rowsize / 4 + 1) + (dv->d_mask ? (size_t)TR * (dv->maskrowsize / 4 + 1) : 0)) * 4;
+}
+static int ingest_rows_per_block(const msb_ctx *ctx, const msb_dataview *dv) {
+  for (int TR : {512, 256, 128}) if (ingest_tile_bytes(dv, TR) <= 56 * 1024) return TR;
+  return ingest_tile_bytes(dv, 64) <= ctx->smem_optin ? 64 : 0;
+}
+static cudaError_t launch_ingest_tile(msb_ctx *ctx, cudaStream_t stream, int TR, const msb_dataview *dv, size_t n_pad, const FeatDev *d_feats,
+                                      int D, uint32_t *d_flags) {
+  const size_t smem = ingest_tile_bytes(dv, TR);
+  const unsigned grid = (unsigned)(n_pad / TR);
+  const uint32_t rw = (uint32_t)(dv->rowsize / 4), mw = (uint32_t)(dv->maskrowsize / 4);
+  ctx->prof.begin("ingest_tile_kernel", stream);
+  switch (TR) {
+    case 512: ingest_tile_kernel<512, 1><<<grid, 512, smem, stream>>>(dv->d_data, dv->d_mask, dv->n, n_pad, rw, mw, d_feats, D, d_flags); break;
+    case 256: ingest_tile_kernel<256, 2><<<grid, 512, smem, stream>>>(dv->d_data, dv->d_mask, dv->n, n_pad, rw, mw, d_feats, D, d_flags); break;
+    case 128: ingest_tile_kernel<128, 4><<<grid, 512, smem, stream>>>(dv->d_data, dv->d_mask, dv->n, n_pad, rw, mw, d_feats, D, d_flags); break;
+    default: ingest_tile_kernel<64, 8><<<grid, 512, smem, stream>>>(dv->d_data, dv->d_mask, dv->n, n_pad, rw, mw, d_feats, D, d_flags); break;
+  }
+  ctx->prof.end(stream);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
 // per-feature "some cell needs the slow path" flags -> host; decides the tables-only kernel variant
 static int ingest_flags(msb_state *st, bool force_dirty) {
   msb_ctx *ctx = st->ctx;
@@ -762,13 +793,11 @@ static int ingest(msb_state *st, bool size_tables) {
   MSB_TRY(sync_small(st));
   CU_TRY(dv_acquire(dv));
   // refresh path: one fused pass over the records staged in shared memory (they are read from HBM once)
-  constexpr int TR = 128;
-  const size_t tile_bytes = ((size_t)TR * (dv->rowsize / 4 + 1) + (dv->d_mask ? (size_t)TR * (dv->maskrowsize / 4 + 1) : 0)) * 4;
-  if (!size_tables && dv->n && st->has_scalar && dv->rowsize % 4 == 0 && (!dv->d_mask || dv->maskrowsize % 4 == 0) &&
-      tile_bytes <= ctx->smem_optin && !getenv("MSB_NO_FUSED_INGEST")) {
+  const int TR = ingest_rows_per_block(ctx, dv);
+  static const bool no_fused = getenv("MSB_NO_FUSED_INGEST") != nullptr;
+  if (!size_tables && dv->n && st->has_scalar && dv->rowsize % 4 == 0 && (!dv->d_mask || dv->maskrowsize % 4 == 0) && TR && !no_fused) {
     CU_TRY(cudaMemsetAsync(st->d_flags, 0, sizeof(uint32_t) * D, ctx->stream));
-    LAUNCH(ctx, ingest_tile_kernel<TR>, (unsigned)(st->n_pad / TR), TR, tile_bytes, dv->d_data, dv->d_mask, dv->n, st->n_pad,
-           (uint32_t)(dv->rowsize / 4), (uint32_t)(dv->maskrowsize / 4), st->d_feats, (int)D, st->d_flags);
+    CU_TRY(launch_ingest_tile(ctx, ctx->stream, TR, dv, st->n_pad, st->d_feats, (int)D, st->d_flags));
     CU_TRY(dv_release(dv));
     return ingest_flags(st, false);
   }
@@ -965,6 +994,8 @@ extern "C" MSB_API int msb_state_refresh(msb_state *st) {
   std::swap(st->cols, st->cols_b);
   std::swap(st->d_feats, st->d_feats_b);
   std::swap(st->d_feats_scalar, st->d_feats_scalar_b);
+  std::swap(st->sc_host, st->sc_host_b);
+  std::swap(st->bundle_key, st->bundle_key_b);
   bool any = false, changed = st->feats_b_dirty;
   for (size_t d = 0; d < st->D; d++) {
     // fields that are not per buffer follow the buffer that was active until now
@@ -994,11 +1025,10 @@ extern "C" MSB_API int msb_state_prefetch(msb_state *st) {
   msb_ctx *ctx = st->ctx;
   msb_dataview *dv = st->dv;
   CU_TRY(cudaSetDevice(ctx->device));
-  constexpr int TR = 128;
   const size_t D = st->D;
-  const size_t tile_bytes = ((size_t)TR * (dv->rowsize / 4 + 1) + (dv->d_mask ? (size_t)TR * (dv->maskrowsize / 4 + 1) : 0)) * 4;
+  const int TR = ingest_rows_per_block(ctx, dv);
   const bool fused_ok = dv->n && dv->owns && st->has_scalar && dv->rowsize % 4 == 0 && (!dv->d_mask || dv->maskrowsize % 4 == 0) &&
-                        tile_bytes <= ctx->smem_optin && st->col_slab;
+                        TR && st->col_slab;
   if (!fused_ok || st->prefetch_pending) return MSB_OK;  // msb_state_refresh converts on the compute stream instead
   if (!st->ev_swap) {
     CU_TRY(cudaEventCreateWithFlags(&st->ev_swap, cudaEventDisableTiming));
@@ -1032,11 +1062,7 @@ extern "C" MSB_API int msb_state_prefetch(msb_state *st) {
   }
   if (st->swap_recorded) CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, st->ev_swap, 0));  // the last readers of that buffer are done
   CU_TRY(cudaMemsetAsync(st->d_flags_b, 0, sizeof(uint32_t) * D, ctx->copy_stream));
-  ingest_tile_kernel<TR><<<(unsigned)(st->n_pad / TR), TR, tile_bytes, ctx->copy_stream>>>(
-      dv->d_data, dv->d_mask, dv->n, st->n_pad, (uint32_t)(dv->rowsize / 4), (uint32_t)(dv->maskrowsize / 4), st->d_feats_b,
-      (int)D, st->d_flags_b);
-  ctx->launches++;
-  CU_TRY(cudaGetLastError());
+  CU_TRY(launch_ingest_tile(ctx, ctx->copy_stream, TR, dv, st->n_pad, st->d_feats_b, (int)D, st->d_flags_b));
   CU_TRY(cudaMemcpyAsync(st->h_flags_b, st->d_flags_b, sizeof(uint32_t) * D, cudaMemcpyDeviceToHost, ctx->copy_stream));
   CU_TRY(cudaEventRecord(st->ev_prefetched, ctx->copy_stream));
   dv->upload_pending = false;  // the copy stream itself consumed the upload; later uploads queue behind this kernel
@@ -1448,8 +1474,11 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
       const size_t fixed_b = st->n_scalar * (sizeof(FeatS) + 8) + 2 * 8 * sizeof(uint64_t) + 256;
       const size_t xm = (RB * 4 + RB / 8 + 127) / 128 * 128;
       const size_t biggest = (xm + st->max_chunk_rows * KT * sizeof(float) + 127) / 128 * 128;
-      static const int want_stages = getenv("MSB_BUNDLE_STAGES") ? atoi(getenv("MSB_BUNDLE_STAGES")) : 3;
-      int Sb = std::max(2, std::min(8, want_stages));
+      // stages: measured on C5 (fused quads of ~64 KB) 2 stages 44.4 ms, 3 stages 47.5 ms; on C3 (nich only) 3 and 6 alike
+      static const int want_stages = getenv("MSB_BUNDLE_STAGES") ? atoi(getenv("MSB_BUNDLE_STAGES")) : 0;
+      bool any_fuse = false;
+      for (const auto &f : st->sc_host) any_fuse |= f.fuse != 0;
+      int Sb = want_stages ? std::max(2, std::min(8, want_stages)) : ((any_fuse || st->bundle_key == 0) && st->V == 4 && st->max_chunk_rows * KT * sizeof(float) > 16384 ? 2 : 3);
       size_t stage_b = (ctx->smem_optin - fixed_b) / Sb / 128 * 128;
       while (Sb > 2 && stage_b < biggest) { Sb--; stage_b = (ctx->smem_optin - fixed_b) / Sb / 128 * 128; }
       if (stage_b >= biggest && (!blocked || (size_t)Sb * stage_b >= tile)) {
@@ -2317,20 +2346,30 @@ extern "C" MSB_API int msb_state_sweep_wait(msb_state *st, msb_sweep_result *res
 extern "C" MSB_API int msb_state_pass(msb_state *st, const msb_pass_opts *opts, msb_sweep_result *res) {
   REQUIRE(st && opts, "NULL argument");
   REQUIRE(st->dv, "no dataview bound");
-  MSB_TRY(msb_state_refresh(st));
+  static const bool dbg = getenv("MSB_DEBUG_SYNC") != nullptr;  // diagnostics: wait for the device after every sub-step
+#define MSB_PASS_STEP(what, expr)                                                                        \
+  do {                                                                                                   \
+    MSB_TRY(expr);                                                                                       \
+    if (dbg) {                                                                                           \
+      const cudaError_t e_ = cudaDeviceSynchronize();                                                    \
+      if (e_ != cudaSuccess) return fail(MSB_ERR_CUDA, std::string("msb_state_pass, after ") + what + ": " + cudaGetErrorString(e_)); \
+    }                                                                                                    \
+  } while (0)
+  MSB_PASS_STEP("refresh", msb_state_refresh(st));
   if (opts->next_data) {
-    MSB_TRY(msb_dataview_upload(st->dv, opts->next_data, opts->next_mask));
-    MSB_TRY(msb_state_prefetch(st));
+    MSB_PASS_STEP("upload", msb_dataview_upload(st->dv, opts->next_data, opts->next_mask));
+    MSB_PASS_STEP("prefetch", msb_state_prefetch(st));
   }
   msb_sweep_opts so = opts->sweep;
   so.flags |= MSB_SWEEP_ASYNC;
   if (opts->nccl_comm) so.defer_apply = 1;
-  MSB_TRY(msb_state_sweep(st, 0, st->n, &so, res));
-  if (opts->nccl_comm) MSB_TRY(msb_state_allreduce_deltas(st, opts->nccl_comm, opts->global_rows));
+  MSB_PASS_STEP("sweep", msb_state_sweep(st, 0, st->n, &so, res));
+  if (opts->nccl_comm) MSB_PASS_STEP("allreduce", msb_state_allreduce_deltas(st, opts->nccl_comm, opts->global_rows));
   if (opts->assign_out) {
-    MSB_TRY(msb_state_assignments_wait(st));
-    MSB_TRY(msb_state_assignments_async(st, opts->assign_out, st->n));
+    MSB_PASS_STEP("assignments_wait", msb_state_assignments_wait(st));
+    MSB_PASS_STEP("assignments_async", msb_state_assignments_async(st, opts->assign_out, st->n));
   }
+#undef MSB_PASS_STEP
   return MSB_OK;
 }
 

@@ -646,13 +646,14 @@ def test_async_assignments_copy_matches_blocking(ctx, oracle):
     st.close()
 
 
+@pytest.mark.parametrize("k", [6, 40, 300])   # 6: one k-tile; 40 / 300: the bundled general kernel (V = 2 / V = 4, fused quads)
 @pytest.mark.parametrize("mask_frac", [0.0, 0.05])
-def test_prefetched_conversion_swaps_column_buffers_correctly(ctx, oracle, mask_frac):
+def test_prefetched_conversion_swaps_column_buffers_correctly(ctx, oracle, mask_frac, k):
     # upload + prefetch of the next dataset run on the copy stream while the compute stream still scores the
     # current one; refresh then swaps the two column buffers (masks included: the tables-only kernel choice can
     # change between buffers).  Scores must follow the data that is current in each pass.
     descs = FAMILIES["mixed"]
-    n, k = 30000, 6
+    n = 30000
     st, view_a, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=43, mask_frac=mask_frac)
     arr_b, _ = cb.synth.make_dataset(descs, n, k, seed=44, mask_frac=0.0)   # B is never masked
     view_b = cb.numpy_dataview(arr_b)
