@@ -45,13 +45,14 @@ using niwtc::TN;
 constexpr int EPI_WARPS = 16;               // epilogue warps: 2 tile parities x 2 group pairs x 4 TMEM lane quadrants
 constexpr int THREADS = (2 + EPI_WARPS) * 32;   // warp 0 A producer, warp 1 MMA issuer, warps 2-17 epilogue
 constexpr int A_HALF_BYTES = TM * 32 * 2;   // one k-half (32 k) of one part (hi or lo): 8 KB
-constexpr int NA = 6;                        // A half-tile buffers in the ring (hi + lo each): the copies run up to three tiles ahead of the MMAs
-constexpr int A_BYTES = NA * 2 * A_HALF_BYTES;   // [buffer][part]: 64 KB
+constexpr int NA = 5;                        // A half-tile buffers in the ring (hi + lo each): the copies run two and a half tiles ahead of the MMAs
+constexpr int A_BYTES = NA * 2 * A_HALF_BYTES;   // [buffer][part]: 80 KB
 constexpr int B_PART_BYTES = TN * D * 2;    // 32 KB
 constexpr int B_BYTES = 2 * B_PART_BYTES;   // hi + lo: 64 KB
+constexpr int NB = 2;                        // B buffers: the next item's group block lands while the current one is multiplied
 constexpr int SB_FLOATS = TN + 16;          // bias r_k [TN], coef[GB x 4] (c0, c1, 1 / (dof r_k^2), -)
-constexpr size_t SMEM_BYTES = (size_t)B_BYTES + A_BYTES + 2 * SB_FLOATS * sizeof(float) + D * sizeof(float) +
-                              20 * sizeof(uint64_t) + 64;
+constexpr size_t SMEM_BYTES = (size_t)NB * B_BYTES + A_BYTES + 2 * SB_FLOATS * sizeof(float) + D * sizeof(float) +
+                              24 * sizeof(uint64_t) + 64;
 
 // byte offset of element (row, k) inside one part of an fp16 operand tile with `rowgroups` 8-row groups:
 // [k/8][row/8][row%8][k%8]  (core matrix = 8 rows x 16 bytes, contiguous)
@@ -84,6 +85,12 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
   const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
   hi = *reinterpret_cast<const uint32_t *>(&h);
   lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -195,8 +202,9 @@ __global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, cons
     const float w = k < ncols ? W[((size_t)k * D + i) * D + j] * s_isx[j] * s_r[GB + g] : 0.f;   // exact: powers of two
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
-    // operand row n' = (i / 8) * 32 + g * 8 + i % 8, as in niw_pack_b_kernel (the epilogue's accumulator order)
-    const uint32_t off = core_off16((uint32_t)((i >> 3) * (GB * 8) + g * 8 + (i & 7)), (uint32_t)j, TN / 8) / 2;
+    // operand row n' = (i / 16) * 64 + g * 16 + i % 16: contraction step st (j in [16 st, 16 st + 16)) of the lower-triangular
+    // W_k reaches the accumulator columns >= 64 st only, and one group's 16 outputs of a step are 16 contiguous columns
+    const uint32_t off = core_off16((uint32_t)((i >> 4) * (GB * 16) + g * 16 + (i & 15)), (uint32_t)j, TN / 8) / 2;
     dst[off] = hi;
     dst[B_PART_BYTES / 2 + off] = lo;
   }
@@ -210,36 +218,38 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
   using namespace niwtc16;
   extern __shared__ __align__(1024) unsigned char niw_smem[];
   unsigned char *sm = niw_smem;
-  unsigned char *sB = sm;                      // [part][...]
-  unsigned char *sA = sm + B_BYTES;            // [half][part][...]
-  float *sBias = reinterpret_cast<float *>(sA + A_BYTES);            // [2][SB_FLOATS]: bias, 1 / r, coef (GB x 4)
+  unsigned char *sB = sm;                      // [buffer][part][...]
+  unsigned char *sA = sm + NB * B_BYTES;       // [ring slot][part][...]
+  float *sBias = reinterpret_cast<float *>(sA + A_BYTES);            // [2][SB_FLOATS]: bias r_k, coef (GB x 4), by item parity
   uint64_t *bars = reinterpret_cast<uint64_t *>(sBias + 2 * SB_FLOATS + D);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 19);
-  // barriers: 0 b_full, 1 b_free, A_FULL.. a_full[NA], A_EMPTY.. a_empty[NA], ACC_FULL.. acc_full[2], ACC_EMPTY.. acc_empty[2]
-  constexpr int A_FULL = 2, A_EMPTY = 2 + NA, ACC_FULL = 2 + 2 * NA, ACC_EMPTY = 4 + 2 * NA;
-  static_assert(ACC_EMPTY + 2 <= 19, "barrier slots");
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 23);
+  // barriers: b_full[2], b_free[2], a_full[NA], a_empty[NA], acc_full[2], acc_empty[2]
+  constexpr int B_FULL = 0, B_FREE = 2, A_FULL = 4, A_EMPTY = 4 + NA, ACC_FULL = 4 + 2 * NA, ACC_EMPTY = 6 + 2 * NA;
+  static_assert(ACC_EMPTY + 2 <= 23, "barrier slots");
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform as far as the compiler is concerned: uniform branches and registers
   const size_t nrows = row_hi - row_lo;
   const int nRT = (int)((nrows + TM - 1) / TM);
   const int nGB = (ncols + GB - 1) / GB;
   // Schedule: the work is cut into items (slice of `slice_tiles` row tiles) x (group block), numbered group block
   // fastest, and CTA c takes the items c, c + gridDim.x, ...  At any moment the CTAs are therefore all inside two or three
   // neighbouring slices: their A tiles are shared through L2 (A streams from HBM about once), and every CTA gets the
-  // same number of items to within one -- the earlier split into one lane of CTAs per group block left 44 of the 64
-  // lanes with two CTAs and 20 with three at C4, i.e. finished 13 % later than the average.
+  // same number of items to within one.
   const int SL = slice_tiles;
   const int nSL = (nRT + SL - 1) / SL;
   const long long nItems = (long long)nSL * nGB;
   if (tid == 0) {
-    mbar_init(smem_u32(&bars[0]), 1);
-    mbar_init(smem_u32(&bars[1]), 1);
+    for (int i = 0; i < NB; i++) {
+      mbar_init(smem_u32(&bars[B_FULL + i]), 1);    // b_full: the producer's expect_tx, completed by the bulk copies
+      mbar_init(smem_u32(&bars[B_FREE + i]), 1);    // b_free: tcgen05.commit after the item's last MMA
+    }
     for (int i = 0; i < NA; i++) {
       mbar_init(smem_u32(&bars[A_FULL + i]), 1);    // a_full: the producer's expect_tx, completed by the bulk copy
       mbar_init(smem_u32(&bars[A_EMPTY + i]), 1);   // a_empty: tcgen05.commit
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(smem_u32(&bars[ACC_FULL + i]), 1);  // acc_full: tcgen05.commit
-      mbar_init(smem_u32(&bars[ACC_EMPTY + i]), EPI_WARPS / 2); // acc_empty: one arrive per warp of the set that owns the accumulator
+      mbar_init(smem_u32(&bars[ACC_EMPTY + i]), EPI_WARPS); // acc_empty: one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -253,178 +263,181 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ===== producer: one thread streams the pre-converted A operand (niw_convert_a16_kernel: scaled fp16 hi / lo parts,
-    // already in core-matrix layout, 16 KB per half-tile) into the ring with bulk copies.  Converting in this kernel,
-    // as the tf32 version does, repeats the conversion once per group block (64 times at C4) and was what the MMAs
-    // waited for.
-    if (tid == 0) {
-      long long h = 0;
-      for (long long item = blockIdx.x; item < nItems; item += gridDim.x) {
+    // ===== producer: streams the pre-converted A operand (niw_convert_a16_kernel: scaled fp16 hi / lo parts, already in
+    // core-matrix layout, 16 KB per half-tile) into the ring with bulk copies, and keeps the B operand (one block of 4
+    // groups, 64 KB) one item ahead: the next item's block is requested a few tiles into the current item -- by then the
+    // MMAs of the previous item, which read the buffer it goes into, have long completed, so the wait below does not hold
+    // the A ring up -- and lands under ~30 tiles of tensor work.  All 32 lanes walk the (warp-uniform) loop and wait;
+    // one elected lane issues the copies.
+    auto load_b = [&](int gb, int buf) {
+      const uint32_t bar = smem_u32(&bars[B_FULL + buf]);
+      mbar_expect_tx(bar, B_BYTES);
+      const unsigned char *gsrc = Bop + (size_t)gb * B_BYTES;
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        bulk_g2s(smem_u32(sB + (size_t)buf * B_BYTES + (size_t)c * (B_BYTES / 4)), gsrc + (size_t)c * (B_BYTES / 4), B_BYTES / 4, bar);
+    };
+    uint32_t abuf = 0, around = 0;   // ring slot and how many times the ring has wrapped
+    int it = 0;
+    for (long long item = blockIdx.x; item < nItems; item += gridDim.x, it++) {
       const int sl = (int)(item / nGB);
       const int rt_lo = sl * SL, rt_hi = rt_lo + SL < nRT ? rt_lo + SL : nRT;
-      for (int rt = rt_lo; rt < rt_hi; rt++)
-      for (int half = 0; half < 2; half++, h++) {
-        const int buf = (int)(h % NA);
-        if (h >= NA) mbar_wait(smem_u32(&bars[A_EMPTY + buf]), (uint32_t)(((h / NA) - 1) & 1));  // MMAs that read this buffer are done
-        const uint32_t bar = smem_u32(&bars[A_FULL + buf]);
-        mbar_expect_tx(bar, 2 * A_HALF_BYTES);
-        bulk_g2s(smem_u32(sA + (size_t)buf * 2 * A_HALF_BYTES), A16 + ((size_t)rt * 2 + half) * (2 * A_HALF_BYTES), 2 * A_HALF_BYTES, bar);
-      }
+      if (it == 0 && elect_one()) load_b((int)(item % nGB), 0);
+      const long long next = item + gridDim.x;
+      const int trig = rt_lo + 4 < rt_hi - 1 ? rt_lo + 4 : rt_hi - 1;
+      for (int rt = rt_lo; rt < rt_hi; rt++) {
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          if (around) mbar_wait(smem_u32(&bars[A_EMPTY + abuf]), (around - 1) & 1u);  // the MMAs that read this slot are done
+          if (elect_one()) {
+            const uint32_t bar = smem_u32(&bars[A_FULL + abuf]);
+            mbar_expect_tx(bar, 2 * A_HALF_BYTES);
+            bulk_g2s(smem_u32(sA) + abuf * (uint32_t)(2 * A_HALF_BYTES), A16 + ((size_t)rt * 2 + half) * (2 * A_HALF_BYTES), 2 * A_HALF_BYTES, bar);
+          }
+          __syncwarp();
+          if (++abuf == (uint32_t)NA) { abuf = 0; around++; }
+        }
+        if (rt == trig && next < nItems) {
+          const int nb = (it + 1) & 1, u = (it + 1) >> 1;   // use u of buffer nb
+          if (u >= 1) mbar_wait(smem_u32(&bars[B_FREE + nb]), (uint32_t)((u - 1) & 1));  // the MMAs of item it - 1 are done
+          if (elect_one()) load_b((int)(next % nGB), nb);
+          __syncwarp();
+        }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer (one elected lane) =====
-    if (lane == 0) {
-      long long h = 0, t = 0;
-      int cur_gb = -1;
-      uint32_t b_loads = 0;
-      for (long long item = blockIdx.x; item < nItems; item += gridDim.x) {
+    // ===== MMA issuer.  All 32 lanes walk the loop (it is warp-uniform: the warp index comes from a shuffle, so the
+    // compiler keeps the addresses and descriptors in uniform registers) and wait on the barriers; one elected lane
+    // issues the MMAs and commits.  This loop paced the earlier versions: one lane, under a divergent branch, spent
+    // ~300 instructions per half-tile on 64-bit ring arithmetic (h % NA, h / NA), descriptor assembly and R2UR moves --
+    // at one warp's issue rate that is ~1900 cycles per tile for ~960 cycles of tensor work (ncu: the tensor pipe 46 %
+    // active, the issuer's samples spread over plain integer instructions, not waits).
+    uint32_t abuf = 0, aphase = 0;
+    int t = 0, it = 0;
+    const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
+    const uint32_t no_tri = (uint32_t)(blocked & 4);
+    for (long long item = blockIdx.x; item < nItems; item += gridDim.x, it++) {
+      const int sl = (int)(item / nGB);
+      const int rt_lo = sl * SL, rt_hi = rt_lo + SL < nRT ? rt_lo + SL : nRT;
+      const int bbuf = it & 1;
+      mbar_wait(smem_u32(&bars[B_FULL + bbuf]), (uint32_t)((it >> 1) & 1));
+      const uint32_t sB_cur = sB0 + (uint32_t)bbuf * B_BYTES;
+      for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
+        const int acc = t & 1;
+        if (t >= 2) mbar_wait(smem_u32(&bars[ACC_EMPTY + acc]), (uint32_t)(((t >> 1) - 1) & 1));  // the epilogue has read this accumulator
+        const uint32_t d_tmem = tmem + (uint32_t)acc * TN;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          mbar_wait(smem_u32(&bars[A_FULL + abuf]), aphase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = sA0 + abuf * (uint32_t)(2 * A_HALF_BYTES), a_lo = a_hi + A_HALF_BYTES;
+          const uint32_t b_hi = sB_cur + (uint32_t)half * (32 / 8) * (TN / 8) * 128u, b_lo = b_hi + B_PART_BYTES;
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++) {  // K = 16 per instruction: 2 core-matrix columns
+              // W_k is lower triangular: contraction step st (j in [16 st, 16 st + 16)) only reaches the outputs i >= 16 st,
+              // which the operand row order n' = (i / 16) * 64 + g * 16 + i % 16 makes the contiguous rows / accumulator
+              // columns [64 st, 256): N = 256, 192, 128, 64 over the four steps, 640 instead of 1024 columns of tensor
+              // work per tile.
+              const uint32_t st = (uint32_t)(half * 2 + ks);
+              const uint32_t n0 = no_tri ? 0u : st * 64u;
+              const uint32_t idn = idesc_f16(TN - n0);
+              const uint32_t ao = (uint32_t)ks * 2u * (TM / 8) * 128u;
+              const uint32_t bo = (uint32_t)ks * 2u * (TN / 8) * 128u + (n0 / 8u) * 128u;
+              const uint64_t dah = niwtc::smem_desc(a_hi + ao, (TM / 8) * 128u, 128u), dal = niwtc::smem_desc(a_lo + ao, (TM / 8) * 128u, 128u);
+              const uint64_t dbh = niwtc::smem_desc(b_hi + bo, (TN / 8) * 128u, 128u), dbl = niwtc::smem_desc(b_lo + bo, (TN / 8) * 128u, 128u);
+              mma_f16(d_tmem + n0, dah, dbh, idn, st ? 1u : 0u);
+              mma_f16(d_tmem + n0, dah, dbl, idn, 1u);
+              mma_f16(d_tmem + n0, dal, dbh, idn, 1u);
+            }
+            niwtc::mma_commit(smem_u32(&bars[A_EMPTY + abuf]));            // A half-buffer free once these MMAs complete
+            if (half == 1) niwtc::mma_commit(smem_u32(&bars[ACC_FULL + acc]));  // accumulator ready for the epilogue
+            if (half == 1 && rt == rt_hi - 1) niwtc::mma_commit(smem_u32(&bars[B_FREE + bbuf]));  // this item's B buffer may be overwritten
+          }
+          __syncwarp();
+          if (++abuf == (uint32_t)NA) { abuf = 0; aphase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..17, all sixteen on EVERY tile.  Warp e reads TMEM lane quadrant warp % 4 (fixed by the
+    // hardware) and the 64 accumulator columns of group e / 4 of the block: four tcgen05.ld 32x32b.x16 issued back to
+    // back, ONE wait, and the accumulator is released as soon as the values are in registers -- before any arithmetic.
+    // The MMAs of tile t + 2 wait for the readers of tile t, so what matters is how long an accumulator stays occupied
+    // after its last MMA: with the tile's columns split over four / eight warps, each walking its loads one behind the
+    // other (one in flight, ~170 cycles each), that was ~2800 / ~1400 cycles against ~1000 cycles of tensor work per
+    // tile; now it is one barrier wake-up plus one TMEM load latency.
+    const int e = warp - 2;
+    const int ew = warp & 3;                 // TMEM lanes 32 ew .. 32 ew + 31
+    const int g = e >> 2;                    // group g of the block
+    const int etid = e * 32 + lane;          // 0..511
+    long long t = 0;
+    int it = 0;
+    for (long long item = blockIdx.x; item < nItems; item += gridDim.x, it++) {
       const int gb = (int)(item % nGB), sl = (int)(item / nGB);
       const int rt_lo = sl * SL, rt_hi = rt_lo + SL < nRT ? rt_lo + SL : nRT;
+      // this group block's bias and coefficients, staged once per item into the copy of the item's parity: a warp that
+      // writes copy it & 1 has passed the barrier of item it - 1, which every warp reaches only after its last read of
+      // item it - 2 -- one barrier per item suffices
+      float *sb = sBias + (size_t)(it & 1) * SB_FLOATS;
+      const float *sc = sb + TN;
+      for (int i = etid; i < SB_FLOATS; i += EPI_WARPS * 32) {
+        float v = 0.f;
+        if (i < TN) {  // bias' = b r_k
+          const int k = gb * GB + i / D;
+          if (k < ncols) v = bias[(size_t)k * D + (i % D)] * rinv[(size_t)k * 2];
+        } else {       // c0, c1, 1 / (dof r_k^2): q' = r_k^2 q
+          const int k = gb * GB + (i - TN) / 4, c = (i - TN) & 3;
+          if (k < ncols) v = coef[(size_t)k * 4 + c] * (c == 2 ? rinv[(size_t)k * 2 + 1] : 1.f);
+        }
+        sb[i] = v;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      const int k = gb * GB + g;
+      const float c0 = sc[g * 4 + 0], c1 = sc[g * 4 + 1], idof = sc[g * 4 + 2];
+      const float4 *sbg = reinterpret_cast<const float4 *>(sb + g * D);
       for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
-        if (gb != cur_gb) {  // (re)load the resident B operand
-          if (cur_gb >= 0) {
-            niwtc::mma_commit(smem_u32(&bars[1]));
-            mbar_wait(smem_u32(&bars[1]), (b_loads - 1) & 1u);  // every MMA that read the old B has completed
-          }
-          mbar_expect_tx(smem_u32(&bars[0]), B_BYTES);
-          const unsigned char *gsrc = Bop + (size_t)gb * B_BYTES;
-          for (int c = 0; c < 4; c++)
-            bulk_g2s(smem_u32(sB + (size_t)c * (B_BYTES / 4)), gsrc + (size_t)c * (B_BYTES / 4), B_BYTES / 4, smem_u32(&bars[0]));
-          mbar_wait(smem_u32(&bars[0]), b_loads & 1u);
-          b_loads++;
-          cur_gb = gb;
-        }
         const int acc = (int)(t & 1);
-        if (t >= 2) mbar_wait(smem_u32(&bars[ACC_EMPTY + acc]), (uint32_t)(((t >> 1) - 1) & 1));  // epilogue drained this accumulator
-        const uint32_t d_tmem = tmem + (uint32_t)acc * TN;
-        for (int half = 0; half < 2; half++, h++) {
-          const int buf = (int)(h % NA);
-          mbar_wait(smem_u32(&bars[A_FULL + buf]), (uint32_t)((h / NA) & 1));
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = smem_u32(sA + (size_t)buf * 2 * A_HALF_BYTES), a_lo = a_hi + A_HALF_BYTES;
-          const uint32_t b_hi = smem_u32(sB) + (uint32_t)half * (32 / 8) * (TN / 8) * 128u, b_lo = b_hi + B_PART_BYTES;
-#pragma unroll
-          for (int ks = 0; ks < 2; ks++) {  // K = 16 per instruction: 2 core-matrix columns
-            // W_k is lower triangular: contraction step st (j in [16 st, 16 st + 16)) only reaches the outputs i >= 16 st,
-            // which the operand row order n' = (i / 8) * 32 + g * 8 + i % 8 makes the contiguous rows / accumulator
-            // columns [64 st, 256): N = 256, 192, 128, 64 over the four steps, 640 instead of 1024 columns of tensor
-            // work per tile.  (The same trick did not pay in the tf32 kernel, which was not bound by the tensor pipe.)
-            const uint32_t st = (uint32_t)(half * 2 + ks);
-            const uint32_t n0 = (blocked & 4) ? 0u : st * 64u;
-            const uint32_t idn = idesc_f16(TN - n0);
-            const uint32_t ao = (uint32_t)ks * 2u * (TM / 8) * 128u;
-            const uint32_t bo = (uint32_t)ks * 2u * (TN / 8) * 128u + (n0 / 8u) * 128u;
-            const uint64_t dah = niwtc::smem_desc(a_hi + ao, (TM / 8) * 128u, 128u), dal = niwtc::smem_desc(a_lo + ao, (TM / 8) * 128u, 128u);
-            const uint64_t dbh = niwtc::smem_desc(b_hi + bo, (TN / 8) * 128u, 128u), dbl = niwtc::smem_desc(b_lo + bo, (TN / 8) * 128u, 128u);
-            mma_f16(d_tmem + n0, dah, dbh, idn, st ? 1u : 0u);
-            mma_f16(d_tmem + n0, dah, dbl, idn, 1u);
-            mma_f16(d_tmem + n0, dal, dbh, idn, 1u);
-          }
-          niwtc::mma_commit(smem_u32(&bars[A_EMPTY + buf]));            // A half-buffer free once these MMAs complete
-          if (half == 1) niwtc::mma_commit(smem_u32(&bars[ACC_FULL + acc]));  // accumulator ready for the epilogue
+        const size_t row = row_lo + (size_t)rt * TM + ew * 32 + lane;
+        float *dst = scores + (row - row_lo) * ld + (size_t)k;
+        float *dstb = scores + (((size_t)rt * (TM / 32) + ew) * ld + (size_t)k) * 32 + lane;
+        float old = 0.f;
+        if (row < row_hi && k < ncols) {
+          if (base) old = __ldg(base + k);
+          else if (blocked & 1) old = dstb[0];
+          else old = *dst;
         }
-      }
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===== epilogue: warps 2..17 in four groups of four (one warp per TMEM lane quadrant = warp id % 4): group index
-    // bit 0 = tile parity (accumulator), bit 1 = which two of the block's four groups the warp reduces.  A tile's epilogue
-    // is a chain of waits (accumulator ready -> TMEM loads -> arithmetic -> release), and the MMAs of tile t + 2 cannot
-    // start before the readers of tile t have released the accumulator.
-    const int e = warp - 2;
-    const int ew = warp & 3;                 // TMEM lanes 32 ew .. 32 ew + 31 (fixed by the hardware: warp id % 4)
-    const int set = (e >> 2) & 1;            // tile parity
-    const int gh = e >> 3;                   // groups 2 gh, 2 gh + 1 of the block
-    const int etid = ((gh << 2) | (e & 3)) * 32 + lane;  // 0..255 within the set
-    long long t = 0;
-    int staged_gb = -1;
-    float *sb = sBias + (size_t)set * SB_FLOATS;
-    float *sc = sb + TN;
-    for (long long item = blockIdx.x; item < nItems; item += gridDim.x) {
-    const int gb = (int)(item % nGB), sl = (int)(item / nGB);
-    const int rt_lo = sl * SL, rt_hi = rt_lo + SL < nRT ? rt_lo + SL : nRT;
-    for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
-      if ((int)(t & 1) != set) continue;
-      const int acc = set;
-      // this group block's bias and coefficients (each set keeps its own copy): staged when the block changes, not per tile
-      if (gb != staged_gb) {
-        if (set == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
-        for (int i = etid; i < SB_FLOATS; i += 256) {
-          float v = 0.f;
-          if (i < TN) {  // bias' = b r_k
-            const int k = gb * GB + i / D;
-            if (k < ncols) v = bias[(size_t)k * D + (i % D)] * rinv[(size_t)k * 2];
-          } else {       // c0, c1, 1 / (dof r_k^2): q' = r_k^2 q
-            const int k = gb * GB + (i - TN) / 4, c = (i - TN) & 3;
-            if (k < ncols) v = coef[(size_t)k * 4 + c] * (c == 2 ? rinv[(size_t)k * 2 + 1] : 1.f);
-          }
-          sb[i] = v;
-        }
-        if (set == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
-        staged_gb = gb;
-      }
-      const size_t row = row_lo + (size_t)rt * TM + ew * 32 + lane;
-      const int g0 = 2 * gh;
-      float2 *dst = reinterpret_cast<float2 *>(scores + (row - row_lo) * ld + (size_t)gb * GB + g0);
-      float *dstb = scores + (((size_t)rt * (TM / 32) + ew) * ld + (size_t)gb * GB + g0) * 32 + lane;
-      float2 old = make_float2(0.f, 0.f);
-      if (row < row_hi) {
-        if (base) old = __ldg(reinterpret_cast<const float2 *>(base + (size_t)gb * GB + g0));
-        else if (blocked & 1) old = make_float2(dstb[0], dstb[32]);
-        else old = *dst;
-      }
-      mbar_wait(smem_u32(&bars[ACC_FULL + acc]), (uint32_t)((t >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float q[2];
-      {
-        float2 q2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        // columns of the accumulator: block ib = i / 8 holds [g][i % 8]; this warp's two groups are 16 contiguous columns of it
-        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN) + (uint32_t)(gh * 16);
-        uint32_t r[2][16];
-        tmem_ld16_issue(tbase, r[0]);
+        mbar_wait(smem_u32(&bars[ACC_FULL + acc]), (uint32_t)((t >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // accumulator columns: block i / 16 holds [g][i % 16]; this warp's group is 16 contiguous columns of each block
+        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN) + (uint32_t)(g * 16);
+        uint32_t r[4][16];
 #pragma unroll
-        for (int ib = 0; ib < D / 8; ib++) {
-          niwtc::tmem_ld_wait();
-          if (ib + 1 < D / 8) tmem_ld16_issue(tbase + (uint32_t)(ib + 1) * 32u, r[(ib + 1) & 1]);
+        for (int ib = 0; ib < 4; ib++) tmem_ld16_issue(tbase + (uint32_t)ib * 64u, r[ib]);
+        niwtc::tmem_ld_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
+        float2 qa = make_float2(0.f, 0.f), qb = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int g = 0; g < 2; g++) {
-            const float4 b0 = *reinterpret_cast<const float4 *>(sb + (g0 + g) * D + ib * 8);
-            const float4 b1 = *reinterpret_cast<const float4 *>(sb + (g0 + g) * D + ib * 8 + 4);
-            const uint32_t *v = r[ib & 1] + g * 8;
+        for (int ib = 0; ib < 4; ib++) {
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const float4 b4 = sbg[ib * 4 + c];
+            const uint32_t *v = r[ib] + c * 4;
             float2 y;
-            y = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(-b0.x, -b0.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
-            y = __fadd2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(-b0.z, -b0.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
-            y = __fadd2_rn(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(-b1.x, -b1.y)); q2[g] = __ffma2_rn(y, y, q2[g]);
-            y = __fadd2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(-b1.z, -b1.w)); q2[g] = __ffma2_rn(y, y, q2[g]);
+            y = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(-b4.x, -b4.y)); qa = __ffma2_rn(y, y, qa);
+            y = __fadd2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(-b4.z, -b4.w)); qb = __ffma2_rn(y, y, qb);
           }
         }
-        q[0] = q2[0].x + q2[0].y;
-        q[1] = q2[1].x + q2[1].y;
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
-      if (row < row_hi) {
-        float o[2] = {old.x, old.y};
-#pragma unroll
-        for (int g = 0; g < 2; g++) {
-          const int k = gb * GB + g0 + g;
-          if (k < ncols && q[g] == q[g]) {  // NaN = masked row: contributes nothing
-            const float c0 = sc[(g0 + g) * 4 + 0], c1 = sc[(g0 + g) * 4 + 1], idof = sc[(g0 + g) * 4 + 2];
-            o[g] += c0 + c1 * log1pf(q[g] * idof);
-          }
-        }
-        if (blocked & 1) {
-          dstb[0] = o[0];
-          dstb[32] = o[1];
-        } else {
-          *dst = make_float2(o[0], o[1]);
+        const float q = (qa.x + qa.y) + (qb.x + qb.y);
+        if (row < row_hi && k < ncols) {
+          float o = old;
+          if (q == q) o += c0 + c1 * log1pf(q * idof);  // NaN = masked row: contributes nothing
+          if (blocked & 1) dstb[0] = o;
+          else *dst = o;
         }
       }
-    }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
