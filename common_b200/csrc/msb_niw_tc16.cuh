@@ -86,6 +86,14 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
   hi = *reinterpret_cast<const uint32_t *>(&h);
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
+// 16 TMEM lanes x 256 bits x 2: thread T gets rows T / 4 (r0 r1, r4 r5) and T / 4 + 8 (r2 r3, r6 r7) of the 16 lanes that
+// start at the address's lane, columns 2 (T % 4) + {0, 1} (r0-r3) and 8 + 2 (T % 4) + {0, 1} (r4-r7)
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -361,18 +369,21 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
     }
   } else {
     // ===== epilogue: warps 2..17, all sixteen on EVERY tile.  Warp e reads TMEM lane quadrant warp % 4 (fixed by the
-    // hardware) and the 64 accumulator columns of group e / 4 of the block: four tcgen05.ld 32x32b.x16 issued back to
-    // back, ONE wait, and the accumulator is released as soon as the values are in registers -- before any arithmetic.
-    // The MMAs of tile t + 2 wait for the readers of tile t, so what matters is how long an accumulator stays occupied
-    // after its last MMA: with the tile's columns split over four / eight warps, each walking its loads one behind the
-    // other (one in flight, ~170 cycles each), that was ~2800 / ~1400 cycles against ~1000 cycles of tensor work per
-    // tile; now it is one barrier wake-up plus one TMEM load latency.
+    // hardware) and the 64 accumulator columns of group e / 4 of the block: eight tcgen05.ld 16x256b.x2 issued back to
+    // back, ONE wait, and the accumulator is released as soon as the values are in registers -- before any arithmetic
+    // (the MMAs of tile t + 2 wait for the readers of tile t).
+    // The 16x256b shape hands a thread two adjacent columns of four rows (the mma accumulator fragment: thread T holds
+    // rows T / 4 + 8 m, columns 8 j + 2 (T % 4) + {0, 1}) instead of all the columns of one row, so a thread needs the bias
+    // of 16 of the group's 64 outputs only: they stay in registers for the whole item, and the per-element shared-memory
+    // read of the bias (ncu: one LDS.128 per 4 elements, ~3 wavefronts each, half of the LSU pipe and the scoreboard
+    // stall of every FADD2) is gone.  The price is a 4-lane transpose-reduce of the row sums (3 shuffles per tile).
     const int e = warp - 2;
     const int ew = warp & 3;                 // TMEM lanes 32 ew .. 32 ew + 31
     const int g = e >> 2;                    // group g of the block
     const int etid = e * 32 + lane;          // 0..511
-    long long t = 0;
-    int it = 0;
+    const int t4 = lane & 3, t8 = lane >> 2;
+    const int rloc = t8 + 8 * (2 * (lane & 1) + ((lane >> 1) & 1));   // the row of the quadrant this lane ends up owning
+    int t = 0, it = 0;
     for (long long item = blockIdx.x; item < nItems; item += gridDim.x, it++) {
       const int gb = (int)(item % nGB), sl = (int)(item / nGB);
       const int rt_lo = sl * SL, rt_hi = rt_lo + SL < nRT ? rt_lo + SL : nRT;
@@ -394,48 +405,69 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       const int k = gb * GB + g;
-      const float c0 = sc[g * 4 + 0], c1 = sc[g * 4 + 1], idof = sc[g * 4 + 2];
-      const float4 *sbg = reinterpret_cast<const float4 *>(sb + g * D);
-      for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
-        const int acc = (int)(t & 1);
-        const size_t row = row_lo + (size_t)rt * TM + ew * 32 + lane;
-        float *dst = scores + (row - row_lo) * ld + (size_t)k;
-        float *dstb = scores + (((size_t)rt * (TM / 32) + ew) * ld + (size_t)k) * 32 + lane;
-        float old = 0.f;
-        if (row < row_hi && k < ncols) {
-          if (base) old = __ldg(base + k);
-          else if (blocked & 1) old = dstb[0];
-          else old = *dst;
+      const bool kok = k < ncols;
+      const float c0 = sc[g * 4 + 0], c1l2 = sc[g * 4 + 1] * 0.6931471805599453f, idof = sc[g * 4 + 2];
+      float2 nb[8];   // minus the bias of this thread's 16 outputs: i = 16 ib + 8 j + 2 t4 + {0, 1}
+#pragma unroll
+      for (int ib = 0; ib < 4; ib++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const float2 b2 = *reinterpret_cast<const float2 *>(sb + g * D + ib * 16 + j * 8 + 2 * t4);
+          nb[ib * 2 + j] = make_float2(-b2.x, -b2.y);
         }
+      const float base_k = (base && kok) ? __ldg(base + k) : 0.f;
+      // this lane's output element of the item's first tile, then one tile (128 rows) further per step
+      const size_t r0 = (size_t)rt_lo * TM + ew * 32 + rloc;                      // row index relative to row_lo
+      float *dst = (blocked & 1) ? scores + (((size_t)rt_lo * (TM / 32) + ew) * ld + (size_t)k) * 32 + rloc
+                                 : scores + r0 * ld + (size_t)k;
+      const size_t dstep = (blocked & 1) ? (size_t)(TM / 32) * ld * 32 : (size_t)TM * ld;
+      long long left = (long long)nrows - (long long)r0;                           // > 0: the row exists
+      const uint32_t tbase0 = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(g * 16);
+      for (int rt = rt_lo; rt < rt_hi; rt++, t++, dst += dstep, left -= TM) {
+        const int acc = t & 1;
+        const bool ok = kok && left > 0;
+        float old = base_k;
+        if (ok && !base) old = *dst;
         mbar_wait(smem_u32(&bars[ACC_FULL + acc]), (uint32_t)((t >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // accumulator columns: block i / 16 holds [g][i % 16]; this warp's group is 16 contiguous columns of each block
-        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN) + (uint32_t)(g * 16);
-        uint32_t r[4][16];
+        const uint32_t tb = tbase0 + (uint32_t)(acc * TN);
+        uint32_t r[2][4][8];   // [lane half][block][j: r0 r1 = row t8, r2 r3 = row t8 + 8]
 #pragma unroll
-        for (int ib = 0; ib < 4; ib++) tmem_ld16_issue(tbase + (uint32_t)ib * 64u, r[ib]);
+        for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+          for (int ib = 0; ib < 4; ib++) tmem_ld_16x256b_x2(tb + ((uint32_t)(hh * 16) << 16) + (uint32_t)ib * 64u, r[hh][ib]);
         niwtc::tmem_ld_wait();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
-        float2 qa = make_float2(0.f, 0.f), qb = make_float2(0.f, 0.f);
+        float2 q2[4];   // rows t8, t8 + 8, t8 + 16, t8 + 24: partial sums over this thread's 16 outputs
 #pragma unroll
-        for (int ib = 0; ib < 4; ib++) {
+        for (int m = 0; m < 4; m++) q2[m] = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int c = 0; c < 4; c++) {
-            const float4 b4 = sbg[ib * 4 + c];
-            const uint32_t *v = r[ib] + c * 4;
-            float2 y;
-            y = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(-b4.x, -b4.y)); qa = __ffma2_rn(y, y, qa);
-            y = __fadd2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(-b4.z, -b4.w)); qb = __ffma2_rn(y, y, qb);
-          }
-        }
-        const float q = (qa.x + qa.y) + (qb.x + qb.y);
-        if (row < row_hi && k < ncols) {
+        for (int ib = 0; ib < 4; ib++)
+#pragma unroll
+          for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+              for (int m = 0; m < 2; m++) {
+                const uint32_t *v = r[hh][ib] + j * 4 + m * 2;
+                const float2 y = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), nb[ib * 2 + j]);
+                q2[hh * 2 + m] = __ffma2_rn(y, y, q2[hh * 2 + m]);
+              }
+        float q4[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) q4[m] = q2[m].x + q2[m].y;
+        // transpose-reduce over the four lanes that share t8: lane bit 0 keeps rows {0, 1} or {2, 3}, bit 1 picks one
+        const bool b0 = lane & 1, b1 = lane & 2;
+        const float s0 = (b0 ? q4[2] : q4[0]) + __shfl_xor_sync(0xffffffffu, b0 ? q4[0] : q4[2], 1);
+        const float s1 = (b0 ? q4[3] : q4[1]) + __shfl_xor_sync(0xffffffffu, b0 ? q4[1] : q4[3], 1);
+        const float q = (b1 ? s1 : s0) + __shfl_xor_sync(0xffffffffu, b1 ? s0 : s1, 2);
+        if (ok) {
           float o = old;
-          if (q == q) o += c0 + c1 * log1pf(q * idof);  // NaN = masked row: contributes nothing
-          if (blocked & 1) dstb[0] = o;
-          else *dst = o;
+          if (q == q) o += fmaf(c1l2, log2_1p_pos(q * idof), c0);  // NaN = masked row: contributes nothing
+          *dst = o;
         }
       }
     }
