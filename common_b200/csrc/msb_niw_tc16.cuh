@@ -16,20 +16,21 @@
 //
 // Kernels of one call:  niw_colmax_kernel -> niw_convert_a16_kernel (A: hi | lo parts of every 128-row tile, in the exact
 // core-matrix bytes of a ring buffer, written once per sweep) + niw_pack_b16_kernel (B: the same for every block of 4
-// groups) -> niw_tc16_kernel:
-//   * thread 0 streams A half-tiles (16 KB) into a 6-deep shared-memory ring with bulk copies;
-//   * one lane of warp 8 keeps the current group block's B (64 KB) resident and issues the MMAs: per 128-row tile four
-//     k-steps x three products, N shrinking 256, 192, 128, 64 (W_k is lower triangular), two 256-column TMEM accumulators;
-//   * sixteen epilogue warps: even tiles (accumulator 0) and odd tiles (accumulator 1) have their own set of eight, and
-//     inside a set the four groups of the block are split two and two -- per TMEM lane quadrant one warp reads the
-//     columns of groups 0-1 and another those of groups 2-3 (tcgen05.ld 32x32b.x16), bias, square-sum per group,
-//     log1p, store.  What paces the kernel is how long an accumulator stays occupied after its last MMA (the MMAs of
-//     tile t + 2 wait for the readers of tile t): with four warps per accumulator that was ~2800 cycles against ~1000
-//     of MMA work per tile; two readers per quadrant halve it.  In the sweep's blocked layout a warp's 32 lanes are
-//     one 32-row block, so every store is a full 128-byte line;
+// groups, the structurally zero rows of the triangular W_k left out, + the bias operand) -> niw_tc16_kernel:
+//   * warp 0 streams A half-tiles (16 KB) into a 6-deep shared-memory ring with bulk copies and keeps B (48 KB per
+//     group block) double-buffered one work item ahead;
+//   * warps 1 and 18 issue the MMAs, even and odd tiles: per 128-row tile one bias product (ones x -b': the accumulator
+//     starts at -b') and four k-steps x three products, N shrinking 256, 192, 128, 64, into the issuer's own 256-column
+//     TMEM accumulator.  Their loops are warp-uniform (descriptors in uniform registers, elect.sync around the issue);
+//   * sixteen epilogue warps, all on every tile: (TMEM lane quadrant) x (group of the block); four tcgen05.ld
+//     32x32b.x16 in flight, the accumulator released before the arithmetic, square sum, log1p, store.  In the sweep's
+//     blocked layout a warp's 32 lanes are one 32-row block, so every store is a full 128-byte line;
 //   * work items = (slice of <= 32 row tiles) x (group block), dealt round-robin to the CTAs, group block fastest: even
 //     load and A shared through L2.
 // Synchronisation is mbarrier-only (bulk-copy complete_tx, tcgen05.commit); every wait is bounded (trap).
+// What paced it, in the order found (C4, ms per score call): the issuer's instruction stream (4.05 -> 3.29), the bias
+// read from shared memory (-> 2.92), barrier waits serialised with the issue (two issuers: -> 2.90 at an SM clock the
+// power cap has by then pulled from 1965 to ~1665 MHz: 3 tensor products per algorithmic one).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -42,17 +43,22 @@ using niwtc::D;
 using niwtc::GB;
 using niwtc::TM;
 using niwtc::TN;
-constexpr int EPI_WARPS = 16;               // epilogue warps: 2 tile parities x 2 group pairs x 4 TMEM lane quadrants
-constexpr int THREADS = (2 + EPI_WARPS) * 32;   // warp 0 A producer, warp 1 MMA issuer, warps 2-17 epilogue
+constexpr int EPI_WARPS = 16;               // epilogue warps: 4 groups of the block x 4 TMEM lane quadrants
+constexpr int THREADS = (3 + EPI_WARPS) * 32;   // warp 0 A / B producer, warps 1 and 18 MMA issuers (even / odd tiles), warps 2-17 epilogue
 constexpr int A_HALF_BYTES = TM * 32 * 2;   // one k-half (32 k) of one part (hi or lo): 8 KB
-constexpr int NA = 5;                        // A half-tile buffers in the ring (hi + lo each): the copies run two and a half tiles ahead of the MMAs
-constexpr int A_BYTES = NA * 2 * A_HALF_BYTES;   // [buffer][part]: 80 KB
-constexpr int B_PART_BYTES = TN * D * 2;    // 32 KB
-constexpr int B_BYTES = 2 * B_PART_BYTES;   // hi + lo: 64 KB
+constexpr int NA = 6;                        // A half-tile buffers in the ring (hi + lo each): the copies run three tiles ahead of the MMAs
+constexpr int A_BYTES = NA * 2 * A_HALF_BYTES;   // [buffer][part]: 96 KB
+// B operand of one group block, compact: W_k is lower triangular, so contraction step st (j in [16 st, 16 st + 16)) only
+// reaches the operand rows n' >= 64 st (see niw_pack_b16_kernel) and only those rows are stored: 256, 192, 128, 64 rows of
+// 16 k each = 20 KB per part instead of 32
+__device__ __host__ constexpr uint32_t b_step_off(uint32_t st) { return st * 8192u - (st * (st - 1u) / 2u) * 2048u; }  // sum_{s<st} (256 - 64 s) * 32
+constexpr int B_PART_BYTES = 20480;         // b_step_off(4)
+constexpr int BIAS_BYTES = 2 * (TN / 8) * 128;   // the bias operand: TN rows x 16 k (k = 0 hi, k = 1 lo, the rest zero): 8 KB
+constexpr int B_BYTES = 2 * B_PART_BYTES + BIAS_BYTES;   // hi + lo + bias: 48 KB
 constexpr int NB = 2;                        // B buffers: the next item's group block lands while the current one is multiplied
-constexpr int SB_FLOATS = TN + 16;          // bias r_k [TN], coef[GB x 4] (c0, c1, 1 / (dof r_k^2), -)
-constexpr size_t SMEM_BYTES = (size_t)NB * B_BYTES + A_BYTES + 2 * SB_FLOATS * sizeof(float) + D * sizeof(float) +
-                              24 * sizeof(uint64_t) + 64;
+constexpr int ONES_BYTES = 2 * (TM / 8) * 128;   // the A operand of the bias product: TM rows x 16 k, columns 0 and 1 = 512: 4 KB
+constexpr float BIAS_SCALE = 512.f;          // ones column = 512, bias operand = -b' / 512: |b'| < 2^24 stays inside fp16's range
+constexpr size_t SMEM_BYTES = (size_t)NB * B_BYTES + A_BYTES + ONES_BYTES + 24 * sizeof(uint64_t) + 64;
 
 // byte offset of element (row, k) inside one part of an fp16 operand tile with `rowgroups` 8-row groups:
 // [k/8][row/8][row%8][k%8]  (core matrix = 8 rows x 16 bytes, contiguous)
@@ -169,10 +175,11 @@ __global__ void niw_convert_a16_kernel(const float *__restrict__ X, size_t row_l
   }
 }
 
-// W[k][i][j] (fp32, row-major per group) -> per group block: [hi | lo] fp16 parts in UMMA layout, scaled; blocks padded
-// with zeros.  rinv[2 k] = r_k, rinv[2 k + 1] = 1 / r_k^2.  sx[j] is derived from colmax[j] (as niw_convert_a16_kernel does).
-__global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, const unsigned int *__restrict__ colmax,
-                                    unsigned char *__restrict__ Bop, float *__restrict__ rinv) {
+// W[k][i][j] (fp32, row-major per group) -> per group block: [hi | lo] fp16 parts in UMMA layout (compact, see
+// b_step_off), scaled, + the bias operand; blocks padded with zeros.  rinv[2 k] = r_k, rinv[2 k + 1] = 1 / r_k^2.
+// sx[j] is derived from colmax[j] (as niw_convert_a16_kernel does).
+__global__ void niw_pack_b16_kernel(const float *__restrict__ W, const float *__restrict__ bias, int ncols,
+                                    const unsigned int *__restrict__ colmax, unsigned char *__restrict__ Bop, float *__restrict__ rinv) {
   using namespace niwtc16;
   __shared__ float s_isx[D];   // 1 / sx_j
   __shared__ float s_r[2 * GB];  // per group: max |W / sx| (as ordered bits), then r_k
@@ -182,9 +189,7 @@ __global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, cons
     s_isx[threadIdx.x] = 1.f / sx;
   }
   __syncthreads();
-  // one scale per group: r_k brings max_ij |W[k][i][j] / sx_j| into [256, 512).  (A scale per output row would keep a
-  // few more bits for rows much smaller than the group's largest, but costs the epilogue a second shared-memory
-  // operand per output -- and the kernel is bound by shared-memory traffic.)
+  // one scale per group: r_k brings max_ij |W[k][i][j] / sx_j| into [256, 512)
   if (threadIdx.x < GB) s_r[threadIdx.x] = 0.f;
   __syncthreads();
   for (int nn = threadIdx.x; nn < TN; nn += blockDim.x) {  // nn = g * D + i
@@ -207,16 +212,40 @@ __global__ void niw_pack_b16_kernel(const float *__restrict__ W, int ncols, cons
     const int nn = e / D, j = e % D;
     const int g = nn / D, i = nn % D;
     const int k = gb * GB + g;
+    // operand row n' = (i / 16) * 64 + g * 16 + i % 16: contraction step st = j / 16 of the lower-triangular W_k reaches
+    // the rows (= accumulator columns) n' >= 64 st only, and one group's 16 outputs of a step are 16 contiguous columns
+    const uint32_t st = (uint32_t)j >> 4, np = (uint32_t)((i >> 4) * (GB * 16) + g * 16 + (i & 15));
+    if (np < 64u * st) continue;  // structurally zero (i < 16 st <= j): not stored
     const float w = k < ncols ? W[((size_t)k * D + i) * D + j] * s_isx[j] * s_r[GB + g] : 0.f;   // exact: powers of two
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
-    // operand row n' = (i / 16) * 64 + g * 16 + i % 16: contraction step st (j in [16 st, 16 st + 16)) of the lower-triangular
-    // W_k reaches the accumulator columns >= 64 st only, and one group's 16 outputs of a step are 16 contiguous columns
-    const uint32_t off = core_off16((uint32_t)((i >> 4) * (GB * 16) + g * 16 + (i & 15)), (uint32_t)j, TN / 8) / 2;
+    const uint32_t off = (b_step_off(st) + core_off16(np - 64u * st, (uint32_t)j & 15u, (TN - 64u * st) / 8)) / 2;
     dst[off] = hi;
     dst[B_PART_BYTES / 2 + off] = lo;
   }
+  // the bias operand: row n', k = 0: hi part of -b' / 512, k = 1: its lo part (b' = b r_k, the scale of Y'); with the
+  // ones operand (columns 0 and 1 = 512) one more MMA starts every accumulator at -b'
+  __half *bd = reinterpret_cast<__half *>(Bop + (size_t)gb * B_BYTES + 2 * B_PART_BYTES);
+  for (int e = threadIdx.x; e < TN * 16; e += blockDim.x) {
+    const int nn = e / 16, kk = e % 16;
+    const int g = nn / D, i = nn % D, k = gb * GB + g;
+    const uint32_t np = (uint32_t)((i >> 4) * (GB * 16) + g * 16 + (i & 15));
+    __half v = __float2half_rn(0.f);
+    if (kk < 2 && k < ncols) {
+      const float b = -bias[(size_t)k * D + i] * s_r[GB + g] * (1.f / BIAS_SCALE);
+      const __half hi = __float2half_rn(b);
+      v = kk == 0 ? hi : __float2half_rn(b - __half2float(hi));
+    }
+    bd[core_off16(np, (uint32_t)kk, TN / 8) / 2] = v;
+  }
 }
+
+#ifdef MSB_NIW_TRACE
+__device__ long long niw_trace[8192];
+#define NIW_TRACE(slot) do { if (blockIdx.x == 0 && t >= 8 && t < 40 && lane == 0) niw_trace[(t - 8) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define NIW_TRACE(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(niwtc16::THREADS, 1)
 niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__restrict__ Bop, const float *__restrict__ rinv,
@@ -228,8 +257,8 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
   unsigned char *sm = niw_smem;
   unsigned char *sB = sm;                      // [buffer][part][...]
   unsigned char *sA = sm + NB * B_BYTES;       // [ring slot][part][...]
-  float *sBias = reinterpret_cast<float *>(sA + A_BYTES);            // [2][SB_FLOATS]: bias r_k, coef (GB x 4), by item parity
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sBias + 2 * SB_FLOATS + D);
+  unsigned char *sOnes = sA + A_BYTES;         // the A operand of the bias product
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sOnes + ONES_BYTES);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 23);
   // barriers: b_full[2], b_free[2], a_full[NA], a_empty[NA], acc_full[2], acc_empty[2]
   constexpr int B_FULL = 0, B_FREE = 2, A_FULL = 4, A_EMPTY = 4 + NA, ACC_FULL = 4 + 2 * NA, ACC_EMPTY = 6 + 2 * NA;
@@ -249,7 +278,7 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
   if (tid == 0) {
     for (int i = 0; i < NB; i++) {
       mbar_init(smem_u32(&bars[B_FULL + i]), 1);    // b_full: the producer's expect_tx, completed by the bulk copies
-      mbar_init(smem_u32(&bars[B_FREE + i]), 1);    // b_free: tcgen05.commit after the item's last MMA
+      mbar_init(smem_u32(&bars[B_FREE + i]), 2);    // b_free: one tcgen05.commit per issuer after its last MMA of the item
     }
     for (int i = 0; i < NA; i++) {
       mbar_init(smem_u32(&bars[A_FULL + i]), 1);    // a_full: the producer's expect_tx, completed by the bulk copy
@@ -261,6 +290,12 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // ones operand: row r, k = 0 and 1 -> 512, everything else 0 (generic-proxy writes, read by the tensor core)
+  for (int i = tid; i < ONES_BYTES / 4; i += THREADS) {
+    const uint32_t byte = (uint32_t)i * 4u;   // [k/8][row/8][row%8][k%8]: the first 16-byte core row holds k = 0..7
+    reinterpret_cast<uint32_t *>(sOnes)[i] = (byte < (TM / 8) * 128u && (byte & 15u) == 0u) ? 0x60006000u : 0u;   // fp16 512 = 0x6000
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 1) {  // TMEM: all 512 columns (2 accumulators x 256)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -313,17 +348,22 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer.  All 32 lanes walk the loop (it is warp-uniform: the warp index comes from a shuffle, so the
-    // compiler keeps the addresses and descriptors in uniform registers) and wait on the barriers; one elected lane
-    // issues the MMAs and commits.  This loop paced the earlier versions: one lane, under a divergent branch, spent
-    // ~300 instructions per half-tile on 64-bit ring arithmetic (h % NA, h / NA), descriptor assembly and R2UR moves --
-    // at one warp's issue rate that is ~1900 cycles per tile for ~960 cycles of tensor work (ncu: the tensor pipe 46 %
-    // active, the issuer's samples spread over plain integer instructions, not waits).
+  } else if (warp == 1 || warp == 2 + EPI_WARPS) {
+    // ===== MMA issuers: warp 1 takes the even tiles (accumulator 0), warp 18 the odd ones (accumulator 1).  All 32 lanes
+    // walk the loop (it is warp-uniform: the warp index comes from a shuffle, so the compiler keeps the addresses and
+    // descriptors in uniform registers) and wait on the barriers; one elected lane issues the MMAs and commits.
+    // Why two: clock64 stamps of a single issuer (scripts/niw_trace.py) show ~1030 of a tile's ~1660 cycles inside the 13
+    // tcgen05.mma issues (~80 cycles each: the issue blocks until the tensor pipe takes the instruction, i.e. the queue
+    // is about one instruction deep) and ~630 cycles in three satisfied barrier waits, fences and the elect -- during
+    // which the pipe runs dry.  With the tiles dealt alternately to two issuers, one waits while the other feeds the pipe.
+    // (Before that, one lane under a divergent branch spent ~300 instructions per half-tile on 64-bit ring arithmetic,
+    // descriptor assembly and R2UR moves: ~1900 cycles per tile.)
+    const int par = warp == 1 ? 0 : 1;
     uint32_t abuf = 0, aphase = 0;
+    auto advance = [&]() { if (++abuf == (uint32_t)NA) { abuf = 0; aphase ^= 1u; } };
     int t = 0, it = 0;
-    const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
-    const uint32_t no_tri = (uint32_t)(blocked & 4);
+    const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB), sOnes0 = smem_u32(sOnes);
+    const uint32_t d_tmem = tmem + (uint32_t)par * TN;
     for (long long item = blockIdx.x; item < nItems; item += gridDim.x, it++) {
       const int sl = (int)(item / nGB);
       const int rt_lo = sl * SL, rt_hi = rt_lo + SL < nRT ? rt_lo + SL : nRT;
@@ -331,94 +371,86 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
       mbar_wait(smem_u32(&bars[B_FULL + bbuf]), (uint32_t)((it >> 1) & 1));
       const uint32_t sB_cur = sB0 + (uint32_t)bbuf * B_BYTES;
       for (int rt = rt_lo; rt < rt_hi; rt++, t++) {
-        const int acc = t & 1;
-        if (t >= 2) mbar_wait(smem_u32(&bars[ACC_EMPTY + acc]), (uint32_t)(((t >> 1) - 1) & 1));  // the epilogue has read this accumulator
-        const uint32_t d_tmem = tmem + (uint32_t)acc * TN;
+        if ((t & 1) != par) { advance(); advance(); continue; }   // the other issuer's tile
+        NIW_TRACE(0);
+        if (t >= 2) mbar_wait(smem_u32(&bars[ACC_EMPTY + par]), (uint32_t)(((t >> 1) - 1) & 1));  // the epilogue has read this accumulator
+        NIW_TRACE(1);
 #pragma unroll
         for (int half = 0; half < 2; half++) {
           mbar_wait(smem_u32(&bars[A_FULL + abuf]), aphase);
+          NIW_TRACE(2 + half * 2);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = sA0 + abuf * (uint32_t)(2 * A_HALF_BYTES), a_lo = a_hi + A_HALF_BYTES;
-          const uint32_t b_hi = sB_cur + (uint32_t)half * (32 / 8) * (TN / 8) * 128u, b_lo = b_hi + B_PART_BYTES;
+          const uint32_t b_hi = sB_cur, b_lo = b_hi + B_PART_BYTES;
           if (elect_one()) {
+            if (half == 0) {
+              // the accumulator starts at -b' (the group's bias in the scale of Y'): ones operand (columns 0, 1 = 512) x
+              // bias operand (k = 0: hi, k = 1: lo part of -b' / 512).  One more K = 16 step at full N (128 of ~1090 tensor
+              // cycles per tile) instead of a subtraction per element in the epilogue.
+              mma_f16(d_tmem, niwtc::smem_desc(sOnes0, (TM / 8) * 128u, 128u), niwtc::smem_desc(sB_cur + 2 * B_PART_BYTES, (TN / 8) * 128u, 128u),
+                      idesc_f16(TN), 0u);
+            }
 #pragma unroll
             for (int ks = 0; ks < 2; ks++) {  // K = 16 per instruction: 2 core-matrix columns
               // W_k is lower triangular: contraction step st (j in [16 st, 16 st + 16)) only reaches the outputs i >= 16 st,
               // which the operand row order n' = (i / 16) * 64 + g * 16 + i % 16 makes the contiguous rows / accumulator
               // columns [64 st, 256): N = 256, 192, 128, 64 over the four steps, 640 instead of 1024 columns of tensor
-              // work per tile.
+              // work per tile, and B keeps those rows only (b_step_off).
               const uint32_t st = (uint32_t)(half * 2 + ks);
-              const uint32_t n0 = no_tri ? 0u : st * 64u;
-              const uint32_t idn = idesc_f16(TN - n0);
+              const uint32_t n0 = st * 64u, nn = TN - n0;
+              const uint32_t idn = idesc_f16(nn);
               const uint32_t ao = (uint32_t)ks * 2u * (TM / 8) * 128u;
-              const uint32_t bo = (uint32_t)ks * 2u * (TN / 8) * 128u + (n0 / 8u) * 128u;
+              const uint32_t bo = b_step_off(st);
               const uint64_t dah = niwtc::smem_desc(a_hi + ao, (TM / 8) * 128u, 128u), dal = niwtc::smem_desc(a_lo + ao, (TM / 8) * 128u, 128u);
-              const uint64_t dbh = niwtc::smem_desc(b_hi + bo, (TN / 8) * 128u, 128u), dbl = niwtc::smem_desc(b_lo + bo, (TN / 8) * 128u, 128u);
-              mma_f16(d_tmem + n0, dah, dbh, idn, st ? 1u : 0u);
+              const uint64_t dbh = niwtc::smem_desc(b_hi + bo, (nn / 8) * 128u, 128u), dbl = niwtc::smem_desc(b_lo + bo, (nn / 8) * 128u, 128u);
+              mma_f16(d_tmem + n0, dah, dbh, idn, 1u);
               mma_f16(d_tmem + n0, dah, dbl, idn, 1u);
               mma_f16(d_tmem + n0, dal, dbh, idn, 1u);
             }
             niwtc::mma_commit(smem_u32(&bars[A_EMPTY + abuf]));            // A half-buffer free once these MMAs complete
-            if (half == 1) niwtc::mma_commit(smem_u32(&bars[ACC_FULL + acc]));  // accumulator ready for the epilogue
-            if (half == 1 && rt == rt_hi - 1) niwtc::mma_commit(smem_u32(&bars[B_FREE + bbuf]));  // this item's B buffer may be overwritten
+            if (half == 1) niwtc::mma_commit(smem_u32(&bars[ACC_FULL + par]));  // accumulator ready for the epilogue
           }
           __syncwarp();
-          if (++abuf == (uint32_t)NA) { abuf = 0; aphase ^= 1u; }
+          NIW_TRACE(3 + half * 2);
+          advance();
         }
       }
+      // this issuer is done with the item's B buffer once its MMAs so far have completed (it commits even when none of
+      // the item's tiles was its own: the barrier counts both issuers)
+      if (elect_one()) niwtc::mma_commit(smem_u32(&bars[B_FREE + bbuf]));
+      __syncwarp();
     }
   } else {
     // ===== epilogue: warps 2..17, all sixteen on EVERY tile.  Warp e reads TMEM lane quadrant warp % 4 (fixed by the
-    // hardware) and the 64 accumulator columns of group e / 4 of the block: eight tcgen05.ld 16x256b.x2 issued back to
-    // back, ONE wait, and the accumulator is released as soon as the values are in registers -- before any arithmetic
-    // (the MMAs of tile t + 2 wait for the readers of tile t).
-    // The 16x256b shape hands a thread two adjacent columns of four rows (the mma accumulator fragment: thread T holds
-    // rows T / 4 + 8 m, columns 8 j + 2 (T % 4) + {0, 1}) instead of all the columns of one row, so a thread needs the bias
-    // of 16 of the group's 64 outputs only: they stay in registers for the whole item, and the per-element shared-memory
-    // read of the bias (ncu: one LDS.128 per 4 elements, ~3 wavefronts each, half of the LSU pipe and the scoreboard
-    // stall of every FADD2) is gone.  The price is a 4-lane transpose-reduce of the row sums (3 shuffles per tile).
+    // hardware: lane = row) and the 64 accumulator columns of group e / 4 of the block: four tcgen05.ld 32x32b.x16
+    // issued back to back, ONE wait, and the accumulator is released as soon as the values are in registers -- before
+    // any arithmetic (the MMAs of tile t + 2 wait for the readers of tile t).  The accumulator already holds Y' - b'
+    // (the bias product of the MMA loop), so what is left per element is one fused multiply-add of the square sum; the
+    // group's three coefficients live in registers for the whole item: no shared-memory traffic, no barrier.
+    // History of this loop, per 128-row tile against ~1000 cycles of tensor work: the columns split over four / eight
+    // warps walking their loads one behind the other with the bias read from shared memory (one LDS.128 per 4 elements,
+    // ~3 wavefronts each): ~1900; sixteen warps, loads in flight together: ~1650 once the MMA issue loop no longer paced
+    // the kernel; bias in registers through the 16x256b load shape (a thread then needs 16 of the 64 values, but that
+    // shape reads TMEM ~5x slower): ~1430.
     const int e = warp - 2;
     const int ew = warp & 3;                 // TMEM lanes 32 ew .. 32 ew + 31
     const int g = e >> 2;                    // group g of the block
-    const int etid = e * 32 + lane;          // 0..511
-    const int t4 = lane & 3, t8 = lane >> 2;
-    const int rloc = t8 + 8 * (2 * (lane & 1) + ((lane >> 1) & 1));   // the row of the quadrant this lane ends up owning
-    int t = 0, it = 0;
-    for (long long item = blockIdx.x; item < nItems; item += gridDim.x, it++) {
+    int t = 0;
+    for (long long item = blockIdx.x; item < nItems; item += gridDim.x) {
       const int gb = (int)(item % nGB), sl = (int)(item / nGB);
       const int rt_lo = sl * SL, rt_hi = rt_lo + SL < nRT ? rt_lo + SL : nRT;
-      // this group block's bias and coefficients, staged once per item into the copy of the item's parity: a warp that
-      // writes copy it & 1 has passed the barrier of item it - 1, which every warp reaches only after its last read of
-      // item it - 2 -- one barrier per item suffices
-      float *sb = sBias + (size_t)(it & 1) * SB_FLOATS;
-      const float *sc = sb + TN;
-      for (int i = etid; i < SB_FLOATS; i += EPI_WARPS * 32) {
-        float v = 0.f;
-        if (i < TN) {  // bias' = b r_k
-          const int k = gb * GB + i / D;
-          if (k < ncols) v = bias[(size_t)k * D + (i % D)] * rinv[(size_t)k * 2];
-        } else {       // c0, c1, 1 / (dof r_k^2): q' = r_k^2 q
-          const int k = gb * GB + (i - TN) / 4, c = (i - TN) & 3;
-          if (k < ncols) v = coef[(size_t)k * 4 + c] * (c == 2 ? rinv[(size_t)k * 2 + 1] : 1.f);
-        }
-        sb[i] = v;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       const int k = gb * GB + g;
       const bool kok = k < ncols;
-      const float c0 = sc[g * 4 + 0], c1l2 = sc[g * 4 + 1] * 0.6931471805599453f, idof = sc[g * 4 + 2];
-      float2 nb[8];   // minus the bias of this thread's 16 outputs: i = 16 ib + 8 j + 2 t4 + {0, 1}
-#pragma unroll
-      for (int ib = 0; ib < 4; ib++)
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          const float2 b2 = *reinterpret_cast<const float2 *>(sb + g * D + ib * 16 + j * 8 + 2 * t4);
-          nb[ib * 2 + j] = make_float2(-b2.x, -b2.y);
-        }
-      const float base_k = (base && kok) ? __ldg(base + k) : 0.f;
+      float c0 = 0.f, c1l2 = 0.f, idof = 0.f, base_k = 0.f;
+      if (kok) {  // c0, c1 ln 2 (the log below is base 2), 1 / (dof r_k^2): q' = r_k^2 q
+        c0 = __ldg(coef + (size_t)k * 4 + 0);
+        c1l2 = __ldg(coef + (size_t)k * 4 + 1) * 0.6931471805599453f;
+        idof = __ldg(coef + (size_t)k * 4 + 2) * __ldg(rinv + (size_t)k * 2 + 1);
+        if (base) base_k = __ldg(base + k);
+      }
       // this lane's output element of the item's first tile, then one tile (128 rows) further per step
-      const size_t r0 = (size_t)rt_lo * TM + ew * 32 + rloc;                      // row index relative to row_lo
-      float *dst = (blocked & 1) ? scores + (((size_t)rt_lo * (TM / 32) + ew) * ld + (size_t)k) * 32 + rloc
+      const size_t r0 = (size_t)rt_lo * TM + ew * 32 + lane;                      // row index relative to row_lo
+      float *dst = (blocked & 1) ? scores + (((size_t)rt_lo * (TM / 32) + ew) * ld + (size_t)k) * 32 + lane
                                  : scores + r0 * ld + (size_t)k;
       const size_t dstep = (blocked & 1) ? (size_t)(TM / 32) * ld * 32 : (size_t)TM * ld;
       long long left = (long long)nrows - (long long)r0;                           // > 0: the row exists
@@ -429,41 +461,29 @@ niw_tc16_kernel(const unsigned char *__restrict__ A16, const unsigned char *__re
         float old = base_k;
         if (ok && !base) old = *dst;
         mbar_wait(smem_u32(&bars[ACC_FULL + acc]), (uint32_t)((t >> 1) & 1));
+        if (warp == 2) NIW_TRACE(6);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // accumulator columns: block i / 16 holds [g][i % 16]; this warp's group is 16 contiguous columns of each block
         const uint32_t tb = tbase0 + (uint32_t)(acc * TN);
-        uint32_t r[2][4][8];   // [lane half][block][j: r0 r1 = row t8, r2 r3 = row t8 + 8]
+        uint32_t r[4][16];
 #pragma unroll
-        for (int hh = 0; hh < 2; hh++)
-#pragma unroll
-          for (int ib = 0; ib < 4; ib++) tmem_ld_16x256b_x2(tb + ((uint32_t)(hh * 16) << 16) + (uint32_t)ib * 64u, r[hh][ib]);
+        for (int ib = 0; ib < 4; ib++) tmem_ld16_issue(tb + (uint32_t)ib * 64u, r[ib]);
         niwtc::tmem_ld_wait();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
-        float2 q2[4];   // rows t8, t8 + 8, t8 + 16, t8 + 24: partial sums over this thread's 16 outputs
+        if (warp == 2) NIW_TRACE(7);
+        float2 q2[4];
 #pragma unroll
-        for (int m = 0; m < 4; m++) q2[m] = make_float2(0.f, 0.f);
+        for (int ib = 0; ib < 4; ib++) {
+          q2[ib] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int ib = 0; ib < 4; ib++)
-#pragma unroll
-          for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int hh = 0; hh < 2; hh++)
-#pragma unroll
-              for (int m = 0; m < 2; m++) {
-                const uint32_t *v = r[hh][ib] + j * 4 + m * 2;
-                const float2 y = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), nb[ib * 2 + j]);
-                q2[hh * 2 + m] = __ffma2_rn(y, y, q2[hh * 2 + m]);
-              }
-        float q4[4];
-#pragma unroll
-        for (int m = 0; m < 4; m++) q4[m] = q2[m].x + q2[m].y;
-        // transpose-reduce over the four lanes that share t8: lane bit 0 keeps rows {0, 1} or {2, 3}, bit 1 picks one
-        const bool b0 = lane & 1, b1 = lane & 2;
-        const float s0 = (b0 ? q4[2] : q4[0]) + __shfl_xor_sync(0xffffffffu, b0 ? q4[0] : q4[2], 1);
-        const float s1 = (b0 ? q4[3] : q4[1]) + __shfl_xor_sync(0xffffffffu, b0 ? q4[1] : q4[3], 1);
-        const float q = (b1 ? s1 : s0) + __shfl_xor_sync(0xffffffffu, b1 ? s0 : s1, 2);
+          for (int c = 0; c < 8; c++) {
+            const float2 y = make_float2(__uint_as_float(r[ib][2 * c]), __uint_as_float(r[ib][2 * c + 1]));
+            q2[ib] = __ffma2_rn(y, y, q2[ib]);
+          }
+        }
+        const float q = ((q2[0].x + q2[0].y) + (q2[1].x + q2[1].y)) + ((q2[2].x + q2[2].y) + (q2[3].x + q2[3].y));
         if (ok) {
           float o = old;
           if (q == q) o += fmaf(c1l2, log2_1p_pos(q * idof), c0);  // NaN = masked row: contributes nothing
@@ -493,7 +513,6 @@ static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, Kernel
                                  const float *coef, float *Bop, unsigned char *A16, size_t ncols, float *scores, size_t ld,
                                  size_t row_lo, size_t row_hi, int sm_count, const float *base, bool blocked, std::string &err) {
   using namespace niwtc16;
-  static const bool no_tri = getenv("MSB_NIW_NO_TRI") != nullptr;  // diagnostics switch, read once
   const int nGB = (int)((ncols + GB - 1) / GB);
   unsigned int *colmax = reinterpret_cast<unsigned int *>(Bop);
   float *rinv = Bop + 2 * D;
@@ -517,7 +536,7 @@ static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, Kernel
   prof->end(stream); (*launches)++;
   if (int s = check("niw_convert_a16_kernel launch")) return s;
   prof->begin("niw_pack_b16_kernel", stream);
-  niw_pack_b16_kernel<<<nGB, 256, 0, stream>>>(W, (int)ncols, colmax, Bblk, rinv);
+  niw_pack_b16_kernel<<<nGB, 256, 0, stream>>>(W, bias, (int)ncols, colmax, Bblk, rinv);
   prof->end(stream); (*launches)++;
   if (int s = check("niw_pack_b16_kernel launch")) return s;
   // about 24 items per CTA (at most 32 tiles per slice): balance to within a few percent, one B reload per item
@@ -526,7 +545,7 @@ static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, Kernel
   const int grid = (int)std::min<long long>(sm_count, nItems);
   prof->begin("niw_tc16_kernel", stream);
   niw_tc16_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(A16, Bblk, rinv, bias, coef, (int)ncols, scores, ld, row_lo, row_hi, SL,
-                                                         base, (blocked ? 1 : 0) | (no_tri ? 4 : 0));
+                                                         base, blocked ? 1 : 0);
   prof->end(stream); (*launches)++;
   return check("niw_tc16_kernel launch");
 }

@@ -76,6 +76,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // bounded wait: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  // fast path: a phase that has already completed costs one try_wait, not a clock read as well
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  if (done) return;
   const long long t0 = clock64();
   while (true) {
     asm volatile(

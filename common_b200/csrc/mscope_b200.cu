@@ -2546,3 +2546,9 @@ extern "C" MSB_API int msb_state_sample_value(msb_state *st, size_t feature, siz
   const FeatDev &f = st->feats[feature];
   return launch_draws(ctx, st->models[feature], 0, st->d_hp + f.hp_off, st->d_ss + f.ss_off + (size_t)slot * f.ss_w, seed, counter, n, out);
 }
+
+#ifdef MSB_NIW_TRACE
+extern "C" MSB_API int msb_debug_niw_trace(long long *out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, msb::niw_trace, (size_t)n * sizeof(long long));
+}
+#endif
