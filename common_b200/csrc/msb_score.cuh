@@ -98,6 +98,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 // global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned), completes on bar
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -592,6 +604,209 @@ score_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restri
         float *dst = scores + (rb * ld + (size_t)kt * KT) * 32 + lane;
 #pragma unroll 8
         for (int c = 0; c < KT; c++) dst[(size_t)c * 32] = tile[lane * (KT + 1) + c];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// score_tables_persistent_kernel -- the sweep's tables-only score kernel (every feature a lookup table, no slow-path
+// cells, blocked output), one CTA per SM for the whole launch.
+//
+// Same mapping as score_kernel<V, RW, NW, true, true> (a warp owns RW rows, lane l owns V groups of the k-tile, one
+// conflict-free wavefront per lookup), but the CTA walks work items (row tile, k-tile) -- item = blockIdx.x + j gridDim.x,
+// k-tile fastest, so the CTAs running together share row tiles through L2 exactly as the one-item-per-block grid did --
+// and the stage ring runs THROUGH the item boundaries: while the warps of an item add the log-prior and store, the
+// copies of the next item's first S features are already in flight.  The epilogue stores straight from registers (see
+// there), so it needs no block-wide barrier, no drained ring and no transposition buffer.  ncu on the
+// one-item-per-block kernel (C2, profiles/r01_prof_score_r1j_C2.txt) put ~13 % of the warp samples on block
+// boundaries: the launch of 6839 blocks of 512 threads, the feature-table build, the first stage's latency, the
+// __syncthreads before the transposition, the ring idle during the stores.
+// ---------------------------------------------------------------------------------------------------
+template <int V, int RW, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, 1)
+score_tables_persistent_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restrict__ params, size_t region_rows,
+                               uint32_t stage_bytes, int S, const float *__restrict__ base, float *__restrict__ scores, size_t ld,
+                               size_t row_org, size_t row_lo, size_t row_hi, int ktiles, int tail_g, long long n_items) {
+  constexpr int KT = 32 * V;
+  constexpr int RL = RW / 32;
+  constexpr int RB = NW * RW;                                   // rows per item
+  constexpr uint32_t X_BYTES = RB * 4;                          // row values
+  constexpr uint32_t CHUNK_OFF = (X_BYTES + RB / 8 + 127) / 128 * 128;   // the stage layout of score_kernel (no slow masks here)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [S stages | mbarriers full[S], empty[S] | feature table]
+  unsigned char *stages = smem_raw;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * stage_bytes);
+  FeatS *ftab = reinterpret_cast<FeatS *>(bars + 2 * S);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < nfeat; i += (NW + 1) * 32) {
+    const FeatDev f = feats[i];
+    FeatS t;
+    t.scol = f.scol; t.slowmask = f.slowmask; t.col = f.col;
+    t.rowoff = f.rowoff; t.rows = f.rows; t.ncat = f.ncat;
+    t.kind = (uint16_t)f.kind; t.has_slow = 0;
+    t.sx_off = t.sc_off = 0; t.last = 1; t.fuse = 0;
+    ftab[i] = t;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) {
+      mbar_init(smem_u32(&bars[s]), 1);
+      mbar_init(smem_u32(&bars[S + s]), NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long my_items = n_items > (long long)blockIdx.x ? (n_items - 1 - (long long)blockIdx.x) / (long long)gridDim.x + 1 : 0;
+  const long long nq = my_items * nfeat;   // (item, feature) pairs this CTA walks, in order
+
+  // item -> (row tile, k-tile) without a division per step: the CTA's items advance by gridDim.x
+  const int dk = (int)(gridDim.x % (unsigned)ktiles);
+  const size_t dr = gridDim.x / (unsigned)ktiles;
+  // thread 0: everything the next (item, feature) pair needs -> stage s (row values, parameter chunk)
+  int iss_d = 0, iss_kt = (int)(blockIdx.x % (unsigned)ktiles);
+  size_t iss_rt = blockIdx.x / (unsigned)ktiles;
+  auto issue_next = [&](int s) {
+    const FeatS t = ftab[iss_d];
+    const uint32_t cbytes = t.rows * (uint32_t)(KT * sizeof(float));
+    const uint32_t bar = smem_u32(&bars[s]);
+    const uint32_t dst = smem_u32(stages + (size_t)s * stage_bytes);
+    mbar_expect_tx(bar, cbytes + X_BYTES);
+    bulk_g2s(dst, t.scol + (row_org + iss_rt * RB), X_BYTES, bar);
+    bulk_g2s(dst + CHUNK_OFF, params + ((size_t)iss_kt * region_rows + t.rowoff) * KT, cbytes, bar);
+    if (++iss_d == nfeat) {
+      iss_d = 0;
+      iss_kt += dk; iss_rt += dr;
+      if (iss_kt >= ktiles) { iss_kt -= ktiles; iss_rt++; }
+    }
+  };
+  if (warp == NW) {
+    // ===== producer warp: one lane keeps the ring full -- the first S pairs at once, then pair q into its stage as soon
+    // as every consumer warp has released pair q - S.  A consumer thread doing this on the side (thread 0 of the
+    // one-item-per-block kernel) has to wait for the slowest warp of every feature before it goes on with its own
+    // lookups: warp 0 becomes the laggard of the block and the others run S features ahead, then wait for it.
+    if (lane == 0) {
+      int rs = 0;
+      uint32_t rpar = 1;   // parity of the release awaited: 0 during the ring's second round, then alternating
+      for (long long q = 0; q < nq; q++) {
+        if (q >= S) mbar_wait(smem_u32(&bars[S + rs]), rpar);
+        issue_next(rs);
+        if (++rs == S) { rs = 0; rpar ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  int s = 0;
+  uint32_t parity = 0;
+  int kt = (int)(blockIdx.x % (unsigned)ktiles);
+  size_t rt = blockIdx.x / (unsigned)ktiles;
+  for (long long it = 0; it < my_items; it++) {
+    if (it) {
+      kt += dk; rt += dr;
+      if (kt >= ktiles) { kt -= ktiles; rt++; }
+    }
+    const size_t row0 = row_org + rt * RB + (size_t)warp * RW;
+    // Ragged last k-tile (V = 1): when it holds tail_g <= 16 groups, build_params_kernel replicates its table columns
+    // 32 / tail_g times across the chunk row, and lane l owns group l % tail_g of the rows r = l / tail_g (mod 32 / tail_g):
+    // one wavefront then serves 32 / tail_g rows (see score_kernel)
+    const bool tail = V == 1 && tail_g > 0 && kt == ktiles - 1;
+
+    float acc[RW][V];
+#pragma unroll
+    for (int r = 0; r < RW; r++)
+#pragma unroll
+      for (int v = 0; v < V; v++) acc[r][v] = 0.f;
+
+    for (int d = 0; d < nfeat; d++) {
+      mbar_wait(smem_u32(&bars[s]), parity);
+      const unsigned char *st = stages + (size_t)s * stage_bytes;
+      const uint4 *xq = reinterpret_cast<const uint4 *>(st) + warp * (RW / 4);
+      const uint32_t chunk_s = smem_u32(reinterpret_cast<const float *>(st + CHUNK_OFF) + lane * V);
+      if (V == 1 && tail) {
+        auto tail_lookup = [&](auto rtag) {
+          constexpr int R = decltype(rtag)::value;  // rows per wavefront
+          const uint32_t *xw = reinterpret_cast<const uint32_t *>(st) + warp * RW + lane / (32 / R);
+#pragma unroll
+          for (int q = 0; q < RW / R; q++) {
+            float tv[1];
+            lds_vec<1>(tv, chunk_s + xw[q * R] * (uint32_t)(KT * sizeof(float)));
+            acc[q][0] += tv[0];
+          }
+        };
+        if (tail_g == 8) tail_lookup(std::integral_constant<int, 4>{});
+        else tail_lookup(std::integral_constant<int, 2>{});
+      } else {
+#pragma unroll
+        for (int r4 = 0; r4 < RW / 4; r4++) {
+          const uint4 q = xq[r4];
+          const uint32_t idx[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            VecF<V> tv;
+            lds_vec<V>(tv.v, chunk_s + idx[e] * (uint32_t)(KT * sizeof(float)));
+            if constexpr (V % 2 == 0) {
+#pragma unroll
+              for (int h = 0; h < V / 2; h++) {
+                const float2 a = __fadd2_rn(make_float2(acc[r4 * 4 + e][2 * h], acc[r4 * 4 + e][2 * h + 1]),
+                                            make_float2(tv.v[2 * h], tv.v[2 * h + 1]));
+                acc[r4 * 4 + e][2 * h] = a.x;
+                acc[r4 * 4 + e][2 * h + 1] = a.y;
+              }
+            } else {
+#pragma unroll
+              for (int v = 0; v < V; v++) acc[r4 * 4 + e][v] += tv.v[v];
+            }
+          }
+        }
+      }
+      // release the stage: the producer warp refills it once every consumer warp has released it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[S + s]));
+      if (++s == S) { s = 0; parity ^= 1u; }
+    }
+
+    // epilogue: + log(pseudocount) (group_manager.hpp:274-283).  No transposition: in the blocked layout the 32 rows of
+    // one (row block, group) are 128 contiguous bytes, and a lane already holds all the rows of its V groups -- it
+    // writes them itself, eight 16-byte stores per (row block, group).  A warp's store instruction then touches 32 lines
+    // (16 bytes each; the next instruction completes the sectors, L2 merges them), twice the write requests of the
+    // transposed form, but no shared-memory round trip (2 x 128 KB of wavefronts per item) and no tile buffers: the
+    // ring keeps all of shared memory.
+    if (V == 1 && tail) {
+      auto tail_epilogue = [&](auto rtag) {
+        constexpr int R = decltype(rtag)::value;  // rows per wavefront; this lane: rows R q + sub, group g
+        constexpr int G = 32 / R;
+        const int sub = lane / G, g = lane % G;
+        const float bg = base[(size_t)kt * KT + g];
+#pragma unroll
+        for (int j = 0; j < RL; j++) {
+          const size_t rb = (row0 - row_org) / 32 + j;
+          if (row0 + (size_t)j * 32 < row_hi) {
+            float *dst = scores + (rb * ld + (size_t)kt * KT + g) * 32 + sub;
+#pragma unroll
+            for (int q = 0; q < G; q++) dst[q * R] = acc[j * G + q][0] + bg;
+          }
+        }
+      };
+      if (tail_g == 8) tail_epilogue(std::integral_constant<int, 4>{});
+      else tail_epilogue(std::integral_constant<int, 2>{});
+    } else {
+      VecF<V> b;
+      b.load(base + (size_t)kt * KT + lane * V);
+#pragma unroll
+      for (int j = 0; j < RL; j++) {
+        const size_t rb = (row0 - row_org) / 32 + j;
+        if (row0 + (size_t)j * 32 < row_hi) {
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            float4 *dst = reinterpret_cast<float4 *>(scores + (rb * ld + (size_t)kt * KT + lane * V + v) * 32);
+#pragma unroll
+            for (int r4 = 0; r4 < 8; r4++)
+              dst[r4] = make_float4(acc[j * 32 + r4 * 4 + 0][v] + b.v[v], acc[j * 32 + r4 * 4 + 1][v] + b.v[v],
+                                    acc[j * 32 + r4 * 4 + 2][v] + b.v[v], acc[j * 32 + r4 * 4 + 3][v] + b.v[v]);
+          }
+        }
       }
     }
   }

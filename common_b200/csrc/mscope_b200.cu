@@ -242,6 +242,10 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   CU_TRY(opt_in_smem(score_kernel<2, 32, 16, true, true>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<4, 32, 8, true, true>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<1, 32, 8, true, true>, c->smem_optin));
+  CU_TRY(opt_in_smem((score_tables_persistent_kernel<1, 64, 16>), c->smem_optin));
+  CU_TRY(opt_in_smem((score_tables_persistent_kernel<2, 32, 16>), c->smem_optin));
+  CU_TRY(opt_in_smem((score_tables_persistent_kernel<4, 32, 8>), c->smem_optin));
+  CU_TRY(opt_in_smem((score_tables_persistent_kernel<1, 32, 8>), c->smem_optin));
   CU_TRY(opt_in_smem((score_bundle_kernel<2, 32, 16, false>), c->smem_optin));
   CU_TRY(opt_in_smem((score_bundle_kernel<2, 32, 16, true>), c->smem_optin));
   CU_TRY(opt_in_smem((score_bundle_kernel<4, 32, 8, false>), c->smem_optin));
@@ -1529,6 +1533,36 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
       }
     }
     if (st->cfg == 4) return fail(MSB_ERR_UNSUPPORTED, "score shape 4 exists for the bundled general kernel only");
+    const bool persistent = getenv("MSB_PERSISTENT") != nullptr;   // read per call: the test switches it
+    if (blocked && st->tables_only && persistent) {
+      // The persistent form of the sweep's tables-only kernel (score_tables_persistent_kernel): one CTA per SM walks
+      // (row tile, k-tile) items, the ring runs through the item boundaries, a seventeenth warp is the producer, the
+      // epilogue stores straight from registers.  Measured on C2 against the one-item-per-block grid (1.378 ms): 1.487 ms
+      // with thread 0 as the producer and transposition tiles of its own (4 stages instead of 6), 1.498 with the direct
+      // stores (6 stages), 1.974 with a producer that polls instead of waiting, 1.394 with the producer warp (96
+      // registers) -- no gain: the kernel sits at 0.79 of the shared-memory wavefront roof either way, and what the block
+      // boundaries cost the grid form, the hardware scheduler's dynamic balance gives back.  Opt-in, kept under test.
+      const size_t stage_p = (chunk_off + st->max_chunk_rows * KT * sizeof(float) + 127) / 128 * 128;
+      const size_t tiles_p = 0;   // the epilogue stores straight from registers
+      if (ctx->smem_optin >= fixed + tiles_p + 2 * stage_p) {
+        const int Sp = (int)std::min<size_t>(8, (ctx->smem_optin - fixed - tiles_p) / stage_p);
+        const size_t smem_p = (size_t)Sp * stage_p + tiles_p + fixed;
+        const long long n_items = (long long)grid;
+        const unsigned grid_p = (unsigned)std::min<long long>(n_items, ctx->sm_count);
+#define MSB_PERSIST_LAUNCH(V_, RW_, NW_)                                                                                        \
+        LAUNCH(ctx, (score_tables_persistent_kernel<V_, RW_, NW_>), grid_p, (NW_ + 1) * 32, smem_p, st->d_feats_scalar, (int)st->n_scalar, \
+               st->d_params, st->region_rows, (uint32_t)stage_p, Sp, st->d_base_score, scores, st->ld, org, row_lo, row_hi,     \
+               (int)ktiles, st->tail_g, n_items)
+        switch (st->cfg) {
+          case 0: MSB_PERSIST_LAUNCH(1, 64, 16); break;
+          case 1: MSB_PERSIST_LAUNCH(2, 32, 16); break;
+          case 2: MSB_PERSIST_LAUNCH(4, 32, 8); break;
+          default: MSB_PERSIST_LAUNCH(1, 32, 8); break;
+        }
+#undef MSB_PERSIST_LAUNCH
+        goto scalar_done;
+      }
+    }
     if (smem > ctx->smem_optin) return fail(MSB_ERR_UNSUPPORTED, "score kernel shared memory does not fit");
 #define MSB_SCORE_ARGS st->d_feats_scalar, (int)st->n_scalar, st->d_params, st->region_rows, (uint32_t)stage, S, st->d_base_score, \
                        scores, st->ld, org, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K, (int)ktiles, st->tail_g

@@ -485,6 +485,24 @@ def test_tile_and_blocked_samplers_draw_identically(ctx, oracle, k, monkeypatch)
     st.close()
 
 
+@pytest.mark.parametrize("k,descs", [(200, [cb.dd(256)] * 4), (40, [cb.dd(7), cb.bb, cb.dd(30)]), (3, [cb.bb] * 5), (70, [cb.dd(12)] * 3)])
+def test_persistent_tables_kernel_scores_identically(ctx, oracle, k, descs, monkeypatch):
+    # MSB_PERSISTENT=1: one CTA per SM walks the (row tile, k-tile) items with a producer warp and stores the blocked
+    # layout straight from registers; scores and draws must equal the one-item-per-block kernel's bit for bit
+    n = 5000
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=77, extra_empty=1)
+    st.sweep(seed=5, sweep=0)
+    a = st.assignments().copy()
+    S = st.read_last_scores().copy()
+    st.close()
+    monkeypatch.setenv("MSB_PERSISTENT", "1")
+    st, view, z, gids, hp, ss, counts = make_state(ctx, oracle, descs, n, k, seed=77, extra_empty=1)
+    st.sweep(seed=5, sweep=0)
+    assert np.array_equal(S.view(np.uint32), st.read_last_scores().view(np.uint32))
+    assert np.array_equal(a, st.assignments())
+    st.close()
+
+
 def test_sampler_division_sequence_equals_ieee_division_on_device(ctx):
     import ctypes as C
     from common_b200 import _lib
