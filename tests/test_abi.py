@@ -41,6 +41,41 @@ def test_library_is_sm100a_native():
     assert archs == {"sm_100a"}, archs
 
 
+def test_sass_holds_the_blackwell_instructions_the_design_claims():
+    # profiles/r02_sass_histogram.txt is scripts/sass_histogram.py's output for the committed sources; here the same
+    # disassembly is checked for what DESIGN.md says the hot kernels are made of
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    per, cur = {}, None
+    for line in out.stdout.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per[cur] = {}
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur:
+            for op in ("UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "SYNCS", "FFMA2", "FADD2", "MUFU"):
+                if m.group(1).startswith(op):
+                    per[cur][op] = per[cur].get(op, 0) + 1
+
+    def kernels(sub):
+        ks = [c for k, c in per.items() if sub in k]
+        assert ks, sub
+        return ks
+
+    niw = kernels("niw_tc16_kernel")[0]
+    assert niw.get("UTCHMMA", 0) >= 13          # bias product + 4 k-steps x 3 products (tcgen05.mma)
+    assert niw.get("LDTM", 0) >= 4 and niw.get("UTCBAR", 0) >= 3 and niw.get("UBLKCP", 0) >= 2
+    for c in kernels("msb12score_kernelI"):         # every shape streams its parameter chunks with bulk copies on mbarriers
+        assert c.get("UBLKCP", 0) >= 1 and c.get("SYNCS", 0) >= 4
+    for k, c in per.items():                    # the nich loop of the V >= 2 shapes runs on packed fp32 operations
+        if "score_bundle_kernelILi4" in k:
+            assert c.get("FFMA2", 0) >= 100 and c.get("FADD2", 0) >= 100 and c.get("MUFU", 0) >= 50
+    assert any(c.get("UBLKCP", 0) for c in kernels("sample_tile_kernel"))
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
