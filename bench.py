@@ -361,25 +361,25 @@ def run_config(ctx, device, stream, comm, workload, args, rank, local_rank, worl
         for kk, v in st.last_timings(back).items():
             phase[kk] += v * steps / timed
     launches = ctx.launch_count() - launches0
-    clk = None
-    if rank == 0:
-        # nvidia-smi cannot sample faster than ~100 ms: when the timed region is shorter than that,
-        # keep the same step running (untimed) until the sampler has seen the GPU under this load
-        extra_t0 = time.perf_counter()
-        extra = 0
-        while len(clocks.rows) < 5 and time.perf_counter() - extra_t0 < 3.0 and world == 1:
-            step(warmup + steps + extra)
-            torch.cuda.synchronize(device)
-            extra += 1
-        torch.cuda.synchronize(device)
-        clk = clocks.stop()
-        clk["sampled_over"] = "timed region" if extra == 0 else "timed region + %d more untimed steps of the same workload" % extra
     t = torch.tensor([ms_total], device=device, dtype=torch.float64)
     u = torch.tensor([float(units)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
     ms_total = float(t.item()); units_all = float(u.item())
+    # nvidia-smi cannot sample faster than ~100 ms: when the timed region is shorter than ~0.6 s, every rank keeps the
+    # same step running (untimed; the same count on every rank, derived from the agreed time, because a step holds a
+    # collective when N > 1) until the sampler has seen the GPU under this load
+    extra = 0
+    if ms_total < 600.0:
+        extra = int(min(2000, max(1, np.ceil((600.0 - ms_total) / max(ms_total / steps, 1e-3)))))
+        for j in range(extra):
+            step(warmup + steps + j)
+        barrier()
+    clk = None
+    if rank == 0:
+        clk = clocks.stop()
+        clk["sampled_over"] = "timed region" if extra == 0 else "timed region + %d more untimed steps of the same workload" % extra
     value = units_all / (ms_total * 1e-3)
     ld_scores = st.last_scores()[1]
 

@@ -72,9 +72,15 @@ def allreduce_deltas(st, device, comm=None, global_rows=0):
     if comm is not None:
         st.allreduce_deltas(comm, global_rows)
         return
+    import torch
     import torch.distributed as dist
     ptr32, n = st.delta_buffer_i32()
-    if ptr32:  # every suffstat is a count of rows: exact int32 deltas, half the bytes on the wire
+    # The int32 form is the library's LOCAL offer (every suffstat a count, local rows < 2^31); the sum runs over all
+    # ranks, so the GLOBAL row count has to fit as well, and every rank must make the same choice or the collective
+    # mismatches: the ranks agree on the minimum of their offers first.
+    use32 = torch.tensor([1 if (ptr32 and int(global_rows) < 2 ** 31) else 0], device=device, dtype=torch.int32)
+    dist.all_reduce(use32, op=dist.ReduceOp.MIN)
+    if int(use32.item()):  # exact int32 deltas, half the bytes on the wire
         t = as_tensor(ptr32, n, device, "<i4")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         st.delta_from_i32()

@@ -231,7 +231,10 @@ class state(object):
 
     def sweep(self, row_lo=0, row_hi=None, seed=0, sweep=0, uniforms=None, row_id_offset=0, defer_apply=False,
               wait=True):
-        """one batched reassignment pass; wait=False only enqueues it (sweep_wait() collects ``moved``)"""
+        """one batched (synchronous) reassignment pass: every row is scored against the same frozen suffstats -- its own
+        contribution included -- and all rows move at once.  Approximate by construction (see msb_state_sweep in
+        include/mscope_b200.h); the exact chain is remove_value / score_value / add_value per entity.
+        wait=False only enqueues it (sweep_wait() collects ``moved``)"""
         row_hi = self.nentities() if row_hi is None else row_hi
         opts = _lib.SweepOpts(int(seed), int(sweep), int(row_id_offset), None, 1 if defer_apply else 0,
                               0 if wait else _lib.SWEEP_ASYNC)

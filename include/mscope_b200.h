@@ -25,7 +25,7 @@
  *   msb_state_score_rows  the same K x D loop of base.hpp:27 for a whole row range
  *   msb_sample_discrete_log
  *                         common/util.hpp:125-156 (scores_to_probs + sample_discrete)
- *   msb_state_sweep       one batched Gibbs reassignment pass: remove/score/sample/add
+ *   msb_state_sweep       one batched (synchronous, approximate) reassignment pass: score/sample/update
  *                          against frozen suffstats
  *   msb_value_*           single-value group::score_value/add_value/remove_value/score_data/sample_value
  *                         (models/base.hpp:25-27), executed on the device
@@ -247,7 +247,13 @@ typedef struct msb_sweep_result {
 } msb_sweep_result;
 
 /* score rows [row_lo,row_hi) against the frozen suffstats, draw a group per row,
- * then apply remove_value(old)/add_value(new) for every row that moved. */
+ * then apply remove_value(old)/add_value(new) for every row that moved.
+ * This is a BATCHED (synchronous) pass, not the sequential kernel of entity_state.hpp:57-72: every row is scored
+ * against suffstats and CRP counts that still contain the row itself, and all rows move at once, so the row's current
+ * group is over-weighted (visibly for tiny groups) and the pass is an approximate Gibbs kernel -- it does not leave
+ * the posterior exactly invariant (tests/test_gpu_parity.py puts the deviation on record on an enumerated example).
+ * The exact chain is the per-entity sequence msb_state_remove_value -> msb_state_score_value -> draw ->
+ * msb_state_add_value, which the same test file holds to the enumerated posterior. */
 MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_hi, const msb_sweep_opts *opts,
                     msb_sweep_result *res);
 
