@@ -511,7 +511,7 @@ static inline int niw_tc16_init(size_t smem_optin, std::string &err) {
 static inline size_t niw_tc16_a_bytes(size_t nrows) { return ((nrows + niwtc16::TM - 1) / niwtc16::TM) * (size_t)(4 * niwtc16::A_HALF_BYTES); }
 static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, KernelProf *prof, const float *X, const float *W, const float *bias,
                                  const float *coef, float *Bop, unsigned char *A16, size_t ncols, float *scores, size_t ld,
-                                 size_t row_lo, size_t row_hi, int sm_count, const float *base, bool blocked, std::string &err) {
+                                 size_t row_lo, size_t row_hi, int sm_count, const float *base, bool blocked, bool a_valid, std::string &err) {
   using namespace niwtc16;
   const int nGB = (int)((ncols + GB - 1) / GB);
   unsigned int *colmax = reinterpret_cast<unsigned int *>(Bop);
@@ -523,18 +523,20 @@ static inline int niw_tc16_score(cudaStream_t stream, uint64_t *launches, Kernel
     err = std::string(what) + ": " + cudaGetErrorString(e);
     return MSB_ERR_CUDA;
   };
-  if (cudaMemsetAsync(colmax, 0, D * sizeof(unsigned int), stream) != cudaSuccess) return check("niw_tc16_score: cudaMemsetAsync");
   const size_t nrows = row_hi - row_lo;
   const long long nRT = (long long)((nrows + TM - 1) / TM);
-  const unsigned cm_grid = (unsigned)std::min<size_t>((nrows + 15) / 16, (size_t)sm_count * 8);
-  prof->begin("niw_colmax_kernel", stream);
-  niw_colmax_kernel<<<cm_grid, 256, 0, stream>>>(X, row_lo, row_hi, colmax);
-  prof->end(stream); (*launches)++;
-  if (int s = check("niw_colmax_kernel launch")) return s;
-  prof->begin("niw_convert_a16_kernel", stream);
-  niw_convert_a16_kernel<<<(unsigned)nRT, 256, 0, stream>>>(X, row_lo, row_hi, colmax, A16);
-  prof->end(stream); (*launches)++;
-  if (int s = check("niw_convert_a16_kernel launch")) return s;
+  if (!a_valid) {  // a_valid: A16 and colmax already hold exactly these rows of this column data (the caller's version check)
+    if (cudaMemsetAsync(colmax, 0, D * sizeof(unsigned int), stream) != cudaSuccess) return check("niw_tc16_score: cudaMemsetAsync");
+    const unsigned cm_grid = (unsigned)std::min<size_t>((nrows + 15) / 16, (size_t)sm_count * 8);
+    prof->begin("niw_colmax_kernel", stream);
+    niw_colmax_kernel<<<cm_grid, 256, 0, stream>>>(X, row_lo, row_hi, colmax);
+    prof->end(stream); (*launches)++;
+    if (int s = check("niw_colmax_kernel launch")) return s;
+    prof->begin("niw_convert_a16_kernel", stream);
+    niw_convert_a16_kernel<<<(unsigned)nRT, 256, 0, stream>>>(X, row_lo, row_hi, colmax, A16);
+    prof->end(stream); (*launches)++;
+    if (int s = check("niw_convert_a16_kernel launch")) return s;
+  }
   prof->begin("niw_pack_b16_kernel", stream);
   niw_pack_b16_kernel<<<nGB, 256, 0, stream>>>(W, bias, (int)ncols, colmax, Bblk, rinv);
   prof->end(stream); (*launches)++;

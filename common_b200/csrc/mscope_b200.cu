@@ -161,6 +161,11 @@ struct msb_state {
   unsigned long long *d_counter = nullptr;
   std::vector<float *> d_niwW, d_niwBias, d_niwCoef, d_niwB;
   void *d_niwA16 = nullptr; size_t niw_a16_cap = 0;  // fp16 A operand of the tensor-core NIW kernel (one feature at a time)
+  // what d_niwA16 (and the column maxima next to the feature's B operand) currently hold: feature, row range and the
+  // version of the column data they were converted from -- rows that did not change between sweeps (bind once, sweep
+  // many) are not scanned and converted again
+  uint64_t col_version = 1, niw_a16_version = 0;
+  size_t niw_a16_feat = 0, niw_a16_lo = 0, niw_a16_hi = 0;
   size_t niw_cols_cap = 0;
   // last score
   int tail_g = 0;  // replication width of the last k-tile's table columns (build_params), 0 = none
@@ -794,6 +799,7 @@ static int ingest(msb_state *st, bool size_tables) {
   msb_ctx *ctx = st->ctx;
   msb_dataview *dv = st->dv;
   const size_t D = st->D;
+  st->col_version++;   // the column data changes: anything derived from it (the fp16 NIW operand) is stale
   MSB_TRY(sync_small(st));
   CU_TRY(dv_acquire(dv));
   // refresh path: one fused pass over the records staged in shared memory (they are read from HBM once)
@@ -993,6 +999,7 @@ extern "C" MSB_API int msb_state_refresh(msb_state *st) {
   CU_TRY(cudaEventSynchronize(st->ev_prefetched));                  // its flags are on the host now
   CU_TRY(cudaStreamWaitEvent(ctx->stream, st->ev_prefetched, 0));   // kernels enqueued from here on see the new columns
   st->prefetch_pending = false;
+  st->col_version++;
   std::swap(st->col_slab, st->col_slab_b);
   std::swap(st->feats, st->feats_b);
   std::swap(st->cols, st->cols_b);
@@ -1418,6 +1425,7 @@ static int build_params(msb_state *st) {
         CU_TRY(cudaMalloc(&st->d_niwBias[d], sizeof(float) * cap * f.dim));
         CU_TRY(cudaMalloc(&st->d_niwCoef[d], sizeof(float) * cap * 4));
         CU_TRY(cudaMalloc(&st->d_niwB[d], niw_tc_operand_bytes(cap, f.dim)));
+        st->niw_a16_version = 0;   // the column maxima lived in the old buffer
       }
       const size_t smem = (2 * (size_t)f.dim * f.dim + f.dim) * sizeof(double);
       LAUNCH(ctx, niw_prepare_kernel, (unsigned)K, 128, smem, f, st->d_hp, st->d_ss, st->d_col2slot, st->d_niwW[d],
@@ -1599,13 +1607,16 @@ scalar_done:
     if (tc_ok && !getenv("MSB_NIW_TF32") && row_hi > row_lo) {  // fp16 operands (msb_niw_tc16.cuh): the default
       const size_t a_bytes = niw_tc16_a_bytes(row_hi - row_lo);   // the rows of this call, converted once per sweep
       if (st->niw_a16_cap < a_bytes) {
-        cudaFree(st->d_niwA16); st->d_niwA16 = nullptr; st->niw_a16_cap = 0;
+        CU_TRY(cudaFree(st->d_niwA16)); st->d_niwA16 = nullptr; st->niw_a16_cap = 0; st->niw_a16_version = 0;
         CU_TRY(cudaMalloc(&st->d_niwA16, a_bytes));
         st->niw_a16_cap = a_bytes;
       }
+      const bool a_valid = st->niw_a16_version == st->col_version && st->niw_a16_feat == d && st->niw_a16_lo == row_lo &&
+                           st->niw_a16_hi == row_hi && !getenv("MSB_NIW_NO_A_CACHE");
       MSB_TRY(niw_tc16_score(ctx->stream, &ctx->launches, &ctx->prof, (const float *)f.scol, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
                              st->d_niwB[d], (unsigned char *)st->d_niwA16, K, scores, st->ld, row_lo, row_hi, ctx->sm_count,
-                             need_init ? st->d_base : nullptr, blocked, g_last_error));
+                             need_init ? st->d_base : nullptr, blocked, a_valid, g_last_error));
+      st->niw_a16_version = st->col_version; st->niw_a16_feat = d; st->niw_a16_lo = row_lo; st->niw_a16_hi = row_hi;
       done = true;
     } else
     MSB_TRY(niw_tc_score(ctx->stream, &ctx->launches, (const float *)f.scol, f.dim, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
