@@ -482,10 +482,6 @@ def run_config(ctx, device, stream, comm, workload, args, rank, local_rank, worl
             roof["binding_resource"] = "shared-memory wavefronts (LSU data pipe, 1 per SM per clock)"
             roof["binding_wavefronts_per_launch"] = wf
             roof["binding_frac"] = wf / (score_ms * 1e-3 * clk["sm_mhz"] * 1e6 * sm_count)
-        if tr:
-            for kk in ("fma_pipe_pct", "xu_pipe_pct", "lsu_pipe_pct", "tensor_pipe_pct", "issue_active_pct"):
-                if kk in tr:
-                    roof["ncu_" + kk] = tr[kk]
         if has_niw:
             dims = [d()._param() for d in descs if d().name() == "niw"]
             flops = sum(2.0 * dd_ * dd_ * n * k for dd_ in dims)   # whitened-GEMM form, SURVEY.md section 8(d)
@@ -496,6 +492,10 @@ def run_config(ctx, device, stream, comm, workload, args, rank, local_rank, worl
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; fp16 runs at the bf16 rate)" if peaks.get("bf16_tflops") else "nominal 2250 TFLOP/s",
                     "traffic_source": (tr or {}).get("capture") if traffic else None,
                     "note": "3 fp16 products per algorithmic product (hi*hi + hi*lo + lo*hi, scaled operands) for fp32-class accuracy, less the structurally zero triangle of W_k: tensor-pipe work = 1.875 x the algorithmic FLOPs"}
+        if tr:   # the pipes ncu saw busy in the committed full-size capture of this kernel (profiles/traffic.json)
+            for kk in ("fma_pipe_pct", "xu_pipe_pct", "lsu_pipe_pct", "tensor_pipe_pct", "issue_active_pct"):
+                if kk in tr:
+                    roof["ncu_" + kk] = tr[kk]
         rec["roofline"] = roof
 
         # ---- the bandwidth-bound kernels, each against the HBM roof (one extra untimed step with an event pair per launch)

@@ -64,6 +64,13 @@ struct FeatS {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// floats as integers that order the same way (an involution: applying it twice gives the float's bits back)
+__device__ __forceinline__ int float_ordered(float f) {
+  const int i = __float_as_int(f);
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -829,7 +836,8 @@ __global__ void __launch_bounds__(NW * 32, 1)
 score_bundle_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *__restrict__ params, size_t region_rows,
                     uint32_t stage_bytes, int S, const float *__restrict__ base, float *__restrict__ scores, size_t ld,
                     size_t row_org, size_t row_lo, size_t row_hi, const double *__restrict__ hp,
-                    const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols, int ktiles) {
+                    const double *__restrict__ ss, const int32_t *__restrict__ col2slot, int ncols, int ktiles,
+                    int *__restrict__ rowmax) {
   constexpr int KT = 32 * V;
   constexpr int RL = (RW + 31) / 32;                            // slow-mask words per warp (RW = 16: half a word)
   constexpr int RB = NW * RW;                                   // rows per block
@@ -1208,8 +1216,14 @@ score_bundle_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *_
       if (prow0 < row_hi) {
         float *dst = scores + (((prow0 - row_org) / 32) * ld + (size_t)kt * KT) * 32 + lane;
         const int c0 = (warp & 1) * (KT / 2);
+        float mx = -CUDART_INF_F;
 #pragma unroll 8
-        for (int c = c0; c < c0 + KT / 2; c++) dst[(size_t)c * 32] = tile[lane * (KT + 1) + c];
+        for (int c = c0; c < c0 + KT / 2; c++) {
+          const float v = tile[lane * (KT + 1) + c];
+          dst[(size_t)c * 32] = v;
+          if (kt * KT + c < ncols) mx = fmaxf(mx, v);
+        }
+        if (rowmax) atomicMax(rowmax + (prow0 - row_org) + lane, float_ordered(mx));
       }
       return;
     }
@@ -1225,8 +1239,16 @@ score_bundle_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *_
       const size_t rb = (row0 - row_org) / 32 + j;
       if (row0 + (size_t)j * 32 < row_hi) {
         float *dst = scores + (rb * ld + (size_t)kt * KT) * 32 + lane;
+        // the row's largest score over this k-tile's real groups goes to the sampler (atomic max over the k-tiles of
+        // the row, floats ordered as integers): its first pass over the score matrix -- the maximum -- is then not needed
+        float mx = -CUDART_INF_F;
 #pragma unroll 8
-        for (int c = 0; c < KT; c++) dst[(size_t)c * 32] = tile[lane * (KT + 1) + c];
+        for (int c = 0; c < KT; c++) {
+          const float v = tile[lane * (KT + 1) + c];
+          dst[(size_t)c * 32] = v;
+          if (kt * KT + c < ncols) mx = fmaxf(mx, v);
+        }
+        if (rowmax) atomicMax(rowmax + rb * 32 + lane, float_ordered(mx));
       }
     }
   }

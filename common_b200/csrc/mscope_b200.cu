@@ -164,6 +164,8 @@ struct msb_state {
   // what d_niwA16 (and the column maxima next to the feature's B operand) currently hold: feature, row range and the
   // version of the column data they were converted from -- rows that did not change between sweeps (bind once, sweep
   // many) are not scanned and converted again
+  int *d_rowmax = nullptr; size_t rowmax_cap = 0;   // per-row score maximum from the bundled score kernel's epilogue (sweep only)
+  bool rowmax_valid = false;                        // the last launch_score filled it
   uint64_t col_version = 1, niw_a16_version = 0;
   size_t niw_a16_feat = 0, niw_a16_lo = 0, niw_a16_hi = 0;
   size_t niw_cols_cap = 0;
@@ -662,6 +664,7 @@ extern "C" MSB_API int msb_state_destroy(msb_state *st) {
   cudaFree(st->col_slab);
   for (size_t d = 0; d < st->D; d++) { cudaFree(st->d_niwW[d]); cudaFree(st->d_niwBias[d]); cudaFree(st->d_niwCoef[d]); cudaFree(st->d_niwB[d]); }
   cudaFree(st->d_niwA16);
+  cudaFree(st->d_rowmax);
   cudaFree(st->d_feats); cudaFree(st->d_feats_scalar); cudaFree(st->d_hp); cudaFree(st->d_ss); cudaFree(st->d_delta); cudaFree(st->d_delta_i32); cudaFree(st->d_counter);
   cudaFree(st->d_slot2gid); cudaFree(st->d_assign64); cudaFree(st->d_flags); cudaFreeHost(st->h_moved); cudaFreeHost(st->h_flags); cudaFree(st->d_assign); cudaFree(st->d_params); cudaFree(st->d_scores);
   cudaFree(st->d_base); cudaFree(st->d_base_score); cudaFree(st->d_col2slot); cudaFree(st->d_newslot); cudaFree(st->d_newcol); cudaFree(st->d_uniforms);
@@ -1458,8 +1461,9 @@ static int launch_dm(msb_ctx *ctx, const FeatDev &f, const double *d_hp, const d
   return MSB_OK;
 }
 
-static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scores, bool blocked = false) {
+static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scores, bool blocked = false, bool want_rowmax = false) {
   msb_ctx *ctx = st->ctx;
+  st->rowmax_valid = false;
   const size_t org = row_origin(row_lo);
   const size_t nrows = row_hi - org;
   const size_t K = st->h_col2slot.size();
@@ -1530,8 +1534,21 @@ static int launch_score(msb_state *st, size_t row_lo, size_t row_hi, float *scor
           if (blocked) LAUNCH(ctx, (score_bundle_kernel<V_, RW_, NW_, true>), (unsigned)grid, NW_ * 32, smem_b, MSB_BUNDLE_ARGS); \
           else LAUNCH(ctx, (score_bundle_kernel<V_, RW_, NW_, false>), (unsigned)grid, NW_ * 32, smem_b, MSB_BUNDLE_ARGS);        \
         } while (0)
+        // the sweep's sampler takes the row maxima from this kernel's epilogue when nothing is added to the matrix afterwards
+        int *rowmax = nullptr;
+        if (want_rowmax && blocked && !st->has_niw && !st->has_dm && !getenv("MSB_NO_ROWMAX")) {
+          const size_t need = nrows + 128;
+          if (st->rowmax_cap < need) {
+            CU_TRY(cudaFree(st->d_rowmax)); st->d_rowmax = nullptr; st->rowmax_cap = 0;
+            CU_TRY(cudaMalloc(&st->d_rowmax, need * sizeof(int)));
+            st->rowmax_cap = need;
+          }
+          CU_TRY(cudaMemsetAsync(st->d_rowmax, 0x80, need * sizeof(int), ctx->stream));   // below every finite float in the ordered encoding
+          rowmax = st->d_rowmax;
+          st->rowmax_valid = true;
+        }
 #define MSB_BUNDLE_ARGS st->d_feats_scalar, (int)st->n_scalar, st->d_params, st->region_rows, (uint32_t)stage_b, Sb, st->d_base_score, \
-                        scores, st->ld, org, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K, (int)ktiles
+                        scores, st->ld, org, row_lo, row_hi, st->d_hp, st->d_ss, st->d_col2slot, (int)K, (int)ktiles, rowmax
         if (st->cfg == 1) MSB_BUNDLE_LAUNCH(2, 32, 16);
         else if (st->cfg == 4) MSB_BUNDLE_LAUNCH(4, 16, 16);
         else MSB_BUNDLE_LAUNCH(4, 32, 8);
@@ -2321,7 +2338,7 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
     PhaseEvents &pe = ev[c + 1];
     CU_TRY(cudaEventRecord(pe.e[0], ctx->stream));
     const size_t skip = lo - row_origin(lo);
-    MSB_TRY(launch_score(st, lo, hi, st->d_scores, blocked));
+    MSB_TRY(launch_score(st, lo, hi, st->d_scores, blocked, true));
     st->last_skip = skip;
     CU_TRY(cudaEventRecord(pe.e[1], ctx->stream));
     const float *d_u = nullptr;
@@ -2348,7 +2365,8 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
                d_u, opts->seed, opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
     } else if (blocked)
       LAUNCH(ctx, sample_blocked_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores, st->ld, skip, (int)K, hi - lo, d_u, opts->seed,
-             opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
+             opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot,
+             (const int *)(st->rowmax_valid ? st->d_rowmax : nullptr));
     else
       LAUNCH(ctx, sample_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores + skip * st->ld, st->ld, (int)K, hi - lo, d_u, opts->seed,
              opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);

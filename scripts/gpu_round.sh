@@ -25,5 +25,14 @@ for leg in "$@"; do
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$kre --launch-skip ${skip:-3} --launch-count 1 \
         -f -o gpurun_out/${tag}_${wl}_${kre%%_kernel*} $cmd > gpurun_out/${tag}_ncu_f_$wl.log 2>&1
       echo "full $wl $kre rc=$?";;
+    fullsum:*)   # as full:, but only the digest travels back (a round of .ncu-rep files overflows gpurun_out's 64 MiB)
+      IFS=: read -r _ wl rows kre skip <<< "$leg"
+      cmd="python bench.py --workload $wl --configs none --rows $rows --steps 1 --warmup 3 --no-cpu --no-e2e --no-parity"
+      rep=/tmp/${tag}_${wl}_${kre%%_kernel*}
+      timeout 600 $cmd > gpurun_out/${tag}_f_$wl.json 2>&1 &&
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$kre --launch-skip ${skip:-3} --launch-count 1 \
+        -f -o $rep $cmd > gpurun_out/${tag}_ncu_f_$wl.log 2>&1 &&
+      python scripts/ncu_summary.py $rep.ncu-rep sm__pipe_tensor_cycles_active.avg l1tex__data_pipe_lsu_wavefronts_mem_shared.sum l1tex__data_pipe_tc_wavefronts > gpurun_out/${tag}_prof_${wl}_full.txt 2>&1
+      echo "fullsum $wl $kre rc=$?"; rm -f $rep.ncu-rep;;
   esac
 done
