@@ -448,7 +448,11 @@ def run_config(ctx, device, stream, comm, workload, args, rank, local_rank, worl
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(uu, op=dist.ReduceOp.SUM)
-        rec["e2e"] = {"value": float(uu.item()) / float(tt.item()), "unit": UNIT,
+        e2e_phase = {}
+        for back in range(min(esteps, 16)):     # device phase times of the end-to-end passes themselves (the library's event ring)
+            for kk, v in s2.last_timings(back).items():
+                e2e_phase[kk] = e2e_phase.get(kk, 0.0) + v / min(esteps, 16)
+        rec["e2e"] = {"value": float(uu.item()) / float(tt.item()), "unit": UNIT, "device_phase_ms_per_pass": e2e_phase,
                       "h2d_bytes_per_step": int(raw.nbytes), "d2h_bytes_per_step": int(n * 8),
                       "ms_per_step": float(tt.item()) * 1e3 / esteps, "steps": esteps,
                       "what": "per pass: one H2D of the host AoS records (pinned) + AoS->SoA conversion, both for the NEXT pass on a copy stream under this pass's sweep (double-buffered columns) -> sweep (score, draw, suffstat update"

@@ -1346,6 +1346,19 @@ __global__ void nich_c0_sum_kernel(const FeatDev *__restrict__ feats, int nfeat,
 }
 
 // scores[r][c] = base[c]: the CRP term, when no scalar feature kernel initialises the matrix
+// Small copies that stay OFF the copy engines: a cudaMemcpyAsync -- device to device included -- queues on a DMA engine
+// behind whatever that engine is moving, and on a pass over host rows that is the next pass's 32 MB of records: with
+// eight GPUs uploading at once the sweep's "build" phase waited 0.3 ms for a 1 KB copy (bench.py, device_phase_ms_per_pass).
+__global__ void copy_f32_kernel(const float *__restrict__ src, float *__restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+__global__ void zero_u64_kernel(unsigned long long *p) { *p = 0ull; }
+// the moved-row counter straight into (mapped, pinned) host memory
+__global__ void publish_counter_kernel(const unsigned long long *__restrict__ d, unsigned long long *__restrict__ h) {
+  *h = *d;
+  __threadfence_system();
+}
 __global__ void fill_rows_kernel(float *__restrict__ scores, size_t ld, const float *__restrict__ base, size_t nrows) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nrows * ld) scores[i] = base[i % ld];

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <map>
 #include <set>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -55,6 +56,11 @@ struct msb_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;  // host -> device record uploads run here, overlapping the kernels on `stream`
+  // device -> host result copies (msb_state_assignments_async) have a stream of their own: behind the uploads on the copy
+  // stream, the NEXT pass's records -- issued right after -- queued behind a copy that waits for the CURRENT sweep to end,
+  // which took a whole sweep of look-ahead away from the upload (8 GPUs streaming at once: 3.0 ms per C2 pass for a
+  // 2.1 ms step, although the box sustains 24-36 GB/s per GPU with all eight copying, scripts/h2d_contention.py)
+  cudaStream_t d2h_stream = nullptr;
   uint64_t launches = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
@@ -114,7 +120,8 @@ struct msb_state {
   std::vector<double> h_counts;
   bool counts_stale = false;      // the device counts (d_ss[0..kmax)) are newer than h_counts
   bool cols_dirty = true;         // groups were created / deleted since the column tables were uploaded
-  unsigned long long *h_moved = nullptr;  // pinned: the moved-row counter of the last sweep lands here
+  unsigned long long *h_moved = nullptr;  // pinned + mapped: the moved-row counter of the last sweep lands here
+  unsigned long long *h_moved_dev = nullptr;  // its device address (publish_counter_kernel writes it: no copy engine)
   uint32_t *h_flags = nullptr;    // pinned scratch for the bind-time device -> host flags
   uint32_t *d_flags = nullptr;
   int64_t *d_assign64 = nullptr; size_t assign64_cap = 0;
@@ -164,6 +171,7 @@ struct msb_state {
   // what d_niwA16 (and the column maxima next to the feature's B operand) currently hold: feature, row range and the
   // version of the column data they were converted from -- rows that did not change between sweeps (bind once, sweep
   // many) are not scanned and converted again
+  std::map<std::string, double> pass_host_ns;       // MSB_PASS_TIMING: host nanoseconds per sub-step of msb_state_pass
   int *d_rowmax = nullptr; size_t rowmax_cap = 0;   // per-row score maximum from the bundled score kernel's epilogue (sweep only)
   bool rowmax_valid = false;                        // the last launch_score filled it
   uint64_t col_version = 1, niw_a16_version = 0;
@@ -230,9 +238,16 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
+  // The sweep's stream outranks the copy streams: the conversion kernel of the NEXT pass's records (copy stream) becomes
+  // runnable at the very moment a sweep starts, and at equal priority its blocks were placed first -- the sweep's
+  // parameter build and score kernel then waited for them (8 GPUs, C2 passes over host rows: build phase 0.36 instead of
+  // 0.03 ms, score 1.50 instead of 1.38 ms).  With priorities the conversion fills what the sweep's kernels leave free.
+  int prio_least = 0, prio_greatest = 0;
+  CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
   if (stream) c->stream = (cudaStream_t)stream;
-  else { CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-  CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  else { CU_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest)); c->own_stream = true; }
+  CU_TRY(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_least));
+  CU_TRY(cudaStreamCreateWithPriority(&c->d2h_stream, cudaStreamNonBlocking, prio_least));
   CU_TRY(opt_in_smem(score_kernel<1, 64, 16, false, false>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<2, 32, 16, false, false>, c->smem_optin));
   CU_TRY(opt_in_smem(score_kernel<4, 32, 8, false, false>, c->smem_optin));
@@ -280,7 +295,9 @@ extern "C" MSB_API int msb_ctx_destroy(msb_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
+  cudaStreamSynchronize(ctx->d2h_stream);
   cudaStreamDestroy(ctx->copy_stream);
+  cudaStreamDestroy(ctx->d2h_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   ctx->prof.destroy();
   delete ctx;
@@ -290,6 +307,7 @@ extern "C" MSB_API int msb_ctx_synchronize(msb_ctx *ctx) {
   REQUIRE(ctx, "ctx is NULL");
   CU_TRY(cudaStreamSynchronize(ctx->copy_stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->d2h_stream));
   return MSB_OK;
 }
 extern "C" MSB_API void *msb_ctx_stream(msb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -640,8 +658,9 @@ extern "C" MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *mode
   CU_TRY(cudaMalloc(&st->d_slot2gid, sizeof(int64_t) * max_groups));
   CU_TRY(cudaMalloc(&st->d_flags, sizeof(uint32_t) * 2 * nfeatures));
   CU_TRY(cudaHostAlloc(&st->h_flags, sizeof(uint32_t) * 2 * nfeatures, cudaHostAllocDefault));
-  CU_TRY(cudaHostAlloc(&st->h_moved, sizeof(unsigned long long), cudaHostAllocDefault));
+  CU_TRY(cudaHostAlloc(&st->h_moved, sizeof(unsigned long long), cudaHostAllocMapped));
   *st->h_moved = 0;
+  CU_TRY(cudaHostGetDevicePointer((void **)&st->h_moved_dev, st->h_moved, 0));
   st->slot2gid.assign(max_groups, -1);
   st->h_counts.assign(max_groups, 0.0);
   st->slot_dirty.assign(max_groups, 0);
@@ -658,6 +677,12 @@ extern "C" MSB_API int msb_state_destroy(msb_state *st) {
   cudaSetDevice(st->ctx->device);
   cudaStreamSynchronize(st->ctx->copy_stream);
   cudaStreamSynchronize(st->ctx->stream);
+  cudaStreamSynchronize(st->ctx->d2h_stream);
+  if (!st->pass_host_ns.empty()) {
+    std::string line = "msb_state_pass host ms:";
+    for (auto &p : st->pass_host_ns) line += " " + p.first + "=" + std::to_string(p.second * 1e-6);
+    fprintf(stderr, "%s\n", line.c_str());
+  }
   if (st->ev_mapped) { cudaEventDestroy(st->ev_mapped); cudaEventDestroy(st->ev_assign_copied); }
   if (st->ev_swap) { cudaEventDestroy(st->ev_swap); cudaEventDestroy(st->ev_prefetched); }
   cudaFree(st->col_slab_b); cudaFree(st->d_feats_b); cudaFree(st->d_feats_scalar_b); cudaFree(st->d_flags_b); cudaFreeHost(st->h_flags_b);
@@ -1406,7 +1431,7 @@ static int build_params(msb_state *st) {
     LAUNCH(ctx, build_params_kernel, grid, 256, 0, st->d_feats, (int)st->D, st->d_hp, st->d_ss, st->d_col2slot, (int)K,
            (int)KT, st->region_rows, st->d_params, st->tail_g);
     MSB_TRY(ensure(&st->d_base_score, &st->base_score_cap, st->ld));
-    CU_TRY(cudaMemcpyAsync(st->d_base_score, st->d_base, sizeof(float) * st->ld, cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(ctx, copy_f32_kernel, cdiv(st->ld, 256), 256, 0, (const float *)st->d_base, st->d_base_score, st->ld);
     if (st->has_nich) {  // fold sum_d c0 of the nich features into the score kernel's base[]
       LAUNCH(ctx, nich_c0_sum_kernel, cdiv(st->ld, 128), 128, 0, st->d_feats, (int)st->D, st->d_params, st->region_rows,
              (int)KT, (int)st->ld, st->d_base_score);
@@ -1790,9 +1815,9 @@ extern "C" MSB_API int msb_state_assignments_async(msb_state *st, int64_t *out, 
   }
   LAUNCH(ctx, map_i32_to_i64_kernel, cdiv(n, 256), 256, 0, st->d_assign, st->d_slot2gid, n, st->d_assign64);
   CU_TRY(cudaEventRecord(st->ev_mapped, ctx->stream));
-  CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, st->ev_mapped, 0));
-  CU_TRY(cudaMemcpyAsync(out, st->d_assign64, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->copy_stream));
-  CU_TRY(cudaEventRecord(st->ev_assign_copied, ctx->copy_stream));
+  CU_TRY(cudaStreamWaitEvent(ctx->d2h_stream, st->ev_mapped, 0));
+  CU_TRY(cudaMemcpyAsync(out, st->d_assign64, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  CU_TRY(cudaEventRecord(st->ev_assign_copied, ctx->d2h_stream));
   st->assign_copy_pending = true;
   return MSB_OK;
 }
@@ -2329,7 +2354,7 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
   for (const auto &f : st->feats) if (f.kind == KIND_NIW && (f.dim != 64 || getenv("MSB_NO_TENSOR"))) niw_tc_only = false;
   if (st->has_dm) niw_tc_only = false;  // dm_score_kernel accumulates row-major
   const bool blocked = niw_tc_only && !getenv("MSB_NO_BLOCKED");
-  CU_TRY(cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned long long), ctx->stream));
+  LAUNCH(ctx, zero_u64_kernel, 1, 1, 0, st->d_counter);
   CU_TRY(cudaEventRecord(ev[0].e[0], ctx->stream));
   MSB_TRY(build_params(st));
   CU_TRY(cudaEventRecord(ev[0].e[1], ctx->stream));
@@ -2379,7 +2404,7 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
   CU_TRY(cudaEventRecord(ev[0].e[2], ctx->stream));
   if (!opts->defer_apply) MSB_TRY(launch_apply(st));
   CU_TRY(cudaEventRecord(ev[0].e[3], ctx->stream));
-  CU_TRY(cudaMemcpyAsync(st->h_moved, st->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  LAUNCH(ctx, publish_counter_kernel, 1, 1, 0, (const unsigned long long *)st->d_counter, st->h_moved_dev);
   MSB_TRY(refresh_counts(st));  // marks the host copy of the group counts stale; no synchronisation
   st->last_res.rows = nrows; st->last_res.units = (uint64_t)nrows * K * st->D; st->last_res.moved = 0;
   if (opts->flags & MSB_SWEEP_ASYNC) {  // everything is enqueued; msb_state_sweep_wait collects the result
@@ -2410,9 +2435,12 @@ extern "C" MSB_API int msb_state_pass(msb_state *st, const msb_pass_opts *opts, 
   REQUIRE(st && opts, "NULL argument");
   REQUIRE(st->dv, "no dataview bound");
   static const bool dbg = getenv("MSB_DEBUG_SYNC") != nullptr;  // diagnostics: wait for the device after every sub-step
+  static const bool timing = getenv("MSB_PASS_TIMING") != nullptr;  // diagnostics: host time per sub-step, printed at destroy
 #define MSB_PASS_STEP(what, expr)                                                                        \
   do {                                                                                                   \
+    const auto t0_ = std::chrono::steady_clock::now();                                                   \
     MSB_TRY(expr);                                                                                       \
+    if (timing) st->pass_host_ns[what] += (double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0_).count(); \
     if (dbg) {                                                                                           \
       const cudaError_t e_ = cudaDeviceSynchronize();                                                    \
       if (e_ != cudaSuccess) return fail(MSB_ERR_CUDA, std::string("msb_state_pass, after ") + what + ": " + cudaGetErrorString(e_)); \
