@@ -335,6 +335,8 @@ class state(object):
     _SS_KEYS = {"dm": ("counts", "ratio"), "bbnc": ("p", "heads", "tails"), "bb": ("heads", "tails"), "bnb": ("count", "sum"), "gp": ("count", "sum", "log_prod"),
                 "nich": ("count", "mean", "count_times_variance"), "dd": ("counts",), "niw": ("count", "sum_x", "sum_xxT")}
 
+    _WIRE_FLOAT_KEYS = ("p", "ratio", "log_prod", "mean", "count_times_variance", "sum_x", "sum_xxT")   # float32 on the wire
+
     def _ss_counts(self, m, key):
         p = m._param() or 0
         return {"counts": p, "sum_x": p, "sum_xxT": p * p}.get(key, 1)
@@ -405,11 +407,30 @@ class state(object):
             _lib.check(_lib.load().msb_state_restore_group(st._h, int(g["id"])))
         a = np.asarray(gm["assignments"], np.int64)
         assert a.size == st.nentities(), "the checkpoint holds another number of entities"
-        st.add_values(a)        # membership (and the suffstats the data implies) ...
-        for g in gm["groups"]:  # ... then the suffstats exactly as they were saved
+        st.add_values(a)        # membership, and the suffstats the data implies in full fp64 ...
+        # ... then the saved ones -- but only where they say something else.  The wire carries its real-valued fields as
+        # float32 (nich mean / count_times_variance, niw sum_x / sum_xxT, gp log_prod, dm ratio, bbnc p): overwriting an
+        # fp64 statistic with its own float32 rounding would leave every later remove_value subtracting exact row values
+        # from rounded sums (residuals in emptied groups, a resumed chain 1e-7 away from the uninterrupted one).  A field
+        # whose data-implied value rounds to what was saved is therefore kept as rebuilt; a real difference (the caller
+        # saved something the data does not imply) is restored as saved.
+        for g in gm["groups"]:
+            gid = int(g["id"])
             bags = wire.decode("MixtureModelGroup", g["data"])["suffstats"]
             for d, bag in enumerate(bags):
-                st.set_suffstats_bag(d, int(g["id"]), bag)
+                m = st._models[d]
+                name = m.name()
+                saved = wire.decode(name + ".Group", bag)
+                for key in cls._SS_KEYS[name]:
+                    cnt = st._ss_counts(m, key)
+                    cur = np.asarray(st.get_suffstats(d, gid, key, cnt), np.float64).ravel()
+                    want = np.atleast_1d(np.asarray(saved[key], np.float64)).ravel()
+                    if key in cls._WIRE_FLOAT_KEYS:
+                        same = cur.size == want.size and np.array_equal(cur.astype(np.float32), want.astype(np.float32))
+                    else:
+                        same = cur.size == want.size and np.array_equal(cur, want)
+                    if not same:
+                        st.set_suffstats(d, gid, key, saved[key])
         return st
 
     def close(self):

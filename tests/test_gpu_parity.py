@@ -758,6 +758,12 @@ def test_checkpoint_round_trip_through_the_wire_format(ctx, oracle):
     _, S = st.score_rows()
     _, S2 = st2.score_rows()
     check(S2, S, 1e-6)      # float32 fields on the wire
+    # ... but the restored state keeps the fp64 statistics its data implies wherever they round to the saved float32
+    # values: resume is exact to fp64 summation order, not to wire precision
+    for g in st.groups():
+        for key in ("mean", "count_times_variance"):
+            a, b = st.get_suffstats(3, g, key, 1)[0], st2.get_suffstats(3, g, key, 1)[0]
+            assert abs(a - b) <= 1e-12 * max(1.0, abs(a)), (g, key, a, b)
     assert st2.suffstats_identifiers(0) == st2.groups()
     # one group's bag moved by hand (entity_state.hpp:53-54): get_suffstats -> set_suffstats
     src, dst = st.groups()[0], st.groups()[1]
