@@ -76,6 +76,9 @@ _PROTOS = {
     "msb_dataview_nfeatures": (C.c_int, [_P, C.POINTER(_SZ)]),
     "msb_dataview_rowsize": (C.c_int, [_P, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "msb_dataview_get_row": (C.c_int, [_P, _SZ, _P, _P]),
+    "msb_dataview_permute": (C.c_int, [_P, C.c_uint64]),
+    "msb_dataview_reset_permutation": (C.c_int, [_P]),
+    "msb_dataview_permutation": (C.c_int, [_P, C.POINTER(C.c_uint64), _SZ]),
     "msb_state_create": (C.c_int, [_P, C.POINTER(ModelDesc), _SZ, _SZ, C.POINTER(_P)]),
     "msb_state_destroy": (C.c_int, [_P]),
     "msb_state_bind": (C.c_int, [_P, _P]),

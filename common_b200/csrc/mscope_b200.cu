@@ -72,6 +72,7 @@ struct msb_dataview {
   size_t n = 0, D = 0, rowsize = 0, maskrowsize = 0;
   std::vector<msb_runtime_type> types;
   std::vector<size_t> off, moff;
+  std::vector<uint64_t> pi;   // iteration order set by msb_dataview_permute (empty: storage order)
   uint8_t *d_data = nullptr, *d_mask = nullptr;
   bool owns = false;
   // ordering between the copy stream (msb_dataview_upload) and the compute stream (kernels that read the records)
@@ -447,6 +448,7 @@ extern "C" MSB_API int msb_dataview_rowsize(const msb_dataview *dv, size_t *rows
 extern "C" MSB_API int msb_dataview_get_row(msb_dataview *dv, size_t idx, void *row_out, void *mask_out) {
   REQUIRE(dv && row_out, "NULL argument");
   REQUIRE(idx < dv->n, "invalid position");  // dataview.cpp:131
+  if (!dv->pi.empty()) idx = (size_t)dv->pi[idx];   // dataview.cpp:127-139: get() reads record pi_[pos_]
   CU_TRY(cudaSetDevice(dv->ctx->device));
   CU_TRY(dv_acquire(dv));
   CU_TRY(cudaMemcpyAsync(row_out, dv->d_data + idx * dv->rowsize, dv->rowsize, cudaMemcpyDeviceToHost, dv->ctx->stream));
@@ -455,6 +457,33 @@ extern "C" MSB_API int msb_dataview_get_row(msb_dataview *dv, size_t idx, void *
     else memset(mask_out, 0, dv->maskrowsize);
   }
   CU_TRY(cudaStreamSynchronize(dv->ctx->stream));
+  return MSB_OK;
+}
+
+extern "C" MSB_API int msb_dataview_permute(msb_dataview *dv, uint64_t seed) {
+  REQUIRE(dv, "NULL argument");
+  // util.hpp:85-94 (Fisher-Yates from the back: swap position i with a uniform position in [0, i]); the draw for
+  // position i is word pair 0-1 of Philox(seed, i, 0), reduced by a multiply-high (bias below 2^-32 for n < 2^32)
+  dv->pi.resize(dv->n);
+  for (size_t i = 0; i < dv->n; i++) dv->pi[i] = i;
+  for (size_t i = dv->n; i-- > 1;) {
+    uint32_t r[4];
+    msb::philox4x32_10(seed, (uint64_t)i, 0, r);
+    const uint64_t r64 = ((uint64_t)r[1] << 32) | r[0];
+    const size_t j = (size_t)(((unsigned __int128)r64 * (unsigned __int128)(i + 1)) >> 64);
+    std::swap(dv->pi[i], dv->pi[j]);
+  }
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_dataview_reset_permutation(msb_dataview *dv) {
+  REQUIRE(dv, "NULL argument");
+  dv->pi.clear();
+  return MSB_OK;
+}
+extern "C" MSB_API int msb_dataview_permutation(const msb_dataview *dv, uint64_t *pi_out, size_t n) {
+  REQUIRE(dv && (pi_out || n == 0), "NULL argument");
+  REQUIRE(n == dv->n, "wrong length");
+  for (size_t i = 0; i < n; i++) pi_out[i] = dv->pi.empty() ? (uint64_t)i : dv->pi[i];
   return MSB_OK;
 }
 

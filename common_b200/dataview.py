@@ -170,6 +170,21 @@ class device_dataview(object):
         mptr = mask.ctypes.data if hasattr(mask, "ctypes") else mask
         _lib.check(_lib.load().msb_dataview_upload(self._h, dptr, mptr))
 
+    def permute(self, seed):
+        """row_major_dataview::permute (dataview.cpp:141-145): a Fisher-Yates iteration order from the Philox stream;
+        get_row_bytes(i) then returns record pi[i] until reset_permutation()"""
+        _lib.check(_lib.load().msb_dataview_permute(self._h, int(seed)))
+
+    def reset_permutation(self):
+        _lib.check(_lib.load().msb_dataview_reset_permutation(self._h))
+
+    def permutation(self):
+        """pi as an array (the identity when no permutation is set)"""
+        n = self.size() if hasattr(self, "size") else self._n
+        out = np.zeros(n, np.uint64)
+        _lib.check(_lib.load().msb_dataview_permutation(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), n))
+        return out
+
     def get_row_bytes(self, idx):
         rs, ms = self.rowsize()
         row = np.zeros(rs, np.uint8)

@@ -141,6 +141,14 @@ MSB_API int msb_dataview_nfeatures(const msb_dataview *dv, size_t *d);
 MSB_API int msb_dataview_rowsize(const msb_dataview *dv, size_t *rowsize, size_t *maskrowsize);
 /* copy record idx (and its mask row, may be NULL) back to the host: dataview::get(idx) */
 MSB_API int msb_dataview_get_row(msb_dataview *dv, size_t idx, void *row_out, void *mask_out);
+/* row_major_dataview::permute / reset_permutation (src/common/recarray/dataview.cpp:141-151, util.hpp:85-94): a
+ * Fisher-Yates order for iteration, drawn from the counter-based Philox stream (key = seed, counter = position).  While
+ * a permutation is set, msb_dataview_get_row(idx) returns record pi[idx]; the stored records -- and the entity ids of a
+ * state bound to the dataview -- keep their order, as in the reference.  msb_dataview_permutation reads pi back (the
+ * identity when none is set): the order in which a caller visits the entities of a sequential pass. */
+MSB_API int msb_dataview_permute(msb_dataview *dv, uint64_t seed);
+MSB_API int msb_dataview_reset_permutation(msb_dataview *dv);
+MSB_API int msb_dataview_permutation(const msb_dataview *dv, uint64_t *pi_out, size_t n);
 
 /* ---- state -------------------------------------------------------------- */
 MSB_API int msb_state_create(msb_ctx *ctx, const msb_model_desc *models, size_t nfeatures,

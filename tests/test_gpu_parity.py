@@ -359,6 +359,36 @@ def test_dataview_roundtrip_on_device(ctx):
         dev.get_row_bytes(2)  # "invalid position", dataview.cpp:131
 
 
+def test_dataview_permutation_on_device(ctx):
+    # row_major_dataview::permute / reset_permutation (dataview.cpp:141-151): an iteration order, not a reshuffle of the
+    # storage -- get(idx) walks the records in the order pi, and a state bound to the view keeps its entity ids
+    n = 257
+    Y = np.zeros(n, dtype=[("", np.int32), ("", np.float32)])
+    Y["f0"] = np.arange(n); Y["f1"] = np.arange(n) * 0.5
+    dev = cb.numpy_dataview(Y).to_device(ctx)
+    assert np.array_equal(dev.permutation(), np.arange(n, dtype=np.uint64))
+    dev.permute(12345)
+    pi = dev.permutation()
+    assert sorted(pi.tolist()) == list(range(n)) and not np.array_equal(pi, np.arange(n, dtype=np.uint64))
+    for i in (0, 1, 100, n - 1):
+        row, _ = dev.get_row_bytes(i)
+        assert row.tobytes() == Y[int(pi[i])].tobytes()
+    dev.permute(12345)
+    assert np.array_equal(dev.permutation(), pi)          # counter-based: the same seed gives the same order
+    dev.permute(54321)
+    assert not np.array_equal(dev.permutation(), pi)
+    st = cb.state(ctx, [cb.gp, cb.nich], max_groups=4)
+    st.bind(dev)                                           # binding ignores the iteration order: entity i is record i
+    g = st.create_group()
+    st.add_values(np.full(n, g))
+    assert st.get_suffstats(0, g, "sum", 1)[0] == float(np.arange(n).sum())
+    st.close()
+    dev.reset_permutation()
+    row, _ = dev.get_row_bytes(5)
+    assert row.tobytes() == Y[5].tobytes()
+    dev.close()
+
+
 def test_empty_and_ragged_inputs(ctx, oracle):
     st = cb.state(ctx, [cb.bb, cb.nich], max_groups=4)
     empty = np.zeros(0, dtype=[("", bool), ("", np.float32)])
