@@ -277,6 +277,8 @@ extern "C" MSB_API int msb_ctx_create(int device, void *stream, msb_ctx **out) {
   CU_TRY(opt_in_smem((score_bundle_kernel<4, 16, 16, true>), c->smem_optin));
   CU_TRY(opt_in_smem((sample_tile_kernel<4, false>), c->smem_optin));
   CU_TRY(opt_in_smem((sample_tile_kernel<4, true>), c->smem_optin));
+  CU_TRY(opt_in_smem((sample_tile_kernel<1, false>), c->smem_optin));
+  CU_TRY(opt_in_smem((sample_tile_kernel<1, true>), c->smem_optin));
   CU_TRY(opt_in_smem((ingest_tile_kernel<512, 1>), c->smem_optin));
   CU_TRY(opt_in_smem((ingest_tile_kernel<256, 2>), c->smem_optin));
   CU_TRY(opt_in_smem((ingest_tile_kernel<128, 4>), c->smem_optin));
@@ -2404,19 +2406,33 @@ extern "C" MSB_API int msb_state_sweep(msb_state *st, size_t row_lo, size_t row_
     if (tile_fits) {
       // 32-row tile staged in shared memory: scores read from HBM exactly once (bulk copy of the blocked layout,
       // or coalesced transposing loads of the row-major one the NIW kernels write)
-      constexpr int SW = 4;
       const size_t tile_bytes = (K * (blocked ? 32 : 33) * 4 + 127) / 128 * 128;
-      const size_t smem = (size_t)SW * tile_bytes + SW * sizeof(uint64_t) + 64;
       const size_t skip_t = blocked ? skip : 0;  // the row-major pointer below already starts at the first valid row
       const size_t nblk = (skip_t + (hi - lo) + 31) / 32 - skip_t / 32;
-      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ctx->smem_optin / smem));
-      const unsigned grid = (unsigned)std::min<size_t>((nblk + SW - 1) / SW, (size_t)ctx->sm_count * per_sm);
-      if (blocked)
-        LAUNCH(ctx, (sample_tile_kernel<SW, false>), grid, SW * 32, smem, st->d_scores, st->ld, skip, (int)K, hi - lo, d_u, opts->seed,
-               opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
-      else
-        LAUNCH(ctx, (sample_tile_kernel<SW, true>), grid, SW * 32, smem, st->d_scores + skip * st->ld, st->ld, (size_t)0, (int)K, hi - lo,
-               d_u, opts->seed, opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);
+      // The kernel is bound by instruction issue and latency, so what counts is warps per SM, and a warp's tile is what
+      // limits them: blocks of four warps waste the remainder (K = 256: 32 KB per warp, one block of four per SM where
+      // seven warps fit), blocks of one warp do not: C4 sample 0.566 -> 0.517 ms.  Four-warp blocks stay where they lose
+      // little -- at equal occupancy they are the faster form (C2: 8 warps in two blocks 0.416 ms, 9 one-warp blocks 0.501).
+      auto warps_per_sm = [&](int sw) {
+        const size_t smem = (size_t)sw * tile_bytes + sw * sizeof(uint64_t) + 64;
+        return (size_t)sw * std::min<size_t>(32 / sw, ctx->smem_optin / smem);
+      };
+      const bool one_warp = 2 * warps_per_sm(1) >= 3 * warps_per_sm(4) && !getenv("MSB_SAMPLER_FOUR_WARPS");
+#define MSB_TILE_SAMPLER(SW)                                                                                                      \
+      do {                                                                                                                        \
+        const size_t smem = (size_t)SW * tile_bytes + SW * sizeof(uint64_t) + 64;                                                 \
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32 / SW, ctx->smem_optin / smem));                           \
+        const unsigned grid = (unsigned)std::min<size_t>((nblk + SW - 1) / SW, (size_t)ctx->sm_count * per_sm);                   \
+        if (blocked)                                                                                                              \
+          LAUNCH(ctx, (sample_tile_kernel<SW, false>), grid, SW * 32, smem, st->d_scores, st->ld, skip, (int)K, hi - lo, d_u, opts->seed, \
+                 opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);                             \
+        else                                                                                                                      \
+          LAUNCH(ctx, (sample_tile_kernel<SW, true>), grid, SW * 32, smem, st->d_scores + skip * st->ld, st->ld, (size_t)0, (int)K, hi - lo, \
+                 d_u, opts->seed, opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot);            \
+      } while (0)
+      if (one_warp) MSB_TILE_SAMPLER(1);
+      else MSB_TILE_SAMPLER(4);
+#undef MSB_TILE_SAMPLER
     } else if (blocked)
       LAUNCH(ctx, sample_blocked_kernel, cdiv(hi - lo, 128), 128, 0, st->d_scores, st->ld, skip, (int)K, hi - lo, d_u, opts->seed,
              opts->sweep, opts->row_id_offset + lo, st->d_col2slot, st->d_newcol, st->d_newslot,
