@@ -549,19 +549,26 @@ __global__ void niw_prepare_kernel(FeatDev f, const double *__restrict__ hp, con
     const double ljj = A[j * d + j];
     for (int i = j + 1 + threadIdx.x; i < d; i += blockDim.x) A[i * d + j] /= ljj;
     __syncthreads();
-    const int rem = d - j - 1;
-    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
-      const int a = j + 1 + e / rem, b = j + 1 + e % rem;
-      if (b <= a) A[a * d + b] -= A[a * d + j] * A[b * d + j];
+    // trailing update of the lower triangle: thread (ta, tb) of a 16 x (blockDim / 16) grid walks rows a and columns b <= a
+    // (no integer division per element; the same subtraction per element as before, so the same bits)
+    {
+      const int tb = threadIdx.x & 15, ta = threadIdx.x >> 4, na = blockDim.x >> 4;
+      for (int a = j + 1 + ta; a < d; a += na) {
+        const double laj = A[a * d + j];
+        for (int b = j + 1 + tb; b <= a; b += 16) A[a * d + b] -= laj * A[b * d + j];
+      }
     }
     __syncthreads();
   }
-  // W = L^-1: thread c solves L w = e_c by forward substitution
+  // W = L^-1: thread c solves L w = e_c by forward substitution, its column kept in registers / local order; the
+  // reciprocal diagonal is NOT precomputed (t / L_ii as before: same bits)
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    for (int i = 0; i < d; i++) {
+    for (int i = 0; i < c; i++) Winv[i * d + c] = 0.0;
+    for (int i = c; i < d; i++) {
       double t = (i == c) ? 1.0 : 0.0;
-      for (int m = c; m < i; m++) t -= A[i * d + m] * Winv[m * d + c];
-      Winv[i * d + c] = i < c ? 0.0 : t / A[i * d + i];
+      const double *Ai = A + i * d;
+      for (int m = c; m < i; m++) t -= Ai[m] * Winv[m * d + c];
+      Winv[i * d + c] = t / Ai[i];
     }
   }
   __syncthreads();
