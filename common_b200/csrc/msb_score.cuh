@@ -888,20 +888,27 @@ score_bundle_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *_
   __syncthreads();
   const int nb = *nb_slot;
 
-  // one thread: everything bundle b needs -> stage s
+  // one WARP (all 32 lanes converged): everything bundle b needs -> stage s.  Lane 0 arms the barrier, then every lane
+  // issues its share of the bundle's copies (three per feature: row values, slow masks, parameter chunk).  One lane
+  // issuing the ~20 bulk copies of a C5 bundle one behind the other was the refill's latency: ncu had every warp waiting
+  // ~1200 cycles for the full barrier at every bundle start (8.8 % of the samples) although the refill is requested a
+  // whole bundle -- ~13000 cycles -- ahead.
   auto issue = [&](int b, int s) {
     const uint32_t bar = smem_u32(&bars[s]);
     const uint32_t dst0 = smem_u32(stages + (size_t)s * stage_bytes);
-    mbar_expect_tx(bar, bbytes[b]);
-    const int d1 = bfirst[b + 1];
-    for (int d = bfirst[b]; d < d1; d++) {
-      const FeatS t = ftab[d];
-      bulk_g2s(dst0 + t.sx_off, t.scol + blk_row0, X_BYTES, bar);
-      if (t.has_slow) bulk_g2s(dst0 + t.sx_off + X_BYTES, t.slowmask + (blk_row0 >> 5), M_BYTES, bar);
-      bulk_g2s(dst0 + t.sc_off, region + (size_t)t.rowoff * KT, t.rows * (uint32_t)(KT * sizeof(float)), bar);
+    if (lane == 0) mbar_expect_tx(bar, bbytes[b]);
+    __syncwarp();
+    const int d0 = bfirst[b], nc = 3 * (bfirst[b + 1] - d0);
+    for (int c = lane; c < nc; c += 32) {
+      const FeatS t = ftab[d0 + c / 3];
+      const int which = c % 3;
+      if (which == 0) bulk_g2s(dst0 + t.sx_off, t.scol + blk_row0, X_BYTES, bar);
+      else if (which == 1) { if (t.has_slow) bulk_g2s(dst0 + t.sx_off + X_BYTES, t.slowmask + (blk_row0 >> 5), M_BYTES, bar); }
+      else bulk_g2s(dst0 + t.sc_off, region + (size_t)t.rowoff * KT, t.rows * (uint32_t)(KT * sizeof(float)), bar);
     }
+    __syncwarp();
   };
-  if (tid == 0)
+  if (warp == 0)
     for (int b = 0; b < S && b < nb; b++) issue(b, b);
 
   float acc[RW][V];
@@ -1174,15 +1181,18 @@ score_bundle_kernel(const FeatDev *__restrict__ feats, int nfeat, const float *_
     // Release the stage: a counter per stage, and the warp that arrives LAST issues the refill with bundle b + S, so
     // that nobody waits here (see score_kernel for what was measured against a fixed producer thread).
     __syncwarp();
+    unsigned int last = 0;
     if (lane == 0) {
       const uint32_t rel = smem_u32(&bars[S + s]);
       unsigned int old;
       asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(rel) : "memory");
       if (old == (unsigned)(NW - 1)) {
         asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(rel), "r"(0u) : "memory");
-        if (b + S < nb) issue(b + S, s);
+        last = 1;
       }
     }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last && b + S < nb) issue(b + S, s);   // the whole warp issues (see issue)
     if (++s == S) { s = 0; parity ^= 1u; }
   }
 
