@@ -1691,10 +1691,12 @@ scalar_done:
                              need_init ? st->d_base : nullptr, blocked, a_valid, g_last_error));
       st->niw_a16_version = st->col_version; st->niw_a16_feat = d; st->niw_a16_lo = row_lo; st->niw_a16_hi = row_hi;
       done = true;
-    } else
+    } else {
+    st->niw_a16_version = 0;   // the tf32 path packs its own operands over the column maxima kept next to the fp16 B operand
     MSB_TRY(niw_tc_score(ctx->stream, &ctx->launches, (const float *)f.scol, f.dim, st->d_niwW[d], st->d_niwBias[d], st->d_niwCoef[d],
                          st->d_niwB[d], K, scores, st->ld, row_lo, row_hi, ctx->sm_count, need_init ? st->d_base : nullptr,
                          blocked, &done, g_last_error));
+    }
     if (blocked && !done) return fail(MSB_ERR_STATE, "internal: blocked score layout without the tensor-core NIW path");
     if (done) need_init = false;
     if (!done) {
